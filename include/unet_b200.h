@@ -1,0 +1,189 @@
+/*
+ * unet_b200.h — C-ABI of libunet_b200.so (sm_100a only).
+ *
+ * The reference (planck-epoch/unet-image-segmentation) has no FFI of its own:
+ * its hot path is a Keras layer graph (model/u_net.py:5-116) plus tensor
+ * algebra in utils/metrics.py:6-62 and utils/loss.py:9-48, executed by
+ * TensorFlow kernels.  Each entry point below replaces the TensorFlow kernel(s)
+ * behind one reference call site; the citation names that call site.
+ *
+ * Conventions
+ *   - every function returns 0 (UNET_OK) on success, a negative UNET_E* code for
+ *     a rejected argument, or a positive cudaError_t; unet_last_error() returns
+ *     a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers owned by the caller unless the name says
+ *     `host`; the library allocates nothing and never synchronises.
+ *   - activations are NHWC.  `ld*` is the distance in ELEMENTS between two
+ *     consecutive pixels (>= C), so a tensor may be a channel slice of a wider
+ *     buffer (this is how Concatenate, u_net.py:96, becomes zero-copy).
+ *   - `dtype` selects the storage type of activations (UNET_F32 / UNET_BF16);
+ *     all arithmetic accumulates in fp32.  Parameters, statistics, losses and
+ *     probabilities are always fp32.
+ *   - `stream` is a cudaStream_t passed as void*.
+ *   - all launches are CUDA-graph capturable.
+ */
+#ifndef UNET_B200_H_
+#define UNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNET_OK            0
+#define UNET_EINVAL       -1   /* bad argument (null pointer, non-positive dim, bad enum) */
+#define UNET_EUNSUPPORTED -2   /* legal request this build has no kernel for            */
+#define UNET_EALIGN       -3   /* pointer / leading dimension violates an alignment rule */
+#define UNET_EDRIVER      -4   /* driver entry point (tensor-map encode) unavailable     */
+
+typedef enum { UNET_F32 = 0, UNET_BF16 = 1 } unet_dtype;
+
+/* GEMM epilogues (fused producers of the ops that follow a contraction in u_net.py) */
+typedef enum {
+  UNET_EPI_NONE      = 0, /* C = acc                                  (dgrad)                          */
+  UNET_EPI_AFFINE    = 1, /* C = acc*scale[n] + shift[n]              (folded BatchNormalization, u_net.py:23; or bias) */
+  UNET_EPI_AFFINE_RELU = 2, /* C = max(acc*scale[n]+shift[n], 0)      (BN + Activation('relu'), u_net.py:23-25) */
+  UNET_EPI_STATS     = 3, /* C = acc, and colsum[n] += C, colsq[n] += C*C over rows (training BN batch statistics) */
+  UNET_EPI_CONVT     = 4  /* Conv2DTranspose(k=2,s=2) pixel-shuffle store + bias (+ dropout), u_net.py:88-98 */
+} unet_epilogue;
+
+/* stateless dropout mask: keep(idx) = lowbias32(idx ^ seed-mix) < keep_prob.  rate == 0 disables. */
+typedef struct {
+  float    rate;      /* Dropout(rate), u_net.py:78,98 */
+  uint32_t seed;
+  int64_t  ctot;      /* channels of the logical tensor the mask is defined on (concat buffer width) */
+  int64_t  c0;        /* channel offset of this view inside that tensor */
+} unet_dropout;
+
+typedef struct {
+  /* C[M,N] (+)= A[M,K] * B[K,N] */
+  int64_t M, N, K;
+  const void* A; int64_t lda;      /* A row-major [M,K] (a_trans=0) or [K,M] (a_trans=1, wgrad)          */
+  const void* B; int64_t ldb;      /* B row-major [K,N] (b_trans=0) or [N,K] (b_trans=1)                   */
+  void*       C; int64_t ldc;      /* row-major [M,N]                                                     */
+  int a_trans, b_trans;
+  int in_dtype;                    /* dtype of A and B                                                     */
+  int out_dtype;                   /* dtype of C; must be UNET_F32 when accumulate=1                       */
+  int accumulate;                  /* 1: C += (atomic, split-K allowed) — used for weight gradients        */
+  int epilogue;                    /* unet_epilogue                                                        */
+  const float* scale;              /* [N] AFFINE*: per-column scale (NULL = 1)                             */
+  const float* shift;              /* [N] AFFINE*: per-column shift;  CONVT: bias[Cout]  (NULL = 0)        */
+  double* colsum; double* colsq;   /* [N] STATS accumulators (caller zeroes)                               */
+  /* CONVT: A rows are pixels (n,i,j) of an [Nimg,H,W,K] tensor, N = 4*Cout ordered (a,b,co); C points at
+     channel 0 of the [Nimg,2H,2W,*] destination with pixel stride ldc.                                    */
+  int convt_H, convt_W;
+  unet_dropout drop;               /* CONVT only */
+} unet_gemm_args;
+
+/* ---- library ---- */
+int         unet_version(void);
+int         unet_sm_arch(void);                /* 100: the only architecture this library is built for */
+const char* unet_last_error(void);
+int         unet_device_check(int device);     /* UNET_OK iff the device is compute capability 10.x    */
+
+/* ---- SeparableConv2D, depthwise half (u_net.py:14-20) ---- */
+/* y[n,i,j,c] = sum_{a,b} x'[n,i+a-1,j+b-1,c] * w[a,b,c], zero 'same' padding.
+   x' = x, or max(x*in_scale[c]+in_shift[c],0) when in_scale != NULL (BN+ReLU of the producer fused into the load;
+   padding is zero in x' space).  flip=1 correlates with the 180-degree rotated kernel (= gradient w.r.t. input).
+   drop (rate>0) multiplies the OUTPUT by the dropout mask (used by the input-gradient of a dropped tensor). */
+int unet_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy,
+                       int N, int H, int W, int C, int dtype, int flip,
+                       const float* in_scale, const float* in_shift,
+                       const unet_dropout* drop, void* stream);
+/* dw[a,b,c] += sum_{n,i,j} x[n,i+a-1,j+b-1,c] * dy[n,i,j,c]   (dw fp32 [3,3,C], accumulated atomically) */
+int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c,
+                              int N, int H, int W, int C, int dtype, void* stream);
+
+/* ---- dense contractions: SeparableConv2D pointwise half, Conv2DTranspose, their gradients ---- */
+/* fp32-exact CUDA-core path (any shape, either dtype) */
+int unet_gemm_simt(const unet_gemm_args* args, void* stream);
+/* tcgen05/TMEM/TMA path: bf16 operands, fp32 accumulation.  Requirements: in_dtype = BF16; lda/ldb multiples of 8;
+   a_trans=0: B must be given as [N,K] (b_trans=1);  a_trans=1 (weight gradient): b_trans=0, accumulate=1. */
+int unet_gemm_tc(const unet_gemm_args* args, void* stream);
+
+/* ---- BatchNormalization (u_net.py:23; Keras defaults momentum .99, eps 1e-3) ---- */
+/* inference: scale = gamma/sqrt(var+eps), shift = beta - mean*scale  (moving statistics) */
+int unet_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 float* scale, float* shift, int C, void* stream);
+/* training: from colsum/colsq over `count` rows -> batch mean / biased var; scale/shift as above with batch stats;
+   saves mean and rstd for backward; moving <- momentum*moving + (1-momentum)*batch.  gamma/beta NULL = 1/0. */
+int unet_bn_finalize(const double* colsum, const double* colsq, int64_t count,
+                     const float* gamma, const float* beta, float eps, float momentum,
+                     float* moving_mean, float* moving_var,
+                     float* scale, float* shift, float* save_mean, float* save_rstd, int C, void* stream);
+/* y = max(z*scale+shift,0) (relu=1) written at (y,ldy), optionally dropped out; optional 2x2/2 max-pool of the
+   un-dropped activation to `pooled` (contiguous [N,H/2,W/2,C]).  Activation + MaxPooling2D + Dropout,
+   u_net.py:25,69,78,98.  z contiguous [N,H,W,C]. */
+int unet_bn_act(const void* z, const float* scale, const float* shift, int relu,
+                void* y, int64_t ldy, void* pooled,
+                int N, int H, int W, int C, int dtype, const unet_dropout* drop, void* stream);
+/* backward of y = relu(bn(z)): given dy (ptr,lddy) and saved z (contiguous),
+   pass 1: dgamma[c] = sum g*xhat, dbeta[c] = sum g, g = dy*[y>0]   (accumulated into the fp32 outputs)
+   pass 2: dz = scale*(g - dbeta/M - xhat*dgamma/M)                 (scale = gamma*rstd)
+   `drop` (rate>0): dy is first multiplied by the dropout mask of the forward pass (y was stored dropped-out).
+   save_mean == NULL: no normalisation (use_batch_norm=False); z is the pre-activation, dbeta is the bias gradient. */
+int unet_bn_bwd_reduce(const void* dy, int64_t lddy, const void* z,
+                       const float* scale, const float* shift, const float* save_mean, const float* save_rstd,
+                       float* dgamma, float* dbeta, int64_t M, int C, int dtype, int relu,
+                       const unet_dropout* drop, void* stream);
+int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
+                      const float* scale, const float* shift, const float* save_mean, const float* save_rstd,
+                      const float* dgamma, const float* dbeta, void* dz,
+                      int64_t M, int C, int dtype, int relu, const unet_dropout* drop, void* stream);
+
+/* ---- MaxPooling2D((2,2)) (u_net.py:69) ---- */
+int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, int H, int W, int C, int dtype, void* stream);
+/* dy_total[n,i,j,c] = dskip[n,i,j,c] (may be NULL) + dpool routed to the first max of each window, where the
+   pooled activation is recomputed as relu(z*scale+shift) (scale NULL: the stored tensor is the activation).
+   (H,W) are the un-pooled dims. */
+int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scale, const float* shift,
+                        const void* dpool, const void* dskip, int64_t lddskip, void* dy,
+                        int N, int H, int W, int C, int dtype, void* stream);
+
+/* ---- Conv2DTranspose backward helper: un-pixel-shuffle dU[N,2H,2W,Cout] (ptr,ld) into G[N*H*W, 4*Cout]
+        (columns (a,b,co)) and accumulate dbias[co] += sum dU ---- */
+int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, float* dbias,
+                          int N, int H, int W, int Cout, int dtype, void* stream);
+
+/* ---- output head: Conv2D(num_classes,1,activation) (u_net.py:105-112) + Dice/IoU sums (utils/metrics.py:29-31) ---- */
+/* probs[M,C] fp32 = sigmoid (C==1) or softmax (C>1) of x[M,K]*w[K,C]+b.  If y_true != NULL also accumulates, per
+   image n and class c, sums[n][c][0..2] += (sum t*p, sum t, sum p)   (double).  hw = pixels per image. */
+int unet_head_fwd(const void* x, int64_t ldx, const float* w, const float* b, float* probs,
+                  const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype, void* stream);
+/* loss finalize (utils/loss.py:9-45, utils/metrics.py:33-38,58-62): kind 0 = dice, 1 = iou.
+   out[0] = loss, out[1] = mean dice_coef, out[2] = mean iou_coef; coef[n][c][0..1] = (ca, cb) with
+   dLoss/dp = ca*t + cb (scaled by grad_scale). */
+int unet_seg_loss_finalize(const double* sums, int NC_pairs, float smooth, int kind, float grad_scale,
+                           float* out3, float* coef, void* stream);
+/* backward through activation + 1x1 conv: dx[M,K] (dtype), dw[K,C] +=, db[C] += */
+int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
+                  const float* coef, void* dx, int64_t lddx, float* dw, float* db,
+                  int64_t M, int64_t hw, int K, int C, int dtype, void* stream);
+/* standalone (I,T,P) sums over [NB,HW,C] fp32 pairs: dice_coef / iou_coef as metrics on arbitrary arrays */
+int unet_seg_sums(const float* y_true, const float* y_pred, double* sums, int64_t NB, int64_t hw, int C, void* stream);
+
+/* ---- tf.keras.metrics.MeanIoU (train.py:231, benchmark.py:237,269): counts[t*C+p] += 1 with int truncation ---- */
+int unet_confusion_matrix_update(const float* y_true, const float* y_pred, int64_t n, int num_classes,
+                                 unsigned long long* counts, void* stream);
+/* thresholded variant used by benchmark.py:260: p = (prob > thr) */
+int unet_confusion_matrix_update_thr(const float* y_true, const float* prob, float thr, int64_t n,
+                                     unsigned long long* counts /*[4]*/, void* stream);
+
+/* ---- AdamW, Keras form (train.py:226): w -= lr*wd*w; m,v update; w -= alpha*m/(sqrt(v)+eps) ---- */
+/* hyper (device, fp32[8]): lr, wd, beta1, beta2, eps, step t (as float), grad_scale, unused — read on device so a
+   captured graph follows ReduceLROnPlateau without re-capture. */
+int unet_adamw_step(float* w, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream);
+
+/* ---- parameter staging for the tensor-core path: dst[r,c] = bf16(src[r,c]); dst_t[c,r] = bf16(src[r,c]) ---- */
+int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream);
+/* dst = cast(src) elementwise between fp32/bf16 (n elements) */
+int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* host helper: the mask bit the kernels use, for reproducing dropout on the host in tests */
+uint32_t unet_host_dropout_hash(uint64_t idx, uint32_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNET_B200_H_ */

@@ -1,0 +1,100 @@
+// Shared device/host helpers for libunet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include "../../include/unet_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libunet_b200 is written for sm_100a only"
+#endif
+
+namespace unet {
+
+// ---------------------------------------------------------------- errors
+int set_error(int code, const char* fmt, ...);
+int set_cuda_error(cudaError_t e, const char* where);
+
+#define UNET_REQUIRE(cond, code, ...)                          \
+  do { if (!(cond)) return ::unet::set_error((code), __VA_ARGS__); } while (0)
+
+#define UNET_LAUNCH_CHECK(where)                               \
+  do { cudaError_t e__ = cudaGetLastError();                   \
+       if (e__ != cudaSuccess) return ::unet::set_cuda_error(e__, where); } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
+int sm_count();
+
+// ---------------------------------------------------------------- dtype helpers
+template <typename T> struct DT;
+template <> struct DT<float>         { static constexpr int id = UNET_F32;  };
+template <> struct DT<__nv_bfloat16> { static constexpr int id = UNET_BF16; };
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 8 consecutive elements <-> 8 floats.  Pointers must be 16-byte aligned (bf16) / 16-byte aligned (fp32).
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {           // bf16 -> fp32 is a 16-bit shift
+    v[2 * i]     = __uint_as_float(u[i] << 16);
+    v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 a;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = a;
+}
+// value a store8/load8 round trip would produce (so statistics match what is stored)
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
+
+// ---------------------------------------------------------------- dropout mask (stateless, reproducible on host)
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t idx, uint32_t seed) {
+  uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B1u) ^ (seed * 0x85EBCA6Bu + 0xC2B2AE35u);
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;   // lowbias32
+  return x;
+}
+// multiplier for element idx: 0 if dropped, 1/(1-rate) if kept
+__host__ __device__ __forceinline__ float dropout_mult(uint64_t idx, uint32_t seed, float keep_prob, float inv_keep) {
+  const float u = static_cast<float>(dropout_hash(idx, seed) >> 8) * (1.0f / 16777216.0f);
+  return u < keep_prob ? inv_keep : 0.0f;
+}
+
+// ---------------------------------------------------------------- reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace unet

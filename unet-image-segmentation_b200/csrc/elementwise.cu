@@ -1,0 +1,665 @@
+// HBM-bound elementwise / reduction kernels of the U-Net hot path: BatchNormalization (reference
+// model/u_net.py:23), Activation('relu') (:25), MaxPooling2D (:69), Dropout (:78,98), the Conv2DTranspose
+// gradient gather, Keras-form AdamW (scripts/train.py:226), MeanIoU confusion counts (scripts/train.py:231,
+// scripts/benchmark.py:237-269) and parameter staging.  All are one-pass, 16-byte vectorised over the NHWC channel
+// dimension, fp32 arithmetic.
+#include "common.cuh"
+
+namespace unet {
+
+struct DropArgs { float keep, inv_keep; uint32_t seed; int on; int64_t ctot, c0; };
+static DropArgs make_drop(const unet_dropout* d) {
+  DropArgs a{1.f, 1.f, 0u, 0, 0, 0};
+  if (d && d->rate > 0.f) {
+    a.on = 1; a.keep = 1.f - d->rate; a.inv_keep = 1.f / (1.f - d->rate);
+    a.seed = d->seed; a.ctot = d->ctot; a.c0 = d->c0;
+  }
+  return a;
+}
+
+static unsigned grid_for(int64_t threads, int block = 256) { return (unsigned)ceil_div(threads, block); }
+
+// ------------------------------------------------------------------------------------------------ BN fold / finalize
+__global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                               float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float s = g / sqrtf(var[c] + eps);
+  scale[c] = s;
+  shift[c] = b - mean[c] * s;
+}
+
+__global__ void bn_finalize_kernel(const double* colsum, const double* colsq, double inv_count,
+                                   const float* gamma, const float* beta, float eps, float momentum,
+                                   float* moving_mean, float* moving_var, float* scale, float* shift,
+                                   float* save_mean, float* save_rstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = colsum[c] * inv_count;
+  double var = colsq[c] * inv_count - mean * mean;   // biased, as Keras uses for both normalisation and moving_var
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float s = g * rstd;
+  scale[c] = s;
+  shift[c] = b - (float)mean * s;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_rstd) save_rstd[c] = rstd;
+  if (moving_mean) moving_mean[c] = moving_mean[c] * momentum + (float)mean * (1.f - momentum);
+  if (moving_var)  moving_var[c]  = moving_var[c]  * momentum + (float)var  * (1.f - momentum);
+}
+
+// ------------------------------------------------------------------------------------------------ BN apply + ReLU (+pool, +dropout)
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+              T* __restrict__ y, int64_t ldy, T* __restrict__ pooled, int N, int H, int W, int C, DropArgs dp) {
+  const int cv = C >> 3;
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)(t % cv) << 3; t /= cv;
+  float sc[8], sh[8];
+  if (POOL) {
+    const int W2 = W >> 1, H2 = H >> 1;
+    const int j2 = (int)(t % W2); t /= W2;
+    const int i2 = (int)(t % H2); const int64_t n = t / H2;
+    if (n >= N) return;
+    load8(scale + c0, sc); load8(shift + c0, sh);
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t pix = (n * H + (2 * i2 + (q >> 1))) * (int64_t)W + 2 * j2 + (q & 1);
+      float v[8];
+      load8(z + pix * C + c0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = fmaf(v[j], sc[j], sh[j]);
+        if (relu) v[j] = fmaxf(v[j], 0.f);
+        v[j] = round_to<T>(v[j]);
+        m[j] = q == 0 ? v[j] : fmaxf(m[j], v[j]);
+      }
+      if (dp.on) {
+        const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+      }
+      store8(y + pix * ldy + c0, v);
+    }
+    store8(pooled + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, m);
+  } else {
+    const int64_t pix = t;
+    if (pix >= (int64_t)N * H * W) return;
+    load8(scale + c0, sc); load8(shift + c0, sh);
+    float v[8];
+    load8(z + pix * C + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = fmaf(v[j], sc[j], sh[j]);
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (dp.on) {
+      const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+    }
+    store8(y + pix * ldy + c0, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN backward
+// thread layout inside a block: (rows = 256/cv) x cv, each thread owns 8 channels and strides over rows.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ z,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C, int relu, DropArgs dp) {
+  extern __shared__ float s_red[];   // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int cv = C >> 3;
+  const int rows_per_block = blockDim.x / cv;
+  const int c0 = (threadIdx.x % cv) << 3;
+  const int r_in = threadIdx.x / cv;
+  float sc[8], sh[8], mu[8], rs[8];
+  const bool norm = mean != nullptr;
+  if (norm) { load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(rstd + c0, rs); }
+  float sg[8], sgx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgx[j] = 0.f; }
+  for (int64_t r = blockIdx.x * (int64_t)rows_per_block + r_in; r < M; r += (int64_t)gridDim.x * rows_per_block) {
+    float g[8], zz[8];
+    load8(dy + r * lddy + c0, g);
+    load8(z + r * C + c0, zz);
+    if (dp.on) {
+      const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float act = norm ? fmaf(zz[j], sc[j], sh[j]) : zz[j];
+      const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
+      sg[j] += gj;
+      if (norm) sgx[j] = fmaf(gj, (zz[j] - mu[j]) * rs[j], sgx[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_red[c0 + j], sg[j]);
+    if (norm) atomicAdd(&s_red[C + c0 + j], sgx[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&dbeta[i], s_red[i]);
+    if (norm && dgamma) atomicAdd(&dgamma[i], s_red[C + i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ z,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, T* __restrict__ dz,
+                    int64_t M, int C, int relu, float inv_m, DropArgs dp) {
+  const int cv = C >> 3;
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)(t % cv) << 3;
+  const int64_t r = t / cv;
+  if (r >= M) return;
+  const bool norm = mean != nullptr;
+  float g[8], zz[8], o[8];
+  load8(dy + r * lddy + c0, g);
+  load8(z + r * C + c0, zz);
+  if (dp.on) {
+    const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+  }
+  if (norm) {
+    float sc[8], sh[8], mu[8], rs[8], dg[8], db[8];
+    load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(rstd + c0, rs);
+    load8(dgamma + c0, dg); load8(dbeta + c0, db);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float act = fmaf(zz[j], sc[j], sh[j]);
+      const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
+      const float xh = (zz[j] - mu[j]) * rs[j];
+      o[j] = sc[j] * (gj - db[j] * inv_m - xh * dg[j] * inv_m);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (relu && !(zz[j] > 0.f)) ? 0.f : g[j];
+  }
+  store8(dz + r * C + c0, o);
+}
+
+// ------------------------------------------------------------------------------------------------ max pooling
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int N, int H, int W, int C) {
+  const int cv = C >> 3, W2 = W >> 1, H2 = H >> 1;
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)(t % cv) << 3; t /= cv;
+  const int j2 = (int)(t % W2); t /= W2;
+  const int i2 = (int)(t % H2); const int64_t n = t / H2;
+  if (n >= N) return;
+  float m[8];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t pix = (n * H + (2 * i2 + (q >> 1))) * (int64_t)W + 2 * j2 + (q & 1);
+    float v[8];
+    load8(x + pix * ldx + c0, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = q == 0 ? v[j] : fmaxf(m[j], v[j]);
+  }
+  store8(y + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, m);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const T* __restrict__ dpool, const T* __restrict__ dskip, int64_t lddskip, T* __restrict__ dy,
+                   int N, int H, int W, int C) {
+  const int cv = C >> 3, W2 = W >> 1, H2 = H >> 1;
+  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int c0 = (int)(t % cv) << 3; t /= cv;
+  const int j2 = (int)(t % W2); t /= W2;
+  const int i2 = (int)(t % H2); const int64_t n = t / H2;
+  if (n >= N) return;
+  float sc[8], sh[8];
+  const bool aff = scale != nullptr;
+  if (aff) { load8(scale + c0, sc); load8(shift + c0, sh); }
+  float v[4][8], dp[8];
+  int64_t pix[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    pix[q] = (n * H + (2 * i2 + (q >> 1))) * (int64_t)W + 2 * j2 + (q & 1);
+    load8(z + pix[q] * ldz + c0, v[q]);
+    if (aff) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[q][j] = round_to<T>(fmaxf(fmaf(v[q][j], sc[j], sh[j]), 0.f));
+    }
+  }
+  load8(dpool + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, dp);
+  int arg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {   // first maximum in window scan order (TF CPU convention)
+    int a = 0; float m = v[0][j];
+#pragma unroll
+    for (int q = 1; q < 4; ++q) if (v[q][j] > m) { m = v[q][j]; a = q; }
+    arg[j] = a;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float o[8];
+    if (dskip) load8(dskip + pix[q] * lddskip + c0, o);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) if (arg[j] == q) o[j] += dp[j];
+    store8(dy + pix[q] * C + c0, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ convT backward gather
+template <typename T>
+__global__ void __launch_bounds__(256)
+convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ g, float* __restrict__ dbias,
+                        int N, int H, int W, int Cout) {
+  extern __shared__ float s_red[];   // [Cout]
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int cv = Cout >> 3;
+  const int per_block = blockDim.x / cv;
+  const int c0 = (threadIdx.x % cv) << 3;
+  const int64_t items = (int64_t)N * H * W * 4;
+  float sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sb[j] = 0.f;
+  for (int64_t it = blockIdx.x * (int64_t)per_block + threadIdx.x / cv; it < items; it += (int64_t)gridDim.x * per_block) {
+    const int ab = (int)(it & 3); int64_t m = it >> 2;
+    const int j = (int)(m % W); const int64_t q = m / W;
+    const int i = (int)(q % H); const int64_t n = q / H;
+    const int64_t src = (n * (2 * H) + 2 * i + (ab >> 1)) * (int64_t)(2 * W) + 2 * j + (ab & 1);
+    float v[8];
+    load8(du + src * lddu + c0, v);
+    store8(g + (m * 4 + ab) * (int64_t)Cout + c0, v);
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) sb[jj] += v[jj];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) atomicAdd(&s_red[c0 + j], sb[j]);
+  __syncthreads();
+  if (dbias)
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) atomicAdd(&dbias[i], s_red[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ AdamW (Keras form)
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             int64_t n, const float* __restrict__ hyper) {
+  const float lr = hyper[0], wd = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4], t = hyper[5], gs = hyper[6];
+  // alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+  const float alpha = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+  const float decay = 1.f - lr * wd;
+  const int64_t i4 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i4 + 3 < n) {
+    float4 ww = *reinterpret_cast<float4*>(w + i4);
+    const float4 gg = *reinterpret_cast<const float4*>(g + i4);
+    float4 mm = *reinterpret_cast<float4*>(m + i4);
+    float4 vv = *reinterpret_cast<float4*>(v + i4);
+    float* pw = &ww.x; const float* pg = &gg.x; float* pm = &mm.x; float* pv = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = pg[j] * gs;
+      float wj = pw[j] * decay;
+      pm[j] = b1 * pm[j] + (1.f - b1) * gj;
+      pv[j] = b2 * pv[j] + (1.f - b2) * gj * gj;
+      wj -= alpha * pm[j] / (sqrtf(pv[j]) + eps);
+      pw[j] = wj;
+    }
+    *reinterpret_cast<float4*>(w + i4) = ww;
+    *reinterpret_cast<float4*>(m + i4) = mm;
+    *reinterpret_cast<float4*>(v + i4) = vv;
+  } else {
+    for (int64_t i = i4; i < n; ++i) {
+      const float gj = g[i] * gs;
+      float wj = w[i] * decay;
+      const float mj = b1 * m[i] + (1.f - b1) * gj;
+      const float vj = b2 * v[i] + (1.f - b2) * gj * gj;
+      wj -= alpha * mj / (sqrtf(vj) + eps);
+      w[i] = wj; m[i] = mj; v[i] = vj;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ casts
+__global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                           __nv_bfloat16* __restrict__ dst_t, int R, int C) {
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = blockIdx.y * 32 + i;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = src[(int64_t)r * C + c];
+      if (dst) dst[(int64_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (!dst_t) return;
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (r2 < R && c2 < C) dst_t[(int64_t)c2 * R + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d[i] = from_f32<D>(to_f32(s[i]));
+}
+
+// ------------------------------------------------------------------------------------------------ MeanIoU confusion counts
+__global__ void confusion_kernel(const float* __restrict__ yt, const float* __restrict__ yp, int64_t n, int C,
+                                 unsigned long long* __restrict__ counts, int use_thr, float thr) {
+  extern __shared__ unsigned int s_cnt[];   // [C*C]
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cnt[i] = 0u;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)yt[i];                                   // tf.cast(..., int64): truncation toward zero
+    const int p = use_thr ? (yp[i] > thr ? 1 : 0) : (int)yp[i];
+    if (t >= 0 && t < C && p >= 0 && p < C) atomicAdd(&s_cnt[t * C + p], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+    if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ (I,T,P) sums
+// sums[nb][c][0..2] += (sum t*p, sum t, sum p) over hw pixels.  blockDim is a multiple of C so that a thread's class is fixed.
+__global__ void seg_sums_kernel(const float* __restrict__ yt, const float* __restrict__ yp, double* __restrict__ sums,
+                                int64_t hw, int C) {
+  extern __shared__ double s_sum[];   // [C][3]
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_sum[i] = 0.0;
+  __syncthreads();
+  const int64_t nb = blockIdx.y;
+  const int64_t per_img = hw * C;
+  const float* t = yt + nb * per_img;
+  const float* p = yp + nb * per_img;
+  const int c = threadIdx.x % C;
+  float si = 0.f, st = 0.f, sp = 0.f;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < per_img; e += (int64_t)gridDim.x * blockDim.x) {
+    const float tv = t[e], pv = p[e];
+    si = fmaf(tv, pv, si); st += tv; sp += pv;
+  }
+  atomicAdd(&s_sum[c * 3 + 0], (double)si);
+  atomicAdd(&s_sum[c * 3 + 1], (double)st);
+  atomicAdd(&s_sum[c * 3 + 2], (double)sp);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) atomicAdd(&sums[nb * 3 * C + i], s_sum[i]);
+}
+
+// loss finalize: one block
+__global__ void seg_loss_finalize_kernel(const double* __restrict__ sums, int npairs, float smooth, int kind,
+                                         float grad_scale, float* __restrict__ out3, float* __restrict__ coef) {
+  __shared__ double s_d[32], s_i[32];
+  double dsum = 0.0, isum = 0.0;
+  const double s = (double)smooth, inv = 1.0 / (double)npairs;
+  for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
+    const double I = sums[3 * i], T = sums[3 * i + 1], P = sums[3 * i + 2];
+    const double D = T + P + s, num = 2.0 * I + s;
+    const double U = T + P - I + s;
+    dsum += num / D;
+    isum += (I + s) / U;
+    if (coef) {
+      double ca, cb;
+      if (kind == 0) { ca = -2.0 * inv / D; cb = num * inv / (D * D); }
+      else           { ca = -inv * (U + (I + s)) / (U * U); cb = inv * (I + s) / (U * U); }
+      coef[2 * i] = (float)(ca * grad_scale);
+      coef[2 * i + 1] = (float)(cb * grad_scale);
+    }
+  }
+  dsum = warp_sum(dsum); isum = warp_sum(isum);
+  if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = dsum; s_i[threadIdx.x >> 5] = isum; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double d = 0.0, i = 0.0;
+    for (int k = 0; k < (blockDim.x >> 5); ++k) { d += s_d[k]; i += s_i[k]; }
+    d *= inv; i *= inv;
+    out3[0] = (float)(1.0 - (kind == 0 ? d : i));
+    out3[1] = (float)d;
+    out3[2] = (float)i;
+  }
+}
+
+}  // namespace unet
+
+using namespace unet;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int unet_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                            float* scale, float* shift, int C, void* stream) {
+  UNET_REQUIRE(mean && var && scale && shift && C > 0, UNET_EINVAL, "bn_fold: bad argument");
+  bn_fold_kernel<<<grid_for(C, 128), 128, 0, ST>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  UNET_LAUNCH_CHECK("bn_fold");
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_finalize(const double* colsum, const double* colsq, int64_t count,
+                                const float* gamma, const float* beta, float eps, float momentum,
+                                float* moving_mean, float* moving_var,
+                                float* scale, float* shift, float* save_mean, float* save_rstd, int C, void* stream) {
+  UNET_REQUIRE(colsum && colsq && scale && shift && C > 0 && count > 0, UNET_EINVAL, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<grid_for(C, 128), 128, 0, ST>>>(colsum, colsq, 1.0 / (double)count, gamma, beta, eps, momentum,
+                                                      moving_mean, moving_var, scale, shift, save_mean, save_rstd, C);
+  UNET_LAUNCH_CHECK("bn_finalize");
+  return UNET_OK;
+}
+
+template <typename T>
+static int bn_act_launch(const void* z, const float* scale, const float* shift, int relu, void* y, int64_t ldy,
+                         void* pooled, int N, int H, int W, int C, DropArgs dp, cudaStream_t st) {
+  const int cv = C / 8;
+  if (pooled) {
+    const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * cv;
+    bn_act_kernel<T, true><<<grid_for(threads), 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, (T*)pooled,
+                                                             N, H, W, C, dp);
+  } else {
+    const int64_t threads = (int64_t)N * H * W * cv;
+    bn_act_kernel<T, false><<<grid_for(threads), 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, nullptr,
+                                                              N, H, W, C, dp);
+  }
+  UNET_LAUNCH_CHECK("bn_act");
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_act(const void* z, const float* scale, const float* shift, int relu,
+                           void* y, int64_t ldy, void* pooled,
+                           int N, int H, int W, int C, int dtype, const unet_dropout* drop, void* stream) {
+  UNET_REQUIRE(z && scale && shift && y, UNET_EINVAL, "bn_act: null pointer");
+  UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldy >= C, UNET_EINVAL, "bn_act: bad dims");
+  UNET_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && aligned16(z) && aligned16(y), UNET_EALIGN, "bn_act: needs C%%8==0, ld%%8==0, 16B pointers");
+  UNET_REQUIRE(!pooled || (H % 2 == 0 && W % 2 == 0), UNET_EINVAL, "bn_act: pooling needs even H,W");
+  const DropArgs dp = make_drop(drop);
+  if (dtype == UNET_F32)  return bn_act_launch<float>(z, scale, shift, relu, y, ldy, pooled, N, H, W, C, dp, ST);
+  if (dtype == UNET_BF16) return bn_act_launch<__nv_bfloat16>(z, scale, shift, relu, y, ldy, pooled, N, H, W, C, dp, ST);
+  return set_error(UNET_EINVAL, "bn_act: bad dtype %d", dtype);
+}
+
+static int bn_bwd_check(const char* who, const void* dy, int64_t lddy, const void* z, int64_t M, int C) {
+  UNET_REQUIRE(dy && z && M > 0 && C > 0 && lddy >= C, UNET_EINVAL, "%s: bad argument", who);
+  UNET_REQUIRE(C % 8 == 0 && lddy % 8 == 0 && aligned16(dy) && aligned16(z), UNET_EALIGN, "%s: needs C%%8==0, ld%%8==0", who);
+  UNET_REQUIRE(256 % (C / 8) == 0, UNET_EUNSUPPORTED, "%s: C/8 must divide 256 (C=%d)", who, C);
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_bwd_reduce(const void* dy, int64_t lddy, const void* z,
+                                  const float* scale, const float* shift, const float* save_mean, const float* save_rstd,
+                                  float* dgamma, float* dbeta, int64_t M, int C, int dtype, int relu,
+                                  const unet_dropout* drop, void* stream) {
+  const DropArgs dp = make_drop(drop);
+  if (int e = bn_bwd_check("bn_bwd_reduce", dy, lddy, z, M, C)) return e;
+  UNET_REQUIRE(dbeta, UNET_EINVAL, "bn_bwd_reduce: dbeta is null");
+  UNET_REQUIRE(!save_mean || (scale && shift && save_rstd && dgamma), UNET_EINVAL, "bn_bwd_reduce: incomplete BN state");
+  const int rows_per_block = 256 / (C / 8);
+  const unsigned grid = (unsigned)i64min(ceil_div(M, rows_per_block), (int64_t)sm_count() * 8);
+  const size_t smem = (size_t)2 * C * sizeof(float);
+  if (dtype == UNET_F32)
+    bn_bwd_reduce_kernel<float><<<grid, 256, smem, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift, save_mean,
+                                                        save_rstd, dgamma, dbeta, M, C, relu, dp);
+  else if (dtype == UNET_BF16)
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+                                                                scale, shift, save_mean, save_rstd, dgamma, dbeta, M, C, relu, dp);
+  else return set_error(UNET_EINVAL, "bn_bwd_reduce: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("bn_bwd_reduce");
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
+                                 const float* scale, const float* shift, const float* save_mean, const float* save_rstd,
+                                 const float* dgamma, const float* dbeta, void* dz,
+                                 int64_t M, int C, int dtype, int relu, const unet_dropout* drop, void* stream) {
+  if (int e = bn_bwd_check("bn_bwd_apply", dy, lddy, z, M, C)) return e;
+  const DropArgs dp = make_drop(drop);
+  UNET_REQUIRE(dz && aligned16(dz), UNET_EINVAL, "bn_bwd_apply: dz null or unaligned");
+  UNET_REQUIRE(!save_mean || (scale && shift && save_rstd && dgamma && dbeta), UNET_EINVAL, "bn_bwd_apply: incomplete BN state");
+  const int64_t threads = M * (C / 8);
+  const float inv_m = (float)(1.0 / (double)M);
+  if (dtype == UNET_F32)
+    bn_bwd_apply_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift,
+                                                                 save_mean, save_rstd, dgamma, dbeta, (float*)dz, M, C, relu, inv_m, dp);
+  else if (dtype == UNET_BF16)
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+                                                                         scale, shift, save_mean, save_rstd, dgamma, dbeta,
+                                                                         (__nv_bfloat16*)dz, M, C, relu, inv_m, dp);
+  else return set_error(UNET_EINVAL, "bn_bwd_apply: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("bn_bwd_apply");
+  return UNET_OK;
+}
+
+extern "C" int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, int H, int W, int C, int dtype, void* stream) {
+  UNET_REQUIRE(x && y && N > 0 && H > 1 && W > 1 && C > 0 && ldx >= C, UNET_EINVAL, "maxpool2x2_fwd: bad argument");
+  UNET_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && aligned16(x) && aligned16(y), UNET_EALIGN, "maxpool2x2_fwd: needs C%%8==0, ld%%8==0");
+  const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  if (dtype == UNET_F32)
+    maxpool_fwd_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)x, ldx, (float*)y, N, H, W, C);
+  else if (dtype == UNET_BF16)
+    maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, N, H, W, C);
+  else return set_error(UNET_EINVAL, "maxpool2x2_fwd: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("maxpool2x2_fwd");
+  return UNET_OK;
+}
+
+extern "C" int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scale, const float* shift,
+                                   const void* dpool, const void* dskip, int64_t lddskip, void* dy,
+                                   int N, int H, int W, int C, int dtype, void* stream) {
+  UNET_REQUIRE(z && dpool && dy && N > 0 && H > 1 && W > 1 && C > 0 && ldz >= C, UNET_EINVAL, "maxpool2x2_bwd: bad argument");
+  UNET_REQUIRE(H % 2 == 0 && W % 2 == 0, UNET_EINVAL, "maxpool2x2_bwd: needs even H,W");
+  UNET_REQUIRE(C % 8 == 0 && ldz % 8 == 0 && (!dskip || lddskip % 8 == 0), UNET_EALIGN, "maxpool2x2_bwd: needs C%%8==0, ld%%8==0");
+  UNET_REQUIRE((scale == nullptr) == (shift == nullptr), UNET_EINVAL, "maxpool2x2_bwd: scale/shift must come together");
+  const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  if (dtype == UNET_F32)
+    maxpool_bwd_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)z, ldz, scale, shift, (const float*)dpool,
+                                                                (const float*)dskip, lddskip, (float*)dy, N, H, W, C);
+  else if (dtype == UNET_BF16)
+    maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)z, ldz, scale, shift,
+                                                                        (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)dskip,
+                                                                        lddskip, (__nv_bfloat16*)dy, N, H, W, C);
+  else return set_error(UNET_EINVAL, "maxpool2x2_bwd: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("maxpool2x2_bwd");
+  return UNET_OK;
+}
+
+extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, float* dbias,
+                                     int N, int H, int W, int Cout, int dtype, void* stream) {
+  UNET_REQUIRE(du && g && N > 0 && H > 0 && W > 0 && Cout > 0 && lddu >= Cout, UNET_EINVAL, "convt_bwd_gather: bad argument");
+  UNET_REQUIRE(Cout % 8 == 0 && lddu % 8 == 0 && aligned16(du) && aligned16(g), UNET_EALIGN, "convt_bwd_gather: needs Cout%%8==0");
+  UNET_REQUIRE(256 % (Cout / 8) == 0, UNET_EUNSUPPORTED, "convt_bwd_gather: Cout/8 must divide 256");
+  const int per_block = 256 / (Cout / 8);
+  const int64_t items = (int64_t)N * H * W * 4;
+  const unsigned grid = (unsigned)i64min(ceil_div(items, per_block), (int64_t)sm_count() * 8);
+  const size_t smem = (size_t)Cout * sizeof(float);
+  if (dtype == UNET_F32)
+    convt_bwd_gather_kernel<float><<<grid, 256, smem, ST>>>((const float*)du, lddu, (float*)g, dbias, N, H, W, Cout);
+  else if (dtype == UNET_BF16)
+    convt_bwd_gather_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)du, lddu, (__nv_bfloat16*)g, dbias, N, H, W, Cout);
+  else return set_error(UNET_EINVAL, "convt_bwd_gather: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("convt_bwd_gather");
+  return UNET_OK;
+}
+
+extern "C" int unet_adamw_step(float* w, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream) {
+  UNET_REQUIRE(w && g && m && v && hyper && n > 0, UNET_EINVAL, "adamw_step: bad argument");
+  UNET_REQUIRE(aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v), UNET_EALIGN, "adamw_step: buffers must be 16B aligned");
+  adamw_kernel<<<grid_for(ceil_div(n, 4)), 256, 0, ST>>>(w, g, m, v, n, hyper);
+  UNET_LAUNCH_CHECK("adamw_step");
+  return UNET_OK;
+}
+
+extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream) {
+  UNET_REQUIRE(src && (dst || dst_t) && R > 0 && C > 0, UNET_EINVAL, "cast_transpose_bf16: bad argument");
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(R, 32));
+  cast_transpose_bf16_kernel<<<grid, dim3(32, 8), 0, ST>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C);
+  UNET_LAUNCH_CHECK("cast_transpose_bf16");
+  return UNET_OK;
+}
+
+extern "C" int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream) {
+  UNET_REQUIRE(src && dst && n > 0, UNET_EINVAL, "cast: bad argument");
+  const unsigned grid = (unsigned)i64min(ceil_div(n, 256), (int64_t)sm_count() * 16);
+  if (src_dtype == UNET_F32 && dst_dtype == UNET_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, ST>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == UNET_BF16 && dst_dtype == UNET_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == UNET_F32 && dst_dtype == UNET_F32)
+    cast_kernel<float, float><<<grid, 256, 0, ST>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == UNET_BF16 && dst_dtype == UNET_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else return set_error(UNET_EINVAL, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  UNET_LAUNCH_CHECK("cast");
+  return UNET_OK;
+}
+
+extern "C" int unet_confusion_matrix_update(const float* y_true, const float* y_pred, int64_t n, int num_classes,
+                                            unsigned long long* counts, void* stream) {
+  UNET_REQUIRE(y_true && y_pred && counts && n > 0, UNET_EINVAL, "confusion_matrix_update: bad argument");
+  UNET_REQUIRE(num_classes >= 1 && num_classes <= 64, UNET_EUNSUPPORTED, "confusion_matrix_update: 1 <= num_classes <= 64");
+  const unsigned grid = (unsigned)i64min(ceil_div(n, 256 * 8), (int64_t)sm_count() * 8);
+  confusion_kernel<<<grid, 256, (size_t)num_classes * num_classes * sizeof(unsigned), ST>>>(y_true, y_pred, n, num_classes, counts, 0, 0.f);
+  UNET_LAUNCH_CHECK("confusion_matrix_update");
+  return UNET_OK;
+}
+
+extern "C" int unet_confusion_matrix_update_thr(const float* y_true, const float* prob, float thr, int64_t n,
+                                                unsigned long long* counts, void* stream) {
+  UNET_REQUIRE(y_true && prob && counts && n > 0, UNET_EINVAL, "confusion_matrix_update_thr: bad argument");
+  const unsigned grid = (unsigned)i64min(ceil_div(n, 256 * 8), (int64_t)sm_count() * 8);
+  confusion_kernel<<<grid, 256, 4 * sizeof(unsigned), ST>>>(y_true, prob, n, 2, counts, 1, thr);
+  UNET_LAUNCH_CHECK("confusion_matrix_update_thr");
+  return UNET_OK;
+}
+
+extern "C" int unet_seg_sums(const float* y_true, const float* y_pred, double* sums, int64_t NB, int64_t hw, int C, void* stream) {
+  UNET_REQUIRE(y_true && y_pred && sums && NB > 0 && hw > 0 && C > 0, UNET_EINVAL, "seg_sums: bad argument");
+  UNET_REQUIRE(C <= 256 && NB <= 65535, UNET_EUNSUPPORTED, "seg_sums: C <= 256, NB <= 65535");
+  const int block = (256 / C) * C;
+  const unsigned gx = (unsigned)i64max(1, i64min(ceil_div(hw * C, (int64_t)block * 16), ceil_div((int64_t)sm_count() * 8, NB)));
+  seg_sums_kernel<<<dim3(gx, (unsigned)NB), block, (size_t)3 * C * sizeof(double), ST>>>(y_true, y_pred, sums, hw, C);
+  UNET_LAUNCH_CHECK("seg_sums");
+  return UNET_OK;
+}
+
+extern "C" int unet_seg_loss_finalize(const double* sums, int NC_pairs, float smooth, int kind, float grad_scale,
+                                      float* out3, float* coef, void* stream) {
+  UNET_REQUIRE(sums && out3 && NC_pairs > 0 && (kind == 0 || kind == 1), UNET_EINVAL, "seg_loss_finalize: bad argument");
+  seg_loss_finalize_kernel<<<1, 256, 0, ST>>>(sums, NC_pairs, smooth, kind, grad_scale, out3, coef);
+  UNET_LAUNCH_CHECK("seg_loss_finalize");
+  return UNET_OK;
+}

@@ -1,0 +1,247 @@
+// Output head: Conv2D(num_classes, 1, activation=sigmoid|softmax) (reference model/u_net.py:105-112) fused with the
+// per-(image, class) Dice/IoU sums of utils/metrics.py:29-31 (forward) and with the gradient of
+// utils/loss.py:9-45 through the activation and the 1x1 convolution (backward).
+//
+// The GEMM is degenerate (N = 1 or 8 output channels, ~1 flop/B) so it runs on CUDA cores: 8 lanes share one
+// pixel, each lane owns K/8 input channels with 16-byte loads, partial dot products are combined with 3 shuffles.
+// Probabilities are always produced in fp32 from the fp32 accumulator (MeanIoU in train.py:231 truncates
+// probabilities to int, so they must not be rounded through bf16).
+#include "common.cuh"
+
+namespace unet {
+
+constexpr int kHeadMaxK = 512;
+
+template <typename T, int MAXC>
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
+                float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
+                int64_t hw, int K, int C, int pix_per_block) {
+  __shared__ float s_w[kHeadMaxK * MAXC];
+  __shared__ float s_b[MAXC];
+  __shared__ double s_sum[MAXC * 3];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_w[(i / C) * MAXC + (i % C)] = w[i];
+  if (threadIdx.x < C) s_b[threadIdx.x] = b ? b[threadIdx.x] : 0.f;
+  if (threadIdx.x < MAXC * 3) s_sum[threadIdx.x] = 0.0;
+  __syncthreads();
+
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7;          // which eighth of the channels
+  const int slot = threadIdx.x >> 3;        // pixel slot inside the block (32 pixels per pass)
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+
+  float si[MAXC], st[MAXC], sp[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) { si[c] = 0.f; st[c] = 0.f; sp[c] = 0.f; }
+
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
+    const int64_t p = p0 + slot;
+    const bool live = p < p_end;
+    const int64_t m = n * hw + (live ? p : p_begin);
+    float acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+    for (int k0 = sub * 8; k0 < K; k0 += 64) {
+      float v[8];
+      load8(x + m * ldx + k0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) acc[c] = fmaf(v[j], s_w[(k0 + j) * MAXC + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
+    }
+    if (live && sub == 0) {
+      float pr[MAXC];
+      if (C == 1) {
+        pr[0] = 1.f / (1.f + expf(-(acc[0] + s_b[0])));
+      } else {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c < C) { acc[c] += s_b[c]; mx = fmaxf(mx, acc[c]); }
+        float den = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c < C) { pr[c] = expf(acc[c] - mx); den += pr[c]; }
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c < C) pr[c] *= inv;
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) if (c < C) {
+        probs[m * C + c] = pr[c];
+        if (y_true) {
+          const float t = y_true[m * C + c];
+          si[c] = fmaf(t, pr[c], si[c]); st[c] += t; sp[c] += pr[c];
+        }
+      }
+    }
+  }
+  if (y_true && sums) {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c < C) {   // lanes with sub != 0 contribute zeros
+        const float a = warp_sum(si[c]), bq = warp_sum(st[c]), cq = warp_sum(sp[c]);
+        if ((threadIdx.x & 31) == 0) {
+          atomicAdd(&s_sum[c * 3 + 0], (double)a);
+          atomicAdd(&s_sum[c * 3 + 1], (double)bq);
+          atomicAdd(&s_sum[c * 3 + 2], (double)cq);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < C * 3) atomicAdd(&sums[n * C * 3 + threadIdx.x], s_sum[threadIdx.x]);
+  }
+}
+
+template <typename T, int MAXC>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ probs,
+                const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
+                float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block) {
+  __shared__ float s_w[kHeadMaxK * MAXC];
+  __shared__ float s_dw[kHeadMaxK * MAXC];
+  __shared__ float s_db[MAXC];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_w[(i / C) * MAXC + (i % C)] = w[i];
+  for (int i = threadIdx.x; i < K * MAXC; i += blockDim.x) s_dw[i] = 0.f;
+  if (threadIdx.x < MAXC) s_db[threadIdx.x] = 0.f;
+  __syncthreads();
+
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7;
+  const int slot = threadIdx.x >> 3;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+  float ca[MAXC], cb[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    ca[c] = c < C ? coef[(n * C + c) * 2] : 0.f;
+    cb[c] = c < C ? coef[(n * C + c) * 2 + 1] : 0.f;
+  }
+  // K == 64 in the reference model: one 8-channel group per lane.  Larger K loops.
+  float dbs[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) dbs[c] = 0.f;
+
+  for (int k0 = sub * 8; k0 < K; k0 += 64) {
+    float dwacc[8][MAXC];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) dwacc[j][c] = 0.f;
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
+      const int64_t p = p0 + slot;
+      if (p >= p_end) continue;
+      const int64_t m = n * hw + p;
+      float dz[MAXC];
+      if (C == 1) {
+        const float pr = probs[m], t = y_true[m];
+        dz[0] = fmaf(ca[0], t, cb[0]) * pr * (1.f - pr);
+      } else {
+        float pr[MAXC], gl[MAXC], dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c < C) {
+          pr[c] = probs[m * C + c];
+          gl[c] = fmaf(ca[c], y_true[m * C + c], cb[c]);
+          dot = fmaf(gl[c], pr[c], dot);
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) dz[c] = c < C ? pr[c] * (gl[c] - dot) : 0.f;
+      }
+      float v[8], o[8];
+      load8(x + m * ldx + k0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+          s = fmaf(dz[c], s_w[(k0 + j) * MAXC + c], s);
+          dwacc[j][c] = fmaf(v[j], dz[c], dwacc[j][c]);
+        }
+        o[j] = s;
+      }
+      if (dx) store8(dx + m * lddx + k0, o);
+      if (k0 == sub * 8 && sub == 0) {
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) dbs[c] += dz[c];
+      }
+    }
+    // lanes 8 apart share `sub`: fold them, then one shared atomic per (channel, class) per warp
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        float s = dwacc[j][c];
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        if ((threadIdx.x & 31) < 8 && c < C) atomicAdd(&s_dw[(k0 + j) * MAXC + c], s);
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const float s = warp_sum(dbs[c]);
+    if ((threadIdx.x & 31) == 0 && c < C) atomicAdd(&s_db[c], s);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(&dw[i], s_dw[(i / C) * MAXC + (i % C)]);
+  if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
+}
+
+static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block) {
+  // enough blocks to fill the machine ~4x, each block a multiple of 32 pixels inside one image
+  int64_t blocks_per_img = i64max(1, ceil_div((int64_t)sm_count() * 4, NB));
+  int64_t ppb = ceil_div(ceil_div(hw, blocks_per_img), 32) * 32;
+  if (ppb < 256) ppb = 256;
+  blocks_per_img = ceil_div(hw, ppb);
+  *grid = dim3((unsigned)blocks_per_img, (unsigned)NB);
+  *pix_per_block = (int)ppb;
+}
+
+}  // namespace unet
+
+using namespace unet;
+
+extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const float* b, float* probs,
+                             const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype, void* stream) {
+  UNET_REQUIRE(x && w && probs && M > 0 && hw > 0 && K > 0 && C > 0 && ldx >= K, UNET_EINVAL, "head_fwd: bad argument");
+  UNET_REQUIRE(M % hw == 0, UNET_EINVAL, "head_fwd: M must be a multiple of hw");
+  UNET_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && aligned16(x), UNET_EALIGN, "head_fwd: needs K%%8==0, ld%%8==0, 16B pointer");
+  UNET_REQUIRE(K <= kHeadMaxK && C <= 8, UNET_EUNSUPPORTED, "head_fwd: K <= %d and num_classes <= 8 (got %d, %d)", kHeadMaxK, K, C);
+  UNET_REQUIRE(M / hw <= 65535, UNET_EUNSUPPORTED, "head_fwd: batch <= 65535");
+  UNET_REQUIRE(!y_true || sums, UNET_EINVAL, "head_fwd: y_true given without sums");
+  dim3 grid; int ppb;
+  head_grid(M / hw, hw, &grid, &ppb);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(T, MC) head_fwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
+  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH(float, 8); }
+  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH(__nv_bfloat16, 8); }
+  else return set_error(UNET_EINVAL, "head_fwd: bad dtype %d", dtype);
+#undef LAUNCH
+  UNET_LAUNCH_CHECK("head_fwd");
+  return UNET_OK;
+}
+
+extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
+                             const float* coef, void* dx, int64_t lddx, float* dw, float* db,
+                             int64_t M, int64_t hw, int K, int C, int dtype, void* stream) {
+  UNET_REQUIRE(x && w && probs && y_true && coef && dw && db, UNET_EINVAL, "head_bwd: null pointer");
+  UNET_REQUIRE(M > 0 && hw > 0 && K > 0 && C > 0 && ldx >= K && M % hw == 0, UNET_EINVAL, "head_bwd: bad dims");
+  UNET_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && aligned16(x) && (!dx || (lddx % 8 == 0 && aligned16(dx))), UNET_EALIGN,
+               "head_bwd: needs K%%8==0, ld%%8==0, 16B pointers");
+  UNET_REQUIRE(K <= kHeadMaxK && C <= 8, UNET_EUNSUPPORTED, "head_bwd: K <= %d and num_classes <= 8", kHeadMaxK);
+  UNET_REQUIRE(M / hw <= 65535, UNET_EUNSUPPORTED, "head_bwd: batch <= 65535");
+  dim3 grid; int ppb;
+  head_grid(M / hw, hw, &grid, &ppb);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH(T, MC) head_bwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
+  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH(float, 8); }
+  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH(__nv_bfloat16, 8); }
+  else return set_error(UNET_EINVAL, "head_bwd: bad dtype %d", dtype);
+#undef LAUNCH
+  UNET_LAUNCH_CHECK("head_bwd");
+  return UNET_OK;
+}

@@ -1,0 +1,8 @@
+"""Import alias: the product package lives in `unet-image-segmentation_b200/` (not a legal Python identifier);
+`import unet_b200` resolves to it."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "unet-image-segmentation_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

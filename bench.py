@@ -1,0 +1,377 @@
+#!/usr/bin/env python3
+"""bench.py — the hot path on synthetic data: U-Net (reference model/u_net.py) Dice-loss training or inference, img/s.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (sm_100a kernels via the C-ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU arm: torch-CPU port of the reference's TF path
+
+Default workload = BASELINE.json configs[2] (the 512x512 configuration the metric is quoted on): U_NET((512,512,3)),
+binary mask, Dice loss + Keras-form AdamW, dropout 0.2, batch 64 per GPU, bf16 activations / fp32 accumulation,
+data-parallel over N GPUs (weak scaling; one NCCL gradient all-reduce per step, overlapped with backward).
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (mode, H, W, classes, batch per GPU, description)
+    "train512": ("train", 512, 512, 1, 64, "BASELINE configs[2]: U-Net 512x512 Dice-loss training, batch 64/GPU"),
+    "train256": ("train", 256, 256, 1, 32, "BASELINE configs[1]: U-Net 256x256 Dice-loss training, batch 32"),
+    "train512c8": ("train", 512, 512, 8, 32, "BASELINE configs[4]: 8-class softmax U-Net 512x512 training, batch 32/GPU"),
+    "infer256": ("infer", 256, 256, 1, 8, "BASELINE configs[0]: U-Net 256x256 inference, batch 8"),
+    "infer512": ("infer", 512, 512, 1, 64, "U-Net 512x512 inference, batch 64/GPU"),
+    "infer1024": ("infer", 1024, 1024, 1, 16, "BASELINE configs[3]: U-Net 1024x1024 inference, batch 16/GPU"),
+}
+RIDGE_FLOP_PER_BYTE = 212.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="train512", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ====================================================================================================== CPU arm
+def cpu_train_sample(H, W, classes, batch, steps, warmup=1):
+    """The oracle's torch-CPU port of the reference training step (oracle/torch_ref.py), all host threads."""
+    import numpy as np
+    import torch
+    from oracle import torch_ref as TR
+    from oracle import unet_ref as R
+    specs = R.layer_specs((H, W, 3), classes, 0.2, True)
+    P = R.init_params(specs, seed=2301)
+    x, y = R.synthetic_batch(batch, H, W, 3, classes, seed=2301)
+    Pt = TR.to_torch(P, dtype=torch.float32, requires_grad=True)
+    train = [v for v in Pt.values() if v.requires_grad]
+    m = [torch.zeros_like(v) for v in train]
+    v2 = [torch.zeros_like(v) for v in train]
+    xt, yt = torch.tensor(x), torch.tensor(y)
+    seeds = {"bneck_dropout": 1, "dec4_dropout": 2, "dec3_dropout": 3, "dec2_dropout": 4}
+    times = []
+    for t in range(1, warmup + steps + 1):
+        t0 = time.perf_counter()
+        probs = TR.forward(Pt, xt, classes, 0.2, True, training=True, drop_seeds=seeds)
+        loss = 1.0 - TR.dice_coef(yt, probs)
+        grads = torch.autograd.grad(loss, train)
+        with torch.no_grad():      # Keras-form AdamW (train.py:226)
+            a = 2e-3 * (1 - 0.999 ** t) ** 0.5 / (1 - 0.9 ** t)
+            for w_, g_, m_, v_ in zip(train, grads, m, v2):
+                w_.mul_(1 - 2e-3 * 1e-4)
+                m_.mul_(0.9).add_(g_, alpha=0.1)
+                v_.mul_(0.999).addcmul_(g_, g_, value=0.001)
+                w_.addcdiv_(m_, v_.sqrt().add_(1e-7), value=-a)
+        float(loss)
+        if t > warmup:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def cpu_infer_sample(H, W, classes, batch, steps, warmup=1):
+    import torch
+    from oracle import torch_ref as TR
+    from oracle import unet_ref as R
+    specs = R.layer_specs((H, W, 3), classes, 0.2, True)
+    Pt = TR.to_torch(R.init_params(specs, seed=2301), dtype=torch.float32)
+    x, _ = R.synthetic_batch(batch, H, W, 3, classes, seed=2301)
+    xt = torch.tensor(x)
+    times = []
+    with torch.no_grad():
+        for t in range(warmup + steps):
+            t0 = time.perf_counter()
+            TR.forward(Pt, xt, classes, 0.2, True, training=False).sum().item()
+            if t >= warmup:
+                times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), sum(times) / len(times)
+
+
+def cpu_sample_size(mode, H, W):
+    """Bounded sample: a few images so one CPU step is seconds, not minutes."""
+    px = H * W
+    if mode == "train":
+        return max(1, min(8, (2 * 512 * 512) // px))
+    return max(1, min(8, (8 * 256 * 256) // px))
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    mode, H, W, classes, _, desc = WORKLOADS[args.workload]
+    b = cpu_sample_size(mode, H, W)
+    cores = torch.get_num_threads()
+    steps = max(1, min(args.steps, 3))
+    fn = cpu_train_sample if mode == "train" else cpu_infer_sample
+    ips, sec = fn(H, W, classes, b, steps, warmup=min(args.warmup, 1))
+    sample = f"{steps} step(s) of batch {b} at {H}x{W} (of the workload's batch), torch-CPU fp32 port of the TF path, {cores} threads"
+    line = {
+        "impl": "reference", "metric": f"{mode} img/s", "value": round(ips, 3), "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "H": H, "W": W, "classes": classes, "cpu_batch": b},
+        "cpu_baseline": {"value": round(ips, 3), "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "TensorFlow is not installable in this image (no wheel, no network): the CPU arm is the oracle's torch port",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ====================================================================================================== B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from unet_b200 import dist as D
+    from unet_b200 import ops
+    from unet_b200.keras_api import AdamW, MeanIoU, Model
+
+    rank, local_rank, world = D.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    mode, H, W, classes, batch, desc = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    hbm_peak, tc_peak, peak_kind = peaks()
+
+    model = Model((H, W, 3), num_classes=classes, dropout_rate=0.2, use_batch_norm=True, dtype=args.dtype,
+                  seed=2301)
+    model.compile(optimizer=AdamW(learning_rate=2e-3, weight_decay=1e-4), loss="dice_loss", metrics=[])
+    eng = model.engine
+    if world > 1:
+        dist.broadcast(eng.w, src=0)
+        dist.broadcast(eng.state, src=0)
+        eng._stage_dirty = True
+        if mode == "train":
+            model.enable_data_parallel()
+
+    # synthetic shard of the global batch: uniform images, filled-quadrilateral masks (oracle generator's recipe restated)
+    g = torch.Generator(device="cuda"); g.manual_seed(2301 + rank)
+    x_dev = torch.rand((batch, H, W, 3), device="cuda", generator=g)
+    yy, xx = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+    cx = (torch.rand(batch, device="cuda", generator=g) * 0.4 + 0.3) * W
+    cy = (torch.rand(batch, device="cuda", generator=g) * 0.4 + 0.3) * H
+    rx = (torch.rand(batch, device="cuda", generator=g) * 0.2 + 0.15) * W
+    ry = (torch.rand(batch, device="cuda", generator=g) * 0.2 + 0.15) * H
+    inside = ((xx[None] - cx[:, None, None]).abs() < rx[:, None, None]) & ((yy[None] - cy[:, None, None]).abs() < ry[:, None, None])
+    if classes == 1:
+        y_dev = inside.float()[..., None].contiguous()
+    else:
+        lab = (inside.long() * (1 + (xx[None] // 32 + yy[None] // 32) % (classes - 1)))
+        y_dev = torch.nn.functional.one_hot(lab, classes).float().contiguous()
+    x_pin, y_pin = x_dev.cpu().pin_memory(), y_dev.cpu().pin_memory()
+
+    def device_step():
+        if mode == "train":
+            out3 = eng.train_forward_backward(x_dev, y_dev, "dice")
+            if model._grad_sync is not None:
+                model._grad_sync.finish()
+                D.average_(eng.state)
+            eng.apply_gradients()
+            return out3
+        return eng.forward_inference(x_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+
+    # ---------------- timed region 1: inputs resident in HBM
+    launches0 = ops.launches
+    ops.profile_begin()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            device_step()
+        e1.record()
+        barrier()
+    prof = ops.profile_end()
+    launches = ops.launches - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = batch * world * args.steps / (ms_total / 1e3)
+
+    # ---------------- timed region 2: end to end through the public (Keras-shaped) API with pinned host buffers
+    e2e = None
+    if not args.no_e2e:
+        def api_step():
+            if mode == "train":
+                return model.train_on_batch(x_pin, y_pin)[0]          # H2D x,y ... D2H loss
+            return model.predict(x_pin, batch_size=batch)             # H2D x ... D2H probabilities
+        for _ in range(2):
+            api_step()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            api_step()
+        e1.record()
+        barrier()
+        ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        h2d = x_pin.numel() * 4 + (y_pin.numel() * 4 if mode == "train" else 0)
+        d2h = 12 if mode == "train" else batch * H * W * classes * 4
+        e2e = {"value": round(batch * world * args.steps / (float(ms2.item()) / 1e3), 2), "unit": "img/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    if rank != 0:
+        return
+    # ---------------- roofline of the dominant kernel
+    rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    kernel_ms = sum(r["ms"] for _, r in rows)
+    top_key, top = rows[0]
+    per_call_ms = top["ms"] / top["calls"]
+    ai = top["flops"] / max(top["bytes"], 1)
+    if top_key.startswith("gemm_tc") and ai > RIDGE_FLOP_PER_BYTE:
+        roof = {"bound": "tensor", "achieved": round(top["flops"] / top["calls"] / (per_call_ms * 1e-3) / 1e12, 2),
+                "peak": tc_peak, "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": round(top["bytes"] / top["calls"] / (per_call_ms * 1e-3) / 1e9, 1),
+                "peak": hbm_peak, "unit": "GB/s"}
+    roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
+    roof["kernel"] = top_key
+    roof["share_of_step"] = round(top["ms"] / kernel_ms, 4)
+    roof["peak_source"] = f"{peak_kind} ({'MEASURED_PEAKS.json' if peak_kind == 'measured' else 'B200_PROFILING.md fallback'}, sustained)"
+    roof["traffic"] = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            roof["traffic"] = json.load(f).get(top_key)
+    except Exception:
+        pass
+    # whole-step HBM view: algorithmic bytes of every launch / step time
+    tot_bytes = sum(r["bytes"] for _, r in rows) / args.steps
+    tot_flops = sum(r["flops"] for _, r in rows) / args.steps
+    table = [{"kernel": k, "calls_per_step": r["calls"] / args.steps, "ms_per_step": round(r["ms"] / args.steps, 3),
+              "GBps": round(r["bytes"] / max(r["ms"], 1e-9) / 1e6, 1), "TFLOPs": round(r["flops"] / max(r["ms"], 1e-9) / 1e9, 2)}
+             for k, r in rows]
+    if args.breakdown:
+        for t in table:
+            print(f"{t['kernel']:58s} {t['calls_per_step']:5.1f} {t['ms_per_step']:9.3f} ms {t['GBps']:8.1f} GB/s {t['TFLOPs']:8.2f} TF/s",
+                  file=sys.stderr)
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        b = cpu_sample_size(mode, H, W)
+        fn = cpu_train_sample if mode == "train" else cpu_infer_sample
+        ips, sec = fn(H, W, classes, b, 2, warmup=1)
+        cpu = {"value": round(ips, 3), "unit": "img/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"2 steps of batch {b} at {H}x{W}, torch-CPU fp32 port of the reference's TF path ({sec:.1f} s/step)"}
+
+    line = {
+        "metric": f"{mode} img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": desc, "H": H, "W": W, "classes": classes, "batch_per_gpu": batch,
+                   "global_batch": batch * world, "dropout": 0.2, "optimizer": "AdamW(2e-3, wd 1e-4)" if mode == "train" else None,
+                   "parallelism": f"dp{world}", "l2": "inputs and activations exceed L2 (126 MB) many times over; no flush needed"},
+        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "cpu_baseline": cpu,
+        "step_hbm": {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 2), "GBps": round(tot_bytes / (ms_total / args.steps) / 1e6, 1),
+                     "frac_of_peak": round(tot_bytes / (ms_total / args.steps) / 1e6 / hbm_peak, 4),
+                     "TFLOP_per_step": round(tot_flops / 1e12, 2)},
+        "kernels": table[:12],
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        pass
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

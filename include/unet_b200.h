@@ -54,6 +54,8 @@ typedef struct {
   uint32_t seed;
   int64_t  ctot;      /* channels of the logical tensor the mask is defined on (concat buffer width) */
   int64_t  c0;        /* channel offset of this view inside that tensor */
+  const uint32_t* seed_dev; /* optional DEVICE word added to `seed` inside the kernel, so that a captured CUDA graph
+                               draws a fresh mask on every replay (unet_step_advance increments it); NULL = 0 */
 } unet_dropout;
 
 typedef struct {
@@ -174,6 +176,8 @@ int unet_confusion_matrix_update_thr(const float* y_true, const float* prob, flo
 /* hyper (device, fp32[8]): lr, wd, beta1, beta2, eps, step t (as float), grad_scale, unused — read on device so a
    captured graph follows ReduceLROnPlateau without re-capture. */
 int unet_adamw_step(float* w, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream);
+/* end of one optimizer step, on device: hyper[5] (t) += 1 and *counter += 1 (the dropout seed_dev word). Either may be NULL. */
+int unet_step_advance(float* hyper, uint32_t* counter, void* stream);
 
 /* ---- parameter staging for the tensor-core path: dst[r,c] = bf16(src[r,c]); dst_t[c,r] = bf16(src[r,c]) ---- */
 int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream);

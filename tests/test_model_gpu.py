@@ -1,0 +1,132 @@
+"""Whole-model parity of the engine (unet_b200/engine.py) against the NumPy oracle on seeded inputs and weights.
+Tolerances are BASELINE.json's: fp32 probabilities <= 1e-4 max abs; bf16 <= 2e-2 max abs and >= 99.9 % agreement of
+the thresholded mask; loss within 1e-3."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(shape, nc, rate, bn, dtype, P):
+    from unet_b200.engine import UNetEngine
+    eng = UNetEngine(shape, num_classes=nc, dropout_rate=rate, use_batch_norm=bn, dtype=dtype)
+    eng.dropout_masks_from_step = False
+    eng.set_weights(P)
+    return eng
+
+
+def _params(shape, nc, rate, bn, seed=3):
+    specs = R.layer_specs(shape, nc, rate, bn)
+    return R.init_params(specs, seed=seed, trained_like=True)
+
+
+def dev(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32), device="cuda")
+
+
+@pytest.mark.parametrize("nc", [1, 8])
+@pytest.mark.parametrize("bn", [True, False])
+def test_forward_fp32(nc, bn):
+    shape = (32, 48, 3)
+    P = _params(shape, nc, 0.2, bn)
+    x, _ = R.synthetic_batch(3, shape[0], shape[1], 3, nc, seed=5)
+    ref = R.UNetOracle(shape, nc, 0.2, bn).forward(P, x)
+    got = _engine(shape, nc, 0.2, bn, "fp32", P).forward_inference(dev(x)).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-4
+
+
+@pytest.mark.parametrize("nc", [1, 8])
+def test_forward_bf16(nc):
+    shape = (64, 64, 3)
+    P = _params(shape, nc, 0.2, True)
+    P["output_mask/kernel"] = P["output_mask/kernel"] * 8.0      # decisive logits, as a trained model has
+    x, _ = R.synthetic_batch(4, 64, 64, 3, nc, seed=6)
+    ref = R.UNetOracle(shape, nc, 0.2, True).forward(P, x)
+    got = _engine(shape, nc, 0.2, True, "bf16", P).forward_inference(dev(x)).cpu().numpy()
+    assert np.abs(got - ref).max() <= 2e-2
+    if nc == 1:
+        agree = np.mean((got > 0.5) == (ref > 0.5))
+    else:
+        agree = np.mean(got.argmax(-1) == ref.argmax(-1))
+    assert agree >= 0.999, agree
+
+
+def _check_grads(eng, grads_ref, rtol_norm):
+    worst = 0.0
+    for name, gr in grads_ref.items():
+        g = eng.wview(name, eng.g).cpu().numpy().reshape(gr.shape).astype(np.float64)
+        denom = np.linalg.norm(gr) + 1e-12
+        rel = np.linalg.norm(g - gr) / denom
+        worst = max(worst, rel)
+        assert rel <= rtol_norm, f"{name}: relative gradient error {rel:.3e} (|g_ref| = {denom:.3e})"
+    return worst
+
+
+@pytest.mark.parametrize("cfg", [(1, True, 0.0, "dice"), (1, True, 0.2, "dice"), (8, True, 0.0, "dice"),
+                                 (1, False, 0.2, "iou"), (1, True, 0.0, "iou")])
+def test_train_step_fp32(cfg):
+    nc, bn, rate, loss = cfg
+    shape = (32, 32, 3)
+    P = _params(shape, nc, rate, bn)
+    x, y = R.synthetic_batch(3, 32, 32, 3, nc, seed=9)
+    eng = _engine(shape, nc, rate, bn, "fp32", P)
+    orc = R.UNetOracle(shape, nc, rate, bn)
+    loss_ref, probs_ref, grads_ref, stats_ref = orc.loss_and_grads(P, x, y, loss=loss, drop_seeds=eng._drop_seed)
+    out3 = eng.train_forward_backward(dev(x), dev(y), loss=loss).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= 1e-4
+    np.testing.assert_allclose(eng._plans[(3, True)].t["probs"].cpu().numpy(), probs_ref, atol=1e-4)
+    _check_grads(eng, grads_ref, 2e-3)
+    for name, v in stats_ref.items():
+        np.testing.assert_allclose(eng.wview(name).cpu().numpy(), v, rtol=1e-4, atol=1e-5)
+    # AdamW, Keras form, on the whole flat buffer
+    w0 = {n: P[n].astype(np.float64) for n in grads_ref}
+    eng.apply_gradients()
+    for n, g in grads_ref.items():
+        w1, _, _ = R.adamw_step(w0[n], g, np.zeros_like(g), np.zeros_like(g), 1)
+        got = eng.wview(n).cpu().numpy().reshape(g.shape)
+        # a parameter moves by ~lr on the first step whatever |g| is; sign(g) is what must agree where g is not ~0
+        big = np.abs(g) > 1e-6 * (np.abs(g).max() + 1e-30)
+        np.testing.assert_allclose(got[big], w1[big], rtol=0, atol=2e-4)
+
+
+def test_train_step_bf16():
+    shape = (64, 64, 3)
+    P = _params(shape, 1, 0.2, True)
+    x, y = R.synthetic_batch(4, 64, 64, 3, 1, seed=10)
+    eng = _engine(shape, 1, 0.2, True, "bf16", P)
+    loss_ref, _, grads_ref, _ = R.UNetOracle(shape, 1, 0.2, True).loss_and_grads(P, x, y, drop_seeds=eng._drop_seed)
+    out3 = eng.train_forward_backward(dev(x), dev(y)).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= 1e-3
+    # bf16 activations: gradients agree in direction and magnitude, not bit for bit
+    num = den_a = den_b = 0.0
+    for name, gr in grads_ref.items():
+        g = eng.wview(name, eng.g).cpu().numpy().reshape(gr.shape).astype(np.float64)
+        num += float((g * gr).sum()); den_a += float((g * g).sum()); den_b += float((gr * gr).sum())
+    cos = num / np.sqrt(den_a * den_b)
+    assert cos > 0.99, cos
+    assert 0.9 < np.sqrt(den_a / den_b) < 1.1
+
+
+def test_training_reduces_loss_bf16():
+    from unet_b200.engine import UNetEngine
+    eng = UNetEngine((64, 64, 3), dtype="bf16", dropout_rate=0.2)
+    x, y = R.synthetic_batch(8, 64, 64, 3, 1, seed=12)
+    xd, yd = dev(x), dev(y)
+    losses = [float(eng.train_step(xd, yd)[0]) for _ in range(30)]
+    assert losses[-1] < losses[0] - 0.05, losses
+
+
+def test_eval_batch_and_shapes():
+    from unet_b200.engine import UNetEngine
+    with pytest.raises(ValueError):
+        UNetEngine((30, 32, 3))
+    with pytest.raises(ValueError):
+        UNetEngine((32, 32))
+    eng = UNetEngine((32, 32, 3), dtype="fp32")
+    x, y = R.synthetic_batch(2, 32, 32, 3, 1, seed=1)
+    out3 = eng.evaluate_batch(dev(x), dev(y)).cpu().numpy()
+    probs = eng.forward_inference(dev(x)).cpu().numpy()
+    assert abs(out3[1] - R.dice_coef(y, probs)) < 1e-5 and abs(out3[2] - R.iou_coef(y, probs)) < 1e-5

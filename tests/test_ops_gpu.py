@@ -1,0 +1,430 @@
+"""Per-kernel parity: every C-ABI entry point of libunet_b200.so against the NumPy oracle (oracle/unet_ref.py) on the
+same seeded inputs.  fp32 kernels: tight tolerances (summation order only).  bf16 kernels: operands are rounded to
+bf16 on the host first, so the only differences are fp32 accumulation order and the final bf16 rounding (2^-8 rel).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_ref as R
+
+pytestmark = pytest.mark.gpu
+
+ops = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _load():
+    global ops
+    from unet_b200 import ops as _ops
+    _ops.device_check(0)
+    ops = _ops
+
+
+def dev(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), device="cuda").to(dtype).contiguous()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.detach().float().cpu().numpy().astype(np.float64)
+
+
+def bf16_round(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+
+
+def tol(dtype):
+    return dict(rtol=2e-5, atol=2e-5) if dtype == torch.float32 else dict(rtol=1.0 / 128, atol=1e-2)
+
+
+RNG = np.random.default_rng(2301)
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+# ------------------------------------------------------------------------------------------------ depthwise
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (3, 33, 9, 24), (2, 8, 8, 3), (1, 1, 1, 16), (1, 64, 48, 128)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_dwconv_fwd(dtype, shape, flip):
+    x = RNG.standard_normal(shape).astype(np.float32)
+    w = RNG.standard_normal((3, 3, shape[3])).astype(np.float32)
+    xr = bf16_round(x) if dtype == torch.bfloat16 else x.astype(np.float64)
+    ref = R.dwconv3x3(xr, w[::-1, ::-1].astype(np.float64) if flip else w.astype(np.float64))
+    xd, wd = dev(x, dtype), dev(w.reshape(9, -1))
+    y = torch.empty_like(xd)
+    ops.dwconv3x3(xd, wd, y, flip=flip)
+    np.testing.assert_allclose(host(y), ref, **tol(dtype))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_fwd_views_affine_dropout(dtype):
+    n, h, w, c, ctot = 2, 12, 10, 32, 96
+    buf = RNG.standard_normal((n, h, w, ctot)).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, c).astype(np.float32)
+    sh = RNG.standard_normal(c).astype(np.float32)
+    bd = dev(buf, dtype)
+    out = torch.zeros((n, h, w, 64), device="cuda", dtype=dtype)
+    xin = bd[..., 40:40 + c]
+    br = bf16_round(buf) if dtype == torch.bfloat16 else buf.astype(np.float64)
+    xa = np.maximum(br[..., 40:40 + c] * sc + sh, 0)
+    ref = R.dwconv3x3(xa, wk.astype(np.float64))
+    drop = ops.make_dropout(0.25, 77, ctot=64, c0=16)
+    ops.dwconv3x3(xin, dev(wk.reshape(9, -1)), out[..., 16:16 + c], in_scale=dev(sc), in_shift=dev(sh), drop=drop)
+    mult = R.dropout_multiplier((n, h, w, 64), 0.25, 77)[..., 16:16 + c]
+    got = host(out)
+    np.testing.assert_allclose(got[..., 16:16 + c], ref * mult, **tol(dtype))
+    assert np.all(got[..., :16] == 0) and np.all(got[..., 48:] == 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (2, 40, 9, 3), (1, 70, 12, 128), (2, 8, 8, 1024)])
+def test_dwconv_bwd_weight(dtype, shape):
+    x = RNG.standard_normal(shape).astype(np.float32)
+    dy = RNG.standard_normal(shape).astype(np.float32)
+    xr, dyr = (bf16_round(x), bf16_round(dy)) if dtype == torch.bfloat16 else (x.astype(np.float64), dy.astype(np.float64))
+    _, ref = R.dwconv3x3_bwd(xr, np.zeros((3, 3, shape[3])), dyr)
+    dw = torch.zeros((9, shape[3]), device="cuda")
+    ops.dwconv3x3_bwd_weight(dev(x, dtype), dev(dy, dtype), dw)
+    np.testing.assert_allclose(host(dw).reshape(3, 3, -1), ref, rtol=1e-4, atol=1e-3 * np.sqrt(np.prod(shape[:3])))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM, CUDA cores
+@pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("mkn", [(70, 3, 64), (129, 40, 33), (64, 64, 1), (256, 128, 96)])
+def test_gemm_simt_fp32(a_trans, b_trans, mkn):
+    M, K, N = mkn
+    A = RNG.standard_normal((K, M) if a_trans else (M, K)).astype(np.float32)
+    B = RNG.standard_normal((N, K) if b_trans else (K, N)).astype(np.float32)
+    ref = (A.T if a_trans else A).astype(np.float64) @ (B.T if b_trans else B).astype(np.float64)
+    Cm = torch.zeros((M, N), device="cuda")
+    ops.gemm(dev(A), dev(B), Cm, a_trans=a_trans, b_trans=b_trans, accumulate=a_trans)
+    np.testing.assert_allclose(host(Cm), ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gemm_simt_epilogues():
+    M, K, N = 300, 24, 40
+    A = RNG.standard_normal((M, K)).astype(np.float32)
+    B = RNG.standard_normal((K, N)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, N).astype(np.float32)
+    sh = RNG.standard_normal(N).astype(np.float32)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    Cm = torch.empty((M, N), device="cuda")
+    ops.gemm(dev(A), dev(B), Cm, epilogue=ops.EPI_AFFINE_RELU, scale=dev(sc), shift=dev(sh))
+    np.testing.assert_allclose(host(Cm), np.maximum(ref * sc + sh, 0), rtol=1e-5, atol=1e-4)
+    cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.gemm(dev(A), dev(B), Cm, epilogue=ops.EPI_STATS, colsum=cs, colsq=cq)
+    np.testing.assert_allclose(host(Cm), ref, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(cs.cpu().numpy(), ref.sum(0), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(cq.cpu().numpy(), (ref ** 2).sum(0), rtol=1e-5, atol=1e-3)
+
+
+def _convt_case(dtype, n, h, w, cin, cout, rate):
+    x = RNG.standard_normal((n, h, w, cin)).astype(np.float32)
+    k = (RNG.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = RNG.standard_normal(cout).astype(np.float32)
+    xr, kr = (bf16_round(x), bf16_round(k)) if dtype == torch.bfloat16 else (x.astype(np.float64), k.astype(np.float64))
+    ref = R.convt2x2(xr, kr, b.astype(np.float64))
+    Bkn = k.transpose(3, 0, 1, 2).reshape(cin, 4 * cout)          # [K, (a,b,co)]
+    concat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), device="cuda", dtype=dtype)
+    drop = ops.make_dropout(rate, 5, ctot=2 * cout, c0=0)
+    if dtype == torch.bfloat16:
+        ops.gemm(dev(x, dtype), dev(Bkn.T.copy(), dtype), concat[..., :cout], b_trans=True, epilogue=ops.EPI_CONVT,
+                 shift=dev(b), convt_hw=(h, w), drop=drop)
+    else:
+        ops.gemm(dev(x), dev(Bkn), concat[..., :cout], epilogue=ops.EPI_CONVT, shift=dev(b), convt_hw=(h, w), drop=drop)
+    if rate > 0:
+        ref = ref * R.dropout_multiplier((n, 2 * h, 2 * w, 2 * cout), rate, 5)[..., :cout]
+    got = host(concat)
+    np.testing.assert_allclose(got[..., :cout], ref, **tol(dtype))
+    assert np.all(got[..., cout:] == 0)
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.2])
+def test_convt_simt(rate):
+    _convt_case(torch.float32, 2, 3, 5, 24, 12, rate)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM, tcgen05
+TC_SHAPES = [(128, 64, 64), (1000, 64, 64), (300, 72, 128), (4096, 512, 512), (257, 1024, 256), (640, 128, 1024),
+             (129, 8, 64), (2048, 256, 192), (96, 1024, 2048)]
+
+
+@pytest.mark.parametrize("mkn", TC_SHAPES)
+@pytest.mark.parametrize("out_dtype", DTYPES)
+def test_gemm_tc_nt(mkn, out_dtype):
+    M, K, N = mkn
+    A = RNG.standard_normal((M, K)).astype(np.float32)
+    Bt = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    ref = bf16_round(A) @ bf16_round(Bt).T
+    Cm = torch.full((M, N), float("nan"), device="cuda", dtype=out_dtype)
+    ops.gemm(dev(A, torch.bfloat16), dev(Bt, torch.bfloat16), Cm, b_trans=True, tensor_core=True)
+    np.testing.assert_allclose(host(Cm), ref, **(dict(rtol=1e-4, atol=1e-4) if out_dtype == torch.float32 else tol(out_dtype)))
+
+
+def test_gemm_tc_nt_strided_affine_relu():
+    M, K, N = 900, 128, 128
+    Abuf = RNG.standard_normal((M, 256)).astype(np.float32)
+    Bt = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, N).astype(np.float32)
+    sh = RNG.standard_normal(N).astype(np.float32)
+    Ad = dev(Abuf, torch.bfloat16)
+    out = torch.zeros((M, 384), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(Ad[:, 64:64 + K], dev(Bt, torch.bfloat16), out[:, 128:128 + N], b_trans=True, tensor_core=True,
+             epilogue=ops.EPI_AFFINE_RELU, scale=dev(sc), shift=dev(sh))
+    ref = np.maximum((bf16_round(Abuf)[:, 64:64 + K] @ bf16_round(Bt).T) * sc + sh, 0)
+    got = host(out)
+    np.testing.assert_allclose(got[:, 128:128 + N], ref, **tol(torch.bfloat16))
+    assert np.all(got[:, :128] == 0) and np.all(got[:, 256:] == 0)
+
+
+@pytest.mark.parametrize("mkn", [(1000, 64, 64), (5000, 256, 512), (333, 128, 192)])
+@pytest.mark.parametrize("out_dtype", DTYPES)
+def test_gemm_tc_stats(mkn, out_dtype):
+    M, K, N = mkn
+    A = RNG.standard_normal((M, K)).astype(np.float32)
+    Bt = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    Cm = torch.empty((M, N), device="cuda", dtype=out_dtype)
+    cs = torch.zeros(N, device="cuda", dtype=torch.float64)
+    cq = torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.gemm(dev(A, torch.bfloat16), dev(Bt, torch.bfloat16), Cm, b_trans=True, tensor_core=True,
+             epilogue=ops.EPI_STATS, colsum=cs, colsq=cq)
+    got = host(Cm)     # the statistics are defined over the STORED values
+    np.testing.assert_allclose(got, bf16_round(A) @ bf16_round(Bt).T, **(dict(rtol=1e-4, atol=1e-4) if out_dtype == torch.float32 else tol(out_dtype)))
+    np.testing.assert_allclose(cs.cpu().numpy(), got.sum(0), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(cq.cpu().numpy(), (got ** 2).sum(0), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.2])
+@pytest.mark.parametrize("cfg", [(2, 4, 4, 128, 64), (1, 8, 6, 1024, 512), (3, 5, 3, 256, 128)])
+def test_convt_tc(cfg, rate):
+    _convt_case(torch.bfloat16, *cfg, rate)
+
+
+@pytest.mark.parametrize("pmn", [(4096, 64, 64), (10000, 128, 256), (777, 1024, 512), (20000, 8, 64), (3000, 512, 1024)])
+def test_gemm_tc_wgrad(pmn):
+    P, Mo, No = pmn
+    A = RNG.standard_normal((P, Mo)).astype(np.float32)
+    B = RNG.standard_normal((P, No)).astype(np.float32)
+    ref = bf16_round(A).T @ bf16_round(B)
+    Cm = torch.zeros((Mo, No), device="cuda")
+    ops.gemm(dev(A, torch.bfloat16), dev(B, torch.bfloat16), Cm, a_trans=True, accumulate=True, tensor_core=True)
+    np.testing.assert_allclose(host(Cm), ref, rtol=1e-4, atol=1e-3 * np.sqrt(P))
+
+
+# ------------------------------------------------------------------------------------------------ batch norm
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_bn_train_fwd_bwd(dtype):
+    n, h, w, c = 2, 8, 12, 64
+    z = RNG.standard_normal((n, h, w, c)).astype(np.float32) * 2 + 0.5
+    dy = RNG.standard_normal((n, h, w, c)).astype(np.float32)
+    gamma = RNG.uniform(0.5, 1.5, c).astype(np.float32)
+    beta = RNG.standard_normal(c).astype(np.float32) * 0.2
+    mm = RNG.standard_normal(c).astype(np.float32)
+    mv = RNG.uniform(0.5, 1.5, c).astype(np.float32)
+    zr, dyr = (bf16_round(z), bf16_round(dy)) if dtype == torch.bfloat16 else (z.astype(np.float64), dy.astype(np.float64))
+    M = n * h * w
+    mean, var = zr.mean((0, 1, 2)), zr.var((0, 1, 2))
+    rstd = 1 / np.sqrt(var + 1e-3)
+    xhat = (zr - mean) * rstd
+    y_ref = np.maximum(xhat * gamma + beta, 0)
+
+    cs = dev(zr.reshape(M, c).sum(0), torch.float64)
+    cq = dev((zr.reshape(M, c) ** 2).sum(0), torch.float64)
+    f = lambda: torch.empty(c, device="cuda")
+    scale, shift, smean, srstd = f(), f(), f(), f()
+    mmd, mvd = dev(mm), dev(mv)
+    ops.bn_finalize(cs, cq, M, dev(gamma), dev(beta), 1e-3, 0.99, mmd, mvd, scale, shift, smean, srstd)
+    np.testing.assert_allclose(host(smean), mean, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(host(srstd), rstd, rtol=1e-5)
+    np.testing.assert_allclose(host(mmd), mm * 0.99 + mean * 0.01, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(host(mvd), mv * 0.99 + var * 0.01, rtol=1e-5, atol=1e-6)
+
+    zd = dev(z, dtype)
+    y = torch.empty_like(zd)
+    pooled = torch.empty((n, h // 2, w // 2, c), device="cuda", dtype=dtype)
+    ops.bn_act(zd, scale, shift, y, relu=True, pooled=pooled)
+    np.testing.assert_allclose(host(y), y_ref, **tol(dtype))
+    np.testing.assert_allclose(host(pooled), R.maxpool2x2(host(y)), rtol=0, atol=0)
+
+    g = dyr * (y_ref > 0)
+    dgamma_ref, dbeta_ref = (g * xhat).sum((0, 1, 2)), g.sum((0, 1, 2))
+    dz_ref = gamma * rstd * (g - dbeta_ref / M - xhat * dgamma_ref / M)
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    dyd = dev(dy, dtype)
+    ops.bn_bwd_reduce(dyd, zd, scale, shift, smean, srstd, dg, db)
+    np.testing.assert_allclose(host(dg), dgamma_ref, rtol=1e-3, atol=2e-2)
+    np.testing.assert_allclose(host(db), dbeta_ref, rtol=1e-3, atol=2e-2)
+    dz = torch.empty_like(zd)
+    ops.bn_bwd_apply(dyd, zd, scale, shift, smean, srstd, dg, db, dz)
+    np.testing.assert_allclose(host(dz), dz_ref, **(dict(rtol=1e-3, atol=1e-4) if dtype == torch.float32 else tol(dtype)))
+
+
+def test_bn_fold_and_act_dropout():
+    c = 32
+    gamma, beta = RNG.uniform(0.5, 1.5, c).astype(np.float32), RNG.standard_normal(c).astype(np.float32)
+    mean, var = RNG.standard_normal(c).astype(np.float32), RNG.uniform(0.5, 1.5, c).astype(np.float32)
+    scale, shift = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    ops.bn_fold(dev(gamma), dev(beta), dev(mean), dev(var), 1e-3, scale, shift)
+    s_ref = gamma / np.sqrt(var + 1e-3)
+    np.testing.assert_allclose(host(scale), s_ref, rtol=1e-6)
+    np.testing.assert_allclose(host(shift), beta - mean * s_ref, rtol=1e-5, atol=1e-6)
+    z = RNG.standard_normal((2, 4, 6, c)).astype(np.float32)
+    buf = torch.zeros((2, 4, 6, 2 * c), device="cuda")
+    drop = ops.make_dropout(0.2, 9, ctot=2 * c, c0=c)
+    ops.bn_act(dev(z), scale, shift, buf[..., c:], relu=True, drop=drop)
+    ref = np.maximum(z * host(scale) + host(shift), 0) * R.dropout_multiplier((2, 4, 6, 2 * c), 0.2, 9)[..., c:]
+    np.testing.assert_allclose(host(buf)[..., c:], ref, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_fwd_bwd(dtype):
+    n, h, w, c = 2, 6, 10, 16
+    x = np.maximum(RNG.standard_normal((n, h, w, c)), 0).astype(np.float32)   # post-ReLU: many exact ties at 0
+    xr = bf16_round(x) if dtype == torch.bfloat16 else x.astype(np.float64)
+    buf = torch.zeros((n, h, w, 3 * c), device="cuda", dtype=dtype)
+    buf[..., c:2 * c] = dev(x, dtype)
+    y = torch.empty((n, h // 2, w // 2, c), device="cuda", dtype=dtype)
+    ops.maxpool2x2(buf[..., c:2 * c], y)
+    np.testing.assert_array_equal(host(y), R.maxpool2x2(xr))
+    dpool = RNG.standard_normal((n, h // 2, w // 2, c)).astype(np.float32)
+    dskip = RNG.standard_normal((n, h, w, c)).astype(np.float32)
+    dpr, dsr = (bf16_round(dpool), bf16_round(dskip)) if dtype == torch.bfloat16 else (dpool.astype(np.float64), dskip.astype(np.float64))
+    dy = torch.empty((n, h, w, c), device="cuda", dtype=dtype)
+    ops.maxpool2x2_bwd(buf[..., c:2 * c], None, None, dev(dpool, dtype), dev(dskip, dtype), dy)
+    np.testing.assert_allclose(host(dy), R.maxpool2x2_bwd(xr, dpr) + dsr, **tol(dtype))
+
+
+def test_convt_bwd_gather():
+    n, h, w, co = 2, 3, 4, 16
+    du = RNG.standard_normal((n, 2 * h, 2 * w, co)).astype(np.float32)
+    buf = torch.zeros((n, 2 * h, 2 * w, 2 * co), device="cuda")
+    buf[..., :co] = dev(du)
+    g = torch.empty((n * h * w, 4 * co), device="cuda")
+    db = torch.zeros(co, device="cuda")
+    ops.convt_bwd_gather(buf[..., :co], g, db)
+    ref = du.reshape(n, h, 2, w, 2, co).transpose(0, 1, 3, 2, 4, 5).reshape(n * h * w, 4 * co)
+    np.testing.assert_array_equal(host(g), ref)
+    np.testing.assert_allclose(host(db), du.sum((0, 1, 2)), rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ head + loss
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C", [1, 8])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_head_and_loss(dtype, C, kind):
+    n, h, w, k = 3, 10, 12, 64
+    x = RNG.standard_normal((n, h, w, k)).astype(np.float32)
+    wk = (RNG.standard_normal((k, C)) / 4).astype(np.float32)
+    b = RNG.standard_normal(C).astype(np.float32) * 0.1
+    _, t = R.synthetic_batch(n, h, w, 3, C, seed=5)
+    xr = bf16_round(x) if dtype == torch.bfloat16 else x.astype(np.float64)
+    logits = xr.reshape(-1, k) @ wk.astype(np.float64) + b
+    p_ref = (R.sigmoid(logits) if C == 1 else R.softmax(logits)).reshape(n, h, w, C)
+    xd = dev(x, dtype)
+    probs = torch.empty((n, h, w, C), device="cuda")
+    sums = torch.zeros((n, C, 3), device="cuda", dtype=torch.float64)
+    td = dev(t)
+    ops.head_fwd(xd, dev(wk), dev(b), probs, td, sums)
+    np.testing.assert_allclose(host(probs), p_ref, rtol=1e-5, atol=1e-6)
+    pg = host(probs)
+    np.testing.assert_allclose(sums.cpu().numpy()[..., 0], (t * pg).sum((1, 2)), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(sums.cpu().numpy()[..., 1], t.sum((1, 2)), rtol=1e-6)
+    np.testing.assert_allclose(sums.cpu().numpy()[..., 2], pg.sum((1, 2)), rtol=1e-5)
+    out3 = torch.empty(3, device="cuda")
+    coef = torch.empty((n, C, 2), device="cuda")
+    ops.seg_loss_finalize(sums, n * C, R.EPSILON, kind, 1.0, out3, coef)
+    o = host(out3)
+    d_ref, i_ref = R.dice_coef(t, pg, dtype=np.float64), R.iou_coef(t, pg, dtype=np.float64)
+    np.testing.assert_allclose(o, [1 - (d_ref if kind == 0 else i_ref), d_ref, i_ref], rtol=1e-5, atol=1e-6)
+    # backward through the activation and the 1x1 convolution vs analytic formula
+    I, T, P = (t * p_ref).sum((1, 2)), t.sum((1, 2)), p_ref.sum((1, 2))
+    if kind == 0:
+        D = T + P + R.EPSILON
+        dp = -(1.0 / (n * C)) * (2 * t * D[:, None, None] - (2 * I + R.EPSILON)[:, None, None]) / (D ** 2)[:, None, None]
+    else:
+        U = T + P - I + R.EPSILON
+        dp = -(1.0 / (n * C)) * (t * U[:, None, None] - (I + R.EPSILON)[:, None, None] * (1 - t)) / (U ** 2)[:, None, None]
+    dl = dp * p_ref * (1 - p_ref) if C == 1 else p_ref * (dp - (dp * p_ref).sum(-1, keepdims=True))
+    dl2 = dl.reshape(-1, C)
+    dx = torch.empty_like(xd)
+    dw, db = torch.zeros((k, C), device="cuda"), torch.zeros(C, device="cuda")
+    ops.head_bwd(xd, dev(wk), probs, td, coef, dx, dw, db)
+    np.testing.assert_allclose(host(dw), xr.reshape(-1, k).T @ dl2, rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(host(db), dl2.sum(0), rtol=2e-3, atol=2e-6)
+    ref_dx = (dl2 @ wk.astype(np.float64).T).reshape(n, h, w, k)
+    np.testing.assert_allclose(host(dx), ref_dx, rtol=1e-2 if dtype == torch.bfloat16 else 1e-3, atol=1e-7)
+
+
+def test_seg_sums_metrics():
+    t = (RNG.random((4, 9, 7, 3)) > 0.5).astype(np.float32)
+    p = RNG.random((4, 9, 7, 3)).astype(np.float32)
+    sums = torch.zeros((4, 3, 3), device="cuda", dtype=torch.float64)
+    ops.seg_sums(dev(t), dev(p), sums)
+    s = sums.cpu().numpy()
+    np.testing.assert_allclose(s[..., 0], (t * p).sum((1, 2)), rtol=1e-5)
+    np.testing.assert_allclose(s[..., 1], t.sum((1, 2)), rtol=1e-6)
+    np.testing.assert_allclose(s[..., 2], p.sum((1, 2)), rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ MeanIoU, AdamW, staging
+def test_confusion_matrix():
+    n = 100003
+    t = RNG.integers(0, 2, n).astype(np.float32)
+    p = RNG.random(n).astype(np.float32)
+    p[::7] = 1.0
+    counts = torch.zeros(4, device="cuda", dtype=torch.int64)
+    ops.confusion_matrix_update(dev(t), dev(p), 2, counts)
+    m = R.MeanIoU(2); m.update_state(t, p)
+    np.testing.assert_array_equal(counts.cpu().numpy().reshape(2, 2), m.cm)
+    counts.zero_()
+    ops.confusion_matrix_update(dev(t), dev(p), 2, counts, threshold=0.5)
+    m = R.MeanIoU(2); m.update_state(t, (p > 0.5).astype(np.uint8))
+    np.testing.assert_array_equal(counts.cpu().numpy().reshape(2, 2), m.cm)
+    t8 = RNG.integers(0, 8, n).astype(np.float32); p8 = RNG.integers(0, 8, n).astype(np.float32)
+    c8 = torch.zeros(64, device="cuda", dtype=torch.int64)
+    ops.confusion_matrix_update(dev(t8), dev(p8), 8, c8)
+    m = R.MeanIoU(8); m.update_state(t8, p8)
+    np.testing.assert_array_equal(c8.cpu().numpy().reshape(8, 8), m.cm)
+
+
+def test_adamw_keras_form():
+    n = 10007
+    w = RNG.standard_normal(n).astype(np.float32)
+    m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+    wd_, md, vd = dev(w), dev(m), dev(v)
+    w64, m64, v64 = w.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for t in range(1, 4):
+        g = RNG.standard_normal(n).astype(np.float32)
+        hyper = dev(np.array([2e-3, 1e-4, 0.9, 0.999, 1e-7, t, 1.0, 0.0], np.float32))
+        ops.adamw_step(wd_, dev(g), md, vd, hyper)
+        w64, m64, v64 = R.adamw_step(w64, g.astype(np.float64), m64, v64, t, *[float(np.float32(h)) for h in (2e-3, 1e-4, 0.9, 0.999, 1e-7)])
+    np.testing.assert_allclose(host(wd_), w64, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(host(md), m64, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(host(vd), v64, rtol=1e-5, atol=1e-9)
+
+
+def test_cast_transpose():
+    a = RNG.standard_normal((70, 45)).astype(np.float32)
+    d = torch.empty((70, 45), device="cuda", dtype=torch.bfloat16)
+    dt_ = torch.empty((45, 70), device="cuda", dtype=torch.bfloat16)
+    ops.cast_transpose_bf16(dev(a), d, dt_)
+    np.testing.assert_array_equal(host(d), bf16_round(a))
+    np.testing.assert_array_equal(host(dt_), bf16_round(a).T)
+    f = torch.empty((70, 45), device="cuda")
+    ops.cast(d, f)
+    np.testing.assert_array_equal(host(f), bf16_round(a))
+
+
+def test_rejects_bad_arguments():
+    from unet_b200._lib import UnetError
+    x = torch.zeros((1, 4, 4, 12), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(UnetError):
+        ops.bn_act(x, torch.ones(12, device="cuda"), torch.zeros(12, device="cuda"), torch.empty_like(x))   # C % 8 != 0
+    A = torch.zeros((16, 12), device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(UnetError):
+        ops.gemm(A, torch.zeros((16, 12), device="cuda", dtype=torch.bfloat16), torch.zeros((16, 16), device="cuda"),
+                 b_trans=True, tensor_core=True)     # lda % 8 != 0

@@ -22,7 +22,8 @@ class UnetError(RuntimeError):
 
 
 class Dropout(C.Structure):
-    _fields_ = [("rate", C.c_float), ("seed", C.c_uint32), ("ctot", C.c_int64), ("c0", C.c_int64)]
+    _fields_ = [("rate", C.c_float), ("seed", C.c_uint32), ("ctot", C.c_int64), ("c0", C.c_int64),
+                ("seed_dev", C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -69,6 +70,7 @@ _SIGNATURES = {
     "unet_confusion_matrix_update": [_vp, _vp, _i64, _i, _vp, _vp],
     "unet_confusion_matrix_update_thr": [_vp, _vp, _f, _i64, _vp, _vp],
     "unet_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "unet_step_advance": [_vp, _vp, _vp],
     "unet_cast_transpose_bf16": [_vp, _vp, _vp, _i, _i, _vp],
     "unet_cast": [_vp, _i, _vp, _i, _i64, _vp],
     "unet_host_dropout_hash": [C.c_uint64, C.c_uint32],

@@ -9,13 +9,14 @@
 
 namespace unet {
 
-struct DropArgs { float keep, inv_keep; uint32_t seed; int on; int64_t ctot, c0; };
+struct DropArgs { float keep, inv_keep; uint32_t seed; int on; int64_t ctot, c0; const uint32_t* seed_dev; };
+__device__ __forceinline__ uint32_t drop_seed(const DropArgs& d) { return d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0u); }
 
 static DropArgs make_drop(const unet_dropout* d) {
-  DropArgs a{1.f, 1.f, 0u, 0, 0, 0};
+  DropArgs a{1.f, 1.f, 0u, 0, 0, 0, nullptr};
   if (d && d->rate > 0.f) {
     a.on = 1; a.keep = 1.f - d->rate; a.inv_keep = 1.f / (1.f - d->rate);
-    a.seed = d->seed; a.ctot = d->ctot; a.c0 = d->c0;
+    a.seed = d->seed; a.ctot = d->ctot; a.c0 = d->c0; a.seed_dev = d->seed_dev;
   }
   return a;
 }
@@ -81,7 +82,7 @@ dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restr
       if (dp.on) {
         const uint64_t base = (uint64_t)((n * H + (r - 1)) * (int64_t)W + wq) * dp.ctot + dp.c0 + c0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+        for (int j = 0; j < 8; ++j) o[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
       }
       store8(ycol + (r - 1) * yrow, o);
     }
@@ -119,7 +120,7 @@ __global__ void dwconv3x3_scalar_kernel(const T* __restrict__ x, int64_t ldx, co
         acc = fmaf(v, w9c[(int64_t)ki * C + c], acc);
       }
     }
-    if (dp.on) acc *= dropout_mult((uint64_t)p * dp.ctot + dp.c0 + c, dp.seed, dp.keep, dp.inv_keep);
+    if (dp.on) acc *= dropout_mult((uint64_t)p * dp.ctot + dp.c0 + c, drop_seed(dp), dp.keep, dp.inv_keep);
     y[p * ldy + c] = from_f32<T>(acc);
   }
 }

@@ -7,12 +7,13 @@
 
 namespace unet {
 
-struct DropArgs { float keep, inv_keep; uint32_t seed; int on; int64_t ctot, c0; };
+struct DropArgs { float keep, inv_keep; uint32_t seed; int on; int64_t ctot, c0; const uint32_t* seed_dev; };
+__device__ __forceinline__ uint32_t drop_seed(const DropArgs& d) { return d.seed + (d.seed_dev ? __ldg(d.seed_dev) : 0u); }
 static DropArgs make_drop(const unet_dropout* d) {
-  DropArgs a{1.f, 1.f, 0u, 0, 0, 0};
+  DropArgs a{1.f, 1.f, 0u, 0, 0, 0, nullptr};
   if (d && d->rate > 0.f) {
     a.on = 1; a.keep = 1.f - d->rate; a.inv_keep = 1.f / (1.f - d->rate);
-    a.seed = d->seed; a.ctot = d->ctot; a.c0 = d->c0;
+    a.seed = d->seed; a.ctot = d->ctot; a.c0 = d->c0; a.seed_dev = d->seed_dev;
   }
   return a;
 }
@@ -81,7 +82,7 @@ bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const fl
       if (dp.on) {
         const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+        for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
       }
       store8(y + pix * ldy + c0, v);
     }
@@ -100,7 +101,7 @@ bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const fl
     if (dp.on) {
       const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+      for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
     }
     store8(y + pix * ldy + c0, v);
   }
@@ -134,7 +135,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict
     if (dp.on) {
       const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+      for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -175,7 +176,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict_
   if (dp.on) {
     const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, dp.seed, dp.keep, dp.inv_keep);
+    for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
   }
   if (norm) {
     float sc[8], sh[8], mu[8], rs[8], dg[8], db[8];
@@ -335,6 +336,11 @@ adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restri
       w[i] = wj; m[i] = mj; v[i] = vj;
     }
   }
+}
+
+__global__ void step_advance_kernel(float* hyper, uint32_t* counter) {
+  if (hyper) hyper[5] += 1.f;
+  if (counter) *counter += 1u;
 }
 
 // ------------------------------------------------------------------------------------------------ casts
@@ -600,6 +606,12 @@ extern "C" int unet_adamw_step(float* w, const float* g, float* m, float* v, int
   UNET_REQUIRE(aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v), UNET_EALIGN, "adamw_step: buffers must be 16B aligned");
   adamw_kernel<<<grid_for(ceil_div(n, 4)), 256, 0, ST>>>(w, g, m, v, n, hyper);
   UNET_LAUNCH_CHECK("adamw_step");
+  return UNET_OK;
+}
+
+extern "C" int unet_step_advance(float* hyper, uint32_t* counter, void* stream) {
+  step_advance_kernel<<<1, 1, 0, ST>>>(hyper, counter);
+  UNET_LAUNCH_CHECK("step_advance");
   return UNET_OK;
 }
 

@@ -19,7 +19,7 @@ struct SimtParams {
   const float* scale; const float* shift;
   double* colsum; double* colsq;
   int convt_H, convt_W; int64_t convt_cout;
-  float keep, inv_keep; uint32_t seed; int drop_on; int64_t ctot, c0;
+  float keep, inv_keep; uint32_t seed; int drop_on; int64_t ctot, c0; const uint32_t* seed_dev;
   int64_t k_per_split;
 };
 
@@ -111,7 +111,7 @@ gemm_simt_kernel(const SimtParams p) {
         const int64_t ab = n / p.convt_cout, co = n % p.convt_cout;
         const int64_t pix = convt_base + (ab >> 1) * (2 * p.convt_W) + (ab & 1);
         v += p.shift ? p.shift[co] : 0.f;
-        if (p.drop_on) v *= dropout_mult((uint64_t)pix * p.ctot + p.c0 + co, p.seed, p.keep, p.inv_keep);
+        if (p.drop_on) v *= dropout_mult((uint64_t)pix * p.ctot + p.c0 + co, p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), p.keep, p.inv_keep);
         C[pix * p.ldc + co] = from_f32<TOut>(v);
       } else if (p.accumulate) {
         atomicAdd(reinterpret_cast<float*>(p.C) + m * p.ldc + n, v);
@@ -170,7 +170,7 @@ extern "C" int unet_gemm_simt(const unet_gemm_args* a, void* stream) {
   p.drop_on = 0; p.keep = 1.f; p.inv_keep = 1.f;
   if (a->epilogue == UNET_EPI_CONVT && a->drop.rate > 0.f) {
     p.drop_on = 1; p.keep = 1.f - a->drop.rate; p.inv_keep = 1.f / (1.f - a->drop.rate);
-    p.seed = a->drop.seed; p.ctot = a->drop.ctot; p.c0 = a->drop.c0;
+    p.seed = a->drop.seed; p.ctot = a->drop.ctot; p.c0 = a->drop.c0; p.seed_dev = a->drop.seed_dev;
   }
   const int64_t tiles = ceil_div(a->M, BM) * ceil_div(a->N, BN);
   int64_t splits = 1;

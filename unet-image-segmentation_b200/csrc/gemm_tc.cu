@@ -132,7 +132,7 @@ struct TcParams {
   const float* scale; const float* shift;
   double* colsum; double* colsq;
   int convt_H, convt_W; int64_t convt_cout;
-  float keep, inv_keep; uint32_t seed; int drop_on; int64_t ctot, c0;
+  float keep, inv_keep; uint32_t seed; int drop_on; int64_t ctot, c0; const uint32_t* seed_dev;
   int64_t kb_per_split;     // wgrad: k-blocks per CTA along P
   int num_m_tiles, num_n_tiles;
 };
@@ -212,7 +212,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
       if (p.drop_on) {
         const uint64_t base = (uint64_t)pix * p.ctot + p.c0 + cv_co;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] *= dropout_mult(base + j, p.seed, p.keep, p.inv_keep);
+        for (int j = 0; j < 4; ++j) v[j] *= dropout_mult(base + j, p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), p.keep, p.inv_keep);
       }
       off = pix * p.ldc + cv_co;
     } else {
@@ -504,10 +504,10 @@ static void fill_params(TcParams& p, const unet_gemm_args* a) {
   p.epilogue = a->epilogue; p.out_bf16 = a->out_dtype == UNET_BF16; p.accumulate = a->accumulate;
   p.scale = a->scale; p.shift = a->shift; p.colsum = a->colsum; p.colsq = a->colsq;
   p.convt_H = a->convt_H; p.convt_W = a->convt_W; p.convt_cout = a->N / 4;
-  p.drop_on = 0; p.keep = 1.f; p.inv_keep = 1.f; p.seed = 0; p.ctot = 0; p.c0 = 0;
+  p.drop_on = 0; p.keep = 1.f; p.inv_keep = 1.f; p.seed = 0; p.ctot = 0; p.c0 = 0; p.seed_dev = nullptr;
   if (a->epilogue == UNET_EPI_CONVT && a->drop.rate > 0.f) {
     p.drop_on = 1; p.keep = 1.f - a->drop.rate; p.inv_keep = 1.f / (1.f - a->drop.rate);
-    p.seed = a->drop.seed; p.ctot = a->drop.ctot; p.c0 = a->drop.c0;
+    p.seed = a->drop.seed; p.ctot = a->drop.ctot; p.c0 = a->drop.c0; p.seed_dev = a->drop.seed_dev;
   }
 }
 

@@ -1,0 +1,487 @@
+"""The B200 execution engine for the reference U-Net (model/u_net.py:28-116): parameters, buffer plan and the
+forward / backward / optimizer schedules, expressed as sequences of C-ABI kernel launches (ops.py).
+
+Replaces, for this one model, what Keras + TensorFlow do behind `model.predict` / `model.fit`
+(scripts/inference.py:116, scripts/train.py:308): layer graph execution, autodiff, AdamW (train.py:226).
+
+Layout in HBM
+  * activations NHWC, bf16 (tcgen05 path) or fp32 (parity path); probabilities, parameters, statistics fp32.
+  * Concatenate (u_net.py:96) is zero-copy: Conv2DTranspose writes channels [0,f) and the encoder skip writes
+    channels [f,2f) of one [N,h,w,2f] buffer.
+  * trainable parameters live in ONE flat fp32 buffer in Keras creation order (grad / Adam m / Adam v mirror it), so
+    AdamW is one launch and the data-parallel gradient exchange is a few contiguous all-reduces.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+from .spec import BN_EPS, BN_MOMENTUM, FILTERS, UNetSpec
+
+SMOOTH = 1e-7   # K.epsilon(), utils/metrics.py:4
+
+
+class _Plan:
+    """Named device buffers for one (batch, mode) configuration; allocated once, reused every step (graph-safe)."""
+
+    def __init__(self, device, act_dtype):
+        self.device, self.act_dtype = device, act_dtype
+        self.t: Dict[str, torch.Tensor] = {}
+
+    def buf(self, name: str, shape, dtype=None, zero=False) -> torch.Tensor:
+        t = self.t.get(name)
+        if t is None:
+            dtype = dtype or self.act_dtype
+            t = (torch.zeros if zero else torch.empty)(tuple(shape), device=self.device, dtype=dtype)
+            self.t[name] = t
+        return t
+
+    def bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+
+class UNetEngine:
+    def __init__(self, input_size, num_classes: int = 1, dropout_rate: float = 0.2, use_batch_norm: bool = True,
+                 dtype: str = "bf16", device: Optional[torch.device] = None, seed: int = 2301):
+        self.spec = UNetSpec(tuple(input_size), num_classes, dropout_rate, use_batch_norm)
+        H, W, _ = self.spec.input_size
+        if H % 16 or W % 16:
+            raise ValueError(f"input height and width must be multiples of 16 (4 MaxPooling2D stages), got {H}x{W}")
+        if num_classes < 1 or num_classes > 8:
+            raise ValueError("num_classes must be in 1..8")
+        if dtype not in ("bf16", "fp32"):
+            raise ValueError("dtype must be 'bf16' or 'fp32'")
+        if not torch.cuda.is_available():
+            raise RuntimeError("unet_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        ops.device_check(self.device.index or 0)
+        self.dtype_name = dtype
+        self.act_dtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        self.num_classes, self.dropout_rate, self.use_bn = num_classes, float(dropout_rate), bool(use_batch_norm)
+        sp = self.spec
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.w = torch.zeros(sp.n_trainable_flat, device=dev)
+            self.g = torch.zeros_like(self.w)
+            self.m = torch.zeros_like(self.w)
+            self.v = torch.zeros_like(self.w)
+            self.state = torch.zeros(max(sp.n_state_flat, 8), device=dev)
+            # per-BN vectors: scale, shift (batch or folded), saved mean, saved rstd; fp64 column sums for statistics
+            self._bn_off: Dict[str, Tuple[int, int]] = {}
+            tot = 0
+            for b in sp.blocks:
+                self._bn_off[b.prefix] = (tot, b.cout)
+                tot += b.cout
+            self._bn_total = tot
+            self.bn_vec = torch.zeros((4, tot), device=dev)
+            self.fold = torch.zeros((2, tot), device=dev)
+            self.colstats = torch.zeros((2, tot), device=dev, dtype=torch.float64)
+            self.ones = torch.ones(max(FILTERS) * 2, device=dev)
+            self.zeros = torch.zeros(max(FILTERS) * 2, device=dev)
+            # lr, wd, beta1, beta2, eps, t, grad_scale, unused
+            self.hyper = torch.tensor([2e-3, 1e-4, 0.9, 0.999, 1e-7, 1.0, 1.0, 0.0], device=dev)
+            self.step_word = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._stage: Dict[str, torch.Tensor] = {}
+        self._stage_dirty = True
+        self._fold_dirty = True
+        self._plans: Dict[Tuple[int, bool], _Plan] = {}
+        self._drop_seed = {name: (seed * 7919 + i * 104729) & 0x7FFFFFFF
+                           for i, name in enumerate(["bneck_dropout", "dec4_dropout", "dec3_dropout", "dec2_dropout"])}
+        self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
+        self.grad_hook = None                   # callable(region) — dist.GradSync.ready; regions: decoder, bottleneck, encoder
+        self.init_weights(seed)
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def wview(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        p = self.spec.params[name]
+        base = (self.w if buf is None else buf) if p.trainable else self.state
+        return base[p.offset:p.offset + p.size]
+
+    def _mat(self, name: str, buf: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """2-D GEMM view of a kernel in its Keras memory order."""
+        p = self.spec.params[name]
+        v = self.wview(name, buf)
+        leaf = name.split("/")[1]
+        if leaf == "depthwise_kernel":
+            return v.view(9, p.shape[2])
+        if leaf == "pointwise_kernel":
+            return v.view(p.shape[2], p.shape[3])                 # [Cin, Cout]
+        if leaf == "kernel" and len(p.shape) == 4 and p.shape[0] == 2:
+            return v.view(4 * p.shape[2], p.shape[3])             # convT: [(a,b,co), Cin]
+        if leaf == "kernel":
+            return v.view(p.shape[2], p.shape[3])                 # head: [64, classes]
+        return v
+
+    def init_weights(self, seed: int = 2301) -> None:
+        """Keras default initialisers (Glorot-uniform kernels, zero biases, gamma 1, beta 0, moving 0/1)."""
+        rng = np.random.default_rng(seed)
+        out = {}
+        for name, p in self.spec.params.items():
+            leaf = name.split("/")[1]
+            if leaf.endswith("kernel"):
+                rf = int(np.prod(p.shape[:-2]))
+                lim = np.sqrt(6.0 / (rf * p.shape[-2] + rf * p.shape[-1]))
+                out[name] = rng.uniform(-lim, lim, size=p.shape).astype(np.float32)
+            elif leaf in ("gamma", "moving_variance"):
+                out[name] = np.ones(p.shape, np.float32)
+            else:
+                out[name] = np.zeros(p.shape, np.float32)
+        self.set_weights(out)
+
+    def set_weights(self, weights: Dict[str, np.ndarray]) -> None:
+        """name -> array in Keras shape.  Unknown names raise; missing names keep their value."""
+        for name, arr in weights.items():
+            if name not in self.spec.params:
+                raise KeyError(f"unknown weight {name!r}")
+            p = self.spec.params[name]
+            a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32))
+            if tuple(a.shape) != tuple(p.shape):
+                raise ValueError(f"{name}: expected shape {p.shape}, got {a.shape}")
+            self.wview(name).copy_(torch.from_numpy(a.reshape(-1)))
+        self._stage_dirty = True
+        self._fold_dirty = True
+
+    def get_weights(self) -> Dict[str, np.ndarray]:
+        return {name: self.wview(name).detach().cpu().numpy().reshape(p.shape).copy()
+                for name, p in self.spec.params.items()}
+
+    def reset_optimizer(self) -> None:
+        self.m.zero_(); self.v.zero_()
+        self.hyper[5] = 1.0
+
+    def set_hyper(self, lr=None, weight_decay=None, beta1=None, beta2=None, eps=None, grad_scale=None) -> None:
+        for i, val in enumerate((lr, weight_decay, beta1, beta2, eps)):
+            if val is not None:
+                self.hyper[i] = float(val)
+        if grad_scale is not None:
+            self.hyper[6] = float(grad_scale)
+
+    # bf16 operand staging for the tensor-core path
+    def _restage(self) -> None:
+        if not self._stage_dirty:
+            return
+        if self.act_dtype == torch.bfloat16:
+            for name, p in self.spec.params.items():
+                leaf = name.split("/")[1]
+                if leaf == "pointwise_kernel" or (leaf == "kernel" and p.shape[0] == 2):
+                    src = self._mat(name)
+                    r, c = src.shape
+                    a = self._stage.get(name)
+                    if a is None:
+                        a = self._stage[name] = torch.empty((r, c), device=self.device, dtype=torch.bfloat16)
+                        self._stage[name + "^T"] = torch.empty((c, r), device=self.device, dtype=torch.bfloat16)
+                    ops.cast_transpose_bf16(src, a, self._stage[name + "^T"])
+        self._stage_dirty = False
+
+    def _refold(self) -> None:
+        if not self._fold_dirty or not self.use_bn:
+            self._fold_dirty = False
+            return
+        for b in self.spec.blocks:
+            o, c = self._bn_off[b.prefix]
+            ops.bn_fold(self.wview(f"{b.prefix}_bn/gamma"), self.wview(f"{b.prefix}_bn/beta"),
+                        self.wview(f"{b.prefix}_bn/moving_mean"), self.wview(f"{b.prefix}_bn/moving_variance"),
+                        BN_EPS, self.fold[0, o:o + c], self.fold[1, o:o + c])
+        self._fold_dirty = False
+
+    # ------------------------------------------------------------------------------------------------ GEMM dispatch
+    def _pw_fwd(self, prefix, d, out, **kw):
+        name = f"{prefix}_sepconv/pointwise_kernel"
+        cin = d.shape[-1]
+        if self.act_dtype == torch.bfloat16:
+            if cin % 8 == 0:
+                ops.gemm(d, self._stage[name + "^T"], out, b_trans=True, **kw)       # tcgen05: B as [Cout, Cin]
+            else:
+                ops.gemm(d, self._stage[name], out, **kw)                            # K = 3: CUDA cores
+        else:
+            ops.gemm(d, self._mat(name), out, **kw)
+
+    def _pw_dgrad(self, prefix, dz, dd):
+        name = f"{prefix}_sepconv/pointwise_kernel"
+        B = self._stage[name] if self.act_dtype == torch.bfloat16 else self._mat(name)    # [Cin, Cout] = [N, K]
+        ops.gemm(dz, B, dd, b_trans=True)
+
+    def _convt_fwd(self, s, x, dst, drop):
+        name = f"dec{s}_upsample/kernel"
+        B = self._stage[name] if self.act_dtype == torch.bfloat16 else self._mat(name)    # [(a,b,co), Cin] = [N, K]
+        ops.gemm(x, B, dst, b_trans=True, epilogue=ops.EPI_CONVT, shift=self.wview(f"dec{s}_upsample/bias"),
+                 convt_hw=(x.shape[1], x.shape[2]), drop=drop)
+
+    def _convt_dgrad(self, s, g2d, dx):
+        name = f"dec{s}_upsample/kernel"
+        if self.act_dtype == torch.bfloat16:
+            ops.gemm(g2d, self._stage[name + "^T"], dx, b_trans=True)                # B as [Cin, 4Cout] = [N, K]
+        else:
+            ops.gemm(g2d, self._mat(name), dx)                                       # B as [4Cout, Cin] = [K, N]
+
+    # ------------------------------------------------------------------------------------------------ plans
+    def _plan(self, batch: int, training: bool) -> _Plan:
+        key = (batch, training)
+        p = self._plans.get(key)
+        if p is None:
+            p = self._plans[key] = _Plan(self.device, self.act_dtype)
+        return p
+
+    def _dims(self, level: int) -> Tuple[int, int]:
+        H, W, _ = self.spec.input_size
+        return H >> level, W >> level
+
+    def _drop(self, name: str, ctot: int, c0: int = 0):
+        if self.dropout_rate <= 0.0:
+            return None
+        return ops.make_dropout(self.dropout_rate, self._drop_seed[name], ctot, c0,
+                                self.step_word if self.dropout_masks_from_step else None)
+
+    # ------------------------------------------------------------------------------------------------ inference
+    def _block_infer(self, pl: _Plan, prefix: str, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        B, h, w, cin = x.shape
+        level = (self.spec.input_size[0] // h).bit_length() - 1
+        max_cin = 1024 if level == 4 else 2 * FILTERS[level]
+        d = pl.buf(f"d{level}", (B * h * w * max_cin,))[: B * h * w * cin].view(B, h, w, cin)
+        ops.dwconv3x3(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
+        if self.use_bn:
+            o, c = self._bn_off[prefix]
+            self._pw_fwd(prefix, d, y, epilogue=ops.EPI_AFFINE_RELU, scale=self.fold[0, o:o + c], shift=self.fold[1, o:o + c])
+        else:
+            self._pw_fwd(prefix, d, y, epilogue=ops.EPI_AFFINE_RELU, shift=self.wview(f"{prefix}_sepconv/bias"))
+        return y
+
+    def forward_inference(self, x: torch.Tensor) -> torch.Tensor:
+        """x: device fp32 [B,H,W,Cin] -> probabilities fp32 [B,H,W,classes] (plan-owned buffer, valid until the next call)."""
+        B = x.shape[0]
+        pl = self._plan(B, False)
+        self._restage(); self._refold()
+        H, W, Cin = self.spec.input_size
+        if tuple(x.shape[1:]) != (H, W, Cin):
+            raise ValueError(f"expected input (B,{H},{W},{Cin}), got {tuple(x.shape)}")
+        if self.act_dtype == torch.bfloat16:
+            cur = pl.buf("x_act", (B, H, W, Cin))
+            ops.cast(x, cur)
+        else:
+            cur = x
+        cats = {}
+        for s in range(1, 5):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            cat = cats[s] = pl.buf(f"cat{s}", (B, h, w, 2 * f))
+            cur = self._block_infer(pl, f"enc{s}_block1", cur, pl.buf(f"ya{s}", (B, h, w, f)))
+            skip = self._block_infer(pl, f"enc{s}_block2", cur, cat[..., f:])
+            cur = pl.buf(f"pool{s}", (B, h // 2, w // 2, f))
+            ops.maxpool2x2(skip, cur)
+        h, w = self._dims(4)
+        cur = self._block_infer(pl, "bneck_block1", cur, pl.buf("ya5", (B, h, w, 1024)))
+        cur = self._block_infer(pl, "bneck_block2", cur, pl.buf("yb5", (B, h, w, 1024)))
+        for s in (4, 3, 2, 1):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            self._convt_fwd(s, cur, cats[s][..., :f], None)
+            cur = self._block_infer(pl, f"dec{s}_block1", cats[s], pl.buf(f"ya{s}", (B, h, w, f)))
+            cur = self._block_infer(pl, f"dec{s}_block2", cur, pl.buf(f"yb{s}", (B, h, w, f)))
+        probs = pl.buf("probs", (B, H, W, self.num_classes), torch.float32)
+        ops.head_fwd(cur, self._mat("output_mask/kernel"), self.wview("output_mask/bias"), probs)
+        return probs
+
+    # ------------------------------------------------------------------------------------------------ training
+    def _bn(self, prefix):
+        o, c = self._bn_off[prefix]
+        return (self.bn_vec[0, o:o + c], self.bn_vec[1, o:o + c], self.bn_vec[2, o:o + c], self.bn_vec[3, o:o + c])
+
+    def _block_train_fwd(self, pl, prefix, x, y, pooled=None, drop=None):
+        B, h, w, cin = x.shape
+        cout = y.shape[-1]
+        d = pl.buf(prefix + "/d", (B, h, w, cin))
+        z = pl.buf(prefix + "/z", (B, h, w, cout))
+        ops.dwconv3x3(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
+        o, c = self._bn_off[prefix]
+        if self.use_bn:
+            scale, shift, smean, srstd = self._bn(prefix)
+            self._pw_fwd(prefix, d, z, epilogue=ops.EPI_STATS, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
+            ops.bn_finalize(self.colstats[0, o:o + c], self.colstats[1, o:o + c], B * h * w,
+                            self.wview(f"{prefix}_bn/gamma"), self.wview(f"{prefix}_bn/beta"), BN_EPS, BN_MOMENTUM,
+                            self.wview(f"{prefix}_bn/moving_mean"), self.wview(f"{prefix}_bn/moving_variance"),
+                            scale, shift, smean, srstd)
+        else:
+            self._pw_fwd(prefix, d, z, epilogue=ops.EPI_AFFINE, shift=self.wview(f"{prefix}_sepconv/bias"))
+            scale, shift = self.ones[:c], self.zeros[:c]
+        ops.bn_act(z, scale, shift, y, relu=True, pooled=pooled, drop=drop)
+        return y
+
+    def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None):
+        """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out."""
+        B, h, w, cin = x.shape
+        d, z = pl.t[prefix + "/d"], pl.t[prefix + "/z"]
+        cout = z.shape[-1]
+        M = B * h * w
+        dz = scr[0][: M * cout].view(B, h, w, cout)
+        dd = scr[1][: M * cin].view(B, h, w, cin)
+        if self.use_bn:
+            scale, shift, smean, srstd = self._bn(prefix)
+            dgamma, dbeta = self.wview(f"{prefix}_bn/gamma", self.g), self.wview(f"{prefix}_bn/beta", self.g)
+        else:
+            o, c = self._bn_off[prefix]
+            scale, shift, smean, srstd = self.ones[:c], self.zeros[:c], None, None
+            dgamma, dbeta = None, self.wview(f"{prefix}_sepconv/bias", self.g)
+        ops.bn_bwd_reduce(dy, z, scale, shift, smean, srstd, dgamma, dbeta, relu=True, drop=ydrop)
+        ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True, drop=ydrop)
+        ops.gemm(d, dz, self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g), a_trans=True, accumulate=True)
+        self._pw_dgrad(prefix, dz, dd)
+        ops.dwconv3x3_bwd_weight(x, dd, self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g))
+        if dx_out is not None:
+            ops.dwconv3x3(dd, self._mat(f"{prefix}_sepconv/depthwise_kernel"), dx_out, flip=True, drop=dx_drop)
+        return dx_out
+
+    def train_forward_backward(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:
+        """One training-mode forward + backward on device tensors (x fp32 [B,H,W,Cin], y_true fp32 [B,H,W,classes]).
+        Leaves d loss / d theta in self.g and updates the BN moving statistics.  Returns out3 = (loss, dice_coef,
+        iou_coef) as a device tensor (no host synchronisation)."""
+        kind = {"dice": 0, "iou": 1}[loss]
+        B = x.shape[0]
+        H, W, Cin = self.spec.input_size
+        NC = self.num_classes
+        if tuple(x.shape) != (B, H, W, Cin) or tuple(y_true.shape) != (B, H, W, NC):
+            raise ValueError(f"expected x (B,{H},{W},{Cin}) and y_true (B,{H},{W},{NC})")
+        pl = self._plan(B, True)
+        self._restage()
+        self.g.zero_()
+        self.colstats.zero_()
+        if self.act_dtype == torch.bfloat16:
+            x0 = pl.buf("x_act", (B, H, W, Cin))
+            ops.cast(x, x0)
+        else:
+            x0 = x
+        # ---------------- forward
+        cur = x0
+        cats, xin = {}, {}
+        for s in range(1, 5):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            cat = cats[s] = pl.buf(f"cat{s}", (B, h, w, 2 * f))
+            xin[f"enc{s}_block1"] = cur
+            y1 = self._block_train_fwd(pl, f"enc{s}_block1", cur, pl.buf(f"enc{s}_block1/y", (B, h, w, f)))
+            xin[f"enc{s}_block2"] = y1
+            pooled = pl.buf(f"pool{s}", (B, h // 2, w // 2, f))
+            sdrop = self._drop(f"dec{s}_dropout", 2 * f, f) if s > 1 else None
+            self._block_train_fwd(pl, f"enc{s}_block2", y1, cat[..., f:], pooled=pooled, drop=sdrop)
+            cur = pooled
+        h, w = self._dims(4)
+        xin["bneck_block1"] = cur
+        y1 = self._block_train_fwd(pl, "bneck_block1", cur, pl.buf("bneck_block1/y", (B, h, w, 1024)))
+        xin["bneck_block2"] = y1
+        cur = self._block_train_fwd(pl, "bneck_block2", y1, pl.buf("bneck_block2/y", (B, h, w, 1024)),
+                                    drop=self._drop("bneck_dropout", 1024))
+        convt_in = {}
+        for s in (4, 3, 2, 1):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            convt_in[s] = cur
+            self._convt_fwd(s, cur, cats[s][..., :f], self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None)
+            xin[f"dec{s}_block1"] = cats[s]
+            y1 = self._block_train_fwd(pl, f"dec{s}_block1", cats[s], pl.buf(f"dec{s}_block1/y", (B, h, w, f)))
+            xin[f"dec{s}_block2"] = y1
+            cur = self._block_train_fwd(pl, f"dec{s}_block2", y1, pl.buf(f"dec{s}_block2/y", (B, h, w, f)))
+        probs = pl.buf("probs", (B, H, W, NC), torch.float32)
+        sums = pl.buf("sums", (B, NC, 3), torch.float64)
+        sums.zero_()
+        wk, bk = self._mat("output_mask/kernel"), self.wview("output_mask/bias")
+        ops.head_fwd(cur, wk, bk, probs, y_true, sums)
+        out3 = pl.buf("out3", (3,), torch.float32)
+        coef = pl.buf("coef", (B, NC, 2), torch.float32)
+        ops.seg_loss_finalize(sums, B * NC, SMOOTH, kind, 1.0, out3, coef)
+        # ---------------- backward
+        n_scr = B * H * W * 128
+        S = [pl.buf(f"scr{i}", (n_scr,)) for i in range(3)]
+        dy = S[0][: B * H * W * 64].view(B, H, W, 64)
+        ops.head_bwd(cur, wk, probs, y_true, coef, dy, self._mat("output_mask/kernel", self.g),
+                     self.wview("output_mask/bias", self.g))
+        ci = 0   # index of the scratch buffer that currently holds dy
+        dcat = {}
+        for s in (1, 2, 3, 4):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            M = B * h * w
+            o1, o2 = (ci + 1) % 3, (ci + 2) % 3
+            # dec{s}_block2: dy (S[ci]) -> dx into S[ci] (dy is dead once dz exists)
+            dx = S[ci][: M * f].view(B, h, w, f)
+            self._block_train_bwd(pl, f"dec{s}_block2", xin[f"dec{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx)
+            # dec{s}_block1: input is the (dropped-out) concat buffer
+            dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
+            self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
+                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None)
+            # Conv2DTranspose backward
+            xi = convt_in[s]
+            Mi = xi.shape[0] * xi.shape[1] * xi.shape[2]
+            gth = S[o1][: Mi * 4 * f].view(Mi, 4 * f)
+            ops.convt_bwd_gather(dcat[s][..., :f], gth, self.wview(f"dec{s}_upsample/bias", self.g))
+            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True)
+            dy = S[ci][: Mi * 2 * f].view(xi.shape)
+            self._convt_dgrad(s, gth, dy)
+        if self.grad_hook:
+            self.grad_hook("decoder")
+        # bottleneck
+        h, w = self._dims(4)
+        M = B * h * w
+        o1, o2 = (ci + 1) % 3, (ci + 2) % 3
+        dx = S[ci][: M * 1024].view(B, h, w, 1024)
+        self._block_train_bwd(pl, "bneck_block2", xin["bneck_block2"], dy, (S[o1], S[o2]), dx_out=dx,
+                              ydrop=self._drop("bneck_dropout", 1024))
+        dpool = S[ci][: M * 512].view(B, h, w, 512)
+        self._block_train_bwd(pl, "bneck_block1", xin["bneck_block1"], dx, (S[o1], S[o2]), dx_out=dpool)
+        if self.grad_hook:
+            self.grad_hook("bottleneck")
+        # encoder
+        for s in (4, 3, 2, 1):
+            f = FILTERS[s - 1]
+            h, w = self._dims(s - 1)
+            M = B * h * w
+            o1, o2 = (ci + 1) % 3, (ci + 2) % 3
+            if self.use_bn:
+                scale, shift, _, _ = self._bn(f"enc{s}_block2")
+            else:
+                scale, shift = self.ones[:f], self.zeros[:f]
+            dy = S[o1][: M * f].view(B, h, w, f)
+            ops.maxpool2x2_bwd(pl.t[f"enc{s}_block2/z"], scale, shift, dpool, dcat[s][..., f:], dy)
+            ci, o1 = o1, ci        # dy now lives in the old o1; the old ci is free
+            dx = S[ci][: M * f].view(B, h, w, f)
+            self._block_train_bwd(pl, f"enc{s}_block2", xin[f"enc{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx)
+            x1 = xin[f"enc{s}_block1"]
+            cin = x1.shape[-1]
+            dpool = S[ci][: M * cin].view(B, h, w, cin) if s > 1 else None
+            self._block_train_bwd(pl, f"enc{s}_block1", x1, dx, (S[o1], S[o2]), dx_out=dpool)
+        if self.grad_hook:
+            self.grad_hook("encoder")
+        self._fold_dirty = True     # moving statistics changed
+        return out3
+
+    def apply_gradients(self) -> None:
+        """Keras-form AdamW over the whole flat parameter buffer (train.py:226), then advance t and the dropout word."""
+        ops.adamw_step(self.w, self.g, self.m, self.v, self.hyper)
+        ops.step_advance(self.hyper, self.step_word)
+        self._stage_dirty = True
+        self._restage()
+
+    def train_step(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:
+        out3 = self.train_forward_backward(x, y_true, loss)
+        self.apply_gradients()
+        return out3
+
+    # ------------------------------------------------------------------------------------------------ evaluation
+    def evaluate_batch(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:
+        """Inference-mode forward + (loss, dice_coef, iou_coef) on device."""
+        probs = self.forward_inference(x)
+        pl = self._plan(x.shape[0], False)
+        B, NC = x.shape[0], self.num_classes
+        sums = pl.buf("sums", (B, NC, 3), torch.float64)
+        sums.zero_()
+        ops.seg_sums(y_true, probs, sums)
+        out3 = pl.buf("out3", (3,), torch.float32)
+        ops.seg_loss_finalize(sums, B * NC, SMOOTH, {"dice": 0, "iou": 1}[loss], 1.0, out3, None)
+        return out3
+
+    def plan_bytes(self) -> int:
+        return sum(p.bytes() for p in self._plans.values())
+
+    def release_plans(self) -> None:
+        self._plans.clear()

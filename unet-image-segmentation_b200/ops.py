@@ -1,0 +1,366 @@
+"""Typed wrappers over the C-ABI (include/unet_b200.h): torch tensors in, kernel launches on the current stream out.
+
+torch is used for device memory and streams only; every function here ends in exactly one call into
+libunet_b200.so.  Activations are NHWC tensors or channel-slice views of wider NHWC buffers (`x[..., c0:c0+C]`):
+the leading dimension handed to the kernels is the pixel stride of the view, which is how Concatenate
+(reference model/u_net.py:96) costs nothing.  Nothing in this module falls back to torch arithmetic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_CONVT, EPI_NONE, EPI_STATS, UNET_BF16, UNET_F32, Dropout,
+                   GemmArgs)
+
+_DT = {torch.float32: UNET_F32, torch.bfloat16: UNET_BF16}
+
+launches = 0   # number of kernel-launching C-ABI calls made through this module (bench.py reports it)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported activation dtype {t.dtype}") from None
+
+
+def _f32(t: Optional[torch.Tensor], name: str) -> None:
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda):
+        raise TypeError(f"{name} must be a contiguous CUDA fp32 tensor")
+
+
+def _nhwc(t: torch.Tensor, name: str) -> Tuple[int, int, int, int, int]:
+    """(N, H, W, C, ld) of an NHWC tensor or channel-slice view."""
+    if t.dim() != 4 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a 4-D CUDA tensor (N,H,W,C)")
+    n, h, w, c = t.shape
+    ld = t.stride(2) if w > 1 else (t.stride(1) if h > 1 else (t.stride(0) if n > 1 else c))
+    if c > 1 and t.stride(3) != 1:
+        raise ValueError(f"{name}: channels must be contiguous")
+    if (w > 1 and t.stride(2) != ld) or (h > 1 and t.stride(1) != w * ld) or (n > 1 and t.stride(0) != h * w * ld):
+        raise ValueError(f"{name}: not a pixel-strided NHWC view (strides {t.stride()})")
+    return n, h, w, c, ld
+
+
+def _rows(t: torch.Tensor, name: str) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a 2-D row-major matrix or column-slice view; NHWC tensors are flattened over pixels."""
+    if t.dim() == 4:
+        n, h, w, c, ld = _nhwc(t, name)
+        return n * h * w, c, ld
+    if t.dim() != 2 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a 2-D CUDA tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        raise ValueError(f"{name}: columns must be contiguous")
+    return t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0)))
+
+
+def make_dropout(rate: float, seed: int, ctot: int, c0: int = 0,
+                 seed_dev: Optional[torch.Tensor] = None) -> Optional[Dropout]:
+    """Dropout(rate) mask descriptor (u_net.py:78,98).  `seed_dev`: int32 device word added to `seed` in-kernel."""
+    if rate <= 0.0:
+        return None
+    if seed_dev is not None and (seed_dev.dtype != torch.int32 or not seed_dev.is_cuda):
+        raise TypeError("seed_dev must be a CUDA int32 tensor")
+    return Dropout(float(rate), int(seed) & 0xFFFFFFFF, int(ctot), int(c0), _p(seed_dev))
+
+
+def _dref(d: Optional[Dropout]):
+    return None if d is None else C.byref(d)
+
+
+# Optional per-launch timing (bench.py): CUDA events recorded on the launching stream around every C-ABI call,
+# keyed by (entry point, shape tag), together with the call's ALGORITHMIC bytes and flops (each distinct input read
+# once + each output written once; 2*M*N*K for contractions) so that a roofline fraction can be formed per kernel.
+_prof = None
+_tag = ""
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = {}
+
+
+def profile_end() -> dict:
+    """-> {key: dict(calls, ms, bytes, flops)}; bytes/flops are per-call algorithmic figures summed over calls."""
+    global _prof
+    torch.cuda.synchronize()
+    out = {}
+    for key, rec in (_prof or {}).items():
+        ms = sum(a.elapsed_time(b) for a, b in rec["ev"])
+        out[key] = dict(calls=len(rec["ev"]), ms=ms, bytes=rec["bytes"], flops=rec["flops"])
+    _prof = None
+    return out
+
+
+def _nbytes(*tensors) -> int:
+    return sum(t.numel() * t.element_size() for t in tensors if t is not None)
+
+
+def _call(name: str, *args, tag: str = "", nbytes: int = 0, flops: int = 0) -> None:
+    global launches
+    launches += 1
+    if _prof is None:
+        _lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    _lib.call(name, *args)
+    e1.record()
+    rec = _prof.setdefault(f"{name[5:]}[{tag}]", dict(ev=[], bytes=0, flops=0))
+    rec["ev"].append((e0, e1)); rec["bytes"] += nbytes; rec["flops"] += flops
+
+
+# ------------------------------------------------------------------------------------------------ depthwise
+def dwconv3x3(x: torch.Tensor, w9c: torch.Tensor, y: torch.Tensor, flip: bool = False,
+              in_scale: Optional[torch.Tensor] = None, in_shift: Optional[torch.Tensor] = None,
+              drop: Optional[Dropout] = None) -> None:
+    """SeparableConv2D depthwise half (u_net.py:14-20); flip=True gives the gradient w.r.t. the input."""
+    n, h, w, c, ldx = _nhwc(x, "x")
+    n2, h2, w2, c2, ldy = _nhwc(y, "y")
+    if (n, h, w, c) != (n2, h2, w2, c2) or x.dtype != y.dtype:
+        raise ValueError("dwconv3x3: x and y disagree")
+    _f32(w9c, "w9c"); _f32(in_scale, "in_scale"); _f32(in_shift, "in_shift")
+    if w9c.numel() != 9 * c:
+        raise ValueError("dwconv3x3: w9c must hold 9*C floats")
+    _call("unet_dwconv3x3_fwd", _p(x), ldx, _p(w9c), _p(y), ldy, n, h, w, c, _dt(x), int(flip),
+          _p(in_scale), _p(in_shift), _dref(drop), _stream(),
+          tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(x, y, w9c), flops=18 * x.numel())
+
+
+def dwconv3x3_bwd_weight(x: torch.Tensor, dy: torch.Tensor, dw9c: torch.Tensor) -> None:
+    n, h, w, c, ldx = _nhwc(x, "x")
+    n2, h2, w2, c2, lddy = _nhwc(dy, "dy")
+    if (n, h, w, c) != (n2, h2, w2, c2) or x.dtype != dy.dtype:
+        raise ValueError("dwconv3x3_bwd_weight: x and dy disagree")
+    _f32(dw9c, "dw9c")
+    _call("unet_dwconv3x3_bwd_weight", _p(x), ldx, _p(dy), lddy, _p(dw9c), n, h, w, c, _dt(x), _stream(),
+          tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(x, dy, dw9c), flops=18 * x.numel())
+
+
+# ------------------------------------------------------------------------------------------------ dense contractions
+def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = False, b_trans: bool = False,
+         accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,
+         shift: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
+         colsq: Optional[torch.Tensor] = None, convt_hw: Tuple[int, int] = (0, 0),
+         drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None) -> None:
+    """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
+    hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
+    CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported)."""
+    ar, ac, lda = _rows(A, "A")
+    br, bc, ldb = _rows(B, "B")
+    M, K = (ac, ar) if a_trans else (ar, ac)
+    N, Kb = (br, bc) if b_trans else (bc, br)
+    if K != Kb:
+        raise ValueError(f"gemm: inner dimensions disagree ({K} vs {Kb})")
+    if A.dtype != B.dtype:
+        raise ValueError("gemm: A and B must share a dtype")
+    if epilogue == EPI_CONVT:
+        _, _, _, cc, ldc = _nhwc(Cm, "C")
+        if cc * 4 != N:
+            raise ValueError("gemm(CONVT): destination view must have N/4 channels")
+    else:
+        cr, cc, ldc = _rows(Cm, "C")
+        if (cr, cc) != (M, N):
+            raise ValueError(f"gemm: C is {cr}x{cc}, expected {M}x{N}")
+    _f32(scale, "scale"); _f32(shift, "shift")
+    for t, nm in ((colsum, "colsum"), (colsq, "colsq")):
+        if t is not None and t.dtype != torch.float64:
+            raise TypeError(f"{nm} must be float64")
+    args = GemmArgs()
+    args.M, args.N, args.K = M, N, K
+    args.A, args.lda = _p(A), lda
+    args.B, args.ldb = _p(B), ldb
+    args.C, args.ldc = _p(Cm), ldc
+    args.a_trans, args.b_trans = int(a_trans), int(b_trans)
+    args.in_dtype, args.out_dtype = _dt(A), _dt(Cm)
+    args.accumulate, args.epilogue = int(accumulate), int(epilogue)
+    args.scale, args.shift = _p(scale), _p(shift)
+    args.colsum, args.colsq = _p(colsum), _p(colsq)
+    args.convt_H, args.convt_W = int(convt_hw[0]), int(convt_hw[1])
+    if drop is not None:
+        args.drop = drop
+    tc_ok = (A.dtype == torch.bfloat16 and N % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and ldc % 4 == 0
+             and ((not a_trans and b_trans and not accumulate and K % 8 == 0)
+                  or (a_trans and not b_trans and accumulate and M % 8 == 0))
+             and (epilogue != EPI_CONVT or (N // 4) % 64 == 0))
+    use_tc = tc_ok if tensor_core is None else tensor_core
+    csz = Cm.numel() * Cm.element_size()
+    _call("unet_gemm_tc" if use_tc else "unet_gemm_simt", C.byref(args), _stream(),
+          tag=f"{'wgrad' if a_trans else ('convt' if epilogue == EPI_CONVT else 'nt')}:{M}x{N}x{K}:e{epilogue}",
+          nbytes=A.numel() * A.element_size() + B.numel() * B.element_size() + csz * (2 if accumulate else 1),
+          flops=2 * M * N * K)
+
+
+# ------------------------------------------------------------------------------------------------ batch normalisation
+def bn_fold(gamma, beta, mean, var, eps: float, scale, shift) -> None:
+    for t, nm in ((gamma, "gamma"), (beta, "beta"), (mean, "mean"), (var, "var"), (scale, "scale"), (shift, "shift")):
+        _f32(t, nm)
+    _call("unet_bn_fold", _p(gamma), _p(beta), _p(mean), _p(var), float(eps), _p(scale), _p(shift),
+          scale.numel(), _stream())
+
+
+def bn_finalize(colsum, colsq, count: int, gamma, beta, eps: float, momentum: float, moving_mean, moving_var,
+                scale, shift, save_mean, save_rstd) -> None:
+    for t, nm in ((gamma, "gamma"), (beta, "beta"), (moving_mean, "moving_mean"), (moving_var, "moving_var"),
+                  (scale, "scale"), (shift, "shift"), (save_mean, "save_mean"), (save_rstd, "save_rstd")):
+        _f32(t, nm)
+    _call("unet_bn_finalize", _p(colsum), _p(colsq), int(count), _p(gamma), _p(beta), float(eps), float(momentum),
+          _p(moving_mean), _p(moving_var), _p(scale), _p(shift), _p(save_mean), _p(save_rstd), scale.numel(), _stream())
+
+
+def bn_act(z: torch.Tensor, scale, shift, y: torch.Tensor, relu: bool = True, pooled: Optional[torch.Tensor] = None,
+           drop: Optional[Dropout] = None) -> None:
+    n, h, w, c, ldz = _nhwc(z, "z")
+    if ldz != c:
+        raise ValueError("bn_act: z must be contiguous")
+    _, _, _, c2, ldy = _nhwc(y, "y")
+    if c2 != c or (pooled is not None and not pooled.is_contiguous()):
+        raise ValueError("bn_act: bad y / pooled")
+    _f32(scale, "scale"); _f32(shift, "shift")
+    _call("unet_bn_act", _p(z), _p(scale), _p(shift), int(relu), _p(y), ldy, _p(pooled), n, h, w, c, _dt(z),
+          _dref(drop), _stream(), tag=f"{n}x{h}x{w}x{c}{'+pool' if pooled is not None else ''}",
+          nbytes=_nbytes(z, y, pooled))
+
+
+def bn_bwd_reduce(dy, z, scale, shift, save_mean, save_rstd, dgamma, dbeta, relu: bool = True,
+                  drop: Optional[Dropout] = None) -> None:
+    M, c, lddy = _rows(dy, "dy")
+    M2, c2, ldz = _rows(z, "z")
+    if (M, c) != (M2, c2) or ldz != c:
+        raise ValueError("bn_bwd_reduce: dy / z disagree or z not contiguous")
+    _call("unet_bn_bwd_reduce", _p(dy), lddy, _p(z), _p(scale), _p(shift), _p(save_mean), _p(save_rstd),
+          _p(dgamma), _p(dbeta), M, c, _dt(z), int(relu), _dref(drop), _stream(), tag=f"{M}x{c}", nbytes=_nbytes(dy, z))
+
+
+def bn_bwd_apply(dy, z, scale, shift, save_mean, save_rstd, dgamma, dbeta, dz, relu: bool = True,
+                 drop: Optional[Dropout] = None) -> None:
+    M, c, lddy = _rows(dy, "dy")
+    M2, c2, ldz = _rows(z, "z")
+    if (M, c) != (M2, c2) or ldz != c or not dz.is_contiguous():
+        raise ValueError("bn_bwd_apply: dy / z disagree or z, dz not contiguous")
+    _call("unet_bn_bwd_apply", _p(dy), lddy, _p(z), _p(scale), _p(shift), _p(save_mean), _p(save_rstd),
+          _p(dgamma), _p(dbeta), _p(dz), M, c, _dt(z), int(relu), _dref(drop), _stream(), tag=f"{M}x{c}",
+          nbytes=_nbytes(dy, z, dz))
+
+
+# ------------------------------------------------------------------------------------------------ pooling
+def maxpool2x2(x: torch.Tensor, y: torch.Tensor) -> None:
+    n, h, w, c, ldx = _nhwc(x, "x")
+    if tuple(y.shape) != (n, h // 2, w // 2, c) or not y.is_contiguous():
+        raise ValueError("maxpool2x2: y must be contiguous (N,H/2,W/2,C)")
+    _call("unet_maxpool2x2_fwd", _p(x), ldx, _p(y), n, h, w, c, _dt(x), _stream(), tag=f"{n}x{h}x{w}x{c}",
+          nbytes=_nbytes(x, y))
+
+
+def maxpool2x2_bwd(z: torch.Tensor, scale, shift, dpool: torch.Tensor, dskip: Optional[torch.Tensor],
+                   dy: torch.Tensor) -> None:
+    n, h, w, c, ldz = _nhwc(z, "z")
+    lds = 0
+    if dskip is not None:
+        lds = _nhwc(dskip, "dskip")[4]
+    if not dpool.is_contiguous() or not dy.is_contiguous():
+        raise ValueError("maxpool2x2_bwd: dpool and dy must be contiguous")
+    _call("unet_maxpool2x2_bwd", _p(z), ldz, _p(scale), _p(shift), _p(dpool), _p(dskip), lds, _p(dy), n, h, w, c,
+          _dt(z), _stream(), tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(z, dpool, dskip, dy))
+
+
+def convt_bwd_gather(du: torch.Tensor, g: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
+    """du: (N,2H,2W,Cout) view -> g: [N*H*W, 4*Cout]; dbias += column sums."""
+    n, h2, w2, co, lddu = _nhwc(du, "du")
+    if not g.is_contiguous() or g.numel() != du.shape[0] * h2 * w2 * co:
+        raise ValueError("convt_bwd_gather: g has the wrong size")
+    _call("unet_convt_bwd_gather", _p(du), lddu, _p(g), _p(dbias), n, h2 // 2, w2 // 2, co, _dt(du), _stream(),
+          tag=f"{n}x{h2}x{w2}x{co}", nbytes=_nbytes(du, g))
+
+
+# ------------------------------------------------------------------------------------------------ head + loss
+def head_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], probs: torch.Tensor,
+             y_true: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None) -> None:
+    n, h, wd, k, ldx = _nhwc(x, "x")
+    c = probs.shape[-1]
+    _f32(w, "w"); _f32(b, "b"); _f32(probs, "probs"); _f32(y_true, "y_true")
+    if sums is not None and sums.dtype != torch.float64:
+        raise TypeError("sums must be float64")
+    _call("unet_head_fwd", _p(x), ldx, _p(w), _p(b), _p(probs), _p(y_true), _p(sums), n * h * wd, h * wd, k, c,
+          _dt(x), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}", nbytes=_nbytes(x, probs, y_true), flops=2 * x.numel() * c)
+
+
+def seg_loss_finalize(sums: torch.Tensor, npairs: int, smooth: float, kind: int, grad_scale: float,
+                      out3: torch.Tensor, coef: Optional[torch.Tensor]) -> None:
+    _f32(out3, "out3"); _f32(coef, "coef")
+    _call("unet_seg_loss_finalize", _p(sums), int(npairs), float(smooth), int(kind), float(grad_scale), _p(out3),
+          _p(coef), _stream())
+
+
+def head_bwd(x, w, probs, y_true, coef, dx: Optional[torch.Tensor], dw, db) -> None:
+    n, h, wd, k, ldx = _nhwc(x, "x")
+    c = probs.shape[-1]
+    lddx = _nhwc(dx, "dx")[4] if dx is not None else 0
+    for t, nm in ((w, "w"), (probs, "probs"), (y_true, "y_true"), (coef, "coef"), (dw, "dw"), (db, "db")):
+        _f32(t, nm)
+    _call("unet_head_bwd", _p(x), ldx, _p(w), _p(probs), _p(y_true), _p(coef), _p(dx), lddx, _p(dw), _p(db),
+          n * h * wd, h * wd, k, c, _dt(x), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}",
+          nbytes=_nbytes(x, probs, y_true, dx), flops=4 * x.numel() * c)
+
+
+def seg_sums(y_true: torch.Tensor, y_pred: torch.Tensor, sums: torch.Tensor) -> None:
+    _f32(y_true, "y_true"); _f32(y_pred, "y_pred")
+    nb, c = y_true.shape[0], y_true.shape[-1]
+    hw = y_true.numel() // (nb * c)
+    _call("unet_seg_sums", _p(y_true), _p(y_pred), _p(sums), nb, hw, c, _stream())
+
+
+def confusion_matrix_update(y_true, y_pred, num_classes: int, counts: torch.Tensor,
+                            threshold: Optional[float] = None) -> None:
+    _f32(y_true, "y_true"); _f32(y_pred, "y_pred")
+    if counts.dtype != torch.int64 or not counts.is_contiguous():
+        raise TypeError("counts must be contiguous int64")
+    if threshold is None:
+        _call("unet_confusion_matrix_update", _p(y_true), _p(y_pred), y_true.numel(), int(num_classes), _p(counts),
+              _stream())
+    else:
+        _call("unet_confusion_matrix_update_thr", _p(y_true), _p(y_pred), float(threshold), y_true.numel(),
+              _p(counts), _stream())
+
+
+# ------------------------------------------------------------------------------------------------ optimiser, staging
+def adamw_step(w, g, m, v, hyper) -> None:
+    for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v"), (hyper, "hyper")):
+        _f32(t, nm)
+    _call("unet_adamw_step", _p(w), _p(g), _p(m), _p(v), w.numel(), _p(hyper), _stream(), tag=str(w.numel()),
+          nbytes=7 * w.numel() * 4)
+
+
+def step_advance(hyper: Optional[torch.Tensor], counter: Optional[torch.Tensor]) -> None:
+    """hyper[5] (AdamW step t) += 1; *counter (dropout seed word) += 1 — on device, so CUDA-graph replays advance."""
+    _f32(hyper, "hyper")
+    _call("unet_step_advance", _p(hyper), _p(counter), _stream())
+
+
+def cast_transpose_bf16(src: torch.Tensor, dst: Optional[torch.Tensor], dst_t: Optional[torch.Tensor]) -> None:
+    _f32(src, "src")
+    r, c = src.shape
+    _call("unet_cast_transpose_bf16", _p(src), _p(dst), _p(dst_t), r, c, _stream())
+
+
+def cast(src: torch.Tensor, dst: torch.Tensor) -> None:
+    if not src.is_contiguous() or not dst.is_contiguous() or src.numel() != dst.numel():
+        raise ValueError("cast: tensors must be contiguous and equal in size")
+    _call("unet_cast", _p(src), _dt(src), _p(dst), _dt(dst), src.numel(), _stream(), tag=str(src.numel()),
+          nbytes=_nbytes(src, dst))
+
+
+def device_check(device: int = 0) -> None:
+    _lib.call("unet_device_check", int(device))

@@ -52,11 +52,12 @@ def forward(P: Dict[str, torch.Tensor], x_nhwc: torch.Tensor, num_classes: int =
             use_batch_norm: bool = True, training: bool = False, drop_seeds: Optional[Dict[str, int]] = None):
     """x: (N,H,W,C) -> probabilities (N,H,W,num_classes)."""
     x = x_nhwc.permute(0, 3, 1, 2)
-    drop_seeds = drop_seeds or {}
 
     def dropout(name, t):
         if not training or dropout_rate <= 0.0:
             return t
+        if drop_seeds is None:          # timing runs: torch's own Bernoulli mask (same cost class as TF's)
+            return F.dropout(t, dropout_rate, training=True)
         n, c, h, w = t.shape
         mult = dropout_multiplier((n, h, w, c), dropout_rate, drop_seeds[name])
         return t * torch.tensor(mult, dtype=t.dtype).permute(0, 3, 1, 2)

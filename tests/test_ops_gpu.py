@@ -44,7 +44,8 @@ DTYPES = [torch.float32, torch.bfloat16]
 
 # ------------------------------------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (3, 33, 9, 24), (2, 8, 8, 3), (1, 1, 1, 16), (1, 64, 48, 128)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (3, 33, 9, 24), (2, 8, 8, 3), (1, 1, 1, 16), (1, 64, 48, 128),
+                                   (2, 100, 70, 72), (1, 131, 33, 200), (2, 7, 5, 1)])
 @pytest.mark.parametrize("flip", [False, True])
 def test_dwconv_fwd(dtype, shape, flip):
     x = RNG.standard_normal(shape).astype(np.float32)
@@ -79,7 +80,7 @@ def test_dwconv_fwd_views_affine_dropout(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (2, 40, 9, 3), (1, 70, 12, 128), (2, 8, 8, 1024)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (2, 40, 9, 3), (1, 70, 12, 128), (2, 8, 8, 1024), (2, 33, 20, 1), (1, 9, 9, 4)])
 def test_dwconv_bwd_weight(dtype, shape):
     x = RNG.standard_normal(shape).astype(np.float32)
     dy = RNG.standard_normal(shape).astype(np.float32)

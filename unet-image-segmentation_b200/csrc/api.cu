@@ -1,5 +1,6 @@
 // Library-level entry points and error plumbing of libunet_b200.so.
 #include "common.cuh"
+#include "ptx.cuh"
 #include <string.h>
 
 namespace unet {
@@ -29,6 +30,20 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
 }
 
 }  // namespace unet

@@ -6,6 +6,7 @@
 // channels of one image column and slides down a segment of rows keeping the running partial sums in
 // registers; the three column taps of a row come from the two neighbouring threads' lines in L1.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace unet {
 
@@ -94,6 +95,192 @@ dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ forward, TMA strips
+// One CTA = one strip: TW output columns x 128 B of channels x a segment of rows of one image.  A producer warp streams
+// the strip top to bottom through a ring of shared-memory stages with 4-D TMA boxes (channels, columns + 2 halo,
+// RH rows, image) issued by thread 0, S-1 stages ahead; rows -1 / H and columns -1 / W come back as zeros from the TMA out-of-bounds fill, which IS the
+// 'same' padding.  Eight consumer warps slide down the strip: a thread owns 16 B of channels of one column, keeps the
+// two open partial sums in registers, and per input row does 3 conflict-free 16-byte shared loads and 27 FMAs per
+// channel-triple; outputs leave as coalesced 16-byte global stores (4 pixels x 128 B per warp instruction).
+// HBM sees every input byte once plus 2/TW column halo (served by L2) and 2/segment rows.
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+
+template <typename T> struct StripCfg {
+  static constexpr int VEC = 16 / (int)sizeof(T);        // channels per thread
+  static constexpr int CB = 128 / (int)sizeof(T);        // channels per CTA
+  static constexpr int TW = 32, RH = 4, S = 5;
+  static constexpr int kStageBytes = RH * (TW + 2) * 128;
+  static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + 128;
+};
+
+template <typename T> __device__ __forceinline__ void unpack16(const uint4& r, float (&v)[16 / sizeof(T)]);
+template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& r, float (&v)[8]) {
+  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+template <> __device__ __forceinline__ void unpack16<float>(const uint4& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+}
+__device__ __forceinline__ uint4 pack16(const float (&v)[8], __nv_bfloat16*) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 pack16(const float (&v)[4], float*) {
+  return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
+                       int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp) {
+  using Cfg = StripCfg<T>;
+  constexpr int VEC = Cfg::VEC, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + S;
+
+  int item = blockIdx.x;
+  const int cb = item % ncb; item /= ncb;
+  const int tw = item % ntw; item /= ntw;
+  const int hs = item % nseg;
+  const int n = item / nseg;
+  const int c0 = cb * Cfg::CB, w0 = tw * TW;
+  const int h0 = hs * seg_rows, h1 = min(H, h0 + seg_rows);
+  const int nst = (h1 - h0 + 2 + RH - 1) / RH;          // input rows h0-1 .. h1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // thread 0 doubles as the TMA producer: it keeps S-1 stages in flight ahead of the stage being consumed
+  auto issue = [&](int k) {
+    const int s = k % S;
+    if (k >= S) mbar_wait(&empty_bar[s], ((k / S) - 1) & 1);
+    mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+    tma_load_4d(smem + s * Cfg::kStageBytes, &tmX, &full_bar[s], c0, w0 - 1, h0 - 1 + k * RH, n, kEvictNormal);
+  };
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int k = 0; k < S - 1 && k < nst; ++k) issue(k);
+  }
+
+  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int c = c0 + cg * VEC;
+  const bool live = (w0 + px < W) && (c < C);
+  float k9[9][VEC];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+    const int src = flip ? 8 - i : i;
+    if (c < C) {
+      if (VEC == 8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c) + 1);
+        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2] = a.z; k9[i][3] = a.w;
+        k9[i][4 % VEC] = b.x; k9[i][5 % VEC] = b.y; k9[i][6 % VEC] = b.z; k9[i][7 % VEC] = b.w;
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
+        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2] = a.z; k9[i][3] = a.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) k9[i][j] = 0.f;
+    }
+  }
+  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
+  float prev[VEC], cur[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
+  T* ycol = y + (((int64_t)n * H) * W + (w0 + px)) * ldy + c;
+  const int64_t yrow = (int64_t)W * ldy;
+  const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 16u;
+
+  for (int k = 0; k < nst; ++k) {
+    const int s = k % S;
+    if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
+    mbar_wait(&full_bar[s], (k / S) & 1);
+    const uint8_t* st = smem + s * Cfg::kStageBytes + tile_off;
+#pragma unroll
+    for (int rr = 0; rr < RH; ++rr) {
+      const int r_in = h0 - 1 + k * RH + rr;
+      if (r_in > h1) break;
+      const uint4 ra = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128);
+      const uint4 rb = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128 + 128);
+      const uint4 rc = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128 + 256);
+      float a[VEC], b[VEC], cc[VEC];
+      unpack16<T>(ra, a); unpack16<T>(rb, b); unpack16<T>(rc, cc);
+      if (r_in - 1 >= h0 && live) {          // output row r_in-1 is complete once kernel row 2 has seen input row r_in
+        float o[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
+        if (dp.on) {
+          const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) o[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+        }
+        *reinterpret_cast<uint4*>(ycol + (int64_t)(r_in - 1) * yrow) = pack16(o, (T*)nullptr);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        prev[j] = fmaf(k9[5][j], cc[j], fmaf(k9[4][j], b[j], fmaf(k9[3][j], a[j], cur[j])));
+        cur[j]  = fmaf(k9[2][j], cc[j], fmaf(k9[1][j], b[j], k9[0][j] * a[j]));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+}
+
+// NHWC view (ptr, ld) as a 4-D tensor map {C, W, H, N}; box {128 B of channels, box_w, box_h, 1}; zero OOB fill
+template <typename T>
+static int make_nhwc_tmap(CUtensorMap* map, const void* base, int64_t ld, int N, int H, int W, int C, int box_w, int box_h,
+                          const char* who) {
+  PFN_encodeTiled fn = get_encode_fn();
+  UNET_REQUIRE(fn, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  constexpr int es = (int)sizeof(T);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * es, (cuuint64_t)W * ld * es, (cuuint64_t)H * W * ld * es};
+  cuuint32_t box[4] = {(cuuint32_t)(128 / es), (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = fn(map, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4,
+                        const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
+  return UNET_OK;
+}
+
+static int pick_seg_rows(int N, int H, int ntw, int ncb, int min_rows, int64_t want_items) {
+  int seg = H;
+  while (seg > min_rows && (int64_t)N * ceil_div(H, seg) * ntw * ncb < want_items) seg = (seg + 1) / 2;
+  return seg;
+}
+
+template <typename T>
+static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
+                               int flip, DropArgs dp, cudaStream_t st) {
+  using Cfg = StripCfg<T>;
+  CUtensorMap tm;
+  if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "dwconv3x3_fwd: cudaFuncSetAttribute");
+    attr_done = true;
+  }
+  const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
+  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 2 * 6);
+  const int nseg = (int)ceil_div(H, seg);
+  const int64_t items = (int64_t)N * nseg * ntw * ncb;
+  UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
+  dwconv3x3_strip_kernel<T><<<(unsigned)items, 256, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
+  UNET_LAUNCH_CHECK("dwconv3x3_fwd(strip)");
+  return UNET_OK;
+}
+
 // any channel count (used for the 3-channel input image)
 template <typename T, bool AFFINE>
 __global__ void dwconv3x3_scalar_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w9c,
@@ -130,6 +317,8 @@ static int dw_fwd_launch(const void* x, int64_t ldx, const float* w9c, void* y, 
                          int flip, const float* in_scale, const float* in_shift, DropArgs dp, cudaStream_t st) {
   const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && aligned16(x) && aligned16(y) &&
                    aligned16(w9c) && (!in_scale || (aligned16(in_scale) && aligned16(in_shift)));
+  if (vec && !in_scale)      // the TMA path pads with zeros in INPUT space, which is wrong under a fused input affine
+    return dw_fwd_strip_launch<T>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, st);
   if (vec) {
     // rows per thread: long segments amortise the 2 halo rows; shrink until the grid covers the machine twice
     int R = 32;
@@ -277,6 +466,73 @@ __global__ void dwconv3x3_bwd_weight_scalar_kernel(const T* __restrict__ x, int6
   }
 }
 
+// C <= 4 (the RGB input image): one thread per (image, row segment, column), all channels, 9*C register accumulators,
+// warp shuffle -> shared -> one global atomic per (tap, channel) per block.
+template <typename T, int CC>
+__global__ void __launch_bounds__(256)
+dwconv3x3_bwd_weight_smallc_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
+                                   float* __restrict__ dw9c, int N, int H, int W, int R, int nseg) {
+  __shared__ float s_acc[9 * CC];
+  if (threadIdx.x < 9 * CC) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  float acc[9][CC];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int c = 0; c < CC; ++c) acc[i][c] = 0.f;
+  const int64_t n_items = (int64_t)N * nseg * W;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < n_items; item += (int64_t)gridDim.x * blockDim.x) {
+    const int wq = (int)(item % W); const int64_t t = item / W;
+    const int hs = (int)(t % nseg); const int64_t n = t / nseg;
+    const int h0 = hs * R, h1 = min(H, h0 + R);
+    const bool has_l = wq > 0, has_r = wq + 1 < W;
+    const T* xcol = x + ((n * H) * (int64_t)W + wq) * ldx;
+    const T* dcol = dy + ((n * H) * (int64_t)W + wq) * lddy;
+    const int64_t xrow = (int64_t)W * ldx, drow = (int64_t)W * lddy;
+    float dm[CC], d0[CC], dp[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) { dm[c] = 0.f; d0[c] = 0.f; dp[c] = h0 < h1 ? to_f32(dcol[(int64_t)h0 * drow + c]) : 0.f; }
+    for (int q = h0 - 1; q <= h1; ++q) {
+      if (q >= 0 && q < H) {
+        const T* p = xcol + q * xrow;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+          const float b = to_f32(p[c]);
+          const float a = has_l ? to_f32(p[c - ldx]) : 0.f;
+          const float cc = has_r ? to_f32(p[c + ldx]) : 0.f;
+          acc[0][c] = fmaf(a, dp[c], acc[0][c]); acc[1][c] = fmaf(b, dp[c], acc[1][c]); acc[2][c] = fmaf(cc, dp[c], acc[2][c]);
+          acc[3][c] = fmaf(a, d0[c], acc[3][c]); acc[4][c] = fmaf(b, d0[c], acc[4][c]); acc[5][c] = fmaf(cc, d0[c], acc[5][c]);
+          acc[6][c] = fmaf(a, dm[c], acc[6][c]); acc[7][c] = fmaf(b, dm[c], acc[7][c]); acc[8][c] = fmaf(cc, dm[c], acc[8][c]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        dm[c] = d0[c]; d0[c] = dp[c];
+        dp[c] = (q + 2 < h1) ? to_f32(dcol[(int64_t)(q + 2) * drow + c]) : 0.f;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+      const float v = warp_sum(acc[i][c]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_acc[i * CC + c], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < 9 * CC) atomicAdd(&dw9c[threadIdx.x], s_acc[threadIdx.x]);
+}
+
+template <typename T, int CC>
+static void dw_bwd_weight_smallc_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c,
+                                        int N, int H, int W, cudaStream_t st) {
+  const int R = 16;
+  const int nseg = (int)ceil_div(H, R);
+  const int64_t items = (int64_t)N * nseg * W;
+  const unsigned grid = (unsigned)i64min(ceil_div(items, 256), (int64_t)sm_count() * 8);
+  dwconv3x3_bwd_weight_smallc_kernel<T, CC><<<grid, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, R, nseg);
+}
+
 template <typename T>
 static int dw_bwd_weight_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c,
                                 int N, int H, int W, int C, cudaStream_t st) {
@@ -295,6 +551,13 @@ static int dw_bwd_weight_launch(const void* x, int64_t ldx, const void* dy, int6
       cudaFuncSetAttribute(dwconv3x3_bwd_weight_vec4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dwconv3x3_bwd_weight_vec4_kernel<T><<<(unsigned)grid, 256, smem, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c,
                                                                            N, H, W, C, R, nseg);
+  } else if (C <= 4) {
+    switch (C) {
+      case 1: dw_bwd_weight_smallc_launch<T, 1>(x, ldx, dy, lddy, dw9c, N, H, W, st); break;
+      case 2: dw_bwd_weight_smallc_launch<T, 2>(x, ldx, dy, lddy, dw9c, N, H, W, st); break;
+      case 3: dw_bwd_weight_smallc_launch<T, 3>(x, ldx, dy, lddy, dw9c, N, H, W, st); break;
+      default: dw_bwd_weight_smallc_launch<T, 4>(x, ldx, dy, lddy, dw9c, N, H, W, st); break;
+    }
   } else {
     UNET_REQUIRE(C <= 64, UNET_EUNSUPPORTED, "dwconv3x3_bwd_weight: C=%d needs C%%4==0 and 16B-aligned views", C);
     dwconv3x3_bwd_weight_scalar_kernel<T><<<9 * C, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, C);

@@ -15,95 +15,11 @@
 //   warps 4-7 epilogue                        tcgen05.ld -> fp32 staging slab in smem (per warp, padded) -> each lane owns
 //                                             4 fixed columns: scale/shift/ReLU/bias/stats in registers -> coalesced stores
 #include "common.cuh"
-#include <cuda.h>
+#include "ptx.cuh"
 
 namespace unet {
 
 int gemm_validate(const unet_gemm_args* a, const char* who);
-
-// ================================================================================================ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ uint64_t global_timer_ns() {
-  uint64_t t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-// Bounded wait: a mis-programmed pipeline traps after ~20 s instead of hanging the device.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = global_timer_ns();
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > 20000000000ull) __trap();
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // streaming activations
-constexpr uint64_t kEvictLast  = 0x14F0000000000000ull;   // weights: re-read by every M tile
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint64_t hint) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ================================================================================================ descriptors
 // Shared-memory matrix descriptor (SM100 format, version 1), SWIZZLE_128B.
@@ -174,13 +90,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
   const int64_t n = n_base + seg * 4;
   const bool col_ok = n < p.N;     // N is a multiple of 8: a 4-column group is all-or-nothing
   float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-  int64_t cv_ab = 0, cv_co = 0;
+  uint32_t cv_ab = 0, cv_co = 0;
   if (col_ok) {
     if (p.epilogue == UNET_EPI_AFFINE || p.epilogue == UNET_EPI_AFFINE_RELU) {
       if (p.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.scale + n)); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
       if (p.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + n)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
     } else if (p.epilogue == UNET_EPI_CONVT) {
-      cv_ab = n / p.convt_cout; cv_co = n % p.convt_cout;
+      cv_ab = (uint32_t)n / (uint32_t)p.convt_cout; cv_co = (uint32_t)n % (uint32_t)p.convt_cout;
       if (p.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + cv_co)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
     }
   }
@@ -206,9 +122,11 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
     }
     int64_t off;
     if (p.epilogue == UNET_EPI_CONVT) {
-      const int64_t jj = m % p.convt_W, q = m / p.convt_W;
-      const int64_t ii = q % p.convt_H, img = q / p.convt_H;
-      const int64_t pix = (img * 2 * p.convt_H + 2 * ii + (cv_ab >> 1)) * (2 * p.convt_W) + 2 * jj + (cv_ab & 1);
+      // 32-bit index arithmetic (M < 2^31 is checked on the host): 64-bit div/mod here cost more than the tile's MMA
+      const uint32_t m32 = (uint32_t)m, cw = (uint32_t)p.convt_W, ch = (uint32_t)p.convt_H;
+      const uint32_t q = m32 / cw, jj = m32 - q * cw;
+      const uint32_t img = q / ch, ii = q - img * ch;
+      const int64_t pix = ((int64_t)img * 2 * ch + 2 * ii + (cv_ab >> 1)) * (2 * cw) + 2 * jj + (cv_ab & 1);
       if (p.drop_on) {
         const uint64_t base = (uint64_t)pix * p.ctot + p.c0 + cv_co;
 #pragma unroll
@@ -465,24 +383,6 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 // ================================================================================================ host side
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
-  }
-  return fn;
-}
-
 // bf16 2-D tensor [outer, inner] with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B; OOB reads give zero
 static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, const char* who) {
   PFN_encodeTiled fn = get_encode_fn();
@@ -566,6 +466,8 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   UNET_REQUIRE(a->ldc % 4 == 0 && aligned16(a->C), UNET_EALIGN, "gemm_tc: C needs a 16B-aligned base and ldc%%4==0");
   UNET_REQUIRE(!a->scale || aligned16(a->scale), UNET_EALIGN, "gemm_tc: scale must be 16B aligned");
   UNET_REQUIRE(!a->shift || aligned16(a->shift), UNET_EALIGN, "gemm_tc: shift must be 16B aligned");
+  if (a->epilogue == UNET_EPI_CONVT)
+    UNET_REQUIRE(a->M < (int64_t)1 << 31, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs M < 2^31");
   if (a->epilogue == UNET_EPI_CONVT)
     UNET_REQUIRE((a->N / 4) % 64 == 0, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs Cout%%64==0 (got %lld)", (long long)(a->N / 4));
   cudaStream_t st = (cudaStream_t)stream;

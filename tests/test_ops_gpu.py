@@ -199,7 +199,8 @@ def test_gemm_tc_stats(mkn, out_dtype):
 
 
 @pytest.mark.parametrize("rate", [0.0, 0.2])
-@pytest.mark.parametrize("cfg", [(2, 4, 4, 128, 64), (1, 8, 6, 1024, 512), (3, 5, 3, 256, 128)])
+@pytest.mark.parametrize("cfg", [(2, 4, 4, 128, 64), (1, 8, 6, 1024, 512), (3, 5, 3, 256, 128), (3, 6, 16, 128, 64),
+                                 (1, 3, 256, 64, 64), (2, 20, 128, 72, 128)])
 def test_convt_tc(cfg, rate):
     _convt_case(torch.bfloat16, *cfg, rate)
 

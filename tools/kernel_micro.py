@@ -1,0 +1,71 @@
+#!/usr/bin/env python3
+"""Run single kernels of libunet_b200 at the level-0 shapes of the train512 workload (batch 64, 512x512) — the
+subject for `ncu --set full` captures and quick CUDA-event timings.  usage: kernel_micro.py <name> [reps]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from unet_b200 import ops
+
+name = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+B, H, W = 64, 512, 512
+M = B * H * W
+bf = torch.bfloat16
+dev = "cuda"
+
+
+def rnd(*shape, dtype=bf):
+    return (torch.rand(shape, device=dev) - 0.5).to(dtype)
+
+
+def run(fn, nbytes):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name}: {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s")
+
+
+if name == "gemm64":          # pointwise 64->64 forward with BN statistics (enc1_block2 / dec1_block2)
+    A, Bt, C = rnd(M, 64), rnd(64, 64), torch.empty((M, 64), device=dev, dtype=bf)
+    cs = torch.zeros(64, device=dev, dtype=torch.float64); cq = torch.zeros_like(cs)
+    run(lambda: ops.gemm(A, Bt, C, b_trans=True, epilogue=ops.EPI_STATS, colsum=cs, colsq=cq), 2 * M * 64 * 2)
+elif name == "gemm64_none":
+    A, Bt, C = rnd(M, 64), rnd(64, 64), torch.empty((M, 64), device=dev, dtype=bf)
+    run(lambda: ops.gemm(A, Bt, C, b_trans=True), 2 * M * 64 * 2)
+elif name == "gemm128_64":    # dec1_block1 pointwise 128->64
+    A, Bt, C = rnd(M, 128), rnd(64, 128), torch.empty((M, 64), device=dev, dtype=bf)
+    run(lambda: ops.gemm(A, Bt, C, b_trans=True), M * 192 * 2)
+elif name == "convt":         # dec1_upsample
+    x, Bt = rnd(B, 256, 256, 128), rnd(256, 128)
+    cat = torch.empty((B, 512, 512, 128), device=dev, dtype=bf)
+    bias = torch.zeros(64, device=dev)
+    run(lambda: ops.gemm(x, Bt, cat[..., :64], b_trans=True, epilogue=ops.EPI_CONVT, shift=bias, convt_hw=(256, 256)),
+        (x.numel() + M * 64) * 2)
+elif name == "wgrad64":
+    A, Bm, C = rnd(M, 64), rnd(M, 64), torch.zeros((64, 64), device=dev)
+    run(lambda: ops.gemm(A, Bm, C, a_trans=True, accumulate=True), 2 * M * 64 * 2)
+elif name == "dw_fwd":
+    x, y, w = rnd(B, H, W, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf), torch.rand((9, 64), device=dev)
+    run(lambda: ops.dwconv3x3(x, w, y), 2 * M * 64 * 2)
+elif name == "dw_bwd_w":
+    x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
+    run(lambda: ops.dwconv3x3_bwd_weight(x, dy, dw), 2 * M * 64 * 2)
+elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
+    z, dy, dz = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf)
+    v = lambda: torch.rand(64, device=dev)
+    sc, sh, mu, rs, dg, db = v(), v(), v(), v(), torch.zeros(64, device=dev), torch.zeros(64, device=dev)
+    if name == "bn_bwd_reduce":
+        run(lambda: ops.bn_bwd_reduce(dy, z, sc, sh, mu, rs, dg, db), 2 * M * 64 * 2)
+    elif name == "bn_bwd_apply":
+        run(lambda: ops.bn_bwd_apply(dy, z, sc, sh, mu, rs, dg, db, dz), 3 * M * 64 * 2)
+    else:
+        run(lambda: ops.bn_act(z, sc, sh, dz), 2 * M * 64 * 2)
+else:
+    raise SystemExit(f"unknown kernel {name}")

@@ -8,12 +8,8 @@
 //   gemm_tc_nt_kernel    C[M,N] = A[M,K] * Bt[N,K]^T      both operands K-major (forward, data gradient)
 //   gemm_tc_wgrad_kernel C[Mo,No] += A[P,Mo]^T * B[P,No]   both operands MN-major (weight gradient, split over P)
 //
-// Warp roles (256 threads, 1 CTA/SM, persistent over output tiles):
-//   warp 0   TMA producer   (one thread)      smem ring of kStages {A 128x64, B BLOCK_Nx64} bf16 tiles, SWIZZLE_128B
-//   warp 1   MMA issuer     (one thread)      tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16, fp32 accumulate
-//   warp 2   TMEM allocator                   2 accumulator stages x BLOCK_N columns
-//   warps 4-7 epilogue                        tcgen05.ld -> fp32 staging slab in smem (per warp, padded) -> each lane owns
-//                                             4 fixed columns: scale/shift/ReLU/bias/stats in registers -> coalesced stores
+// Warp roles are described at each kernel.  The weight-gradient kernel keeps a slab epilogue (TMEM -> padded fp32 slab ->
+// lane owns 4 fixed columns -> fp32 atomics); the NT kernel stages bf16 rows for TMA stores.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -178,18 +174,61 @@ __device__ __forceinline__ void stats_flush(const TcParams& p, int lane, int64_t
 }
 
 // ------------------------------------------------------------------------------------------------ NT kernel
+// Warp roles (384 threads, 1 CTA/SM, persistent over output tiles):
+//   warp 0      TMA producer (one thread)   smem ring of NtCfg::kStages {A 128x64, B BLOCK_Nx64} bf16 tiles, SWIZZLE_128B
+//   warp 1      MMA issuer   (one thread)   tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16, fp32 accumulators in TMEM
+//   warp 2      TMEM allocator              2 accumulator stages x BLOCK_N columns
+//   warps 4-7   epilogue group 0            tiles 0, 2, 4, ... of this CTA (accumulator stage 0)
+//   warps 8-11  epilogue group 1            tiles 1, 3, 5, ... (accumulator stage 1)
+// Epilogue (per group, 128 threads, thread = accumulator row): tcgen05.ld 32 columns -> scale/shift/ReLU/bias/dropout in
+// registers -> bf16 (or fp32) rows into a 128B-swizzled staging tile (conflict-free 16 B shared stores) -> ONE TMA
+// store per 128-byte-wide column chunk (2-D box for row-major C, 5-D box for the Conv2DTranspose pixel shuffle, so the
+// scatter into the concat buffer costs no address arithmetic) -> BN batch statistics re-read column-wise from the
+// staged tile (one shared load per row per lane, fp32 sums kept in registers across tiles).  Staging is double
+// buffered per group, so the store of chunk c overlaps the math of chunk c+1 and the other group's tile.
+constexpr int kNumEpiGroups = 2;
+constexpr int kStageTileBytes = 128 * 128;       // 128 rows x 128 B
+
+template <int BLOCK_N> struct NtCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5);
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kParBytes = kNumEpiGroups * 2 * BLOCK_N * 4;        // per group: scale[BLOCK_N], shift[BLOCK_N]
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kNumEpiGroups * 2 * kStageTileBytes + kParBytes + 256;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
 template <int BLOCK_N, bool OUT_BF16>
-__global__ void __launch_bounds__(256, 1)
-gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+__global__ void __launch_bounds__(384, 1)
+gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  using Cfg = NtCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kChunks = BLOCK_N / 64;
+  constexpr int CW = OUT_BF16 ? 64 : 32;          // output columns per 128-byte staging row
+  constexpr int kChunks = BLOCK_N / CW;
+  constexpr int CPL = CW / 32;                    // statistic columns owned by a lane per chunk
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-  uint8_t* slabs = smem + kStages * Cfg::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(slabs + kNumEpiWarps * kSlabBytes);
+  uint8_t* stage_tiles = smem + kStages * Cfg::kStageBytes;                                // [group][2][16 KB]
+  float* s_par = reinterpret_cast<float*>(stage_tiles + kNumEpiGroups * 2 * kStageTileBytes);  // [group][2][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_par) + Cfg::kParBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -200,10 +239,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_k = (int)((p.K + kBlockK - 1) / kBlockK);
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], kNumEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::kTmemCols); tmem_relinquish(); }
@@ -250,39 +289,168 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;                       // == warp % 4: the TMEM lane quarter this warp may read
-    uint8_t* slab = slabs + q * kSlabBytes;
-    float st_sum[kChunks][4], st_sq[kChunks][4];
+    const int g = (warp - 4) >> 2;                // epilogue group = accumulator stage
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                // accumulator row of this thread inside the tile
+    const int gtid = (warp - 4 - 4 * g) * 32 + lane;
+    const bool issuer = gtid == 0;
+    uint8_t* tiles = stage_tiles + g * 2 * kStageTileBytes;
+    float* par_scale = s_par + g * 2 * BLOCK_N;
+    float* par_shift = par_scale + BLOCK_N;
+    const int epi = p.epilogue;
+    const bool affine = epi == UNET_EPI_AFFINE || epi == UNET_EPI_AFFINE_RELU || epi == UNET_EPI_CONVT;
+    const bool relu = epi == UNET_EPI_AFFINE_RELU;
+    const bool stats = epi == UNET_EPI_STATS;
+    const uint32_t seed = p.drop_on ? p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u) : 0u;
+    // Conv2DTranspose: tile rows are input pixels (q = image*H + i, j); the box covers bj columns x bq rows of them
+    const int cw = p.convt_W, bj = cw < kBlockM ? cw : kBlockM;
+    float st_sum[kChunks][CPL], st_sq[kChunks][CPL];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { st_sum[c][j] = 0.f; st_sq[c][j] = 0.f; }
-    int it = 0, last_n_blk = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int j = 0; j < CPL; ++j) { st_sum[c][j] = 0.f; st_sq[c][j] = 0.f; }
+    const uint32_t sw = (uint32_t)(row & 7);
+    int last_n_blk = -1, chunk_ctr = 0;
+
+    auto flush_stats = [&](int n_blk_) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          const int64_t n = (int64_t)n_blk_ * BLOCK_N + c * CW + lane * CPL + j;
+          if (n < p.N) { atomicAdd(p.colsum + n, (double)st_sum[c][j]); atomicAdd(p.colsq + n, (double)st_sq[c][j]); }
+          st_sum[c][j] = 0.f; st_sq[c][j] = 0.f;
+        }
+    };
+
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-      if (p.epilogue == UNET_EPI_STATS && last_n_blk >= 0 && last_n_blk != n_blk) {
-#pragma unroll
-        for (int c = 0; c < kChunks; ++c) stats_flush(p, lane, (int64_t)last_n_blk * BLOCK_N + c * 64, st_sum[c], st_sq[c]);
+      if (n_blk != last_n_blk) {
+        if (stats && last_n_blk >= 0) flush_stats(last_n_blk);
+        if (affine) {
+          named_bar_sync(1 + g, 128);             // nobody still reads the previous tile's parameters
+          for (int i = gtid; i < BLOCK_N; i += 128) {
+            const int64_t n = (int64_t)n_blk * BLOCK_N + i;
+            float sc = 1.f, sh = 0.f;
+            if (n < p.N) {
+              if (epi == UNET_EPI_CONVT) { if (p.shift) sh = __ldg(p.shift + (n % p.convt_cout)); }
+              else { if (p.scale) sc = __ldg(p.scale + n); if (p.shift) sh = __ldg(p.shift + n); }
+            }
+            par_scale[i] = sc; par_shift[i] = sh;
+          }
+          // visibility is provided by the first named barrier of the chunk loop below
+        }
+        last_n_blk = n_blk;
       }
-      last_n_blk = n_blk;
-      const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full[acc], acc_phase);
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[g], acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
-      const int64_t row0 = (int64_t)m_blk * kBlockM + q * 32;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N;
+      const int m0 = m_blk * kBlockM;
 #pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int64_t n_base = (int64_t)n_blk * BLOCK_N + c * 64;
-        epilogue_chunk<OUT_BF16>(p, t_addr + c * 64, slab, lane, row0, n_base, st_sum[c], st_sq[c]);
+      for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
+        uint8_t* buf = tiles + (chunk_ctr & 1) * kStageTileBytes;
+        const int n_base = n_blk * BLOCK_N + c * CW;
+        if (n_base >= p.N) break;                 // uniform: ragged last N tile
+        if (issuer) bulk_wait_read<1>();          // the store that last used `buf` (two chunks ago) has read it
+        named_bar_sync(1 + g, 128);
+        uint8_t* my_row = buf + row * 128;
+        // Conv2DTranspose destination of this thread's row (dropout indexes the destination element)
+        uint64_t drop_base = 0;
+        int cv_a = 0, cv_b = 0, co0 = 0;
+        if (epi == UNET_EPI_CONVT) {
+          const uint32_t cc = (uint32_t)p.convt_cout;
+          const uint32_t ab = (uint32_t)n_base / cc;
+          co0 = (int)((uint32_t)n_base - ab * cc); cv_a = (int)(ab >> 1); cv_b = (int)(ab & 1);
+          if (p.drop_on) {
+            const uint32_t m32 = (uint32_t)(m0 + row), qq = m32 / (uint32_t)cw, jj = m32 - qq * (uint32_t)cw;
+            const uint64_t pix = ((uint64_t)(2 * qq + cv_a)) * (uint64_t)(2 * cw) + 2 * jj + cv_b;
+            drop_base = pix * (uint64_t)p.ctot + (uint64_t)p.c0 + (uint64_t)co0;
+          }
+        }
+#pragma unroll
+        for (int half = 0; half < CW / 32; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c * CW + half * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (affine) {
+            const float* ps = par_scale + c * CW + half * 32;
+            const float* ph = par_shift + c * CW + half * 32;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {     // warp-uniform addresses: broadcast shared loads
+              const float4 s4 = *reinterpret_cast<const float4*>(ps + i);
+              const float4 h4 = *reinterpret_cast<const float4*>(ph + i);
+              v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
+              v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
+            }
+            if (relu) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (p.drop_on) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= dropout_mult(drop_base + half * 32 + i, seed, p.keep, p.inv_keep);
+            }
+          }
+          if (OUT_BF16) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {         // 4 x 16 B = 32 bf16 columns; chunk index = half*4 + j
+              const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                         pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+              *reinterpret_cast<uint4*>(my_row + ((((uint32_t)(half * 4 + j)) ^ sw) << 4)) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {         // 8 x 16 B = 32 fp32 columns
+              const uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                         __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+              *reinterpret_cast<uint4*>(my_row + ((((uint32_t)j) ^ sw) << 4)) = o;
+            }
+          }
+        }
+        if (c == kChunks - 1 || n_base + CW >= p.N) {   // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[g]);
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + g, 128);
+        if (issuer) {
+          if (epi == UNET_EPI_CONVT) {
+            const int q0 = m0 / cw, j0 = m0 - q0 * cw;
+            tma_store_5d(&tmC, buf, co0, j0, q0, cv_b, cv_a);
+          } else {
+            tma_store_2d(&tmC, buf, n_base, m0);
+          }
+          bulk_commit();
+        }
+        if (stats) {
+          // column sums over this warp's 32 rows, from the values as stored; lane owns CPL adjacent columns
+          const uint8_t* wrows = buf + (q * 32) * 128;
+          float s0 = 0.f, q0s = 0.f, s1 = 0.f, q1s = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            if (m0 + q * 32 + rr >= p.M) break;   // rows past M hold zero-filled operand garbage-free zeros, but skip anyway
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(wrows + rr * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(rr & 7)) << 4) + ((lane & 3) << 2));
+            if (OUT_BF16) {
+              const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
+              s0 += a; q0s = fmaf(a, a, q0s); s1 += b; q1s = fmaf(b, b, q1s);
+            } else {
+              const float a = __uint_as_float(w);
+              s0 += a; q0s = fmaf(a, a, q0s);
+            }
+          }
+          st_sum[c][0] += s0; st_sq[c][0] += q0s;
+          if (CPL == 2) { st_sum[c][CPL - 1] += s1; st_sq[c][CPL - 1] += q1s; }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    if (p.epilogue == UNET_EPI_STATS && last_n_blk >= 0) {
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) stats_flush(p, lane, (int64_t)last_n_blk * BLOCK_N + c * 64, st_sum[c], st_sq[c]);
-    }
+    if (stats && last_n_blk >= 0) flush_stats(last_n_blk);
+    if (issuer) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -411,9 +579,42 @@ static void fill_params(TcParams& p, const unet_gemm_args* a) {
   }
 }
 
+// C as a TMA store target.  Row-major C[M,N] (ptr, ldc): 2-D {N, M}, box {128 B of columns, 128 rows}.
+// Conv2DTranspose: destination [Nimg, 2H, 2W, ldc] seen as 5-D {co, j, q = image*H + i, b, a} so that one box of
+// {128 B of channels, bj input columns, 128/bj input rows} lands on the pixels (2i+a, 2j+b) of the upsampled image.
+static int make_c_tmap(CUtensorMap* map, const unet_gemm_args* a, const char* who) {
+  PFN_encodeTiled fn = get_encode_fn();
+  UNET_REQUIRE(fn, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  const bool bf = a->out_dtype == UNET_BF16;
+  const cuuint64_t es = bf ? 2 : 4;
+  const cuuint32_t cwid = bf ? 64u : 32u;
+  UNET_REQUIRE((a->ldc * es) % 16 == 0, UNET_EALIGN, "%s: C row pitch must be a multiple of 16 bytes", who);
+  const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r;
+  if (a->epilogue == UNET_EPI_CONVT) {
+    const cuuint64_t W = a->convt_W, H = a->convt_H, cout = a->N / 4, nimg = a->M / ((int64_t)a->convt_H * a->convt_W);
+    const cuuint32_t bj = (cuuint32_t)(W < (cuuint64_t)kBlockM ? W : kBlockM), bq = kBlockM / bj;
+    cuuint64_t dims[5] = {cout, W, nimg * H, 2, 2};
+    cuuint64_t strides[4] = {2 * a->ldc * es, 4 * W * a->ldc * es, a->ldc * es, 2 * W * a->ldc * es};
+    cuuint32_t box[5] = {cwid, bj, bq, 1u, 1u};
+    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    r = fn(map, dt, 5, a->C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[2] = {(cuuint64_t)a->N, (cuuint64_t)a->M};
+    cuuint64_t strides[1] = {a->ldc * es};
+    cuuint32_t box[2] = {cwid, (cuuint32_t)kBlockM};
+    cuuint32_t estr[2] = {1u, 1u};
+    r = fn(map, dt, 2, a->C, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled(C) failed with CUresult %d", who, (int)r);
+  return UNET_OK;
+}
+
 template <int BLOCK_N, bool OUT_BF16>
-static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
+static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st) {
+  using Cfg = NtCfg<BLOCK_N>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -424,7 +625,7 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   const unsigned grid = (unsigned)i64min(tiles, sm_count());
-  gemm_tc_nt_kernel<BLOCK_N, OUT_BF16><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  gemm_tc_nt_kernel<BLOCK_N, OUT_BF16><<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, p);
   UNET_LAUNCH_CHECK("gemm_tc_nt");
   return UNET_OK;
 }
@@ -468,8 +669,12 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   UNET_REQUIRE(!a->shift || aligned16(a->shift), UNET_EALIGN, "gemm_tc: shift must be 16B aligned");
   if (a->epilogue == UNET_EPI_CONVT)
     UNET_REQUIRE(a->M < (int64_t)1 << 31, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs M < 2^31");
-  if (a->epilogue == UNET_EPI_CONVT)
+  if (a->epilogue == UNET_EPI_CONVT) {
     UNET_REQUIRE((a->N / 4) % 64 == 0, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs Cout%%64==0 (got %lld)", (long long)(a->N / 4));
+    const int w = a->convt_W;   // a 128-row tile must be a whole box of input pixels: W | 128 or 128 | W
+    UNET_REQUIRE(w > 0 && (w >= kBlockM ? w % kBlockM == 0 : kBlockM % w == 0), UNET_EUNSUPPORTED,
+                 "gemm_tc: CONVT needs the input width to divide 128 or be a multiple of it (got %d)", w);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   TcParams p{};
   fill_params(p, a);
@@ -482,10 +687,12 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
     UNET_REQUIRE(a->K % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: K must be a multiple of 8 (got %lld)", (long long)a->K);
     if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A)")) return e;
     if (int e = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, bn, "gemm_tc(B)")) return e;
+    CUtensorMap tmC;
+    if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
     const bool ob = a->out_dtype == UNET_BF16;
-    if (bn == 256) return ob ? launch_nt<256, true>(tmA, tmB, p, st) : launch_nt<256, false>(tmA, tmB, p, st);
-    if (bn == 128) return ob ? launch_nt<128, true>(tmA, tmB, p, st) : launch_nt<128, false>(tmA, tmB, p, st);
-    return ob ? launch_nt<64, true>(tmA, tmB, p, st) : launch_nt<64, false>(tmA, tmB, p, st);
+    if (bn == 256) return ob ? launch_nt<256, true>(tmA, tmB, tmC, p, st) : launch_nt<256, false>(tmA, tmB, tmC, p, st);
+    if (bn == 128) return ob ? launch_nt<128, true>(tmA, tmB, tmC, p, st) : launch_nt<128, false>(tmA, tmB, tmC, p, st);
+    return ob ? launch_nt<64, true>(tmA, tmB, tmC, p, st) : launch_nt<64, false>(tmA, tmB, tmC, p, st);
   }
   // weight gradient: C[M,N] += A[K,M]^T * B[K,N]
   UNET_REQUIRE(a->b_trans == 0 && a->accumulate == 1, UNET_EUNSUPPORTED, "gemm_tc: a_trans=1 needs b_trans=0 and accumulate=1");

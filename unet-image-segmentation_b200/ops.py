@@ -194,7 +194,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = 
     tc_ok = (A.dtype == torch.bfloat16 and N % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and ldc % 4 == 0
              and ((not a_trans and b_trans and not accumulate and K % 8 == 0)
                   or (a_trans and not b_trans and accumulate and M % 8 == 0))
-             and (epilogue != EPI_CONVT or (N // 4) % 64 == 0))
+             and (epilogue != EPI_CONVT or ((N // 4) % 64 == 0 and convt_hw[1] > 0 and
+                                           (128 % convt_hw[1] == 0 or convt_hw[1] % 128 == 0))))
     use_tc = tc_ok if tensor_core is None else tensor_core
     csz = Cm.numel() * Cm.element_size()
     _call("unet_gemm_tc" if use_tc else "unet_gemm_simt", C.byref(args), _stream(),

@@ -88,7 +88,7 @@ def test_train_step_fp32(cfg):
         w1, _, _ = R.adamw_step(w0[n], g, np.zeros_like(g), np.zeros_like(g), 1)
         got = eng.wview(n).cpu().numpy().reshape(g.shape)
         # a parameter moves by ~lr on the first step whatever |g| is; sign(g) is what must agree where g is not ~0
-        big = np.abs(g) > 1e-6 * (np.abs(g).max() + 1e-30)
+        big = np.abs(g) > 0.2 * (np.abs(g).mean() + 1e-30)
         np.testing.assert_allclose(got[big], w1[big], rtol=0, atol=2e-4)
 
 

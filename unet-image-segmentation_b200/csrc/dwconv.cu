@@ -466,6 +466,154 @@ __global__ void dwconv3x3_bwd_weight_scalar_kernel(const T* __restrict__ x, int6
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient, TMA strips
+// Same strip decomposition as the forward kernel, two TMA streams per stage: x with its column halo (rows h0-1 ..)
+// and dy one row ahead (rows h0 ..).  512 consumer threads: a thread owns 8 B of channels of one column, keeps the
+// 9 tap accumulators of those channels in registers for the whole strip and the three live dy rows in a register
+// window; per input row it does 4 conflict-free 8-byte shared loads and 9 FMAs per channel.  The strip's partial
+// sums are folded with one shuffle, shared-memory atomics across the 16 warps, then 9 x 128 B of global atomics.
+template <typename T> struct WgCfg {
+  static constexpr int NV = 8 / (int)sizeof(T);          // channels per thread
+  static constexpr int CB = 128 / (int)sizeof(T);        // channels per CTA
+  static constexpr int TW = 32, RH = 4, S = 5;
+  static constexpr int kXBytes = RH * (TW + 2) * 128;
+  static constexpr int kDBytes = RH * TW * 128;
+  static constexpr int kStageBytes = kXBytes + kDBytes;
+  static constexpr int kSmemBytes = S * kStageBytes + 9 * CB * 4 + 2 * S * 8 + 128;
+};
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float (&v)[8 / sizeof(T)]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void unpack8<float>(const uint2& r, float (&v)[2]) {
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(512, 1)
+dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
+                             float* __restrict__ dw9c, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb) {
+  using Cfg = WgCfg<T>;
+  constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* s_acc = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);       // [9][CB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_acc + 9 * Cfg::CB);
+  uint64_t* empty_bar = full_bar + S;
+
+  int item = blockIdx.x;
+  const int cb = item % ncb; item /= ncb;
+  const int tw = item % ntw; item /= ntw;
+  const int hs = item % nseg;
+  const int n = item / nseg;
+  const int c0 = cb * Cfg::CB, w0 = tw * TW;
+  const int h0 = hs * seg_rows, h1 = min(H, h0 + seg_rows);
+  const int nst = (h1 - h0 + 2 + RH - 1) / RH;          // x rows h0-1 .. h1
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < 9 * Cfg::CB; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 16); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {
+    const int s = k % S;
+    if (k >= S) mbar_wait(&empty_bar[s], ((k / S) - 1) & 1);
+    mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+    uint8_t* st = smem + s * Cfg::kStageBytes;
+    tma_load_4d(st, &tmX, &full_bar[s], c0, w0 - 1, h0 - 1 + k * RH, n, kEvictNormal);
+    tma_load_4d(st + Cfg::kXBytes, &tmD, &full_bar[s], c0, w0, h0 + k * RH, n, kEvictNormal);
+  };
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmD);
+    for (int k = 0; k < S - 1 && k < nst; ++k) issue(k);
+  }
+
+  const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
+  float acc[9][NV], dm[NV], d0[NV];
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc[i][j] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) { dm[j] = 0.f; d0[j] = 0.f; }
+  const uint32_t xoff = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+
+  for (int k = 0; k < nst; ++k) {
+    const int s = k % S;
+    if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
+    mbar_wait(&full_bar[s], (k / S) & 1);
+    const uint8_t* sx = smem + s * Cfg::kStageBytes + xoff;
+    const uint8_t* sd = smem + s * Cfg::kStageBytes + Cfg::kXBytes + xoff;
+#pragma unroll
+    for (int rr = 0; rr < RH; ++rr) {
+      const int q = h0 - 1 + k * RH + rr;           // x row; dy row q+1 sits at the same stage row
+      if (q > h1) break;
+      float a[NV], b[NV], c[NV], dp[NV];
+      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128), a);
+      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 128), b);
+      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 256), c);
+      if (q + 1 < h1) unpack8<T>(*reinterpret_cast<const uint2*>(sd + rr * TW * 128), dp);
+      else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) dp[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        // kernel row r multiplies input row q into output row q - r + 1
+        acc[0][j] = fmaf(a[j], dp[j], acc[0][j]); acc[1][j] = fmaf(b[j], dp[j], acc[1][j]); acc[2][j] = fmaf(c[j], dp[j], acc[2][j]);
+        acc[3][j] = fmaf(a[j], d0[j], acc[3][j]); acc[4][j] = fmaf(b[j], d0[j], acc[4][j]); acc[5][j] = fmaf(c[j], d0[j], acc[5][j]);
+        acc[6][j] = fmaf(a[j], dm[j], acc[6][j]); acc[7][j] = fmaf(b[j], dm[j], acc[7][j]); acc[8][j] = fmaf(c[j], dm[j], acc[8][j]);
+        dm[j] = d0[j]; d0[j] = dp[j];
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // lanes l and l^16 hold the same channels of neighbouring columns
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float v = acc[i][j] + __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+      if (lane < 16) atomicAdd(&s_acc[i * Cfg::CB + cg * NV + j], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * Cfg::CB; i += blockDim.x) {
+    const int tap = i / Cfg::CB, ch = c0 + i % Cfg::CB;
+    if (ch < C) atomicAdd(&dw9c[(int64_t)tap * C + ch], s_acc[i]);
+  }
+}
+
+template <typename T>
+static int dw_wgrad_strip_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c, int N, int H, int W, int C,
+                                 cudaStream_t st) {
+  using Cfg = WgCfg<T>;
+  CUtensorMap tmX, tmD;
+  if (int e = make_nhwc_tmap<T>(&tmX, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_bwd_weight(x)")) return e;
+  if (int e = make_nhwc_tmap<T>(&tmD, dy, lddy, N, H, W, C, Cfg::TW, Cfg::RH, "dwconv3x3_bwd_weight(dy)")) return e;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_wgrad_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return set_cuda_error(e, "dwconv3x3_bwd_weight: cudaFuncSetAttribute");
+    attr_done = true;
+  }
+  const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
+  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 4);
+  const int nseg = (int)ceil_div(H, seg);
+  const int64_t items = (int64_t)N * nseg * ntw * ncb;
+  UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd_weight: too many strips");
+  dwconv3x3_wgrad_strip_kernel<T><<<(unsigned)items, 512, Cfg::kSmemBytes, st>>>(tmX, tmD, dw9c, H, W, C, seg, nseg, ntw, ncb);
+  UNET_LAUNCH_CHECK("dwconv3x3_bwd_weight(strip)");
+  return UNET_OK;
+}
+
 // C <= 4 (the RGB input image): one thread per (image, row segment, column), all channels, 9*C register accumulators,
 // warp shuffle -> shared -> one global atomic per (tap, channel) per block.
 template <typename T, int CC>
@@ -539,6 +687,9 @@ static int dw_bwd_weight_launch(const void* x, int64_t ldx, const void* dy, int6
   const int cv = C / 4;
   const bool vec = (C % 4 == 0) && (ldx % 8 == 0) && (lddy % 8 == 0) && aligned16(x) && aligned16(dy) &&
                    (256 % cv == 0 || cv % 256 == 0) && (9 * C * 4 <= 160 * 1024);
+  constexpr int kNV = 8 / (int)sizeof(T);
+  if ((C % kNV == 0) && ((ldx * sizeof(T)) % 16 == 0) && ((lddy * sizeof(T)) % 16 == 0) && aligned16(x) && aligned16(dy) && C >= 8)
+    return dw_wgrad_strip_launch<T>(x, ldx, dy, lddy, dw9c, N, H, W, C, st);
   if (vec) {
     const int R = 32;
     const int nseg = (int)ceil_div(H, R);

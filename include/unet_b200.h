@@ -97,6 +97,16 @@ int unet_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w9c, void* y, in
 int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c,
                               int N, int H, int W, int C, int dtype, void* stream);
 
+/* ---- first conv_block, fused (enc1_block1_sepconv on the RGB image, u_net.py:14-20,63-66; Cin = 3, Cout = 64 only) ---- */
+/* out = pw(dw(x)) [* scale + shift, ReLU if relu]; x contiguous [N,H,W,3]; with colsum/colsq also the BN batch statistics
+   of the stored values.  UNET_EUNSUPPORTED for other channel counts (callers then use dwconv3x3_fwd + gemm). */
+int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, void* out, int64_t ldo,
+                  int N, int H, int W, int Cin, int Cout, int dtype,
+                  const float* scale, const float* shift, int relu, double* colsum, double* colsq, void* stream);
+/* given dz = gradient w.r.t. pw(dw(x)): dwp[3,64] += d^T dz (d = dw(x) recomputed on chip), dwd9c[3,3,3] += x (*) (dz Wp^T) */
+int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const float* wd9c, const float* wp,
+                  float* dwd9c, float* dwp, int N, int H, int W, int Cin, int Cout, int dtype, void* stream);
+
 /* ---- dense contractions: SeparableConv2D pointwise half, Conv2DTranspose, their gradients ---- */
 /* fp32-exact CUDA-core path (any shape, either dtype) */
 int unet_gemm_simt(const unet_gemm_args* args, void* stream);

@@ -91,6 +91,39 @@ def test_dwconv_bwd_weight(dtype, shape):
     np.testing.assert_allclose(host(dw).reshape(3, 3, -1), ref, rtol=1e-4, atol=1e-3 * np.sqrt(np.prod(shape[:3])))
 
 
+# ------------------------------------------------------------------------------------------------ fused first block
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 32), (3, 21, 45), (1, 64, 64)])
+def test_stem_fwd_bwd(dtype, shape):
+    n, h, w = shape
+    x = RNG.random((n, h, w, 3)).astype(np.float32)
+    wd = RNG.standard_normal((3, 3, 3)).astype(np.float32)
+    wp = RNG.standard_normal((3, 64)).astype(np.float32)
+    dz = RNG.standard_normal((n, h, w, 64)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, 64).astype(np.float32); sh = RNG.standard_normal(64).astype(np.float32)
+    xr, dzr = (bf16_round(x), bf16_round(dz)) if dtype == torch.bfloat16 else (x.astype(np.float64), dz.astype(np.float64))
+    d = R.dwconv3x3(xr, wd.astype(np.float64))
+    z = d.reshape(-1, 3) @ wp.astype(np.float64)
+    xd = dev(x, dtype)
+    out = torch.empty((n, h, w, 64), device="cuda", dtype=dtype)
+    cs = torch.zeros(64, device="cuda", dtype=torch.float64); cq = torch.zeros_like(cs)
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), out, colsum=cs, colsq=cq)
+    got = host(out).reshape(-1, 64)
+    np.testing.assert_allclose(got, z, **tol(dtype))
+    np.testing.assert_allclose(cs.cpu().numpy(), got.sum(0), rtol=1e-4, atol=1e-2)
+    np.testing.assert_allclose(cq.cpu().numpy(), (got ** 2).sum(0), rtol=1e-4, atol=1e-2)
+    buf = torch.zeros((n, h, w, 128), device="cuda", dtype=dtype)
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), buf[..., 64:], scale=dev(sc), shift=dev(sh), relu=True)
+    np.testing.assert_allclose(host(buf)[..., 64:].reshape(-1, 64), np.maximum(z * sc + sh, 0), **tol(dtype))
+    assert np.all(host(buf)[..., :64] == 0)
+    gwd = torch.zeros((9, 3), device="cuda"); gwp = torch.zeros((3, 64), device="cuda")
+    ops.stem_bwd(xd, dev(dz, dtype), dev(wd.reshape(9, 3)), dev(wp), gwd, gwp)
+    dd = (dzr.reshape(-1, 64) @ wp.astype(np.float64).T).reshape(n, h, w, 3)
+    _, gwd_ref = R.dwconv3x3_bwd(xr, wd.astype(np.float64), dd)
+    np.testing.assert_allclose(host(gwp), d.reshape(-1, 3).T @ dzr.reshape(-1, 64), rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(host(gwd).reshape(3, 3, 3), gwd_ref, rtol=1e-3, atol=1e-2)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM, CUDA cores
 @pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("mkn", [(70, 3, 64), (129, 40, 33), (64, 64, 1), (256, 128, 96)])

@@ -108,7 +108,26 @@ bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ BN backward
-// thread layout inside a block: (rows = 256/cv) x cv, each thread owns 8 channels and strides over rows.
+// thread layout inside a block: (rows = 256/cv) x cv, each thread owns 8 channels and strides over rows, kUnroll rows
+// per trip with all loads issued before the first use (2*kUnroll 16-byte loads in flight per thread).
+constexpr int kBnUnroll = 4;
+
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+template <> struct Raw8<float> { float4 a, b; };
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.a = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void unraw(const Raw8<__nv_bfloat16>& r, float (&v)[8]) {
+  const uint32_t u[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void unraw(const Raw8<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ z,
@@ -125,24 +144,36 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict
   float sc[8], sh[8], mu[8], rs[8];
   const bool norm = mean != nullptr;
   if (norm) { load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(rstd + c0, rs); }
+  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
   float sg[8], sgx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sg[j] = 0.f; sgx[j] = 0.f; }
-  for (int64_t r = blockIdx.x * (int64_t)rows_per_block + r_in; r < M; r += (int64_t)gridDim.x * rows_per_block) {
-    float g[8], zz[8];
-    load8(dy + r * lddy + c0, g);
-    load8(z + r * C + c0, zz);
-    if (dp.on) {
-      const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
+  const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+  for (int64_t r0 = blockIdx.x * (int64_t)rows_per_block + r_in; r0 < M; r0 += stride * kBnUnroll) {
+    Raw8<T> rg[kBnUnroll], rz[kBnUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < M) { ldraw(dy + r * lddy + c0, rg[u]); ldraw(z + r * C + c0, rz[u]); }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float act = norm ? fmaf(zz[j], sc[j], sh[j]) : zz[j];
-      const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
-      sg[j] += gj;
-      if (norm) sgx[j] = fmaf(gj, (zz[j] - mu[j]) * rs[j], sgx[j]);
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= M) break;
+      float g[8], zz[8];
+      unraw(rg[u], g); unraw(rz[u], zz);
+      if (dp.on) {
+        const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float act = norm ? fmaf(zz[j], sc[j], sh[j]) : zz[j];
+        const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
+        sg[j] += gj;
+        if (norm) sgx[j] = fmaf(gj, (zz[j] - mu[j]) * rs[j], sgx[j]);
+      }
     }
   }
 #pragma unroll
@@ -165,35 +196,56 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict_
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, T* __restrict__ dz,
                     int64_t M, int C, int relu, float inv_m, DropArgs dp) {
   const int cv = C >> 3;
-  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int c0 = (int)(t % cv) << 3;
-  const int64_t r = t / cv;
-  if (r >= M) return;
+  const int rows_per_block = blockDim.x / cv;
+  const int c0 = (threadIdx.x % cv) << 3;
+  const int r_in = threadIdx.x / cv;
   const bool norm = mean != nullptr;
-  float g[8], zz[8], o[8];
-  load8(dy + r * lddy + c0, g);
-  load8(z + r * C + c0, zz);
-  if (dp.on) {
-    const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
-  }
+  // dz = sc*(g - dbeta/M - (zz-mu)*rs*dgamma/M) = sc*g - k1 - zz*k2  with  k2 = sc*rs*dgamma/M,  k1 = sc*dbeta/M - mu*k2
+  float sc[8], sh[8], k1[8], k2[8];
   if (norm) {
-    float sc[8], sh[8], mu[8], rs[8], dg[8], db[8];
+    float mu[8], rs[8], dg[8], db[8];
     load8(scale + c0, sc); load8(shift + c0, sh); load8(mean + c0, mu); load8(rstd + c0, rs);
     load8(dgamma + c0, dg); load8(dbeta + c0, db);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float act = fmaf(zz[j], sc[j], sh[j]);
-      const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
-      const float xh = (zz[j] - mu[j]) * rs[j];
-      o[j] = sc[j] * (gj - db[j] * inv_m - xh * dg[j] * inv_m);
+      k2[j] = sc[j] * rs[j] * dg[j] * inv_m;
+      k1[j] = sc[j] * db[j] * inv_m - mu[j] * k2[j];
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = (relu && !(zz[j] > 0.f)) ? 0.f : g[j];
   }
-  store8(dz + r * C + c0, o);
+  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
+  const int64_t stride = (int64_t)gridDim.x * rows_per_block;
+  for (int64_t r0 = blockIdx.x * (int64_t)rows_per_block + r_in; r0 < M; r0 += stride * kBnUnroll) {
+    Raw8<T> rg[kBnUnroll], rz[kBnUnroll];
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r < M) { ldraw(dy + r * lddy + c0, rg[u]); ldraw(z + r * C + c0, rz[u]); }
+    }
+#pragma unroll
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const int64_t r = r0 + u * stride;
+      if (r >= M) break;
+      float g[8], zz[8], o[8];
+      unraw(rg[u], g); unraw(rz[u], zz);
+      if (dp.on) {
+        const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+      }
+      if (norm) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float act = fmaf(zz[j], sc[j], sh[j]);
+          const float gj = (relu && !(act > 0.f)) ? 0.f : g[j];
+          o[j] = fmaf(sc[j], gj, -fmaf(zz[j], k2[j], k1[j]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (relu && !(zz[j] > 0.f)) ? 0.f : g[j];
+      }
+      store8(dz + r * C + c0, o);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ max pooling
@@ -515,7 +567,7 @@ extern "C" int unet_bn_bwd_reduce(const void* dy, int64_t lddy, const void* z,
   UNET_REQUIRE(dbeta, UNET_EINVAL, "bn_bwd_reduce: dbeta is null");
   UNET_REQUIRE(!save_mean || (scale && shift && save_rstd && dgamma), UNET_EINVAL, "bn_bwd_reduce: incomplete BN state");
   const int rows_per_block = 256 / (C / 8);
-  const unsigned grid = (unsigned)i64min(ceil_div(M, rows_per_block), (int64_t)sm_count() * 8);
+  const unsigned grid = (unsigned)i64min(ceil_div(M, (int64_t)rows_per_block * kBnUnroll), (int64_t)sm_count() * 8);
   const size_t smem = (size_t)2 * C * sizeof(float);
   if (dtype == UNET_F32)
     bn_bwd_reduce_kernel<float><<<grid, 256, smem, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift, save_mean,
@@ -536,15 +588,16 @@ extern "C" int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
   const DropArgs dp = make_drop(drop);
   UNET_REQUIRE(dz && aligned16(dz), UNET_EINVAL, "bn_bwd_apply: dz null or unaligned");
   UNET_REQUIRE(!save_mean || (scale && shift && save_rstd && dgamma && dbeta), UNET_EINVAL, "bn_bwd_apply: incomplete BN state");
-  const int64_t threads = M * (C / 8);
   const float inv_m = (float)(1.0 / (double)M);
+  const int rows_per_block = 256 / (C / 8);
+  const unsigned grid = (unsigned)i64min(ceil_div(M, (int64_t)rows_per_block * kBnUnroll), (int64_t)sm_count() * 16);
   if (dtype == UNET_F32)
-    bn_bwd_apply_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift,
-                                                                 save_mean, save_rstd, dgamma, dbeta, (float*)dz, M, C, relu, inv_m, dp);
+    bn_bwd_apply_kernel<float><<<grid, 256, 0, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift,
+                                                    save_mean, save_rstd, dgamma, dbeta, (float*)dz, M, C, relu, inv_m, dp);
   else if (dtype == UNET_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
-                                                                         scale, shift, save_mean, save_rstd, dgamma, dbeta,
-                                                                         (__nv_bfloat16*)dz, M, C, relu, inv_m, dp);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+                                                            scale, shift, save_mean, save_rstd, dgamma, dbeta,
+                                                            (__nv_bfloat16*)dz, M, C, relu, inv_m, dp);
   else return set_error(UNET_EINVAL, "bn_bwd_apply: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("bn_bwd_apply");
   return UNET_OK;

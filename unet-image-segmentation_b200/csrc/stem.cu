@@ -1,0 +1,266 @@
+// The first conv_block of the U-Net (enc1_block1: SeparableConv2D(64, 3) on the RGB image, reference
+// model/u_net.py:14-20,63-66) as ONE kernel per direction.  With 3 input channels the depthwise half has almost no
+// data and the pointwise half is a K = 3 contraction (1 flop/B): both are bound by the 64-channel tensor on the
+// other side, so the fused kernels touch that tensor exactly once and everything else stays on chip.
+//
+//   forward : x[N,H,W,3] -> dw 3x3 (smem) -> pw 3->64 (registers) -> z (pre-BN) + batch statistics, or BN+ReLU applied
+//   backward: x, dz[N,H,W,64] -> d(pointwise_kernel), d(depthwise_kernel)   (no input gradient: x is the image)
+//
+// A CTA walks 8x32-pixel tiles (grid-stride); 256 threads; a thread owns 8 output channels of 8 pixels of the tile,
+// so a warp's 16-byte stores / loads cover 4 pixels x 128 B contiguous.
+#include "common.cuh"
+
+namespace unet {
+
+constexpr int kStemCin = 3, kStemCout = 64, kTH = 8, kTW = 32;
+
+template <typename T>
+__device__ __forceinline__ void stem_load_tile(const T* __restrict__ x, int n, int h0, int w0, int H, int W, float* s_x) {
+  // (kTH+2) x (kTW+2) x 3 halo tile, zero padded ('same'), as fp32
+  constexpr int kRowElems = (kTW + 2) * kStemCin;
+  for (int i = threadIdx.x; i < (kTH + 2) * kRowElems; i += blockDim.x) {
+    const int r = i / kRowElems, e = i - r * kRowElems;
+    const int hh = h0 - 1 + r, ww = w0 - 1 + e / kStemCin;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = to_f32(x[(((int64_t)n * H + hh) * W + w0 - 1) * kStemCin + e]);
+    s_x[i] = v;
+  }
+}
+
+__device__ __forceinline__ void stem_depthwise(const float* s_x, const float* s_wd, float* s_d) {
+  // one pixel per thread: d[px][ci] = sum_taps x * wd
+  const int pr = threadIdx.x >> 5, pc = threadIdx.x & 31;
+  float d[kStemCin] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+#pragma unroll
+      for (int ci = 0; ci < kStemCin; ++ci)
+        d[ci] = fmaf(s_x[((pr + a) * (kTW + 2) + pc + b) * kStemCin + ci], s_wd[(a * 3 + b) * kStemCin + ci], d[ci]);
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci) s_d[threadIdx.x * kStemCin + ci] = d[ci];
+}
+
+// mode 0: out = z, statistics;  mode 1: out = act(z*scale+shift)
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const float* __restrict__ wp, T* __restrict__ out,
+                int64_t ldo, int N, int H, int W, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                double* __restrict__ colsum, double* __restrict__ colsq, int tiles_h, int tiles_w) {
+  __shared__ float s_x[(kTH + 2) * (kTW + 2) * kStemCin];
+  __shared__ float s_d[kTH * kTW * kStemCin];
+  __shared__ float s_wd[9 * kStemCin];
+  __shared__ float s_stat[2 * kStemCout];
+  if (threadIdx.x < 9 * kStemCin) s_wd[threadIdx.x] = wd9c[threadIdx.x];
+  if (threadIdx.x < 2 * kStemCout) s_stat[threadIdx.x] = 0.f;
+  const int cg = threadIdx.x & 7, pslot = threadIdx.x >> 3;       // 8 channel groups x 32 pixel slots
+  float w[kStemCin][8], sc[8], sh[8], ssum[8], ssq[8];
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci) load8(wp + ci * kStemCout + cg * 8, w[ci]);
+  const bool affine = scale != nullptr || shift != nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; ssum[j] = 0.f; ssq[j] = 0.f; }
+  if (scale) load8(scale + cg * 8, sc);
+  if (shift) load8(shift + cg * 8, sh);
+  const bool stats = colsum != nullptr;
+  const int64_t total = (int64_t)N * tiles_h * tiles_w;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tw = (int)(t % tiles_w); const int64_t q = t / tiles_w;
+    const int th = (int)(q % tiles_h); const int n = (int)(q / tiles_h);
+    const int h0 = th * kTH, w0 = tw * kTW;
+    __syncthreads();                                 // previous tile's s_d readers are done
+    stem_load_tile<T>(x, n, h0, w0, H, W, s_x);
+    __syncthreads();
+    stem_depthwise(s_x, s_wd, s_d);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = pslot + 32 * i;                  // pixel of the tile: row p/32, column p%32
+      const int hh = h0 + (p >> 5), ww = w0 + (p & 31);
+      if (hh >= H || ww >= W) continue;
+      const float d0 = s_d[p * 3], d1 = s_d[p * 3 + 1], d2 = s_d[p * 3 + 2];
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(d2, w[2][j], fmaf(d1, w[1][j], d0 * w[0][j]));
+        if (affine) { v = fmaf(v, sc[j], sh[j]); if (relu) v = fmaxf(v, 0.f); }
+        o[j] = v;
+      }
+      store8(out + (((int64_t)n * H + hh) * W + ww) * ldo + cg * 8, o);
+      if (stats) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float r = round_to<T>(o[j]); ssum[j] += r; ssq[j] = fmaf(r, r, ssq[j]); }
+      }
+    }
+  }
+  if (stats) {
+    // lanes with equal cg (lane & 7) hold the same channels: fold 4 pixel slots per warp, then shared, then global
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8); ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
+      ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);   ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&s_stat[cg * 8 + j], ssum[j]); atomicAdd(&s_stat[kStemCout + cg * 8 + j], ssq[j]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < kStemCout) {
+      atomicAdd(&colsum[threadIdx.x], (double)s_stat[threadIdx.x]);
+      atomicAdd(&colsq[threadIdx.x], (double)s_stat[kStemCout + threadIdx.x]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz, const float* __restrict__ wd9c,
+                const float* __restrict__ wp, float* __restrict__ dwd9c, float* __restrict__ dwp, int N, int H, int W,
+                int tiles_h, int tiles_w) {
+  __shared__ float s_x[(kTH + 2) * (kTW + 2) * kStemCin];
+  __shared__ float s_d[kTH * kTW * kStemCin];
+  __shared__ float s_dd[kTH * kTW * kStemCin];
+  __shared__ float s_wd[9 * kStemCin];
+  __shared__ float s_gp[kStemCin * kStemCout];
+  __shared__ float s_gd[9 * kStemCin];
+  if (threadIdx.x < 9 * kStemCin) { s_wd[threadIdx.x] = wd9c[threadIdx.x]; s_gd[threadIdx.x] = 0.f; }
+  if (threadIdx.x < kStemCin * kStemCout) s_gp[threadIdx.x] = 0.f;
+  const int cg = threadIdx.x & 7, pslot = threadIdx.x >> 3;
+  float w[kStemCin][8], gp[kStemCin][8], gd[9][kStemCin];
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci) {
+    load8(wp + ci * kStemCout + cg * 8, w[ci]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gp[ci][j] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int ci = 0; ci < kStemCin; ++ci) gd[i][ci] = 0.f;
+  const int64_t total = (int64_t)N * tiles_h * tiles_w;
+  for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+    const int tw = (int)(t % tiles_w); const int64_t q = t / tiles_w;
+    const int th = (int)(q % tiles_h); const int n = (int)(q / tiles_h);
+    const int h0 = th * kTH, w0 = tw * kTW;
+    __syncthreads();
+    stem_load_tile<T>(x, n, h0, w0, H, W, s_x);
+    __syncthreads();
+    stem_depthwise(s_x, s_wd, s_d);
+    __syncthreads();
+    // pointwise gradient and dd = dz . Wp^T
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = pslot + 32 * i;
+      const int hh = h0 + (p >> 5), ww = w0 + (p & 31);
+      float g[8];
+      const bool live = hh < H && ww < W;
+      if (live) load8(dz + (((int64_t)n * H + hh) * W + ww) * lddz + cg * 8, g);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+      }
+      const float d0 = s_d[p * 3], d1 = s_d[p * 3 + 1], d2 = s_d[p * 3 + 2];
+      float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gp[0][j] = fmaf(d0, g[j], gp[0][j]); gp[1][j] = fmaf(d1, g[j], gp[1][j]); gp[2][j] = fmaf(d2, g[j], gp[2][j]);
+        dd0 = fmaf(g[j], w[0][j], dd0); dd1 = fmaf(g[j], w[1][j], dd1); dd2 = fmaf(g[j], w[2][j], dd2);
+      }
+      // the 8 channel groups of a pixel are 8 adjacent lanes
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        dd0 += __shfl_xor_sync(0xffffffffu, dd0, o); dd1 += __shfl_xor_sync(0xffffffffu, dd1, o); dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);
+      }
+      if (cg == 0) { s_dd[p * 3] = dd0; s_dd[p * 3 + 1] = dd1; s_dd[p * 3 + 2] = dd2; }
+    }
+    __syncthreads();
+    // depthwise gradient: one pixel per thread
+    {
+      const int pr = threadIdx.x >> 5, pc = threadIdx.x & 31;
+      const float e0 = s_dd[threadIdx.x * 3], e1 = s_dd[threadIdx.x * 3 + 1], e2 = s_dd[threadIdx.x * 3 + 2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const float* xp = s_x + ((pr + a) * (kTW + 2) + pc + b) * kStemCin;
+          gd[a * 3 + b][0] = fmaf(xp[0], e0, gd[a * 3 + b][0]);
+          gd[a * 3 + b][1] = fmaf(xp[1], e1, gd[a * 3 + b][1]);
+          gd[a * 3 + b][2] = fmaf(xp[2], e2, gd[a * 3 + b][2]);
+        }
+    }
+  }
+  // fold and publish
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = gp[ci][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_gp[ci * kStemCout + cg * 8 + j], v);
+    }
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int ci = 0; ci < kStemCin; ++ci) {
+      const float v = warp_sum(gd[i][ci]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&s_gd[i * kStemCin + ci], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < kStemCin * kStemCout) atomicAdd(&dwp[threadIdx.x], s_gp[threadIdx.x]);
+  if (threadIdx.x < 9 * kStemCin) atomicAdd(&dwd9c[threadIdx.x], s_gd[threadIdx.x]);
+}
+
+static int stem_check(const char* who, const void* x, int N, int H, int W, int Cin, int Cout) {
+  UNET_REQUIRE(x && N > 0 && H > 0 && W > 0, UNET_EINVAL, "%s: bad argument", who);
+  UNET_REQUIRE(Cin == kStemCin && Cout == kStemCout, UNET_EUNSUPPORTED,
+               "%s: the fused stem is built for %d -> %d channels (got %d -> %d); use dwconv3x3 + gemm", who, kStemCin,
+               kStemCout, Cin, Cout);
+  return UNET_OK;
+}
+
+}  // namespace unet
+
+using namespace unet;
+
+extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, void* out, int64_t ldo,
+                             int N, int H, int W, int Cin, int Cout, int dtype,
+                             const float* scale, const float* shift, int relu, double* colsum, double* colsq, void* stream) {
+  if (int e = stem_check("stem_fwd", x, N, H, W, Cin, Cout)) return e;
+  UNET_REQUIRE(wd9c && wp && out && ldo >= Cout, UNET_EINVAL, "stem_fwd: bad argument");
+  UNET_REQUIRE((colsum == nullptr) == (colsq == nullptr), UNET_EINVAL, "stem_fwd: colsum/colsq must come together");
+  UNET_REQUIRE(ldo % 8 == 0 && aligned16(out) && aligned16(wp) && (!scale || aligned16(scale)) && (!shift || aligned16(shift)),
+               UNET_EALIGN, "stem_fwd: out / parameters must be 16B aligned, ldo%%8==0");
+  const int th = (int)ceil_div(H, kTH), tw = (int)ceil_div(W, kTW);
+  const int64_t tiles = (int64_t)N * th * tw;
+  const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 6);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_F32)
+    stem_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, wd9c, wp, (float*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw);
+  else if (dtype == UNET_BF16)
+    stem_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, wd9c, wp, (__nv_bfloat16*)out, ldo, N, H, W, scale,
+                                                        shift, relu, colsum, colsq, th, tw);
+  else return set_error(UNET_EINVAL, "stem_fwd: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("stem_fwd");
+  return UNET_OK;
+}
+
+extern "C" int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const float* wd9c, const float* wp,
+                             float* dwd9c, float* dwp, int N, int H, int W, int Cin, int Cout, int dtype, void* stream) {
+  if (int e = stem_check("stem_bwd", x, N, H, W, Cin, Cout)) return e;
+  UNET_REQUIRE(dz && wd9c && wp && dwd9c && dwp && lddz >= Cout, UNET_EINVAL, "stem_bwd: bad argument");
+  UNET_REQUIRE(lddz % 8 == 0 && aligned16(dz) && aligned16(wp), UNET_EALIGN, "stem_bwd: dz / wp must be 16B aligned, lddz%%8==0");
+  const int th = (int)ceil_div(H, kTH), tw = (int)ceil_div(W, kTW);
+  const int64_t tiles = (int64_t)N * th * tw;
+  const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_F32)
+    stem_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dz, lddz, wd9c, wp, dwd9c, dwp, N, H, W, th, tw);
+  else if (dtype == UNET_BF16)
+    stem_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, lddz, wd9c, wp, dwd9c, dwp,
+                                                        N, H, W, th, tw);
+  else return set_error(UNET_EINVAL, "stem_bwd: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("stem_bwd");
+  return UNET_OK;
+}

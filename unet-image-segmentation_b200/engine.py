@@ -238,6 +238,12 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------------ inference
     def _block_infer(self, pl: _Plan, prefix: str, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         B, h, w, cin = x.shape
+        if ops.stem_supported(cin, y.shape[-1]) and x.is_contiguous():
+            o, c = self._bn_off[prefix]
+            ops.stem_fwd(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel"), y,
+                         scale=self.fold[0, o:o + c] if self.use_bn else None,
+                         shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True)
+            return y
         level = (self.spec.input_size[0] // h).bit_length() - 1
         max_cin = 1024 if level == 4 else 2 * FILTERS[level]
         d = pl.buf(f"d{level}", (B * h * w * max_cin,))[: B * h * w * cin].view(B, h, w, cin)
@@ -292,19 +298,28 @@ class UNetEngine:
     def _block_train_fwd(self, pl, prefix, x, y, pooled=None, drop=None):
         B, h, w, cin = x.shape
         cout = y.shape[-1]
-        d = pl.buf(prefix + "/d", (B, h, w, cin))
         z = pl.buf(prefix + "/z", (B, h, w, cout))
-        ops.dwconv3x3(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
         o, c = self._bn_off[prefix]
+        stem = ops.stem_supported(cin, cout) and x.is_contiguous()
+        wd, wp = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel")
+        if not stem:
+            d = pl.buf(prefix + "/d", (B, h, w, cin))
+            ops.dwconv3x3(x, wd, d)
         if self.use_bn:
             scale, shift, smean, srstd = self._bn(prefix)
-            self._pw_fwd(prefix, d, z, epilogue=ops.EPI_STATS, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
+            if stem:
+                ops.stem_fwd(x, wd, wp, z, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
+            else:
+                self._pw_fwd(prefix, d, z, epilogue=ops.EPI_STATS, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
             ops.bn_finalize(self.colstats[0, o:o + c], self.colstats[1, o:o + c], B * h * w,
                             self.wview(f"{prefix}_bn/gamma"), self.wview(f"{prefix}_bn/beta"), BN_EPS, BN_MOMENTUM,
                             self.wview(f"{prefix}_bn/moving_mean"), self.wview(f"{prefix}_bn/moving_variance"),
                             scale, shift, smean, srstd)
         else:
-            self._pw_fwd(prefix, d, z, epilogue=ops.EPI_AFFINE, shift=self.wview(f"{prefix}_sepconv/bias"))
+            if stem:
+                ops.stem_fwd(x, wd, wp, z, shift=self.wview(f"{prefix}_sepconv/bias"))
+            else:
+                self._pw_fwd(prefix, d, z, epilogue=ops.EPI_AFFINE, shift=self.wview(f"{prefix}_sepconv/bias"))
             scale, shift = self.ones[:c], self.zeros[:c]
         ops.bn_act(z, scale, shift, y, relu=True, pooled=pooled, drop=drop)
         return y
@@ -312,9 +327,10 @@ class UNetEngine:
     def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None):
         """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out."""
         B, h, w, cin = x.shape
-        d, z = pl.t[prefix + "/d"], pl.t[prefix + "/z"]
+        z = pl.t[prefix + "/z"]
         cout = z.shape[-1]
         M = B * h * w
+        stem = (prefix + "/d") not in pl.t
         dz = scr[0][: M * cout].view(B, h, w, cout)
         dd = scr[1][: M * cin].view(B, h, w, cin)
         if self.use_bn:
@@ -326,6 +342,11 @@ class UNetEngine:
             dgamma, dbeta = None, self.wview(f"{prefix}_sepconv/bias", self.g)
         ops.bn_bwd_reduce(dy, z, scale, shift, smean, srstd, dgamma, dbeta, relu=True, drop=ydrop)
         ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True, drop=ydrop)
+        if stem:       # fused first block: both weight gradients from one pass over dz; the image needs no gradient
+            ops.stem_bwd(x, dz, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel"),
+                         self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g), self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g))
+            return None
+        d = pl.t[prefix + "/d"]
         ops.gemm(d, dz, self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g), a_trans=True, accumulate=True)
         self._pw_dgrad(prefix, dz, dd)
         ops.dwconv3x3_bwd_weight(x, dd, self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g))

@@ -149,6 +149,35 @@ def dwconv3x3_bwd_weight(x: torch.Tensor, dy: torch.Tensor, dw9c: torch.Tensor) 
           tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(x, dy, dw9c), flops=18 * x.numel())
 
 
+# ------------------------------------------------------------------------------------------------ fused first block
+def stem_supported(cin: int, cout: int) -> bool:
+    return cin == 3 and cout == 64
+
+
+def stem_fwd(x: torch.Tensor, wd9c: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, scale=None, shift=None,
+             relu: bool = False, colsum=None, colsq=None) -> None:
+    """enc1_block1_sepconv (u_net.py:63-66 on the RGB image): depthwise 3x3 + pointwise 3->64 in one kernel."""
+    n, h, w, cin, ldx = _nhwc(x, "x")
+    _, _, _, cout, ldo = _nhwc(out, "out")
+    if ldx != cin or x.dtype != out.dtype:
+        raise ValueError("stem_fwd: x must be contiguous and share out's dtype")
+    _f32(wd9c, "wd9c"); _f32(wp, "wp"); _f32(scale, "scale"); _f32(shift, "shift")
+    _call("unet_stem_fwd", _p(x), _p(wd9c), _p(wp), _p(out), ldo, n, h, w, cin, cout, _dt(x), _p(scale), _p(shift),
+          int(relu), _p(colsum), _p(colsq), _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, out),
+          flops=(18 * cin + 2 * cin * cout) * n * h * w)
+
+
+def stem_bwd(x: torch.Tensor, dz: torch.Tensor, wd9c, wp, dwd9c, dwp) -> None:
+    n, h, w, cin, ldx = _nhwc(x, "x")
+    _, _, _, cout, lddz = _nhwc(dz, "dz")
+    if ldx != cin or x.dtype != dz.dtype:
+        raise ValueError("stem_bwd: x must be contiguous and share dz's dtype")
+    for t, nm in ((wd9c, "wd9c"), (wp, "wp"), (dwd9c, "dwd9c"), (dwp, "dwp")):
+        _f32(t, nm)
+    _call("unet_stem_bwd", _p(x), _p(dz), lddz, _p(wd9c), _p(wp), _p(dwd9c), _p(dwp), n, h, w, cin, cout, _dt(x),
+          _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, dz), flops=(36 * cin + 4 * cin * cout) * n * h * w)
+
+
 # ------------------------------------------------------------------------------------------------ dense contractions
 def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = False, b_trans: bool = False,
          accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,

@@ -65,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     (BUILD / "ptxas.log").write_text("\n".join(f"==== {s}\n{log}" for s, (_, log) in zip(SOURCES, results)))
     if verbose:
         print((BUILD / "ptxas.log").read_text())
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-cudart", "static"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs, "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

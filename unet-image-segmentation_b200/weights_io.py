@@ -23,14 +23,13 @@ from .spec import UNetSpec
 KERAS_VERSION = "2.15.0"
 
 
-def _model_config(model) -> dict:
+def _model_config(sp: UNetSpec, name: str = "U-NET-Segmentation") -> dict:
     """A Keras-style functional-model config: enough for our own loader (the `unet_b200` block) and for a human
     reading the file; layer class names and names follow model/u_net.py."""
-    sp = model.spec
     return {
         "class_name": "Functional",
         "config": {
-            "name": model.name,
+            "name": name,
             "layers": [{"class_name": l.kind, "name": l.name, "inbound_nodes": l.connected_to} for l in sp.layers],
             "input_layers": [["input_image", 0, 0]],
             "output_layers": [["output_mask", 0, 0]],
@@ -62,23 +61,27 @@ def spec_from_config(cfg: dict) -> UNetSpec:
 
 
 # ------------------------------------------------------------------------------------------------ writers
-def _weights_by_layer(model) -> Dict[str, Dict[str, np.ndarray]]:
-    w = model.get_weights_dict()
+def _weights_by_layer(spec: UNetSpec, w: Dict[str, np.ndarray]) -> Dict[str, Dict[str, np.ndarray]]:
     out: Dict[str, Dict[str, np.ndarray]] = {}
-    for name in model.spec.params:
+    for name in spec.params:
         layer, leaf = name.split("/")
-        out.setdefault(layer, {})[leaf] = w[name]
+        out.setdefault(layer, {})[leaf] = np.asarray(w[name], np.float32)
     return out
 
 
 def save_model(model, path: str, weights_only: bool = False) -> None:
+    write_model_file(path, model.spec, model.get_weights_dict(), model.name, weights_only)
+
+
+def write_model_file(path: str, spec: UNetSpec, weights: Dict[str, np.ndarray], name: str = "U-NET-Segmentation",
+                     weights_only: bool = False) -> None:
     ext = os.path.splitext(path)[1].lower()
     d = os.path.dirname(path)
     if d:
         os.makedirs(d, exist_ok=True)
-    cfg = _model_config(model)
+    cfg = _model_config(spec, name)
     if ext == ".npz":
-        arrays = dict(model.get_weights_dict())
+        arrays = dict(weights)
         arrays["__config__"] = np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8)
         with open(path, "wb") as f:
             np.savez(f, **arrays)
@@ -87,7 +90,7 @@ def save_model(model, path: str, weights_only: bool = False) -> None:
     if ext == ".keras":
         root = h5lite.Group()
         layers = root.group("layers")
-        for layer, ws in _weights_by_layer(model).items():
+        for layer, ws in _weights_by_layer(spec, weights).items():
             vars_ = layers.group(layer).group("vars")
             for i, (leaf, arr) in enumerate(ws.items()):
                 vars_.dataset(str(i), arr)
@@ -101,8 +104,8 @@ def save_model(model, path: str, weights_only: bool = False) -> None:
     # legacy HDF5 (.h5, .hdf5, anything else — Keras also treats unknown suffixes as HDF5 in 2.x)
     root = h5lite.Group()
     mw = root if weights_only else root.group("model_weights")
-    by_layer = _weights_by_layer(model)
-    layer_names = [l.name for l in model.spec.layers]
+    by_layer = _weights_by_layer(spec, weights)
+    layer_names = [l.name for l in spec.layers]
     mw.attrs["layer_names"] = [n.encode() for n in layer_names]
     mw.attrs["backend"] = b"tensorflow"
     mw.attrs["keras_version"] = KERAS_VERSION.encode()

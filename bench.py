@@ -159,6 +159,13 @@ def cpu_infer_sample(H, W, classes, batch, steps, warmup=1):
     return batch * len(times) / sum(times), sum(times) / len(times)
 
 
+def host_threads() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_size(mode, H, W):
     """Bounded sample: a few images so one CPU step is seconds, not minutes."""
     px = H * W
@@ -174,6 +181,7 @@ def run_reference(args):
         return
     mode, H, W, classes, _, desc = WORKLOADS[args.workload]
     b = cpu_sample_size(mode, H, W)
+    torch.set_num_threads(host_threads())        # torchrun exports OMP_NUM_THREADS=1; the CPU arm gets every host core
     cores = torch.get_num_threads()
     steps = max(1, min(args.steps, 3))
     fn = cpu_train_sample if mode == "train" else cpu_infer_sample
@@ -200,6 +208,7 @@ def run_b200(args):
     from unet_b200 import ops
     from unet_b200.keras_api import AdamW, MeanIoU, Model
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
     rank, local_rank, world = D.init_from_env("nccl")
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
@@ -333,6 +342,7 @@ def run_b200(args):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(host_threads())
         b = cpu_sample_size(mode, H, W)
         fn = cpu_train_sample if mode == "train" else cpu_infer_sample
         ips, sec = fn(H, W, classes, b, 2, warmup=1)

@@ -54,6 +54,12 @@ elif name == "wgrad64":
 elif name == "dw_fwd":
     x, y, w = rnd(B, H, W, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf), torch.rand((9, 64), device=dev)
     run(lambda: ops.dwconv3x3(x, w, y), 2 * M * 64 * 2)
+elif name == "dw_fwd128":
+    x, y, w = rnd(B, H, W, 128), torch.empty((B, H, W, 128), device=dev, dtype=bf), torch.rand((9, 128), device=dev)
+    run(lambda: ops.dwconv3x3(x, w, y), 2 * M * 128 * 2)
+elif name == "dw_fwd256":
+    x, y, w = rnd(B, 256, 256, 256), torch.empty((B, 256, 256, 256), device=dev, dtype=bf), torch.rand((9, 256), device=dev)
+    run(lambda: ops.dwconv3x3(x, w, y), 2 * B * 256 * 256 * 256 * 2)
 elif name == "dw_bwd_w":
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     run(lambda: ops.dwconv3x3_bwd_weight(x, dy, dw), 2 * M * 64 * 2)

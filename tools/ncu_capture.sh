@@ -1,0 +1,14 @@
+#!/bin/bash
+# One gpurun call: plain runs first (must exit 0), then the ncu launch list of a short bench and `--set full`
+# captures of the hot kernels at the train512 level-0 shapes.  Outputs land in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+$B > gpurun_out/plain_bench.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
+for spec in "dw_fwd128:dwconv3x3_strip" "gemm64:gemm_tc_nt" "dw_bwd_w:dwconv3x3_wgrad_strip" "bn_bwd_apply:bn_bwd_apply" "wgrad64:gemm_tc_wgrad"; do
+  name=${spec%%:*}; pat=${spec##*:}
+  python tools/kernel_micro.py $name 2 > gpurun_out/plain_$name.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 -o gpurun_out/prof_$name python tools/kernel_micro.py $name 2 > gpurun_out/ncu_$name.log 2>&1
+done
+ls -la gpurun_out/*.ncu-rep

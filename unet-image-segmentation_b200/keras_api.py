@@ -315,6 +315,70 @@ class Layer:
         self._model.set_weights_dict(dict(zip(names, arrays)))
 
 
+# ====================================================================================================== input prefetch
+class _Prefetcher:
+    """Host -> device staging for `fit`: batch i+1 is uploaded on a copy stream (from pinned memory) while batch i
+    computes.  Two device slots; a slot is rewritten only after the step that read it has been enqueued and has
+    finished on the compute stream (event), and a step starts only after its upload has landed (event)."""
+
+    def __init__(self, source):
+        import torch
+        self.src = iter(source)
+        self.copy_stream = torch.cuda.Stream()
+        self.slots = [dict(dev={}, pin={}, ready=None, done=None) for _ in range(2)]
+        self.h2d_bytes = 0
+
+    def _upload(self, batch, slot):
+        import torch
+        x, y = batch[0], batch[1]
+        out = []
+        with torch.cuda.stream(self.copy_stream):
+            if slot["done"] is not None:
+                self.copy_stream.wait_event(slot["done"])
+            for key, arr in (("x", x), ("y", y)):
+                if isinstance(arr, torch.Tensor) and arr.is_cuda:
+                    out.append(arr.to(torch.float32).contiguous())
+                    continue
+                if isinstance(arr, torch.Tensor) and arr.is_pinned() and arr.dtype == torch.float32 and arr.is_contiguous():
+                    host = arr
+                else:
+                    a = arr.numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+                    host = slot["pin"].get((key, a.shape))
+                    if host is None:
+                        host = slot["pin"][(key, a.shape)] = torch.empty(a.shape, dtype=torch.float32).pin_memory()
+                    if slot["ready"] is not None:
+                        slot["ready"].synchronize()          # the previous DMA out of this pinned buffer has finished
+                    np.copyto(host.numpy(), a, casting="unsafe")
+                dev = slot["dev"].get((key, tuple(host.shape)))
+                if dev is None:
+                    dev = slot["dev"][(key, tuple(host.shape))] = torch.empty(host.shape, dtype=torch.float32, device="cuda")
+                dev.copy_(host, non_blocking=True)
+                self.h2d_bytes += host.numel() * 4
+                out.append(dev)
+            slot["ready"] = torch.cuda.Event()
+            slot["ready"].record(self.copy_stream)
+        return out
+
+    def __iter__(self):
+        import torch
+        i = 0
+        try:
+            nxt = self._upload(next(self.src), self.slots[0])
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, cur_slot = nxt, self.slots[i % 2]
+            try:
+                nxt = self._upload(next(self.src), self.slots[(i + 1) % 2])
+            except StopIteration:
+                nxt = None
+            torch.cuda.current_stream().wait_event(cur_slot["ready"])
+            yield cur[0], cur[1]
+            cur_slot["done"] = torch.cuda.Event()
+            cur_slot["done"].record(torch.cuda.current_stream())
+            i += 1
+
+
 # ====================================================================================================== model
 class Model:
     """What `U_NET(...)` returns.  The engine (device buffers, kernels) is created on first use, so constructing the
@@ -514,6 +578,12 @@ class Model:
                 m.update_state(yd, eng._plans[(xd.shape[0], True)].t["probs"])
         return out3, None
 
+    def _loss_ring(self):
+        import torch
+        if getattr(self, "_ring", None) is None:
+            self._ring = torch.empty((8, 3), dtype=torch.float32).pin_memory()
+        return self._ring
+
     def test_on_batch(self, x, y):
         eng = self.engine
         xd, yd = self._stage_in(x, "vx"), self._stage_in(y, "vy")
@@ -574,19 +644,31 @@ class Model:
                 if steps_per_epoch is None:
                     raise ValueError("steps_per_epoch is required when fitting from a generator")
                 it = _take(x, steps_per_epoch)
-            acc = torch.zeros(3, device="cuda", dtype=torch.float64)
             n = 0
             t0 = time.time()
             if verbose:
                 print(f"Epoch {epoch + 1}/{epochs}")
-            for bx, by in it:
+            ring = self._loss_ring()
+            host_sum = np.zeros(3, np.float64)
+            pending = []                                   # (ring slot, event) of steps whose loss is still in flight
+            pf = _Prefetcher(it)
+            for bx, by in pf:
                 out3, _ = self._train_step_device(bx, by)
-                acc += out3.double()
+                slot = n % ring.shape[0]
+                if len(pending) >= ring.shape[0] - 1:      # ring full: retire the oldest read first
+                    k, ev = pending.pop(0); ev.synchronize(); host_sum += ring[k].numpy()
+                ring[slot].copy_(out3, non_blocking=True)  # the step's device -> host read; never stalls the step
+                ev = torch.cuda.Event(); ev.record()
+                pending.append((slot, ev))
                 n += 1
-                if verbose == 1 and (n % 10 == 0):
-                    v = (acc / n).cpu().numpy()
-                    print(f"\r{n}/{steps_per_epoch or '?'} - loss: {v[0]:.4f}", end="", flush=True)
-            vals = (acc / max(n, 1)).cpu().numpy()
+                while len(pending) > 1 and pending[0][1].query():
+                    k, e0 = pending.pop(0); host_sum += ring[k].numpy()
+                if verbose == 1 and (n % 10 == 0) and n > len(pending):
+                    print(f"\r{n}/{steps_per_epoch or '?'} - loss: {host_sum[0] / (n - len(pending)):.4f}", end="", flush=True)
+            for k, ev in pending:
+                ev.synchronize(); host_sum += ring[k].numpy()
+            self.last_h2d_bytes = pf.h2d_bytes
+            vals = host_sum / max(n, 1)
             logs: Dict[str, float] = {"loss": float(vals[0])}
             for m in self.metrics:
                 if isinstance(m, MeanIoU):

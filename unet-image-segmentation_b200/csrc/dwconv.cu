@@ -107,35 +107,35 @@ dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restr
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
 template <typename T> struct StripCfg {
-  static constexpr int VEC = 16 / (int)sizeof(T);        // channels per thread
-  static constexpr int CB = 128 / (int)sizeof(T);        // channels per CTA
-  static constexpr int TW = 32, RH = 4, S = 5;
+  static constexpr int NV = 8 / (int)sizeof(T);          // channels per thread (8 bytes)
+  static constexpr int CB = 128 / (int)sizeof(T);        // channels per CTA (128 bytes)
+  static constexpr int TW = 32, RH = 4, S = 8;
+  static constexpr int kThreads = TW * 16;
   static constexpr int kStageBytes = RH * (TW + 2) * 128;
   static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + 128;
 };
 
-template <typename T> __device__ __forceinline__ void unpack16(const uint4& r, float (&v)[16 / sizeof(T)]);
-template <> __device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& r, float (&v)[8]) {
-  const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float (&v)[8 / sizeof(T)]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float (&v)[4]) {
+  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
 }
-template <> __device__ __forceinline__ void unpack16<float>(const uint4& r, float (&v)[4]) {
-  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+template <> __device__ __forceinline__ void unpack8<float>(const uint2& r, float (&v)[2]) {
+  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
 }
-__device__ __forceinline__ uint4 pack16(const float (&v)[8], __nv_bfloat16*) {
-  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+__device__ __forceinline__ uint2 pack8(const float (&v)[4], __nv_bfloat16*) {
+  return make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
-__device__ __forceinline__ uint4 pack16(const float (&v)[4], float*) {
-  return make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+__device__ __forceinline__ uint2 pack8(const float (&v)[2], float*) {
+  return make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1]));
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, bool DROP>
+__global__ void __launch_bounds__(StripCfg<T>::kThreads, 1)
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
                        int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp) {
   using Cfg = StripCfg<T>;
-  constexpr int VEC = Cfg::VEC, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
+  constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
@@ -149,10 +149,10 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   const int c0 = cb * Cfg::CB, w0 = tw * TW;
   const int h0 = hs * seg_rows, h1 = min(H, h0 + seg_rows);
   const int nst = (h1 - h0 + 2 + RH - 1) / RH;          // input rows h0-1 .. h1
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 8); }
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], Cfg::kThreads / 32); }
     fence_barrier_init();
   }
   __syncthreads();
@@ -169,63 +169,64 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     for (int k = 0; k < S - 1 && k < nst; ++k) issue(k);
   }
 
-  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;
-  const int c = c0 + cg * VEC;
+  const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
+  const int c = c0 + cg * NV;
   const bool live = (w0 + px < W) && (c < C);
-  float k9[9][VEC];
+  float k9[9][NV];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const int src = flip ? 8 - i : i;
-    if (c < C) {
-      if (VEC == 8) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c) + 1);
-        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2] = a.z; k9[i][3] = a.w;
-        k9[i][4 % VEC] = b.x; k9[i][5 % VEC] = b.y; k9[i][6 % VEC] = b.z; k9[i][7 % VEC] = b.w;
-      } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
-        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2] = a.z; k9[i][3] = a.w;
-      }
-    } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) k9[i][j] = 0.f;
+    for (int j = 0; j < NV; ++j) k9[i][j] = 0.f;
+    if (c < C) {
+      if (NV == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
+        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2 % NV] = a.z; k9[i][3 % NV] = a.w;
+      } else {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(w9c + (int64_t)src * C + c));
+        k9[i][0] = a.x; k9[i][1] = a.y;
+      }
     }
   }
-  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
-  float prev[VEC], cur[VEC];
+  uint32_t seed = 0u;
+  if (DROP) seed = drop_seed(dp);
+  float prev[NV], cur[NV];
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
-  T* ycol = y + (((int64_t)n * H) * W + (w0 + px)) * ldy + c;
+  for (int j = 0; j < NV; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
+  T* yptr = y + (((int64_t)n * H + (h0 - 2)) * W + (w0 + px)) * ldy + c;   // advanced one row per input row
   const int64_t yrow = (int64_t)W * ldy;
-  const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 16u;
+  const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+  int r_in = h0 - 1;
 
   for (int k = 0; k < nst; ++k) {
     const int s = k % S;
     if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
     mbar_wait(&full_bar[s], (k / S) & 1);
     const uint8_t* st = smem + s * Cfg::kStageBytes + tile_off;
+    uint2 ra[RH], rb[RH], rc[RH];
 #pragma unroll
-    for (int rr = 0; rr < RH; ++rr) {
-      const int r_in = h0 - 1 + k * RH + rr;
-      if (r_in > h1) break;
-      const uint4 ra = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128);
-      const uint4 rb = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128 + 128);
-      const uint4 rc = *reinterpret_cast<const uint4*>(st + rr * (TW + 2) * 128 + 256);
-      float a[VEC], b[VEC], cc[VEC];
-      unpack16<T>(ra, a); unpack16<T>(rb, b); unpack16<T>(rc, cc);
-      if (r_in - 1 >= h0 && live) {          // output row r_in-1 is complete once kernel row 2 has seen input row r_in
-        float o[VEC];
+    for (int rr = 0; rr < RH; ++rr) {        // all shared loads of the stage first: 12 independent requests in flight
+      ra[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128);
+      rb[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128 + 128);
+      rc[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128 + 256);
+    }
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
-        if (dp.on) {
+    for (int rr = 0; rr < RH; ++rr, ++r_in, yptr += yrow) {
+      float a[NV], b[NV], cc[NV];
+      unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc);
+      if (r_in > h0 && r_in <= h1 && live) {   // output row r_in-1 is complete once kernel row 2 has seen input row r_in
+        float o[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
+        if (DROP) {
           const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
 #pragma unroll
-          for (int j = 0; j < VEC; ++j) o[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+          for (int j = 0; j < NV; ++j) o[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
         }
-        *reinterpret_cast<uint4*>(ycol + (int64_t)(r_in - 1) * yrow) = pack16(o, (T*)nullptr);
+        *reinterpret_cast<uint2*>(yptr) = pack8(o, (T*)nullptr);
       }
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
+      for (int j = 0; j < NV; ++j) {
         prev[j] = fmaf(k9[5][j], cc[j], fmaf(k9[4][j], b[j], fmaf(k9[3][j], a[j], cur[j])));
         cur[j]  = fmaf(k9[2][j], cc[j], fmaf(k9[1][j], b[j], k9[0][j] * a[j]));
       }
@@ -267,16 +268,20 @@ static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, voi
   if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return set_cuda_error(e, "dwconv3x3_fwd: cudaFuncSetAttribute");
     attr_done = true;
   }
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
-  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 2 * 6);
+  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6);
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
-  dwconv3x3_strip_kernel<T><<<(unsigned)items, 256, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
+  if (dp.on)
+    dwconv3x3_strip_kernel<T, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
+  else
+    dwconv3x3_strip_kernel<T, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
   UNET_LAUNCH_CHECK("dwconv3x3_fwd(strip)");
   return UNET_OK;
 }
@@ -483,14 +488,6 @@ template <typename T> struct WgCfg {
   static constexpr int kSmemBytes = S * kStageBytes + 9 * CB * 4 + 2 * S * 8 + 128;
 };
 
-template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float (&v)[8 / sizeof(T)]);
-template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float (&v)[4]) {
-  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
-}
-template <> __device__ __forceinline__ void unpack8<float>(const uint2& r, float (&v)[2]) {
-  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
-}
 
 template <typename T>
 __global__ void __launch_bounds__(512, 1)
@@ -550,26 +547,29 @@ dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
     mbar_wait(&full_bar[s], (k / S) & 1);
     const uint8_t* sx = smem + s * Cfg::kStageBytes + xoff;
     const uint8_t* sd = smem + s * Cfg::kStageBytes + Cfg::kXBytes + xoff;
+    uint2 ra[RH], rb[RH], rc[RH], rd[RH];
+#pragma unroll
+    for (int rr = 0; rr < RH; ++rr) {        // all shared loads of the stage first (16 independent requests in flight)
+      ra[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128);
+      rb[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 128);
+      rc[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 256);
+      rd[rr] = *reinterpret_cast<const uint2*>(sd + rr * TW * 128);
+    }
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr) {
       const int q = h0 - 1 + k * RH + rr;           // x row; dy row q+1 sits at the same stage row
-      if (q > h1) break;
       float a[NV], b[NV], c[NV], dp[NV];
-      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128), a);
-      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 128), b);
-      unpack8<T>(*reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 256), c);
-      if (q + 1 < h1) unpack8<T>(*reinterpret_cast<const uint2*>(sd + rr * TW * 128), dp);
-      else {
-#pragma unroll
-        for (int j = 0; j < NV; ++j) dp[j] = 0.f;
-      }
+      unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], c); unpack8<T>(rd[rr], dp);
+      const bool dp_live = q + 1 < h1;              // dy rows of other segments (or past the image) do not belong to this strip
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
+        const float dpj = dp_live ? dp[j] : 0.f;
+        const float aj = a[j], bj = b[j], cj = c[j];   // rows past h1 meet only zeroed dy rows
         // kernel row r multiplies input row q into output row q - r + 1
-        acc[0][j] = fmaf(a[j], dp[j], acc[0][j]); acc[1][j] = fmaf(b[j], dp[j], acc[1][j]); acc[2][j] = fmaf(c[j], dp[j], acc[2][j]);
-        acc[3][j] = fmaf(a[j], d0[j], acc[3][j]); acc[4][j] = fmaf(b[j], d0[j], acc[4][j]); acc[5][j] = fmaf(c[j], d0[j], acc[5][j]);
-        acc[6][j] = fmaf(a[j], dm[j], acc[6][j]); acc[7][j] = fmaf(b[j], dm[j], acc[7][j]); acc[8][j] = fmaf(c[j], dm[j], acc[8][j]);
-        dm[j] = d0[j]; d0[j] = dp[j];
+        acc[0][j] = fmaf(aj, dpj, acc[0][j]); acc[1][j] = fmaf(bj, dpj, acc[1][j]); acc[2][j] = fmaf(cj, dpj, acc[2][j]);
+        acc[3][j] = fmaf(aj, d0[j], acc[3][j]); acc[4][j] = fmaf(bj, d0[j], acc[4][j]); acc[5][j] = fmaf(cj, d0[j], acc[5][j]);
+        acc[6][j] = fmaf(aj, dm[j], acc[6][j]); acc[7][j] = fmaf(bj, dm[j], acc[7][j]); acc[8][j] = fmaf(cj, dm[j], acc[8][j]);
+        dm[j] = d0[j]; d0[j] = dpj;
       }
     }
     __syncwarp();

@@ -48,7 +48,8 @@ typedef enum {
   UNET_EPI_CONVT     = 4  /* Conv2DTranspose(k=2,s=2) pixel-shuffle store + bias (+ dropout), u_net.py:88-98 */
 } unet_epilogue;
 
-/* stateless dropout mask: keep(idx) = lowbias32(idx ^ seed-mix) < keep_prob.  rate == 0 disables. */
+/* stateless dropout mask: elements 2k and 2k+1 (linear NHWC offsets in the ctot-wide tensor) share h = lowbias32(k ^ seed-mix);
+   element e keeps iff its 16-bit half of h (low half for even e) < floor((1-rate) * 65536).  rate == 0 disables. */
 typedef struct {
   float    rate;      /* Dropout(rate), u_net.py:78,98 */
   uint32_t seed;

@@ -142,13 +142,17 @@ def dropout_hash(idx: np.ndarray, seed: int) -> np.ndarray:
 
 
 def dropout_multiplier(shape: Tuple[int, int, int, int], rate: float, seed: int) -> np.ndarray:
-    """Mask * 1/(1-rate) over an NHWC tensor, indexed by the element's linear offset (Dropout, u_net.py:78,98)."""
+    """Mask * 1/(1-rate) over an NHWC tensor, indexed by the element's linear offset (Dropout, u_net.py:78,98).
+    Restates dropout_mult() of csrc/common.cuh: one hash per pair of adjacent elements (2k, 2k+1); element e keeps iff
+    its 16-bit half (low half for even e) is below floor(keep_prob * 65536)."""
     n = int(np.prod(shape))
-    h = dropout_hash(np.arange(n, dtype=np.uint64), seed)
-    u = (h >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    idx = np.arange(n, dtype=np.uint64)
+    h = dropout_hash(idx >> np.uint64(1), seed)
+    r = np.where((idx & np.uint64(1)) == 1, h >> np.uint32(16), h & np.uint32(0xFFFF)).astype(np.uint32)
     keep = np.float32(1.0 - rate)
+    thr = np.uint32(np.float32(keep) * np.float32(65536.0))
     inv = np.float32(1.0) / keep
-    return np.where(u < keep, inv, np.float32(0)).astype(np.float32).reshape(shape)
+    return np.where(r < thr, inv, np.float32(0)).astype(np.float32).reshape(shape)
 
 
 # ----------------------------------------------------------------------------------------------- primitive ops

@@ -74,15 +74,36 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
 template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
 
 // ---------------------------------------------------------------- dropout mask (stateless, reproducible on host)
+// One 32-bit hash serves TWO adjacent elements (indices 2k, 2k+1): element e keeps iff its 16-bit half of the hash of
+// pair k is below floor(keep_prob * 65536).  (16 bits: |P(keep) - keep_prob| < 2^-16.)
 __host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t idx, uint32_t seed) {
   uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B1u) ^ (seed * 0x85EBCA6Bu + 0xC2B2AE35u);
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;   // lowbias32
   return x;
 }
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float keep_prob) { return static_cast<uint32_t>(keep_prob * 65536.0f); }
 // multiplier for element idx: 0 if dropped, 1/(1-rate) if kept
 __host__ __device__ __forceinline__ float dropout_mult(uint64_t idx, uint32_t seed, float keep_prob, float inv_keep) {
-  const float u = static_cast<float>(dropout_hash(idx, seed) >> 8) * (1.0f / 16777216.0f);
-  return u < keep_prob ? inv_keep : 0.0f;
+  const uint32_t h = dropout_hash(idx >> 1, seed);
+  const uint32_t r = (idx & 1) ? (h >> 16) : (h & 0xffffu);
+  return r < dropout_threshold(keep_prob) ? inv_keep : 0.0f;
+}
+// multipliers of elements even_idx and even_idx + 1 from one hash
+__host__ __device__ __forceinline__ void dropout_mult2(uint64_t even_idx, uint32_t seed, uint32_t thr, float inv_keep, float& m0, float& m1) {
+  const uint32_t h = dropout_hash(even_idx >> 1, seed);
+  m0 = (h & 0xffffu) < thr ? inv_keep : 0.0f;
+  m1 = (h >> 16) < thr ? inv_keep : 0.0f;
+}
+// n consecutive elements starting at an EVEN index (n even)
+template <int N>
+__device__ __forceinline__ void dropout_apply(float (&v)[N], uint64_t even_base, uint32_t seed, float keep_prob, float inv_keep) {
+  const uint32_t thr = dropout_threshold(keep_prob);
+#pragma unroll
+  for (int j = 0; j < N; j += 2) {
+    float m0, m1;
+    dropout_mult2(even_base + j, seed, thr, inv_keep, m0, m1);
+    v[j] *= m0; v[j + 1] *= m1;
+  }
 }
 
 // ---------------------------------------------------------------- reductions

@@ -82,8 +82,7 @@ dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restr
         o[j] = fmaf(k[8][j], c[j], fmaf(k[7][j], b[j], fmaf(k[6][j], a[j], prev[j])));
       if (dp.on) {
         const uint64_t base = (uint64_t)((n * H + (r - 1)) * (int64_t)W + wq) * dp.ctot + dp.c0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
+        dropout_apply(o, base, drop_seed(dp), dp.keep, dp.inv_keep);
       }
       store8(ycol + (r - 1) * yrow, o);
     }
@@ -220,8 +219,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
         for (int j = 0; j < NV; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
         if (DROP) {
           const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
-#pragma unroll
-          for (int j = 0; j < NV; ++j) o[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+          dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
         }
         *reinterpret_cast<uint2*>(yptr) = pack8(o, (T*)nullptr);
       }

@@ -52,58 +52,66 @@ __global__ void bn_finalize_kernel(const double* colsum, const double* colsq, do
 }
 
 // ------------------------------------------------------------------------------------------------ BN apply + ReLU (+pool, +dropout)
+// thread layout inside a block: (256/cv pixel slots) x cv channel groups; a thread keeps its 8 channels' scale/shift in
+// registers and strides over pixels (POOL: over 2x2 windows, four 16-byte loads in flight per window).
 template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
               T* __restrict__ y, int64_t ldy, T* __restrict__ pooled, int N, int H, int W, int C, DropArgs dp) {
   const int cv = C >> 3;
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int c0 = (int)(t % cv) << 3; t /= cv;
+  const int slots = blockDim.x / cv;
+  const int c0 = (threadIdx.x % cv) << 3;
+  const int slot = threadIdx.x / cv;
   float sc[8], sh[8];
+  load8(scale + c0, sc); load8(shift + c0, sh);
+  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
+  const int64_t stride = (int64_t)gridDim.x * slots;
   if (POOL) {
     const int W2 = W >> 1, H2 = H >> 1;
-    const int j2 = (int)(t % W2); t /= W2;
-    const int i2 = (int)(t % H2); const int64_t n = t / H2;
-    if (n >= N) return;
-    load8(scale + c0, sc); load8(shift + c0, sh);
-    float m[8];
+    const int64_t nwin = (int64_t)N * H2 * W2;
+    for (int64_t wi = blockIdx.x * (int64_t)slots + slot; wi < nwin; wi += stride) {
+      const int j2 = (int)(wi % W2); const int64_t t = wi / W2;
+      const int i2 = (int)(t % H2); const int64_t n = t / H2;
+      const int64_t pix0 = (n * H + 2 * i2) * (int64_t)W + 2 * j2;
+      float v[4][8], m[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t pix = (n * H + (2 * i2 + (q >> 1))) * (int64_t)W + 2 * j2 + (q & 1);
-      float v[8];
-      load8(z + pix * C + c0, v);
+      for (int q = 0; q < 4; ++q) load8(z + (pix0 + (q >> 1) * W + (q & 1)) * C + c0, v[q]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v[j] = fmaf(v[j], sc[j], sh[j]);
-        if (relu) v[j] = fmaxf(v[j], 0.f);
-        v[j] = round_to<T>(v[j]);
-        m[j] = q == 0 ? v[j] : fmaxf(m[j], v[j]);
+      for (int q = 0; q < 4; ++q) {
+        const int64_t pix = pix0 + (q >> 1) * W + (q & 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = fmaf(v[q][j], sc[j], sh[j]);
+          if (relu) a = fmaxf(a, 0.f);
+          a = round_to<T>(a);
+          v[q][j] = a;
+          m[j] = q == 0 ? a : fmaxf(m[j], a);
+        }
+        if (dp.on) dropout_apply(v[q], (uint64_t)pix * dp.ctot + dp.c0 + c0, seed, dp.keep, dp.inv_keep);
+        store8(y + pix * ldy + c0, v[q]);
       }
-      if (dp.on) {
-        const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
-      }
-      store8(y + pix * ldy + c0, v);
+      store8(pooled + wi * C + c0, m);
     }
-    store8(pooled + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, m);
   } else {
-    const int64_t pix = t;
-    if (pix >= (int64_t)N * H * W) return;
-    load8(scale + c0, sc); load8(shift + c0, sh);
-    float v[8];
-    load8(z + pix * C + c0, v);
+    const int64_t npix = (int64_t)N * H * W;
+    constexpr int U = 4;
+    for (int64_t p0 = blockIdx.x * (int64_t)slots + slot; p0 < npix; p0 += stride * U) {
+      float v[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      v[j] = fmaf(v[j], sc[j], sh[j]);
-      if (relu) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (dp.on) {
-      const uint64_t base = (uint64_t)pix * dp.ctot + dp.c0 + c0;
+      for (int u = 0; u < U; ++u) if (p0 + u * stride < npix) load8(z + (p0 + u * stride) * C + c0, v[u]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= dropout_mult(base + j, drop_seed(dp), dp.keep, dp.inv_keep);
+      for (int u = 0; u < U; ++u) {
+        const int64_t pix = p0 + u * stride;
+        if (pix >= npix) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[u][j] = fmaf(v[u][j], sc[j], sh[j]);
+          if (relu) v[u][j] = fmaxf(v[u][j], 0.f);
+        }
+        if (dp.on) dropout_apply(v[u], (uint64_t)pix * dp.ctot + dp.c0 + c0, seed, dp.keep, dp.inv_keep);
+        store8(y + pix * ldy + c0, v[u]);
+      }
     }
-    store8(y + pix * ldy + c0, v);
   }
 }
 
@@ -164,8 +172,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict
       unraw(rg[u], g); unraw(rz[u], zz);
       if (dp.on) {
         const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+        dropout_apply(g, base, seed, dp.keep, dp.inv_keep);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -229,8 +236,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict_
       unraw(rg[u], g); unraw(rz[u], zz);
       if (dp.on) {
         const uint64_t base = (uint64_t)r * dp.ctot + dp.c0 + c0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] *= dropout_mult(base + j, seed, dp.keep, dp.inv_keep);
+        dropout_apply(g, base, seed, dp.keep, dp.inv_keep);
       }
       if (norm) {
 #pragma unroll
@@ -276,45 +282,39 @@ maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict
                    const T* __restrict__ dpool, const T* __restrict__ dskip, int64_t lddskip, T* __restrict__ dy,
                    int N, int H, int W, int C) {
   const int cv = C >> 3, W2 = W >> 1, H2 = H >> 1;
-  int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int c0 = (int)(t % cv) << 3; t /= cv;
-  const int j2 = (int)(t % W2); t /= W2;
-  const int i2 = (int)(t % H2); const int64_t n = t / H2;
-  if (n >= N) return;
+  const int slots = blockDim.x / cv;
+  const int c0 = (threadIdx.x % cv) << 3;
+  const int slot = threadIdx.x / cv;
   float sc[8], sh[8];
   const bool aff = scale != nullptr;
   if (aff) { load8(scale + c0, sc); load8(shift + c0, sh); }
-  float v[4][8], dp[8];
-  int64_t pix[4];
+  const int64_t nwin = (int64_t)N * H2 * W2;
+  const int64_t stride = (int64_t)gridDim.x * slots;
+  for (int64_t wi = blockIdx.x * (int64_t)slots + slot; wi < nwin; wi += stride) {
+    const int j2 = (int)(wi % W2); const int64_t t = wi / W2;
+    const int i2 = (int)(t % H2); const int64_t n = t / H2;
+    const int64_t pix0 = (n * H + 2 * i2) * (int64_t)W + 2 * j2;
+    float v[4][8], o[4][8], dp[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    pix[q] = (n * H + (2 * i2 + (q >> 1))) * (int64_t)W + 2 * j2 + (q & 1);
-    load8(z + pix[q] * ldz + c0, v[q]);
-    if (aff) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[q][j] = round_to<T>(fmaxf(fmaf(v[q][j], sc[j], sh[j]), 0.f));
+    for (int q = 0; q < 4; ++q) {                       // nine 16-byte loads in flight
+      const int64_t pix = pix0 + (q >> 1) * W + (q & 1);
+      load8(z + pix * ldz + c0, v[q]);
+      if (dskip) load8(dskip + pix * lddskip + c0, o[q]);
     }
-  }
-  load8(dpool + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, dp);
-  int arg[8];
+    load8(dpool + wi * C + c0, dp);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {   // first maximum in window scan order (TF CPU convention)
-    int a = 0; float m = v[0][j];
+    for (int j = 0; j < 8; ++j) {   // first maximum in window scan order (TF CPU convention)
+      float a[4];
 #pragma unroll
-    for (int q = 1; q < 4; ++q) if (v[q][j] > m) { m = v[q][j]; a = q; }
-    arg[j] = a;
-  }
+      for (int q = 0; q < 4; ++q) a[q] = aff ? round_to<T>(fmaxf(fmaf(v[q][j], sc[j], sh[j]), 0.f)) : v[q][j];
+      int arg = 0; float m = a[0];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float o[8];
-    if (dskip) load8(dskip + pix[q] * lddskip + c0, o);
-    else {
+      for (int q = 1; q < 4; ++q) if (a[q] > m) { m = a[q]; arg = q; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      for (int q = 0; q < 4; ++q) o[q][j] = (dskip ? o[q][j] : 0.f) + (arg == q ? dp[j] : 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) if (arg[j] == q) o[j] += dp[j];
-    store8(dy + pix[q] * C + c0, o);
+    for (int q = 0; q < 4; ++q) store8(dy + (pix0 + (q >> 1) * W + (q & 1)) * C + c0, o[q]);
   }
 }
 
@@ -524,15 +524,15 @@ extern "C" int unet_bn_finalize(const double* colsum, const double* colsq, int64
 template <typename T>
 static int bn_act_launch(const void* z, const float* scale, const float* shift, int relu, void* y, int64_t ldy,
                          void* pooled, int N, int H, int W, int C, DropArgs dp, cudaStream_t st) {
-  const int cv = C / 8;
+  const int cv = C / 8, slots = 256 / cv;
   if (pooled) {
-    const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * cv;
-    bn_act_kernel<T, true><<<grid_for(threads), 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, (T*)pooled,
-                                                             N, H, W, C, dp);
+    const int64_t items = (int64_t)N * (H / 2) * (W / 2);
+    const unsigned grid = (unsigned)i64min(ceil_div(items, slots), (int64_t)sm_count() * 16);
+    bn_act_kernel<T, true><<<grid, 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, (T*)pooled, N, H, W, C, dp);
   } else {
-    const int64_t threads = (int64_t)N * H * W * cv;
-    bn_act_kernel<T, false><<<grid_for(threads), 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, nullptr,
-                                                              N, H, W, C, dp);
+    const int64_t items = (int64_t)N * H * W;
+    const unsigned grid = (unsigned)i64min(ceil_div(items, (int64_t)slots * 4), (int64_t)sm_count() * 16);
+    bn_act_kernel<T, false><<<grid, 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, nullptr, N, H, W, C, dp);
   }
   UNET_LAUNCH_CHECK("bn_act");
   return UNET_OK;
@@ -545,6 +545,7 @@ extern "C" int unet_bn_act(const void* z, const float* scale, const float* shift
   UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && ldy >= C, UNET_EINVAL, "bn_act: bad dims");
   UNET_REQUIRE(C % 8 == 0 && ldy % 8 == 0 && aligned16(z) && aligned16(y), UNET_EALIGN, "bn_act: needs C%%8==0, ld%%8==0, 16B pointers");
   UNET_REQUIRE(!pooled || (H % 2 == 0 && W % 2 == 0), UNET_EINVAL, "bn_act: pooling needs even H,W");
+  UNET_REQUIRE(256 % (C / 8) == 0, UNET_EUNSUPPORTED, "bn_act: C/8 must divide 256 (C=%d)", C);
   const DropArgs dp = make_drop(drop);
   if (dtype == UNET_F32)  return bn_act_launch<float>(z, scale, shift, relu, y, ldy, pooled, N, H, W, C, dp, ST);
   if (dtype == UNET_BF16) return bn_act_launch<__nv_bfloat16>(z, scale, shift, relu, y, ldy, pooled, N, H, W, C, dp, ST);
@@ -623,14 +624,16 @@ extern "C" int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scal
   UNET_REQUIRE(H % 2 == 0 && W % 2 == 0, UNET_EINVAL, "maxpool2x2_bwd: needs even H,W");
   UNET_REQUIRE(C % 8 == 0 && ldz % 8 == 0 && (!dskip || lddskip % 8 == 0), UNET_EALIGN, "maxpool2x2_bwd: needs C%%8==0, ld%%8==0");
   UNET_REQUIRE((scale == nullptr) == (shift == nullptr), UNET_EINVAL, "maxpool2x2_bwd: scale/shift must come together");
-  const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
+  UNET_REQUIRE(256 % (C / 8) == 0, UNET_EUNSUPPORTED, "maxpool2x2_bwd: C/8 must divide 256 (C=%d)", C);
+  const int64_t items = (int64_t)N * (H / 2) * (W / 2);
+  const unsigned grid = (unsigned)i64min(ceil_div(items, 256 / (C / 8)), (int64_t)sm_count() * 16);
   if (dtype == UNET_F32)
-    maxpool_bwd_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)z, ldz, scale, shift, (const float*)dpool,
-                                                                (const float*)dskip, lddskip, (float*)dy, N, H, W, C);
+    maxpool_bwd_kernel<float><<<grid, 256, 0, ST>>>((const float*)z, ldz, scale, shift, (const float*)dpool,
+                                                   (const float*)dskip, lddskip, (float*)dy, N, H, W, C);
   else if (dtype == UNET_BF16)
-    maxpool_bwd_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)z, ldz, scale, shift,
-                                                                        (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)dskip,
-                                                                        lddskip, (__nv_bfloat16*)dy, N, H, W, C);
+    maxpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)z, ldz, scale, shift,
+                                                           (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)dskip,
+                                                           lddskip, (__nv_bfloat16*)dy, N, H, W, C);
   else return set_error(UNET_EINVAL, "maxpool2x2_bwd: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("maxpool2x2_bwd");
   return UNET_OK;

@@ -125,8 +125,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
       const int64_t pix = ((int64_t)img * 2 * ch + 2 * ii + (cv_ab >> 1)) * (2 * cw) + 2 * jj + (cv_ab & 1);
       if (p.drop_on) {
         const uint64_t base = (uint64_t)pix * p.ctot + p.c0 + cv_co;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] *= dropout_mult(base + j, p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), p.keep, p.inv_keep);
+        dropout_apply(v, base, p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), p.keep, p.inv_keep);
       }
       off = pix * p.ldc + cv_co;
     } else {
@@ -391,10 +390,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.drop_on) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] *= dropout_mult(drop_base + half * 32 + i, seed, p.keep, p.inv_keep);
-            }
+            if (p.drop_on) dropout_apply(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
           }
           if (OUT_BF16) {
 #pragma unroll

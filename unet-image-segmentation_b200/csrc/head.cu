@@ -13,7 +13,7 @@ namespace unet {
 constexpr int kHeadMaxK = 512;
 
 template <typename T, int MAXC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXC == 1 ? 3 : 1)
 head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
                 int64_t hw, int K, int C, int pix_per_block) {
@@ -35,48 +35,65 @@ head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) { si[c] = 0.f; st[c] = 0.f; sp[c] = 0.f; }
 
-  for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
-    const int64_t p = p0 + slot;
-    const bool live = p < p_end;
-    const int64_t m = n * hw + (live ? p : p_begin);
-    float acc[MAXC];
+  constexpr int U = 4;                                  // pixel slots per trip: U independent 16-byte loads in flight
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += 32 * U) {
+    float acc[U][MAXC];
+    int64_t mrow[U];
+    bool live[U];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * 32 + slot;
+      live[u] = p < p_end;
+      mrow[u] = n * hw + (live[u] ? p : p_begin);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) acc[u][c] = 0.f;
+    }
     for (int k0 = sub * 8; k0 < K; k0 += 64) {
-      float v[8];
-      load8(x + m * ldx + k0, v);
+      float v[U][8], wk[8][MAXC];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load8(x + mrow[u] * ldx + k0, v[u]);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) acc[c] = fmaf(v[j], s_w[(k0 + j) * MAXC + c], acc[c]);
+        for (int c = 0; c < MAXC; ++c) wk[j][c] = s_w[(k0 + j) * MAXC + c];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) acc[u][c] = fmaf(v[u][j], wk[j][c], acc[u][c]);
     }
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
-      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 4);
-    }
-    if (live && sub == 0) {
-      float pr[MAXC];
-      if (C == 1) {
-        pr[0] = 1.f / (1.f + expf(-(acc[0] + s_b[0])));
-      } else {
-        float mx = -INFINITY;
+    for (int u = 0; u < U; ++u) {
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) if (c < C) { acc[c] += s_b[c]; mx = fmaxf(mx, acc[c]); }
-        float den = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) if (c < C) { pr[c] = expf(acc[c] - mx); den += pr[c]; }
-        const float inv = 1.f / den;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) if (c < C) pr[c] *= inv;
+      for (int c = 0; c < MAXC; ++c) {
+        acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], 1);
+        acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], 2);
+        acc[u][c] += __shfl_xor_sync(0xffffffffu, acc[u][c], 4);
       }
+      if (live[u] && sub == 0) {
+        const int64_t m = mrow[u];
+        float pr[MAXC];
+        if (C == 1) {
+          pr[0] = 1.f / (1.f + expf(-(acc[u][0] + s_b[0])));
+        } else {
+          float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < MAXC; ++c) if (c < C) {
-        probs[m * C + c] = pr[c];
-        if (y_true) {
-          const float t = y_true[m * C + c];
-          si[c] = fmaf(t, pr[c], si[c]); st[c] += t; sp[c] += pr[c];
+          for (int c = 0; c < MAXC; ++c) if (c < C) { acc[u][c] += s_b[c]; mx = fmaxf(mx, acc[u][c]); }
+          float den = 0.f;
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) if (c < C) { pr[c] = expf(acc[u][c] - mx); den += pr[c]; }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) if (c < C) pr[c] *= inv;
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) if (c < C) {
+          probs[m * C + c] = pr[c];
+          if (y_true) {
+            const float t = y_true[m * C + c];
+            si[c] = fmaf(t, pr[c], si[c]); st[c] += t; sp[c] += pr[c];
+          }
         }
       }
     }
@@ -99,7 +116,7 @@ head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
 }
 
 template <typename T, int MAXC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, MAXC == 1 ? 3 : 1)
 head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ probs,
                 const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
                 float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block) {
@@ -133,41 +150,59 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) dwacc[j][c] = 0.f;
-    for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
-      const int64_t p = p0 + slot;
-      if (p >= p_end) continue;
-      const int64_t m = n * hw + p;
-      float dz[MAXC];
-      if (C == 1) {
-        const float pr = probs[m], t = y_true[m];
-        dz[0] = fmaf(ca[0], t, cb[0]) * pr * (1.f - pr);
-      } else {
-        float pr[MAXC], gl[MAXC], dot = 0.f;
+    constexpr int U = 4;                                // pixel slots per trip, loads issued before use
+    float wk[8][MAXC];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) if (c < C) {
-          pr[c] = probs[m * C + c];
-          gl[c] = fmaf(ca[c], y_true[m * C + c], cb[c]);
-          dot = fmaf(gl[c], pr[c], dot);
-        }
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) dz[c] = c < C ? pr[c] * (gl[c] - dot) : 0.f;
+      for (int c = 0; c < MAXC; ++c) wk[j][c] = s_w[(k0 + j) * MAXC + c];
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += 32 * U) {
+      float v[U][8], dz[U][MAXC];
+      int64_t mrow[U];
+      bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t p = p0 + u * 32 + slot;
+        live[u] = p < p_end;
+        mrow[u] = n * hw + (live[u] ? p : p_begin);
+        load8(x + mrow[u] * ldx + k0, v[u]);
       }
-      float v[8], o[8];
-      load8(x + m * ldx + k0, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float s = 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int64_t m = mrow[u];
+        if (C == 1) {
+          const float pr = __ldg(probs + m), t = __ldg(y_true + m);
+          dz[u][0] = live[u] ? fmaf(ca[0], t, cb[0]) * pr * (1.f - pr) : 0.f;
+        } else {
+          float pr[MAXC], gl[MAXC], dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-          s = fmaf(dz[c], s_w[(k0 + j) * MAXC + c], s);
-          dwacc[j][c] = fmaf(v[j], dz[c], dwacc[j][c]);
+          for (int c = 0; c < MAXC; ++c) if (c < C) {
+            pr[c] = __ldg(probs + m * C + c);
+            gl[c] = fmaf(ca[c], __ldg(y_true + m * C + c), cb[c]);
+            dot = fmaf(gl[c], pr[c], dot);
+          }
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) dz[u][c] = (c < C && live[u]) ? pr[c] * (gl[c] - dot) : 0.f;
         }
-        o[j] = s;
       }
-      if (dx) store8(dx + m * lddx + k0, o);
-      if (k0 == sub * 8 && sub == 0) {
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) dbs[c] += dz[c];
+      for (int u = 0; u < U; ++u) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float sacc = 0.f;
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) {
+            sacc = fmaf(dz[u][c], wk[j][c], sacc);
+            dwacc[j][c] = fmaf(v[u][j], dz[u][c], dwacc[j][c]);
+          }
+          o[j] = sacc;
+        }
+        if (dx && live[u]) store8(dx + mrow[u] * lddx + k0, o);
+        if (k0 == sub * 8 && sub == 0) {
+#pragma unroll
+          for (int c = 0; c < MAXC; ++c) dbs[c] += dz[u][c];
+        }
       }
     }
     // lanes 8 apart share `sub`: fold them, then one shared atomic per (channel, class) per warp
@@ -191,11 +226,11 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
 }
 
-static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block) {
+static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block, int waves = 16) {
   // enough blocks to fill the machine ~4x, each block a multiple of 32 pixels inside one image
-  int64_t blocks_per_img = i64max(1, ceil_div((int64_t)sm_count() * 4, NB));
+  int64_t blocks_per_img = i64max(1, ceil_div((int64_t)sm_count() * waves, NB));
   int64_t ppb = ceil_div(ceil_div(hw, blocks_per_img), 32) * 32;
-  if (ppb < 256) ppb = 256;
+  if (ppb < 512) ppb = 512;
   blocks_per_img = ceil_div(hw, ppb);
   *grid = dim3((unsigned)blocks_per_img, (unsigned)NB);
   *pix_per_block = (int)ppb;
@@ -235,7 +270,7 @@ extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const f
   UNET_REQUIRE(K <= kHeadMaxK && C <= 8, UNET_EUNSUPPORTED, "head_bwd: K <= %d and num_classes <= 8", kHeadMaxK);
   UNET_REQUIRE(M / hw <= 65535, UNET_EUNSUPPORTED, "head_bwd: batch <= 65535");
   dim3 grid; int ppb;
-  head_grid(M / hw, hw, &grid, &ppb);
+  head_grid(M / hw, hw, &grid, &ppb, 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(T, MC) head_bwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
   if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH(float, 8); }

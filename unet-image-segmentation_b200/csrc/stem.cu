@@ -42,9 +42,9 @@ __device__ __forceinline__ void stem_depthwise(const float* s_x, const float* s_
   for (int ci = 0; ci < kStemCin; ++ci) s_d[threadIdx.x * kStemCin + ci] = d[ci];
 }
 
-// mode 0: out = z, statistics;  mode 1: out = act(z*scale+shift)
-template <typename T>
-__global__ void __launch_bounds__(256)
+// STATS: out = z and batch statistics;  otherwise: out = act(z*scale+shift)
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(256, 4)
 stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const float* __restrict__ wp, T* __restrict__ out,
                 int64_t ldo, int N, int H, int W, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                 double* __restrict__ colsum, double* __restrict__ colsq, int tiles_h, int tiles_w) {
@@ -55,15 +55,13 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
   if (threadIdx.x < 9 * kStemCin) s_wd[threadIdx.x] = wd9c[threadIdx.x];
   if (threadIdx.x < 2 * kStemCout) s_stat[threadIdx.x] = 0.f;
   const int cg = threadIdx.x & 7, pslot = threadIdx.x >> 3;       // 8 channel groups x 32 pixel slots
-  float w[kStemCin][8], sc[8], sh[8], ssum[8], ssq[8];
+  float w[kStemCin][8], sa[8], sb[8];            // STATS: running sum / sum of squares;  else: scale / shift
 #pragma unroll
   for (int ci = 0; ci < kStemCin; ++ci) load8(wp + ci * kStemCout + cg * 8, w[ci]);
-  const bool affine = scale != nullptr || shift != nullptr;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; ssum[j] = 0.f; ssq[j] = 0.f; }
-  if (scale) load8(scale + cg * 8, sc);
-  if (shift) load8(shift + cg * 8, sh);
-  const bool stats = colsum != nullptr;
+  for (int j = 0; j < 8; ++j) { sa[j] = STATS ? 0.f : 1.f; sb[j] = 0.f; }
+  if (!STATS && scale) load8(scale + cg * 8, sa);
+  if (!STATS && shift) load8(shift + cg * 8, sb);
   const int64_t total = (int64_t)N * tiles_h * tiles_w;
   for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
     const int tw = (int)(t % tiles_w); const int64_t q = t / tiles_w;
@@ -84,27 +82,27 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float v = fmaf(d2, w[2][j], fmaf(d1, w[1][j], d0 * w[0][j]));
-        if (affine) { v = fmaf(v, sc[j], sh[j]); if (relu) v = fmaxf(v, 0.f); }
+        if (!STATS) { v = fmaf(v, sa[j], sb[j]); if (relu) v = fmaxf(v, 0.f); }
         o[j] = v;
       }
       store8(out + (((int64_t)n * H + hh) * W + ww) * ldo + cg * 8, o);
-      if (stats) {
+      if (STATS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float r = round_to<T>(o[j]); ssum[j] += r; ssq[j] = fmaf(r, r, ssq[j]); }
+        for (int j = 0; j < 8; ++j) { const float r = round_to<T>(o[j]); sa[j] += r; sb[j] = fmaf(r, r, sb[j]); }
       }
     }
   }
-  if (stats) {
+  if (STATS) {
     // lanes with equal cg (lane & 7) hold the same channels: fold 4 pixel slots per warp, then shared, then global
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 8); ssum[j] += __shfl_xor_sync(0xffffffffu, ssum[j], 16);
-      ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 8);   ssq[j] += __shfl_xor_sync(0xffffffffu, ssq[j], 16);
+      sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], 8); sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], 16);
+      sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], 8); sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], 16);
     }
     __syncthreads();
     if ((threadIdx.x & 31) < 8) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { atomicAdd(&s_stat[cg * 8 + j], ssum[j]); atomicAdd(&s_stat[kStemCout + cg * 8 + j], ssq[j]); }
+      for (int j = 0; j < 8; ++j) { atomicAdd(&s_stat[cg * 8 + j], sa[j]); atomicAdd(&s_stat[kStemCout + cg * 8 + j], sb[j]); }
     }
     __syncthreads();
     if (threadIdx.x < kStemCout) {
@@ -114,8 +112,26 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
   }
 }
 
+template <typename T> struct StemRaw;
+template <> struct StemRaw<__nv_bfloat16> { uint4 a; };
+template <> struct StemRaw<float> { float4 a, b; };
+__device__ __forceinline__ void ldraw8(const __nv_bfloat16* p, StemRaw<__nv_bfloat16>& r) { r.a = __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void ldraw8(const float* p, StemRaw<float>& r) {
+  r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+}
+__device__ __forceinline__ void zero8(StemRaw<__nv_bfloat16>& r) { r.a = make_uint4(0u, 0u, 0u, 0u); }
+__device__ __forceinline__ void zero8(StemRaw<float>& r) { r.a = make_float4(0.f, 0.f, 0.f, 0.f); r.b = r.a; }
+__device__ __forceinline__ void unraw8(const StemRaw<__nv_bfloat16>& r, float (&v)[8]) {
+  const uint32_t u[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ void unraw8(const StemRaw<float>& r, float (&v)[8]) {
+  v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz, const float* __restrict__ wd9c,
                 const float* __restrict__ wp, float* __restrict__ dwd9c, float* __restrict__ dwp, int N, int H, int W,
                 int tiles_h, int tiles_w) {
@@ -144,23 +160,26 @@ stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz,
     const int tw = (int)(t % tiles_w); const int64_t q = t / tiles_w;
     const int th = (int)(q % tiles_h); const int n = (int)(q / tiles_h);
     const int h0 = th * kTH, w0 = tw * kTW;
+    StemRaw<T> graw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int p = pslot + 32 * i;
+      const int hh = h0 + (p >> 5), ww = w0 + (p & 31);
+      if (hh < H && ww < W) ldraw8(dz + (((int64_t)n * H + hh) * W + ww) * lddz + cg * 8, graw[i]);
+      else zero8(graw[i]);
+    }
     __syncthreads();
     stem_load_tile<T>(x, n, h0, w0, H, W, s_x);
     __syncthreads();
     stem_depthwise(s_x, s_wd, s_d);
     __syncthreads();
-    // pointwise gradient and dd = dz . Wp^T
+    // pointwise gradient and dd = dz . Wp^T  (the tile's eight 16-byte dz loads are issued before the first use; they
+    // were started before the depthwise phase so that their latency overlaps the two barriers above)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int p = pslot + 32 * i;
-      const int hh = h0 + (p >> 5), ww = w0 + (p & 31);
       float g[8];
-      const bool live = hh < H && ww < W;
-      if (live) load8(dz + (((int64_t)n * H + hh) * W + ww) * lddz + cg * 8, g);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = 0.f;
-      }
+      unraw8(graw[i], g);
       const float d0 = s_d[p * 3], d1 = s_d[p * 3 + 1], d2 = s_d[p * 3 + 2];
       float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
 #pragma unroll
@@ -234,13 +253,13 @@ extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, 
                UNET_EALIGN, "stem_fwd: out / parameters must be 16B aligned, ldo%%8==0");
   const int th = (int)ceil_div(H, kTH), tw = (int)ceil_div(W, kTW);
   const int64_t tiles = (int64_t)N * th * tw;
-  const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 6);
+  const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == UNET_F32)
-    stem_fwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, wd9c, wp, (float*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw);
-  else if (dtype == UNET_BF16)
-    stem_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, wd9c, wp, (__nv_bfloat16*)out, ldo, N, H, W, scale,
-                                                        shift, relu, colsum, colsq, th, tw);
+  UNET_REQUIRE(!(colsum && (scale || shift)), UNET_EINVAL, "stem_fwd: statistics are taken on the raw contraction (no scale/shift)");
+#define STEM_FWD(T, S) stem_fwd_kernel<T, S><<<grid, 256, 0, st>>>((const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw)
+  if (dtype == UNET_F32) { if (colsum) STEM_FWD(float, true); else STEM_FWD(float, false); }
+  else if (dtype == UNET_BF16) { if (colsum) STEM_FWD(__nv_bfloat16, true); else STEM_FWD(__nv_bfloat16, false); }
+#undef STEM_FWD
   else return set_error(UNET_EINVAL, "stem_fwd: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("stem_fwd");
   return UNET_OK;

@@ -73,5 +73,21 @@ elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
         run(lambda: ops.bn_bwd_apply(dy, z, sc, sh, mu, rs, dg, db, dz), 3 * M * 64 * 2)
     else:
         run(lambda: ops.bn_act(z, sc, sh, dz), 2 * M * 64 * 2)
+elif name in ("head8_fwd", "head8_bwd", "head1_fwd", "head1_bwd"):
+    C = 8 if "8" in name else 1
+    Bh = 32
+    Mh = Bh * H * W
+    x = rnd(Bh, H, W, 64)
+    wk, bk = torch.rand((64, C), device=dev) - 0.5, torch.zeros(C, device=dev)
+    probs = torch.empty((Bh, H, W, C), device=dev)
+    yt = (torch.rand((Bh, H, W, C), device=dev) > 0.5).float()
+    sums = torch.zeros((Bh, C, 3), device=dev, dtype=torch.float64)
+    coef = torch.rand((Bh, C, 2), device=dev)
+    dx = torch.empty_like(x); dw = torch.zeros((64, C), device=dev); db = torch.zeros(C, device=dev)
+    ops.head_fwd(x, wk, bk, probs, yt, sums)
+    if name.endswith("fwd"):
+        run(lambda: ops.head_fwd(x, wk, bk, probs, yt, sums), Mh * (128 + 8 * C))
+    else:
+        run(lambda: ops.head_bwd(x, wk, probs, yt, coef, dx, dw, db), Mh * (256 + 8 * C))
 else:
     raise SystemExit(f"unknown kernel {name}")

@@ -226,6 +226,181 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------------ multi-class head (2 <= C <= 8)
+// Same 8-lanes-per-pixel layout, but after the contraction the 8 lanes of a pixel each OWN one class: partial logits are
+// combined with a 7-shuffle reduce-scatter, softmax runs across the 8 lanes (max / sum by butterfly), and probabilities,
+// y_true and the Dice sums are touched as one coalesced 32-byte segment per pixel.
+// weight row r (8 class slots, 32 B) lives at float offset r*8 + (r/8)*4: the 8 lanes of a pixel read rows 8 apart, and the
+// 16-byte pad per 8 rows spreads them over all banks (conflict-free 16-byte loads)
+__device__ __forceinline__ int mc_row(int r) { return r * 8 + ((r >> 3) << 2); }
+constexpr int kMcWeightFloats = kHeadMaxK * 8 + (kHeadMaxK / 8) * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+head_fwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
+                   float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
+                   int64_t hw, int K, int C, int pix_per_block) {
+  __shared__ __align__(16) float s_w[kMcWeightFloats];
+  __shared__ double s_sum[8 * 3];
+  for (int i = threadIdx.x; i < K * 8; i += blockDim.x) s_w[mc_row(i >> 3) + (i & 7)] = (i & 7) < C ? w[(i >> 3) * C + (i & 7)] : 0.f;
+  if (threadIdx.x < 24) s_sum[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const float bias = (sub < C && b) ? b[sub] : 0.f;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+  float si = 0.f, st = 0.f, sp = 0.f;
+  constexpr int U = 2;
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += 32 * U) {
+    float acc[U][8];
+    int64_t mrow[U]; bool live[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t p = p0 + u * 32 + slot;
+      live[u] = p < p_end;
+      mrow[u] = n * hw + (live[u] ? p : p_begin);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[u][c] = 0.f;
+    }
+    for (int k0 = sub * 8; k0 < K; k0 += 64) {
+      float v[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) load8(x + mrow[u] * ldx + k0, v[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j)]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j) + 4]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          acc[u][0] = fmaf(v[u][j], w0.x, acc[u][0]); acc[u][1] = fmaf(v[u][j], w0.y, acc[u][1]);
+          acc[u][2] = fmaf(v[u][j], w0.z, acc[u][2]); acc[u][3] = fmaf(v[u][j], w0.w, acc[u][3]);
+          acc[u][4] = fmaf(v[u][j], w1.x, acc[u][4]); acc[u][5] = fmaf(v[u][j], w1.y, acc[u][5]);
+          acc[u][6] = fmaf(v[u][j], w1.z, acc[u][6]); acc[u][7] = fmaf(v[u][j], w1.w, acc[u][7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // reduce-scatter over the 8 lanes of the pixel: lane `sub` ends with the full logit of class `sub`
+      float r4[4], r2[2], logit;
+      const bool hi4 = sub & 4, hi2 = sub & 2, hi1 = sub & 1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = hi4 ? acc[u][i] : acc[u][i + 4];
+        const float keep = hi4 ? acc[u][i + 4] : acc[u][i];
+        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float send = hi2 ? r4[i] : r4[i + 2];
+        const float keep = hi2 ? r4[i + 2] : r4[i];
+        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const float send = hi1 ? r2[0] : r2[1];
+        const float keep = hi1 ? r2[1] : r2[0];
+        logit = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      logit = sub < C ? logit + bias : -INFINITY;
+      float mx = logit;
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      const float e = sub < C ? expf(logit - mx) : 0.f;
+      float den = e;
+      den += __shfl_xor_sync(0xffffffffu, den, 1); den += __shfl_xor_sync(0xffffffffu, den, 2); den += __shfl_xor_sync(0xffffffffu, den, 4);
+      const float pr = e / den;
+      if (live[u] && sub < C) {
+        probs[mrow[u] * C + sub] = pr;
+        if (y_true) {
+          const float t = __ldg(y_true + mrow[u] * C + sub);
+          si = fmaf(t, pr, si); st += t; sp += pr;
+        }
+      }
+    }
+  }
+  if (y_true && sums) {
+    // lanes with equal `sub` own the same class
+    si += __shfl_xor_sync(0xffffffffu, si, 8); si += __shfl_xor_sync(0xffffffffu, si, 16);
+    st += __shfl_xor_sync(0xffffffffu, st, 8); st += __shfl_xor_sync(0xffffffffu, st, 16);
+    sp += __shfl_xor_sync(0xffffffffu, sp, 8); sp += __shfl_xor_sync(0xffffffffu, sp, 16);
+    if ((threadIdx.x & 31) < 8 && sub < C) {
+      atomicAdd(&s_sum[sub * 3 + 0], (double)si); atomicAdd(&s_sum[sub * 3 + 1], (double)st); atomicAdd(&s_sum[sub * 3 + 2], (double)sp);
+    }
+    __syncthreads();
+    if (threadIdx.x < C * 3) atomicAdd(&sums[n * C * 3 + threadIdx.x], s_sum[threadIdx.x]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ probs,
+                   const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
+                   float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block) {
+  __shared__ __align__(16) float s_w[kMcWeightFloats];
+  __shared__ float s_dw[kHeadMaxK * 8];
+  __shared__ float s_db[8];
+  for (int i = threadIdx.x; i < K * 8; i += blockDim.x) { s_w[mc_row(i >> 3) + (i & 7)] = (i & 7) < C ? w[(i >> 3) * C + (i & 7)] : 0.f; s_dw[i] = 0.f; }
+  if (threadIdx.x < 8) s_db[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3, lane = threadIdx.x & 31;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+  const float ca = sub < C ? coef[(n * C + sub) * 2] : 0.f, cb = sub < C ? coef[(n * C + sub) * 2 + 1] : 0.f;
+  float dbs = 0.f;
+  for (int k0 = sub * 8; k0 < K; k0 += 64) {
+    float dwacc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dwacc[j][c] = 0.f;
+    for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
+      const int64_t p = p0 + slot;
+      const bool live = p < p_end;
+      const int64_t m = n * hw + (live ? p : p_begin);
+      float v[8];
+      load8(x + m * ldx + k0, v);
+      // lane `sub` owns class `sub`: dz_c = p_c (g_c - sum_c' g_c' p_c')
+      float pr = 0.f, g = 0.f;
+      if (sub < C) { pr = __ldg(probs + m * C + sub); g = fmaf(ca, __ldg(y_true + m * C + sub), cb); }
+      float dot = g * pr;
+      dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2); dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+      const float dz_own = live ? pr * (g - dot) : 0.f;
+      float dz[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dz[c] = __shfl_sync(0xffffffffu, dz_own, (lane & ~7) + c);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j)]);      // 16-byte shared loads, 8 distinct rows per warp
+        const float4 w1 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j) + 4]);
+        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        float sacc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { sacc = fmaf(dz[c], wk[c], sacc); dwacc[j][c] = fmaf(v[j], dz[c], dwacc[j][c]); }
+        o[j] = sacc;
+      }
+      if (dx && live) store8(dx + m * lddx + k0, o);
+      if (k0 == sub * 8) dbs += dz_own;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float sacc = dwacc[j][c];
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+        if (lane < 8) atomicAdd(&s_dw[(k0 + j) * 8 + c], sacc);
+      }
+  }
+  dbs += __shfl_xor_sync(0xffffffffu, dbs, 8); dbs += __shfl_xor_sync(0xffffffffu, dbs, 16);
+  if (lane < 8 && sub < C) atomicAdd(&s_db[sub], dbs);
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(&dw[i], s_dw[(i / C) * 8 + (i % C)]);
+  if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
+}
+
 static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block, int waves = 16) {
   // enough blocks to fill the machine ~4x, each block a multiple of 32 pixels inside one image
   int64_t blocks_per_img = i64max(1, ceil_div((int64_t)sm_count() * waves, NB));
@@ -252,8 +427,10 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
   head_grid(M / hw, hw, &grid, &ppb);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(T, MC) head_fwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
-  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH(float, 8); }
-  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH(__nv_bfloat16, 8); }
+#define LAUNCH_MC(T) head_fwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
+  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }
+  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH_MC(__nv_bfloat16); }
+#undef LAUNCH_MC
   else return set_error(UNET_EINVAL, "head_fwd: bad dtype %d", dtype);
 #undef LAUNCH
   UNET_LAUNCH_CHECK("head_fwd");
@@ -273,8 +450,10 @@ extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const f
   head_grid(M / hw, hw, &grid, &ppb, 8);
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH(T, MC) head_bwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
-  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH(float, 8); }
-  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH(__nv_bfloat16, 8); }
+#define LAUNCH_MC(T) head_bwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
+  if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }
+  else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH_MC(__nv_bfloat16); }
+#undef LAUNCH_MC
   else return set_error(UNET_EINVAL, "head_bwd: bad dtype %d", dtype);
 #undef LAUNCH
   UNET_LAUNCH_CHECK("head_bwd");

@@ -91,6 +91,8 @@ class UNetEngine:
         self._drop_seed = {name: (seed * 7919 + i * 104729) & 0x7FFFFFFF
                            for i, name in enumerate(["bneck_dropout", "dec4_dropout", "dec3_dropout", "dec2_dropout"])}
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
+        self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
+        self._graphs: Dict[tuple, tuple] = {}
         self.grad_hook = None                   # callable(region) — dist.GradSync.ready; regions: decoder, bottleneck, encoder
         self.init_weights(seed)
 
@@ -256,7 +258,31 @@ class UNetEngine:
         return y
 
     def forward_inference(self, x: torch.Tensor) -> torch.Tensor:
-        """x: device fp32 [B,H,W,Cin] -> probabilities fp32 [B,H,W,classes] (plan-owned buffer, valid until the next call)."""
+        """x: device fp32 [B,H,W,Cin] -> probabilities fp32 [B,H,W,classes] (plan-owned buffer, valid until the next call).
+        With `use_graphs` the launch sequence of a batch size is captured once into a CUDA graph and replayed."""
+        if not self.use_graphs or ops._prof is not None:
+            return self._forward_inference_eager(x)
+        B = x.shape[0]
+        self._restage(); self._refold()              # parameter staging stays outside the graph (it is conditional)
+        key = ("infer", B)
+        ent = self._graphs.get(key)
+        if ent is None:
+            pl = self._plan(B, False)
+            gx = pl.buf("graph_x", tuple(x.shape), torch.float32)
+            gx.copy_(x)
+            out = self._forward_inference_eager(gx)          # warm-up: allocates every buffer, sets kernel attributes
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._forward_inference_eager(gx)
+            ent = self._graphs[key] = (g, gx, out)
+        g, gx, out = ent
+        if x.data_ptr() != gx.data_ptr():
+            gx.copy_(x)
+        g.replay()
+        return out
+
+    def _forward_inference_eager(self, x: torch.Tensor) -> torch.Tensor:
         B = x.shape[0]
         pl = self._plan(B, False)
         self._restage(); self._refold()
@@ -484,8 +510,36 @@ class UNetEngine:
         self._restage()
 
     def train_step(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:
-        out3 = self.train_forward_backward(x, y_true, loss)
-        self.apply_gradients()
+        """forward + backward + AdamW.  Single-GPU steps are replayed from a CUDA graph when `use_graphs` is set (the
+        learning rate, the Adam step count and the dropout seed word live in device memory, so a replay is a new step)."""
+        if not self.use_graphs or self.grad_hook is not None or ops._prof is not None:
+            out3 = self.train_forward_backward(x, y_true, loss)
+            self.apply_gradients()
+            return out3
+        B = x.shape[0]
+        key = ("train", B, loss)
+        ent = self._graphs.get(key)
+        if ent is None:
+            pl = self._plan(B, True)
+            gx = pl.buf("graph_x", tuple(x.shape), torch.float32)
+            gy = pl.buf("graph_y", tuple(y_true.shape), torch.float32)
+            gx.copy_(x); gy.copy_(y_true)
+            out3 = self.train_forward_backward(gx, gy, loss)     # a real (eager) step doubles as the warm-up
+            self.apply_gradients()
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cap = self.train_forward_backward(gx, gy, loss)
+                self.apply_gradients()
+            self._graphs[key] = (g, gx, gy, cap)
+            return out3
+        g, gx, gy, out3 = ent
+        if x.data_ptr() != gx.data_ptr():
+            gx.copy_(x)
+        if y_true.data_ptr() != gy.data_ptr():
+            gy.copy_(y_true)
+        g.replay()
+        self._fold_dirty = True
         return out3
 
     # ------------------------------------------------------------------------------------------------ evaluation
@@ -505,4 +559,5 @@ class UNetEngine:
         return sum(p.bytes() for p in self._plans.values())
 
     def release_plans(self) -> None:
+        self._graphs.clear()
         self._plans.clear()

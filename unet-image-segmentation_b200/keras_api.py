@@ -321,11 +321,14 @@ class _Prefetcher:
     computes.  Two device slots; a slot is rewritten only after the step that read it has been enqueued and has
     finished on the compute stream (event), and a step starts only after its upload has landed (event)."""
 
-    def __init__(self, source):
+    def __init__(self, source, cache: Optional[dict] = None):
         import torch
         self.src = iter(source)
-        self.copy_stream = torch.cuda.Stream()
-        self.slots = [dict(dev={}, pin={}, ready=None, done=None) for _ in range(2)]
+        cache = cache if cache is not None else {}
+        if "stream" not in cache:           # the copy stream and the staging buffers outlive one fit()/evaluate() call
+            cache["stream"] = torch.cuda.Stream()
+            cache["slots"] = [dict(dev={}, pin={}, ready=None, done=None) for _ in range(2)]
+        self.copy_stream, self.slots = cache["stream"], cache["slots"]
         self.h2d_bytes = 0
 
     def _upload(self, batch, slot):
@@ -413,6 +416,7 @@ class Model:
             if self._pending_weights:
                 self._engine.set_weights(self._pending_weights)
                 self._pending_weights = {}
+            self._engine.use_graphs = os.environ.get("UNET_B200_GRAPHS", "1") != "0"
             self._push_hyper()
         return self._engine
 
@@ -567,12 +571,14 @@ class Model:
             raise RuntimeError("You must call `compile()` before using the model for training.")
         eng = self.engine
         xd, yd = self._stage_in(x, "tx"), self._stage_in(y, "ty")
-        out3 = eng.train_forward_backward(xd, yd, self._loss_kind)
-        if self._grad_sync is not None:
+        if self._grad_sync is None:
+            out3 = eng.train_step(xd, yd, self._loss_kind)
+        else:
+            out3 = eng.train_forward_backward(xd, yd, self._loss_kind)
             self._grad_sync.finish()
             from . import dist as D
             D.average_(eng.state)
-        eng.apply_gradients()
+            eng.apply_gradients()
         for m in self.metrics:
             if isinstance(m, MeanIoU):
                 m.update_state(yd, eng._plans[(xd.shape[0], True)].t["probs"])
@@ -651,7 +657,7 @@ class Model:
             ring = self._loss_ring()
             host_sum = np.zeros(3, np.float64)
             pending = []                                   # (ring slot, event) of steps whose loss is still in flight
-            pf = _Prefetcher(it)
+            pf = _Prefetcher(it, self._pinned.setdefault("prefetch", {}))
             for bx, by in pf:
                 out3, _ = self._train_step_device(bx, by)
                 slot = n % ring.shape[0]

@@ -321,9 +321,10 @@ class _Prefetcher:
     computes.  Two device slots; a slot is rewritten only after the step that read it has been enqueued and has
     finished on the compute stream (event), and a step starts only after its upload has landed (event)."""
 
-    def __init__(self, source, cache: Optional[dict] = None):
+    def __init__(self, source, cache: Optional[dict] = None, with_y: bool = True):
         import torch
         self.src = iter(source)
+        self.with_y = with_y
         cache = cache if cache is not None else {}
         if "stream" not in cache:           # the copy stream and the staging buffers outlive one fit()/evaluate() call
             cache["stream"] = torch.cuda.Stream()
@@ -338,7 +339,7 @@ class _Prefetcher:
         with torch.cuda.stream(self.copy_stream):
             if slot["done"] is not None:
                 self.copy_stream.wait_event(slot["done"])
-            for key, arr in (("x", x), ("y", y)):
+            for key, arr in ((("x", x), ("y", y)) if self.with_y else (("x", x),)):
                 if isinstance(arr, torch.Tensor) and arr.is_cuda:
                     out.append(arr.to(torch.float32).contiguous())
                     continue
@@ -376,7 +377,7 @@ class _Prefetcher:
             except StopIteration:
                 nxt = None
             torch.cuda.current_stream().wait_event(cur_slot["ready"])
-            yield cur[0], cur[1]
+            yield cur[0], (cur[1] if self.with_y else None)
             cur_slot["done"] = torch.cuda.Event()
             cur_slot["done"].record(torch.cuda.current_stream())
             i += 1
@@ -525,7 +526,10 @@ class Model:
 
     # ---------------------------------------------------------------- inference
     def predict(self, x, batch_size: Optional[int] = 32, verbose=0, steps=None) -> np.ndarray:
-        """model.predict (inference.py:116, benchmark.py:254): NHWC float array in, NHWC fp32 probabilities out."""
+        """model.predict (inference.py:116, benchmark.py:254): NHWC float array in, NHWC fp32 probabilities out.
+        Chunks of `batch_size` are pipelined: upload of chunk i+1 (copy stream), forward of chunk i (compute stream) and
+        download of chunk i-1 (second copy stream, into pinned memory) overlap; the host copies finished chunks into the
+        result array while the GPU works."""
         import torch
         x = np.asarray(x) if not isinstance(x, torch.Tensor) else x
         if x.ndim != 4 or tuple(x.shape[1:]) != tuple(self.spec.input_size):
@@ -533,11 +537,47 @@ class Model:
                              f'(None, {", ".join(map(str, self.spec.input_size))}), found shape={tuple(x.shape)}')
         bs = int(batch_size or 32)
         n = x.shape[0]
-        out = np.empty((n,) + tuple(self.spec.input_size[:2]) + (self.spec.num_classes,), np.float32)
-        for lo in range(0, n, bs):
-            xd = self._stage_in(x[lo:lo + bs], "px")
-            probs = self.engine.forward_inference(xd)
-            out[lo:lo + bs] = probs.cpu().numpy()
+        H, W = self.spec.input_size[:2]
+        NC = self.spec.num_classes
+        out = np.empty((n, H, W, NC), np.float32)
+        if n == 0:
+            return out
+        eng = self.engine
+        cache = self._pinned.setdefault(("predict", bs), {})
+        if "in" not in cache:
+            cache["in"] = torch.cuda.Stream(); cache["out"] = torch.cuda.Stream()
+            cache["dev_out"] = [torch.empty((bs, H, W, NC), dtype=torch.float32, device="cuda") for _ in range(2)]
+            cache["pin_out"] = [torch.empty((bs, H, W, NC), dtype=torch.float32).pin_memory() for _ in range(2)]
+            cache["pf"] = {}
+        s_out = cache["out"]
+        compute = torch.cuda.current_stream()
+        pending = [None, None]                       # per output slot: (event, lo, hi)
+
+        def retire(slot):
+            if pending[slot] is not None:
+                ev, lo, hi = pending[slot]
+                ev.synchronize()
+                out[lo:hi] = cache["pin_out"][slot][: hi - lo].numpy()
+                pending[slot] = None
+
+        chunks = ((x[lo:lo + bs], None) for lo in range(0, n, bs))
+        lo = 0
+        for i, (xd, _) in enumerate(_Prefetcher(chunks, cache["pf"], with_y=False)):
+            k = xd.shape[0]
+            slot = i % 2
+            probs = eng.forward_inference(xd)
+            retire(slot)                             # the slot's previous download has been consumed by the host
+            dev_out = cache["dev_out"][slot]
+            dev_out[:k].copy_(probs[:k])             # device-to-device: frees the engine's output buffer for the next chunk
+            ev_c = torch.cuda.Event(); ev_c.record(compute)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_c)
+                cache["pin_out"][slot][:k].copy_(dev_out[:k], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(s_out)
+            pending[slot] = (ev, lo, lo + k)
+            retire(1 - slot)                         # copy the previous chunk out while this one computes
+            lo += k
+        retire(0); retire(1)
         return out
 
     __call__ = predict

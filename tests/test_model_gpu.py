@@ -135,3 +135,36 @@ def test_eval_batch_and_shapes():
     out3 = eng.evaluate_batch(dev(x), dev(y)).cpu().numpy()
     probs = eng.forward_inference(dev(x)).cpu().numpy()
     assert abs(out3[1] - R.dice_coef(y, probs)) < 1e-5 and abs(out3[2] - R.iou_coef(y, probs)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape,batch", [((16, 16, 3), 1), ((16, 32, 3), 3), ((128, 128, 3), 1)])
+def test_extreme_shapes(dtype, shape, batch):
+    """Smallest legal input (1x1 bottleneck), batch 1, non-square, and 128-wide rows (the TMA pixel-shuffle path)."""
+    P = _params(shape, 1, 0.2, True, seed=11)
+    x, y = R.synthetic_batch(batch, shape[0], shape[1], 3, 1, seed=12)
+    eng = _engine(shape, 1, 0.2, True, dtype, P)
+    ref = R.UNetOracle(shape, 1, 0.2, True).forward(P, x)
+    got = eng.forward_inference(dev(x)).cpu().numpy()
+    assert np.abs(got - ref).max() <= (1e-4 if dtype == "fp32" else 2e-2)
+    loss_ref, _, _, _ = R.UNetOracle(shape, 1, 0.2, True).loss_and_grads(P, x, y, drop_seeds=eng._drop_seed)
+    out3 = eng.train_forward_backward(dev(x), dev(y)).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= (1e-4 if dtype == "fp32" else 2e-3)
+
+
+def test_graph_replay_matches_eager():
+    """CUDA-graph replays are new steps: same losses as eager launches (dropout off), weights move every replay."""
+    from unet_b200.engine import UNetEngine
+    x, y = R.synthetic_batch(4, 64, 64, 3, 1, seed=13)
+    xd, yd = dev(x), dev(y)
+    runs = []
+    for graphs in (False, True):
+        eng = UNetEngine((64, 64, 3), dtype="fp32", dropout_rate=0.0, seed=5)
+        eng.use_graphs = graphs
+        runs.append([float(eng.train_step(xd, yd)[0]) for _ in range(6)])
+        p = eng.forward_inference(xd).clone()
+        np.testing.assert_allclose(eng.forward_inference(xd).cpu().numpy(), p.cpu().numpy())
+    np.testing.assert_allclose(runs[0][:2], runs[1][:2], rtol=2e-4, atol=1e-5)
+    # later steps drift apart the way two eager runs do (fp32 atomics order, amplified by every Adam step)
+    np.testing.assert_allclose(runs[0], runs[1], rtol=2e-2, atol=1e-3)
+    assert runs[1][-1] < runs[1][0]

@@ -45,7 +45,10 @@ typedef enum {
   UNET_EPI_AFFINE    = 1, /* C = acc*scale[n] + shift[n]              (folded BatchNormalization, u_net.py:23; or bias) */
   UNET_EPI_AFFINE_RELU = 2, /* C = max(acc*scale[n]+shift[n], 0)      (BN + Activation('relu'), u_net.py:23-25) */
   UNET_EPI_STATS     = 3, /* C = acc, and colsum[n] += C, colsq[n] += C*C over rows (training BN batch statistics) */
-  UNET_EPI_CONVT     = 4  /* Conv2DTranspose(k=2,s=2) pixel-shuffle store + bias (+ dropout), u_net.py:88-98 */
+  UNET_EPI_CONVT     = 4, /* Conv2DTranspose(k=2,s=2) pixel-shuffle store + bias (+ dropout), u_net.py:88-98 */
+  UNET_EPI_HEAD      = 5  /* y = max(acc*scale+shift,0) (stored only if C != NULL) and, from the same registers, the output head
+                             Conv2D(classes,1,sigmoid|softmax) (u_net.py:105-112): head_out[m,:] = act(y[m,:] . head_w + head_b).
+                             Inference only; tensor-core path only; needs N <= 64 (one column tile) and classes <= 8. */
 } unet_epilogue;
 
 /* stateless dropout mask: elements 2k and 2k+1 (linear NHWC offsets in the ctot-wide tensor) share h = lowbias32(k ^ seed-mix);
@@ -77,6 +80,11 @@ typedef struct {
      channel 0 of the [Nimg,2H,2W,*] destination with pixel stride ldc.                                    */
   int convt_H, convt_W;
   unet_dropout drop;               /* CONVT only */
+  /* HEAD only: */
+  const float* head_w;             /* [N, head_classes] (Keras output_mask kernel (1,1,N,classes))                          */
+  const float* head_b;             /* [head_classes] or NULL                                                              */
+  float*       head_out;           /* [M, head_classes] fp32 probabilities                                                */
+  int          head_classes;
 } unet_gemm_args;
 
 /* ---- library ---- */

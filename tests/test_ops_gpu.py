@@ -214,6 +214,27 @@ def test_gemm_tc_nt_strided_affine_relu():
     assert np.all(got[:, :128] == 0) and np.all(got[:, 256:] == 0)
 
 
+@pytest.mark.parametrize("classes", [1, 3, 8])
+@pytest.mark.parametrize("store_y", [False, True])
+def test_gemm_tc_fused_head(classes, store_y):
+    """dec1_block2 pointwise + folded BN + ReLU + Conv2D(classes, 1, sigmoid|softmax) in one epilogue (u_net.py:105-112)."""
+    M, K, N = 1000, 64, 64
+    A = RNG.standard_normal((M, K)).astype(np.float32)
+    Bt = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, N).astype(np.float32); sh = RNG.standard_normal(N).astype(np.float32) * 0.3
+    hw = (RNG.standard_normal((N, classes)) / 4).astype(np.float32); hb = RNG.standard_normal(classes).astype(np.float32) * 0.1
+    y = bf16_round(np.maximum((bf16_round(A) @ bf16_round(Bt).T) * sc + sh, 0))
+    logits = y @ hw.astype(np.float64) + hb
+    ref = R.sigmoid(logits) if classes == 1 else R.softmax(logits)
+    Cm = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16) if store_y else None
+    probs = torch.full((M, classes), float("nan"), device="cuda")
+    ops.gemm(dev(A, torch.bfloat16), dev(Bt, torch.bfloat16), Cm, b_trans=True, epilogue=ops.EPI_HEAD, scale=dev(sc), shift=dev(sh),
+             head_w=dev(hw), head_b=dev(hb), head_out=probs)
+    np.testing.assert_allclose(host(probs), ref, rtol=0, atol=3e-3)      # y may round one bf16 ulp differently than the host
+    if store_y:
+        np.testing.assert_allclose(host(Cm), y, **tol(torch.bfloat16))
+
+
 @pytest.mark.parametrize("mkn", [(1000, 64, 64), (5000, 256, 512), (333, 128, 192)])
 @pytest.mark.parametrize("out_dtype", DTYPES)
 def test_gemm_tc_stats(mkn, out_dtype):

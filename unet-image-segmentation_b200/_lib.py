@@ -12,7 +12,7 @@ PKG_DIR = Path(__file__).resolve().parent
 LIB_PATH = PKG_DIR / "libunet_b200.so"
 
 UNET_F32, UNET_BF16 = 0, 1
-EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU, EPI_STATS, EPI_CONVT = 0, 1, 2, 3, 4
+EPI_NONE, EPI_AFFINE, EPI_AFFINE_RELU, EPI_STATS, EPI_CONVT, EPI_HEAD = 0, 1, 2, 3, 4, 5
 
 
 class UnetError(RuntimeError):
@@ -39,6 +39,7 @@ class GemmArgs(C.Structure):
         ("colsum", C.c_void_p), ("colsq", C.c_void_p),
         ("convt_H", C.c_int), ("convt_W", C.c_int),
         ("drop", Dropout),
+        ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_classes", C.c_int),
     ]
 
 

@@ -134,14 +134,17 @@ gemm_simt_kernel(const SimtParams p) {
 
 int gemm_validate(const unet_gemm_args* a, const char* who) {
   UNET_REQUIRE(a, UNET_EINVAL, "%s: null args", who);
-  UNET_REQUIRE(a->A && a->B && a->C, UNET_EINVAL, "%s: null operand", who);
+  UNET_REQUIRE(a->A && a->B && (a->C || a->epilogue == UNET_EPI_HEAD), UNET_EINVAL, "%s: null operand", who);
   UNET_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, UNET_EINVAL, "%s: bad shape %lld %lld %lld", who,
                (long long)a->M, (long long)a->N, (long long)a->K);
   UNET_REQUIRE(a->lda >= (a->a_trans ? a->M : a->K), UNET_EINVAL, "%s: lda too small", who);
   UNET_REQUIRE(a->ldb >= (a->b_trans ? a->K : a->N), UNET_EINVAL, "%s: ldb too small", who);
   UNET_REQUIRE(a->in_dtype == UNET_F32 || a->in_dtype == UNET_BF16, UNET_EINVAL, "%s: bad in_dtype", who);
   UNET_REQUIRE(a->out_dtype == UNET_F32 || a->out_dtype == UNET_BF16, UNET_EINVAL, "%s: bad out_dtype", who);
-  UNET_REQUIRE(a->epilogue >= UNET_EPI_NONE && a->epilogue <= UNET_EPI_CONVT, UNET_EINVAL, "%s: bad epilogue", who);
+  UNET_REQUIRE(a->epilogue >= UNET_EPI_NONE && a->epilogue <= UNET_EPI_HEAD, UNET_EINVAL, "%s: bad epilogue", who);
+  if (a->epilogue == UNET_EPI_HEAD)
+    UNET_REQUIRE(a->head_w && a->head_out && a->head_classes >= 1 && a->head_classes <= 8 && a->N <= 64, UNET_EINVAL,
+                 "%s: HEAD needs head_w, head_out, 1 <= classes <= 8 and N <= 64", who);
   UNET_REQUIRE(!a->accumulate || (a->out_dtype == UNET_F32 && a->epilogue == UNET_EPI_NONE), UNET_EINVAL,
                "%s: accumulate needs fp32 output and no epilogue", who);
   UNET_REQUIRE(a->epilogue != UNET_EPI_STATS || (a->colsum && a->colsq), UNET_EINVAL, "%s: STATS needs colsum/colsq", who);
@@ -150,7 +153,7 @@ int gemm_validate(const unet_gemm_args* a, const char* who) {
     UNET_REQUIRE(a->M % ((int64_t)a->convt_H * a->convt_W) == 0, UNET_EINVAL, "%s: CONVT M must be images*H*W", who);
     UNET_REQUIRE(a->ldc >= a->N / 4, UNET_EINVAL, "%s: CONVT ldc < Cout", who);
   } else {
-    UNET_REQUIRE(a->ldc >= a->N, UNET_EINVAL, "%s: ldc too small", who);
+    UNET_REQUIRE(a->C == nullptr || a->ldc >= a->N, UNET_EINVAL, "%s: ldc too small", who);
   }
   return UNET_OK;
 }
@@ -161,6 +164,7 @@ using namespace unet;
 
 extern "C" int unet_gemm_simt(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_simt")) return e;
+  UNET_REQUIRE(a->epilogue != UNET_EPI_HEAD, UNET_EUNSUPPORTED, "gemm_simt: the fused output head exists on the tensor-core path only");
   SimtParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.A = a->A; p.lda = a->lda; p.B = a->B; p.ldb = a->ldb; p.C = a->C; p.ldc = a->ldc;

@@ -47,6 +47,7 @@ struct TcParams {
   float keep, inv_keep; uint32_t seed; int drop_on; int64_t ctot, c0; const uint32_t* seed_dev;
   int64_t kb_per_split;     // wgrad: k-blocks per CTA along P
   int num_m_tiles, num_n_tiles;
+  const float* head_w; const float* head_b; float* head_out; int head_classes;   // UNET_EPI_HEAD
 };
 
 constexpr int kBlockM = 128, kBlockK = 64;
@@ -194,7 +195,8 @@ template <int BLOCK_N> struct NtCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5);
   static constexpr int kTmemCols = 2 * BLOCK_N;
-  static constexpr int kParBytes = kNumEpiGroups * 2 * BLOCK_N * 4;        // per group: scale[BLOCK_N], shift[BLOCK_N]
+  static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;        // fused output head: w[class][64] + bias[8]
+  static constexpr int kParBytes = kNumEpiGroups * (2 * BLOCK_N + kHeadFloats) * 4;   // per group: scale, shift[, head]
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kNumEpiGroups * 2 * kStageTileBytes + kParBytes + 256;
 };
 
@@ -294,11 +296,22 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int gtid = (warp - 4 - 4 * g) * 32 + lane;
     const bool issuer = gtid == 0;
     uint8_t* tiles = stage_tiles + g * 2 * kStageTileBytes;
-    float* par_scale = s_par + g * 2 * BLOCK_N;
+    float* par_scale = s_par + g * (2 * BLOCK_N + Cfg::kHeadFloats);
     float* par_shift = par_scale + BLOCK_N;
+    float* par_head = par_shift + BLOCK_N;         // [8][64] class-major weights, then 8 biases (BLOCK_N == 64 only)
     const int epi = p.epilogue;
-    const bool affine = epi == UNET_EPI_AFFINE || epi == UNET_EPI_AFFINE_RELU || epi == UNET_EPI_CONVT;
-    const bool relu = epi == UNET_EPI_AFFINE_RELU;
+    constexpr bool kHeadCapable = BLOCK_N == 64 && OUT_BF16;
+    const bool head = kHeadCapable && epi == UNET_EPI_HEAD;
+    const bool affine = epi == UNET_EPI_AFFINE || epi == UNET_EPI_AFFINE_RELU || epi == UNET_EPI_CONVT || epi == UNET_EPI_HEAD;
+    const bool relu = epi == UNET_EPI_AFFINE_RELU || epi == UNET_EPI_HEAD;
+    const bool store_c = p.C != nullptr;
+    if (kHeadCapable && head) {                    // visible to the group after the first named barrier of the chunk loop
+      for (int i = gtid; i < 8 * 64; i += 128) {
+        const int cls = i >> 6, k = i & 63;
+        par_head[i] = (cls < p.head_classes && k < p.N) ? __ldg(p.head_w + (int64_t)k * p.head_classes + cls) : 0.f;
+      }
+      if (gtid < 8) par_head[8 * 64 + gtid] = (gtid < p.head_classes && p.head_b) ? __ldg(p.head_b + gtid) : 0.f;
+    }
     const bool stats = epi == UNET_EPI_STATS;
     const uint32_t seed = p.drop_on ? p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u) : 0u;
     // Conv2DTranspose: tile rows are input pixels (q = image*H + i, j); the box covers bj columns x bq rows of them
@@ -347,6 +360,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N;
       const int m0 = m_blk * kBlockM;
+      float hacc[kHeadCapable ? 8 : 1];
+#pragma unroll
+      for (int i = 0; i < (kHeadCapable ? 8 : 1); ++i) hacc[i] = 0.f;
 #pragma unroll
       for (int c = 0; c < kChunks; ++c, ++chunk_ctr) {
         uint8_t* buf = tiles + (chunk_ctr & 1) * kStageTileBytes;
@@ -392,6 +408,24 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (p.drop_on) dropout_apply(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
           }
+          if (kHeadCapable && head) {             // 1x1 output convolution from the activations as they will be stored (bf16)
+            const int ncls = p.head_classes;
+#pragma unroll
+            for (int cls = 0; cls < 8; ++cls) {
+              if (cls < ncls) {
+                const float* hw = par_head + cls * 64 + half * 32;
+                float a = hacc[cls];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(hw + i);
+                  a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
+                  a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
+                }
+                hacc[cls] = a;
+              }
+            }
+          }
+          if (!store_c) continue;
           if (OUT_BF16) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {         // 4 x 16 B = 32 bf16 columns; chunk index = half*4 + j
@@ -415,7 +449,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         fence_proxy_async();
         named_bar_sync(1 + g, 128);
-        if (issuer) {
+        if (issuer && store_c) {
           if (epi == UNET_EPI_CONVT) {
             const int q0 = m0 / cw, j0 = m0 - q0 * cw;
             tma_store_5d(&tmC, buf, co0, j0, q0, cv_b, cv_a);
@@ -442,6 +476,22 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           st_sum[c][0] += s0; st_sq[c][0] += q0s;
           if (CPL == 2) { st_sum[c][CPL - 1] += s1; st_sq[c][CPL - 1] += q1s; }
+        }
+      }
+      if (kHeadCapable && head && (int64_t)m0 + row < p.M) {
+        const int ncls = p.head_classes;
+        float* dst = p.head_out + ((int64_t)m0 + row) * ncls;
+        if (ncls == 1) {
+          dst[0] = 1.f / (1.f + expf(-(hacc[0] + par_head[8 * 64])));
+        } else {
+          float mx = -INFINITY, e[8], den = 0.f;
+#pragma unroll
+          for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { hacc[cls] += par_head[8 * 64 + cls]; mx = fmaxf(mx, hacc[cls]); }
+#pragma unroll
+          for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { e[cls] = expf(hacc[cls] - mx); den += e[cls]; }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int cls = 0; cls < 8; ++cls) if (cls < ncls) dst[cls] = e[cls] * inv;
         }
       }
     }
@@ -569,6 +619,7 @@ static void fill_params(TcParams& p, const unet_gemm_args* a) {
   p.scale = a->scale; p.shift = a->shift; p.colsum = a->colsum; p.colsq = a->colsq;
   p.convt_H = a->convt_H; p.convt_W = a->convt_W; p.convt_cout = a->N / 4;
   p.drop_on = 0; p.keep = 1.f; p.inv_keep = 1.f; p.seed = 0; p.ctot = 0; p.c0 = 0; p.seed_dev = nullptr;
+  p.head_w = a->head_w; p.head_b = a->head_b; p.head_out = a->head_out; p.head_classes = a->head_classes;
   if (a->epilogue == UNET_EPI_CONVT && a->drop.rate > 0.f) {
     p.drop_on = 1; p.keep = 1.f - a->drop.rate; p.inv_keep = 1.f / (1.f - a->drop.rate);
     p.seed = a->drop.seed; p.ctot = a->drop.ctot; p.c0 = a->drop.c0; p.seed_dev = a->drop.seed_dev;
@@ -660,7 +711,10 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;
   UNET_REQUIRE(a->in_dtype == UNET_BF16, UNET_EUNSUPPORTED, "gemm_tc: operands must be bf16 (fp32 mode uses gemm_simt)");
   UNET_REQUIRE(a->N % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: N must be a multiple of 8 (got %lld)", (long long)a->N);
-  UNET_REQUIRE(a->ldc % 4 == 0 && aligned16(a->C), UNET_EALIGN, "gemm_tc: C needs a 16B-aligned base and ldc%%4==0");
+  UNET_REQUIRE(a->C == nullptr || (a->ldc % 4 == 0 && aligned16(a->C)), UNET_EALIGN, "gemm_tc: C needs a 16B-aligned base and ldc%%4==0");
+  if (a->epilogue == UNET_EPI_HEAD)
+    UNET_REQUIRE(a->N <= 64 && a->out_dtype == UNET_BF16 && !a->a_trans, UNET_EUNSUPPORTED,
+                 "gemm_tc: the fused output head needs N <= 64 and bf16 activations");
   UNET_REQUIRE(!a->scale || aligned16(a->scale), UNET_EALIGN, "gemm_tc: scale must be 16B aligned");
   UNET_REQUIRE(!a->shift || aligned16(a->shift), UNET_EALIGN, "gemm_tc: shift must be 16B aligned");
   if (a->epilogue == UNET_EPI_CONVT)
@@ -683,8 +737,9 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
     UNET_REQUIRE(a->K % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: K must be a multiple of 8 (got %lld)", (long long)a->K);
     if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A)")) return e;
     if (int e = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, bn, "gemm_tc(B)")) return e;
-    CUtensorMap tmC;
-    if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
+    CUtensorMap tmC = tmA;       // placeholder descriptor when nothing is stored (HEAD without C)
+    if (a->C)
+      if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
     const bool ob = a->out_dtype == UNET_BF16;
     if (bn == 256) return ob ? launch_nt<256, true>(tmA, tmB, tmC, p, st) : launch_nt<256, false>(tmA, tmB, tmC, p, st);
     if (bn == 128) return ob ? launch_nt<128, true>(tmA, tmB, tmC, p, st) : launch_nt<128, false>(tmA, tmB, tmC, p, st);

@@ -91,6 +91,7 @@ class UNetEngine:
         self._drop_seed = {name: (seed * 7919 + i * 104729) & 0x7FFFFFFF
                            for i, name in enumerate(["bneck_dropout", "dec4_dropout", "dec3_dropout", "dec2_dropout"])}
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
+        self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
         self.grad_hook = None                   # callable(region) — dist.GradSync.ready; regions: decoder, bottleneck, encoder
@@ -311,9 +312,22 @@ class UNetEngine:
             h, w = self._dims(s - 1)
             self._convt_fwd(s, cur, cats[s][..., :f], None)
             cur = self._block_infer(pl, f"dec{s}_block1", cats[s], pl.buf(f"ya{s}", (B, h, w, f)))
-            cur = self._block_infer(pl, f"dec{s}_block2", cur, pl.buf(f"yb{s}", (B, h, w, f)))
+            if s > 1 or not self.fuse_head or self.act_dtype != torch.bfloat16:
+                cur = self._block_infer(pl, f"dec{s}_block2", cur, pl.buf(f"yb{s}", (B, h, w, f)))
         probs = pl.buf("probs", (B, H, W, self.num_classes), torch.float32)
-        ops.head_fwd(cur, self._mat("output_mask/kernel"), self.wview("output_mask/bias"), probs)
+        if self.fuse_head and self.act_dtype == torch.bfloat16:
+            # dec1_block2's pointwise GEMM applies BN + ReLU and the 1x1 sigmoid/softmax head in its epilogue; the
+            # 64-channel activation it would have produced is never written
+            prefix = "dec1_block2"
+            d = pl.buf("d0", (B * H * W * 2 * FILTERS[0],))[: B * H * W * FILTERS[0]].view(B, H, W, FILTERS[0])
+            ops.dwconv3x3(cur, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
+            o, c = self._bn_off[prefix]
+            ops.gemm(d, self._stage[f"{prefix}_sepconv/pointwise_kernel^T"], None, b_trans=True, epilogue=ops.EPI_HEAD,
+                     scale=self.fold[0, o:o + c] if self.use_bn else None,
+                     shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"),
+                     head_w=self._mat("output_mask/kernel"), head_b=self.wview("output_mask/bias"), head_out=probs)
+        else:
+            ops.head_fwd(cur, self._mat("output_mask/kernel"), self.wview("output_mask/bias"), probs)
         return probs
 
     # ------------------------------------------------------------------------------------------------ training

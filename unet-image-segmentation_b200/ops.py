@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_CONVT, EPI_NONE, EPI_STATS, UNET_BF16, UNET_F32, Dropout,
+from ._lib import (EPI_AFFINE, EPI_AFFINE_RELU, EPI_CONVT, EPI_HEAD, EPI_NONE, EPI_STATS, UNET_BF16, UNET_F32, Dropout,
                    GemmArgs)
 
 _DT = {torch.float32: UNET_F32, torch.bfloat16: UNET_BF16}
@@ -179,11 +179,13 @@ def stem_bwd(x: torch.Tensor, dz: torch.Tensor, wd9c, wp, dwd9c, dwp) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ dense contractions
-def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = False, b_trans: bool = False,
+def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_trans: bool = False, b_trans: bool = False,
          accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,
          shift: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
          colsq: Optional[torch.Tensor] = None, convt_hw: Tuple[int, int] = (0, 0),
-         drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None) -> None:
+         drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None,
+         head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
+         head_out: Optional[torch.Tensor] = None) -> None:
     """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
     hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
     CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported)."""
@@ -195,7 +197,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = 
         raise ValueError(f"gemm: inner dimensions disagree ({K} vs {Kb})")
     if A.dtype != B.dtype:
         raise ValueError("gemm: A and B must share a dtype")
-    if epilogue == EPI_CONVT:
+    if Cm is None:
+        if epilogue != EPI_HEAD:
+            raise ValueError("gemm: C may be omitted only with the fused output head")
+        ldc = N
+    elif epilogue == EPI_CONVT:
         _, _, _, cc, ldc = _nhwc(Cm, "C")
         if cc * 4 != N:
             raise ValueError("gemm(CONVT): destination view must have N/4 channels")
@@ -213,20 +219,25 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: torch.Tensor, *, a_trans: bool = 
     args.B, args.ldb = _p(B), ldb
     args.C, args.ldc = _p(Cm), ldc
     args.a_trans, args.b_trans = int(a_trans), int(b_trans)
-    args.in_dtype, args.out_dtype = _dt(A), _dt(Cm)
+    args.in_dtype, args.out_dtype = _dt(A), (_dt(Cm) if Cm is not None else _dt(A))
     args.accumulate, args.epilogue = int(accumulate), int(epilogue)
     args.scale, args.shift = _p(scale), _p(shift)
     args.colsum, args.colsq = _p(colsum), _p(colsq)
     args.convt_H, args.convt_W = int(convt_hw[0]), int(convt_hw[1])
     if drop is not None:
         args.drop = drop
+    if epilogue == EPI_HEAD:
+        _f32(head_w, "head_w"); _f32(head_b, "head_b"); _f32(head_out, "head_out")
+        if head_w is None or head_out is None or head_w.shape[0] != N or head_out.numel() != M * head_w.shape[1]:
+            raise ValueError("gemm(HEAD): head_w must be [N, classes] and head_out [M, classes]")
+        args.head_w, args.head_b, args.head_out, args.head_classes = _p(head_w), _p(head_b), _p(head_out), head_w.shape[1]
     tc_ok = (A.dtype == torch.bfloat16 and N % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and ldc % 4 == 0
              and ((not a_trans and b_trans and not accumulate and K % 8 == 0)
                   or (a_trans and not b_trans and accumulate and M % 8 == 0))
              and (epilogue != EPI_CONVT or ((N // 4) % 64 == 0 and convt_hw[1] > 0 and
                                            (128 % convt_hw[1] == 0 or convt_hw[1] % 128 == 0))))
     use_tc = tc_ok if tensor_core is None else tensor_core
-    csz = Cm.numel() * Cm.element_size()
+    csz = (Cm.numel() * Cm.element_size() if Cm is not None else 0) + (head_out.numel() * 4 if head_out is not None else 0)
     _call("unet_gemm_tc" if use_tc else "unet_gemm_simt", C.byref(args), _stream(),
           tag=f"{'wgrad' if a_trans else ('convt' if epilogue == EPI_CONVT else 'nt')}:{M}x{N}x{K}:e{epilogue}",
           nbytes=A.numel() * A.element_size() + B.numel() * B.element_size() + csz * (2 if accumulate else 1),

@@ -203,6 +203,14 @@ int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, in
 /* dst = cast(src) elementwise between fp32/bf16 (n elements) */
 int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 
+/* ---- pre/post-processing of the inference / benchmark CLIs (scripts/inference.py:98-110,147-160; scripts/benchmark.py:95-110) ---- */
+/* img: DEVICE uint8 [H0,W0,C] as cv2.imread returns it (BGR kept) -> out[h,w,C] fp32 = cv2.resize(img / divisor, INTER_LINEAR) */
+int unet_preprocess_u8(const uint8_t* img, int H0, int W0, int C, int64_t row_stride_bytes, float* out, int h, int w,
+                       float divisor, void* stream);
+/* prob: fp32 [h,w] with element stride ld (class channel of an NHWC tensor) -> mask[H0,W0] u8 = (cv2.resize(prob) > threshold) * 255 */
+int unet_postprocess_mask(const float* prob, int h, int w, int64_t ld, uint8_t* mask, int H0, int W0, float threshold,
+                          void* stream);
+
 /* host helper: the mask bit the kernels use, for reproducing dropout on the host in tests */
 uint32_t unet_host_dropout_hash(uint64_t idx, uint32_t seed);
 

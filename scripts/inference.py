@@ -32,6 +32,8 @@ def parse_args(argv=None) -> argparse.Namespace:
                    help="Threshold value (0.0 to 1.0) to convert probability mask to binary mask.")
     p.add_argument("--min_area", type=float, default=MIN_CONTOUR_AREA,
                    help=f"Minimum contour area threshold for cropping (default: {MIN_CONTOUR_AREA}).")
+    p.add_argument("--gpu-prepost", action="store_true",
+                   help="Extension: resize/normalise and upsample/threshold on the GPU (same arithmetic as the cv2 path).")
     return p.parse_args(argv)
 
 
@@ -80,13 +82,18 @@ def main(argv=None):
 
     h, w = model.spec.input_size[:2]
     print(f"Loading and preprocessing image: {args.input} ...")
-    x, bgr = imaging.read_image_for_model(args.input, h, w)
+    if args.gpu_prepost:
+        import cv2
+        bgr = cv2.imread(args.input, cv2.IMREAD_COLOR)
+        x = None if bgr is None else imaging.gpu_preprocess([bgr], h, w)
+    else:
+        x, bgr = imaging.read_image_for_model(args.input, h, w)
     if x is None:
         print(f"Error: Could not read image from {args.input}")
         sys.exit(1)
     print("Running prediction...")
     try:
-        pred = model.predict(x, verbose=0)
+        pred = model.predict_on_device(x) if args.gpu_prepost else model.predict(x, verbose=0)
     except Exception as e:
         print(f"Error during model prediction: {e}")
         sys.exit(1)
@@ -96,7 +103,10 @@ def main(argv=None):
 
     print("Postprocessing results...")
     print("Processing predicted mask...")
-    mask = imaging.probability_to_mask(pred[0], bgr.shape[0], bgr.shape[1], args.threshold)
+    if args.gpu_prepost:
+        mask = imaging.gpu_probability_to_mask(pred[0], bgr.shape[0], bgr.shape[1], args.threshold)
+    else:
+        mask = imaging.probability_to_mask(pred[0], bgr.shape[0], bgr.shape[1], args.threshold)
     print(f"Saving binary mask to {args.output_mask} ...")
     _write(args.output_mask, mask, "mask")
     print("Finding largest contour for cropping...")

@@ -157,6 +157,11 @@ def test_cli_train_inference_benchmark(tmp_path):
     m = cv2.imread(str(tmp_path / "out" / "mask.png"), cv2.IMREAD_UNCHANGED)
     assert m.shape == (120, 160) and set(np.unique(m).tolist()) <= {0, 255}
     assert "Inference script finished." in r.stdout
+    r = _run([os.path.join(ROOT, "scripts", "inference.py"), "in.png", "--model", "models/m.h5", "--output_mask", "out/mask_gpu.png",
+              "--output_cropped", "out/crop_gpu.png", "--min_area", "0", "--gpu-prepost"], cwd)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    mg = cv2.imread(str(tmp_path / "out" / "mask_gpu.png"), cv2.IMREAD_UNCHANGED)
+    assert mg.shape == m.shape and (mg == m).mean() > 0.999          # same arithmetic as the cv2 path
     r = _run([os.path.join(ROOT, "scripts", "inference.py"), "in.png", "--model", "models/m.h5", "--threshold", "1.0"], cwd)
     assert r.returncode == 1 and "Threshold must be between" in r.stdout
     # benchmark CLI (layout of scripts/prepare_dataset.py: images/**.tif + ground_truth/**.json)

@@ -484,3 +484,31 @@ def test_rejects_bad_arguments():
     with pytest.raises(UnetError):
         ops.gemm(A, torch.zeros((16, 12), device="cuda", dtype=torch.bfloat16), torch.zeros((16, 16), device="cuda"),
                  b_trans=True, tensor_core=True)     # lda % 8 != 0
+
+
+# ------------------------------------------------------------------------------------------------ CLI pre/post-processing
+@pytest.mark.parametrize("src,dst", [((540, 960), (256, 256)), ((100, 37), (64, 64)), ((256, 256), (256, 256)), ((31, 500), (48, 16))])
+def test_preprocess_matches_cv2(src, dst):
+    import cv2
+    img = RNG.integers(0, 256, (src[0], src[1], 3), dtype=np.uint8)
+    ref = cv2.resize(img.astype(np.float32) / 255.0, (dst[1], dst[0]), interpolation=cv2.INTER_LINEAR)
+    out = torch.empty((dst[0], dst[1], 3), device="cuda")
+    ops.preprocess_u8(torch.tensor(img, device="cuda"), out)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
+
+
+@pytest.mark.parametrize("src,dst", [((256, 256), (540, 960)), ((64, 64), (100, 37)), ((32, 32), (32, 32))])
+def test_postprocess_matches_cv2(src, dst):
+    import cv2
+    prob = RNG.random((src[0], src[1], 1)).astype(np.float32)
+    prob[8:20, 8:24] = 0.97
+    big = cv2.resize(prob, (dst[1], dst[0]), interpolation=cv2.INTER_LINEAR)
+    ref = (big > 0.5).astype(np.uint8) * 255
+    mask = torch.empty(dst, device="cuda", dtype=torch.uint8)
+    pd = torch.zeros((src[0], src[1], 4), device="cuda")
+    pd[..., 2] = torch.tensor(prob[..., 0], device="cuda")
+    ops.postprocess_mask(pd[..., 2], mask, 0.5)
+    got = mask.cpu().numpy()
+    assert set(np.unique(got).tolist()) <= {0, 255}
+    borderline = np.abs(big - 0.5) < 1e-5            # pixels whose value sits on the threshold may round either way
+    assert np.all((got == ref) | borderline) and (got == ref).mean() > 0.9999

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "unet_step_advance": [_vp, _vp, _vp],
     "unet_cast_transpose_bf16": [_vp, _vp, _vp, _i, _i, _vp],
     "unet_cast": [_vp, _i, _vp, _i, _i64, _vp],
+    "unet_preprocess_u8": [_vp, _i, _i, _i, _i64, _vp, _i, _i, _f, _vp],
+    "unet_postprocess_mask": [_vp, _i, _i, _i64, _vp, _i, _i, _f, _vp],
     "unet_host_dropout_hash": [C.c_uint64, C.c_uint32],
 }
 _RESTYPES = {"unet_last_error": C.c_char_p, "unet_host_dropout_hash": C.c_uint32}

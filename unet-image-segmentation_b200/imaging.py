@@ -81,3 +81,26 @@ def sample_iou(y_true: np.ndarray, y_pred: np.ndarray, smooth: float = SMOOTH) -
     inter = np.float32((t * p).sum(dtype=np.float32))
     union = np.float32(t.sum(dtype=np.float32)) + np.float32(p.sum(dtype=np.float32)) - inter
     return float((inter + np.float32(smooth)) / (union + np.float32(smooth)))
+
+
+# ------------------------------------------------------------------------------------------------ GPU variants (opt-in)
+def gpu_preprocess(images_bgr, height: int, width: int):
+    """uint8 BGR images (any sizes) -> one CUDA fp32 batch [B, height, width, 3]: the same /255 + INTER_LINEAR resize as
+    read_image_for_model, done by unet_preprocess_u8 (one upload of the raw bytes per image instead of 4x as many floats)."""
+    import torch
+    from . import ops
+    out = torch.empty((len(images_bgr), height, width, 3), dtype=torch.float32, device="cuda")
+    for i, img in enumerate(images_bgr):
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+            raise ValueError("gpu_preprocess expects uint8 HxWx3 images")
+        ops.preprocess_u8(torch.from_numpy(np.ascontiguousarray(img)).cuda(), out[i])
+    return out
+
+
+def gpu_probability_to_mask(prob_dev, out_height: int, out_width: int, threshold: float) -> np.ndarray:
+    """CUDA probabilities [h, w, 1] (a slice of the model output) -> uint8 {0,255} mask at the original size on the host."""
+    import torch
+    from . import ops
+    mask = torch.empty((out_height, out_width), dtype=torch.uint8, device="cuda")
+    ops.postprocess_mask(prob_dev[..., 0], mask, threshold)
+    return mask.cpu().numpy()

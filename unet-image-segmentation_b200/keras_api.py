@@ -582,6 +582,10 @@ class Model:
 
     __call__ = predict
 
+    def predict_on_device(self, x):
+        """Device tensor in, device probabilities out (plan-owned buffer, valid until the next call); no host copies."""
+        return self.engine.forward_inference(x)
+
     # ---------------------------------------------------------------- training
     def _metric_names(self) -> List[str]:
         return [m.name if isinstance(m, MeanIoU) else m.__name__ for m in self.metrics]

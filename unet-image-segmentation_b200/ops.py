@@ -405,3 +405,28 @@ def cast(src: torch.Tensor, dst: torch.Tensor) -> None:
 
 def device_check(device: int = 0) -> None:
     _lib.call("unet_device_check", int(device))
+
+
+# ------------------------------------------------------------------------------------------------ CLI pre/post-processing
+def preprocess_u8(img: torch.Tensor, out: torch.Tensor, divisor: float = 255.0) -> None:
+    """img: CUDA uint8 [H0,W0,C] (cv2.imread order) -> out: fp32 [h,w,C] = cv2.resize(img/255, INTER_LINEAR)."""
+    if img.dtype != torch.uint8 or img.dim() != 3 or not img.is_cuda or img.stride(2) != 1 or img.stride(1) != img.shape[2]:
+        raise TypeError("preprocess_u8: img must be a CUDA uint8 [H,W,C] tensor with packed pixels")
+    _f32(out, "out")
+    h, w, c = out.shape[-3:]
+    if c != img.shape[2]:
+        raise ValueError("preprocess_u8: channel mismatch")
+    _call("unet_preprocess_u8", _p(img), img.shape[0], img.shape[1], c, img.stride(0), _p(out), h, w, float(divisor), _stream())
+
+
+def postprocess_mask(prob: torch.Tensor, mask: torch.Tensor, threshold: float) -> None:
+    """prob: fp32 view [h,w] (any element stride) -> mask: CUDA uint8 [H0,W0] = (cv2.resize(prob) > threshold) * 255."""
+    if prob.dtype != torch.float32 or prob.dim() != 2 or not prob.is_cuda:
+        raise TypeError("postprocess_mask: prob must be a CUDA fp32 [h,w] view")
+    ld = prob.stride(1) if prob.shape[1] > 1 else 1
+    if prob.shape[0] > 1 and prob.stride(0) != prob.shape[1] * ld:
+        raise ValueError("postprocess_mask: rows must be densely packed at the element stride")
+    if mask.dtype != torch.uint8 or not mask.is_contiguous() or not mask.is_cuda:
+        raise TypeError("postprocess_mask: mask must be a contiguous CUDA uint8 tensor")
+    _call("unet_postprocess_mask", _p(prob), prob.shape[0], prob.shape[1], ld, _p(mask), mask.shape[0], mask.shape[1],
+          float(threshold), _stream())

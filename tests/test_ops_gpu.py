@@ -512,3 +512,23 @@ def test_postprocess_matches_cv2(src, dst):
     assert set(np.unique(got).tolist()) <= {0, 255}
     borderline = np.abs(big - 0.5) < 1e-5            # pixels whose value sits on the threshold may round either way
     assert np.all((got == ref) | borderline) and (got == ref).mean() > 0.9999
+
+
+# ------------------------------------------------------------------------------------------------ fused conv_block (inference)
+@pytest.mark.parametrize("cfg", [(2, 16, 32, 64, 64), (1, 8, 16, 64, 64), (3, 21, 45, 128, 64), (2, 40, 24, 64, 128),
+                                 (1, 64, 64, 256, 128), (2, 9, 7, 8, 16), (1, 33, 70, 72, 104)])
+def test_sepconv_fused(cfg):
+    n, h, w, cin, cout = cfg
+    x = RNG.standard_normal((n, h, w, cin)).astype(np.float32)
+    wd = RNG.standard_normal((3, 3, cin)).astype(np.float32) / 3
+    wp = (RNG.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, cout).astype(np.float32); sh = RNG.standard_normal(cout).astype(np.float32) * 0.3
+    d = bf16_round(R.dwconv3x3(bf16_round(x), wd.astype(np.float64)))       # the A operand is bf16, as in the unfused path
+    ref = np.maximum((d.reshape(-1, cin) @ bf16_round(wp)) * sc + sh, 0).reshape(n, h, w, cout)
+    buf = torch.zeros((n, h, w, cout + 64), device="cuda", dtype=torch.bfloat16)
+    xin = torch.zeros((n, h, w, cin + 8), device="cuda", dtype=torch.bfloat16)
+    xin[..., 8:] = dev(x, torch.bfloat16)
+    ops.sepconv_fused(xin[..., 8:], dev(wd.reshape(9, cin)), dev(wp.T.copy(), torch.bfloat16), buf[..., 64:], scale=dev(sc), shift=dev(sh))
+    got = host(buf)
+    np.testing.assert_allclose(got[..., 64:], ref, rtol=1.0 / 64, atol=2e-2)
+    assert np.all(got[..., :64] == 0)

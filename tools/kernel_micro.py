@@ -73,6 +73,12 @@ elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
         run(lambda: ops.bn_bwd_apply(dy, z, sc, sh, mu, rs, dg, db, dz), 3 * M * 64 * 2)
     else:
         run(lambda: ops.bn_act(z, sc, sh, dz), 2 * M * 64 * 2)
+elif name in ("fused64", "fused128_64", "fused64_128"):
+    cin, cout, hh = {"fused64": (64, 64, 512), "fused128_64": (128, 64, 512), "fused64_128": (64, 128, 256)}[name]
+    x = rnd(B, hh, hh, cin); y = torch.empty((B, hh, hh, cout), device=dev, dtype=bf)
+    wd = torch.rand((9, cin), device=dev); wpt = rnd(cout, cin)
+    sc, sh = torch.rand(cout, device=dev), torch.rand(cout, device=dev)
+    run(lambda: ops.sepconv_fused(x, wd, wpt, y, scale=sc, shift=sh), (x.numel() + y.numel()) * 2)
 elif name in ("head8_fwd", "head8_bwd", "head1_fwd", "head1_bwd"):
     C = 8 if "8" in name else 1
     Bh = 32

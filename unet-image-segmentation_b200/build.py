@@ -16,7 +16,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 BUILD = PKG_DIR / "build"
 LIB = PKG_DIR / "libunet_b200.so"
-SOURCES = ["api.cu", "dwconv.cu", "stem.cu", "elementwise.cu", "head.cu", "gemm_simt.cu", "gemm_tc.cu", "imaging.cu"]
+SOURCES = ["api.cu", "dwconv.cu", "stem.cu", "elementwise.cu", "head.cu", "gemm_simt.cu", "gemm_tc.cu", "sepconv_fused.cu", "imaging.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

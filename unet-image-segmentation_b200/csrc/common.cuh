@@ -29,6 +29,18 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
 __host__ __device__ inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per (kernel instantiation, device)
+struct SmemAttrOnce { bool done[64] = {}; };
+template <typename F>
+inline cudaError_t ensure_dynamic_smem(SmemAttrOnce& once, F func, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && once.done[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) once.done[dev] = true;
+  return e;
+}
 
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> struct DT;

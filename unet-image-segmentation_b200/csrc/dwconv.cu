@@ -264,13 +264,10 @@ static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, voi
   using Cfg = StripCfg<T>;
   CUtensorMap tm;
   if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(dwconv3x3_strip_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "dwconv3x3_fwd: cudaFuncSetAttribute");
-    attr_done = true;
-  }
+  static SmemAttrOnce once_plain, once_drop;
+  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true>, Cfg::kSmemBytes);
+  if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_fwd: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
   const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6);
   const int nseg = (int)ceil_div(H, seg);
@@ -596,12 +593,9 @@ static int dw_wgrad_strip_launch(const void* x, int64_t ldx, const void* dy, int
   CUtensorMap tmX, tmD;
   if (int e = make_nhwc_tmap<T>(&tmX, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_bwd_weight(x)")) return e;
   if (int e = make_nhwc_tmap<T>(&tmD, dy, lddy, N, H, W, C, Cfg::TW, Cfg::RH, "dwconv3x3_bwd_weight(dy)")) return e;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_wgrad_strip_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "dwconv3x3_bwd_weight: cudaFuncSetAttribute");
-    attr_done = true;
-  }
+  static SmemAttrOnce once;
+  if (cudaError_t e = ensure_dynamic_smem(once, dwconv3x3_wgrad_strip_kernel<T>, Cfg::kSmemBytes))
+    return set_cuda_error(e, "dwconv3x3_bwd_weight: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
   const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 4);
   const int nseg = (int)ceil_div(H, seg);

@@ -662,12 +662,9 @@ static int make_c_tmap(CUtensorMap* map, const unet_gemm_args* a, const char* wh
 template <int BLOCK_N, bool OUT_BF16>
 static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st) {
   using Cfg = NtCfg<BLOCK_N>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
-    attr_done = true;
-  }
+  static SmemAttrOnce once;
+  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, Cfg::kSmemBytes))
+    return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
   p.num_m_tiles = (int)ceil_div(p.M, kBlockM);
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
@@ -680,12 +677,9 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
 template <int BLOCK_N>
 static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_wgrad_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
-    attr_done = true;
-  }
+  static SmemAttrOnce once;
+  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_wgrad_kernel<BLOCK_N>, Cfg::kSmemBytes))
+    return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
   p.num_m_tiles = (int)ceil_div(p.M, kBlockM);
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;

@@ -1,0 +1,334 @@
+// Inference conv_block in ONE kernel: SeparableConv2D (depthwise 3x3 + pointwise 1x1) + folded BatchNormalization +
+// ReLU (reference model/u_net.py:5-26).  The depthwise result never touches HBM: CUDA-core warps compute it from a
+// TMA-staged halo patch straight into the 128B-swizzled shared-memory tile that tcgen05.mma reads as its A operand.
+//
+// One CTA per SM, persistent over 8x16-pixel output patches (128 GEMM rows).  640 threads:
+//   warp 0        TMA producer: per 64-channel block k, one 4-D box {64 ch, 18 cols, 10 rows, image} of x (zero OOB fill =
+//                 'same' padding and ragged patches) + the {64 k, BLOCK_N} slice of the pointwise kernel
+//   warp 1        MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16, accumulating over the channel blocks
+//   warp 2        TMEM allocator (2 accumulator stages)
+//   warps 4-11    depthwise producers: thread = (patch column, 4 channels); slides down the 10 halo rows with two open
+//                 partial sums per channel in registers (3 conflict-free 8-byte shared loads + 27 FMA per channel-triple
+//                 per row), packs bf16 and stores into the A tile (K-major, SWIZZLE_128B) -> fence.proxy.async -> mbarrier
+//   warps 12-19   two epilogue groups (one per accumulator stage): tcgen05.ld -> scale/shift/ReLU -> bf16 -> swizzled staging
+//                 tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC destination
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace unet {
+
+// shared with gemm_tc.cu (same encodings)
+__device__ __forceinline__ uint64_t fs_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
+  d |= (uint64_t)((1024u >> 4) & 0x3fffu) << 32;   // SBO = 8 rows x 128 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t fs_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void fs_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void fs_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fs_tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+constexpr int kPH = 8, kPW = 16;                        // output patch = 128 pixels
+constexpr int kXRows = kPH + 2, kXCols = kPW + 2;
+constexpr int kXBytes = kXRows * kXCols * 128;          // 23040
+constexpr int kXStage = 23 * 1024;                      // padded so that the B tile behind it is 1024 B aligned
+constexpr int kTileBytes = 128 * 128;
+constexpr int kMaxCin = 512;
+
+template <int BLOCK_N> struct FsCfg {
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kXStage + kBBytes;
+  static constexpr int kStages = 3;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
+                                    2 * 2 * BLOCK_N * 4 /*scale,shift per group*/ + 9 * kMaxCin * 4 /*dw weights*/ + 256;
+};
+
+struct FsParams {
+  int H, W, Cin, Cout, relu;
+  int tiles_h, tiles_w, total_tiles, num_k;
+  const float* wd9c; const float* scale; const float* shift;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(640, 1)
+sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmY, const FsParams p) {
+  using Cfg = FsCfg<BLOCK_N>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* a_tiles = stages + S * Cfg::kStageBytes;                  // [2][16 KB]
+  uint8_t* out_tiles = a_tiles + 2 * kTileBytes;                     // [group][16 KB]
+  float* s_par = reinterpret_cast<float*>(out_tiles + 2 * kTileBytes);   // [group][2][BLOCK_N]
+  float* s_wd = s_par + 2 * 2 * BLOCK_N;                             // [9][Cin]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_wd + 9 * kMaxCin);
+  uint64_t* ld_full = bars;              // [S]
+  uint64_t* x_empty = bars + S;          // [S]
+  uint64_t* a_full = bars + 2 * S;       // [2]
+  uint64_t* a_empty = bars + 2 * S + 2;  // [2]
+  uint64_t* tmem_full = bars + 2 * S + 4;
+  uint64_t* tmem_empty = bars + 2 * S + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = p.num_k;
+
+  for (int i = threadIdx.x; i < 9 * p.Cin; i += blockDim.x) s_wd[i] = p.wd9c[i];
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 9); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr, 2 * BLOCK_N); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int wb = tile % p.tiles_w; const int t2 = tile / p.tiles_w;
+        const int hb = t2 % p.tiles_h; const int n = t2 / p.tiles_h;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&x_empty[s], ph ^ 1);
+          mbar_expect_tx(&ld_full[s], kXBytes + Cfg::kBBytes);
+          uint8_t* st = stages + s * Cfg::kStageBytes;
+          tma_load_4d(st, &tmX, &ld_full[s], kb * 64, wb * kPW - 1, hb * kPH - 1, n, 0x1000000000000000ull);
+          tma_load_2d(st + kXStage, &tmB, &ld_full[s], kb * 64, 0, kEvictLast);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = fs_idesc(BLOCK_N);
+      int s = 0; uint32_t ph = 0; int ai = 0; uint32_t aph = 0; int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&ld_full[s], ph);            // pointwise-kernel slice has landed
+          mbar_wait(&a_full[ai], aph);           // depthwise tile is complete and visible to the async proxy
+          tc_fence_after();
+          const uint64_t adesc = fs_smem_desc(smem_u32(a_tiles + ai * kTileBytes));
+          const uint64_t bdesc = fs_smem_desc(smem_u32(stages + s * Cfg::kStageBytes + kXStage));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&a_empty[ai]);
+          umma_commit(&x_empty[s]);
+          if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
+          if (++s == S) { s = 0; ph ^= 1; }
+          if (++ai == 2) { ai = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================================== depthwise producers
+    const int t = (warp - 4) * 32 + lane;
+    const int col = t >> 4, cg = t & 15;
+    const uint32_t x_off = (uint32_t)col * 128u + (uint32_t)cg * 8u;
+    int s = 0; uint32_t ph = 0; int ai = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_k; ++kb) {
+        float k9[9][4];
+        const int c = kb * 64 + cg * 4;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          if (c < p.Cin) {
+            const float4 w4 = *reinterpret_cast<const float4*>(s_wd + i * p.Cin + c);
+            k9[i][0] = w4.x; k9[i][1] = w4.y; k9[i][2] = w4.z; k9[i][3] = w4.w;
+          } else { k9[i][0] = k9[i][1] = k9[i][2] = k9[i][3] = 0.f; }
+        }
+        mbar_wait(&ld_full[s], ph);
+        mbar_wait(&a_empty[ai], aph ^ 1);
+        const uint8_t* xs = stages + s * Cfg::kStageBytes + x_off;
+        uint8_t* at = a_tiles + ai * kTileBytes;
+        float prev[4] = {0.f, 0.f, 0.f, 0.f}, cur[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < kXRows; ++r) {
+          const uint2 ra = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128);
+          const uint2 rb = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128 + 128);
+          const uint2 rc = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128 + 256);
+          const float a[4] = {__uint_as_float(ra.x << 16), __uint_as_float(ra.x & 0xffff0000u), __uint_as_float(ra.y << 16), __uint_as_float(ra.y & 0xffff0000u)};
+          const float b[4] = {__uint_as_float(rb.x << 16), __uint_as_float(rb.x & 0xffff0000u), __uint_as_float(rb.y << 16), __uint_as_float(rb.y & 0xffff0000u)};
+          const float cc[4] = {__uint_as_float(rc.x << 16), __uint_as_float(rc.x & 0xffff0000u), __uint_as_float(rc.y << 16), __uint_as_float(rc.y & 0xffff0000u)};
+          if (r >= 2) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
+            const uint32_t m = (uint32_t)((r - 2) * kPW + col);
+            *reinterpret_cast<uint2*>(at + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + (((uint32_t)cg & 1u) << 3)) =
+                make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            prev[j] = fmaf(k9[5][j], cc[j], fmaf(k9[4][j], b[j], fmaf(k9[3][j], a[j], cur[j])));
+            cur[j]  = fmaf(k9[2][j], cc[j], fmaf(k9[1][j], b[j], k9[0][j] * a[j]));
+          }
+        }
+        fs_fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05 (async proxy)
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&a_full[ai]); mbar_arrive(&x_empty[s]); }
+        if (++s == S) { s = 0; ph ^= 1; }
+        if (++ai == 2) { ai = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 12) {
+    // ===================================================================== epilogue groups
+    const int g = (warp - 12) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int gtid = (warp - 12 - 4 * g) * 32 + lane;
+    const bool issuer = gtid == 0;
+    uint8_t* buf = out_tiles + g * kTileBytes;
+    float* par_scale = s_par + g * 2 * BLOCK_N;
+    float* par_shift = par_scale + BLOCK_N;
+    for (int i = gtid; i < BLOCK_N; i += 128) {
+      par_scale[i] = (i < p.Cout && p.scale) ? __ldg(p.scale + i) : 1.f;
+      par_shift[i] = (i < p.Cout && p.shift) ? __ldg(p.shift + i) : 0.f;
+    }
+    fs_bar_sync(1 + g, 128);
+    const uint32_t sw = (uint32_t)(row & 7);
+    uint8_t* my_row = buf + row * 128;
+    int it = g;
+    for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int wb = tile % p.tiles_w; const int t2 = tile / p.tiles_w;
+      const int hb = t2 % p.tiles_h; const int n = t2 / p.tiles_h;
+      mbar_wait(&tmem_full[g], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N;
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 64; ++c) {
+        if (c * 64 >= p.Cout) break;
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read `buf`
+        fs_bar_sync(1 + g, 128);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c * 64 + half * 32, r);
+          tmem_ld_wait();
+          const float* ps = par_scale + c * 64 + half * 32;
+          const float* phf = par_shift + c * 64 + half * 32;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ps + i);
+            const float4 h4 = *reinterpret_cast<const float4*>(phf + i);
+            v[i] = fmaf(__uint_as_float(r[i]), s4.x, h4.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s4.y, h4.y);
+            v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s4.z, h4.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s4.w, h4.w);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            *reinterpret_cast<uint4*>(my_row + ((((uint32_t)(half * 4 + j)) ^ sw) << 4)) = o;
+          }
+        }
+        if (c == BLOCK_N / 64 - 1 || (c + 1) * 64 >= p.Cout) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[g]);
+        }
+        fs_fence_proxy_async();
+        fs_bar_sync(1 + g, 128);
+        if (issuer) {
+          fs_tma_store_4d(&tmY, buf, c * 64, wb * kPW, hb * kPH, n);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+}
+
+static int fs_tmap_4d(CUtensorMap* map, const void* base, int64_t ld, int N, int H, int W, int C, int box_w, int box_h,
+                      CUtensorMapSwizzle swz, const char* who) {
+  PFN_encodeTiled fn = get_encode_fn();
+  UNET_REQUIRE(fn, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64u, (cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
+  return UNET_OK;
+}
+
+template <int BLOCK_N>
+static int fs_launch(const CUtensorMap& tmX, const CUtensorMap& tmB, const CUtensorMap& tmY, const FsParams& p, cudaStream_t st) {
+  using Cfg = FsCfg<BLOCK_N>;
+  static SmemAttrOnce once;
+  if (cudaError_t e = ensure_dynamic_smem(once, sepconv_fused_kernel<BLOCK_N>, Cfg::kSmemBytes))
+    return set_cuda_error(e, "sepconv_fused: cudaFuncSetAttribute");
+  const unsigned grid = (unsigned)i64min(p.total_tiles, sm_count());
+  sepconv_fused_kernel<BLOCK_N><<<grid, 640, Cfg::kSmemBytes, st>>>(tmX, tmB, tmY, p);
+  UNET_LAUNCH_CHECK("sepconv_fused");
+  return UNET_OK;
+}
+
+}  // namespace unet
+
+using namespace unet;
+
+extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* wd9c, const void* wp_t, int64_t ldw,
+                                      const float* scale, const float* shift, int relu, void* y, int64_t ldy,
+                                      int N, int H, int W, int Cin, int Cout, void* stream) {
+  UNET_REQUIRE(x && wd9c && wp_t && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UNET_EINVAL, "sepconv_fused: bad argument");
+  UNET_REQUIRE(ldx >= Cin && ldy >= Cout && ldw >= Cin, UNET_EINVAL, "sepconv_fused: leading dimension too small");
+  UNET_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin <= kMaxCin && Cout <= 128, UNET_EUNSUPPORTED,
+               "sepconv_fused: needs Cin%%8==0, Cout%%8==0, Cin <= %d, Cout <= 128 (got %d -> %d)", kMaxCin, Cin, Cout);
+  UNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(wp_t) && aligned16(wd9c),
+               UNET_EALIGN, "sepconv_fused: operands need 16B-aligned bases and ld%%8==0");
+  UNET_REQUIRE((!scale || aligned16(scale)) && (!shift || aligned16(shift)), UNET_EALIGN, "sepconv_fused: scale/shift must be 16B aligned");
+  CUtensorMap tmX, tmB, tmY;
+  if (int e = fs_tmap_4d(&tmX, x, ldx, N, H, W, Cin, kXCols, kXRows, CU_TENSOR_MAP_SWIZZLE_NONE, "sepconv_fused(x)")) return e;
+  if (int e = fs_tmap_4d(&tmY, y, ldy, N, H, W, Cout, kPW, kPH, CU_TENSOR_MAP_SWIZZLE_128B, "sepconv_fused(y)")) return e;
+  const int bn = Cout > 64 ? 128 : 64;
+  {
+    PFN_encodeTiled fn = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wp_t), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "sepconv_fused(w): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  }
+  FsParams p{};
+  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu;
+  p.tiles_h = (int)ceil_div(H, kPH); p.tiles_w = (int)ceil_div(W, kPW);
+  const int64_t tiles = (int64_t)N * p.tiles_h * p.tiles_w;
+  UNET_REQUIRE(tiles < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "sepconv_fused: too many tiles");
+  p.total_tiles = (int)tiles; p.num_k = (int)ceil_div(Cin, 64);
+  p.wd9c = wd9c; p.scale = scale; p.shift = shift;
+  cudaStream_t st = (cudaStream_t)stream;
+  return bn == 128 ? fs_launch<128>(tmX, tmB, tmY, p, st) : fs_launch<64>(tmX, tmB, tmY, p, st);
+}

@@ -91,6 +91,7 @@ class UNetEngine:
         self._drop_seed = {name: (seed * 7919 + i * 104729) & 0x7FFFFFFF
                            for i, name in enumerate(["bneck_dropout", "dec4_dropout", "dec3_dropout", "dec2_dropout"])}
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
+        self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
@@ -246,6 +247,14 @@ class UNetEngine:
             ops.stem_fwd(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel"), y,
                          scale=self.fold[0, o:o + c] if self.use_bn else None,
                          shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True)
+            return y
+        if self.fuse_sepconv and ops.sepconv_fused_supported(x, y.shape[-1]):
+            # whole conv_block in one kernel: the depthwise result is produced on chip as the GEMM's A operand
+            name = f"{prefix}_sepconv/pointwise_kernel"
+            o, c = self._bn_off[prefix]
+            ops.sepconv_fused(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._stage[name + "^T"], y,
+                              scale=self.fold[0, o:o + c] if self.use_bn else None,
+                              shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True)
             return y
         level = (self.spec.input_size[0] // h).bit_length() - 1
         max_cin = 1024 if level == 4 else 2 * FILTERS[level]

@@ -178,6 +178,28 @@ def stem_bwd(x: torch.Tensor, dz: torch.Tensor, wd9c, wp, dwd9c, dwp) -> None:
           _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, dz), flops=(36 * cin + 4 * cin * cout) * n * h * w)
 
 
+# ------------------------------------------------------------------------------------------------ fused conv_block (inference)
+def sepconv_fused_supported(x: torch.Tensor, cout: int) -> bool:
+    cin = x.shape[-1]
+    return x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and cin <= 512 and cout <= 128
+
+
+def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: torch.Tensor,
+                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu: bool = True) -> None:
+    """conv_block for inference in one kernel: depthwise 3x3 produced on chip as the tcgen05 A operand, pointwise GEMM,
+    folded BN + ReLU epilogue, TMA store into the (possibly channel-sliced) destination."""
+    n, h, w, cin, ldx = _nhwc(x, "x")
+    n2, h2, w2, cout, ldy = _nhwc(y, "y")
+    if (n, h, w) != (n2, h2, w2) or x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
+        raise ValueError("sepconv_fused: x / y disagree or are not bf16")
+    if wp_t.dtype != torch.bfloat16 or tuple(wp_t.shape) != (cout, cin) or wp_t.stride(1) != 1:
+        raise ValueError("sepconv_fused: wp_t must be bf16 [Cout, Cin]")
+    _f32(wd9c, "wd9c"); _f32(scale, "scale"); _f32(shift, "shift")
+    _call("unet_sepconv_fused_fwd", _p(x), ldx, _p(wd9c), _p(wp_t), wp_t.stride(0), _p(scale), _p(shift), int(relu), _p(y), ldy,
+          n, h, w, cin, cout, _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, y, wp_t),
+          flops=(18 * cin + 2 * cin * cout) * n * h * w)
+
+
 # ------------------------------------------------------------------------------------------------ dense contractions
 def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_trans: bool = False, b_trans: bool = False,
          accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,

@@ -532,3 +532,21 @@ def test_sepconv_fused(cfg):
     got = host(buf)
     np.testing.assert_allclose(got[..., 64:], ref, rtol=1.0 / 64, atol=2e-2)
     assert np.all(got[..., :64] == 0)
+
+
+@pytest.mark.parametrize("classes", [1, 8])
+def test_sepconv_fused_with_head(classes):
+    n, h, w, cin, cout = 2, 19, 37, 64, 64
+    x = RNG.standard_normal((n, h, w, cin)).astype(np.float32)
+    wd = RNG.standard_normal((3, 3, cin)).astype(np.float32) / 3
+    wp = (RNG.standard_normal((cin, cout)) / np.sqrt(cin)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, cout).astype(np.float32); sh = RNG.standard_normal(cout).astype(np.float32) * 0.3
+    hw = (RNG.standard_normal((cout, classes)) / 4).astype(np.float32); hb = RNG.standard_normal(classes).astype(np.float32) * 0.1
+    d = bf16_round(R.dwconv3x3(bf16_round(x), wd.astype(np.float64)))
+    y = bf16_round(np.maximum((d.reshape(-1, cin) @ bf16_round(wp)) * sc + sh, 0))
+    logits = y @ hw.astype(np.float64) + hb
+    ref = (R.sigmoid(logits) if classes == 1 else R.softmax(logits)).reshape(n, h, w, classes)
+    probs = torch.full((n, h, w, classes), float("nan"), device="cuda")
+    ops.sepconv_fused(dev(x, torch.bfloat16), dev(wd.reshape(9, cin)), dev(wp.T.copy(), torch.bfloat16), None, scale=dev(sc), shift=dev(sh),
+                      head_w=dev(hw), head_b=dev(hb), head_out=probs)
+    np.testing.assert_allclose(host(probs), ref, rtol=0, atol=5e-3)

@@ -47,14 +47,18 @@ template <int BLOCK_N> struct FsCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kXStage + kBBytes;
   static constexpr int kStages = 3;
+  static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;     // fused output head: w[class][64] + bias[8], per group
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
-                                    2 * 2 * BLOCK_N * 4 /*scale,shift per group*/ + 9 * kMaxCin * 4 /*dw weights*/ + 256;
+                                    2 * (2 * BLOCK_N + kHeadFloats) * 4 /*scale,shift[,head] per group*/ +
+                                    9 * kMaxCin * 4 /*dw weights*/ + 256;
 };
 
 struct FsParams {
   int H, W, Cin, Cout, relu;
   int tiles_h, tiles_w, total_tiles, num_k;
   const float* wd9c; const float* scale; const float* shift;
+  int store_y;                                                       // 0: the activation itself is not needed (head only)
+  const float* head_w; const float* head_b; float* head_out; int head_classes;   // optional fused 1x1 output head (Cout <= 64)
 };
 
 template <int BLOCK_N>
@@ -69,7 +73,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* a_tiles = stages + S * Cfg::kStageBytes;                  // [2][16 KB]
   uint8_t* out_tiles = a_tiles + 2 * kTileBytes;                     // [group][16 KB]
   float* s_par = reinterpret_cast<float*>(out_tiles + 2 * kTileBytes);   // [group][2][BLOCK_N]
-  float* s_wd = s_par + 2 * 2 * BLOCK_N;                             // [9][Cin]
+  float* s_wd = s_par + 2 * (2 * BLOCK_N + Cfg::kHeadFloats);        // [9][Cin]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_wd + 9 * kMaxCin);
   uint64_t* ld_full = bars;              // [S]
   uint64_t* x_empty = bars + S;          // [S]
@@ -200,11 +204,21 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int gtid = (warp - 12 - 4 * g) * 32 + lane;
     const bool issuer = gtid == 0;
     uint8_t* buf = out_tiles + g * kTileBytes;
-    float* par_scale = s_par + g * 2 * BLOCK_N;
+    float* par_scale = s_par + g * (2 * BLOCK_N + Cfg::kHeadFloats);
     float* par_shift = par_scale + BLOCK_N;
+    float* par_head = par_shift + BLOCK_N;
+    constexpr bool kHeadCapable = BLOCK_N == 64;
+    const bool head = kHeadCapable && p.head_out != nullptr;
     for (int i = gtid; i < BLOCK_N; i += 128) {
       par_scale[i] = (i < p.Cout && p.scale) ? __ldg(p.scale + i) : 1.f;
       par_shift[i] = (i < p.Cout && p.shift) ? __ldg(p.shift + i) : 0.f;
+    }
+    if (kHeadCapable && head) {
+      for (int i = gtid; i < 8 * 64; i += 128) {
+        const int cls = i >> 6, k = i & 63;
+        par_head[i] = (cls < p.head_classes && k < p.Cout) ? __ldg(p.head_w + (int64_t)k * p.head_classes + cls) : 0.f;
+      }
+      if (gtid < 8) par_head[8 * 64 + gtid] = (gtid < p.head_classes && p.head_b) ? __ldg(p.head_b + gtid) : 0.f;
     }
     fs_bar_sync(1 + g, 128);
     const uint32_t sw = (uint32_t)(row & 7);
@@ -216,6 +230,9 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       mbar_wait(&tmem_full[g], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N;
+      float hacc[kHeadCapable ? 8 : 1];
+#pragma unroll
+      for (int i = 0; i < (kHeadCapable ? 8 : 1); ++i) hacc[i] = 0.f;
 #pragma unroll
       for (int c = 0; c < BLOCK_N / 64; ++c) {
         if (c * 64 >= p.Cout) break;
@@ -240,6 +257,23 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
           }
+          if (kHeadCapable && head) {             // 1x1 output convolution from the activations as they would be stored (bf16)
+#pragma unroll
+            for (int cls = 0; cls < 8; ++cls) {
+              if (cls < p.head_classes) {
+                const float* hw = par_head + cls * 64 + half * 32;
+                float a = hacc[cls];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                  const float4 w4 = *reinterpret_cast<const float4*>(hw + i);
+                  a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
+                  a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
+                }
+                hacc[cls] = a;
+              }
+            }
+          }
+          if (!p.store_y) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
@@ -254,9 +288,28 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         fs_fence_proxy_async();
         fs_bar_sync(1 + g, 128);
-        if (issuer) {
+        if (issuer && p.store_y) {
           fs_tma_store_4d(&tmY, buf, c * 64, wb * kPW, hb * kPH, n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (kHeadCapable && head) {
+        const int hh = hb * kPH + (row >> 4), ww = wb * kPW + (row & 15);
+        if (hh < p.H && ww < p.W) {
+          const int ncls = p.head_classes;
+          float* dst = p.head_out + (((int64_t)n * p.H + hh) * p.W + ww) * ncls;
+          if (ncls == 1) {
+            dst[0] = 1.f / (1.f + expf(-(hacc[0] + par_head[8 * 64])));
+          } else {
+            float mx = -INFINITY, e[8], den = 0.f;
+#pragma unroll
+            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { hacc[cls] += par_head[8 * 64 + cls]; mx = fmaxf(mx, hacc[cls]); }
+#pragma unroll
+            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { e[cls] = expf(hacc[cls] - mx); den += e[cls]; }
+            const float inv = 1.f / den;
+#pragma unroll
+            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) dst[cls] = e[cls] * inv;
+          }
         }
       }
     }
@@ -299,17 +352,21 @@ using namespace unet;
 
 extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* wd9c, const void* wp_t, int64_t ldw,
                                       const float* scale, const float* shift, int relu, void* y, int64_t ldy,
-                                      int N, int H, int W, int Cin, int Cout, void* stream) {
-  UNET_REQUIRE(x && wd9c && wp_t && y && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UNET_EINVAL, "sepconv_fused: bad argument");
-  UNET_REQUIRE(ldx >= Cin && ldy >= Cout && ldw >= Cin, UNET_EINVAL, "sepconv_fused: leading dimension too small");
+                                      int N, int H, int W, int Cin, int Cout,
+                                      const float* head_w, const float* head_b, float* head_out, int head_classes, void* stream) {
+  UNET_REQUIRE(x && wd9c && wp_t && (y || head_out) && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UNET_EINVAL, "sepconv_fused: bad argument");
+  UNET_REQUIRE(ldx >= Cin && (!y || ldy >= Cout) && ldw >= Cin, UNET_EINVAL, "sepconv_fused: leading dimension too small");
+  UNET_REQUIRE(!head_out || (head_w && head_classes >= 1 && head_classes <= 8 && Cout <= 64), UNET_EINVAL,
+               "sepconv_fused: the fused head needs head_w, 1 <= classes <= 8 and Cout <= 64");
   UNET_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin <= kMaxCin && Cout <= 128, UNET_EUNSUPPORTED,
                "sepconv_fused: needs Cin%%8==0, Cout%%8==0, Cin <= %d, Cout <= 128 (got %d -> %d)", kMaxCin, Cin, Cout);
-  UNET_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldw % 8 == 0 && aligned16(x) && aligned16(y) && aligned16(wp_t) && aligned16(wd9c),
+  UNET_REQUIRE(ldx % 8 == 0 && (!y || (ldy % 8 == 0 && aligned16(y))) && ldw % 8 == 0 && aligned16(x) && aligned16(wp_t) && aligned16(wd9c),
                UNET_EALIGN, "sepconv_fused: operands need 16B-aligned bases and ld%%8==0");
   UNET_REQUIRE((!scale || aligned16(scale)) && (!shift || aligned16(shift)), UNET_EALIGN, "sepconv_fused: scale/shift must be 16B aligned");
   CUtensorMap tmX, tmB, tmY;
   if (int e = fs_tmap_4d(&tmX, x, ldx, N, H, W, Cin, kXCols, kXRows, CU_TENSOR_MAP_SWIZZLE_NONE, "sepconv_fused(x)")) return e;
-  if (int e = fs_tmap_4d(&tmY, y, ldy, N, H, W, Cout, kPW, kPH, CU_TENSOR_MAP_SWIZZLE_128B, "sepconv_fused(y)")) return e;
+  if (y) { if (int e = fs_tmap_4d(&tmY, y, ldy, N, H, W, Cout, kPW, kPH, CU_TENSOR_MAP_SWIZZLE_128B, "sepconv_fused(y)")) return e; }
+  else tmY = tmX;        // placeholder descriptor: nothing is stored through it
   const int bn = Cout > 64 ? 128 : 64;
   {
     PFN_encodeTiled fn = get_encode_fn();
@@ -329,6 +386,8 @@ extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* w
   UNET_REQUIRE(tiles < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "sepconv_fused: too many tiles");
   p.total_tiles = (int)tiles; p.num_k = (int)ceil_div(Cin, 64);
   p.wd9c = wd9c; p.scale = scale; p.shift = shift;
+  p.store_y = y != nullptr;
+  p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_classes = head_classes;
   cudaStream_t st = (cudaStream_t)stream;
   return bn == 128 ? fs_launch<128>(tmX, tmB, tmY, p, st) : fs_launch<64>(tmX, tmB, tmY, p, st);
 }

@@ -328,13 +328,18 @@ class UNetEngine:
             # dec1_block2's pointwise GEMM applies BN + ReLU and the 1x1 sigmoid/softmax head in its epilogue; the
             # 64-channel activation it would have produced is never written
             prefix = "dec1_block2"
-            d = pl.buf("d0", (B * H * W * 2 * FILTERS[0],))[: B * H * W * FILTERS[0]].view(B, H, W, FILTERS[0])
-            ops.dwconv3x3(cur, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
             o, c = self._bn_off[prefix]
-            ops.gemm(d, self._stage[f"{prefix}_sepconv/pointwise_kernel^T"], None, b_trans=True, epilogue=ops.EPI_HEAD,
-                     scale=self.fold[0, o:o + c] if self.use_bn else None,
-                     shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"),
-                     head_w=self._mat("output_mask/kernel"), head_b=self.wview("output_mask/bias"), head_out=probs)
+            sc = self.fold[0, o:o + c] if self.use_bn else None
+            sh = self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias")
+            wpt = self._stage[f"{prefix}_sepconv/pointwise_kernel^T"]
+            hw, hb = self._mat("output_mask/kernel"), self.wview("output_mask/bias")
+            if self.fuse_sepconv and ops.sepconv_fused_supported(cur, FILTERS[0]):
+                ops.sepconv_fused(cur, self._mat(f"{prefix}_sepconv/depthwise_kernel"), wpt, None, scale=sc, shift=sh,
+                                  head_w=hw, head_b=hb, head_out=probs)
+            else:
+                d = pl.buf("d0", (B * H * W * 2 * FILTERS[0],))[: B * H * W * FILTERS[0]].view(B, H, W, FILTERS[0])
+                ops.dwconv3x3(cur, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
+                ops.gemm(d, wpt, None, b_trans=True, epilogue=ops.EPI_HEAD, scale=sc, shift=sh, head_w=hw, head_b=hb, head_out=probs)
         else:
             ops.head_fwd(cur, self._mat("output_mask/kernel"), self.wview("output_mask/bias"), probs)
         return probs

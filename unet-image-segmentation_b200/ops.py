@@ -184,20 +184,34 @@ def sepconv_fused_supported(x: torch.Tensor, cout: int) -> bool:
     return x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and cin <= 512 and cout <= 128
 
 
-def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: torch.Tensor,
-                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu: bool = True) -> None:
+def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Optional[torch.Tensor],
+                  scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu: bool = True,
+                  head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
+                  head_out: Optional[torch.Tensor] = None) -> None:
     """conv_block for inference in one kernel: depthwise 3x3 produced on chip as the tcgen05 A operand, pointwise GEMM,
-    folded BN + ReLU epilogue, TMA store into the (possibly channel-sliced) destination."""
+    folded BN + ReLU epilogue, TMA store into the (possibly channel-sliced) destination; optionally the 1x1 output head
+    (sigmoid / softmax) from the same registers, in which case `y` may be None."""
     n, h, w, cin, ldx = _nhwc(x, "x")
-    n2, h2, w2, cout, ldy = _nhwc(y, "y")
-    if (n, h, w) != (n2, h2, w2) or x.dtype != torch.bfloat16 or y.dtype != torch.bfloat16:
-        raise ValueError("sepconv_fused: x / y disagree or are not bf16")
-    if wp_t.dtype != torch.bfloat16 or tuple(wp_t.shape) != (cout, cin) or wp_t.stride(1) != 1:
-        raise ValueError("sepconv_fused: wp_t must be bf16 [Cout, Cin]")
-    _f32(wd9c, "wd9c"); _f32(scale, "scale"); _f32(shift, "shift")
+    cout = wp_t.shape[0]
+    ldy = 0
+    if y is not None:
+        n2, h2, w2, c2, ldy = _nhwc(y, "y")
+        if (n, h, w, cout) != (n2, h2, w2, c2) or y.dtype != torch.bfloat16:
+            raise ValueError("sepconv_fused: x / y disagree or y is not bf16")
+    if x.dtype != torch.bfloat16 or wp_t.dtype != torch.bfloat16 or wp_t.shape[1] != cin or wp_t.stride(1) != 1:
+        raise ValueError("sepconv_fused: x must be bf16 and wp_t bf16 [Cout, Cin]")
+    _f32(wd9c, "wd9c"); _f32(scale, "scale"); _f32(shift, "shift"); _f32(head_w, "head_w"); _f32(head_b, "head_b"); _f32(head_out, "head_out")
+    classes = 0
+    if head_out is not None:
+        if head_w is None or head_w.shape[0] != cout or head_out.numel() != n * h * w * head_w.shape[1]:
+            raise ValueError("sepconv_fused: head_w must be [Cout, classes] and head_out [N,H,W,classes]")
+        classes = head_w.shape[1]
+    elif y is None:
+        raise ValueError("sepconv_fused: nothing to produce")
     _call("unet_sepconv_fused_fwd", _p(x), ldx, _p(wd9c), _p(wp_t), wp_t.stride(0), _p(scale), _p(shift), int(relu), _p(y), ldy,
-          n, h, w, cin, cout, _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, y, wp_t),
-          flops=(18 * cin + 2 * cin * cout) * n * h * w)
+          n, h, w, cin, cout, _p(head_w), _p(head_b), _p(head_out), classes, _stream(),
+          tag=f"{n}x{h}x{w}x{cin}->{cout}{'+head' if head_out is not None else ''}",
+          nbytes=_nbytes(x, y, wp_t, head_out), flops=(18 * cin + 2 * cin * cout) * n * h * w)
 
 
 # ------------------------------------------------------------------------------------------------ dense contractions

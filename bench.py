@@ -325,26 +325,45 @@ def run_b200(args):
 
     if rank != 0:
         return
-    # ---------------- roofline of the dominant kernel
+    # ---------------- roofline of the dominant kernel: the C-ABI entry point (one CUDA kernel, all its shapes) with the
+    # largest share of the step; achieved = its algorithmic bytes (or flops) over all launches / its summed launch time
     rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     kernel_ms = sum(r["ms"] for _, r in rows)
-    top_key, top = rows[0]
-    per_call_ms = top["ms"] / top["calls"]
+    byname = {}
+    for k, r in rows:
+        nm = k.split("[")[0]
+        if nm == "gemm_tc":
+            nm = "gemm_tc(" + k.split("[")[1].split(":")[0] + ")"      # nt / convt / wgrad are different kernels
+        a = byname.setdefault(nm, dict(ms=0.0, calls=0, bytes=0, flops=0, top=k, top_ms=0.0))
+        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]
+        if r["ms"] > a["top_ms"]:
+            a["top"], a["top_ms"] = k, r["ms"]
+    top_name, top = max(byname.items(), key=lambda kv: kv[1]["ms"])
     ai = top["flops"] / max(top["bytes"], 1)
-    if top_key.startswith("gemm_tc") and ai > RIDGE_FLOP_PER_BYTE:
-        roof = {"bound": "tensor", "achieved": round(top["flops"] / top["calls"] / (per_call_ms * 1e-3) / 1e12, 2),
-                "peak": tc_peak, "unit": "TFLOP/s"}
+    if top_name.startswith("gemm_tc") and ai > RIDGE_FLOP_PER_BYTE:
+        roof = {"bound": "tensor", "achieved": round(top["flops"] / (top["ms"] * 1e-3) / 1e12, 2), "peak": tc_peak, "unit": "TFLOP/s"}
     else:
-        roof = {"bound": "hbm", "achieved": round(top["bytes"] / top["calls"] / (per_call_ms * 1e-3) / 1e9, 1),
-                "peak": hbm_peak, "unit": "GB/s"}
+        roof = {"bound": "hbm", "achieved": round(top["bytes"] / (top["ms"] * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s"}
     roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
-    roof["kernel"] = top_key
+    roof["kernel"] = top_name
+    roof["launches_per_step"] = round(top["calls"] / args.steps, 1)
+    roof["avg_launch_ms"] = round(top["ms"] / top["calls"], 4)
+    roof["algorithmic_bytes_per_launch"] = int(top["bytes"] / top["calls"])
     roof["share_of_step"] = round(top["ms"] / kernel_ms, 4)
     roof["peak_source"] = f"{peak_kind} ({'MEASURED_PEAKS.json' if peak_kind == 'measured' else 'B200_PROFILING.md fallback'}, sustained)"
     roof["traffic"] = None
-    try:
+    try:        # ncu --set full dram bytes of this kernel's largest shape, scaled to the average launch of the step
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            roof["traffic"] = json.load(f).get(top_key)
+            tr = json.load(f)
+        shape_key = top["top"]
+        if shape_key not in tr:     # another shape of the same kernel was captured
+            cands = [k for k in tr if k.split("[")[0] == shape_key.split("[")[0] and k in prof]
+            shape_key = cands[0] if cands else shape_key
+        if shape_key in tr and shape_key in prof:
+            ratio = tr[shape_key] / (prof[shape_key]["bytes"] / prof[shape_key]["calls"])
+            roof["traffic"] = int(ratio * top["bytes"] / top["calls"])
+            roof["traffic_over_algorithmic"] = round(ratio, 4)
+            roof["traffic_shape"] = shape_key
     except Exception:
         pass
     # whole-step HBM view: algorithmic bytes of every launch / step time

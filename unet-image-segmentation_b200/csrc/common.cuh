@@ -82,6 +82,33 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = a;
 }
+// 8-byte shared-memory load through an explicit shared-window address (pointer arithmetic on the dynamic-smem base
+// otherwise degrades to generic LD)
+__device__ __forceinline__ uint2 lds64(uint32_t saddr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
+  return r;
+}
+// Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2): two IEEE round-to-nearest FMAs per issued instruction, bit-identical
+// to two scalar fmaf() calls.  The depthwise kernels are issue-bound on the FMA pipe without it.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 // value a store8/load8 round trip would produce (so statistics match what is stored)
 template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
 

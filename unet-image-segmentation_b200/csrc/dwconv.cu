@@ -114,13 +114,14 @@ template <typename T> struct StripCfg {
   static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + 128;
 };
 
-template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float (&v)[8 / sizeof(T)]);
-template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float (&v)[4]) {
-  v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
-  v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+// 8 bytes of channels -> fp32 pairs (the operands of the packed FFMA2 path)
+template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float2 (&v)[4 / sizeof(T)]);
+template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float2 (&v)[2]) {
+  v[0] = make_float2(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xffff0000u));
+  v[1] = make_float2(__uint_as_float(r.y << 16), __uint_as_float(r.y & 0xffff0000u));
 }
-template <> __device__ __forceinline__ void unpack8<float>(const uint2& r, float (&v)[2]) {
-  v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y);
+template <> __device__ __forceinline__ void unpack8<float>(const uint2& r, float2 (&v)[1]) {
+  v[0] = make_float2(__uint_as_float(r.x), __uint_as_float(r.y));
 }
 __device__ __forceinline__ uint2 pack8(const float (&v)[4], __nv_bfloat16*) {
   return make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
@@ -171,52 +172,57 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
   const int c = c0 + cg * NV;
   const bool live = (w0 + px < W) && (c < C);
-  float k9[9][NV];
+  constexpr int NP = NV / 2;                       // fp32 pairs per thread: every FMA below is a packed FFMA2
+  float2 k9[9][NP];
 #pragma unroll
   for (int i = 0; i < 9; ++i) {
     const int src = flip ? 8 - i : i;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) k9[i][j] = 0.f;
+    for (int j = 0; j < NP; ++j) k9[i][j] = make_float2(0.f, 0.f);
     if (c < C) {
       if (NV == 4) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)src * C + c));
-        k9[i][0] = a.x; k9[i][1] = a.y; k9[i][2 % NV] = a.z; k9[i][3 % NV] = a.w;
+        k9[i][0] = make_float2(a.x, a.y); k9[i][1 % NP] = make_float2(a.z, a.w);
       } else {
         const float2 a = __ldg(reinterpret_cast<const float2*>(w9c + (int64_t)src * C + c));
-        k9[i][0] = a.x; k9[i][1] = a.y;
+        k9[i][0] = a;
       }
     }
   }
   uint32_t seed = 0u;
   if (DROP) seed = drop_seed(dp);
-  float prev[NV], cur[NV];
+  float2 prev[NP], cur[NP];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) { prev[j] = 0.f; cur[j] = 0.f; }
+  for (int j = 0; j < NP; ++j) { prev[j] = make_float2(0.f, 0.f); cur[j] = make_float2(0.f, 0.f); }
   T* yptr = y + (((int64_t)n * H + (h0 - 2)) * W + (w0 + px)) * ldy + c;   // advanced one row per input row
   const int64_t yrow = (int64_t)W * ldy;
   const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+  const uint32_t smem_base = smem_u32(smem);
   int r_in = h0 - 1;
 
   for (int k = 0; k < nst; ++k) {
     const int s = k % S;
     if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
     mbar_wait(&full_bar[s], (k / S) & 1);
-    const uint8_t* st = smem + s * Cfg::kStageBytes + tile_off;
+    const uint32_t st = smem_base + s * Cfg::kStageBytes + tile_off;
     uint2 ra[RH], rb[RH], rc[RH];
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr) {        // all shared loads of the stage first: 12 independent requests in flight
-      ra[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128);
-      rb[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128 + 128);
-      rc[rr] = *reinterpret_cast<const uint2*>(st + rr * (TW + 2) * 128 + 256);
+      ra[rr] = lds64(st + rr * (TW + 2) * 128);
+      rb[rr] = lds64(st + rr * (TW + 2) * 128 + 128);
+      rc[rr] = lds64(st + rr * (TW + 2) * 128 + 256);
     }
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr, ++r_in, yptr += yrow) {
-      float a[NV], b[NV], cc[NV];
+      float2 a[NP], b[NP], cc[NP];
       unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc);
       if (r_in > h0 && r_in <= h1 && live) {   // output row r_in-1 is complete once kernel row 2 has seen input row r_in
         float o[NV];
 #pragma unroll
-        for (int j = 0; j < NV; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
+        for (int j = 0; j < NP; ++j) {
+          const float2 v = fma2(k9[8][j], cc[j], fma2(k9[7][j], b[j], fma2(k9[6][j], a[j], prev[j])));
+          o[2 * j] = v.x; o[2 * j + 1] = v.y;
+        }
         if (DROP) {
           const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
           dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
@@ -224,9 +230,9 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
         *reinterpret_cast<uint2*>(yptr) = pack8(o, (T*)nullptr);
       }
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        prev[j] = fmaf(k9[5][j], cc[j], fmaf(k9[4][j], b[j], fmaf(k9[3][j], a[j], cur[j])));
-        cur[j]  = fmaf(k9[2][j], cc[j], fmaf(k9[1][j], b[j], k9[0][j] * a[j]));
+      for (int j = 0; j < NP; ++j) {
+        prev[j] = fma2(k9[5][j], cc[j], fma2(k9[4][j], b[j], fma2(k9[3][j], a[j], cur[j])));
+        cur[j]  = fma2(k9[2][j], cc[j], fma2(k9[1][j], b[j], mul2(k9[0][j], a[j])));
       }
     }
     __syncwarp();
@@ -527,43 +533,45 @@ dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
   }
 
   const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
-  float acc[9][NV], dm[NV], d0[NV];
+  constexpr int NP = NV / 2;                       // fp32 pairs per thread (packed FFMA2)
+  float2 acc[9][NP], dm[NP], d0[NP];
 #pragma unroll
   for (int i = 0; i < 9; ++i)
 #pragma unroll
-    for (int j = 0; j < NV; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NP; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < NV; ++j) { dm[j] = 0.f; d0[j] = 0.f; }
+  for (int j = 0; j < NP; ++j) { dm[j] = make_float2(0.f, 0.f); d0[j] = make_float2(0.f, 0.f); }
   const uint32_t xoff = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+  const uint32_t smem_base = smem_u32(smem);
 
   for (int k = 0; k < nst; ++k) {
     const int s = k % S;
     if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
     mbar_wait(&full_bar[s], (k / S) & 1);
-    const uint8_t* sx = smem + s * Cfg::kStageBytes + xoff;
-    const uint8_t* sd = smem + s * Cfg::kStageBytes + Cfg::kXBytes + xoff;
+    const uint32_t sx = smem_base + s * Cfg::kStageBytes + xoff;
+    const uint32_t sd = sx + Cfg::kXBytes;
     uint2 ra[RH], rb[RH], rc[RH], rd[RH];
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr) {        // all shared loads of the stage first (16 independent requests in flight)
-      ra[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128);
-      rb[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 128);
-      rc[rr] = *reinterpret_cast<const uint2*>(sx + rr * (TW + 2) * 128 + 256);
-      rd[rr] = *reinterpret_cast<const uint2*>(sd + rr * TW * 128);
+      ra[rr] = lds64(sx + rr * (TW + 2) * 128);
+      rb[rr] = lds64(sx + rr * (TW + 2) * 128 + 128);
+      rc[rr] = lds64(sx + rr * (TW + 2) * 128 + 256);
+      rd[rr] = lds64(sd + rr * TW * 128);
     }
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr) {
       const int q = h0 - 1 + k * RH + rr;           // x row; dy row q+1 sits at the same stage row
-      float a[NV], b[NV], c[NV], dp[NV];
+      float2 a[NP], b[NP], c[NP], dp[NP];
       unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], c); unpack8<T>(rd[rr], dp);
       const bool dp_live = q + 1 < h1;              // dy rows of other segments (or past the image) do not belong to this strip
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const float dpj = dp_live ? dp[j] : 0.f;
-        const float aj = a[j], bj = b[j], cj = c[j];   // rows past h1 meet only zeroed dy rows
+      for (int j = 0; j < NP; ++j) {
+        const float2 dpj = dp_live ? dp[j] : make_float2(0.f, 0.f);
+        const float2 aj = a[j], bj = b[j], cj = c[j];   // rows past h1 meet only zeroed dy rows
         // kernel row r multiplies input row q into output row q - r + 1
-        acc[0][j] = fmaf(aj, dpj, acc[0][j]); acc[1][j] = fmaf(bj, dpj, acc[1][j]); acc[2][j] = fmaf(cj, dpj, acc[2][j]);
-        acc[3][j] = fmaf(aj, d0[j], acc[3][j]); acc[4][j] = fmaf(bj, d0[j], acc[4][j]); acc[5][j] = fmaf(cj, d0[j], acc[5][j]);
-        acc[6][j] = fmaf(aj, dm[j], acc[6][j]); acc[7][j] = fmaf(bj, dm[j], acc[7][j]); acc[8][j] = fmaf(cj, dm[j], acc[8][j]);
+        acc[0][j] = fma2(aj, dpj, acc[0][j]);   acc[1][j] = fma2(bj, dpj, acc[1][j]);   acc[2][j] = fma2(cj, dpj, acc[2][j]);
+        acc[3][j] = fma2(aj, d0[j], acc[3][j]); acc[4][j] = fma2(bj, d0[j], acc[4][j]); acc[5][j] = fma2(cj, d0[j], acc[5][j]);
+        acc[6][j] = fma2(aj, dm[j], acc[6][j]); acc[7][j] = fma2(bj, dm[j], acc[7][j]); acc[8][j] = fma2(cj, dm[j], acc[8][j]);
         dm[j] = d0[j]; d0[j] = dpj;
       }
     }
@@ -576,7 +584,8 @@ dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
   for (int i = 0; i < 9; ++i)
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
-      const float v = acc[i][j] + __shfl_xor_sync(0xffffffffu, acc[i][j], 16);
+      const float mine = (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x;
+      const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
       if (lane < 16) atomicAdd(&s_acc[i * Cfg::CB + cg * NV + j], v);
     }
   __syncthreads();

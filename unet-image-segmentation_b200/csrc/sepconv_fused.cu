@@ -153,40 +153,43 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     int s = 0; uint32_t ph = 0; int ai = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_k; ++kb) {
-        float k9[9][4];
+        float2 k9[9][2];                        // fp32 pairs: every FMA below is a packed FFMA2
         const int c = kb * 64 + cg * 4;
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
           if (c < p.Cin) {
             const float4 w4 = *reinterpret_cast<const float4*>(s_wd + i * p.Cin + c);
-            k9[i][0] = w4.x; k9[i][1] = w4.y; k9[i][2] = w4.z; k9[i][3] = w4.w;
-          } else { k9[i][0] = k9[i][1] = k9[i][2] = k9[i][3] = 0.f; }
+            k9[i][0] = make_float2(w4.x, w4.y); k9[i][1] = make_float2(w4.z, w4.w);
+          } else { k9[i][0] = k9[i][1] = make_float2(0.f, 0.f); }
         }
         mbar_wait(&ld_full[s], ph);
         mbar_wait(&a_empty[ai], aph ^ 1);
-        const uint8_t* xs = stages + s * Cfg::kStageBytes + x_off;
+        const uint32_t xs = smem_u32(stages + s * Cfg::kStageBytes) + x_off;
         uint8_t* at = a_tiles + ai * kTileBytes;
-        float prev[4] = {0.f, 0.f, 0.f, 0.f}, cur[4] = {0.f, 0.f, 0.f, 0.f};
+        float2 prev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cur[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int r = 0; r < kXRows; ++r) {
-          const uint2 ra = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128);
-          const uint2 rb = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128 + 128);
-          const uint2 rc = *reinterpret_cast<const uint2*>(xs + r * kXCols * 128 + 256);
-          const float a[4] = {__uint_as_float(ra.x << 16), __uint_as_float(ra.x & 0xffff0000u), __uint_as_float(ra.y << 16), __uint_as_float(ra.y & 0xffff0000u)};
-          const float b[4] = {__uint_as_float(rb.x << 16), __uint_as_float(rb.x & 0xffff0000u), __uint_as_float(rb.y << 16), __uint_as_float(rb.y & 0xffff0000u)};
-          const float cc[4] = {__uint_as_float(rc.x << 16), __uint_as_float(rc.x & 0xffff0000u), __uint_as_float(rc.y << 16), __uint_as_float(rc.y & 0xffff0000u)};
+          const uint2 ra = lds64(xs + r * kXCols * 128);
+          const uint2 rb = lds64(xs + r * kXCols * 128 + 128);
+          const uint2 rc = lds64(xs + r * kXCols * 128 + 256);
+          const float2 a[2] = {make_float2(__uint_as_float(ra.x << 16), __uint_as_float(ra.x & 0xffff0000u)),
+                               make_float2(__uint_as_float(ra.y << 16), __uint_as_float(ra.y & 0xffff0000u))};
+          const float2 b[2] = {make_float2(__uint_as_float(rb.x << 16), __uint_as_float(rb.x & 0xffff0000u)),
+                               make_float2(__uint_as_float(rb.y << 16), __uint_as_float(rb.y & 0xffff0000u))};
+          const float2 cc[2] = {make_float2(__uint_as_float(rc.x << 16), __uint_as_float(rc.x & 0xffff0000u)),
+                                make_float2(__uint_as_float(rc.y << 16), __uint_as_float(rc.y & 0xffff0000u))};
           if (r >= 2) {
-            float o[4];
+            float2 o[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = fmaf(k9[8][j], cc[j], fmaf(k9[7][j], b[j], fmaf(k9[6][j], a[j], prev[j])));
+            for (int j = 0; j < 2; ++j) o[j] = fma2(k9[8][j], cc[j], fma2(k9[7][j], b[j], fma2(k9[6][j], a[j], prev[j])));
             const uint32_t m = (uint32_t)((r - 2) * kPW + col);
             *reinterpret_cast<uint2*>(at + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + (((uint32_t)cg & 1u) << 3)) =
-                make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+                make_uint2(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y));
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            prev[j] = fmaf(k9[5][j], cc[j], fmaf(k9[4][j], b[j], fmaf(k9[3][j], a[j], cur[j])));
-            cur[j]  = fmaf(k9[2][j], cc[j], fmaf(k9[1][j], b[j], k9[0][j] * a[j]));
+          for (int j = 0; j < 2; ++j) {
+            prev[j] = fma2(k9[5][j], cc[j], fma2(k9[4][j], b[j], fma2(k9[3][j], a[j], cur[j])));
+            cur[j]  = fma2(k9[2][j], cc[j], fma2(k9[1][j], b[j], mul2(k9[0][j], a[j])));
           }
         }
         fs_fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05 (async proxy)

@@ -91,6 +91,42 @@ def test_dwconv_bwd_weight(dtype, shape):
     np.testing.assert_allclose(host(dw).reshape(3, 3, -1), ref, rtol=1e-4, atol=1e-3 * np.sqrt(np.prod(shape[:3])))
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (1, 70, 12, 128), (2, 8, 8, 1024), (2, 33, 40, 16), (1, 67, 35, 32)])
+@pytest.mark.parametrize("mode", ["plain", "mask", "drop"])
+def test_dwconv_bwd_fused(dtype, shape, mode):
+    """one pass over dy: dx (+ReLU mask from x>0, BN-backward sums, or dropout on dx) and dw; ragged strips, views"""
+    n, h, w, c = shape
+    x = RNG.standard_normal(shape).astype(np.float32)
+    if mode == "mask":
+        x = np.maximum(x, 0)                            # x is a post-ReLU activation
+    dy = RNG.standard_normal(shape).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    xr, dyr = (bf16_round(x), bf16_round(dy)) if dtype == torch.bfloat16 else (x.astype(np.float64), dy.astype(np.float64))
+    dx_ref, dw_ref = R.dwconv3x3_bwd(xr, wk.astype(np.float64), dyr)
+    ctot = c + 16
+    xbuf = torch.zeros((n, h, w, ctot), device="cuda", dtype=dtype); xbuf[..., 8:8 + c] = dev(x, dtype)
+    dxbuf = torch.zeros((n, h, w, ctot), device="cuda", dtype=dtype)
+    dw = torch.zeros((9, c), device="cuda")
+    sums = torch.zeros((2, c), device="cuda") if mode == "mask" else None
+    drop = ops.make_dropout(0.25, 91, ctot=ctot, c0=8) if mode == "drop" else None
+    assert ops.dwconv3x3_bwd_supported(xbuf[..., 8:8 + c], dev(dy, dtype), dxbuf[..., 8:8 + c])
+    ops.dwconv3x3_bwd(xbuf[..., 8:8 + c], dev(dy, dtype), dev(wk.reshape(9, -1)), dxbuf[..., 8:8 + c], dw,
+                      relu_mask=(mode == "mask"), bn_sums=sums, drop=drop)
+    if mode == "mask":
+        dx_ref = dx_ref * (xr > 0)
+    if mode == "drop":
+        dx_ref = dx_ref * R.dropout_multiplier((n, h, w, ctot), 0.25, 91)[..., 8:8 + c]
+    got = host(dxbuf)
+    np.testing.assert_allclose(got[..., 8:8 + c], dx_ref, **tol(dtype))
+    assert np.all(got[..., :8] == 0) and np.all(got[..., 8 + c:] == 0)
+    np.testing.assert_allclose(host(dw).reshape(3, 3, -1), dw_ref, rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+    if mode == "mask":
+        g = got[..., 8:8 + c].astype(np.float64)
+        np.testing.assert_allclose(host(sums)[0], g.sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+        np.testing.assert_allclose(host(sums)[1], (g * xr).sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+
+
 # ------------------------------------------------------------------------------------------------ fused first block
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 16, 32), (3, 21, 45), (1, 64, 64)])

@@ -63,6 +63,11 @@ elif name == "dw_fwd256":
 elif name == "dw_bwd_w":
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     run(lambda: ops.dwconv3x3_bwd_weight(x, dy, dw), 2 * M * 64 * 2)
+elif name in ("dw_bwd", "dw_bwd_mask"):
+    x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
+    dx, w, sums = torch.empty_like(x), torch.rand((9, 64), device=dev), torch.zeros((2, 64), device=dev)
+    mask = name.endswith("mask")
+    run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, relu_mask=mask, bn_sums=sums if mask else None), 3 * M * 64 * 2)
 elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
     z, dy, dz = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf)
     v = lambda: torch.rand(64, device=dev)

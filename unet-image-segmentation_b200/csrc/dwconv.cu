@@ -5,6 +5,7 @@
 // input element is requested from DRAM once.  Each thread owns 8 (forward) or 4 (weight gradient) consecutive
 // channels of one image column and slides down a segment of rows keeping the running partial sums in
 // registers; the three column taps of a row come from the two neighbouring threads' lines in L1.
+#include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -615,6 +616,231 @@ static int dw_wgrad_strip_launch(const void* x, int64_t ldx, const void* dy, int
   return UNET_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ fused backward, TMA strips
+// Both gradients of the depthwise convolution from ONE pass over dy (SeparableConv2D backward, u_net.py:14-20):
+//   dx = dy (*) rot180(w)                      (the forward strip kernel with the flipped taps)
+//   dw[r][s] += sum x[i][j] * dy[i-r+1][j-s+1]  (x centre column only; the column halo is on dy, which dx needs anyway)
+// so dy is read once instead of twice and x needs no halo.  Two TMA streams per stage: dy with its column halo (rows
+// h0-1 ..) and x one row ahead (rows h0 ..).  RELU_MASK: x is the post-ReLU output y of the producing conv_block, so
+// (x > 0) is that block's ReLU mask: the kernel stores dx * (x > 0) — the gradient w.r.t. the BatchNormalization output —
+// and accumulates the two reductions BatchNormalization backward needs, sum(g) and sum(g * y), from the stored values.
+template <typename T> struct BwCfg {
+  static constexpr int NV = 8 / (int)sizeof(T);         // channels per thread (8 bytes)
+  static constexpr int CB = 128 / (int)sizeof(T);       // channels per CTA (128 bytes)
+  // 24 columns x 16 channel groups = 384 threads: up to 170 registers per thread hold the 9 taps, the 9 tap accumulators,
+  // the sliding sums and a 4-row window of shared loads without spilling (512 threads would cap at 128)
+  static constexpr int TW = 24, RH = 4, S = 6;
+  static constexpr int kThreads = TW * 16;
+  static constexpr int kDBytes = RH * (TW + 2) * 128;
+  static constexpr int kXBytes = RH * TW * 128;
+  static constexpr int kStageBytes = kDBytes + kXBytes;
+  static constexpr int kSmemBytes = S * kStageBytes + 11 * CB * 4 + 2 * S * 8 + 128;
+};
+
+template <typename T, bool DROP, bool RELU_MASK>
+__global__ void __launch_bounds__(BwCfg<T>::kThreads, 1)
+dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
+                           const float* __restrict__ w9c, T* __restrict__ dx, int64_t lddx, float* __restrict__ dw9c,
+                           float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp) {
+  using Cfg = BwCfg<T>;
+  constexpr int NV = Cfg::NV, NP = NV / 2, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  float* s_acc = reinterpret_cast<float*>(smem + S * Cfg::kStageBytes);       // [9 taps + 2 sums][CB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_acc + 11 * Cfg::CB);
+  uint64_t* empty_bar = full_bar + S;
+
+  int item = blockIdx.x;
+  const int cb = item % ncb; item /= ncb;
+  const int tw = item % ntw; item /= ntw;
+  const int hs = item % nseg;
+  const int n = item / nseg;
+  const int c0 = cb * Cfg::CB, w0 = tw * TW;
+  const int h0 = hs * seg_rows, h1 = min(H, h0 + seg_rows);
+  const int nst = (h1 - h0 + 2 + RH - 1) / RH;          // dy rows h0-1 .. h1
+  const int lane = threadIdx.x & 31;
+
+  for (int i = threadIdx.x; i < 11 * Cfg::CB; i += blockDim.x) s_acc[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], Cfg::kThreads / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {
+    const int s = k % S;
+    if (k >= S) mbar_wait(&empty_bar[s], ((k / S) - 1) & 1);
+    mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+    uint8_t* st = smem + s * Cfg::kStageBytes;
+    tma_load_4d(st, &tmD, &full_bar[s], c0, w0 - 1, h0 - 1 + k * RH, n, kEvictNormal);
+    tma_load_4d(st + Cfg::kDBytes, &tmX, &full_bar[s], c0, w0, h0 + k * RH, n, kEvictNormal);
+  };
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmX);
+    for (int k = 0; k < S - 1 && k < nst; ++k) issue(k);
+  }
+
+  const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
+  const int c = c0 + cg * NV;
+  const bool live = (w0 + px < W) && (c < C);
+  float2 kf[9][NP];                                // flipped taps: kf[i] = w[8 - i]
+#pragma unroll
+  for (int i = 0; i < 9; ++i) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) kf[i][j] = make_float2(0.f, 0.f);
+    if (c < C) {
+      if (NV == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w9c + (int64_t)(8 - i) * C + c));
+        kf[i][0] = make_float2(a.x, a.y); kf[i][1 % NP] = make_float2(a.z, a.w);
+      } else {
+        kf[i][0] = __ldg(reinterpret_cast<const float2*>(w9c + (int64_t)(8 - i) * C + c));
+      }
+    }
+  }
+  uint32_t seed = 0u;
+  if (DROP) seed = drop_seed(dp);
+  const float2 zero2 = make_float2(0.f, 0.f);
+  float2 acc[9][NP], prev[NP], cur[NP], xm[NP], x0[NP], s1[NP], s2[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[i][j] = zero2;
+    prev[j] = cur[j] = xm[j] = x0[j] = s1[j] = s2[j] = zero2;
+  }
+  T* optr = dx + (((int64_t)n * H + (h0 - 2)) * W + (w0 + px)) * lddx + c;   // advanced one row per dy row
+  const int64_t orow = (int64_t)W * lddx;
+  const uint32_t off = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+  const uint32_t smem_base = smem_u32(smem);
+  int t = h0 - 1;                                   // dy row being consumed; the x row of the same stage slot is t + 1
+
+  // EDGE stages (the first and the last two of a strip) carry the segment predicates; the stages in between never need them
+  auto stage_rows = [&](uint32_t sd, auto edge_tag) {
+    constexpr bool EDGE = decltype(edge_tag)::value;
+    const uint32_t sx = sd + Cfg::kDBytes;
+    uint2 ra[RH], rb[RH], rc[RH], rx[RH];
+#pragma unroll
+    for (int rr = 0; rr < RH; ++rr) {
+      ra[rr] = lds64(sd + rr * (TW + 2) * 128);
+      rb[rr] = lds64(sd + rr * (TW + 2) * 128 + 128);
+      rc[rr] = lds64(sd + rr * (TW + 2) * 128 + 256);
+      rx[rr] = lds64(sx + rr * TW * 128);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RH; ++rr, ++t, optr += orow) {
+      float2 a[NP], b[NP], cc[NP], xp[NP];
+      unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc); unpack8<T>(rx[rr], xp);
+      const bool xp_dead = EDGE && !((t + 1 >= h0) && (t + 1 < h1));   // x rows of other segments belong to other strips
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        if (xp_dead) xp[j] = zero2;
+        // weight gradient: dw[r][s] += x[t+r-1][w] * dy[t][w-s+1]   (a, b, cc = dy at columns w-1, w, w+1)
+        acc[0][j] = fma2(xm[j], cc[j], acc[0][j]); acc[1][j] = fma2(xm[j], b[j], acc[1][j]); acc[2][j] = fma2(xm[j], a[j], acc[2][j]);
+        acc[3][j] = fma2(x0[j], cc[j], acc[3][j]); acc[4][j] = fma2(x0[j], b[j], acc[4][j]); acc[5][j] = fma2(x0[j], a[j], acc[5][j]);
+        acc[6][j] = fma2(xp[j], cc[j], acc[6][j]); acc[7][j] = fma2(xp[j], b[j], acc[7][j]); acc[8][j] = fma2(xp[j], a[j], acc[8][j]);
+      }
+      if ((!EDGE || (t > h0 && t <= h1)) && live) {   // dx row t-1 is complete once flipped-kernel row 2 has seen dy row t
+        float o[NV];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          float2 v = fma2(kf[8][j], cc[j], fma2(kf[7][j], b[j], fma2(kf[6][j], a[j], prev[j])));
+          if (RELU_MASK) { v.x = xm[j].x > 0.f ? v.x : 0.f; v.y = xm[j].y > 0.f ? v.y : 0.f; }   // xm = x[t-1] = y of the producer
+          o[2 * j] = v.x; o[2 * j + 1] = v.y;
+        }
+        if (DROP) {
+          const uint64_t base = (uint64_t)(((int64_t)n * H + (t - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
+          dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
+        }
+        if (RELU_MASK) {
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const float2 g = make_float2(round_to<T>(o[2 * j]), round_to<T>(o[2 * j + 1]));
+            s1[j].x += g.x; s1[j].y += g.y;
+            s2[j] = fma2(g, xm[j], s2[j]);
+          }
+        }
+        *reinterpret_cast<uint2*>(optr) = pack8(o, (T*)nullptr);
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        prev[j] = fma2(kf[5][j], cc[j], fma2(kf[4][j], b[j], fma2(kf[3][j], a[j], cur[j])));
+        cur[j]  = fma2(kf[2][j], cc[j], fma2(kf[1][j], b[j], mul2(kf[0][j], a[j])));
+        xm[j] = x0[j]; x0[j] = xp[j];
+      }
+    }
+  };
+
+  for (int k = 0; k < nst; ++k) {
+    const int s = k % S;
+    if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
+    mbar_wait(&full_bar[s], (k / S) & 1);
+    const uint32_t sd = smem_base + s * Cfg::kStageBytes + off;
+    if (k == 0 || k >= nst - 2) stage_rows(sd, std::true_type{});
+    else stage_rows(sd, std::false_type{});
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+
+  // lanes l and l^16 hold the same channels of neighbouring columns
+  auto fold = [&](float mine, int slot, int j) {
+    const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
+    if (lane < 16) atomicAdd(&s_acc[slot * Cfg::CB + cg * NV + j], v);
+  };
+#pragma unroll
+  for (int i = 0; i < 9; ++i)
+#pragma unroll
+    for (int j = 0; j < NV; ++j) fold((j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x, i, j);
+  if (RELU_MASK) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      fold((j & 1) ? s1[j / 2].y : s1[j / 2].x, 9, j);
+      fold((j & 1) ? s2[j / 2].y : s2[j / 2].x, 10, j);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * Cfg::CB; i += blockDim.x) {
+    const int tap = i / Cfg::CB, ch = c0 + i % Cfg::CB;
+    if (ch < C) atomicAdd(&dw9c[(int64_t)tap * C + ch], s_acc[i]);
+  }
+  if (RELU_MASK && bn_sums) {
+    for (int i = threadIdx.x; i < 2 * Cfg::CB; i += blockDim.x) {
+      const int which = i / Cfg::CB, ch = c0 + i % Cfg::CB;
+      if (ch < C) atomicAdd(&bn_sums[(int64_t)which * C + ch], s_acc[9 * Cfg::CB + i]);
+    }
+  }
+}
+
+template <typename T> static bool dw_strip_ok(const void* a, int64_t lda, const void* b, int64_t ldb, int C) {
+  constexpr int kNV = 8 / (int)sizeof(T);
+  return (C % kNV == 0) && C >= 8 && ((lda * sizeof(T)) % 16 == 0) && ((ldb * sizeof(T)) % 16 == 0) && aligned16(a) && aligned16(b);
+}
+
+template <typename T>
+static int dw_bwd_strip_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c, void* dx, int64_t lddx,
+                               float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, cudaStream_t st) {
+  using Cfg = BwCfg<T>;
+  CUtensorMap tmD, tmX;
+  if (int e = make_nhwc_tmap<T>(&tmD, dy, lddy, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_bwd(dy)")) return e;
+  if (int e = make_nhwc_tmap<T>(&tmX, x, ldx, N, H, W, C, Cfg::TW, Cfg::RH, "dwconv3x3_bwd(x)")) return e;
+  static SmemAttrOnce o00, o01, o10, o11;
+  cudaError_t ea = ensure_dynamic_smem(o00, dwconv3x3_bwd_strip_kernel<T, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o01, dwconv3x3_bwd_strip_kernel<T, false, true>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o10, dwconv3x3_bwd_strip_kernel<T, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o11, dwconv3x3_bwd_strip_kernel<T, true, true>, Cfg::kSmemBytes);
+  if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_bwd: cudaFuncSetAttribute");
+  const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
+  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 4);
+  const int nseg = (int)ceil_div(H, seg);
+  const int64_t items = (int64_t)N * nseg * ntw * ncb;
+  UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd: too many strips");
+#define UNET_BW_LAUNCH(D, M) dwconv3x3_bwd_strip_kernel<T, D, M><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp)
+  if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true); else UNET_BW_LAUNCH(true, false); }
+  else       { if (relu_mask) UNET_BW_LAUNCH(false, true); else UNET_BW_LAUNCH(false, false); }
+#undef UNET_BW_LAUNCH
+  UNET_LAUNCH_CHECK("dwconv3x3_bwd(strip)");
+  return UNET_OK;
+}
+
 // C <= 4 (the RGB input image): one thread per (image, row segment, column), all channels, 9*C register accumulators,
 // warp shuffle -> shared -> one global atomic per (tap, channel) per block.
 template <typename T, int CC>
@@ -746,4 +972,26 @@ extern "C" int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void*
   if (dtype == UNET_F32)  return dw_bwd_weight_launch<float>(x, ldx, dy, lddy, dw9c, N, H, W, C, st);
   if (dtype == UNET_BF16) return dw_bwd_weight_launch<__nv_bfloat16>(x, ldx, dy, lddy, dw9c, N, H, W, C, st);
   return set_error(UNET_EINVAL, "dwconv3x3_bwd_weight: bad dtype %d", dtype);
+}
+
+extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
+                                  void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
+                                  int relu_mask, float* bn_sums, const unet_dropout* drop, void* stream) {
+  UNET_REQUIRE(x && dy && w9c && dx && dw9c, UNET_EINVAL, "dwconv3x3_bwd: null pointer");
+  UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, UNET_EINVAL, "dwconv3x3_bwd: bad dims %d %d %d %d", N, H, W, C);
+  UNET_REQUIRE(ldx >= C && lddy >= C && lddx >= C, UNET_EINVAL, "dwconv3x3_bwd: ld < C");
+  UNET_REQUIRE(!bn_sums || relu_mask, UNET_EINVAL, "dwconv3x3_bwd: bn_sums needs relu_mask");
+  const DropArgs dp = make_drop(drop);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_F32) {
+    UNET_REQUIRE(dw_strip_ok<float>(x, ldx, dy, lddy, C) && dw_strip_ok<float>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
+                 "dwconv3x3_bwd: needs C%%2==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
+    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, st);
+  }
+  if (dtype == UNET_BF16) {
+    UNET_REQUIRE(dw_strip_ok<__nv_bfloat16>(x, ldx, dy, lddy, C) && dw_strip_ok<__nv_bfloat16>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
+                 "dwconv3x3_bwd: needs C%%4==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
+    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, st);
+  }
+  return set_error(UNET_EINVAL, "dwconv3x3_bwd: bad dtype %d", dtype);
 }

@@ -92,6 +92,7 @@ class UNetEngine:
                            for i, name in enumerate(["bneck_dropout", "dec4_dropout", "dec3_dropout", "dec2_dropout"])}
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
+        self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
         self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
@@ -403,9 +404,13 @@ class UNetEngine:
         d = pl.t[prefix + "/d"]
         ops.gemm(d, dz, self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g), a_trans=True, accumulate=True)
         self._pw_dgrad(prefix, dz, dd)
-        ops.dwconv3x3_bwd_weight(x, dd, self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g))
+        wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
+        if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
+            ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop)      # both gradients from one pass over dd
+            return dx_out
+        ops.dwconv3x3_bwd_weight(x, dd, gwd)
         if dx_out is not None:
-            ops.dwconv3x3(dd, self._mat(f"{prefix}_sepconv/depthwise_kernel"), dx_out, flip=True, drop=dx_drop)
+            ops.dwconv3x3(dd, wd, dx_out, flip=True, drop=dx_drop)
         return dx_out
 
     def train_forward_backward(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:

@@ -149,6 +149,30 @@ def dwconv3x3_bwd_weight(x: torch.Tensor, dy: torch.Tensor, dw9c: torch.Tensor) 
           tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(x, dy, dw9c), flops=18 * x.numel())
 
 
+def dwconv3x3_bwd_supported(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor) -> bool:
+    nv = 8 // x.element_size()
+    c = x.shape[-1]
+    return (c % nv == 0 and c >= 8 and all(t.data_ptr() % 16 == 0 and (t.stride(-2) * t.element_size()) % 16 == 0
+                                          for t in (x, dy, dx)))
+
+
+def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torch.Tensor, dw9c: torch.Tensor,
+                  relu_mask: bool = False, bn_sums: Optional[torch.Tensor] = None, drop: Optional[Dropout] = None) -> None:
+    """SeparableConv2D depthwise backward in one pass over dy: input gradient (optionally ReLU-masked by x > 0, with the
+    BatchNormalization-backward reductions sum(g), sum(g*x) accumulated into bn_sums [2,C]) + weight gradient."""
+    n, h, w, c, ldx = _nhwc(x, "x")
+    n2, h2, w2, c2, lddy = _nhwc(dy, "dy")
+    n3, h3, w3, c3, lddx = _nhwc(dx, "dx")
+    if (n, h, w, c) != (n2, h2, w2, c2) or (n, h, w, c) != (n3, h3, w3, c3) or x.dtype != dy.dtype or x.dtype != dx.dtype:
+        raise ValueError("dwconv3x3_bwd: x, dy and dx disagree")
+    _f32(w9c, "w9c"); _f32(dw9c, "dw9c"); _f32(bn_sums, "bn_sums")
+    if w9c.numel() != 9 * c or dw9c.numel() != 9 * c or (bn_sums is not None and bn_sums.numel() != 2 * c):
+        raise ValueError("dwconv3x3_bwd: w9c / dw9c must hold 9*C floats and bn_sums 2*C")
+    _call("unet_dwconv3x3_bwd", _p(x), ldx, _p(dy), lddy, _p(w9c), _p(dx), lddx, _p(dw9c), n, h, w, c, _dt(x),
+          int(relu_mask), _p(bn_sums), _dref(drop), _stream(),
+          tag=f"{n}x{h}x{w}x{c}" + ("+mask" if relu_mask else ""), nbytes=_nbytes(x, dy, dx, w9c), flops=36 * x.numel())
+
+
 # ------------------------------------------------------------------------------------------------ fused first block
 def stem_supported(cin: int, cout: int) -> bool:
     return cin == 3 and cout == 64

@@ -85,6 +85,13 @@ typedef struct {
   const float* head_b;             /* [head_classes] or NULL                                                              */
   float*       head_out;           /* [M, head_classes] fp32 probabilities                                                */
   int          head_classes;
+  /* Operand concatenation (tensor-core path only; used to fold BatchNormalization backward into the pointwise
+     data / weight gradients, see unet_bn_bwd_coef).  split == 0 or NULL second operand: none.
+       a_trans=0: A = [A | A2] along K — columns [0,k_split) from A (pitch lda), [k_split,K) from A2 (pitch lda2);
+       a_trans=1: B = [B | B2] along N — columns [0,n_split) from B (pitch ldb), [n_split,N) from B2 (pitch ldb2).
+     The split must be a multiple of 64. */
+  const void* A2; int64_t lda2; int64_t k_split;
+  const void* B2; int64_t ldb2; int64_t n_split;
 } unet_gemm_args;
 
 /* ---- library ---- */
@@ -97,11 +104,13 @@ int         unet_device_check(int device);     /* UNET_OK iff the device is comp
 /* y[n,i,j,c] = sum_{a,b} x'[n,i+a-1,j+b-1,c] * w[a,b,c], zero 'same' padding.
    x' = x, or max(x*in_scale[c]+in_shift[c],0) when in_scale != NULL (BN+ReLU of the producer fused into the load;
    padding is zero in x' space).  flip=1 correlates with the 180-degree rotated kernel (= gradient w.r.t. input).
-   drop (rate>0) multiplies the OUTPUT by the dropout mask (used by the input-gradient of a dropped tensor). */
+   drop (rate>0) multiplies the OUTPUT by the dropout mask (used by the input-gradient of a dropped tensor).
+   colsum (fp32 [C], accumulated, may be NULL): column sums over (n,i,j) of the stored outputs — the rank-1 term of the
+   folded BatchNormalization backward (unet_bn_bwd_wgrad_combine); TMA-strip path only, not with dropout. */
 int unet_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy,
                        int N, int H, int W, int C, int dtype, int flip,
                        const float* in_scale, const float* in_shift,
-                       const unet_dropout* drop, void* stream);
+                       const unet_dropout* drop, float* colsum, void* stream);
 /* dw[a,b,c] += sum_{n,i,j} x[n,i+a-1,j+b-1,c] * dy[n,i,j,c]   (dw fp32 [3,3,C], accumulated atomically) */
 int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_t lddy, float* dw9c,
                               int N, int H, int W, int C, int dtype, void* stream);
@@ -172,6 +181,20 @@ int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
                       const float* scale, const float* shift, const float* save_mean, const float* save_rstd,
                       const float* dgamma, const float* dbeta, void* dz,
                       int64_t M, int C, int dtype, int relu, const unet_dropout* drop, void* stream);
+
+/* BatchNormalization backward folded into the pointwise contractions (no dz tensor).  With g = dy*[y>0] produced — together
+   with sums[0,c] = sum(g), sums[1,c] = sum(g*y) — by unet_dwconv3x3_bwd(relu_mask=1) (or any producer that has y in
+   registers), BN backward is per-channel affine: dz = A*g + B*z + K.  This call turns the sums into
+     dgamma[c] += sum(g*xhat) = (sums[1]-beta*sums[0])/gamma,  dbeta[c] += sums[0],  coef = [A | B | K] (fp32 [3,C]),
+   and, when w (pointwise kernel, fp32 [Cin,C]) is given, the operands of the folded data gradient
+     wab (bf16 [Cin,2C]) = [w diag(A) | w diag(B)],  bias[i] = sum_c K[c]*w[i,c]
+   so that  dd = [g | z] * wab^T + bias  (unet_gemm_tc, A2 = z, UNET_EPI_AFFINE)  and
+            dW += combine(d^T [g | z], coef, colsum(d))  (unet_gemm_tc a_trans, B2 = z;  unet_bn_bwd_wgrad_combine). */
+int unet_bn_bwd_coef(const float* sums, const float* gamma, const float* beta, const float* save_mean,
+                     const float* save_rstd, int64_t count, float* dgamma, float* dbeta, float* coef,
+                     const float* w, int Cin, int C, void* wab, float* bias, void* stream);
+/* dw[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c];  G fp32 [Cin,2C] = d^T [g | z], coef = [A|B|K], sd[i] = sum_m d[m,i] */
+int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd, float* dw, int Cin, int C, void* stream);
 
 /* ---- MaxPooling2D((2,2)) (u_net.py:69) ---- */
 int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, int H, int W, int C, int dtype, void* stream);

@@ -127,6 +127,71 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
         np.testing.assert_allclose(host(sums)[1], (g * xr).sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
 
 
+def test_dwconv_fwd_colsum():
+    for dtype in DTYPES:
+        shape = (2, 37, 45, 72)
+        x = RNG.standard_normal(shape).astype(np.float32)
+        w = RNG.standard_normal((3, 3, shape[3])).astype(np.float32)
+        y = torch.empty(shape, device="cuda", dtype=dtype)
+        cs = torch.zeros(shape[3], device="cuda")
+        ops.dwconv3x3(dev(x, dtype), dev(w.reshape(9, -1)), y, colsum=cs)
+        np.testing.assert_allclose(host(cs), host(y).sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+
+
+def test_gemm_tc_operand_concatenation():
+    """[A | A2] along K (forward/dgrad layout) and [B | B2] along N (weight-gradient layout) == the concatenated operand"""
+    bf = torch.bfloat16
+    M, K1, K2, N = 1000, 64, 128, 96
+    A, A2, Bt = dev(RNG.standard_normal((M, K1)), bf), dev(RNG.standard_normal((M, K2)), bf), dev(RNG.standard_normal((N, K1 + K2)), bf)
+    bias = dev(RNG.standard_normal(N))
+    ref = torch.empty((M, N), device="cuda", dtype=bf); got = torch.empty_like(ref)
+    ops.gemm(torch.cat([A, A2], 1).contiguous(), Bt, ref, b_trans=True, epilogue=ops.EPI_AFFINE, shift=bias, tensor_core=True)
+    ops.gemm(A, Bt, got, b_trans=True, A2=A2, epilogue=ops.EPI_AFFINE, shift=bias, tensor_core=True)
+    assert torch.equal(ref, got)
+    P, Mo, N1, N2 = 3000, 72, 128, 64
+    Aw, B1, B2 = dev(RNG.standard_normal((P, Mo)), bf), dev(RNG.standard_normal((P, N1)), bf), dev(RNG.standard_normal((P, N2)), bf)
+    ref = torch.zeros((Mo, N1 + N2), device="cuda"); got = torch.zeros_like(ref)
+    ops.gemm(Aw, torch.cat([B1, B2], 1).contiguous(), ref, a_trans=True, accumulate=True, tensor_core=True)
+    ops.gemm(Aw, B1, got, a_trans=True, accumulate=True, B2=B2, tensor_core=True)
+    np.testing.assert_allclose(host(got), host(ref), rtol=1e-5, atol=1e-3)
+    want = host(Aw).T @ np.concatenate([host(B1), host(B2)], 1)
+    np.testing.assert_allclose(host(got), want, rtol=1e-3, atol=5e-2)
+
+
+def test_bn_bwd_folded_into_gemms():
+    """dz = A*g + B*z + K from the sums (sum g, sum g*y): folded data / weight gradients == explicit BatchNormalization backward"""
+    bf = torch.bfloat16
+    M, cin, c = 4096, 128, 64
+    d = bf16_round(RNG.standard_normal((M, cin)))
+    w = RNG.standard_normal((cin, c)).astype(np.float32) / np.sqrt(cin)
+    z = bf16_round(d @ w.astype(np.float64) + 0.3)
+    gamma = RNG.uniform(0.5, 1.5, c); beta = RNG.standard_normal(c) * 0.3
+    mean, var = z.mean(0), z.var(0)
+    rstd = 1.0 / np.sqrt(var + 1e-3)
+    xhat = (z - mean) * rstd
+    y = bf16_round(np.maximum(gamma * xhat + beta, 0))
+    g = bf16_round(RNG.standard_normal((M, c)) * (y > 0))
+    # explicit backward in fp64 (xhat from z, as unet_bn_bwd_reduce/apply do)
+    dgamma, dbeta = (g * xhat).sum(0), g.sum(0)
+    dz = gamma * rstd * (g - dbeta / M - xhat * dgamma / M)
+    dd_ref, dw_ref = dz @ w.astype(np.float64).T, d.T @ dz
+    sums = dev(np.stack([g.sum(0), (g * y).sum(0)]))
+    dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    coef = torch.empty((3, c), device="cuda"); wab = torch.empty((cin, 2 * c), device="cuda", dtype=bf); bias = torch.empty(cin, device="cuda")
+    ops.bn_bwd_coef(sums, dev(gamma), dev(beta), dev(mean), dev(rstd), M, dg, db, coef, w=dev(w), wab=wab, bias=bias)
+    np.testing.assert_allclose(host(db), dbeta, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(host(dg), dgamma, rtol=2e-2, atol=0.5)        # xhat recovered from the bf16 activation
+    gd, zd, dd_ = dev(g, bf), dev(z, bf), dev(d, bf)
+    dd = torch.empty((M, cin), device="cuda", dtype=bf)
+    ops.gemm(gd, wab, dd, b_trans=True, A2=zd, epilogue=ops.EPI_AFFINE, shift=bias)
+    G = torch.zeros((cin, 2 * c), device="cuda"); dw = torch.zeros((cin, c), device="cuda")
+    ops.gemm(dd_, gd, G, a_trans=True, accumulate=True, B2=zd)
+    ops.bn_bwd_wgrad_combine(G, coef, dev(d.sum(0)), dw)
+    scale = np.abs(dd_ref).max()
+    assert np.abs(host(dd) - dd_ref).max() <= 2e-2 * scale
+    assert np.linalg.norm(host(dw) - dw_ref) <= 2e-2 * np.linalg.norm(dw_ref)
+
+
 # ------------------------------------------------------------------------------------------------ fused first block
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 16, 32), (3, 21, 45), (1, 64, 64)])

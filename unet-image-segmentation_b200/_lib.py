@@ -40,6 +40,8 @@ class GemmArgs(C.Structure):
         ("convt_H", C.c_int), ("convt_W", C.c_int),
         ("drop", Dropout),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_classes", C.c_int),
+        ("A2", C.c_void_p), ("lda2", C.c_int64), ("k_split", C.c_int64),
+        ("B2", C.c_void_p), ("ldb2", C.c_int64), ("n_split", C.c_int64),
     ]
 
 
@@ -52,8 +54,10 @@ _SIGNATURES = {
     "unet_sm_arch": [],
     "unet_last_error": [],
     "unet_device_check": [_i],
-    "unet_dwconv3x3_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _dp, _vp],
+    "unet_dwconv3x3_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _dp, _vp, _vp],
     "unet_dwconv3x3_bwd_weight": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
+    "unet_bn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "unet_bn_bwd_wgrad_combine": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "unet_dwconv3x3_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp, _dp, _vp],
     "unet_stem_fwd": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp],
     "unet_stem_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],

@@ -112,7 +112,7 @@ template <typename T> struct StripCfg {
   static constexpr int TW = 32, RH = 4, S = 8;
   static constexpr int kThreads = TW * 16;
   static constexpr int kStageBytes = RH * (TW + 2) * 128;
-  static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + 128;
+  static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + CB * 4 + 128;
 };
 
 // 8 bytes of channels -> fp32 pairs (the operands of the packed FFMA2 path)
@@ -131,16 +131,18 @@ __device__ __forceinline__ uint2 pack8(const float (&v)[2], float*) {
   return make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1]));
 }
 
-template <typename T, bool DROP>
+template <typename T, bool DROP, bool SUMS>
 __global__ void __launch_bounds__(StripCfg<T>::kThreads, 1)
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
-                       int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp) {
+                       int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp,
+                       float* __restrict__ colsum) {
   using Cfg = StripCfg<T>;
   constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + S;
+  float* s_sum = reinterpret_cast<float*>(empty_bar + S);      // [CB] column sums of the stored outputs (SUMS)
 
   int item = blockIdx.x;
   const int cb = item % ncb; item /= ncb;
@@ -152,6 +154,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   const int nst = (h1 - h0 + 2 + RH - 1) / RH;          // input rows h0-1 .. h1
   const int lane = threadIdx.x & 31;
 
+  if (SUMS) for (int i = threadIdx.x; i < Cfg::CB; i += blockDim.x) s_sum[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], Cfg::kThreads / 32); }
     fence_barrier_init();
@@ -192,9 +195,9 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   }
   uint32_t seed = 0u;
   if (DROP) seed = drop_seed(dp);
-  float2 prev[NP], cur[NP];
+  float2 prev[NP], cur[NP], csum[NP];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) { prev[j] = make_float2(0.f, 0.f); cur[j] = make_float2(0.f, 0.f); }
+  for (int j = 0; j < NP; ++j) { prev[j] = make_float2(0.f, 0.f); cur[j] = make_float2(0.f, 0.f); csum[j] = make_float2(0.f, 0.f); }
   T* yptr = y + (((int64_t)n * H + (h0 - 2)) * W + (w0 + px)) * ldy + c;   // advanced one row per input row
   const int64_t yrow = (int64_t)W * ldy;
   const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 8u;
@@ -228,7 +231,14 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
           const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
           dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
         }
-        *reinterpret_cast<uint2*>(yptr) = pack8(o, (T*)nullptr);
+        const uint2 packed = pack8(o, (T*)nullptr);
+        *reinterpret_cast<uint2*>(yptr) = packed;
+        if (SUMS) {                               // column sums of the values as stored (what the pointwise GEMM reads)
+          float2 st2[NP];
+          unpack8<T>(packed, st2);
+#pragma unroll
+          for (int j = 0; j < NP; ++j) { csum[j].x += st2[j].x; csum[j].y += st2[j].y; }
+        }
       }
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
@@ -238,6 +248,17 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
+  }
+  if (SUMS) {                                     // lanes l and l^16 hold the same channels of neighbouring columns
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float mine = (j & 1) ? csum[j / 2].y : csum[j / 2].x;
+      const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
+      if (lane < 16) atomicAdd(&s_sum[cg * NV + j], v);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cfg::CB; i += blockDim.x)
+      if (c0 + i < C) atomicAdd(&colsum[c0 + i], s_sum[i]);
   }
 }
 
@@ -267,13 +288,15 @@ static int pick_seg_rows(int N, int H, int ntw, int ncb, int min_rows, int64_t w
 
 template <typename T>
 static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
-                               int flip, DropArgs dp, cudaStream_t st) {
+                               int flip, DropArgs dp, float* colsum, cudaStream_t st) {
   using Cfg = StripCfg<T>;
+  UNET_REQUIRE(!(colsum && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum and dropout cannot be combined");
   CUtensorMap tm;
   if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
-  static SmemAttrOnce once_plain, once_drop;
-  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true>, Cfg::kSmemBytes);
+  static SmemAttrOnce once_plain, once_drop, once_sums;
+  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_sums, dwconv3x3_strip_kernel<T, false, true>, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_fwd: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
   const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6);
@@ -281,9 +304,11 @@ static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, voi
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
   if (dp.on)
-    dwconv3x3_strip_kernel<T, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
+    dwconv3x3_strip_kernel<T, true, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, nullptr);
+  else if (colsum)
+    dwconv3x3_strip_kernel<T, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, colsum);
   else
-    dwconv3x3_strip_kernel<T, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp);
+    dwconv3x3_strip_kernel<T, false, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, nullptr);
   UNET_LAUNCH_CHECK("dwconv3x3_fwd(strip)");
   return UNET_OK;
 }
@@ -321,11 +346,12 @@ __global__ void dwconv3x3_scalar_kernel(const T* __restrict__ x, int64_t ldx, co
 
 template <typename T>
 static int dw_fwd_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
-                         int flip, const float* in_scale, const float* in_shift, DropArgs dp, cudaStream_t st) {
+                         int flip, const float* in_scale, const float* in_shift, DropArgs dp, float* colsum, cudaStream_t st) {
   const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && aligned16(x) && aligned16(y) &&
                    aligned16(w9c) && (!in_scale || (aligned16(in_scale) && aligned16(in_shift)));
   if (vec && !in_scale)      // the TMA path pads with zeros in INPUT space, which is wrong under a fused input affine
-    return dw_fwd_strip_launch<T>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, st);
+    return dw_fwd_strip_launch<T>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, st);
+  UNET_REQUIRE(!colsum, UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum needs the strip path (C%%8==0, 16B-aligned views, no input affine)");
   if (vec) {
     // rows per thread: long segments amortise the 2 halo rows; shrink until the grid covers the machine twice
     int R = 32;
@@ -951,15 +977,15 @@ using namespace unet;
 extern "C" int unet_dwconv3x3_fwd(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy,
                                   int N, int H, int W, int C, int dtype, int flip,
                                   const float* in_scale, const float* in_shift,
-                                  const unet_dropout* drop, void* stream) {
+                                  const unet_dropout* drop, float* colsum, void* stream) {
   UNET_REQUIRE(x && w9c && y, UNET_EINVAL, "dwconv3x3_fwd: null pointer");
   UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, UNET_EINVAL, "dwconv3x3_fwd: bad dims %d %d %d %d", N, H, W, C);
   UNET_REQUIRE(ldx >= C && ldy >= C, UNET_EINVAL, "dwconv3x3_fwd: ld < C");
   UNET_REQUIRE((in_scale == nullptr) == (in_shift == nullptr), UNET_EINVAL, "dwconv3x3_fwd: scale/shift must come together");
   const DropArgs dp = make_drop(drop);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == UNET_F32)  return dw_fwd_launch<float>(x, ldx, w9c, y, ldy, N, H, W, C, flip, in_scale, in_shift, dp, st);
-  if (dtype == UNET_BF16) return dw_fwd_launch<__nv_bfloat16>(x, ldx, w9c, y, ldy, N, H, W, C, flip, in_scale, in_shift, dp, st);
+  if (dtype == UNET_F32)  return dw_fwd_launch<float>(x, ldx, w9c, y, ldy, N, H, W, C, flip, in_scale, in_shift, dp, colsum, st);
+  if (dtype == UNET_BF16) return dw_fwd_launch<__nv_bfloat16>(x, ldx, w9c, y, ldy, N, H, W, C, flip, in_scale, in_shift, dp, colsum, st);
   return set_error(UNET_EINVAL, "dwconv3x3_fwd: bad dtype %d", dtype);
 }
 

@@ -51,6 +51,63 @@ __global__ void bn_finalize_kernel(const double* colsum, const double* colsq, do
   if (moving_var)  moving_var[c]  = moving_var[c]  * momentum + (float)var  * (1.f - momentum);
 }
 
+// ------------------------------------------------------------------------------------------------ BN backward folded into the GEMMs
+// BatchNormalization backward is affine per channel in (g, z):  dz = A*g + B*z + K  with g = dy*[y>0],
+//   c1 = mean(g), c2 = mean(g*xhat), A = gamma*rstd, B = -A*c2*rstd, K = A*(c2*rstd*mean - c1),
+// so the pointwise data gradient dz*W^T and weight gradient d^T*dz never need dz in memory:
+//   dd = [g | z] * [W diag(A) | W diag(B)]^T + (K W^T)          (one GEMM, K-concatenated A operand, bias epilogue)
+//   dW = (d^T g) diag(A) + (d^T z) diag(B) + colsum(d) K^T       (one GEMM, N-concatenated B operand, then bn_bwd_wgrad_combine)
+// The two reductions arrive as sums[0] = sum(g), sums[1] = sum(g*y) from the kernel that produced g (y = gamma*xhat + beta
+// wherever g != 0, so sum(g*xhat) = (sums[1] - beta*sums[0]) / gamma).  One block per row of W (input channel).
+__global__ void __launch_bounds__(256)
+bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, float inv_count,
+                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
+                   const float* __restrict__ w, int Cin, int C, __nv_bfloat16* __restrict__ wab, float* __restrict__ bias) {
+  __shared__ float s_red[8];
+  const int i = blockIdx.x;
+  float part = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma[c], b = beta[c];
+    const float s1 = sums[c], s2 = sums[C + c];
+    const float dg = g != 0.f ? (s2 - b * s1) / g : 0.f;     // sum(g * xhat)
+    const float c1 = s1 * inv_count, c2 = dg * inv_count;
+    const float A = g * rstd[c];
+    const float B = -A * c2 * rstd[c];
+    const float K = A * (c2 * rstd[c] * mean[c] - c1);
+    if (i == 0) {
+      if (dgamma) dgamma[c] += dg;
+      if (dbeta) dbeta[c] += s1;
+      if (coef) { coef[c] = A; coef[C + c] = B; coef[2 * C + c] = K; }
+    }
+    if (w) {
+      const float wv = w[(int64_t)i * C + c];
+      wab[(int64_t)i * 2 * C + c] = __float2bfloat16_rn(wv * A);
+      wab[(int64_t)i * 2 * C + C + c] = __float2bfloat16_rn(wv * B);
+      part = fmaf(wv, K, part);
+    }
+  }
+  if (w) {
+    part = warp_sum(part);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_red[k];
+      bias[i] = t;
+    }
+  }
+}
+
+// dW[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c]     (G = d^T [g | z], sd = column sums of d)
+__global__ void bn_bwd_wgrad_combine_kernel(const float* __restrict__ G, const float* __restrict__ coef, const float* __restrict__ sd,
+                                            float* __restrict__ dw, int Cin, int C) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Cin * C) return;
+  const int i = (int)(idx / C), c = (int)(idx % C);
+  dw[idx] += G[(int64_t)i * 2 * C + c] * coef[c] + G[(int64_t)i * 2 * C + C + c] * coef[C + c] + sd[i] * coef[2 * C + c];
+}
+
 // ------------------------------------------------------------------------------------------------ BN apply + ReLU (+pool, +dropout)
 // thread layout inside a block: (256/cv pixel slots) x cv channel groups; a thread keeps its 8 channels' scale/shift in
 // registers and strides over pixels (POOL: over 2x2 windows, four 16-byte loads in flight per window).
@@ -729,5 +786,23 @@ extern "C" int unet_seg_loss_finalize(const double* sums, int NC_pairs, float sm
   UNET_REQUIRE(sums && out3 && NC_pairs > 0 && (kind == 0 || kind == 1), UNET_EINVAL, "seg_loss_finalize: bad argument");
   seg_loss_finalize_kernel<<<1, 256, 0, ST>>>(sums, NC_pairs, smooth, kind, grad_scale, out3, coef);
   UNET_LAUNCH_CHECK("seg_loss_finalize");
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_bwd_coef(const float* sums, const float* gamma, const float* beta, const float* save_mean,
+                                const float* save_rstd, int64_t count, float* dgamma, float* dbeta, float* coef,
+                                const float* w, int Cin, int C, void* wab, float* bias, void* stream) {
+  UNET_REQUIRE(sums && gamma && beta && save_mean && save_rstd && C > 0 && count > 0, UNET_EINVAL, "bn_bwd_coef: bad argument");
+  UNET_REQUIRE(!w || (wab && bias && Cin > 0), UNET_EINVAL, "bn_bwd_coef: w needs wab, bias and Cin");
+  bn_bwd_coef_kernel<<<w ? Cin : 1, 256, 0, ST>>>(sums, gamma, beta, save_mean, save_rstd, 1.f / (float)count, dgamma, dbeta, coef,
+                                                 w, Cin, C, (__nv_bfloat16*)wab, bias);
+  UNET_LAUNCH_CHECK("bn_bwd_coef");
+  return UNET_OK;
+}
+
+extern "C" int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd, float* dw, int Cin, int C, void* stream) {
+  UNET_REQUIRE(G && coef && sd && dw && Cin > 0 && C > 0, UNET_EINVAL, "bn_bwd_wgrad_combine: bad argument");
+  bn_bwd_wgrad_combine_kernel<<<grid_for((int64_t)Cin * C), 256, 0, ST>>>(G, coef, sd, dw, Cin, C);
+  UNET_LAUNCH_CHECK("bn_bwd_wgrad_combine");
   return UNET_OK;
 }

@@ -137,8 +137,8 @@ int gemm_validate(const unet_gemm_args* a, const char* who) {
   UNET_REQUIRE(a->A && a->B && (a->C || a->epilogue == UNET_EPI_HEAD), UNET_EINVAL, "%s: null operand", who);
   UNET_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, UNET_EINVAL, "%s: bad shape %lld %lld %lld", who,
                (long long)a->M, (long long)a->N, (long long)a->K);
-  UNET_REQUIRE(a->lda >= (a->a_trans ? a->M : a->K), UNET_EINVAL, "%s: lda too small", who);
-  UNET_REQUIRE(a->ldb >= (a->b_trans ? a->K : a->N), UNET_EINVAL, "%s: ldb too small", who);
+  UNET_REQUIRE(a->lda >= (a->a_trans ? a->M : (a->A2 ? a->k_split : a->K)), UNET_EINVAL, "%s: lda too small", who);
+  UNET_REQUIRE(a->ldb >= (a->b_trans ? a->K : (a->B2 ? a->n_split : a->N)), UNET_EINVAL, "%s: ldb too small", who);
   UNET_REQUIRE(a->in_dtype == UNET_F32 || a->in_dtype == UNET_BF16, UNET_EINVAL, "%s: bad in_dtype", who);
   UNET_REQUIRE(a->out_dtype == UNET_F32 || a->out_dtype == UNET_BF16, UNET_EINVAL, "%s: bad out_dtype", who);
   UNET_REQUIRE(a->epilogue >= UNET_EPI_NONE && a->epilogue <= UNET_EPI_HEAD, UNET_EINVAL, "%s: bad epilogue", who);
@@ -165,6 +165,7 @@ using namespace unet;
 extern "C" int unet_gemm_simt(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_simt")) return e;
   UNET_REQUIRE(a->epilogue != UNET_EPI_HEAD, UNET_EUNSUPPORTED, "gemm_simt: the fused output head exists on the tensor-core path only");
+  UNET_REQUIRE(!a->A2 && !a->B2, UNET_EUNSUPPORTED, "gemm_simt: operand concatenation exists on the tensor-core path only");
   SimtParams p{};
   p.M = a->M; p.N = a->N; p.K = a->K;
   p.A = a->A; p.lda = a->lda; p.B = a->B; p.ldb = a->ldb; p.C = a->C; p.ldc = a->ldc;

@@ -48,6 +48,7 @@ struct TcParams {
   int64_t kb_per_split;     // wgrad: k-blocks per CTA along P
   int num_m_tiles, num_n_tiles;
   const float* head_w; const float* head_b; float* head_out; int head_classes;   // UNET_EPI_HEAD
+  int split_kb;             // nt: k-blocks [split_kb, ...) come from the second A map;  wgrad: column chunks (64) >= split_kb from the second B map
 };
 
 constexpr int kBlockM = 128, kBlockK = 64;
@@ -216,8 +217,8 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
 
 template <int BLOCK_N, bool OUT_BF16>
 __global__ void __launch_bounds__(384, 1)
-gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
   using Cfg = NtCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CW = OUT_BF16 ? 64 : 32;          // output columns per 128-byte staging row
@@ -240,7 +241,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int num_k = (int)((p.K + kBlockK - 1) / kBlockK);
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
@@ -260,7 +261,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, kEvictFirst);
+          if (kb < p.split_kb) tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, kEvictFirst);
+          else tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA2, &full_bar[stage], (kb - p.split_kb) * kBlockK, m_blk * kBlockM, kEvictFirst);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N, kEvictLast);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -508,7 +510,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // with fp32 atomics.  Operands are MN-major: each 64-row (P) x 64-column box lands as an 8 KB SWIZZLE_128B chunk.
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kChunks = BLOCK_N / 64;
@@ -532,7 +535,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int64_t kb_end = min(total_kb, kb_begin + p.kb_per_split);
   const int num_k = (int)i64max(0, kb_end - kb_begin);
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmB2); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full[0], 1);
@@ -556,8 +559,11 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           for (int c = 0; c < 2; ++c)
             tma_load_2d(smem_a + stage * Cfg::kABytes + c * kBoxBytes, &tmA, &full_bar[stage], m_blk * kBlockM + c * 64, prow, kEvictFirst);
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c)
-            tma_load_2d(smem_b + stage * Cfg::kBBytes + c * kBoxBytes, &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 64, prow, kEvictFirst);
+          for (int c = 0; c < kChunks; ++c) {
+            const int nc = n_blk * (BLOCK_N / 64) + c;           // 64-column chunk of the (possibly concatenated) B operand
+            if (nc < p.split_kb) tma_load_2d(smem_b + stage * Cfg::kBBytes + c * kBoxBytes, &tmB, &full_bar[stage], nc * 64, prow, kEvictFirst);
+            else tma_load_2d(smem_b + stage * Cfg::kBBytes + c * kBoxBytes, &tmB2, &full_bar[stage], (nc - p.split_kb) * 64, prow, kEvictFirst);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -660,7 +666,7 @@ static int make_c_tmap(CUtensorMap* map, const unet_gemm_args* a, const char* wh
 }
 
 template <int BLOCK_N, bool OUT_BF16>
-static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st) {
+static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st) {
   using Cfg = NtCfg<BLOCK_N>;
   static SmemAttrOnce once;
   if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, Cfg::kSmemBytes))
@@ -669,13 +675,13 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUten
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   const unsigned grid = (unsigned)i64min(tiles, sm_count());
-  gemm_tc_nt_kernel<BLOCK_N, OUT_BF16><<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmB, tmC, p);
+  gemm_tc_nt_kernel<BLOCK_N, OUT_BF16><<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmA2, tmB, tmC, p);
   UNET_LAUNCH_CHECK("gemm_tc_nt");
   return UNET_OK;
 }
 
 template <int BLOCK_N>
-static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams& p, cudaStream_t st) {
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, TcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static SmemAttrOnce once;
   if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_wgrad_kernel<BLOCK_N>, Cfg::kSmemBytes))
@@ -690,7 +696,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, TcParams
   p.kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, p.kb_per_split);
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  gemm_tc_wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  gemm_tc_wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, tmB2, p);
   UNET_LAUNCH_CHECK("gemm_tc_wgrad");
   return UNET_OK;
 }
@@ -729,22 +735,46 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
     UNET_REQUIRE(a->b_trans == 1, UNET_EUNSUPPORTED, "gemm_tc: forward/dgrad needs B given as [N,K] (b_trans=1)");
     UNET_REQUIRE(!a->accumulate, UNET_EUNSUPPORTED, "gemm_tc: accumulate is only implemented for a_trans=1");
     UNET_REQUIRE(a->K % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: K must be a multiple of 8 (got %lld)", (long long)a->K);
-    if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A)")) return e;
+    UNET_REQUIRE(!a->B2, UNET_EUNSUPPORTED, "gemm_tc: B2 (N concatenation) is only implemented for a_trans=1");
+    CUtensorMap tmA2;
+    p.split_kb = 1 << 30;
+    if (a->A2) {     // A = [A | A2] along K
+      UNET_REQUIRE(a->k_split > 0 && a->k_split < a->K && a->k_split % kBlockK == 0 && a->lda2 >= a->K - a->k_split, UNET_EINVAL,
+                   "gemm_tc: k_split must be a multiple of %d inside (0,K) and lda2 >= K - k_split", kBlockK);
+      if (int e = make_tmap(&tmA, a->A, a->k_split, a->M, a->lda, kBlockM, "gemm_tc(A)")) return e;
+      if (int e = make_tmap(&tmA2, a->A2, a->K - a->k_split, a->M, a->lda2, kBlockM, "gemm_tc(A2)")) return e;
+      p.split_kb = (int)(a->k_split / kBlockK);
+    } else {
+      if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A)")) return e;
+      tmA2 = tmA;
+    }
     if (int e = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, bn, "gemm_tc(B)")) return e;
     CUtensorMap tmC = tmA;       // placeholder descriptor when nothing is stored (HEAD without C)
     if (a->C)
       if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
     const bool ob = a->out_dtype == UNET_BF16;
-    if (bn == 256) return ob ? launch_nt<256, true>(tmA, tmB, tmC, p, st) : launch_nt<256, false>(tmA, tmB, tmC, p, st);
-    if (bn == 128) return ob ? launch_nt<128, true>(tmA, tmB, tmC, p, st) : launch_nt<128, false>(tmA, tmB, tmC, p, st);
-    return ob ? launch_nt<64, true>(tmA, tmB, tmC, p, st) : launch_nt<64, false>(tmA, tmB, tmC, p, st);
+    if (bn == 256) return ob ? launch_nt<256, true>(tmA, tmA2, tmB, tmC, p, st) : launch_nt<256, false>(tmA, tmA2, tmB, tmC, p, st);
+    if (bn == 128) return ob ? launch_nt<128, true>(tmA, tmA2, tmB, tmC, p, st) : launch_nt<128, false>(tmA, tmA2, tmB, tmC, p, st);
+    return ob ? launch_nt<64, true>(tmA, tmA2, tmB, tmC, p, st) : launch_nt<64, false>(tmA, tmA2, tmB, tmC, p, st);
   }
   // weight gradient: C[M,N] += A[K,M]^T * B[K,N]
   UNET_REQUIRE(a->b_trans == 0 && a->accumulate == 1, UNET_EUNSUPPORTED, "gemm_tc: a_trans=1 needs b_trans=0 and accumulate=1");
   UNET_REQUIRE(a->M % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: wgrad M must be a multiple of 8");
+  UNET_REQUIRE(!a->A2, UNET_EUNSUPPORTED, "gemm_tc: A2 (K concatenation) is only implemented for a_trans=0");
   if (int e = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 64, "gemm_tc(wgrad A)")) return e;
-  if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 64, "gemm_tc(wgrad B)")) return e;
-  if (bn == 256) return launch_wgrad<256>(tmA, tmB, p, st);
-  if (bn == 128) return launch_wgrad<128>(tmA, tmB, p, st);
-  return launch_wgrad<64>(tmA, tmB, p, st);
+  CUtensorMap tmB2;
+  p.split_kb = 1 << 30;
+  if (a->B2) {       // B = [B | B2] along N
+    UNET_REQUIRE(a->n_split > 0 && a->n_split < a->N && a->n_split % 64 == 0 && a->ldb2 >= a->N - a->n_split, UNET_EINVAL,
+                 "gemm_tc: n_split must be a multiple of 64 inside (0,N) and ldb2 >= N - n_split");
+    if (int e = make_tmap(&tmB, a->B, a->n_split, a->K, a->ldb, 64, "gemm_tc(wgrad B)")) return e;
+    if (int e = make_tmap(&tmB2, a->B2, a->N - a->n_split, a->K, a->ldb2, 64, "gemm_tc(wgrad B2)")) return e;
+    p.split_kb = (int)(a->n_split / 64);
+  } else {
+    if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 64, "gemm_tc(wgrad B)")) return e;
+    tmB2 = tmB;
+  }
+  if (bn == 256) return launch_wgrad<256>(tmA, tmB, tmB2, p, st);
+  if (bn == 128) return launch_wgrad<128>(tmA, tmB, tmB2, p, st);
+  return launch_wgrad<64>(tmA, tmB, tmB2, p, st);
 }

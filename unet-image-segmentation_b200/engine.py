@@ -84,6 +84,16 @@ class UNetEngine:
             # lr, wd, beta1, beta2, eps, t, grad_scale, unused
             self.hyper = torch.tensor([2e-3, 1e-4, 0.9, 0.999, 1e-7, 1.0, 1.0, 0.0], device=dev)
             self.step_word = torch.zeros(1, device=dev, dtype=torch.int32)
+            # folded BN backward (per *_block1): sums [2,Cout] | sd [Cin] | G [Cin,2Cout] live in ONE fp32 buffer zeroed per step
+            self._fz_off: Dict[str, Tuple[int, int, int]] = {}
+            tot = 0
+            for b in sp.blocks:
+                if b.prefix.endswith("_block1"):
+                    self._fz_off[b.prefix] = (tot, b.cin, b.cout)
+                    tot += 2 * b.cout + b.cin + 2 * b.cin * b.cout
+                    tot = (tot + 63) // 64 * 64
+            self._fz = torch.zeros(max(tot, 64), device=dev)
+            self._fold_w: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._stage: Dict[str, torch.Tensor] = {}
         self._stage_dirty = True
         self._fold_dirty = True
@@ -93,6 +103,8 @@ class UNetEngine:
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
+        self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward of every *_block1 folded into its
+                                                # pointwise data / weight gradient GEMMs (no reduce / apply passes, no dz tensor)
         self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
@@ -346,6 +358,28 @@ class UNetEngine:
         return probs
 
     # ------------------------------------------------------------------------------------------------ training
+    def _folds(self, prefix: str) -> bool:
+        """BatchNormalization backward of this block is folded into its GEMMs (its output feeds *_block2's depthwise
+        convolution directly, whose fused backward kernel delivers the ReLU-masked gradient and the two BN reductions)."""
+        if not (self.fold_bn_bwd and self.fuse_dw_bwd and self.use_bn and self.act_dtype == torch.bfloat16
+                and prefix in self._fz_off):
+            return False
+        _, cin, cout = self._fz_off[prefix]
+        return ops.stem_supported(cin, cout) or cin % 8 == 0      # the depthwise strip kernel supplies colsum(d)
+
+    def _fold_bufs(self, prefix: str):
+        """(sums [2,Cout], sd [Cin], G [Cin,2Cout]) views of the per-step zeroed buffer; (coef, wab, bias) persistent."""
+        o, cin, cout = self._fz_off[prefix]
+        sums = self._fz[o:o + 2 * cout].view(2, cout)
+        sd = self._fz[o + 2 * cout:o + 2 * cout + cin]
+        G = self._fz[o + 2 * cout + cin:o + 2 * cout + cin + 2 * cin * cout].view(cin, 2 * cout)
+        w = self._fold_w.get(prefix)
+        if w is None:
+            w = self._fold_w[prefix] = (torch.empty((3, cout), device=self.device),
+                                        torch.empty((cin, 2 * cout), device=self.device, dtype=torch.bfloat16),
+                                        torch.empty(cin, device=self.device))
+        return sums, sd, G, w[0], w[1], w[2]
+
     def _bn(self, prefix):
         o, c = self._bn_off[prefix]
         return (self.bn_vec[0, o:o + c], self.bn_vec[1, o:o + c], self.bn_vec[2, o:o + c], self.bn_vec[3, o:o + c])
@@ -359,7 +393,7 @@ class UNetEngine:
         wd, wp = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel")
         if not stem:
             d = pl.buf(prefix + "/d", (B, h, w, cin))
-            ops.dwconv3x3(x, wd, d)
+            ops.dwconv3x3(x, wd, d, colsum=self._fold_bufs(prefix)[1] if self._folds(prefix) else None)
         if self.use_bn:
             scale, shift, smean, srstd = self._bn(prefix)
             if stem:
@@ -379,8 +413,11 @@ class UNetEngine:
         ops.bn_act(z, scale, shift, y, relu=True, pooled=pooled, drop=drop)
         return y
 
-    def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None):
-        """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out."""
+    def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None, mask_for=None, folded=False):
+        """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out.
+        mask_for: prefix of the block that produced x (= its post-ReLU output): dx_out then is the ReLU-masked gradient
+        w.r.t. that block's BatchNormalization output and its two BN-backward reductions are accumulated on the way.
+        folded: dy arrived that way, and this block's BatchNormalization backward is folded into the GEMMs below."""
         B, h, w, cin = x.shape
         z = pl.t[prefix + "/z"]
         cout = z.shape[-1]
@@ -395,19 +432,39 @@ class UNetEngine:
             o, c = self._bn_off[prefix]
             scale, shift, smean, srstd = self.ones[:c], self.zeros[:c], None, None
             dgamma, dbeta = None, self.wview(f"{prefix}_sepconv/bias", self.g)
-        ops.bn_bwd_reduce(dy, z, scale, shift, smean, srstd, dgamma, dbeta, relu=True, drop=ydrop)
-        ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True, drop=ydrop)
+        gwp = self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g)
+        if folded:
+            sums, sd, G, coef, wab, bias = self._fold_bufs(prefix)
+            gamma, beta = self.wview(f"{prefix}_bn/gamma"), self.wview(f"{prefix}_bn/beta")
+            if stem:   # the reductions are already there: only the apply pass remains in front of the fused first-block kernel
+                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta)
+                ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True)
+            else:      # dz = A*g + B*z + K never exists: both contractions read [g | z]
+                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef,
+                                w=self._mat(f"{prefix}_sepconv/pointwise_kernel"), wab=wab, bias=bias)
+                d = pl.t[prefix + "/d"]
+                ops.gemm(d, dy, G, a_trans=True, accumulate=True, B2=z)
+                ops.bn_bwd_wgrad_combine(G, coef, sd, gwp)
+                ops.gemm(dy, wab, dd, b_trans=True, A2=z, epilogue=ops.EPI_AFFINE, shift=bias)
+        else:
+            ops.bn_bwd_reduce(dy, z, scale, shift, smean, srstd, dgamma, dbeta, relu=True, drop=ydrop)
+            ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True, drop=ydrop)
         if stem:       # fused first block: both weight gradients from one pass over dz; the image needs no gradient
             ops.stem_bwd(x, dz, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel"),
-                         self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g), self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g))
+                         self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g), gwp)
             return None
-        d = pl.t[prefix + "/d"]
-        ops.gemm(d, dz, self._mat(f"{prefix}_sepconv/pointwise_kernel", self.g), a_trans=True, accumulate=True)
-        self._pw_dgrad(prefix, dz, dd)
+        if not folded:
+            d = pl.t[prefix + "/d"]
+            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True)
+            self._pw_dgrad(prefix, dz, dd)
         wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
-            ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop)      # both gradients from one pass over dd
+            # both gradients from one pass over dd (+ the producer's ReLU mask and BN-backward reductions)
+            ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop, relu_mask=mask_for is not None,
+                              bn_sums=self._fold_bufs(mask_for)[0] if mask_for is not None else None)
             return dx_out
+        if mask_for is not None:
+            raise RuntimeError(f"{prefix}: the folded BatchNormalization backward of {mask_for} needs the fused depthwise backward kernel")
         ops.dwconv3x3_bwd_weight(x, dd, gwd)
         if dx_out is not None:
             ops.dwconv3x3(dd, wd, dx_out, flip=True, drop=dx_drop)
@@ -427,6 +484,7 @@ class UNetEngine:
         self._restage()
         self.g.zero_()
         self.colstats.zero_()
+        self._fz.zero_()
         if self.act_dtype == torch.bfloat16:
             x0 = pl.buf("x_act", (B, H, W, Cin))
             ops.cast(x, x0)
@@ -485,11 +543,13 @@ class UNetEngine:
             o1, o2 = (ci + 1) % 3, (ci + 2) % 3
             # dec{s}_block2: dy (S[ci]) -> dx into S[ci] (dy is dead once dz exists)
             dx = S[ci][: M * f].view(B, h, w, f)
-            self._block_train_bwd(pl, f"dec{s}_block2", xin[f"dec{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx)
+            fold = self._folds(f"dec{s}_block1")
+            self._block_train_bwd(pl, f"dec{s}_block2", xin[f"dec{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
+                                  mask_for=f"dec{s}_block1" if fold else None)
             # dec{s}_block1: input is the (dropped-out) concat buffer
             dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
             self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
-                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None)
+                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None, folded=fold)
             # Conv2DTranspose backward
             xi = convt_in[s]
             Mi = xi.shape[0] * xi.shape[1] * xi.shape[2]
@@ -505,10 +565,11 @@ class UNetEngine:
         M = B * h * w
         o1, o2 = (ci + 1) % 3, (ci + 2) % 3
         dx = S[ci][: M * 1024].view(B, h, w, 1024)
+        fold = self._folds("bneck_block1")
         self._block_train_bwd(pl, "bneck_block2", xin["bneck_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                              ydrop=self._drop("bneck_dropout", 1024))
+                              ydrop=self._drop("bneck_dropout", 1024), mask_for="bneck_block1" if fold else None)
         dpool = S[ci][: M * 512].view(B, h, w, 512)
-        self._block_train_bwd(pl, "bneck_block1", xin["bneck_block1"], dx, (S[o1], S[o2]), dx_out=dpool)
+        self._block_train_bwd(pl, "bneck_block1", xin["bneck_block1"], dx, (S[o1], S[o2]), dx_out=dpool, folded=fold)
         if self.grad_hook:
             self.grad_hook("bottleneck")
         # encoder
@@ -525,11 +586,13 @@ class UNetEngine:
             ops.maxpool2x2_bwd(pl.t[f"enc{s}_block2/z"], scale, shift, dpool, dcat[s][..., f:], dy)
             ci, o1 = o1, ci        # dy now lives in the old o1; the old ci is free
             dx = S[ci][: M * f].view(B, h, w, f)
-            self._block_train_bwd(pl, f"enc{s}_block2", xin[f"enc{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx)
+            fold = self._folds(f"enc{s}_block1")
+            self._block_train_bwd(pl, f"enc{s}_block2", xin[f"enc{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
+                                  mask_for=f"enc{s}_block1" if fold else None)
             x1 = xin[f"enc{s}_block1"]
             cin = x1.shape[-1]
             dpool = S[ci][: M * cin].view(B, h, w, cin) if s > 1 else None
-            self._block_train_bwd(pl, f"enc{s}_block1", x1, dx, (S[o1], S[o2]), dx_out=dpool)
+            self._block_train_bwd(pl, f"enc{s}_block1", x1, dx, (S[o1], S[o2]), dx_out=dpool, folded=fold)
         if self.grad_hook:
             self.grad_hook("encoder")
         self._fold_dirty = True     # moving statistics changed

@@ -125,17 +125,18 @@ def _call(name: str, *args, tag: str = "", nbytes: int = 0, flops: int = 0) -> N
 # ------------------------------------------------------------------------------------------------ depthwise
 def dwconv3x3(x: torch.Tensor, w9c: torch.Tensor, y: torch.Tensor, flip: bool = False,
               in_scale: Optional[torch.Tensor] = None, in_shift: Optional[torch.Tensor] = None,
-              drop: Optional[Dropout] = None) -> None:
-    """SeparableConv2D depthwise half (u_net.py:14-20); flip=True gives the gradient w.r.t. the input."""
+              drop: Optional[Dropout] = None, colsum: Optional[torch.Tensor] = None) -> None:
+    """SeparableConv2D depthwise half (u_net.py:14-20); flip=True gives the gradient w.r.t. the input.
+    colsum (fp32 [C], accumulated): per-channel sums of the stored output."""
     n, h, w, c, ldx = _nhwc(x, "x")
     n2, h2, w2, c2, ldy = _nhwc(y, "y")
     if (n, h, w, c) != (n2, h2, w2, c2) or x.dtype != y.dtype:
         raise ValueError("dwconv3x3: x and y disagree")
-    _f32(w9c, "w9c"); _f32(in_scale, "in_scale"); _f32(in_shift, "in_shift")
-    if w9c.numel() != 9 * c:
-        raise ValueError("dwconv3x3: w9c must hold 9*C floats")
+    _f32(w9c, "w9c"); _f32(in_scale, "in_scale"); _f32(in_shift, "in_shift"); _f32(colsum, "colsum")
+    if w9c.numel() != 9 * c or (colsum is not None and colsum.numel() != c):
+        raise ValueError("dwconv3x3: w9c must hold 9*C floats (and colsum C)")
     _call("unet_dwconv3x3_fwd", _p(x), ldx, _p(w9c), _p(y), ldy, n, h, w, c, _dt(x), int(flip),
-          _p(in_scale), _p(in_shift), _dref(drop), _stream(),
+          _p(in_scale), _p(in_shift), _dref(drop), _p(colsum), _stream(),
           tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(x, y, w9c), flops=18 * x.numel())
 
 
@@ -245,14 +246,32 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
          colsq: Optional[torch.Tensor] = None, convt_hw: Tuple[int, int] = (0, 0),
          drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None,
          head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
-         head_out: Optional[torch.Tensor] = None) -> None:
+         head_out: Optional[torch.Tensor] = None, A2: Optional[torch.Tensor] = None,
+         B2: Optional[torch.Tensor] = None) -> None:
     """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
     hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
-    CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported)."""
+    CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported).
+    A2 (a_trans=False): the A operand is [A | A2] along K;  B2 (a_trans=True): the B operand is [B | B2] along N
+    (tensor-core path only; the first part must be a multiple of 64 columns wide)."""
     ar, ac, lda = _rows(A, "A")
     br, bc, ldb = _rows(B, "B")
     M, K = (ac, ar) if a_trans else (ar, ac)
     N, Kb = (br, bc) if b_trans else (bc, br)
+    lda2 = ldb2 = k_split = n_split = 0
+    if A2 is not None:
+        if a_trans or A2.dtype != A.dtype:
+            raise ValueError("gemm: A2 needs a_trans=False and the dtype of A")
+        a2r, a2c, lda2 = _rows(A2, "A2")
+        if a2r != M:
+            raise ValueError("gemm: A and A2 must have the same number of rows")
+        k_split, K = K, K + a2c
+    if B2 is not None:
+        if not a_trans or b_trans or B2.dtype != B.dtype:
+            raise ValueError("gemm: B2 needs a_trans=True, b_trans=False and the dtype of B")
+        b2r, b2c, ldb2 = _rows(B2, "B2")
+        if b2r != Kb:
+            raise ValueError("gemm: B and B2 must have the same number of rows")
+        n_split, N = N, N + b2c
     if K != Kb:
         raise ValueError(f"gemm: inner dimensions disagree ({K} vs {Kb})")
     if A.dtype != B.dtype:
@@ -291,6 +310,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
         if head_w is None or head_out is None or head_w.shape[0] != N or head_out.numel() != M * head_w.shape[1]:
             raise ValueError("gemm(HEAD): head_w must be [N, classes] and head_out [M, classes]")
         args.head_w, args.head_b, args.head_out, args.head_classes = _p(head_w), _p(head_b), _p(head_out), head_w.shape[1]
+    args.A2, args.lda2, args.k_split = _p(A2), lda2, k_split
+    args.B2, args.ldb2, args.n_split = _p(B2), ldb2, n_split
     tc_ok = (A.dtype == torch.bfloat16 and N % 8 == 0 and lda % 8 == 0 and ldb % 8 == 0 and ldc % 4 == 0
              and ((not a_trans and b_trans and not accumulate and K % 8 == 0)
                   or (a_trans and not b_trans and accumulate and M % 8 == 0))
@@ -300,11 +321,40 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
     csz = (Cm.numel() * Cm.element_size() if Cm is not None else 0) + (head_out.numel() * 4 if head_out is not None else 0)
     _call("unet_gemm_tc" if use_tc else "unet_gemm_simt", C.byref(args), _stream(),
           tag=f"{'wgrad' if a_trans else ('convt' if epilogue == EPI_CONVT else 'nt')}:{M}x{N}x{K}:e{epilogue}",
-          nbytes=A.numel() * A.element_size() + B.numel() * B.element_size() + csz * (2 if accumulate else 1),
+          nbytes=_nbytes(A, B, A2, B2) + csz * (2 if accumulate else 1),
           flops=2 * M * N * K)
 
 
 # ------------------------------------------------------------------------------------------------ batch normalisation
+def bn_bwd_coef(sums, gamma, beta, save_mean, save_rstd, count: int, dgamma, dbeta, coef=None, w=None, wab=None, bias=None) -> None:
+    """BatchNormalization backward as per-channel coefficients dz = A*g + B*z + K (coef fp32 [3,C]); accumulates dgamma/dbeta;
+    with the pointwise kernel w [Cin,C] also the folded data-gradient operands wab (bf16 [Cin,2C]) and bias [Cin]."""
+    for t, nm in ((sums, "sums"), (gamma, "gamma"), (beta, "beta"), (save_mean, "save_mean"), (save_rstd, "save_rstd"),
+                  (dgamma, "dgamma"), (dbeta, "dbeta"), (coef, "coef"), (w, "w"), (bias, "bias")):
+        _f32(t, nm)
+    c = gamma.numel()
+    cin = 0
+    if w is not None:
+        cin = w.shape[0]
+        if tuple(w.shape) != (cin, c) or wab is None or wab.dtype != torch.bfloat16 or tuple(wab.shape) != (cin, 2 * c) \
+                or not wab.is_contiguous() or bias is None or bias.numel() != cin:
+            raise ValueError("bn_bwd_coef: w [Cin,C] needs wab bf16 [Cin,2C] and bias [Cin]")
+    if sums.numel() != 2 * c or (coef is not None and coef.numel() != 3 * c):
+        raise ValueError("bn_bwd_coef: sums must hold 2*C and coef 3*C floats")
+    _call("unet_bn_bwd_coef", _p(sums), _p(gamma), _p(beta), _p(save_mean), _p(save_rstd), int(count), _p(dgamma), _p(dbeta),
+          _p(coef), _p(w), cin, c, _p(wab), _p(bias), _stream())
+
+
+def bn_bwd_wgrad_combine(G, coef, sd, dw) -> None:
+    """dw[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c]  (G = d^T [g | z] fp32 [Cin,2C])."""
+    for t, nm in ((G, "G"), (coef, "coef"), (sd, "sd"), (dw, "dw")):
+        _f32(t, nm)
+    cin, c = dw.shape
+    if tuple(G.shape) != (cin, 2 * c) or coef.numel() != 3 * c or sd.numel() != cin:
+        raise ValueError("bn_bwd_wgrad_combine: shapes disagree")
+    _call("unet_bn_bwd_wgrad_combine", _p(G), _p(coef), _p(sd), _p(dw), cin, c, _stream())
+
+
 def bn_fold(gamma, beta, mean, var, eps: float, scale, shift) -> None:
     for t, nm in ((gamma, "gamma"), (beta, "beta"), (mean, "mean"), (var, "var"), (scale, "scale"), (shift, "shift")):
         _f32(t, nm)

@@ -200,15 +200,18 @@ int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd
 int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, int H, int W, int C, int dtype, void* stream);
 /* dy_total[n,i,j,c] = dskip[n,i,j,c] (may be NULL) + dpool routed to the first max of each window, where the
    pooled activation is recomputed as relu(z*scale+shift) (scale NULL: the stored tensor is the activation).
-   (H,W) are the un-pooled dims. */
+   (H,W) are the un-pooled dims.  bn_sums (fp32 [2,C], accumulated, may be NULL; needs scale/shift): dy is additionally
+   multiplied by the ReLU mask [y>0] and sum(dy), sum(dy*y) are accumulated (see unet_bn_bwd_coef).
+   skip_drop (rate>0): dskip is first multiplied by the Dropout mask of the concat buffer it is a slice of (u_net.py:96-98). */
 int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scale, const float* shift,
                         const void* dpool, const void* dskip, int64_t lddskip, void* dy,
-                        int N, int H, int W, int C, int dtype, void* stream);
+                        int N, int H, int W, int C, int dtype, float* bn_sums, const unet_dropout* skip_drop, void* stream);
 
 /* ---- Conv2DTranspose backward helper: un-pixel-shuffle dU[N,2H,2W,Cout] (ptr,ld) into G[N*H*W, 4*Cout]
-        (columns (a,b,co)) and accumulate dbias[co] += sum dU ---- */
+        (columns (a,b,co)) and accumulate dbias[co] += sum dU; drop (rate>0): dU is first multiplied by the Dropout mask of
+        the concat buffer it is a slice of ---- */
 int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, float* dbias,
-                          int N, int H, int W, int Cout, int dtype, void* stream);
+                          int N, int H, int W, int Cout, int dtype, const unet_dropout* drop, void* stream);
 
 /* ---- output head: Conv2D(num_classes,1,activation) (u_net.py:105-112) + Dice/IoU sums (utils/metrics.py:29-31) ---- */
 /* probs[M,C] fp32 = sigmoid (C==1) or softmax (C>1) of x[M,K]*w[K,C]+b.  If y_true != NULL also accumulates, per
@@ -220,10 +223,12 @@ int unet_head_fwd(const void* x, int64_t ldx, const float* w, const float* b, fl
    dLoss/dp = ca*t + cb (scaled by grad_scale). */
 int unet_seg_loss_finalize(const double* sums, int NC_pairs, float smooth, int kind, float grad_scale,
                            float* out3, float* coef, void* stream);
-/* backward through activation + 1x1 conv: dx[M,K] (dtype), dw[K,C] +=, db[C] += */
+/* backward through activation + 1x1 conv: dx[M,K] (dtype), dw[K,C] +=, db[C] +=.
+   bn_sums (fp32 [2,K], accumulated, may be NULL): x is the post-ReLU output of dec1_block2, so dx is multiplied by [x>0] and
+   sum(dx), sum(dx*x) are accumulated for the folded BatchNormalization backward (see unet_bn_bwd_coef). */
 int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
                   const float* coef, void* dx, int64_t lddx, float* dw, float* db,
-                  int64_t M, int64_t hw, int K, int C, int dtype, void* stream);
+                  int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums, void* stream);
 /* standalone (I,T,P) sums over [NB,HW,C] fp32 pairs: dice_coef / iou_coef as metrics on arbitrary arrays */
 int unet_seg_sums(const float* y_true, const float* y_pred, double* sums, int64_t NB, int64_t hw, int C, void* stream);
 

@@ -453,6 +453,27 @@ def test_maxpool_fwd_bwd(dtype):
     dy = torch.empty((n, h, w, c), device="cuda", dtype=dtype)
     ops.maxpool2x2_bwd(buf[..., c:2 * c], None, None, dev(dpool, dtype), dev(dskip, dtype), dy)
     np.testing.assert_allclose(host(dy), R.maxpool2x2_bwd(xr, dpr) + dsr, **tol(dtype))
+    # activation recomputed from z, ReLU-masked output and BatchNormalization's backward reductions
+    z = RNG.standard_normal((n, h, w, c)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, c).astype(np.float32); sh = (RNG.standard_normal(c) * 0.3).astype(np.float32)
+    zd = dev(z, dtype)
+    yact = torch.empty_like(zd)
+    ops.bn_act(zd, dev(sc), dev(sh), yact, relu=True)
+    ya = host(yact)
+    plain, masked = torch.empty_like(zd), torch.empty_like(zd)
+    bsum = torch.zeros((2, c), device="cuda")
+    ops.maxpool2x2_bwd(zd, dev(sc), dev(sh), dev(dpool, dtype), dev(dskip, dtype), plain)
+    ops.maxpool2x2_bwd(zd, dev(sc), dev(sh), dev(dpool, dtype), dev(dskip, dtype), masked, bn_sums=bsum)
+    np.testing.assert_allclose(host(plain), R.maxpool2x2_bwd(ya, dpr) + dsr, **tol(dtype))
+    dropped = torch.empty_like(zd)
+    cat = torch.zeros((n, h, w, 2 * c), device="cuda", dtype=dtype); cat[..., c:] = dev(dskip, dtype)
+    ops.maxpool2x2_bwd(zd, dev(sc), dev(sh), dev(dpool, dtype), cat[..., c:], dropped, skip_drop=ops.make_dropout(0.25, 23, ctot=2 * c, c0=c))
+    mult = R.dropout_multiplier((n, h, w, 2 * c), 0.25, 23)[..., c:]
+    np.testing.assert_allclose(host(dropped), R.maxpool2x2_bwd(ya, dpr) + dsr * mult, **tol(dtype))
+    gm = host(masked)
+    np.testing.assert_array_equal(gm, host(plain) * (ya > 0))
+    np.testing.assert_allclose(host(bsum)[0], gm.sum((0, 1, 2)), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(host(bsum)[1], (gm * ya).sum((0, 1, 2)), rtol=1e-4, atol=1e-4)
 
 
 def test_convt_bwd_gather():
@@ -466,6 +487,12 @@ def test_convt_bwd_gather():
     ref = du.reshape(n, h, 2, w, 2, co).transpose(0, 1, 3, 2, 4, 5).reshape(n * h * w, 4 * co)
     np.testing.assert_array_equal(host(g), ref)
     np.testing.assert_allclose(host(db), du.sum((0, 1, 2)), rtol=1e-5, atol=1e-5)
+    # the concat buffer's Dropout mask applied on the way (deferred from the kernel that wrote du)
+    g2 = torch.empty_like(g); db2 = torch.zeros(co, device="cuda")
+    ops.convt_bwd_gather(buf[..., :co], g2, db2, drop=ops.make_dropout(0.25, 19, ctot=2 * co, c0=0))
+    dud = du * R.dropout_multiplier((n, 2 * h, 2 * w, 2 * co), 0.25, 19)[..., :co]
+    np.testing.assert_allclose(host(g2), dud.reshape(n, h, 2, w, 2, co).transpose(0, 1, 3, 2, 4, 5).reshape(n * h * w, 4 * co), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(host(db2), dud.sum((0, 1, 2)), rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ head + loss
@@ -514,6 +541,20 @@ def test_head_and_loss(dtype, C, kind):
     np.testing.assert_allclose(host(db), dl2.sum(0), rtol=2e-3, atol=2e-6)
     ref_dx = (dl2 @ wk.astype(np.float64).T).reshape(n, h, w, k)
     np.testing.assert_allclose(host(dx), ref_dx, rtol=1e-2 if dtype == torch.bfloat16 else 1e-3, atol=1e-7)
+    # ReLU mask of the producing block + BatchNormalization's backward reductions from the same pass (x is then a
+    # post-ReLU activation: x >= 0, which the kernel relies on for sum(g*x))
+    xp = np.maximum(x, 0); xpr = np.maximum(xr, 0)
+    xpd = dev(xp, dtype)
+    dxp, dxm = torch.empty_like(xd), torch.empty_like(xd); bsum = torch.zeros((2, k), device="cuda")
+    dw1, db1 = torch.zeros((k, C), device="cuda"), torch.zeros(C, device="cuda")
+    dw2, db2 = torch.zeros((k, C), device="cuda"), torch.zeros(C, device="cuda")
+    ops.head_bwd(xpd, dev(wk), probs, td, coef, dxp, dw1, db1)
+    ops.head_bwd(xpd, dev(wk), probs, td, coef, dxm, dw2, db2, bn_sums=bsum)
+    gm = host(dxm)
+    np.testing.assert_allclose(gm, host(dxp) * (xpr > 0), rtol=0, atol=0)
+    np.testing.assert_allclose(host(dw2), host(dw1), rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(host(bsum)[0], gm.sum((0, 1, 2)), rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-5)
+    np.testing.assert_allclose(host(bsum)[1], (gm * xpr).sum((0, 1, 2)), rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-5)
 
 
 def test_seg_sums_metrics():

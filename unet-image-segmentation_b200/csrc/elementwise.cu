@@ -333,11 +333,20 @@ maxpool_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int 
   store8(y + ((n * H2 + i2) * (int64_t)W2 + j2) * C + c0, m);
 }
 
-template <typename T>
+template <typename T, bool SUMS, bool DROP>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict__ scale, const float* __restrict__ shift,
                    const T* __restrict__ dpool, const T* __restrict__ dskip, int64_t lddskip, T* __restrict__ dy,
-                   int N, int H, int W, int C) {
+                   int N, int H, int W, int C, float* __restrict__ bn_sums, DropArgs drp) {
+  extern __shared__ float s_bn[];      // [2][C] when bn_sums
+  const uint32_t seed = DROP ? drop_seed(drp) : 0u;
+  if (SUMS) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_bn[i] = 0.f;
+    __syncthreads();
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   const int cv = C >> 3, W2 = W >> 1, H2 = H >> 1;
   const int slots = blockDim.x / cv;
   const int c0 = (threadIdx.x % cv) << 3;
@@ -356,7 +365,10 @@ maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict
     for (int q = 0; q < 4; ++q) {                       // nine 16-byte loads in flight
       const int64_t pix = pix0 + (q >> 1) * W + (q & 1);
       load8(z + pix * ldz + c0, v[q]);
-      if (dskip) load8(dskip + pix * lddskip + c0, o[q]);
+      if (dskip) {
+        load8(dskip + pix * lddskip + c0, o[q]);
+        if (DROP) dropout_apply(o[q], (uint64_t)pix * drp.ctot + drp.c0 + c0, seed, drp.keep, drp.inv_keep);   // skip tensor was stored dropped-out
+      }
     }
     load8(dpool + wi * C + c0, dp);
 #pragma unroll
@@ -369,9 +381,22 @@ maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict
       for (int q = 1; q < 4; ++q) if (a[q] > m) { m = a[q]; arg = q; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) o[q][j] = (dskip ? o[q][j] : 0.f) + (arg == q ? dp[j] : 0.f);
+      if (SUMS) {                     // gradient w.r.t. the BatchNormalization output + its two backward reductions
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float g = a[q] > 0.f ? round_to<T>(o[q][j]) : 0.f;
+          o[q][j] = g; s1[j] += g; s2[j] = fmaf(g, a[q], s2[j]);
+        }
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) store8(dy + (pix0 + (q >> 1) * W + (q & 1)) * C + c0, o[q]);
+  }
+  if (SUMS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { atomicAdd(&s_bn[c0 + j], s1[j]); atomicAdd(&s_bn[C + c0 + j], s2[j]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&bn_sums[i], s_bn[i]);
   }
 }
 
@@ -379,8 +404,9 @@ maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256)
 convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ g, float* __restrict__ dbias,
-                        int N, int H, int W, int Cout) {
+                        int N, int H, int W, int Cout, DropArgs dp) {
   extern __shared__ float s_red[];   // [Cout]
+  const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   const int cv = Cout >> 3;
@@ -397,6 +423,7 @@ convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ 
     const int64_t src = (n * (2 * H) + 2 * i + (ab >> 1)) * (int64_t)(2 * W) + 2 * j + (ab & 1);
     float v[8];
     load8(du + src * lddu + c0, v);
+    if (dp.on) dropout_apply(v, (uint64_t)src * dp.ctot + dp.c0 + c0, seed, dp.keep, dp.inv_keep);   // the upsampled half was stored dropped-out
     store8(g + (m * 4 + ab) * (int64_t)Cout + c0, v);
 #pragma unroll
     for (int jj = 0; jj < 8; ++jj) sb[jj] += v[jj];
@@ -676,7 +703,8 @@ extern "C" int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, i
 
 extern "C" int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scale, const float* shift,
                                    const void* dpool, const void* dskip, int64_t lddskip, void* dy,
-                                   int N, int H, int W, int C, int dtype, void* stream) {
+                                   int N, int H, int W, int C, int dtype, float* bn_sums, const unet_dropout* skip_drop, void* stream) {
+  const DropArgs dp = make_drop(skip_drop);
   UNET_REQUIRE(z && dpool && dy && N > 0 && H > 1 && W > 1 && C > 0 && ldz >= C, UNET_EINVAL, "maxpool2x2_bwd: bad argument");
   UNET_REQUIRE(H % 2 == 0 && W % 2 == 0, UNET_EINVAL, "maxpool2x2_bwd: needs even H,W");
   UNET_REQUIRE(C % 8 == 0 && ldz % 8 == 0 && (!dskip || lddskip % 8 == 0), UNET_EALIGN, "maxpool2x2_bwd: needs C%%8==0, ld%%8==0");
@@ -684,20 +712,24 @@ extern "C" int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scal
   UNET_REQUIRE(256 % (C / 8) == 0, UNET_EUNSUPPORTED, "maxpool2x2_bwd: C/8 must divide 256 (C=%d)", C);
   const int64_t items = (int64_t)N * (H / 2) * (W / 2);
   const unsigned grid = (unsigned)i64min(ceil_div(items, 256 / (C / 8)), (int64_t)sm_count() * 16);
-  if (dtype == UNET_F32)
-    maxpool_bwd_kernel<float><<<grid, 256, 0, ST>>>((const float*)z, ldz, scale, shift, (const float*)dpool,
-                                                   (const float*)dskip, lddskip, (float*)dy, N, H, W, C);
-  else if (dtype == UNET_BF16)
-    maxpool_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)z, ldz, scale, shift,
-                                                           (const __nv_bfloat16*)dpool, (const __nv_bfloat16*)dskip,
-                                                           lddskip, (__nv_bfloat16*)dy, N, H, W, C);
+  UNET_REQUIRE(!bn_sums || scale, UNET_EINVAL, "maxpool2x2_bwd: bn_sums needs the activation recomputed from z (scale/shift)");
+  const size_t smem = bn_sums ? (size_t)2 * C * sizeof(float) : 0;
+#define UNET_MPB(T, S_, D_) maxpool_bwd_kernel<T, S_, D_><<<grid, 256, smem, ST>>>((const T*)z, ldz, scale, shift, (const T*)dpool, \
+                                                                          (const T*)dskip, lddskip, (T*)dy, N, H, W, C, bn_sums, dp)
+#define UNET_MPB4(T) do { if (bn_sums) { if (dp.on) UNET_MPB(T, true, true); else UNET_MPB(T, true, false); } \
+                          else { if (dp.on) UNET_MPB(T, false, true); else UNET_MPB(T, false, false); } } while (0)
+  if (dtype == UNET_F32) UNET_MPB4(float);
+  else if (dtype == UNET_BF16) UNET_MPB4(__nv_bfloat16);
   else return set_error(UNET_EINVAL, "maxpool2x2_bwd: bad dtype %d", dtype);
+#undef UNET_MPB4
+#undef UNET_MPB
   UNET_LAUNCH_CHECK("maxpool2x2_bwd");
   return UNET_OK;
 }
 
 extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, float* dbias,
-                                     int N, int H, int W, int Cout, int dtype, void* stream) {
+                                     int N, int H, int W, int Cout, int dtype, const unet_dropout* drop, void* stream) {
+  const DropArgs dp = make_drop(drop);
   UNET_REQUIRE(du && g && N > 0 && H > 0 && W > 0 && Cout > 0 && lddu >= Cout, UNET_EINVAL, "convt_bwd_gather: bad argument");
   UNET_REQUIRE(Cout % 8 == 0 && lddu % 8 == 0 && aligned16(du) && aligned16(g), UNET_EALIGN, "convt_bwd_gather: needs Cout%%8==0");
   UNET_REQUIRE(256 % (Cout / 8) == 0, UNET_EUNSUPPORTED, "convt_bwd_gather: Cout/8 must divide 256");
@@ -706,9 +738,9 @@ extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, floa
   const unsigned grid = (unsigned)i64min(ceil_div(items, per_block), (int64_t)sm_count() * 8);
   const size_t smem = (size_t)Cout * sizeof(float);
   if (dtype == UNET_F32)
-    convt_bwd_gather_kernel<float><<<grid, 256, smem, ST>>>((const float*)du, lddu, (float*)g, dbias, N, H, W, Cout);
+    convt_bwd_gather_kernel<float><<<grid, 256, smem, ST>>>((const float*)du, lddu, (float*)g, dbias, N, H, W, Cout, dp);
   else if (dtype == UNET_BF16)
-    convt_bwd_gather_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)du, lddu, (__nv_bfloat16*)g, dbias, N, H, W, Cout);
+    convt_bwd_gather_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)du, lddu, (__nv_bfloat16*)g, dbias, N, H, W, Cout, dp);
   else return set_error(UNET_EINVAL, "convt_bwd_gather: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("convt_bwd_gather");
   return UNET_OK;

@@ -115,14 +115,17 @@ head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   }
 }
 
-template <typename T, int MAXC>
+template <typename T, int MAXC, bool SUMS>
 __global__ void __launch_bounds__(256, MAXC == 1 ? 3 : 1)
 head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ probs,
                 const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
-                float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block) {
+                float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block,
+                float* __restrict__ bn_sums) {
   __shared__ float s_w[kHeadMaxK * MAXC];
   __shared__ float s_dw[kHeadMaxK * MAXC];
   __shared__ float s_db[MAXC];
+  __shared__ float s_bn[SUMS ? 2 * kHeadMaxK : 1];
+  if (SUMS) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) s_bn[i] = 0.f;
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) s_w[(i / C) * MAXC + (i % C)] = w[i];
   for (int i = threadIdx.x; i < K * MAXC; i += blockDim.x) s_dw[i] = 0.f;
   if (threadIdx.x < MAXC) s_db[threadIdx.x] = 0.f;
@@ -156,6 +159,10 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) wk[j][c] = s_w[(k0 + j) * MAXC + c];
+    // SUMS: sum(g) needs its own accumulators; sum(g*x) = sum_c w[k,c] * dw[k,c] because x >= 0 is its own ReLU mask
+    float s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = 0.f;
     for (int64_t p0 = p_begin; p0 < p_end; p0 += 32 * U) {
       float v[U][8], dz[U][MAXC];
       int64_t mrow[U];
@@ -198,6 +205,13 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
           }
           o[j] = sacc;
         }
+        if (SUMS && live[u]) {       // x is the post-ReLU activation: mask, and BatchNormalization's two backward reductions
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g = v[u][j] > 0.f ? o[j] : 0.f;
+            o[j] = g; s1[j] += g;
+          }
+        }
         if (dx && live[u]) store8(dx + mrow[u] * lddx + k0, o);
         if (k0 == sub * 8 && sub == 0) {
 #pragma unroll
@@ -215,6 +229,17 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
         s += __shfl_xor_sync(0xffffffffu, s, 16);
         if ((threadIdx.x & 31) < 8 && c < C) atomicAdd(&s_dw[(k0 + j) * MAXC + c], s);
       }
+    if (SUMS) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = s1[j], b = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) b = fmaf(wk[j][c], dwacc[j][c], b);
+        a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+        b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+        if ((threadIdx.x & 31) < 8) { atomicAdd(&s_bn[k0 + j], a); atomicAdd(&s_bn[K + k0 + j], b); }
+      }
+    }
   }
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
@@ -224,6 +249,7 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   __syncthreads();
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(&dw[i], s_dw[(i / C) * MAXC + (i % C)]);
   if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
+  if (SUMS) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) atomicAdd(&bn_sums[i], s_bn[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ multi-class head (2 <= C <= 8)
@@ -336,10 +362,13 @@ template <typename T>
 __global__ void __launch_bounds__(256, 2)
 head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ probs,
                    const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
-                   float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block) {
+                   float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block,
+                   float* __restrict__ bn_sums) {
   __shared__ __align__(16) float s_w[kMcWeightFloats];
   __shared__ float s_dw[kHeadMaxK * 8];
   __shared__ float s_db[8];
+  __shared__ float s_bn[2 * kHeadMaxK];
+  if (bn_sums) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) s_bn[i] = 0.f;
   for (int i = threadIdx.x; i < K * 8; i += blockDim.x) { s_w[mc_row(i >> 3) + (i & 7)] = (i & 7) < C ? w[(i >> 3) * C + (i & 7)] : 0.f; s_dw[i] = 0.f; }
   if (threadIdx.x < 8) s_db[threadIdx.x] = 0.f;
   __syncthreads();
@@ -355,6 +384,9 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int c = 0; c < 8; ++c) dwacc[j][c] = 0.f;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
     for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
       const int64_t p = p0 + slot;
       const bool live = p < p_end;
@@ -381,8 +413,24 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
         for (int c = 0; c < 8; ++c) { sacc = fmaf(dz[c], wk[c], sacc); dwacc[j][c] = fmaf(v[j], dz[c], dwacc[j][c]); }
         o[j] = sacc;
       }
+      if (bn_sums && live) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gm = v[j] > 0.f ? round_to<T>(o[j]) : 0.f;
+          o[j] = gm; s1[j] += gm; s2[j] = fmaf(gm, v[j], s2[j]);
+        }
+      }
       if (dx && live) store8(dx + m * lddx + k0, o);
       if (k0 == sub * 8) dbs += dz_own;
+    }
+    if (bn_sums) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = s1[j], b = s2[j];
+        a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+        b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16);
+        if (lane < 8) { atomicAdd(&s_bn[k0 + j], a); atomicAdd(&s_bn[K + k0 + j], b); }
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -399,6 +447,7 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
   __syncthreads();
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(&dw[i], s_dw[(i / C) * 8 + (i % C)]);
   if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
+  if (bn_sums) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) atomicAdd(&bn_sums[i], s_bn[i]);
 }
 
 static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block, int waves = 16) {
@@ -439,18 +488,20 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
 
 extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
                              const float* coef, void* dx, int64_t lddx, float* dw, float* db,
-                             int64_t M, int64_t hw, int K, int C, int dtype, void* stream) {
+                             int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums, void* stream) {
   UNET_REQUIRE(x && w && probs && y_true && coef && dw && db, UNET_EINVAL, "head_bwd: null pointer");
   UNET_REQUIRE(M > 0 && hw > 0 && K > 0 && C > 0 && ldx >= K && M % hw == 0, UNET_EINVAL, "head_bwd: bad dims");
   UNET_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && aligned16(x) && (!dx || (lddx % 8 == 0 && aligned16(dx))), UNET_EALIGN,
                "head_bwd: needs K%%8==0, ld%%8==0, 16B pointers");
   UNET_REQUIRE(K <= kHeadMaxK && C <= 8, UNET_EUNSUPPORTED, "head_bwd: K <= %d and num_classes <= 8", kHeadMaxK);
   UNET_REQUIRE(M / hw <= 65535, UNET_EUNSUPPORTED, "head_bwd: batch <= 65535");
+  UNET_REQUIRE(!bn_sums || dx, UNET_EINVAL, "head_bwd: bn_sums needs dx");
   dim3 grid; int ppb;
   head_grid(M / hw, hw, &grid, &ppb, 8);
   cudaStream_t st = (cudaStream_t)stream;
-#define LAUNCH(T, MC) head_bwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
-#define LAUNCH_MC(T) head_bwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb)
+#define LAUNCH(T, MC) do { if (bn_sums) head_bwd_kernel<T, MC, true><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); \
+                           else head_bwd_kernel<T, MC, false><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); } while (0)
+#define LAUNCH_MC(T) head_bwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums)
   if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }
   else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH_MC(__nv_bfloat16); }
 #undef LAUNCH_MC

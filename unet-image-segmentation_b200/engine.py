@@ -84,11 +84,11 @@ class UNetEngine:
             # lr, wd, beta1, beta2, eps, t, grad_scale, unused
             self.hyper = torch.tensor([2e-3, 1e-4, 0.9, 0.999, 1e-7, 1.0, 1.0, 0.0], device=dev)
             self.step_word = torch.zeros(1, device=dev, dtype=torch.int32)
-            # folded BN backward (per *_block1): sums [2,Cout] | sd [Cin] | G [Cin,2Cout] live in ONE fp32 buffer zeroed per step
+            # folded BN backward (per block): sums [2,Cout] | sd [Cin] | G [Cin,2Cout] live in ONE fp32 buffer zeroed per step
             self._fz_off: Dict[str, Tuple[int, int, int]] = {}
             tot = 0
             for b in sp.blocks:
-                if b.prefix.endswith("_block1"):
+                if b.prefix.endswith("_block1") or b.prefix.startswith("enc") or b.prefix == "dec1_block2":
                     self._fz_off[b.prefix] = (tot, b.cin, b.cout)
                     tot += 2 * b.cout + b.cin + 2 * b.cin * b.cout
                     tot = (tot + 63) // 64 * 64
@@ -103,8 +103,11 @@ class UNetEngine:
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
-        self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward of every *_block1 folded into its
-                                                # pointwise data / weight gradient GEMMs (no reduce / apply passes, no dz tensor)
+        self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward folded into the block's pointwise
+                                                # data / weight gradient GEMMs (no reduce / apply passes, no dz tensor) wherever the
+                                                # producer of dy has the block's activation in registers: every *_block1 (depthwise
+                                                # backward of *_block2), enc*_block2 (max-pool backward), dec1_block2 (head backward)
+        self.defer_dropout = True               # training: the concat-buffer Dropout mask of dcat is applied by its readers
         self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
@@ -532,8 +535,9 @@ class UNetEngine:
         n_scr = B * H * W * 128
         S = [pl.buf(f"scr{i}", (n_scr,)) for i in range(3)]
         dy = S[0][: B * H * W * 64].view(B, H, W, 64)
+        fold_d1 = self._folds("dec1_block2")
         ops.head_bwd(cur, wk, probs, y_true, coef, dy, self._mat("output_mask/kernel", self.g),
-                     self.wview("output_mask/bias", self.g))
+                     self.wview("output_mask/bias", self.g), bn_sums=self._fold_bufs("dec1_block2")[0] if fold_d1 else None)
         ci = 0   # index of the scratch buffer that currently holds dy
         dcat = {}
         for s in (1, 2, 3, 4):
@@ -545,16 +549,20 @@ class UNetEngine:
             dx = S[ci][: M * f].view(B, h, w, f)
             fold = self._folds(f"dec{s}_block1")
             self._block_train_bwd(pl, f"dec{s}_block2", xin[f"dec{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                                  mask_for=f"dec{s}_block1" if fold else None)
+                                  mask_for=f"dec{s}_block1" if fold else None, folded=(s == 1 and fold_d1))
             # dec{s}_block1: input is the (dropped-out) concat buffer
             dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
+            # the Dropout mask of the concat buffer is applied by the two readers of dcat (memory-bound kernels with ALU to
+            # spare), not by the depthwise backward kernel that writes it
+            defer = self.defer_dropout and s > 1
             self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
-                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None, folded=fold)
+                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if (s > 1 and not defer) else None, folded=fold)
             # Conv2DTranspose backward
             xi = convt_in[s]
             Mi = xi.shape[0] * xi.shape[1] * xi.shape[2]
             gth = S[o1][: Mi * 4 * f].view(Mi, 4 * f)
-            ops.convt_bwd_gather(dcat[s][..., :f], gth, self.wview(f"dec{s}_upsample/bias", self.g))
+            ops.convt_bwd_gather(dcat[s][..., :f], gth, self.wview(f"dec{s}_upsample/bias", self.g),
+                                 drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
             ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True)
             dy = S[ci][: Mi * 2 * f].view(xi.shape)
             self._convt_dgrad(s, gth, dy)
@@ -583,12 +591,15 @@ class UNetEngine:
             else:
                 scale, shift = self.ones[:f], self.zeros[:f]
             dy = S[o1][: M * f].view(B, h, w, f)
-            ops.maxpool2x2_bwd(pl.t[f"enc{s}_block2/z"], scale, shift, dpool, dcat[s][..., f:], dy)
+            fold2 = self._folds(f"enc{s}_block2")
+            ops.maxpool2x2_bwd(pl.t[f"enc{s}_block2/z"], scale, shift, dpool, dcat[s][..., f:], dy,
+                               bn_sums=self._fold_bufs(f"enc{s}_block2")[0] if fold2 else None,
+                               skip_drop=self._drop(f"dec{s}_dropout", 2 * f, f) if (self.defer_dropout and s > 1) else None)
             ci, o1 = o1, ci        # dy now lives in the old o1; the old ci is free
             dx = S[ci][: M * f].view(B, h, w, f)
             fold = self._folds(f"enc{s}_block1")
             self._block_train_bwd(pl, f"enc{s}_block2", xin[f"enc{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                                  mask_for=f"enc{s}_block1" if fold else None)
+                                  mask_for=f"enc{s}_block1" if fold else None, folded=fold2)
             x1 = xin[f"enc{s}_block1"]
             cin = x1.shape[-1]
             dpool = S[ci][: M * cin].view(B, h, w, cin) if s > 1 else None

@@ -416,23 +416,26 @@ def maxpool2x2(x: torch.Tensor, y: torch.Tensor) -> None:
 
 
 def maxpool2x2_bwd(z: torch.Tensor, scale, shift, dpool: torch.Tensor, dskip: Optional[torch.Tensor],
-                   dy: torch.Tensor) -> None:
+                   dy: torch.Tensor, bn_sums: Optional[torch.Tensor] = None, skip_drop: Optional[Dropout] = None) -> None:
     n, h, w, c, ldz = _nhwc(z, "z")
     lds = 0
     if dskip is not None:
         lds = _nhwc(dskip, "dskip")[4]
     if not dpool.is_contiguous() or not dy.is_contiguous():
         raise ValueError("maxpool2x2_bwd: dpool and dy must be contiguous")
+    _f32(bn_sums, "bn_sums")
+    if bn_sums is not None and bn_sums.numel() != 2 * c:
+        raise ValueError("maxpool2x2_bwd: bn_sums must hold 2*C floats")
     _call("unet_maxpool2x2_bwd", _p(z), ldz, _p(scale), _p(shift), _p(dpool), _p(dskip), lds, _p(dy), n, h, w, c,
-          _dt(z), _stream(), tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(z, dpool, dskip, dy))
+          _dt(z), _p(bn_sums), _dref(skip_drop), _stream(), tag=f"{n}x{h}x{w}x{c}", nbytes=_nbytes(z, dpool, dskip, dy))
 
 
-def convt_bwd_gather(du: torch.Tensor, g: torch.Tensor, dbias: Optional[torch.Tensor]) -> None:
+def convt_bwd_gather(du: torch.Tensor, g: torch.Tensor, dbias: Optional[torch.Tensor], drop: Optional[Dropout] = None) -> None:
     """du: (N,2H,2W,Cout) view -> g: [N*H*W, 4*Cout]; dbias += column sums."""
     n, h2, w2, co, lddu = _nhwc(du, "du")
     if not g.is_contiguous() or g.numel() != du.shape[0] * h2 * w2 * co:
         raise ValueError("convt_bwd_gather: g has the wrong size")
-    _call("unet_convt_bwd_gather", _p(du), lddu, _p(g), _p(dbias), n, h2 // 2, w2 // 2, co, _dt(du), _stream(),
+    _call("unet_convt_bwd_gather", _p(du), lddu, _p(g), _p(dbias), n, h2 // 2, w2 // 2, co, _dt(du), _dref(drop), _stream(),
           tag=f"{n}x{h2}x{w2}x{co}", nbytes=_nbytes(du, g))
 
 
@@ -455,14 +458,17 @@ def seg_loss_finalize(sums: torch.Tensor, npairs: int, smooth: float, kind: int,
           _p(coef), _stream())
 
 
-def head_bwd(x, w, probs, y_true, coef, dx: Optional[torch.Tensor], dw, db) -> None:
+def head_bwd(x, w, probs, y_true, coef, dx: Optional[torch.Tensor], dw, db, bn_sums: Optional[torch.Tensor] = None) -> None:
     n, h, wd, k, ldx = _nhwc(x, "x")
     c = probs.shape[-1]
     lddx = _nhwc(dx, "dx")[4] if dx is not None else 0
     for t, nm in ((w, "w"), (probs, "probs"), (y_true, "y_true"), (coef, "coef"), (dw, "dw"), (db, "db")):
         _f32(t, nm)
+    _f32(bn_sums, "bn_sums")
+    if bn_sums is not None and bn_sums.numel() != 2 * k:
+        raise ValueError("head_bwd: bn_sums must hold 2*K floats")
     _call("unet_head_bwd", _p(x), ldx, _p(w), _p(probs), _p(y_true), _p(coef), _p(dx), lddx, _p(dw), _p(db),
-          n * h * wd, h * wd, k, c, _dt(x), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}",
+          n * h * wd, h * wd, k, c, _dt(x), _p(bn_sums), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}",
           nbytes=_nbytes(x, probs, y_true, dx), flops=4 * x.numel() * c)
 
 

@@ -120,10 +120,12 @@ int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_
    relu_mask=1: x is the post-ReLU output y of the producing conv_block (u_net.py:22-25), so (x > 0) is its ReLU mask and
    the stored dx becomes dL/d(BN output) of that block; bn_sums (fp32 [2,C], accumulated, may be NULL) then receives
    sum(dx) and sum(dx * y) over (n,i,j) — the two reductions BatchNormalization backward needs — from the stored values.
+   drop (rate>0) multiplies dx by the Dropout mask for channels >= drop_c_from (a multiple of the 128-byte channel block;
+   the channels below are left to another reader of dx, e.g. unet_convt_bwd_gather).
    UNET_EUNSUPPORTED unless C % (8/sizeof(T)) == 0, C >= 8 and all views are 16-byte aligned. */
 int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                        void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
-                       int relu_mask, float* bn_sums, const unet_dropout* drop, void* stream);
+                       int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from, void* stream);
 
 /* ---- first conv_block, fused (enc1_block1_sepconv on the RGB image, u_net.py:14-20,63-66; Cin = 3, Cout = 64 only) ---- */
 /* out = pw(dw(x)) [* scale + shift, ReLU if relu]; x contiguous [N,H,W,3]; with colsum/colsq also the BN batch statistics

@@ -127,6 +127,22 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
         np.testing.assert_allclose(host(sums)[1], (g * xr).sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dwconv_bwd_fused_partial_dropout(dtype):
+    """the Dropout mask is applied to channels >= drop_c_from only (the other half is masked by the reader of dx)"""
+    n, h, w, c = 2, 9, 30, 128
+    x = RNG.standard_normal((n, h, w, c)).astype(np.float32); dy = RNG.standard_normal((n, h, w, c)).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    xr, dyr = (bf16_round(x), bf16_round(dy)) if dtype == torch.bfloat16 else (x.astype(np.float64), dy.astype(np.float64))
+    dx_ref, _ = R.dwconv3x3_bwd(xr, wk.astype(np.float64), dyr)
+    mult = R.dropout_multiplier((n, h, w, c), 0.25, 91)
+    mult[..., :64] = 1.0
+    dx = torch.empty((n, h, w, c), device="cuda", dtype=dtype); dw = torch.zeros((9, c), device="cuda")
+    ops.dwconv3x3_bwd(dev(x, dtype), dev(dy, dtype), dev(wk.reshape(9, -1)), dx, dw,
+                      drop=ops.make_dropout(0.25, 91, ctot=c, c0=0), drop_c_from=64)
+    np.testing.assert_allclose(host(dx), dx_ref * mult, **tol(dtype))
+
+
 def test_dwconv_fwd_colsum():
     for dtype in DTYPES:
         shape = (2, 37, 45, 72)

@@ -667,7 +667,8 @@ template <typename T, bool DROP, bool RELU_MASK>
 __global__ void __launch_bounds__(BwCfg<T>::kThreads, 1)
 dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
                            const float* __restrict__ w9c, T* __restrict__ dx, int64_t lddx, float* __restrict__ dw9c,
-                           float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp) {
+                           float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp,
+                           int drop_c_from) {
   using Cfg = BwCfg<T>;
   constexpr int NV = Cfg::NV, NP = NV / 2, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
@@ -772,7 +773,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
           if (RELU_MASK) { v.x = xm[j].x > 0.f ? v.x : 0.f; v.y = xm[j].y > 0.f ? v.y : 0.f; }   // xm = x[t-1] = y of the producer
           o[2 * j] = v.x; o[2 * j + 1] = v.y;
         }
-        if (DROP) {
+        if (DROP && c0 >= drop_c_from) {          // CTA-uniform: a 128-byte channel block lies on one side of drop_c_from
           const uint64_t base = (uint64_t)(((int64_t)n * H + (t - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
           dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
         }
@@ -842,7 +843,8 @@ template <typename T> static bool dw_strip_ok(const void* a, int64_t lda, const 
 
 template <typename T>
 static int dw_bwd_strip_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c, void* dx, int64_t lddx,
-                               float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, cudaStream_t st) {
+                               float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, int drop_c_from,
+                               cudaStream_t st) {
   using Cfg = BwCfg<T>;
   CUtensorMap tmD, tmX;
   if (int e = make_nhwc_tmap<T>(&tmD, dy, lddy, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_bwd(dy)")) return e;
@@ -859,7 +861,7 @@ static int dw_bwd_strip_launch(const void* x, int64_t ldx, const void* dy, int64
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd: too many strips");
 #define UNET_BW_LAUNCH(D, M) dwconv3x3_bwd_strip_kernel<T, D, M><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
-      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp)
+      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from)
   if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true); else UNET_BW_LAUNCH(true, false); }
   else       { if (relu_mask) UNET_BW_LAUNCH(false, true); else UNET_BW_LAUNCH(false, false); }
 #undef UNET_BW_LAUNCH
@@ -1002,8 +1004,10 @@ extern "C" int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void*
 
 extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                                   void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
-                                  int relu_mask, float* bn_sums, const unet_dropout* drop, void* stream) {
+                                  int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from, void* stream) {
   UNET_REQUIRE(x && dy && w9c && dx && dw9c, UNET_EINVAL, "dwconv3x3_bwd: null pointer");
+  UNET_REQUIRE(drop_c_from >= 0 && drop_c_from % (128 / (dtype == UNET_F32 ? 4 : 2)) == 0, UNET_EINVAL,
+               "dwconv3x3_bwd: drop_c_from must be a multiple of the 128-byte channel block");
   UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, UNET_EINVAL, "dwconv3x3_bwd: bad dims %d %d %d %d", N, H, W, C);
   UNET_REQUIRE(ldx >= C && lddy >= C && lddx >= C, UNET_EINVAL, "dwconv3x3_bwd: ld < C");
   UNET_REQUIRE(!bn_sums || relu_mask, UNET_EINVAL, "dwconv3x3_bwd: bn_sums needs relu_mask");
@@ -1012,12 +1016,12 @@ extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, in
   if (dtype == UNET_F32) {
     UNET_REQUIRE(dw_strip_ok<float>(x, ldx, dy, lddy, C) && dw_strip_ok<float>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%2==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, st);
+    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, st);
   }
   if (dtype == UNET_BF16) {
     UNET_REQUIRE(dw_strip_ok<__nv_bfloat16>(x, ldx, dy, lddy, C) && dw_strip_ok<__nv_bfloat16>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%4==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, st);
+    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, st);
   }
   return set_error(UNET_EINVAL, "dwconv3x3_bwd: bad dtype %d", dtype);
 }

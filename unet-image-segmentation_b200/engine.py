@@ -416,7 +416,8 @@ class UNetEngine:
         ops.bn_act(z, scale, shift, y, relu=True, pooled=pooled, drop=drop)
         return y
 
-    def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None, mask_for=None, folded=False):
+    def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None, mask_for=None, folded=False,
+                         dx_drop_from=0):
         """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out.
         mask_for: prefix of the block that produced x (= its post-ReLU output): dx_out then is the ReLU-masked gradient
         w.r.t. that block's BatchNormalization output and its two BN-backward reductions are accumulated on the way.
@@ -463,7 +464,7 @@ class UNetEngine:
         wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
             # both gradients from one pass over dd (+ the producer's ReLU mask and BN-backward reductions)
-            ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop, relu_mask=mask_for is not None,
+            ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop, drop_c_from=dx_drop_from, relu_mask=mask_for is not None,
                               bn_sums=self._fold_bufs(mask_for)[0] if mask_for is not None else None)
             return dx_out
         if mask_for is not None:
@@ -552,11 +553,12 @@ class UNetEngine:
                                   mask_for=f"dec{s}_block1" if fold else None, folded=(s == 1 and fold_d1))
             # dec{s}_block1: input is the (dropped-out) concat buffer
             dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
-            # the Dropout mask of the concat buffer is applied by the two readers of dcat (memory-bound kernels with ALU to
-            # spare), not by the depthwise backward kernel that writes it
-            defer = self.defer_dropout and s > 1
+            # the Dropout mask of the upsampled half of the concat gradient is applied by its reader (the un-pixel-shuffle
+            # gather, a memory-bound kernel with ALU to spare); the depthwise backward kernel masks only the skip half
+            defer = self.defer_dropout and s > 1 and f % 64 == 0
             self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
-                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if (s > 1 and not defer) else None, folded=fold)
+                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None,
+                                  dx_drop_from=f if defer else 0, folded=fold)
             # Conv2DTranspose backward
             xi = convt_in[s]
             Mi = xi.shape[0] * xi.shape[1] * xi.shape[2]
@@ -593,8 +595,7 @@ class UNetEngine:
             dy = S[o1][: M * f].view(B, h, w, f)
             fold2 = self._folds(f"enc{s}_block2")
             ops.maxpool2x2_bwd(pl.t[f"enc{s}_block2/z"], scale, shift, dpool, dcat[s][..., f:], dy,
-                               bn_sums=self._fold_bufs(f"enc{s}_block2")[0] if fold2 else None,
-                               skip_drop=self._drop(f"dec{s}_dropout", 2 * f, f) if (self.defer_dropout and s > 1) else None)
+                               bn_sums=self._fold_bufs(f"enc{s}_block2")[0] if fold2 else None)
             ci, o1 = o1, ci        # dy now lives in the old o1; the old ci is free
             dx = S[ci][: M * f].view(B, h, w, f)
             fold = self._folds(f"enc{s}_block1")

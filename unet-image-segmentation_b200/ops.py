@@ -158,7 +158,8 @@ def dwconv3x3_bwd_supported(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor)
 
 
 def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torch.Tensor, dw9c: torch.Tensor,
-                  relu_mask: bool = False, bn_sums: Optional[torch.Tensor] = None, drop: Optional[Dropout] = None) -> None:
+                  relu_mask: bool = False, bn_sums: Optional[torch.Tensor] = None, drop: Optional[Dropout] = None,
+                  drop_c_from: int = 0) -> None:
     """SeparableConv2D depthwise backward in one pass over dy: input gradient (optionally ReLU-masked by x > 0, with the
     BatchNormalization-backward reductions sum(g), sum(g*x) accumulated into bn_sums [2,C]) + weight gradient."""
     n, h, w, c, ldx = _nhwc(x, "x")
@@ -170,8 +171,8 @@ def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torc
     if w9c.numel() != 9 * c or dw9c.numel() != 9 * c or (bn_sums is not None and bn_sums.numel() != 2 * c):
         raise ValueError("dwconv3x3_bwd: w9c / dw9c must hold 9*C floats and bn_sums 2*C")
     _call("unet_dwconv3x3_bwd", _p(x), ldx, _p(dy), lddy, _p(w9c), _p(dx), lddx, _p(dw9c), n, h, w, c, _dt(x),
-          int(relu_mask), _p(bn_sums), _dref(drop), _stream(),
-          tag=f"{n}x{h}x{w}x{c}" + ("+mask" if relu_mask else ""), nbytes=_nbytes(x, dy, dx, w9c), flops=36 * x.numel())
+          int(relu_mask), _p(bn_sums), _dref(drop), int(drop_c_from), _stream(),
+          tag=f"{n}x{h}x{w}x{c}" + ("+mask" if relu_mask else "") + ("+drop" if drop is not None else ""), nbytes=_nbytes(x, dy, dx, w9c), flops=36 * x.numel())
 
 
 # ------------------------------------------------------------------------------------------------ fused first block

@@ -89,6 +89,19 @@ __device__ __forceinline__ uint2 lds64(uint32_t saddr) {
   asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(saddr));
   return r;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
+  return r;
+}
 // Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2): two IEEE round-to-nearest FMAs per issued instruction, bit-identical
 // to two scalar fmaf() calls.  The depthwise kernels are issue-bound on the FMA pipe without it.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {

@@ -325,6 +325,9 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int j = 0; j < CPL; ++j) { st_sum[c][j] = 0.f; st_sq[c][j] = 0.f; }
     const uint32_t sw = (uint32_t)(row & 7);
     int last_n_blk = -1, chunk_ctr = 0;
+    uint32_t stat_off[8];                          // statistics: byte offset of this lane's word inside a staged row r (r & 7 = i)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) stat_off[i] = ((((uint32_t)lane >> 2) ^ (uint32_t)i) << 4) + (((uint32_t)lane & 3u) << 2);
 
     auto flush_stats = [&](int n_blk_) {
 #pragma unroll
@@ -372,7 +375,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (n_base >= p.N) break;                 // uniform: ragged last N tile
         if (issuer) bulk_wait_read<1>();          // the store that last used `buf` (two chunks ago) has read it
         named_bar_sync(1 + g, 128);
-        uint8_t* my_row = buf + row * 128;
+        const uint32_t my_row_s = smem_u32(buf) + (uint32_t)row * 128u;
         // Conv2DTranspose destination of this thread's row (dropout indexes the destination element)
         uint64_t drop_base = 0;
         int cv_a = 0, cv_b = 0, co0 = 0;
@@ -395,12 +398,12 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
           if (affine) {
-            const float* ps = par_scale + c * CW + half * 32;
-            const float* ph = par_shift + c * CW + half * 32;
+            const uint32_t ps_s = smem_u32(par_scale + c * CW + half * 32);
+            const uint32_t ph_s = smem_u32(par_shift + c * CW + half * 32);
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {     // warp-uniform addresses: broadcast shared loads
-              const float4 s4 = *reinterpret_cast<const float4*>(ps + i);
-              const float4 h4 = *reinterpret_cast<const float4*>(ph + i);
+              const float4 s4 = lds128f(ps_s + i * 4);
+              const float4 h4 = lds128f(ph_s + i * 4);
               v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
               v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
             }
@@ -415,11 +418,11 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int cls = 0; cls < 8; ++cls) {
               if (cls < ncls) {
-                const float* hw = par_head + cls * 64 + half * 32;
+                const uint32_t hw_s = smem_u32(par_head + cls * 64 + half * 32);
                 float a = hacc[cls];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(hw + i);
+                  const float4 w4 = lds128f(hw_s + i * 4);
                   a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
                   a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
                 }
@@ -433,14 +436,14 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 4; ++j) {         // 4 x 16 B = 32 bf16 columns; chunk index = half*4 + j
               const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-              *reinterpret_cast<uint4*>(my_row + ((((uint32_t)(half * 4 + j)) ^ sw) << 4)) = o;
+              sts128(my_row_s + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), o);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {         // 8 x 16 B = 32 fp32 columns
               const uint4 o = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                          __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-              *reinterpret_cast<uint4*>(my_row + ((((uint32_t)j) ^ sw) << 4)) = o;
+              sts128(my_row_s + ((((uint32_t)j) ^ sw) << 4), o);
             }
           }
         }
@@ -461,23 +464,25 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           bulk_commit();
         }
         if (stats) {
-          // column sums over this warp's 32 rows, from the values as stored; lane owns CPL adjacent columns
-          const uint8_t* wrows = buf + (q * 32) * 128;
-          float s0 = 0.f, q0s = 0.f, s1 = 0.f, q1s = 0.f;
-#pragma unroll 8
+          // column sums over this warp's 32 rows, from the values as stored; lane owns CPL adjacent columns.  Rows past M
+          // are exact zeros (TMA zero-fills the A operand), so no bounds check; shared addresses carry the 128B-swizzle XOR
+          // of the row in 8 precomputed lane offsets, everything else is an immediate.
+          const uint32_t wbase = smem_u32(buf) + (uint32_t)(q * 32) * 128u;
+          float2 s01 = make_float2(0.f, 0.f), q01 = make_float2(0.f, 0.f);
+#pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
-            if (m0 + q * 32 + rr >= p.M) break;   // rows past M hold zero-filled operand garbage-free zeros, but skip anyway
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(wrows + rr * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(rr & 7)) << 4) + ((lane & 3) << 2));
+            const uint32_t w = lds32(wbase + (uint32_t)rr * 128u + stat_off[rr & 7]);
             if (OUT_BF16) {
-              const float a = __uint_as_float(w << 16), b = __uint_as_float(w & 0xffff0000u);
-              s0 += a; q0s = fmaf(a, a, q0s); s1 += b; q1s = fmaf(b, b, q1s);
+              const float2 ab = make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+              s01.x += ab.x; s01.y += ab.y;
+              q01 = fma2(ab, ab, q01);
             } else {
               const float a = __uint_as_float(w);
-              s0 += a; q0s = fmaf(a, a, q0s);
+              s01.x += a; q01.x = fmaf(a, a, q01.x);
             }
           }
-          st_sum[c][0] += s0; st_sq[c][0] += q0s;
-          if (CPL == 2) { st_sum[c][CPL - 1] += s1; st_sq[c][CPL - 1] += q1s; }
+          st_sum[c][0] += s01.x; st_sq[c][0] += q01.x;
+          if (CPL == 2) { st_sum[c][CPL - 1] += s01.y; st_sq[c][CPL - 1] += q01.y; }
         }
       }
       if (kHeadCapable && head && (int64_t)m0 + row < p.M) {

@@ -225,7 +225,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
     fs_bar_sync(1 + g, 128);
     const uint32_t sw = (uint32_t)(row & 7);
-    uint8_t* my_row = buf + row * 128;
+    const uint32_t my_row_s = smem_u32(buf) + (uint32_t)row * 128u;
     int it = g;
     for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
       const int wb = tile % p.tiles_w; const int t2 = tile / p.tiles_w;
@@ -246,13 +246,13 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c * 64 + half * 32, r);
           tmem_ld_wait();
-          const float* ps = par_scale + c * 64 + half * 32;
-          const float* phf = par_shift + c * 64 + half * 32;
+          const uint32_t ps_s = smem_u32(par_scale + c * 64 + half * 32);
+          const uint32_t ph_s = smem_u32(par_shift + c * 64 + half * 32);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            const float4 s4 = *reinterpret_cast<const float4*>(ps + i);
-            const float4 h4 = *reinterpret_cast<const float4*>(phf + i);
+            const float4 s4 = lds128f(ps_s + i * 4);
+            const float4 h4 = lds128f(ph_s + i * 4);
             v[i] = fmaf(__uint_as_float(r[i]), s4.x, h4.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s4.y, h4.y);
             v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s4.z, h4.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s4.w, h4.w);
           }
@@ -264,11 +264,11 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int cls = 0; cls < 8; ++cls) {
               if (cls < p.head_classes) {
-                const float* hw = par_head + cls * 64 + half * 32;
+                const uint32_t hw_s = smem_u32(par_head + cls * 64 + half * 32);
                 float a = hacc[cls];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                  const float4 w4 = *reinterpret_cast<const float4*>(hw + i);
+                  const float4 w4 = lds128f(hw_s + i * 4);
                   a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
                   a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
                 }
@@ -281,7 +281,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           for (int j = 0; j < 4; ++j) {
             const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                        pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            *reinterpret_cast<uint4*>(my_row + ((((uint32_t)(half * 4 + j)) ^ sw) << 4)) = o;
+            sts128(my_row_s + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), o);
           }
         }
         if (c == BLOCK_N / 64 - 1 || (c + 1) * 64 >= p.Cout) {

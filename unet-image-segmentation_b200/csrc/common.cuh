@@ -102,6 +102,14 @@ __device__ __forceinline__ float4 lds128f(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
   return r;
 }
+__device__ __forceinline__ void sts64(uint32_t saddr, const uint2& v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void sts32f(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
+__device__ __forceinline__ float lds32f(uint32_t saddr) { float r; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr)); return r; }
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 // Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2): two IEEE round-to-nearest FMAs per issued instruction, bit-identical
 // to two scalar fmaf() calls.  The depthwise kernels are issue-bound on the FMA pipe without it.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {

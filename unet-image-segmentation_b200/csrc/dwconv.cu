@@ -254,7 +254,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     for (int j = 0; j < NV; ++j) {
       const float mine = (j & 1) ? csum[j / 2].y : csum[j / 2].x;
       const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
-      if (lane < 16) atomicAdd(&s_sum[cg * NV + j], v);
+      if (lane < 16) red_shared_add(smem_u32(&s_sum[cg * NV + j]), v);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < Cfg::CB; i += blockDim.x)
@@ -613,7 +613,7 @@ dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
     for (int j = 0; j < NV; ++j) {
       const float mine = (j & 1) ? acc[i][j / 2].y : acc[i][j / 2].x;
       const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
-      if (lane < 16) atomicAdd(&s_acc[i * Cfg::CB + cg * NV + j], v);
+      if (lane < 16) red_shared_add(smem_u32(&s_acc[i * Cfg::CB + cg * NV + j]), v);
     }
   __syncthreads();
   for (int i = threadIdx.x; i < 9 * Cfg::CB; i += blockDim.x) {
@@ -810,7 +810,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
   // lanes l and l^16 hold the same channels of neighbouring columns
   auto fold = [&](float mine, int slot, int j) {
     const float v = mine + __shfl_xor_sync(0xffffffffu, mine, 16);
-    if (lane < 16) atomicAdd(&s_acc[slot * Cfg::CB + cg * NV + j], v);
+    if (lane < 16) red_shared_add(smem_u32(&s_acc[slot * Cfg::CB + cg * NV + j]), v);
   };
 #pragma unroll
   for (int i = 0; i < 9; ++i)

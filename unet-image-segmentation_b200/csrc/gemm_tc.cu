@@ -77,9 +77,9 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
     uint32_t r[32];
     tmem_ld_32x32(tmem_addr + half * 32, r);
     tmem_ld_wait();
-    uint4* dst = reinterpret_cast<uint4*>(slab + lane * kSlabPitch + half * 128);
+    const uint32_t dst = smem_u32(slab) + (uint32_t)(lane * kSlabPitch + half * 128);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) dst[i] = make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    for (int i = 0; i < 8; ++i) sts128(dst + i * 16, make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
   }
   __syncwarp();
 
@@ -104,7 +104,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
   for (int it = 0; it < 16; ++it) {
     const int r = it * 2 + rsub;
     const int64_t m = row0 + r;
-    const float4 a = *reinterpret_cast<const float4*>(slab + r * kSlabPitch + seg * 16);
+    const float4 a = lds128f(smem_u32(slab) + (uint32_t)(r * kSlabPitch + seg * 16));
     if (!col_ok || m >= p.M) continue;
     float v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll

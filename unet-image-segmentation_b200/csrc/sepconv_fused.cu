@@ -158,14 +158,14 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
           if (c < p.Cin) {
-            const float4 w4 = *reinterpret_cast<const float4*>(s_wd + i * p.Cin + c);
+            const float4 w4 = lds128f(smem_u32(s_wd + i * p.Cin + c));
             k9[i][0] = make_float2(w4.x, w4.y); k9[i][1] = make_float2(w4.z, w4.w);
           } else { k9[i][0] = k9[i][1] = make_float2(0.f, 0.f); }
         }
         mbar_wait(&ld_full[s], ph);
         mbar_wait(&a_empty[ai], aph ^ 1);
         const uint32_t xs = smem_u32(stages + s * Cfg::kStageBytes) + x_off;
-        uint8_t* at = a_tiles + ai * kTileBytes;
+        const uint32_t at_s = smem_u32(a_tiles + ai * kTileBytes);
         float2 prev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cur[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
         for (int r = 0; r < kXRows; ++r) {
@@ -183,8 +183,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 #pragma unroll
             for (int j = 0; j < 2; ++j) o[j] = fma2(k9[8][j], cc[j], fma2(k9[7][j], b[j], fma2(k9[6][j], a[j], prev[j])));
             const uint32_t m = (uint32_t)((r - 2) * kPW + col);
-            *reinterpret_cast<uint2*>(at + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + (((uint32_t)cg & 1u) << 3)) =
-                make_uint2(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y));
+            sts64(at_s + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + (((uint32_t)cg & 1u) << 3),
+                  make_uint2(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y)));
           }
 #pragma unroll
           for (int j = 0; j < 2; ++j) {

@@ -248,8 +248,10 @@ int unet_adamw_step(float* w, const float* g, float* m, float* v, int64_t n, con
 /* end of one optimizer step, on device: hyper[5] (t) += 1 and *counter += 1 (the dropout seed_dev word). Either may be NULL. */
 int unet_step_advance(float* hyper, uint32_t* counter, void* stream);
 
-/* ---- parameter staging for the tensor-core path: dst[r,c] = bf16(src[r,c]); dst_t[c,r] = bf16(src[r,c]) ---- */
-int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream);
+/* ---- parameter staging for the tensor-core path: dst[r,c] = bf16(src[r,c]); dst_t[c,r] = bf16(src[r,c]).
+        col_scale (fp32 [C], may be NULL) multiplies column c first: the folded BatchNormalization scale of inference
+        (u_net.py:23) goes into the pointwise kernel, so the GEMM epilogue only adds the shift ---- */
+int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, const float* col_scale, void* stream);
 /* dst = cast(src) elementwise between fp32/bf16 (n elements) */
 int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 

@@ -340,14 +340,15 @@ def test_gemm_tc_fused_head(classes, store_y):
     Bt = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     sc = RNG.uniform(0.5, 1.5, N).astype(np.float32); sh = RNG.standard_normal(N).astype(np.float32) * 0.3
     hw = (RNG.standard_normal((N, classes)) / 4).astype(np.float32); hb = RNG.standard_normal(classes).astype(np.float32) * 0.1
-    y = bf16_round(np.maximum((bf16_round(A) @ bf16_round(Bt).T) * sc + sh, 0))
-    logits = y @ hw.astype(np.float64) + hb
+    y_exact = np.maximum((bf16_round(A) @ bf16_round(Bt).T) * sc + sh, 0)
+    y = bf16_round(y_exact)
+    logits = y_exact @ hw.astype(np.float64) + hb            # the head reads the fp32 activations in registers, not the stored bf16
     ref = R.sigmoid(logits) if classes == 1 else R.softmax(logits)
     Cm = torch.zeros((M, N), device="cuda", dtype=torch.bfloat16) if store_y else None
     probs = torch.full((M, classes), float("nan"), device="cuda")
     ops.gemm(dev(A, torch.bfloat16), dev(Bt, torch.bfloat16), Cm, b_trans=True, epilogue=ops.EPI_HEAD, scale=dev(sc), shift=dev(sh),
              head_w=dev(hw), head_b=dev(hb), head_out=probs)
-    np.testing.assert_allclose(host(probs), ref, rtol=0, atol=3e-3)      # y may round one bf16 ulp differently than the host
+    np.testing.assert_allclose(host(probs), ref, rtol=0, atol=3e-3)
     if store_y:
         np.testing.assert_allclose(host(Cm), y, **tol(torch.bfloat16))
 
@@ -701,7 +702,7 @@ def test_sepconv_fused_with_head(classes):
     sc = RNG.uniform(0.5, 1.5, cout).astype(np.float32); sh = RNG.standard_normal(cout).astype(np.float32) * 0.3
     hw = (RNG.standard_normal((cout, classes)) / 4).astype(np.float32); hb = RNG.standard_normal(classes).astype(np.float32) * 0.1
     d = bf16_round(R.dwconv3x3(bf16_round(x), wd.astype(np.float64)))
-    y = bf16_round(np.maximum((d.reshape(-1, cin) @ bf16_round(wp)) * sc + sh, 0))
+    y = np.maximum((d.reshape(-1, cin) @ bf16_round(wp)) * sc + sh, 0)     # the head reads the fp32 activations in registers
     logits = y @ hw.astype(np.float64) + hb
     ref = (R.sigmoid(logits) if classes == 1 else R.softmax(logits)).reshape(n, h, w, classes)
     probs = torch.full((n, h, w, classes), float("nan"), device="cuda")

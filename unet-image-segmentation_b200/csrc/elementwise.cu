@@ -481,7 +481,7 @@ __global__ void step_advance_kernel(float* hyper, uint32_t* counter) {
 
 // ------------------------------------------------------------------------------------------------ casts
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                           __nv_bfloat16* __restrict__ dst_t, int R, int C) {
+                                           __nv_bfloat16* __restrict__ dst_t, int R, int C, const float* __restrict__ col_scale) {
   __shared__ float tile[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -489,6 +489,7 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
     float v = 0.f;
     if (r < R && c < C) {
       v = src[(int64_t)r * C + c];
+      if (col_scale) v *= col_scale[c];
       if (dst) dst[(int64_t)r * C + c] = __float2bfloat16_rn(v);
     }
     tile[i][threadIdx.x] = v;
@@ -760,10 +761,10 @@ extern "C" int unet_step_advance(float* hyper, uint32_t* counter, void* stream) 
   return UNET_OK;
 }
 
-extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, void* stream) {
+extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, const float* col_scale, void* stream) {
   UNET_REQUIRE(src && (dst || dst_t) && R > 0 && C > 0, UNET_EINVAL, "cast_transpose_bf16: bad argument");
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(R, 32));
-  cast_transpose_bf16_kernel<<<grid, dim3(32, 8), 0, ST>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C);
+  cast_transpose_bf16_kernel<<<grid, dim3(32, 8), 0, ST>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C, col_scale);
   UNET_LAUNCH_CHECK("cast_transpose_bf16");
   return UNET_OK;
 }

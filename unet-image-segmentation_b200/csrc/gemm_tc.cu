@@ -400,12 +400,20 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (affine) {
             const uint32_t ps_s = smem_u32(par_scale + c * CW + half * 32);
             const uint32_t ph_s = smem_u32(par_shift + c * CW + half * 32);
+            if (p.scale && epi != UNET_EPI_CONVT) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {     // warp-uniform addresses: broadcast shared loads
-              const float4 s4 = lds128f(ps_s + i * 4);
-              const float4 h4 = lds128f(ph_s + i * 4);
-              v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
-              v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
+              for (int i = 0; i < 32; i += 4) {   // warp-uniform addresses: broadcast shared loads
+                const float4 s4 = lds128f(ps_s + i * 4);
+                const float4 h4 = lds128f(ph_s + i * 4);
+                v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
+                v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
+              }
+            } else {                              // bias only (Conv2DTranspose, folded BN scale, folded BN backward)
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 h4 = lds128f(ph_s + i * 4);
+                v[i] += h4.x; v[i + 1] += h4.y; v[i + 2] += h4.z; v[i + 3] += h4.w;
+              }
             }
             if (relu) {
 #pragma unroll
@@ -419,14 +427,14 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int cls = 0; cls < 8; ++cls) {
               if (cls < ncls) {
                 const uint32_t hw_s = smem_u32(par_head + cls * 64 + half * 32);
-                float a = hacc[cls];
+                float2 a2 = make_float2(hacc[cls], 0.f);     // fp32 activations (not re-rounded to bf16), packed FMAs
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 w4 = lds128f(hw_s + i * 4);
-                  a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
-                  a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
+                  a2 = fma2(make_float2(v[i], v[i + 1]), make_float2(w4.x, w4.y), a2);
+                  a2 = fma2(make_float2(v[i + 2], v[i + 3]), make_float2(w4.z, w4.w), a2);
                 }
-                hacc[cls] = a;
+                hacc[cls] = a2.x + a2.y;
               }
             }
           }

@@ -7,9 +7,10 @@
 //                 'same' padding and ragged patches) + the {64 k, BLOCK_N} slice of the pointwise kernel
 //   warp 1        MMA issuer: tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16, accumulating over the channel blocks
 //   warp 2        TMEM allocator (2 accumulator stages)
-//   warps 4-11    depthwise producers: thread = (patch column, 4 channels); slides down the 10 halo rows with two open
-//                 partial sums per channel in registers (3 conflict-free 8-byte shared loads + 27 FMA per channel-triple
-//                 per row), packs bf16 and stores into the A tile (K-major, SWIZZLE_128B) -> fence.proxy.async -> mbarrier
+//   warps 4-11    depthwise producers, two groups of 4 warps, each owning one A-tile buffer and every second (tile, channel
+//                 block) step: thread = (2 adjacent patch columns, 4 channels); slides down the 10 halo rows with two open
+//                 partial sums per output in registers (4 conflict-free 8-byte shared loads + 2 x 9 packed FFMA2 per row),
+//                 packs bf16 and stores into the A tile (K-major, SWIZZLE_128B) -> fence.proxy.async -> mbarrier
 //   warps 12-19   two epilogue groups (one per accumulator stage): tcgen05.ld -> scale/shift/ReLU -> bf16 -> swizzled staging
 //                 tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC destination
 #include "common.cuh"
@@ -89,9 +90,9 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   for (int i = threadIdx.x; i < 9 * p.Cin; i += blockDim.x) s_wd[i] = p.wd9c[i];
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 9); }
+    for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 5); }   // 4 producer warps + the MMA commit
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 8); mbar_init(&a_empty[i], 1);
+      mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1);
       mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
     }
     fence_barrier_init();
@@ -147,56 +148,75 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     }
   } else if (warp >= 4 && warp < 12) {
     // ===================================================================== depthwise producers
-    const int t = (warp - 4) * 32 + lane;
-    const int col = t >> 4, cg = t & 15;
-    const uint32_t x_off = (uint32_t)col * 128u + (uint32_t)cg * 8u;
-    int s = 0; uint32_t ph = 0; int ai = 0; uint32_t aph = 0;
+    // Two groups of 4 warps; group g owns A-tile buffer g and produces every second (tile, channel block) step on its own, so
+    // a thread covers TWO adjacent patch columns (4 shared loads per row for 2 outputs instead of 6) and, when the number of
+    // channel blocks is 1 or 2, always meets the same channel block: its 9 taps stay in registers for the whole kernel.
+    const int g = (warp - 4) >> 2;
+    const int t = ((warp - 4) & 3) * 32 + lane;
+    const int cp = t >> 4, cg = t & 15;                   // column pair (patch columns 2cp, 2cp+1), 4-channel group
+    const uint32_t x_off = (uint32_t)(2 * cp) * 128u + (uint32_t)cg * 8u;
+    const uint32_t at_s = smem_u32(a_tiles + g * kTileBytes);
+    float2 k9[9][2];                            // fp32 pairs: every FMA below is a packed FFMA2
+    int k9_kb = -1;
+    uint32_t aph = 0;
+    int step = 0;                               // global (tile, channel block) counter; this group takes step % 2 == g
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < num_k; ++kb) {
-        float2 k9[9][2];                        // fp32 pairs: every FMA below is a packed FFMA2
-        const int c = kb * 64 + cg * 4;
+      for (int kb = 0; kb < num_k; ++kb, ++step) {
+        if ((step & 1) != g) continue;
+        const int s = step % S; const uint32_t ph = (uint32_t)(step / S) & 1u;
+        if (k9_kb != kb) {
+          k9_kb = kb;
+          const int c = kb * 64 + cg * 4;
 #pragma unroll
-        for (int i = 0; i < 9; ++i) {
-          if (c < p.Cin) {
-            const float4 w4 = lds128f(smem_u32(s_wd + i * p.Cin + c));
-            k9[i][0] = make_float2(w4.x, w4.y); k9[i][1] = make_float2(w4.z, w4.w);
-          } else { k9[i][0] = k9[i][1] = make_float2(0.f, 0.f); }
+          for (int i = 0; i < 9; ++i) {
+            if (c < p.Cin) {
+              const float4 w4 = lds128f(smem_u32(s_wd + i * p.Cin + c));
+              k9[i][0] = make_float2(w4.x, w4.y); k9[i][1] = make_float2(w4.z, w4.w);
+            } else { k9[i][0] = k9[i][1] = make_float2(0.f, 0.f); }
+          }
         }
         mbar_wait(&ld_full[s], ph);
-        mbar_wait(&a_empty[ai], aph ^ 1);
+        mbar_wait(&a_empty[g], aph ^ 1);
         const uint32_t xs = smem_u32(stages + s * Cfg::kStageBytes) + x_off;
-        const uint32_t at_s = smem_u32(a_tiles + ai * kTileBytes);
-        float2 prev[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, cur[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+        const float2 z2 = make_float2(0.f, 0.f);
+        float2 prev0[2] = {z2, z2}, cur0[2] = {z2, z2}, prev1[2] = {z2, z2}, cur1[2] = {z2, z2};
 #pragma unroll
         for (int r = 0; r < kXRows; ++r) {
-          const uint2 ra = lds64(xs + r * kXCols * 128);
-          const uint2 rb = lds64(xs + r * kXCols * 128 + 128);
-          const uint2 rc = lds64(xs + r * kXCols * 128 + 256);
-          const float2 a[2] = {make_float2(__uint_as_float(ra.x << 16), __uint_as_float(ra.x & 0xffff0000u)),
-                               make_float2(__uint_as_float(ra.y << 16), __uint_as_float(ra.y & 0xffff0000u))};
-          const float2 b[2] = {make_float2(__uint_as_float(rb.x << 16), __uint_as_float(rb.x & 0xffff0000u)),
-                               make_float2(__uint_as_float(rb.y << 16), __uint_as_float(rb.y & 0xffff0000u))};
-          const float2 cc[2] = {make_float2(__uint_as_float(rc.x << 16), __uint_as_float(rc.x & 0xffff0000u)),
-                                make_float2(__uint_as_float(rc.y << 16), __uint_as_float(rc.y & 0xffff0000u))};
+          const uint2 r0 = lds64(xs + r * kXCols * 128);           // halo columns 2cp .. 2cp+3 of this row
+          const uint2 r1 = lds64(xs + r * kXCols * 128 + 128);
+          const uint2 r2 = lds64(xs + r * kXCols * 128 + 256);
+          const uint2 r3 = lds64(xs + r * kXCols * 128 + 384);
+          float2 q0[2], q1[2], q2[2], q3[2];
+          q0[0] = make_float2(__uint_as_float(r0.x << 16), __uint_as_float(r0.x & 0xffff0000u)); q0[1] = make_float2(__uint_as_float(r0.y << 16), __uint_as_float(r0.y & 0xffff0000u));
+          q1[0] = make_float2(__uint_as_float(r1.x << 16), __uint_as_float(r1.x & 0xffff0000u)); q1[1] = make_float2(__uint_as_float(r1.y << 16), __uint_as_float(r1.y & 0xffff0000u));
+          q2[0] = make_float2(__uint_as_float(r2.x << 16), __uint_as_float(r2.x & 0xffff0000u)); q2[1] = make_float2(__uint_as_float(r2.y << 16), __uint_as_float(r2.y & 0xffff0000u));
+          q3[0] = make_float2(__uint_as_float(r3.x << 16), __uint_as_float(r3.x & 0xffff0000u)); q3[1] = make_float2(__uint_as_float(r3.y << 16), __uint_as_float(r3.y & 0xffff0000u));
           if (r >= 2) {
-            float2 o[2];
+            float2 o0[2], o1[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) o[j] = fma2(k9[8][j], cc[j], fma2(k9[7][j], b[j], fma2(k9[6][j], a[j], prev[j])));
-            const uint32_t m = (uint32_t)((r - 2) * kPW + col);
-            sts64(at_s + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + (((uint32_t)cg & 1u) << 3),
-                  make_uint2(pack_bf16x2(o[0].x, o[0].y), pack_bf16x2(o[1].x, o[1].y)));
+            for (int j = 0; j < 2; ++j) {
+              o0[j] = fma2(k9[8][j], q2[j], fma2(k9[7][j], q1[j], fma2(k9[6][j], q0[j], prev0[j])));
+              o1[j] = fma2(k9[8][j], q3[j], fma2(k9[7][j], q2[j], fma2(k9[6][j], q1[j], prev1[j])));
+            }
+            const uint32_t m = (uint32_t)((r - 2) * kPW + 2 * cp);      // GEMM rows m (column 2cp) and m + 1
+            const uint32_t hi = ((uint32_t)cg & 1u) << 3;
+            sts64(at_s + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + hi,
+                  make_uint2(pack_bf16x2(o0[0].x, o0[0].y), pack_bf16x2(o0[1].x, o0[1].y)));
+            sts64(at_s + (m + 1u) * 128u + ((((uint32_t)cg >> 1) ^ ((m + 1u) & 7u)) << 4) + hi,
+                  make_uint2(pack_bf16x2(o1[0].x, o1[0].y), pack_bf16x2(o1[1].x, o1[1].y)));
           }
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            prev[j] = fma2(k9[5][j], cc[j], fma2(k9[4][j], b[j], fma2(k9[3][j], a[j], cur[j])));
-            cur[j]  = fma2(k9[2][j], cc[j], fma2(k9[1][j], b[j], mul2(k9[0][j], a[j])));
+            prev0[j] = fma2(k9[5][j], q2[j], fma2(k9[4][j], q1[j], fma2(k9[3][j], q0[j], cur0[j])));
+            prev1[j] = fma2(k9[5][j], q3[j], fma2(k9[4][j], q2[j], fma2(k9[3][j], q1[j], cur1[j])));
+            cur0[j]  = fma2(k9[2][j], q2[j], fma2(k9[1][j], q1[j], mul2(k9[0][j], q0[j])));
+            cur1[j]  = fma2(k9[2][j], q3[j], fma2(k9[1][j], q2[j], mul2(k9[0][j], q1[j])));
           }
         }
         fs_fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05 (async proxy)
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&a_full[ai]); mbar_arrive(&x_empty[s]); }
-        if (++s == S) { s = 0; ph ^= 1; }
-        if (++ai == 2) { ai = 0; aph ^= 1; }
+        if (lane == 0) { mbar_arrive(&a_full[g]); mbar_arrive(&x_empty[s]); }
+        aph ^= 1;
       }
     }
   } else if (warp >= 12) {
@@ -249,12 +269,21 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const uint32_t ps_s = smem_u32(par_scale + c * 64 + half * 32);
           const uint32_t ph_s = smem_u32(par_shift + c * 64 + half * 32);
           float v[32];
+          if (p.scale) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 s4 = lds128f(ps_s + i * 4);
-            const float4 h4 = lds128f(ph_s + i * 4);
-            v[i] = fmaf(__uint_as_float(r[i]), s4.x, h4.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s4.y, h4.y);
-            v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s4.z, h4.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s4.w, h4.w);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = lds128f(ps_s + i * 4);
+              const float4 h4 = lds128f(ph_s + i * 4);
+              v[i] = fmaf(__uint_as_float(r[i]), s4.x, h4.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s4.y, h4.y);
+              v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s4.z, h4.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s4.w, h4.w);
+            }
+          } else {                                // scale folded into the pointwise kernel: half the broadcast shared loads
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 h4 = lds128f(ph_s + i * 4);
+              v[i] = __uint_as_float(r[i]) + h4.x; v[i + 1] = __uint_as_float(r[i + 1]) + h4.y;
+              v[i + 2] = __uint_as_float(r[i + 2]) + h4.z; v[i + 3] = __uint_as_float(r[i + 3]) + h4.w;
+            }
           }
           if (p.relu) {
 #pragma unroll
@@ -265,14 +294,14 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             for (int cls = 0; cls < 8; ++cls) {
               if (cls < p.head_classes) {
                 const uint32_t hw_s = smem_u32(par_head + cls * 64 + half * 32);
-                float a = hacc[cls];
+                float2 a2 = make_float2(hacc[cls], 0.f);     // fp32 activations (not re-rounded to bf16), packed FMAs
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                   const float4 w4 = lds128f(hw_s + i * 4);
-                  a = fmaf(round_to<__nv_bfloat16>(v[i]), w4.x, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 1]), w4.y, a);
-                  a = fmaf(round_to<__nv_bfloat16>(v[i + 2]), w4.z, a); a = fmaf(round_to<__nv_bfloat16>(v[i + 3]), w4.w, a);
+                  a2 = fma2(make_float2(v[i], v[i + 1]), make_float2(w4.x, w4.y), a2);
+                  a2 = fma2(make_float2(v[i + 2], v[i + 3]), make_float2(w4.z, w4.w), a2);
                 }
-                hacc[cls] = a;
+                hacc[cls] = a2.x + a2.y;
               }
             }
           }

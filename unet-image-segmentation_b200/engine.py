@@ -95,6 +95,8 @@ class UNetEngine:
             self._fz = torch.zeros(max(tot, 64), device=dev)
             self._fold_w: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._stage: Dict[str, torch.Tensor] = {}
+        self._stage_fold: Dict[str, torch.Tensor] = {}     # inference: bf16 [Cout, Cin] pointwise kernels with the BN scale folded in
+        self.fold_scale_into_weights = True
         self._stage_dirty = True
         self._fold_dirty = True
         self._plans: Dict[Tuple[int, bool], _Plan] = {}
@@ -205,6 +207,14 @@ class UNetEngine:
             ops.bn_fold(self.wview(f"{b.prefix}_bn/gamma"), self.wview(f"{b.prefix}_bn/beta"),
                         self.wview(f"{b.prefix}_bn/moving_mean"), self.wview(f"{b.prefix}_bn/moving_variance"),
                         BN_EPS, self.fold[0, o:o + c], self.fold[1, o:o + c])
+            if self.act_dtype == torch.bfloat16 and b.cin % 8 == 0:
+                # inference: the BatchNormalization scale goes into the bf16 pointwise kernel ([Cout, Cin] staging), so the
+                # GEMM epilogue only adds the shift (half the broadcast shared-memory loads per accumulator row)
+                name = f"{b.prefix}_sepconv/pointwise_kernel"
+                t = self._stage_fold.get(name)
+                if t is None:
+                    t = self._stage_fold[name] = torch.empty((b.cout, b.cin), device=self.device, dtype=torch.bfloat16)
+                ops.cast_transpose_bf16(self._mat(name), None, t, col_scale=self.fold[0, o:o + c])
         self._fold_dirty = False
 
     # ------------------------------------------------------------------------------------------------ GEMM dispatch
@@ -256,6 +266,17 @@ class UNetEngine:
                                 self.step_word if self.dropout_masks_from_step else None)
 
     # ------------------------------------------------------------------------------------------------ inference
+    def _infer_pw(self, prefix: str):
+        """(bf16 [Cout, Cin] pointwise kernel, scale, shift) of an inference conv_block on the tensor-core path: with
+        BatchNormalization the scale is already inside the kernel (scale None)."""
+        name = f"{prefix}_sepconv/pointwise_kernel"
+        o, c = self._bn_off[prefix]
+        if not self.use_bn:
+            return self._stage[name + "^T"], None, self.wview(f"{prefix}_sepconv/bias")
+        if self.fold_scale_into_weights and name in self._stage_fold:
+            return self._stage_fold[name], None, self.fold[1, o:o + c]
+        return self._stage[name + "^T"], self.fold[0, o:o + c], self.fold[1, o:o + c]
+
     def _block_infer(self, pl: _Plan, prefix: str, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         B, h, w, cin = x.shape
         if ops.stem_supported(cin, y.shape[-1]) and x.is_contiguous():
@@ -266,17 +287,17 @@ class UNetEngine:
             return y
         if self.fuse_sepconv and ops.sepconv_fused_supported(x, y.shape[-1]):
             # whole conv_block in one kernel: the depthwise result is produced on chip as the GEMM's A operand
-            name = f"{prefix}_sepconv/pointwise_kernel"
-            o, c = self._bn_off[prefix]
-            ops.sepconv_fused(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._stage[name + "^T"], y,
-                              scale=self.fold[0, o:o + c] if self.use_bn else None,
-                              shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True)
+            wpt, sc, sh = self._infer_pw(prefix)
+            ops.sepconv_fused(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), wpt, y, scale=sc, shift=sh, relu=True)
             return y
         level = (self.spec.input_size[0] // h).bit_length() - 1
         max_cin = 1024 if level == 4 else 2 * FILTERS[level]
         d = pl.buf(f"d{level}", (B * h * w * max_cin,))[: B * h * w * cin].view(B, h, w, cin)
         ops.dwconv3x3(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), d)
-        if self.use_bn:
+        if self.act_dtype == torch.bfloat16 and cin % 8 == 0:
+            wpt, sc, sh = self._infer_pw(prefix)
+            ops.gemm(d, wpt, y, b_trans=True, epilogue=ops.EPI_AFFINE_RELU, scale=sc, shift=sh)
+        elif self.use_bn:
             o, c = self._bn_off[prefix]
             self._pw_fwd(prefix, d, y, epilogue=ops.EPI_AFFINE_RELU, scale=self.fold[0, o:o + c], shift=self.fold[1, o:o + c])
         else:
@@ -344,10 +365,7 @@ class UNetEngine:
             # dec1_block2's pointwise GEMM applies BN + ReLU and the 1x1 sigmoid/softmax head in its epilogue; the
             # 64-channel activation it would have produced is never written
             prefix = "dec1_block2"
-            o, c = self._bn_off[prefix]
-            sc = self.fold[0, o:o + c] if self.use_bn else None
-            sh = self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias")
-            wpt = self._stage[f"{prefix}_sepconv/pointwise_kernel^T"]
+            wpt, sc, sh = self._infer_pw(prefix)
             hw, hb = self._mat("output_mask/kernel"), self.wview("output_mask/bias")
             if self.fuse_sepconv and ops.sepconv_fused_supported(cur, FILTERS[0]):
                 ops.sepconv_fused(cur, self._mat(f"{prefix}_sepconv/depthwise_kernel"), wpt, None, scale=sc, shift=sh,

@@ -507,10 +507,14 @@ def step_advance(hyper: Optional[torch.Tensor], counter: Optional[torch.Tensor])
     _call("unet_step_advance", _p(hyper), _p(counter), _stream())
 
 
-def cast_transpose_bf16(src: torch.Tensor, dst: Optional[torch.Tensor], dst_t: Optional[torch.Tensor]) -> None:
-    _f32(src, "src")
+def cast_transpose_bf16(src: torch.Tensor, dst: Optional[torch.Tensor], dst_t: Optional[torch.Tensor],
+                        col_scale: Optional[torch.Tensor] = None) -> None:
+    """dst[r,c] = bf16(src[r,c] * col_scale[c]), dst_t = its transpose (either may be None)."""
+    _f32(src, "src"); _f32(col_scale, "col_scale")
     r, c = src.shape
-    _call("unet_cast_transpose_bf16", _p(src), _p(dst), _p(dst_t), r, c, _stream())
+    if col_scale is not None and col_scale.numel() != c:
+        raise ValueError("cast_transpose_bf16: col_scale must hold one value per column")
+    _call("unet_cast_transpose_bf16", _p(src), _p(dst), _p(dst_t), r, c, _p(col_scale), _stream())
 
 
 def cast(src: torch.Tensor, dst: torch.Tensor) -> None:

@@ -63,6 +63,14 @@ elif name == "dw_fwd256":
 elif name == "dw_bwd_w":
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     run(lambda: ops.dwconv3x3_bwd_weight(x, dy, dw), 2 * M * 64 * 2)
+elif name == "gemm_fold_dgrad":   # dec1_block1 data gradient with BatchNormalization backward folded in: dd = [g | z] * wab^T + bias
+    g_, z_, wab = rnd(M, 64), rnd(M, 64), rnd(128, 128)
+    bias, dd = torch.rand(128, device=dev), torch.empty((M, 128), device=dev, dtype=bf)
+    run(lambda: ops.gemm(g_, wab, dd, b_trans=True, A2=z_, epilogue=ops.EPI_AFFINE, shift=bias), M * (64 + 64 + 128) * 2)
+elif name == "gemm_fold_wgrad":   # its weight gradient: G = d^T [g | z]
+    d_, g_, z_ = rnd(M, 128), rnd(M, 64), rnd(M, 64)
+    G = torch.zeros((128, 128), device=dev)
+    run(lambda: ops.gemm(d_, g_, G, a_trans=True, accumulate=True, B2=z_), M * (128 + 64 + 64) * 2)
 elif name in ("dw_bwd", "dw_bwd_mask"):
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     dx, w, sums = torch.empty_like(x), torch.rand((9, 64), device=dev), torch.zeros((2, 64), device=dev)

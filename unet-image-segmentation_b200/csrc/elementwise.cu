@@ -401,6 +401,8 @@ maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ convT backward gather
+// One block item = one input-image row (n, i): the two upsampled rows 2i and 2i+1 are read as contiguous runs and each
+// 16-byte channel group goes to column block (a,b) of G row (n,i,j) — no division in the inner loop, 32-bit offsets.
 template <typename T>
 __global__ void __launch_bounds__(256)
 convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ g, float* __restrict__ dbias,
@@ -410,23 +412,27 @@ convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ 
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   const int cv = Cout >> 3;
-  const int per_block = blockDim.x / cv;
+  const int per_block = blockDim.x / cv;          // upsampled pixels handled per pass
   const int c0 = (threadIdx.x % cv) << 3;
-  const int64_t items = (int64_t)N * H * W * 4;
+  const int slot = threadIdx.x / cv;
+  const int W2 = 2 * W;
   float sb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) sb[j] = 0.f;
-  for (int64_t it = blockIdx.x * (int64_t)per_block + threadIdx.x / cv; it < items; it += (int64_t)gridDim.x * per_block) {
-    const int ab = (int)(it & 3); int64_t m = it >> 2;
-    const int j = (int)(m % W); const int64_t q = m / W;
-    const int i = (int)(q % H); const int64_t n = q / H;
-    const int64_t src = (n * (2 * H) + 2 * i + (ab >> 1)) * (int64_t)(2 * W) + 2 * j + (ab & 1);
-    float v[8];
-    load8(du + src * lddu + c0, v);
-    if (dp.on) dropout_apply(v, (uint64_t)src * dp.ctot + dp.c0 + c0, seed, dp.keep, dp.inv_keep);   // the upsampled half was stored dropped-out
-    store8(g + (m * 4 + ab) * (int64_t)Cout + c0, v);
+  const int64_t rows = (int64_t)N * H * 2;        // upsampled rows (n, 2i + a)
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int a = (int)(r & 1); const int64_t q = r >> 1;          // q = n*H + i
+    const T* src_row = du + (r * W2) * lddu + c0;                  // upsampled row index == r because rows are (n, 2i+a) in order
+    T* dst_row = g + (q * W) * (int64_t)(4 * Cout) + (int64_t)(a * 2) * Cout + c0;
+    const uint64_t drop_row = (uint64_t)(r * W2) * (uint64_t)dp.ctot + dp.c0 + c0;
+    for (int x2 = slot; x2 < W2; x2 += per_block) {                // upsampled column 2j + b
+      float v[8];
+      load8(src_row + (int64_t)x2 * lddu, v);
+      if (dp.on) dropout_apply(v, drop_row + (uint64_t)x2 * (uint64_t)dp.ctot, seed, dp.keep, dp.inv_keep);   // du was stored dropped-out
+      store8(dst_row + (int64_t)(x2 >> 1) * (4 * Cout) + (x2 & 1) * Cout, v);
 #pragma unroll
-    for (int jj = 0; jj < 8; ++jj) sb[jj] += v[jj];
+      for (int jj = 0; jj < 8; ++jj) sb[jj] += v[jj];
+    }
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) atomicAdd(&s_red[c0 + j], sb[j]);
@@ -734,9 +740,7 @@ extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, floa
   UNET_REQUIRE(du && g && N > 0 && H > 0 && W > 0 && Cout > 0 && lddu >= Cout, UNET_EINVAL, "convt_bwd_gather: bad argument");
   UNET_REQUIRE(Cout % 8 == 0 && lddu % 8 == 0 && aligned16(du) && aligned16(g), UNET_EALIGN, "convt_bwd_gather: needs Cout%%8==0");
   UNET_REQUIRE(256 % (Cout / 8) == 0, UNET_EUNSUPPORTED, "convt_bwd_gather: Cout/8 must divide 256");
-  const int per_block = 256 / (Cout / 8);
-  const int64_t items = (int64_t)N * H * W * 4;
-  const unsigned grid = (unsigned)i64min(ceil_div(items, per_block), (int64_t)sm_count() * 8);
+  const unsigned grid = (unsigned)i64min((int64_t)N * H * 2, (int64_t)sm_count() * 8);
   const size_t smem = (size_t)Cout * sizeof(float);
   if (dtype == UNET_F32)
     convt_bwd_gather_kernel<float><<<grid, 256, smem, ST>>>((const float*)du, lddu, (float*)g, dbias, N, H, W, Cout, dp);

@@ -132,10 +132,17 @@ int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy,
    of the stored values.  UNET_EUNSUPPORTED for other channel counts (callers then use dwconv3x3_fwd + gemm). */
 int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, void* out, int64_t ldo,
                   int N, int H, int W, int Cin, int Cout, int dtype,
-                  const float* scale, const float* shift, int relu, double* colsum, double* colsq, void* stream);
+                  const float* scale, const float* shift, int relu, double* colsum, double* colsq,
+                  float* d_out /* optional fp32 [N*H*W,3]: the depthwise output, kept for unet_stem_bwd_folded */, void* stream);
 /* given dz = gradient w.r.t. pw(dw(x)): dwp[3,64] += d^T dz (d = dw(x) recomputed on chip), dwd9c[3,3,3] += x (*) (dz Wp^T) */
 int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const float* wd9c, const float* wp,
                   float* dwd9c, float* dwp, int N, int H, int W, int Cin, int Cout, int dtype, void* stream);
+/* streaming backward of the first block with BatchNormalization backward folded in (no dz tensor): given g = dy*[y>0] (ptr,ldg),
+   the saved pre-BN z (contiguous [M,64]), coef = [A|B|K] from unet_bn_bwd_coef and d3 from unet_stem_fwd:
+   dz = A*g + B*z + K in registers; dwp[3,64] += d3^T dz; dd[M,3] (dtype) = dz Wp^T.  The depthwise weight gradient follows
+   as unet_dwconv3x3_bwd_weight(x, dd). */
+int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, const float* coef, const float* d3,
+                         const float* wp, float* dwp, void* dd, int64_t M, int dtype, void* stream);
 
 /* ---- whole conv_block for inference (u_net.py:5-26): y = act((dw3x3(x) . Wp) * scale + shift), depthwise result kept on chip ---- */
 /* bf16 only.  x: [N,H,W,Cin] view (ldx); wp_t: pointwise kernel TRANSPOSED, bf16 [Cout, Cin] (ldw); scale/shift: folded

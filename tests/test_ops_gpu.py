@@ -241,6 +241,34 @@ def test_stem_fwd_bwd(dtype, shape):
     np.testing.assert_allclose(host(gwd).reshape(3, 3, 3), gwd_ref, rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_stem_bwd_folded(dtype):
+    """streaming first-block backward: dz = A*g + B*z + K formed in registers == explicit dz fed to the tiled kernel"""
+    n, h, w = 2, 19, 37
+    x = RNG.random((n, h, w, 3)).astype(np.float32)
+    wd = RNG.standard_normal((3, 3, 3)).astype(np.float32); wp = RNG.standard_normal((3, 64)).astype(np.float32)
+    g = RNG.standard_normal((n, h, w, 64)).astype(np.float32); z = RNG.standard_normal((n, h, w, 64)).astype(np.float32)
+    coef = np.stack([RNG.uniform(0.5, 1.5, 64), RNG.standard_normal(64) * 0.1, RNG.standard_normal(64) * 0.05]).astype(np.float32)
+    xr, gr, zr = (bf16_round(x), bf16_round(g), bf16_round(z)) if dtype == torch.bfloat16 else (x.astype(np.float64), g.astype(np.float64), z.astype(np.float64))
+    dz = coef[0] * gr + coef[1] * zr + coef[2]
+    d = R.dwconv3x3(xr, wd.astype(np.float64))
+    xd = dev(x, dtype)
+    out = torch.empty((n, h, w, 64), device="cuda", dtype=dtype)
+    cs = torch.zeros(64, device="cuda", dtype=torch.float64); cq = torch.zeros_like(cs)
+    d3 = torch.empty((n, h, w, 3), device="cuda")
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), out, colsum=cs, colsq=cq, d_out=d3)
+    np.testing.assert_allclose(host(d3), d, rtol=1e-5, atol=1e-5)
+    gwp = torch.zeros((3, 64), device="cuda"); dd = torch.empty((n, h, w, 3), device="cuda", dtype=dtype)
+    ops.stem_bwd_folded(dev(g, dtype), dev(z, dtype), dev(coef), d3, dev(wp), gwp, dd)
+    np.testing.assert_allclose(host(gwp), d.reshape(-1, 3).T @ dz.reshape(-1, 64), rtol=1e-3, atol=1e-2)
+    dd_ref = (dz.reshape(-1, 64) @ wp.astype(np.float64).T).reshape(n, h, w, 3)
+    np.testing.assert_allclose(host(dd), dd_ref, **(dict(rtol=1e-4, atol=1e-4) if dtype == torch.float32 else dict(rtol=1e-2, atol=5e-2)))
+    gwd = torch.zeros((9, 3), device="cuda")
+    ops.dwconv3x3_bwd_weight(xd, dd, gwd)
+    _, gwd_ref = R.dwconv3x3_bwd(xr, wd.astype(np.float64), host(dd))
+    np.testing.assert_allclose(host(gwd).reshape(3, 3, 3), gwd_ref, rtol=1e-3, atol=1e-2)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM, CUDA cores
 @pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("mkn", [(70, 3, 64), (129, 40, 33), (64, 64, 1), (256, 128, 96)])

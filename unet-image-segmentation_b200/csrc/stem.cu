@@ -47,7 +47,7 @@ template <typename T, bool STATS>
 __global__ void __launch_bounds__(256, 4)
 stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const float* __restrict__ wp, T* __restrict__ out,
                 int64_t ldo, int N, int H, int W, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                double* __restrict__ colsum, double* __restrict__ colsq, int tiles_h, int tiles_w) {
+                double* __restrict__ colsum, double* __restrict__ colsq, int tiles_h, int tiles_w, float* __restrict__ d_out) {
   __shared__ float s_x[(kTH + 2) * (kTW + 2) * kStemCin];
   __shared__ float s_d[kTH * kTW * kStemCin];
   __shared__ float s_wd[9 * kStemCin];
@@ -71,6 +71,13 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
     stem_load_tile<T>(x, n, h0, w0, H, W, s_x);
     __syncthreads();
     stem_depthwise(s_x, s_wd, s_d);
+    if (d_out) {                                     // depthwise output of this thread's pixel, kept for the streaming backward
+      const int hh = h0 + (threadIdx.x >> 5), ww = w0 + (threadIdx.x & 31);
+      if (hh < H && ww < W) {
+        float* dp = d_out + (((int64_t)n * H + hh) * W + ww) * 3;
+        dp[0] = s_d[threadIdx.x * 3]; dp[1] = s_d[threadIdx.x * 3 + 1]; dp[2] = s_d[threadIdx.x * 3 + 2];
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -231,6 +238,76 @@ stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz,
   if (threadIdx.x < 9 * kStemCin) atomicAdd(&dwd9c[threadIdx.x], s_gd[threadIdx.x]);
 }
 
+// Streaming backward of the first block with BatchNormalization backward folded in (see unet_bn_bwd_coef): no dz tensor,
+// no shared-memory tiles, no block barriers.  Per pixel (8 lanes x 8 channels): dz = A*g + B*z + K in registers,
+//   dwp[ci][co] += d[ci] * dz[co]        (d = depthwise output stored by the forward kernel, 3 floats per pixel)
+//   dd[ci]       = sum_co dz[co] * wp[ci][co]   (8-lane shuffle reduction) -> stored, 3 values per pixel
+// The depthwise weight gradient then is unet_dwconv3x3_bwd_weight(x, dd) on two 3-channel tensors.
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+stem_bwd_folded_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ z, const float* __restrict__ coef,
+                       const float* __restrict__ d3, const float* __restrict__ wp, float* __restrict__ dwp, T* __restrict__ dd,
+                       int64_t M) {
+  __shared__ float s_gp[kStemCin * kStemCout];
+  if (threadIdx.x < kStemCin * kStemCout) s_gp[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  float w[kStemCin][8], gp[kStemCin][8], ca[8], cb[8], ck[8];
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci) {
+    load8(wp + ci * kStemCout + cg * 8, w[ci]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gp[ci][j] = 0.f;
+  }
+  load8(coef + cg * 8, ca); load8(coef + kStemCout + cg * 8, cb); load8(coef + 2 * kStemCout + cg * 8, ck);
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * 32 * U;
+  for (int64_t m0 = (int64_t)blockIdx.x * 32 * U; m0 < M; m0 += stride) {
+    StemRaw<T> graw[U], zraw[U];
+    float dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                   // all loads of the trip first
+      const int64_t m = m0 + u * 32 + slot;
+      if (m < M) {
+        ldraw8(g + m * ldg + cg * 8, graw[u]); ldraw8(z + m * kStemCout + cg * 8, zraw[u]);
+        dv[u] = cg < 3 ? __ldg(d3 + m * 3 + cg) : 0.f;
+      } else { zero8(graw[u]); zero8(zraw[u]); dv[u] = 0.f; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = m0 + u * 32 + slot;
+      float gv[8], zv[8];
+      unraw8(graw[u], gv); unraw8(zraw[u], zv);
+      const int base = threadIdx.x & 24;            // first lane of this pixel's 8-lane group (within the warp)
+      const float d0 = __shfl_sync(0xffffffffu, dv[u], base), d1 = __shfl_sync(0xffffffffu, dv[u], base + 1),
+                  d2 = __shfl_sync(0xffffffffu, dv[u], base + 2);
+      float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+      const bool live = m < M;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dz = live ? fmaf(ca[j], gv[j], fmaf(cb[j], zv[j], ck[j])) : 0.f;
+        gp[0][j] = fmaf(d0, dz, gp[0][j]); gp[1][j] = fmaf(d1, dz, gp[1][j]); gp[2][j] = fmaf(d2, dz, gp[2][j]);
+        dd0 = fmaf(dz, w[0][j], dd0); dd1 = fmaf(dz, w[1][j], dd1); dd2 = fmaf(dz, w[2][j], dd2);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        dd0 += __shfl_xor_sync(0xffffffffu, dd0, o); dd1 += __shfl_xor_sync(0xffffffffu, dd1, o); dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);
+      }
+      if (live && cg < 3) dd[m * 3 + cg] = from_f32<T>(cg == 0 ? dd0 : (cg == 1 ? dd1 : dd2));
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = gp[ci][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if ((threadIdx.x & 31) < 8) atomicAdd(&s_gp[ci * kStemCout + cg * 8 + j], v);
+    }
+  __syncthreads();
+  if (threadIdx.x < kStemCin * kStemCout) atomicAdd(&dwp[threadIdx.x], s_gp[threadIdx.x]);
+}
+
 static int stem_check(const char* who, const void* x, int N, int H, int W, int Cin, int Cout) {
   UNET_REQUIRE(x && N > 0 && H > 0 && W > 0, UNET_EINVAL, "%s: bad argument", who);
   UNET_REQUIRE(Cin == kStemCin && Cout == kStemCout, UNET_EUNSUPPORTED,
@@ -245,7 +322,7 @@ using namespace unet;
 
 extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, void* out, int64_t ldo,
                              int N, int H, int W, int Cin, int Cout, int dtype,
-                             const float* scale, const float* shift, int relu, double* colsum, double* colsq, void* stream) {
+                             const float* scale, const float* shift, int relu, double* colsum, double* colsq, float* d_out, void* stream) {
   if (int e = stem_check("stem_fwd", x, N, H, W, Cin, Cout)) return e;
   UNET_REQUIRE(wd9c && wp && out && ldo >= Cout, UNET_EINVAL, "stem_fwd: bad argument");
   UNET_REQUIRE((colsum == nullptr) == (colsq == nullptr), UNET_EINVAL, "stem_fwd: colsum/colsq must come together");
@@ -256,7 +333,7 @@ extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, 
   const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 8);
   cudaStream_t st = (cudaStream_t)stream;
   UNET_REQUIRE(!(colsum && (scale || shift)), UNET_EINVAL, "stem_fwd: statistics are taken on the raw contraction (no scale/shift)");
-#define STEM_FWD(T, S) stem_fwd_kernel<T, S><<<grid, 256, 0, st>>>((const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw)
+#define STEM_FWD(T, S) stem_fwd_kernel<T, S><<<grid, 256, 0, st>>>((const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw, d_out)
   if (dtype == UNET_F32) { if (colsum) STEM_FWD(float, true); else STEM_FWD(float, false); }
   else if (dtype == UNET_BF16) { if (colsum) STEM_FWD(__nv_bfloat16, true); else STEM_FWD(__nv_bfloat16, false); }
 #undef STEM_FWD
@@ -281,5 +358,22 @@ extern "C" int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const 
                                                         N, H, W, th, tw);
   else return set_error(UNET_EINVAL, "stem_bwd: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("stem_bwd");
+  return UNET_OK;
+}
+
+extern "C" int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, const float* coef, const float* d3,
+                                    const float* wp, float* dwp, void* dd, int64_t M, int dtype, void* stream) {
+  UNET_REQUIRE(g && z && coef && d3 && wp && dwp && dd && M > 0 && ldg >= kStemCout, UNET_EINVAL, "stem_bwd_folded: bad argument");
+  UNET_REQUIRE(ldg % 8 == 0 && aligned16(g) && aligned16(z) && aligned16(wp) && aligned16(coef), UNET_EALIGN,
+               "stem_bwd_folded: g / z / wp / coef must be 16B aligned, ldg%%8==0");
+  const unsigned grid = (unsigned)i64min(ceil_div(M, 128), (int64_t)sm_count() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_F32)
+    stem_bwd_folded_kernel<float><<<grid, 256, 0, st>>>((const float*)g, ldg, (const float*)z, coef, d3, wp, dwp, (float*)dd, M);
+  else if (dtype == UNET_BF16)
+    stem_bwd_folded_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, ldg, (const __nv_bfloat16*)z, coef, d3, wp, dwp,
+                                                               (__nv_bfloat16*)dd, M);
+  else return set_error(UNET_EINVAL, "stem_bwd_folded: bad dtype %d", dtype);
+  UNET_LAUNCH_CHECK("stem_bwd_folded");
   return UNET_OK;
 }

@@ -418,7 +418,8 @@ class UNetEngine:
         if self.use_bn:
             scale, shift, smean, srstd = self._bn(prefix)
             if stem:
-                ops.stem_fwd(x, wd, wp, z, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
+                d3 = pl.buf(prefix + "/d3", (B, h, w, cin), torch.float32) if self._folds(prefix) else None
+                ops.stem_fwd(x, wd, wp, z, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c], d_out=d3)
             else:
                 self._pw_fwd(prefix, d, z, epilogue=ops.EPI_STATS, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])
             ops.bn_finalize(self.colstats[0, o:o + c], self.colstats[1, o:o + c], B * h * w,
@@ -458,9 +459,12 @@ class UNetEngine:
         if folded:
             sums, sd, G, coef, wab, bias = self._fold_bufs(prefix)
             gamma, beta = self.wview(f"{prefix}_bn/gamma"), self.wview(f"{prefix}_bn/beta")
-            if stem:   # the reductions are already there: only the apply pass remains in front of the fused first-block kernel
-                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta)
-                ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True)
+            if stem:   # streaming first-block backward: dz = A*g + B*z + K in registers, then a 3-channel depthwise weight gradient
+                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef)
+                dd3 = pl.buf(prefix + "/dd3", (B, h, w, cin))
+                ops.stem_bwd_folded(dy, z, coef, pl.t[prefix + "/d3"], self._mat(f"{prefix}_sepconv/pointwise_kernel"), gwp, dd3)
+                ops.dwconv3x3_bwd_weight(x, dd3, self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g))
+                return None
             else:      # dz = A*g + B*z + K never exists: both contractions read [g | z]
                 ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef,
                                 w=self._mat(f"{prefix}_sepconv/pointwise_kernel"), wab=wab, bias=bias)

@@ -181,15 +181,18 @@ def stem_supported(cin: int, cout: int) -> bool:
 
 
 def stem_fwd(x: torch.Tensor, wd9c: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, scale=None, shift=None,
-             relu: bool = False, colsum=None, colsq=None) -> None:
-    """enc1_block1_sepconv (u_net.py:63-66 on the RGB image): depthwise 3x3 + pointwise 3->64 in one kernel."""
+             relu: bool = False, colsum=None, colsq=None, d_out: Optional[torch.Tensor] = None) -> None:
+    """enc1_block1_sepconv (u_net.py:63-66 on the RGB image): depthwise 3x3 + pointwise 3->64 in one kernel.
+    d_out (fp32 [N,H,W,3]): also keep the depthwise output (input of stem_bwd_folded)."""
     n, h, w, cin, ldx = _nhwc(x, "x")
     _, _, _, cout, ldo = _nhwc(out, "out")
     if ldx != cin or x.dtype != out.dtype:
         raise ValueError("stem_fwd: x must be contiguous and share out's dtype")
-    _f32(wd9c, "wd9c"); _f32(wp, "wp"); _f32(scale, "scale"); _f32(shift, "shift")
+    _f32(wd9c, "wd9c"); _f32(wp, "wp"); _f32(scale, "scale"); _f32(shift, "shift"); _f32(d_out, "d_out")
+    if d_out is not None and d_out.numel() != n * h * w * cin:
+        raise ValueError("stem_fwd: d_out must hold N*H*W*Cin floats")
     _call("unet_stem_fwd", _p(x), _p(wd9c), _p(wp), _p(out), ldo, n, h, w, cin, cout, _dt(x), _p(scale), _p(shift),
-          int(relu), _p(colsum), _p(colsq), _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, out),
+          int(relu), _p(colsum), _p(colsq), _p(d_out), _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, out, d_out),
           flops=(18 * cin + 2 * cin * cout) * n * h * w)
 
 
@@ -202,6 +205,20 @@ def stem_bwd(x: torch.Tensor, dz: torch.Tensor, wd9c, wp, dwd9c, dwp) -> None:
         _f32(t, nm)
     _call("unet_stem_bwd", _p(x), _p(dz), lddz, _p(wd9c), _p(wp), _p(dwd9c), _p(dwp), n, h, w, cin, cout, _dt(x),
           _stream(), tag=f"{n}x{h}x{w}x{cin}->{cout}", nbytes=_nbytes(x, dz), flops=(36 * cin + 4 * cin * cout) * n * h * w)
+
+
+def stem_bwd_folded(g: torch.Tensor, z: torch.Tensor, coef: torch.Tensor, d3: torch.Tensor, wp, dwp, dd: torch.Tensor) -> None:
+    """First block backward with BatchNormalization backward folded in: dwp += d3^T dz, dd = dz Wp^T, dz = A*g + B*z + K."""
+    n, h, w, cout, ldg = _nhwc(g, "g")
+    if not z.is_contiguous() or z.shape != g.shape or z.dtype != g.dtype or dd.dtype != g.dtype or not dd.is_contiguous():
+        raise ValueError("stem_bwd_folded: z must be contiguous like g; dd contiguous of the same dtype")
+    for t, nm in ((coef, "coef"), (d3, "d3"), (wp, "wp"), (dwp, "dwp")):
+        _f32(t, nm)
+    m = n * h * w
+    if coef.numel() != 3 * cout or d3.numel() != 3 * m or dd.numel() != 3 * m:
+        raise ValueError("stem_bwd_folded: coef [3,64], d3 [M,3], dd [M,3]")
+    _call("unet_stem_bwd_folded", _p(g), ldg, _p(z), _p(coef), _p(d3), _p(wp), _p(dwp), _p(dd), m, _dt(g), _stream(),
+          tag=f"{n}x{h}x{w}x3->{cout}", nbytes=_nbytes(g, z, d3, dd), flops=12 * 3 * cout * m // 3)
 
 
 # ------------------------------------------------------------------------------------------------ fused conv_block (inference)

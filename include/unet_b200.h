@@ -133,7 +133,8 @@ int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy,
 int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, void* out, int64_t ldo,
                   int N, int H, int W, int Cin, int Cout, int dtype,
                   const float* scale, const float* shift, int relu, double* colsum, double* colsq,
-                  float* d_out /* optional fp32 [N*H*W,3]: the depthwise output, kept for unet_stem_bwd_folded */, void* stream);
+                  float* d_out /* optional fp32 [N*H*W,3] workspace: the depthwise output is materialised there (kept for
+                                  unet_stem_bwd_folded) and the pointwise half runs as a barrier-free stream over it */, void* stream);
 /* given dz = gradient w.r.t. pw(dw(x)): dwp[3,64] += d^T dz (d = dw(x) recomputed on chip), dwd9c[3,3,3] += x (*) (dz Wp^T) */
 int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const float* wd9c, const float* wp,
                   float* dwd9c, float* dwp, int N, int H, int W, int Cin, int Cout, int dtype, void* stream);

@@ -258,6 +258,17 @@ def test_stem_bwd_folded(dtype):
     d3 = torch.empty((n, h, w, 3), device="cuda")
     ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), out, colsum=cs, colsq=cq, d_out=d3)
     np.testing.assert_allclose(host(d3), d, rtol=1e-5, atol=1e-5)
+    # the streaming pair (depthwise into d3, barrier-free pointwise) against the tiled kernel: statistics and BN+ReLU modes
+    out_t = torch.empty_like(out); cs_t = torch.zeros_like(cs); cq_t = torch.zeros_like(cq)
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), out_t, colsum=cs_t, colsq=cq_t)
+    np.testing.assert_allclose(host(out), host(out_t), **tol(dtype))
+    np.testing.assert_allclose(cs.cpu().numpy(), cs_t.cpu().numpy(), rtol=1e-3, atol=5e-1)
+    np.testing.assert_allclose(cq.cpu().numpy(), cq_t.cpu().numpy(), rtol=1e-3, atol=5e-1)
+    sc = RNG.uniform(0.5, 1.5, 64).astype(np.float32); sh = RNG.standard_normal(64).astype(np.float32)
+    buf_s = torch.zeros((n, h, w, 128), device="cuda", dtype=dtype); buf_t = torch.zeros_like(buf_s)
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), buf_s[..., 64:], scale=dev(sc), shift=dev(sh), relu=True, d_out=d3)
+    ops.stem_fwd(xd, dev(wd.reshape(9, 3)), dev(wp), buf_t[..., 64:], scale=dev(sc), shift=dev(sh), relu=True)
+    np.testing.assert_allclose(host(buf_s), host(buf_t), **tol(dtype))
     gwp = torch.zeros((3, 64), device="cuda"); dd = torch.empty((n, h, w, 3), device="cuda", dtype=dtype)
     ops.stem_bwd_folded(dev(g, dtype), dev(z, dtype), dev(coef), d3, dev(wp), gwp, dd)
     np.testing.assert_allclose(host(gwp), d.reshape(-1, 3).T @ dz.reshape(-1, 64), rtol=1e-3, atol=1e-2)

@@ -119,6 +119,101 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
   }
 }
 
+// ------------------------------------------------------------------------------------------------ streaming forward
+// The same first block as two barrier-free kernels: (1) depthwise 3x3 on the 3-channel image, one pixel per thread, fp32
+// result d3 (12 B per pixel: 2 % of the 64-channel output), (2) pointwise 3 -> 64 as a pure stream over d3 whose only real
+// traffic is the 128 B/pixel output; 8 lanes x 8 channels per pixel, a warp stores 4 pixels x 128 B contiguous.
+template <typename T>
+__global__ void __launch_bounds__(256)
+stem_dw_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, float* __restrict__ d3, int N, int H, int W) {
+  __shared__ float s_wd[9 * kStemCin];
+  if (threadIdx.x < 9 * kStemCin) s_wd[threadIdx.x] = wd9c[threadIdx.x];
+  __syncthreads();
+  const int64_t M = (int64_t)N * H * W;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(m % W); const int64_t q = m / W; const int i = (int)(q % H);
+    float d[kStemCin] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int ii = i + a - 1;
+      if (ii < 0 || ii >= H) continue;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const int jj = j + b - 1;
+        if (jj < 0 || jj >= W) continue;
+        const T* px = x + (m + (int64_t)(a - 1) * W + (b - 1)) * kStemCin;
+#pragma unroll
+        for (int ci = 0; ci < kStemCin; ++ci) d[ci] = fmaf(to_f32(px[ci]), s_wd[(a * 3 + b) * kStemCin + ci], d[ci]);
+      }
+    }
+    d3[m * 3] = d[0]; d3[m * 3 + 1] = d[1]; d3[m * 3 + 2] = d[2];
+  }
+}
+
+template <typename T, bool STATS>
+__global__ void __launch_bounds__(256, 4)
+stem_pw_kernel(const float* __restrict__ d3, const float* __restrict__ wp, T* __restrict__ out, int64_t ldo, int64_t M,
+               const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+               double* __restrict__ colsum, double* __restrict__ colsq) {
+  __shared__ float s_stat[2 * kStemCout];
+  if (threadIdx.x < 2 * kStemCout) s_stat[threadIdx.x] = 0.f;
+  const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  float w[kStemCin][8], sa[8], sb[8];            // STATS: running sum / sum of squares;  else: scale / shift
+#pragma unroll
+  for (int ci = 0; ci < kStemCin; ++ci) load8(wp + ci * kStemCout + cg * 8, w[ci]);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sa[j] = STATS ? 0.f : 1.f; sb[j] = 0.f; }
+  if (!STATS && scale) load8(scale + cg * 8, sa);
+  if (!STATS && shift) load8(shift + cg * 8, sb);
+  constexpr int U = 8;
+  const int base = threadIdx.x & 24;              // first lane of this pixel's 8-lane group
+  const int64_t stride = (int64_t)gridDim.x * 32 * U;
+  for (int64_t m0 = (int64_t)blockIdx.x * 32 * U; m0 < M; m0 += stride) {
+    float dv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = m0 + u * 32 + slot;
+      dv[u] = (m < M && cg < 3) ? __ldg(d3 + m * 3 + cg) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t m = m0 + u * 32 + slot;
+      const float d0 = __shfl_sync(0xffffffffu, dv[u], base), d1 = __shfl_sync(0xffffffffu, dv[u], base + 1),
+                  d2 = __shfl_sync(0xffffffffu, dv[u], base + 2);
+      if (m >= M) continue;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = fmaf(d2, w[2][j], fmaf(d1, w[1][j], d0 * w[0][j]));
+        if (!STATS) { v = fmaf(v, sa[j], sb[j]); if (relu) v = fmaxf(v, 0.f); }
+        o[j] = v;
+      }
+      store8(out + m * ldo + cg * 8, o);
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float r = round_to<T>(o[j]); sa[j] += r; sb[j] = fmaf(r, r, sb[j]); }
+      }
+    }
+  }
+  if (STATS) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], 8); sa[j] += __shfl_xor_sync(0xffffffffu, sa[j], 16);
+      sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], 8); sb[j] += __shfl_xor_sync(0xffffffffu, sb[j], 16);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { atomicAdd(&s_stat[cg * 8 + j], sa[j]); atomicAdd(&s_stat[kStemCout + cg * 8 + j], sb[j]); }
+    }
+    __syncthreads();
+    if (threadIdx.x < kStemCout) {
+      atomicAdd(&colsum[threadIdx.x], (double)s_stat[threadIdx.x]);
+      atomicAdd(&colsq[threadIdx.x], (double)s_stat[kStemCout + threadIdx.x]);
+    }
+  }
+}
+
 template <typename T> struct StemRaw;
 template <> struct StemRaw<__nv_bfloat16> { uint4 a; };
 template <> struct StemRaw<float> { float4 a, b; };
@@ -333,6 +428,20 @@ extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, 
   const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 8);
   cudaStream_t st = (cudaStream_t)stream;
   UNET_REQUIRE(!(colsum && (scale || shift)), UNET_EINVAL, "stem_fwd: statistics are taken on the raw contraction (no scale/shift)");
+  if (d_out) {     // streaming pair: depthwise into the caller's d workspace, then a barrier-free pointwise stream
+    const int64_t M = (int64_t)N * H * W;
+    const unsigned g1 = (unsigned)i64min(ceil_div(M, 256), (int64_t)sm_count() * 32);
+    const unsigned g2 = (unsigned)i64min(ceil_div(M, 256), (int64_t)sm_count() * 16);
+#define STEM_STREAM(T) do { stem_dw_kernel<T><<<g1, 256, 0, st>>>((const T*)x, wd9c, d_out, N, H, W); \
+      if (colsum) stem_pw_kernel<T, true><<<g2, 256, 0, st>>>(d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); \
+      else stem_pw_kernel<T, false><<<g2, 256, 0, st>>>(d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); } while (0)
+    if (dtype == UNET_F32) STEM_STREAM(float);
+    else if (dtype == UNET_BF16) STEM_STREAM(__nv_bfloat16);
+    else return set_error(UNET_EINVAL, "stem_fwd: bad dtype %d", dtype);
+#undef STEM_STREAM
+    UNET_LAUNCH_CHECK("stem_fwd(stream)");
+    return UNET_OK;
+  }
 #define STEM_FWD(T, S) stem_fwd_kernel<T, S><<<grid, 256, 0, st>>>((const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw, d_out)
   if (dtype == UNET_F32) { if (colsum) STEM_FWD(float, true); else STEM_FWD(float, false); }
   else if (dtype == UNET_BF16) { if (colsum) STEM_FWD(__nv_bfloat16, true); else STEM_FWD(__nv_bfloat16, false); }

@@ -283,7 +283,8 @@ class UNetEngine:
             o, c = self._bn_off[prefix]
             ops.stem_fwd(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel"), y,
                          scale=self.fold[0, o:o + c] if self.use_bn else None,
-                         shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True)
+                         shift=self.fold[1, o:o + c] if self.use_bn else self.wview(f"{prefix}_sepconv/bias"), relu=True,
+                         d_out=pl.buf(prefix + "/d3", (B, h, w, cin), torch.float32))
             return y
         if self.fuse_sepconv and ops.sepconv_fused_supported(x, y.shape[-1]):
             # whole conv_block in one kernel: the depthwise result is produced on chip as the GEMM's A operand
@@ -418,7 +419,7 @@ class UNetEngine:
         if self.use_bn:
             scale, shift, smean, srstd = self._bn(prefix)
             if stem:
-                d3 = pl.buf(prefix + "/d3", (B, h, w, cin), torch.float32) if self._folds(prefix) else None
+                d3 = pl.buf(prefix + "/d3", (B, h, w, cin), torch.float32)
                 ops.stem_fwd(x, wd, wp, z, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c], d_out=d3)
             else:
                 self._pw_fwd(prefix, d, z, epilogue=ops.EPI_STATS, colsum=self.colstats[0, o:o + c], colsq=self.colstats[1, o:o + c])

@@ -110,6 +110,20 @@ __device__ __forceinline__ float lds32f(uint32_t saddr) { float r; asm volatile(
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, float v) {
   asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
+// Per-thread asynchronous global -> shared copies (LDGSTS): bytes in flight without holding registers
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds128u(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
 // Packed fp32x2 arithmetic (sm_100a FFMA2 / FMUL2): two IEEE round-to-nearest FMAs per issued instruction, bit-identical
 // to two scalar fmaf() calls.  The depthwise kernels are issue-bound on the FMA pipe without it.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {

@@ -7,13 +7,14 @@
 // Probabilities are always produced in fp32 from the fp32 accumulator (MeanIoU in train.py:231 truncates
 // probabilities to int, so they must not be rounded through bf16).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace unet {
 
 constexpr int kHeadMaxK = 512;
 
 template <typename T, int MAXC>
-__global__ void __launch_bounds__(256, MAXC == 1 ? 3 : 1)
+__global__ void __launch_bounds__(256, MAXC == 1 ? 4 : 1)
 head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
                 int64_t hw, int K, int C, int pix_per_block) {
@@ -40,11 +41,13 @@ head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
     float acc[U][MAXC];
     int64_t mrow[U];
     bool live[U];
+    float tq[U];                                        // binary head: y_true of the trip's pixels, requested with the x loads
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t p = p0 + u * 32 + slot;
       live[u] = p < p_end;
       mrow[u] = n * hw + (live[u] ? p : p_begin);
+      tq[u] = (MAXC == 1 && y_true && sub == 0) ? __ldg(y_true + mrow[u]) : 0.f;
 #pragma unroll
       for (int c = 0; c < MAXC; ++c) acc[u][c] = 0.f;
     }
@@ -91,7 +94,7 @@ head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
         for (int c = 0; c < MAXC; ++c) if (c < C) {
           probs[m * C + c] = pr[c];
           if (y_true) {
-            const float t = y_true[m * C + c];
+            const float t = MAXC == 1 ? tq[u] : y_true[m * C + c];
             si[c] = fmaf(t, pr[c], si[c]); st[c] += t; sp[c] += pr[c];
           }
         }
@@ -250,6 +253,89 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(&dw[i], s_dw[(i / C) * MAXC + (i % C)]);
   if (threadIdx.x < C) atomicAdd(&db[threadIdx.x], s_db[threadIdx.x]);
   if (SUMS) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) atomicAdd(&bn_sums[i], s_bn[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ binary head backward, streamed
+// The reference configuration (num_classes = 1, 64 channels, bf16): dx[m,k] = dz[m]*w[k], dw[k] += sum_m x[m,k]*dz[m],
+// db += sum dz, with dz = (ca*t + cb)*p*(1-p).  A thread owns 16 bytes of channels of one pixel slot and walks its pixels
+// through a ring of D per-thread cp.async slots (x, p and t): D*24 bytes per thread are in flight with no registers held,
+// which is what the register-staged kernel above lacks (it runs at 0.45 of the HBM peak).  SUMS: dx is ReLU-masked by
+// x > 0 and sum(dx), sum(dx*x) = w[k]*dw[k] (x >= 0 is its own mask) are accumulated for the folded BatchNormalization backward.
+constexpr int kH1D = 6;
+template <bool SUMS>
+__global__ void __launch_bounds__(256, 4)
+head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ probs,
+                        const float* __restrict__ y_true, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx,
+                        float* __restrict__ dw, float* __restrict__ db, int64_t hw, int pix_per_block, float* __restrict__ bn_sums) {
+  __shared__ uint4 ring_x[kH1D][256];
+  __shared__ float ring_p[kH1D][256], ring_t[kH1D][256];
+  __shared__ float s_red[3 * 64 + 1];              // dw | sum g | (unused) | db
+  for (int i = threadIdx.x; i < 3 * 64 + 1; i += blockDim.x) s_red[i] = 0.f;
+  __syncthreads();
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+  const float ca = coef[n * 2], cb = coef[n * 2 + 1];
+  float wk[8], dwacc[8], s1[8];
+  load8(w + sub * 8, wk);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { dwacc[j] = 0.f; s1[j] = 0.f; }
+  float dbs = 0.f;
+  const uint32_t sx = smem_u32(&ring_x[0][threadIdx.x]), sp = smem_u32(&ring_p[0][threadIdx.x]), st = smem_u32(&ring_t[0][threadIdx.x]);
+  const int64_t first = p_begin + slot;
+  const int count = first < p_end ? (int)((p_end - first + 31) / 32) : 0;      // pixels of this thread
+  auto issue = [&](int i) {
+    if (i < count) {
+      const int64_t m = n * hw + first + (int64_t)i * 32;
+      const int sl = i % kH1D;
+      cp_async16(sx + sl * (256 * 16), x + m * 64 + sub * 8);
+      cp_async4(sp + sl * (256 * 4), probs + m);
+      cp_async4(st + sl * (256 * 4), y_true + m);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < kH1D; ++i) issue(i);
+  for (int i = 0; i < count; ++i) {
+    cp_async_wait<kH1D - 1>();
+    const int sl = i % kH1D;
+    const uint4 raw = lds128u(sx + sl * (256 * 16));
+    const float pr = lds32f(sp + sl * (256 * 4)), t = lds32f(st + sl * (256 * 4));
+    const int64_t m = n * hw + first + (int64_t)i * 32;
+    const float dz = fmaf(ca, t, cb) * pr * (1.f - pr);
+    const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
+      dwacc[2 * q] = fmaf(v0, dz, dwacc[2 * q]); dwacc[2 * q + 1] = fmaf(v1, dz, dwacc[2 * q + 1]);
+      float g0 = dz * wk[2 * q], g1 = dz * wk[2 * q + 1];
+      if (SUMS) { g0 = v0 > 0.f ? g0 : 0.f; g1 = v1 > 0.f ? g1 : 0.f; s1[2 * q] += g0; s1[2 * q + 1] += g1; }
+      o[2 * q] = g0; o[2 * q + 1] = g1;
+    }
+    store8(dx + m * 64 + sub * 8, o);
+    if (sub == 0) dbs += dz;
+    issue(i + kH1D);
+  }
+  cp_async_wait<0>();
+  // lanes 8 apart share `sub`
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = dwacc[j], b = s1[j];
+    a += __shfl_xor_sync(0xffffffffu, a, 8); a += __shfl_xor_sync(0xffffffffu, a, 16);
+    if (SUMS) { b += __shfl_xor_sync(0xffffffffu, b, 8); b += __shfl_xor_sync(0xffffffffu, b, 16); }
+    if ((threadIdx.x & 31) < 8) { atomicAdd(&s_red[sub * 8 + j], a); if (SUMS) atomicAdd(&s_red[64 + sub * 8 + j], b); }
+  }
+  dbs = warp_sum(dbs);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_red[192], dbs);
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const float dwk = s_red[threadIdx.x];
+    atomicAdd(&dw[threadIdx.x], dwk);
+    if (SUMS) { atomicAdd(&bn_sums[threadIdx.x], s_red[64 + threadIdx.x]); atomicAdd(&bn_sums[64 + threadIdx.x], w[threadIdx.x] * dwk); }
+  }
+  if (threadIdx.x == 0) atomicAdd(&db[0], s_red[192]);
 }
 
 // ------------------------------------------------------------------------------------------------ multi-class head (2 <= C <= 8)
@@ -499,6 +585,13 @@ extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const f
   dim3 grid; int ppb;
   head_grid(M / hw, hw, &grid, &ppb, 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64 && dx && lddx == 64) {     // the reference head: streamed kernel
+    head_grid(M / hw, hw, &grid, &ppb, 16);
+    if (bn_sums) head1_bwd_stream_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums);
+    else head1_bwd_stream_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums);
+    UNET_LAUNCH_CHECK("head_bwd(stream)");
+    return UNET_OK;
+  }
 #define LAUNCH(T, MC) do { if (bn_sums) head_bwd_kernel<T, MC, true><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); \
                            else head_bwd_kernel<T, MC, false><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); } while (0)
 #define LAUNCH_MC(T) head_bwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums)

@@ -255,6 +255,69 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
   if (SUMS) for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) atomicAdd(&bn_sums[i], s_bn[i]);
 }
 
+// ------------------------------------------------------------------------------------------------ binary head forward, streamed
+// probs[m] = sigmoid(x[m,:] . w + b) and the per-image Dice sums (I, T, P), same cp.async ring as the backward kernel below.
+constexpr int kH1FD = 8;
+__global__ void __launch_bounds__(256, 4)
+head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                        float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
+                        int64_t hw, int pix_per_block) {
+  __shared__ uint4 ring_x[kH1FD][256];
+  __shared__ float ring_t[kH1FD][256];
+  __shared__ double s_sum[3];
+  if (threadIdx.x < 3) s_sum[threadIdx.x] = 0.0;
+  __syncthreads();
+  const int64_t n = blockIdx.y;
+  const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
+  const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
+  const int64_t p_end = i64min(hw, p_begin + pix_per_block);
+  float wk[8];
+  load8(w + sub * 8, wk);
+  const float bias = b ? __ldg(b) : 0.f;
+  float si = 0.f, st_ = 0.f, sp_ = 0.f;
+  const uint32_t sx = smem_u32(&ring_x[0][threadIdx.x]), stq = smem_u32(&ring_t[0][threadIdx.x]);
+  const int64_t first = p_begin + slot;
+  const int count = first < p_end ? (int)((p_end - first + 31) / 32) : 0;
+  auto issue = [&](int i) {
+    if (i < count) {
+      const int64_t m = n * hw + first + (int64_t)i * 32;
+      const int sl = i % kH1FD;
+      cp_async16(sx + sl * (256 * 16), x + m * 64 + sub * 8);
+      if (y_true && sub == 0) cp_async4(stq + sl * (256 * 4), y_true + m);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < kH1FD; ++i) issue(i);
+  for (int i = 0; i < count; ++i) {
+    cp_async_wait<kH1FD - 1>();
+    const int sl = i % kH1FD;
+    const uint4 raw = lds128u(sx + sl * (256 * 16));
+    const float t = (y_true && sub == 0) ? lds32f(stq + sl * (256 * 4)) : 0.f;
+    const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc = fmaf(__uint_as_float(u[q] << 16), wk[2 * q], acc);
+      acc = fmaf(__uint_as_float(u[q] & 0xffff0000u), wk[2 * q + 1], acc);
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0) {
+      const float pr = 1.f / (1.f + expf(-(acc + bias)));
+      probs[n * hw + first + (int64_t)i * 32] = pr;
+      si = fmaf(t, pr, si); st_ += t; sp_ += pr;
+    }
+    issue(i + kH1FD);
+  }
+  cp_async_wait<0>();
+  if (y_true && sums) {
+    const float a = warp_sum(si), bq = warp_sum(st_), cq = warp_sum(sp_);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_sum[0], (double)a); atomicAdd(&s_sum[1], (double)bq); atomicAdd(&s_sum[2], (double)cq); }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(&sums[n * 3 + threadIdx.x], s_sum[threadIdx.x]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ binary head backward, streamed
 // The reference configuration (num_classes = 1, 64 channels, bf16): dx[m,k] = dz[m]*w[k], dw[k] += sum_m x[m,k]*dz[m],
 // db += sum dz, with dz = (ca*t + cb)*p*(1-p).  A thread owns 16 bytes of channels of one pixel slot and walks its pixels
@@ -561,6 +624,11 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
   dim3 grid; int ppb;
   head_grid(M / hw, hw, &grid, &ppb);
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64) {     // the reference head: streamed kernel
+    head1_fwd_stream_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, probs, y_true, sums, hw, ppb);
+    UNET_LAUNCH_CHECK("head_fwd(stream)");
+    return UNET_OK;
+  }
 #define LAUNCH(T, MC) head_fwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
 #define LAUNCH_MC(T) head_fwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
   if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }

@@ -9,6 +9,7 @@
 // A CTA walks 8x32-pixel tiles (grid-stride); 256 threads; a thread owns 8 output channels of 8 pixels of the tile,
 // so a warp's 16-byte stores / loads cover 4 pixels x 128 B contiguous.
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace unet {
 
@@ -338,11 +339,17 @@ stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz,
 //   dwp[ci][co] += d[ci] * dz[co]        (d = depthwise output stored by the forward kernel, 3 floats per pixel)
 //   dd[ci]       = sum_co dz[co] * wp[ci][co]   (8-lane shuffle reduction) -> stored, 3 values per pixel
 // The depthwise weight gradient then is unet_dwconv3x3_bwd_weight(x, dd) on two 3-channel tensors.
+// ring depth: 4 (bf16) x (16 B of g + 16 B of z [+ 4 B of d]) per thread in flight; fp32 (parity path) halves it to fit 48 KB
 template <typename T>
 __global__ void __launch_bounds__(256, 2)
 stem_bwd_folded_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ z, const float* __restrict__ coef,
                        const float* __restrict__ d3, const float* __restrict__ wp, float* __restrict__ dwp, T* __restrict__ dd,
                        int64_t M) {
+  constexpr int kRaw = 8 * (int)sizeof(T);          // bytes of 8 channels
+  constexpr int kSbD = sizeof(T) == 2 ? 4 : 2;
+  __shared__ __align__(16) uint8_t ring_g[kSbD][256 * kRaw];
+  __shared__ __align__(16) uint8_t ring_z[kSbD][256 * kRaw];
+  __shared__ float ring_d[kSbD][256];
   __shared__ float s_gp[kStemCin * kStemCout];
   if (threadIdx.x < kStemCin * kStemCout) s_gp[threadIdx.x] = 0.f;
   __syncthreads();
@@ -355,42 +362,66 @@ stem_bwd_folded_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict
     for (int j = 0; j < 8; ++j) gp[ci][j] = 0.f;
   }
   load8(coef + cg * 8, ca); load8(coef + kStemCout + cg * 8, cb); load8(coef + 2 * kStemCout + cg * 8, ck);
-  constexpr int U = 4;
-  const int64_t stride = (int64_t)gridDim.x * 32 * U;
-  for (int64_t m0 = (int64_t)blockIdx.x * 32 * U; m0 < M; m0 += stride) {
-    StemRaw<T> graw[U], zraw[U];
-    float dv[U];
+  const uint32_t sg = smem_u32(&ring_g[0][threadIdx.x * kRaw]), sz = smem_u32(&ring_z[0][threadIdx.x * kRaw]),
+                 sd = smem_u32(&ring_d[0][threadIdx.x]);
+  const int64_t first = (int64_t)blockIdx.x * 32 + slot;          // this thread's pixels: first + i * gridDim.x * 32
+  const int64_t step = (int64_t)gridDim.x * 32;
+  const int count = first < M ? (int)((M - first + step - 1) / step) : 0;
+  const int base = threadIdx.x & 24;                // first lane of this pixel's 8-lane group (within the warp)
+  auto issue = [&](int i) {
+    if (i < count) {
+      const int64_t m = first + (int64_t)i * step;
+      const int sl = i % kSbD;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {                   // all loads of the trip first
-      const int64_t m = m0 + u * 32 + slot;
-      if (m < M) {
-        ldraw8(g + m * ldg + cg * 8, graw[u]); ldraw8(z + m * kStemCout + cg * 8, zraw[u]);
-        dv[u] = cg < 3 ? __ldg(d3 + m * 3 + cg) : 0.f;
-      } else { zero8(graw[u]); zero8(zraw[u]); dv[u] = 0.f; }
+      for (int q = 0; q < kRaw / 16; ++q) {
+        cp_async16(sg + sl * (256 * kRaw) + q * 16, reinterpret_cast<const uint8_t*>(g + m * ldg + cg * 8) + q * 16);
+        cp_async16(sz + sl * (256 * kRaw) + q * 16, reinterpret_cast<const uint8_t*>(z + m * kStemCout + cg * 8) + q * 16);
+      }
+      if (cg < 3) cp_async4(sd + sl * (256 * 4), d3 + m * 3 + cg);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int i = 0; i < kSbD; ++i) issue(i);
+  // every lane of a warp runs the same number of trips only if the pixel counts agree; lanes past their count idle in the shuffles
+  const int trips = __reduce_max_sync(0xffffffffu, count);
+  for (int i = 0; i < trips; ++i) {
+    cp_async_wait<kSbD - 1>();
+    const int sl = i % kSbD;
+    const bool live = i < count;
+    StemRaw<T> graw, zraw;
+    zero8(graw); zero8(zraw);
+    float dv = 0.f;
+    if (live) {
+      if (sizeof(T) == 2) {
+        const uint4 a = lds128u(sg + sl * (256 * kRaw)), bq = lds128u(sz + sl * (256 * kRaw));
+        *reinterpret_cast<uint4*>(&graw) = a; *reinterpret_cast<uint4*>(&zraw) = bq;
+      } else {
+        uint4* gq = reinterpret_cast<uint4*>(&graw); uint4* zq = reinterpret_cast<uint4*>(&zraw);
+        gq[0] = lds128u(sg + sl * (256 * kRaw)); gq[1] = lds128u(sg + sl * (256 * kRaw) + 16);
+        zq[0] = lds128u(sz + sl * (256 * kRaw)); zq[1] = lds128u(sz + sl * (256 * kRaw) + 16);
+      }
+      if (cg < 3) dv = lds32f(sd + sl * (256 * 4));
+    }
+    float gv[8], zv[8];
+    unraw8(graw, gv); unraw8(zraw, zv);
+    const float d0 = __shfl_sync(0xffffffffu, dv, base), d1 = __shfl_sync(0xffffffffu, dv, base + 1),
+                d2 = __shfl_sync(0xffffffffu, dv, base + 2);
+    float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dz = live ? fmaf(ca[j], gv[j], fmaf(cb[j], zv[j], ck[j])) : 0.f;
+      gp[0][j] = fmaf(d0, dz, gp[0][j]); gp[1][j] = fmaf(d1, dz, gp[1][j]); gp[2][j] = fmaf(d2, dz, gp[2][j]);
+      dd0 = fmaf(dz, w[0][j], dd0); dd1 = fmaf(dz, w[1][j], dd1); dd2 = fmaf(dz, w[2][j], dd2);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t m = m0 + u * 32 + slot;
-      float gv[8], zv[8];
-      unraw8(graw[u], gv); unraw8(zraw[u], zv);
-      const int base = threadIdx.x & 24;            // first lane of this pixel's 8-lane group (within the warp)
-      const float d0 = __shfl_sync(0xffffffffu, dv[u], base), d1 = __shfl_sync(0xffffffffu, dv[u], base + 1),
-                  d2 = __shfl_sync(0xffffffffu, dv[u], base + 2);
-      float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
-      const bool live = m < M;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dz = live ? fmaf(ca[j], gv[j], fmaf(cb[j], zv[j], ck[j])) : 0.f;
-        gp[0][j] = fmaf(d0, dz, gp[0][j]); gp[1][j] = fmaf(d1, dz, gp[1][j]); gp[2][j] = fmaf(d2, dz, gp[2][j]);
-        dd0 = fmaf(dz, w[0][j], dd0); dd1 = fmaf(dz, w[1][j], dd1); dd2 = fmaf(dz, w[2][j], dd2);
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {
-        dd0 += __shfl_xor_sync(0xffffffffu, dd0, o); dd1 += __shfl_xor_sync(0xffffffffu, dd1, o); dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);
-      }
-      if (live && cg < 3) dd[m * 3 + cg] = from_f32<T>(cg == 0 ? dd0 : (cg == 1 ? dd1 : dd2));
+    for (int o = 1; o < 8; o <<= 1) {
+      dd0 += __shfl_xor_sync(0xffffffffu, dd0, o); dd1 += __shfl_xor_sync(0xffffffffu, dd1, o); dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);
     }
+    if (live && cg < 3) dd[(first + (int64_t)i * step) * 3 + cg] = from_f32<T>(cg == 0 ? dd0 : (cg == 1 ? dd1 : dd2));
+    issue(i + kSbD);
   }
+  cp_async_wait<0>();
 #pragma unroll
   for (int ci = 0; ci < kStemCin; ++ci)
 #pragma unroll
@@ -475,7 +506,7 @@ extern "C" int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, c
   UNET_REQUIRE(g && z && coef && d3 && wp && dwp && dd && M > 0 && ldg >= kStemCout, UNET_EINVAL, "stem_bwd_folded: bad argument");
   UNET_REQUIRE(ldg % 8 == 0 && aligned16(g) && aligned16(z) && aligned16(wp) && aligned16(coef), UNET_EALIGN,
                "stem_bwd_folded: g / z / wp / coef must be 16B aligned, ldg%%8==0");
-  const unsigned grid = (unsigned)i64min(ceil_div(M, 128), (int64_t)sm_count() * 16);
+  const unsigned grid = (unsigned)i64min(ceil_div(M, 32 * 64), (int64_t)sm_count() * 12);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_F32)
     stem_bwd_folded_kernel<float><<<grid, 256, 0, st>>>((const float*)g, ldg, (const float*)z, coef, d3, wp, dwp, (float*)dd, M);

@@ -102,8 +102,9 @@ int         unet_device_check(int device);     /* UNET_OK iff the device is comp
 
 /* ---- SeparableConv2D, depthwise half (u_net.py:14-20) ---- */
 /* y[n,i,j,c] = sum_{a,b} x'[n,i+a-1,j+b-1,c] * w[a,b,c], zero 'same' padding.
-   x' = x, or max(x*in_scale[c]+in_shift[c],0) when in_scale != NULL (BN+ReLU of the producer fused into the load;
-   padding is zero in x' space).  flip=1 correlates with the 180-degree rotated kernel (= gradient w.r.t. input).
+   x' = x, or max(x*in_scale[c]+in_shift[c],0) when in_scale != NULL (BN+ReLU of the producer fused into the load, so the
+   producer's activation is never materialised; padding is zero in x' space: the TMA-strip kernel re-imposes it after the
+   transform).  flip=1 correlates with the 180-degree rotated kernel (= gradient w.r.t. input).
    drop (rate>0) multiplies the OUTPUT by the dropout mask (used by the input-gradient of a dropped tensor).
    colsum (fp32 [C], accumulated, may be NULL): column sums over (n,i,j) of the stored outputs — the rank-1 term of the
    folded BatchNormalization backward (unet_bn_bwd_wgrad_combine); TMA-strip path only, not with dropout. */
@@ -122,10 +123,13 @@ int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_
    sum(dx) and sum(dx * y) over (n,i,j) — the two reductions BatchNormalization backward needs — from the stored values.
    drop (rate>0) multiplies dx by the Dropout mask for channels >= drop_c_from (a multiple of the 128-byte channel block;
    the channels below are left to another reader of dx, e.g. unet_convt_bwd_gather).
+   x_scale/x_shift (fp32 [C], may be NULL): x is the producer's PRE-BatchNormalization output z and the activation
+   y = max(z*x_scale + x_shift, 0) is formed on load (the producer's BN+ReLU pass never materialises y); not with dropout.
    UNET_EUNSUPPORTED unless C % (8/sizeof(T)) == 0, C >= 8 and all views are 16-byte aligned. */
 int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                        void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
-                       int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from, void* stream);
+                       int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from,
+                       const float* x_scale, const float* x_shift, void* stream);
 
 /* ---- first conv_block, fused (enc1_block1_sepconv on the RGB image, u_net.py:14-20,63-66; Cin = 3, Cout = 64 only) ---- */
 /* out = pw(dw(x)) [* scale + shift, ReLU if relu]; x contiguous [N,H,W,3]; with colsum/colsq also the BN batch statistics

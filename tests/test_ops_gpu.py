@@ -143,6 +143,47 @@ def test_dwconv_bwd_fused_partial_dropout(dtype):
     np.testing.assert_allclose(host(dx), dx_ref * mult, **tol(dtype))
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 37, 45, 72), (2, 70, 33, 128), (1, 9, 100, 8)])
+def test_dwconv_fwd_affine_on_load(dtype, shape):
+    """TMA-strip kernel with the producer's BN+ReLU applied on load: zero padding lives in the transformed space"""
+    n, h, w, c = shape
+    z = RNG.standard_normal(shape).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, c).astype(np.float32); sh = (RNG.standard_normal(c) * 0.5 + 0.3).astype(np.float32)
+    zr = bf16_round(z) if dtype == torch.bfloat16 else z.astype(np.float64)
+    ref = R.dwconv3x3(np.maximum(zr * sc + sh, 0), wk.astype(np.float64))
+    y = torch.empty(shape, device="cuda", dtype=dtype); cs = torch.zeros(c, device="cuda")
+    ops.dwconv3x3(dev(z, dtype), dev(wk.reshape(9, -1)), y, in_scale=dev(sc), in_shift=dev(sh), colsum=cs)
+    np.testing.assert_allclose(host(y), ref, **tol(dtype))
+    np.testing.assert_allclose(host(cs), host(y).sum((0, 1, 2)), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mask", [False, True])
+def test_dwconv_bwd_fused_affine_on_load(dtype, mask):
+    """fused depthwise backward whose x stream is the producer's pre-BN tensor: y = relu(z*scale+shift) formed on load"""
+    n, h, w, c = 2, 37, 45, 72
+    z = RNG.standard_normal((n, h, w, c)).astype(np.float32); dy = RNG.standard_normal((n, h, w, c)).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, c).astype(np.float32); sh = (RNG.standard_normal(c) * 0.5).astype(np.float32)
+    zr, dyr = (bf16_round(z), bf16_round(dy)) if dtype == torch.bfloat16 else (z.astype(np.float64), dy.astype(np.float64))
+    yact = np.maximum(zr * sc + sh, 0)
+    dx_ref, dw_ref = R.dwconv3x3_bwd(yact, wk.astype(np.float64), dyr)
+    if mask:
+        dx_ref = dx_ref * (yact > 0)
+    dx = torch.empty((n, h, w, c), device="cuda", dtype=dtype); dw = torch.zeros((9, c), device="cuda")
+    sums = torch.zeros((2, c), device="cuda") if mask else None
+    ops.dwconv3x3_bwd(dev(z, dtype), dev(dy, dtype), dev(wk.reshape(9, -1)), dx, dw, relu_mask=mask, bn_sums=sums,
+                      x_scale=dev(sc), x_shift=dev(sh))
+    np.testing.assert_allclose(host(dx), dx_ref, **tol(dtype))
+    np.testing.assert_allclose(host(dw).reshape(3, 3, -1), dw_ref, rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+    if mask:
+        g = host(dx)
+        np.testing.assert_allclose(host(sums)[0], g.sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+        np.testing.assert_allclose(host(sums)[1], (g * yact).sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+
+
 def test_dwconv_fwd_colsum():
     for dtype in DTYPES:
         shape = (2, 37, 45, 72)

@@ -12,6 +12,7 @@ B, H, W = 64, 512, 512
 VARIANTS = {
     "all on": {},
     "no fold_bn_bwd": {"fold_bn_bwd": False},
+    "no fuse_bn_act": {"fuse_bn_act": False},
     "no defer_dropout": {"defer_dropout": False},
     "no fuse_dw_bwd": {"fuse_dw_bwd": False, "fold_bn_bwd": False},
 }
@@ -23,9 +24,9 @@ eng.use_graphs = True
 res = {k: [] for k in VARIANTS}
 for rnd in range(3):
     for name, flags in VARIANTS.items():
-        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd"):
+        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act"):
             setattr(eng, k, flags.get(k, True))
-        eng._graphs.clear()
+        eng.release_plans()
         for _ in range(3):
             eng.train_step(x, y)
         torch.cuda.synchronize()

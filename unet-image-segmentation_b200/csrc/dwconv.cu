@@ -131,11 +131,14 @@ __device__ __forceinline__ uint2 pack8(const float (&v)[2], float*) {
   return make_uint2(__float_as_uint(v[0]), __float_as_uint(v[1]));
 }
 
-template <typename T, bool DROP, bool SUMS>
+// AFFINE: the input tensor is the producer's PRE-BatchNormalization output z; x' = max(z*in_scale + in_shift, 0) is formed in
+// registers on every load (3 columns x the thread's channels per row), and the 'same' padding is re-imposed in x' space:
+// rows outside the image and the two halo columns at the image border are forced to zero after the transform.
+template <typename T, bool DROP, bool SUMS, bool AFFINE>
 __global__ void __launch_bounds__(StripCfg<T>::kThreads, 1)
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
                        int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp,
-                       float* __restrict__ colsum) {
+                       float* __restrict__ colsum, const float* __restrict__ in_scale, const float* __restrict__ in_shift) {
   using Cfg = StripCfg<T>;
   constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
@@ -195,6 +198,21 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   }
   uint32_t seed = 0u;
   if (DROP) seed = drop_seed(dp);
+  float2 asc[NP], ash[NP];                          // AFFINE: scale / shift of this thread's channels
+  bool l_ok = true, r_ok = true;
+  if (AFFINE) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { asc[j] = make_float2(0.f, 0.f); ash[j] = make_float2(0.f, 0.f); }
+    if (c < C) {
+      if (NV == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in_scale + c)), b = __ldg(reinterpret_cast<const float4*>(in_shift + c));
+        asc[0] = make_float2(a.x, a.y); asc[1 % NP] = make_float2(a.z, a.w); ash[0] = make_float2(b.x, b.y); ash[1 % NP] = make_float2(b.z, b.w);
+      } else {
+        asc[0] = __ldg(reinterpret_cast<const float2*>(in_scale + c)); ash[0] = __ldg(reinterpret_cast<const float2*>(in_shift + c));
+      }
+    }
+    l_ok = w0 + px - 1 >= 0; r_ok = w0 + px + 1 < W;
+  }
   float2 prev[NP], cur[NP], csum[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) { prev[j] = make_float2(0.f, 0.f); cur[j] = make_float2(0.f, 0.f); csum[j] = make_float2(0.f, 0.f); }
@@ -220,6 +238,16 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     for (int rr = 0; rr < RH; ++rr, ++r_in, yptr += yrow) {
       float2 a[NP], b[NP], cc[NP];
       unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc);
+      if (AFFINE) {
+        const bool row_ok = (unsigned)r_in < (unsigned)H;     // uniform over the CTA
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float2 ta = fma2(a[j], asc[j], ash[j]), tb = fma2(b[j], asc[j], ash[j]), tc = fma2(cc[j], asc[j], ash[j]);
+          a[j]  = (row_ok && l_ok) ? make_float2(fmaxf(ta.x, 0.f), fmaxf(ta.y, 0.f)) : make_float2(0.f, 0.f);
+          b[j]  = row_ok ? make_float2(fmaxf(tb.x, 0.f), fmaxf(tb.y, 0.f)) : make_float2(0.f, 0.f);
+          cc[j] = (row_ok && r_ok) ? make_float2(fmaxf(tc.x, 0.f), fmaxf(tc.y, 0.f)) : make_float2(0.f, 0.f);
+        }
+      }
       if (r_in > h0 && r_in <= h1 && live) {   // output row r_in-1 is complete once kernel row 2 has seen input row r_in
         float o[NV];
 #pragma unroll
@@ -288,27 +316,31 @@ static int pick_seg_rows(int N, int H, int ntw, int ncb, int min_rows, int64_t w
 
 template <typename T>
 static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
-                               int flip, DropArgs dp, float* colsum, cudaStream_t st) {
+                               int flip, DropArgs dp, float* colsum, const float* in_scale, const float* in_shift, cudaStream_t st) {
   using Cfg = StripCfg<T>;
   UNET_REQUIRE(!(colsum && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum and dropout cannot be combined");
+  UNET_REQUIRE(!(in_scale && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: input affine and dropout cannot be combined");
   CUtensorMap tm;
   if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
-  static SmemAttrOnce once_plain, once_drop, once_sums;
-  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_sums, dwconv3x3_strip_kernel<T, false, true>, Cfg::kSmemBytes);
+  static SmemAttrOnce once_plain, once_drop, once_sums, once_aff, once_aff_sums;
+  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_sums, dwconv3x3_strip_kernel<T, false, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff, dwconv3x3_strip_kernel<T, false, false, true>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff_sums, dwconv3x3_strip_kernel<T, false, true, true>, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_fwd: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
   const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6);
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
-  if (dp.on)
-    dwconv3x3_strip_kernel<T, true, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, nullptr);
-  else if (colsum)
-    dwconv3x3_strip_kernel<T, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, colsum);
-  else
-    dwconv3x3_strip_kernel<T, false, false><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, nullptr);
+#define UNET_DWF(D_, S_, A_) dwconv3x3_strip_kernel<T, D_, S_, A_><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+      tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, colsum, in_scale, in_shift)
+  if (dp.on) UNET_DWF(true, false, false);
+  else if (in_scale) { if (colsum) UNET_DWF(false, true, true); else UNET_DWF(false, false, true); }
+  else if (colsum) UNET_DWF(false, true, false);
+  else UNET_DWF(false, false, false);
+#undef UNET_DWF
   UNET_LAUNCH_CHECK("dwconv3x3_fwd(strip)");
   return UNET_OK;
 }
@@ -349,8 +381,8 @@ static int dw_fwd_launch(const void* x, int64_t ldx, const float* w9c, void* y, 
                          int flip, const float* in_scale, const float* in_shift, DropArgs dp, float* colsum, cudaStream_t st) {
   const bool vec = (C % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && aligned16(x) && aligned16(y) &&
                    aligned16(w9c) && (!in_scale || (aligned16(in_scale) && aligned16(in_shift)));
-  if (vec && !in_scale)      // the TMA path pads with zeros in INPUT space, which is wrong under a fused input affine
-    return dw_fwd_strip_launch<T>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, st);
+  if (vec && !(in_scale && dp.on))   // TMA strips; a fused input affine re-imposes the zero padding after the transform
+    return dw_fwd_strip_launch<T>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, in_scale, in_shift, st);
   UNET_REQUIRE(!colsum, UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum needs the strip path (C%%8==0, 16B-aligned views, no input affine)");
   if (vec) {
     // rows per thread: long segments amortise the 2 halo rows; shrink until the grid covers the machine twice
@@ -663,12 +695,12 @@ template <typename T> struct BwCfg {
   static constexpr int kSmemBytes = S * kStageBytes + 11 * CB * 4 + 2 * S * 8 + 128;
 };
 
-template <typename T, bool DROP, bool RELU_MASK>
+template <typename T, bool DROP, bool RELU_MASK, bool AFFINE>
 __global__ void __launch_bounds__(BwCfg<T>::kThreads, 1)
 dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
                            const float* __restrict__ w9c, T* __restrict__ dx, int64_t lddx, float* __restrict__ dw9c,
                            float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp,
-                           int drop_c_from) {
+                           int drop_c_from, const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
   using Cfg = BwCfg<T>;
   constexpr int NV = Cfg::NV, NP = NV / 2, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
@@ -727,6 +759,21 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
   uint32_t seed = 0u;
   if (DROP) seed = drop_seed(dp);
   const float2 zero2 = make_float2(0.f, 0.f);
+  // AFFINE: the x stream is the producer's pre-BN output z; the activation y = max(z*scale + shift, 0) is formed on load.
+  // Columns past W and channels past C get scale = shift = 0, i.e. y = 0 there (what the TMA zero fill gives without AFFINE).
+  float2 asc[NP], ash[NP];
+  if (AFFINE) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { asc[j] = zero2; ash[j] = zero2; }
+    if (live) {
+      if (NV == 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x_scale + c)), b = __ldg(reinterpret_cast<const float4*>(x_shift + c));
+        asc[0] = make_float2(a.x, a.y); asc[1 % NP] = make_float2(a.z, a.w); ash[0] = make_float2(b.x, b.y); ash[1 % NP] = make_float2(b.z, b.w);
+      } else {
+        asc[0] = __ldg(reinterpret_cast<const float2*>(x_scale + c)); ash[0] = __ldg(reinterpret_cast<const float2*>(x_shift + c));
+      }
+    }
+  }
   float2 acc[9][NP], prev[NP], cur[NP], xm[NP], x0[NP], s1[NP], s2[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
@@ -756,6 +803,13 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
     for (int rr = 0; rr < RH; ++rr, ++t, optr += orow) {
       float2 a[NP], b[NP], cc[NP], xp[NP];
       unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc); unpack8<T>(rx[rr], xp);
+      if (AFFINE) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float2 ty = fma2(xp[j], asc[j], ash[j]);
+          xp[j] = make_float2(fmaxf(ty.x, 0.f), fmaxf(ty.y, 0.f));
+        }
+      }
       const bool xp_dead = EDGE && !((t + 1 >= h0) && (t + 1 < h1));   // x rows of other segments belong to other strips
 #pragma unroll
       for (int j = 0; j < NP; ++j) {
@@ -844,26 +898,30 @@ template <typename T> static bool dw_strip_ok(const void* a, int64_t lda, const 
 template <typename T>
 static int dw_bwd_strip_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c, void* dx, int64_t lddx,
                                float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, int drop_c_from,
-                               cudaStream_t st) {
+                               const float* x_scale, const float* x_shift, cudaStream_t st) {
   using Cfg = BwCfg<T>;
   CUtensorMap tmD, tmX;
   if (int e = make_nhwc_tmap<T>(&tmD, dy, lddy, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_bwd(dy)")) return e;
   if (int e = make_nhwc_tmap<T>(&tmX, x, ldx, N, H, W, C, Cfg::TW, Cfg::RH, "dwconv3x3_bwd(x)")) return e;
-  static SmemAttrOnce o00, o01, o10, o11;
-  cudaError_t ea = ensure_dynamic_smem(o00, dwconv3x3_bwd_strip_kernel<T, false, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o01, dwconv3x3_bwd_strip_kernel<T, false, true>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o10, dwconv3x3_bwd_strip_kernel<T, true, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o11, dwconv3x3_bwd_strip_kernel<T, true, true>, Cfg::kSmemBytes);
+  UNET_REQUIRE(!(x_scale && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_bwd: x affine and dropout cannot be combined");
+  static SmemAttrOnce o000, o010, o100, o110, o001, o011;
+  cudaError_t ea = ensure_dynamic_smem(o000, dwconv3x3_bwd_strip_kernel<T, false, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o010, dwconv3x3_bwd_strip_kernel<T, false, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o100, dwconv3x3_bwd_strip_kernel<T, true, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o110, dwconv3x3_bwd_strip_kernel<T, true, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o001, dwconv3x3_bwd_strip_kernel<T, false, false, true>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(o011, dwconv3x3_bwd_strip_kernel<T, false, true, true>, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_bwd: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
   const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 4);
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd: too many strips");
-#define UNET_BW_LAUNCH(D, M) dwconv3x3_bwd_strip_kernel<T, D, M><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
-      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from)
-  if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true); else UNET_BW_LAUNCH(true, false); }
-  else       { if (relu_mask) UNET_BW_LAUNCH(false, true); else UNET_BW_LAUNCH(false, false); }
+#define UNET_BW_LAUNCH(D, M, A) dwconv3x3_bwd_strip_kernel<T, D, M, A><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift)
+  if (x_scale) { if (relu_mask) UNET_BW_LAUNCH(false, true, true); else UNET_BW_LAUNCH(false, false, true); }
+  else if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true, false); else UNET_BW_LAUNCH(true, false, false); }
+  else            { if (relu_mask) UNET_BW_LAUNCH(false, true, false); else UNET_BW_LAUNCH(false, false, false); }
 #undef UNET_BW_LAUNCH
   UNET_LAUNCH_CHECK("dwconv3x3_bwd(strip)");
   return UNET_OK;
@@ -1004,8 +1062,11 @@ extern "C" int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void*
 
 extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                                   void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
-                                  int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from, void* stream) {
+                                  int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from,
+                                  const float* x_scale, const float* x_shift, void* stream) {
   UNET_REQUIRE(x && dy && w9c && dx && dw9c, UNET_EINVAL, "dwconv3x3_bwd: null pointer");
+  UNET_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), UNET_EINVAL, "dwconv3x3_bwd: x_scale/x_shift must come together");
+  UNET_REQUIRE(!x_scale || (aligned16(x_scale) && aligned16(x_shift)), UNET_EALIGN, "dwconv3x3_bwd: x_scale/x_shift must be 16B aligned");
   UNET_REQUIRE(drop_c_from >= 0 && drop_c_from % (128 / (dtype == UNET_F32 ? 4 : 2)) == 0, UNET_EINVAL,
                "dwconv3x3_bwd: drop_c_from must be a multiple of the 128-byte channel block");
   UNET_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, UNET_EINVAL, "dwconv3x3_bwd: bad dims %d %d %d %d", N, H, W, C);
@@ -1016,12 +1077,12 @@ extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, in
   if (dtype == UNET_F32) {
     UNET_REQUIRE(dw_strip_ok<float>(x, ldx, dy, lddy, C) && dw_strip_ok<float>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%2==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, st);
+    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, st);
   }
   if (dtype == UNET_BF16) {
     UNET_REQUIRE(dw_strip_ok<__nv_bfloat16>(x, ldx, dy, lddy, C) && dw_strip_ok<__nv_bfloat16>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%4==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, st);
+    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, st);
   }
   return set_error(UNET_EINVAL, "dwconv3x3_bwd: bad dtype %d", dtype);
 }

@@ -109,6 +109,8 @@ class UNetEngine:
                                                 # data / weight gradient GEMMs (no reduce / apply passes, no dz tensor) wherever the
                                                 # producer of dy has the block's activation in registers: every *_block1 (depthwise
                                                 # backward of *_block2), enc*_block2 (max-pool backward), dec1_block2 (head backward)
+        self.fuse_bn_act = True                 # training: the BN+ReLU pass of every *_block1 is not run; *_block2's depthwise kernels
+                                                # (forward and fused backward) read the pre-BN tensor and apply it on load
         self.defer_dropout = True               # training: the concat-buffer Dropout mask of dcat is applied by its readers
         self.fuse_head = True                   # inference: output head fused into dec1_block2's GEMM epilogue (bf16 path)
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
@@ -406,16 +408,37 @@ class UNetEngine:
         o, c = self._bn_off[prefix]
         return (self.bn_vec[0, o:o + c], self.bn_vec[1, o:o + c], self.bn_vec[2, o:o + c], self.bn_vec[3, o:o + c])
 
-    def _block_train_fwd(self, pl, prefix, x, y, pooled=None, drop=None):
-        B, h, w, cin = x.shape
-        cout = y.shape[-1]
-        z = pl.buf(prefix + "/z", (B, h, w, cout))
+    def _act_fused(self, prefix: str) -> bool:
+        """The BN+ReLU pass of this *_block1 is skipped: its only consumers, *_block2's depthwise forward and fused
+        depthwise backward kernels, form y = max(z*scale + shift, 0) on load."""
+        return (self.fuse_bn_act and self.fuse_dw_bwd and prefix.endswith("_block1") and self._bn_off[prefix][1] % 8 == 0)
+
+    def _act_affine(self, prefix: str):
+        """(scale, shift) of a block's BatchNormalization + ReLU as applied to its pre-activation tensor."""
         o, c = self._bn_off[prefix]
+        return (self.bn_vec[0, o:o + c], self.bn_vec[1, o:o + c]) if self.use_bn else (self.ones[:c], self.zeros[:c])
+
+    def _b1_fwd(self, pl, prefix, x, yshape, xaff):
+        """Forward of a *_block1; with `fuse_bn_act` its activation is never materialised and the pre-BN tensor is returned."""
+        if self._act_fused(prefix):
+            z = self._block_train_fwd(pl, prefix, x, None, defer_act=True)
+            xaff[prefix[:-1] + "2"] = self._act_affine(prefix)
+            return z
+        return self._block_train_fwd(pl, prefix, x, pl.buf(prefix + "/y", yshape))
+
+    def _block_train_fwd(self, pl, prefix, x, y, pooled=None, drop=None, x_affine=None, defer_act=False):
+        """x_affine: x is the producer's pre-BN tensor; apply (scale, shift) + ReLU on load.  defer_act: do not run this
+        block's own BN+ReLU pass (the consumer does it on load) and return the pre-BN tensor."""
+        B, h, w, cin = x.shape
+        o, c = self._bn_off[prefix]
+        cout = c
+        z = pl.buf(prefix + "/z", (B, h, w, cout))
         stem = ops.stem_supported(cin, cout) and x.is_contiguous()
         wd, wp = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/pointwise_kernel")
         if not stem:
             d = pl.buf(prefix + "/d", (B, h, w, cin))
-            ops.dwconv3x3(x, wd, d, colsum=self._fold_bufs(prefix)[1] if self._folds(prefix) else None)
+            ops.dwconv3x3(x, wd, d, colsum=self._fold_bufs(prefix)[1] if self._folds(prefix) else None,
+                          in_scale=x_affine[0] if x_affine else None, in_shift=x_affine[1] if x_affine else None)
         if self.use_bn:
             scale, shift, smean, srstd = self._bn(prefix)
             if stem:
@@ -433,11 +456,13 @@ class UNetEngine:
             else:
                 self._pw_fwd(prefix, d, z, epilogue=ops.EPI_AFFINE, shift=self.wview(f"{prefix}_sepconv/bias"))
             scale, shift = self.ones[:c], self.zeros[:c]
+        if defer_act:
+            return z
         ops.bn_act(z, scale, shift, y, relu=True, pooled=pooled, drop=drop)
         return y
 
     def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None, mask_for=None, folded=False,
-                         dx_drop_from=0):
+                         dx_drop_from=0, x_affine=None):
         """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out.
         mask_for: prefix of the block that produced x (= its post-ReLU output): dx_out then is the ReLU-masked gradient
         w.r.t. that block's BatchNormalization output and its two BN-backward reductions are accumulated on the way.
@@ -488,10 +513,11 @@ class UNetEngine:
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
             # both gradients from one pass over dd (+ the producer's ReLU mask and BN-backward reductions)
             ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop, drop_c_from=dx_drop_from, relu_mask=mask_for is not None,
-                              bn_sums=self._fold_bufs(mask_for)[0] if mask_for is not None else None)
+                              bn_sums=self._fold_bufs(mask_for)[0] if mask_for is not None else None,
+                              x_scale=x_affine[0] if x_affine else None, x_shift=x_affine[1] if x_affine else None)
             return dx_out
-        if mask_for is not None:
-            raise RuntimeError(f"{prefix}: the folded BatchNormalization backward of {mask_for} needs the fused depthwise backward kernel")
+        if mask_for is not None or x_affine is not None:
+            raise RuntimeError(f"{prefix}: folded BN backward / BN+ReLU on load need the fused depthwise backward kernel")
         ops.dwconv3x3_bwd_weight(x, dd, gwd)
         if dx_out is not None:
             ops.dwconv3x3(dd, wd, dx_out, flip=True, drop=dx_drop)
@@ -520,23 +546,24 @@ class UNetEngine:
         # ---------------- forward
         cur = x0
         cats, xin = {}, {}
+        xaff: Dict[str, tuple] = {}       # *_block2 -> (scale, shift) of *_block1 when its BN+ReLU is applied on load
         for s in range(1, 5):
             f = FILTERS[s - 1]
             h, w = self._dims(s - 1)
             cat = cats[s] = pl.buf(f"cat{s}", (B, h, w, 2 * f))
             xin[f"enc{s}_block1"] = cur
-            y1 = self._block_train_fwd(pl, f"enc{s}_block1", cur, pl.buf(f"enc{s}_block1/y", (B, h, w, f)))
+            y1 = self._b1_fwd(pl, f"enc{s}_block1", cur, (B, h, w, f), xaff)
             xin[f"enc{s}_block2"] = y1
             pooled = pl.buf(f"pool{s}", (B, h // 2, w // 2, f))
             sdrop = self._drop(f"dec{s}_dropout", 2 * f, f) if s > 1 else None
-            self._block_train_fwd(pl, f"enc{s}_block2", y1, cat[..., f:], pooled=pooled, drop=sdrop)
+            self._block_train_fwd(pl, f"enc{s}_block2", y1, cat[..., f:], pooled=pooled, drop=sdrop, x_affine=xaff.get(f"enc{s}_block2"))
             cur = pooled
         h, w = self._dims(4)
         xin["bneck_block1"] = cur
-        y1 = self._block_train_fwd(pl, "bneck_block1", cur, pl.buf("bneck_block1/y", (B, h, w, 1024)))
+        y1 = self._b1_fwd(pl, "bneck_block1", cur, (B, h, w, 1024), xaff)
         xin["bneck_block2"] = y1
         cur = self._block_train_fwd(pl, "bneck_block2", y1, pl.buf("bneck_block2/y", (B, h, w, 1024)),
-                                    drop=self._drop("bneck_dropout", 1024))
+                                    drop=self._drop("bneck_dropout", 1024), x_affine=xaff.get("bneck_block2"))
         convt_in = {}
         for s in (4, 3, 2, 1):
             f = FILTERS[s - 1]
@@ -544,9 +571,10 @@ class UNetEngine:
             convt_in[s] = cur
             self._convt_fwd(s, cur, cats[s][..., :f], self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None)
             xin[f"dec{s}_block1"] = cats[s]
-            y1 = self._block_train_fwd(pl, f"dec{s}_block1", cats[s], pl.buf(f"dec{s}_block1/y", (B, h, w, f)))
+            y1 = self._b1_fwd(pl, f"dec{s}_block1", cats[s], (B, h, w, f), xaff)
             xin[f"dec{s}_block2"] = y1
-            cur = self._block_train_fwd(pl, f"dec{s}_block2", y1, pl.buf(f"dec{s}_block2/y", (B, h, w, f)))
+            cur = self._block_train_fwd(pl, f"dec{s}_block2", y1, pl.buf(f"dec{s}_block2/y", (B, h, w, f)),
+                                        x_affine=xaff.get(f"dec{s}_block2"))
         probs = pl.buf("probs", (B, H, W, NC), torch.float32)
         sums = pl.buf("sums", (B, NC, 3), torch.float64)
         sums.zero_()
@@ -573,7 +601,8 @@ class UNetEngine:
             dx = S[ci][: M * f].view(B, h, w, f)
             fold = self._folds(f"dec{s}_block1")
             self._block_train_bwd(pl, f"dec{s}_block2", xin[f"dec{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                                  mask_for=f"dec{s}_block1" if fold else None, folded=(s == 1 and fold_d1))
+                                  mask_for=f"dec{s}_block1" if fold else None, folded=(s == 1 and fold_d1),
+                                  x_affine=xaff.get(f"dec{s}_block2"))
             # dec{s}_block1: input is the (dropped-out) concat buffer
             dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
             # the Dropout mask of the upsampled half of the concat gradient is applied by its reader (the un-pixel-shuffle
@@ -600,7 +629,8 @@ class UNetEngine:
         dx = S[ci][: M * 1024].view(B, h, w, 1024)
         fold = self._folds("bneck_block1")
         self._block_train_bwd(pl, "bneck_block2", xin["bneck_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                              ydrop=self._drop("bneck_dropout", 1024), mask_for="bneck_block1" if fold else None)
+                              ydrop=self._drop("bneck_dropout", 1024), mask_for="bneck_block1" if fold else None,
+                              x_affine=xaff.get("bneck_block2"))
         dpool = S[ci][: M * 512].view(B, h, w, 512)
         self._block_train_bwd(pl, "bneck_block1", xin["bneck_block1"], dx, (S[o1], S[o2]), dx_out=dpool, folded=fold)
         if self.grad_hook:
@@ -623,7 +653,7 @@ class UNetEngine:
             dx = S[ci][: M * f].view(B, h, w, f)
             fold = self._folds(f"enc{s}_block1")
             self._block_train_bwd(pl, f"enc{s}_block2", xin[f"enc{s}_block2"], dy, (S[o1], S[o2]), dx_out=dx,
-                                  mask_for=f"enc{s}_block1" if fold else None, folded=fold2)
+                                  mask_for=f"enc{s}_block1" if fold else None, folded=fold2, x_affine=xaff.get(f"enc{s}_block2"))
             x1 = xin[f"enc{s}_block1"]
             cin = x1.shape[-1]
             dpool = S[ci][: M * cin].view(B, h, w, cin) if s > 1 else None

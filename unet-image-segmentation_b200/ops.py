@@ -159,7 +159,7 @@ def dwconv3x3_bwd_supported(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor)
 
 def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torch.Tensor, dw9c: torch.Tensor,
                   relu_mask: bool = False, bn_sums: Optional[torch.Tensor] = None, drop: Optional[Dropout] = None,
-                  drop_c_from: int = 0) -> None:
+                  drop_c_from: int = 0, x_scale: Optional[torch.Tensor] = None, x_shift: Optional[torch.Tensor] = None) -> None:
     """SeparableConv2D depthwise backward in one pass over dy: input gradient (optionally ReLU-masked by x > 0, with the
     BatchNormalization-backward reductions sum(g), sum(g*x) accumulated into bn_sums [2,C]) + weight gradient."""
     n, h, w, c, ldx = _nhwc(x, "x")
@@ -167,11 +167,11 @@ def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torc
     n3, h3, w3, c3, lddx = _nhwc(dx, "dx")
     if (n, h, w, c) != (n2, h2, w2, c2) or (n, h, w, c) != (n3, h3, w3, c3) or x.dtype != dy.dtype or x.dtype != dx.dtype:
         raise ValueError("dwconv3x3_bwd: x, dy and dx disagree")
-    _f32(w9c, "w9c"); _f32(dw9c, "dw9c"); _f32(bn_sums, "bn_sums")
+    _f32(w9c, "w9c"); _f32(dw9c, "dw9c"); _f32(bn_sums, "bn_sums"); _f32(x_scale, "x_scale"); _f32(x_shift, "x_shift")
     if w9c.numel() != 9 * c or dw9c.numel() != 9 * c or (bn_sums is not None and bn_sums.numel() != 2 * c):
         raise ValueError("dwconv3x3_bwd: w9c / dw9c must hold 9*C floats and bn_sums 2*C")
     _call("unet_dwconv3x3_bwd", _p(x), ldx, _p(dy), lddy, _p(w9c), _p(dx), lddx, _p(dw9c), n, h, w, c, _dt(x),
-          int(relu_mask), _p(bn_sums), _dref(drop), int(drop_c_from), _stream(),
+          int(relu_mask), _p(bn_sums), _dref(drop), int(drop_c_from), _p(x_scale), _p(x_shift), _stream(),
           tag=f"{n}x{h}x{w}x{c}" + ("+mask" if relu_mask else "") + ("+drop" if drop is not None else ""), nbytes=_nbytes(x, dy, dx, w9c), flops=36 * x.numel())
 
 

@@ -229,9 +229,12 @@ int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, float* dbias,
 
 /* ---- output head: Conv2D(num_classes,1,activation) (u_net.py:105-112) + Dice/IoU sums (utils/metrics.py:29-31) ---- */
 /* probs[M,C] fp32 = sigmoid (C==1) or softmax (C>1) of x[M,K]*w[K,C]+b.  If y_true != NULL also accumulates, per
-   image n and class c, sums[n][c][0..2] += (sum t*p, sum t, sum p)   (double).  hw = pixels per image. */
+   image n and class c, sums[n][c][0..2] += (sum t*p, sum t, sum p)   (double).  hw = pixels per image.
+   x_scale/x_shift (fp32 [K], may be NULL; binary bf16 head with 64 contiguous channels only): x is dec1_block2's PRE-BatchNormalization
+   tensor and max(x*x_scale + x_shift, 0) is formed on load, so that block's BN+ReLU pass never runs (same for unet_head_bwd). */
 int unet_head_fwd(const void* x, int64_t ldx, const float* w, const float* b, float* probs,
-                  const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype, void* stream);
+                  const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype,
+                  const float* x_scale, const float* x_shift, void* stream);
 /* loss finalize (utils/loss.py:9-45, utils/metrics.py:33-38,58-62): kind 0 = dice, 1 = iou.
    out[0] = loss, out[1] = mean dice_coef, out[2] = mean iou_coef; coef[n][c][0..1] = (ca, cb) with
    dLoss/dp = ca*t + cb (scaled by grad_scale). */
@@ -242,7 +245,8 @@ int unet_seg_loss_finalize(const double* sums, int NC_pairs, float smooth, int k
    sum(dx), sum(dx*x) are accumulated for the folded BatchNormalization backward (see unet_bn_bwd_coef). */
 int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
                   const float* coef, void* dx, int64_t lddx, float* dw, float* db,
-                  int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums, void* stream);
+                  int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums,
+                  const float* x_scale, const float* x_shift, void* stream);
 /* standalone (I,T,P) sums over [NB,HW,C] fp32 pairs: dice_coef / iou_coef as metrics on arbitrary arrays */
 int unet_seg_sums(const float* y_true, const float* y_pred, double* sums, int64_t NB, int64_t hw, int C, void* stream);
 

@@ -654,6 +654,36 @@ def test_head_and_loss(dtype, C, kind):
     np.testing.assert_allclose(host(bsum)[1], (gm * xpr).sum((0, 1, 2)), rtol=1e-2 if dtype == torch.bfloat16 else 1e-4, atol=1e-5)
 
 
+def test_head_stream_affine_on_load():
+    """streamed binary head with dec1_block2's BN+ReLU applied on load == the same kernels on the materialised activation"""
+    n, h, w, k = 3, 20, 24, 64
+    bf = torch.bfloat16
+    z = RNG.standard_normal((n, h, w, k)).astype(np.float32)
+    sc = RNG.uniform(0.5, 1.5, k).astype(np.float32); sh = (RNG.standard_normal(k) * 0.4).astype(np.float32)
+    wk = (RNG.standard_normal((k, 1)) / 4).astype(np.float32); b = np.array([0.1], np.float32)
+    _, t = R.synthetic_batch(n, h, w, 3, 1, seed=7)
+    zd = dev(z, bf)
+    yd = torch.clamp_min(zd.float() * dev(sc) + dev(sh), 0)          # fp32 activation the kernels form in registers
+    assert ops.head_stream_supported(zd, 1)
+    res = []
+    for x_in, aff in ((zd, True), (yd.to(bf), False)):
+        probs = torch.empty((n, h, w, 1), device="cuda"); sums = torch.zeros((n, 1, 3), device="cuda", dtype=torch.float64)
+        ops.head_fwd(x_in, dev(wk), dev(b), probs, dev(t), sums, x_scale=dev(sc) if aff else None, x_shift=dev(sh) if aff else None)
+        out3 = torch.empty(3, device="cuda"); coef = torch.empty((n, 1, 2), device="cuda")
+        ops.seg_loss_finalize(sums, n, R.EPSILON, 0, 1.0, out3, coef)
+        dx = torch.empty_like(zd); dw = torch.zeros((k, 1), device="cuda"); db = torch.zeros(1, device="cuda"); bs = torch.zeros((2, k), device="cuda")
+        ops.head_bwd(x_in, dev(wk), probs, dev(t), coef, dx, dw, db, bn_sums=bs, x_scale=dev(sc) if aff else None, x_shift=dev(sh) if aff else None)
+        res.append((host(probs), host(dx), host(dw), host(db), host(bs)))
+    a, m = res          # m rounds the activation to bf16 first: agreement to bf16 noise
+    np.testing.assert_allclose(a[0], m[0], atol=5e-3)
+    np.testing.assert_allclose(a[2], m[2], rtol=2e-2, atol=1e-4)
+    np.testing.assert_allclose(a[3], m[3], rtol=2e-2, atol=1e-5)
+    np.testing.assert_allclose(a[4], m[4], rtol=3e-2, atol=1e-4)
+    # the mask itself is exact: dx is zero exactly where the activation is zero
+    y_exact = host(yd)
+    assert np.all(a[1][y_exact <= 0] == 0)
+
+
 def test_seg_sums_metrics():
     t = (RNG.random((4, 9, 7, 3)) > 0.5).astype(np.float32)
     p = RNG.random((4, 9, 7, 3)).astype(np.float32)

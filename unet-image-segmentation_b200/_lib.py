@@ -73,9 +73,9 @@ _SIGNATURES = {
     "unet_maxpool2x2_fwd": [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
     "unet_maxpool2x2_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _dp, _vp],
     "unet_convt_bwd_gather": [_vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _dp, _vp],
-    "unet_head_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp],
+    "unet_head_fwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp],
     "unet_seg_loss_finalize": [_vp, _i, _f, _i, _f, _vp, _vp, _vp],
-    "unet_head_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp],
+    "unet_head_bwd": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp],
     "unet_seg_sums": [_vp, _vp, _vp, _i64, _i64, _i, _vp],
     "unet_confusion_matrix_update": [_vp, _vp, _i64, _i, _vp, _vp],
     "unet_confusion_matrix_update_thr": [_vp, _vp, _f, _i64, _vp, _vp],

@@ -261,7 +261,7 @@ constexpr int kH1FD = 8;
 __global__ void __launch_bounds__(256, 4)
 head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                         float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
-                        int64_t hw, int pix_per_block) {
+                        int64_t hw, int pix_per_block, const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
   __shared__ uint4 ring_x[kH1FD][256];
   __shared__ float ring_t[kH1FD][256];
   __shared__ double s_sum[3];
@@ -271,8 +271,10 @@ head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
   const int sub = threadIdx.x & 7, slot = threadIdx.x >> 3;
   const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p_end = i64min(hw, p_begin + pix_per_block);
-  float wk[8];
+  float wk[8], xs[8], xt[8];
   load8(w + sub * 8, wk);
+  const bool aff = x_scale != nullptr;             // x is dec1_block2's pre-BN tensor: BN + ReLU on load
+  if (aff) { load8(x_scale + sub * 8, xs); load8(x_shift + sub * 8, xt); }
   const float bias = b ? __ldg(b) : 0.f;
   float si = 0.f, st_ = 0.f, sp_ = 0.f;
   const uint32_t sx = smem_u32(&ring_x[0][threadIdx.x]), stq = smem_u32(&ring_t[0][threadIdx.x]);
@@ -298,8 +300,10 @@ head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      acc = fmaf(__uint_as_float(u[q] << 16), wk[2 * q], acc);
-      acc = fmaf(__uint_as_float(u[q] & 0xffff0000u), wk[2 * q + 1], acc);
+      float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
+      if (aff) { v0 = fmaxf(fmaf(v0, xs[2 * q], xt[2 * q]), 0.f); v1 = fmaxf(fmaf(v1, xs[2 * q + 1], xt[2 * q + 1]), 0.f); }
+      acc = fmaf(v0, wk[2 * q], acc);
+      acc = fmaf(v1, wk[2 * q + 1], acc);
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     if (sub == 0) {
@@ -329,7 +333,8 @@ template <bool SUMS>
 __global__ void __launch_bounds__(256, 4)
 head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ probs,
                         const float* __restrict__ y_true, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx,
-                        float* __restrict__ dw, float* __restrict__ db, int64_t hw, int pix_per_block, float* __restrict__ bn_sums) {
+                        float* __restrict__ dw, float* __restrict__ db, int64_t hw, int pix_per_block, float* __restrict__ bn_sums,
+                        const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
   __shared__ uint4 ring_x[kH1D][256];
   __shared__ float ring_p[kH1D][256], ring_t[kH1D][256];
   __shared__ float s_red[3 * 64 + 1];              // dw | sum g | (unused) | db
@@ -340,8 +345,10 @@ head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
   const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p_end = i64min(hw, p_begin + pix_per_block);
   const float ca = coef[n * 2], cb = coef[n * 2 + 1];
-  float wk[8], dwacc[8], s1[8];
+  float wk[8], dwacc[8], s1[8], xs[8], xt[8];
   load8(w + sub * 8, wk);
+  const bool aff = x_scale != nullptr;             // x is dec1_block2's pre-BN tensor: BN + ReLU on load
+  if (aff) { load8(x_scale + sub * 8, xs); load8(x_shift + sub * 8, xt); }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { dwacc[j] = 0.f; s1[j] = 0.f; }
   float dbs = 0.f;
@@ -371,7 +378,8 @@ head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     float o[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
+      float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
+      if (aff) { v0 = fmaxf(fmaf(v0, xs[2 * q], xt[2 * q]), 0.f); v1 = fmaxf(fmaf(v1, xs[2 * q + 1], xt[2 * q + 1]), 0.f); }
       dwacc[2 * q] = fmaf(v0, dz, dwacc[2 * q]); dwacc[2 * q + 1] = fmaf(v1, dz, dwacc[2 * q + 1]);
       float g0 = dz * wk[2 * q], g1 = dz * wk[2 * q + 1];
       if (SUMS) { g0 = v0 > 0.f ? g0 : 0.f; g1 = v1 > 0.f ? g1 : 0.f; s1[2 * q] += g0; s1[2 * q + 1] += g1; }
@@ -614,7 +622,11 @@ static void head_grid(int64_t NB, int64_t hw, dim3* grid, int* pix_per_block, in
 using namespace unet;
 
 extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const float* b, float* probs,
-                             const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype, void* stream) {
+                             const float* y_true, double* sums, int64_t M, int64_t hw, int K, int C, int dtype,
+                             const float* x_scale, const float* x_shift, void* stream) {
+  UNET_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), UNET_EINVAL, "head_fwd: x_scale/x_shift must come together");
+  UNET_REQUIRE(!x_scale || (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64 && aligned16(x_scale) && aligned16(x_shift)), UNET_EUNSUPPORTED,
+               "head_fwd: BN+ReLU on load exists for the streamed binary head only (bf16, 64 channels, contiguous x)");
   UNET_REQUIRE(x && w && probs && M > 0 && hw > 0 && K > 0 && C > 0 && ldx >= K, UNET_EINVAL, "head_fwd: bad argument");
   UNET_REQUIRE(M % hw == 0, UNET_EINVAL, "head_fwd: M must be a multiple of hw");
   UNET_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && aligned16(x), UNET_EALIGN, "head_fwd: needs K%%8==0, ld%%8==0, 16B pointer");
@@ -625,7 +637,7 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
   head_grid(M / hw, hw, &grid, &ppb);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64) {     // the reference head: streamed kernel
-    head1_fwd_stream_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, probs, y_true, sums, hw, ppb);
+    head1_fwd_stream_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, probs, y_true, sums, hw, ppb, x_scale, x_shift);
     UNET_LAUNCH_CHECK("head_fwd(stream)");
     return UNET_OK;
   }
@@ -642,7 +654,11 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
 
 extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const float* probs, const float* y_true,
                              const float* coef, void* dx, int64_t lddx, float* dw, float* db,
-                             int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums, void* stream) {
+                             int64_t M, int64_t hw, int K, int C, int dtype, float* bn_sums,
+                             const float* x_scale, const float* x_shift, void* stream) {
+  UNET_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), UNET_EINVAL, "head_bwd: x_scale/x_shift must come together");
+  UNET_REQUIRE(!x_scale || (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64 && dx && lddx == 64 && aligned16(x_scale) && aligned16(x_shift)),
+               UNET_EUNSUPPORTED, "head_bwd: BN+ReLU on load exists for the streamed binary head only (bf16, 64 channels, contiguous x and dx)");
   UNET_REQUIRE(x && w && probs && y_true && coef && dw && db, UNET_EINVAL, "head_bwd: null pointer");
   UNET_REQUIRE(M > 0 && hw > 0 && K > 0 && C > 0 && ldx >= K && M % hw == 0, UNET_EINVAL, "head_bwd: bad dims");
   UNET_REQUIRE(K % 8 == 0 && ldx % 8 == 0 && aligned16(x) && (!dx || (lddx % 8 == 0 && aligned16(dx))), UNET_EALIGN,
@@ -655,8 +671,8 @@ extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const f
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64 && dx && lddx == 64) {     // the reference head: streamed kernel
     head_grid(M / hw, hw, &grid, &ppb, 16);
-    if (bn_sums) head1_bwd_stream_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums);
-    else head1_bwd_stream_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums);
+    if (bn_sums) head1_bwd_stream_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
+    else head1_bwd_stream_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
     UNET_LAUNCH_CHECK("head_bwd(stream)");
     return UNET_OK;
   }

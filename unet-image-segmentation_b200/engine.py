@@ -547,6 +547,7 @@ class UNetEngine:
         cur = x0
         cats, xin = {}, {}
         xaff: Dict[str, tuple] = {}       # *_block2 -> (scale, shift) of *_block1 when its BN+ReLU is applied on load
+        head_aff = None                   # (scale, shift) of dec1_block2 when the head kernels apply its BN+ReLU on load
         for s in range(1, 5):
             f = FILTERS[s - 1]
             h, w = self._dims(s - 1)
@@ -573,13 +574,19 @@ class UNetEngine:
             xin[f"dec{s}_block1"] = cats[s]
             y1 = self._b1_fwd(pl, f"dec{s}_block1", cats[s], (B, h, w, f), xaff)
             xin[f"dec{s}_block2"] = y1
-            cur = self._block_train_fwd(pl, f"dec{s}_block2", y1, pl.buf(f"dec{s}_block2/y", (B, h, w, f)),
-                                        x_affine=xaff.get(f"dec{s}_block2"))
+            if s == 1 and self.fuse_bn_act and self.act_dtype == torch.bfloat16 and NC == 1 and f == 64:
+                # dec1_block2's BN+ReLU is applied on load by the streamed head kernels (forward and backward)
+                cur = self._block_train_fwd(pl, "dec1_block2", y1, None, x_affine=xaff.get("dec1_block2"), defer_act=True)
+                head_aff = self._act_affine("dec1_block2")
+            else:
+                cur = self._block_train_fwd(pl, f"dec{s}_block2", y1, pl.buf(f"dec{s}_block2/y", (B, h, w, f)),
+                                            x_affine=xaff.get(f"dec{s}_block2"))
         probs = pl.buf("probs", (B, H, W, NC), torch.float32)
         sums = pl.buf("sums", (B, NC, 3), torch.float64)
         sums.zero_()
         wk, bk = self._mat("output_mask/kernel"), self.wview("output_mask/bias")
-        ops.head_fwd(cur, wk, bk, probs, y_true, sums)
+        ops.head_fwd(cur, wk, bk, probs, y_true, sums, x_scale=head_aff[0] if head_aff else None,
+                     x_shift=head_aff[1] if head_aff else None)
         out3 = pl.buf("out3", (3,), torch.float32)
         coef = pl.buf("coef", (B, NC, 2), torch.float32)
         ops.seg_loss_finalize(sums, B * NC, SMOOTH, kind, 1.0, out3, coef)
@@ -589,7 +596,8 @@ class UNetEngine:
         dy = S[0][: B * H * W * 64].view(B, H, W, 64)
         fold_d1 = self._folds("dec1_block2")
         ops.head_bwd(cur, wk, probs, y_true, coef, dy, self._mat("output_mask/kernel", self.g),
-                     self.wview("output_mask/bias", self.g), bn_sums=self._fold_bufs("dec1_block2")[0] if fold_d1 else None)
+                     self.wview("output_mask/bias", self.g), bn_sums=self._fold_bufs("dec1_block2")[0] if fold_d1 else None,
+                     x_scale=head_aff[0] if head_aff else None, x_shift=head_aff[1] if head_aff else None)
         ci = 0   # index of the scratch buffer that currently holds dy
         dcat = {}
         for s in (1, 2, 3, 4):

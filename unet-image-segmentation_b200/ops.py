@@ -459,14 +459,15 @@ def convt_bwd_gather(du: torch.Tensor, g: torch.Tensor, dbias: Optional[torch.Te
 
 # ------------------------------------------------------------------------------------------------ head + loss
 def head_fwd(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], probs: torch.Tensor,
-             y_true: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None) -> None:
+             y_true: Optional[torch.Tensor] = None, sums: Optional[torch.Tensor] = None,
+             x_scale: Optional[torch.Tensor] = None, x_shift: Optional[torch.Tensor] = None) -> None:
     n, h, wd, k, ldx = _nhwc(x, "x")
     c = probs.shape[-1]
-    _f32(w, "w"); _f32(b, "b"); _f32(probs, "probs"); _f32(y_true, "y_true")
+    _f32(w, "w"); _f32(b, "b"); _f32(probs, "probs"); _f32(y_true, "y_true"); _f32(x_scale, "x_scale"); _f32(x_shift, "x_shift")
     if sums is not None and sums.dtype != torch.float64:
         raise TypeError("sums must be float64")
     _call("unet_head_fwd", _p(x), ldx, _p(w), _p(b), _p(probs), _p(y_true), _p(sums), n * h * wd, h * wd, k, c,
-          _dt(x), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}", nbytes=_nbytes(x, probs, y_true), flops=2 * x.numel() * c)
+          _dt(x), _p(x_scale), _p(x_shift), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}", nbytes=_nbytes(x, probs, y_true), flops=2 * x.numel() * c)
 
 
 def seg_loss_finalize(sums: torch.Tensor, npairs: int, smooth: float, kind: int, grad_scale: float,
@@ -476,17 +477,23 @@ def seg_loss_finalize(sums: torch.Tensor, npairs: int, smooth: float, kind: int,
           _p(coef), _stream())
 
 
-def head_bwd(x, w, probs, y_true, coef, dx: Optional[torch.Tensor], dw, db, bn_sums: Optional[torch.Tensor] = None) -> None:
+def head_stream_supported(x: torch.Tensor, classes: int) -> bool:
+    """the streamed binary-head kernels (and with them BN+ReLU on load) apply"""
+    return x.dtype == torch.bfloat16 and classes == 1 and x.shape[-1] == 64 and x.is_contiguous()
+
+
+def head_bwd(x, w, probs, y_true, coef, dx: Optional[torch.Tensor], dw, db, bn_sums: Optional[torch.Tensor] = None,
+             x_scale: Optional[torch.Tensor] = None, x_shift: Optional[torch.Tensor] = None) -> None:
     n, h, wd, k, ldx = _nhwc(x, "x")
     c = probs.shape[-1]
     lddx = _nhwc(dx, "dx")[4] if dx is not None else 0
     for t, nm in ((w, "w"), (probs, "probs"), (y_true, "y_true"), (coef, "coef"), (dw, "dw"), (db, "db")):
         _f32(t, nm)
-    _f32(bn_sums, "bn_sums")
+    _f32(bn_sums, "bn_sums"); _f32(x_scale, "x_scale"); _f32(x_shift, "x_shift")
     if bn_sums is not None and bn_sums.numel() != 2 * k:
         raise ValueError("head_bwd: bn_sums must hold 2*K floats")
     _call("unet_head_bwd", _p(x), ldx, _p(w), _p(probs), _p(y_true), _p(coef), _p(dx), lddx, _p(dw), _p(db),
-          n * h * wd, h * wd, k, c, _dt(x), _p(bn_sums), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}",
+          n * h * wd, h * wd, k, c, _dt(x), _p(bn_sums), _p(x_scale), _p(x_shift), _stream(), tag=f"{n}x{h}x{wd}x{k}->{c}",
           nbytes=_nbytes(x, probs, y_true, dx), flops=4 * x.numel() * c)
 
 

@@ -45,7 +45,7 @@ DTYPES = [torch.float32, torch.bfloat16]
 # ------------------------------------------------------------------------------------------------ depthwise
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (3, 33, 9, 24), (2, 8, 8, 3), (1, 1, 1, 16), (1, 64, 48, 128),
-                                   (2, 100, 70, 72), (1, 131, 33, 200), (2, 7, 5, 1)])
+                                   (2, 100, 70, 72), (1, 131, 33, 200), (2, 7, 5, 1), (1, 21, 64, 64), (2, 9, 130, 72), (1, 40, 32, 16)])
 @pytest.mark.parametrize("flip", [False, True])
 def test_dwconv_fwd(dtype, shape, flip):
     x = RNG.standard_normal(shape).astype(np.float32)
@@ -77,6 +77,24 @@ def test_dwconv_fwd_views_affine_dropout(dtype):
     got = host(out)
     np.testing.assert_allclose(got[..., 16:16 + c], ref * mult, **tol(dtype))
     assert np.all(got[..., :16] == 0) and np.all(got[..., 48:] == 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape", [(2, 10, 66, 64), (1, 9, 32, 72), (2, 6, 18, 32)])
+def test_dwconv_fwd_dropout_strip(dtype, shape):
+    """Dropout on the stored output of the TMA-strip kernel (one and two columns per thread), written into a channel view"""
+    n, h, w, c = shape
+    x = RNG.standard_normal(shape).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    xr = bf16_round(x) if dtype == torch.bfloat16 else x.astype(np.float64)
+    ref = R.dwconv3x3(xr, wk.astype(np.float64))
+    ctot = c + 24
+    out = torch.zeros((n, h, w, ctot), device="cuda", dtype=dtype)
+    ops.dwconv3x3(dev(x, dtype), dev(wk.reshape(9, -1)), out[..., 8:8 + c], drop=ops.make_dropout(0.25, 77, ctot=ctot, c0=8))
+    mult = R.dropout_multiplier((n, h, w, ctot), 0.25, 77)[..., 8:8 + c]
+    got = host(out)
+    np.testing.assert_allclose(got[..., 8:8 + c], ref * mult, **tol(dtype))
+    assert np.all(got[..., :8] == 0) and np.all(got[..., 8 + c:] == 0)
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -144,7 +162,8 @@ def test_dwconv_bwd_fused_partial_dropout(dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 37, 45, 72), (2, 70, 33, 128), (1, 9, 100, 8)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 37, 45, 72), (2, 70, 33, 128), (1, 9, 100, 8), (2, 12, 64, 128), (1, 21, 98, 72),
+                                   (1, 35, 32, 64)])
 def test_dwconv_fwd_affine_on_load(dtype, shape):
     """TMA-strip kernel with the producer's BN+ReLU applied on load: zero padding lives in the transformed space"""
     n, h, w, c = shape
@@ -184,9 +203,9 @@ def test_dwconv_bwd_fused_affine_on_load(dtype, mask):
         np.testing.assert_allclose(host(sums)[1], (g * yact).sum((0, 1, 2)), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
 
 
-def test_dwconv_fwd_colsum():
+@pytest.mark.parametrize("shape", [(2, 37, 45, 72), (2, 19, 70, 72), (1, 33, 128, 64)])
+def test_dwconv_fwd_colsum(shape):
     for dtype in DTYPES:
-        shape = (2, 37, 45, 72)
         x = RNG.standard_normal(shape).astype(np.float32)
         w = RNG.standard_normal((3, 3, shape[3])).astype(np.float32)
         y = torch.empty(shape, device="cuda", dtype=dtype)

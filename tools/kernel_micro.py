@@ -60,6 +60,11 @@ elif name == "dw_fwd128":
 elif name == "dw_fwd256":
     x, y, w = rnd(B, 256, 256, 256), torch.empty((B, 256, 256, 256), device=dev, dtype=bf), torch.rand((9, 256), device=dev)
     run(lambda: ops.dwconv3x3(x, w, y), 2 * B * 256 * 256 * 256 * 2)
+elif name in ("dw_fwd_aff", "dw_fwd_aff128_256", "dw_fwd_aff256_128"):   # *_block2 depthwise: BN+ReLU of block1 applied on load, colsum
+    cc, hh = {"dw_fwd_aff": (64, 512), "dw_fwd_aff128_256": (128, 256), "dw_fwd_aff256_128": (256, 128)}[name]
+    x, y, w = rnd(B, hh, hh, cc), torch.empty((B, hh, hh, cc), device=dev, dtype=bf), torch.rand((9, cc), device=dev)
+    sc, sh, cs = torch.rand(cc, device=dev) + 0.5, torch.rand(cc, device=dev) - 0.5, torch.zeros(cc, device=dev)
+    run(lambda: ops.dwconv3x3(x, w, y, in_scale=sc, in_shift=sh, colsum=cs), 2 * B * hh * hh * cc * 2)
 elif name == "dw_bwd_w":
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     run(lambda: ops.dwconv3x3_bwd_weight(x, dy, dw), 2 * M * 64 * 2)

@@ -97,20 +97,24 @@ dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restr
 
 
 // ------------------------------------------------------------------------------------------------ forward, TMA strips
-// One CTA = one strip: TW output columns x 128 B of channels x a segment of rows of one image.  A producer warp streams
-// the strip top to bottom through a ring of shared-memory stages with 4-D TMA boxes (channels, columns + 2 halo,
-// RH rows, image) issued by thread 0, S-1 stages ahead; rows -1 / H and columns -1 / W come back as zeros from the TMA out-of-bounds fill, which IS the
-// 'same' padding.  Eight consumer warps slide down the strip: a thread owns 16 B of channels of one column, keeps the
-// two open partial sums in registers, and per input row does 3 conflict-free 16-byte shared loads and 27 FMAs per
-// channel-triple; outputs leave as coalesced 16-byte global stores (4 pixels x 128 B per warp instruction).
+// One CTA = one strip: TW = PXT*CW output columns x 128 B of channels x a segment of rows of one image.  Thread 0 streams
+// the strip top to bottom through a ring of S shared-memory stages with 4-D TMA boxes (channels, columns + 2 halo, RH rows,
+// image), S-1 stages ahead; rows -1 / H and columns -1 / W come back as zeros from the TMA out-of-bounds fill, which IS
+// the 'same' padding.  The PXT*16 threads slide down the strip: a thread owns 8 B of channels of CW adjacent columns, keeps
+// the two open partial sums of each in registers, and per input row does CW+2 conflict-free 8-byte shared loads and
+// 9*CW packed FFMA2 per channel pair; outputs leave as 8-byte global stores (128 B contiguous per column).
 // HBM sees every input byte once plus 2/TW column halo (served by L2) and 2/segment rows.
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 
-template <typename T> struct StripCfg {
+// CW = output columns per thread, PXT = column threads per CTA (x 16 channel groups of 8 bytes).  CW = 2 loads 4 columns
+// for 2 outputs instead of 3 for 1: a third fewer shared loads / unpacks / on-load transforms per output element.
+template <typename T, int CW_ = 1, int PXT_ = 32> struct StripCfg {
   static constexpr int NV = 8 / (int)sizeof(T);          // channels per thread (8 bytes)
   static constexpr int CB = 128 / (int)sizeof(T);        // channels per CTA (128 bytes)
-  static constexpr int TW = 32, RH = 4, S = 8;
-  static constexpr int kThreads = TW * 16;
+  static constexpr int CW = CW_, PXT = PXT_;
+  static constexpr int TW = PXT * CW, RH = 4, S = (TW > 32) ? 6 : (PXT == 8 ? 4 : (PXT < 32 ? 5 : 8));
+  static constexpr int kThreads = PXT * 16;
+  static constexpr int kMinBlocks = PXT == 8 ? 3 : (PXT < 32 ? 2 : 1);
   static constexpr int kStageBytes = RH * (TW + 2) * 128;
   static constexpr int kSmemBytes = S * kStageBytes + 2 * S * 8 + CB * 4 + 128;
 };
@@ -132,15 +136,16 @@ __device__ __forceinline__ uint2 pack8(const float (&v)[2], float*) {
 }
 
 // AFFINE: the input tensor is the producer's PRE-BatchNormalization output z; x' = max(z*in_scale + in_shift, 0) is formed in
-// registers on every load (3 columns x the thread's channels per row), and the 'same' padding is re-imposed in x' space:
-// rows outside the image and the two halo columns at the image border are forced to zero after the transform.
-template <typename T, bool DROP, bool SUMS, bool AFFINE>
-__global__ void __launch_bounds__(StripCfg<T>::kThreads, 1)
+// registers on every load (CW+2 columns x the thread's channels per row), and the 'same' padding is re-imposed in x' space:
+// rows outside the image are zeroed by a CTA-uniform branch, the two halo columns are multiplied by a per-thread 0/1 factor
+// (0 only for the threads at the image's left / right border).
+template <typename T, int CW, int PXT, bool DROP, bool SUMS, bool AFFINE>
+__global__ void __launch_bounds__((StripCfg<T, CW, PXT>::kThreads), (StripCfg<T, CW, PXT>::kMinBlocks))
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
                        int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp,
                        float* __restrict__ colsum, const float* __restrict__ in_scale, const float* __restrict__ in_shift) {
-  using Cfg = StripCfg<T>;
-  constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
+  using Cfg = StripCfg<T, CW, PXT>;
+  constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S, NQ = CW + 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
@@ -178,7 +183,8 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
 
   const int px = threadIdx.x >> 4, cg = threadIdx.x & 15;
   const int c = c0 + cg * NV;
-  const bool live = (w0 + px < W) && (c < C);
+  const int col0 = w0 + px * CW;                   // first output column of this thread (W % CW == 0: all CW are live or none)
+  const bool live = (col0 < W) && (c < C);
   constexpr int NP = NV / 2;                       // fp32 pairs per thread: every FMA below is a packed FFMA2
   float2 k9[9][NP];
 #pragma unroll
@@ -199,7 +205,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
   uint32_t seed = 0u;
   if (DROP) seed = drop_seed(dp);
   float2 asc[NP], ash[NP];                          // AFFINE: scale / shift of this thread's channels
-  bool l_ok = true, r_ok = true;
+  float2 lm2 = make_float2(1.f, 1.f), rm2 = make_float2(1.f, 1.f);
   if (AFFINE) {
 #pragma unroll
     for (int j = 0; j < NP; ++j) { asc[j] = make_float2(0.f, 0.f); ash[j] = make_float2(0.f, 0.f); }
@@ -211,14 +217,19 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
         asc[0] = __ldg(reinterpret_cast<const float2*>(in_scale + c)); ash[0] = __ldg(reinterpret_cast<const float2*>(in_shift + c));
       }
     }
-    l_ok = w0 + px - 1 >= 0; r_ok = w0 + px + 1 < W;
+    if (col0 - 1 < 0) lm2 = make_float2(0.f, 0.f);
+    if (col0 + CW >= W) rm2 = make_float2(0.f, 0.f);
   }
-  float2 prev[NP], cur[NP], csum[NP];
+  float2 prev[CW][NP], cur[CW][NP], csum[NP];
 #pragma unroll
-  for (int j = 0; j < NP; ++j) { prev[j] = make_float2(0.f, 0.f); cur[j] = make_float2(0.f, 0.f); csum[j] = make_float2(0.f, 0.f); }
-  T* yptr = y + (((int64_t)n * H + (h0 - 2)) * W + (w0 + px)) * ldy + c;   // advanced one row per input row
+  for (int j = 0; j < NP; ++j) {
+    csum[j] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < CW; ++q) { prev[q][j] = make_float2(0.f, 0.f); cur[q][j] = make_float2(0.f, 0.f); }
+  }
+  T* yptr = y + (((int64_t)n * H + (h0 - 2)) * W + col0) * ldy + c;   // advanced one row per input row
   const int64_t yrow = (int64_t)W * ldy;
-  const uint32_t tile_off = (uint32_t)px * 128u + (uint32_t)cg * 8u;
+  const uint32_t tile_off = (uint32_t)(px * CW) * 128u + (uint32_t)cg * 8u;
   const uint32_t smem_base = smem_u32(smem);
   int r_in = h0 - 1;
 
@@ -227,52 +238,64 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     if (threadIdx.x == 0 && k + S - 1 < nst) issue(k + S - 1);
     mbar_wait(&full_bar[s], (k / S) & 1);
     const uint32_t st = smem_base + s * Cfg::kStageBytes + tile_off;
-    uint2 ra[RH], rb[RH], rc[RH];
+    uint2 raw[RH][NQ];
 #pragma unroll
-    for (int rr = 0; rr < RH; ++rr) {        // all shared loads of the stage first: 12 independent requests in flight
-      ra[rr] = lds64(st + rr * (TW + 2) * 128);
-      rb[rr] = lds64(st + rr * (TW + 2) * 128 + 128);
-      rc[rr] = lds64(st + rr * (TW + 2) * 128 + 256);
-    }
+    for (int rr = 0; rr < RH; ++rr)          // all shared loads of the stage first: RH * (CW+2) independent requests in flight
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) raw[rr][q] = lds64(st + rr * (TW + 2) * 128 + q * 128);
 #pragma unroll
     for (int rr = 0; rr < RH; ++rr, ++r_in, yptr += yrow) {
-      float2 a[NP], b[NP], cc[NP];
-      unpack8<T>(ra[rr], a); unpack8<T>(rb[rr], b); unpack8<T>(rc[rr], cc);
-      if (AFFINE) {
-        const bool row_ok = (unsigned)r_in < (unsigned)H;     // uniform over the CTA
+      float2 v[NQ][NP];
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          const float2 ta = fma2(a[j], asc[j], ash[j]), tb = fma2(b[j], asc[j], ash[j]), tc = fma2(cc[j], asc[j], ash[j]);
-          a[j]  = (row_ok && l_ok) ? make_float2(fmaxf(ta.x, 0.f), fmaxf(ta.y, 0.f)) : make_float2(0.f, 0.f);
-          b[j]  = row_ok ? make_float2(fmaxf(tb.x, 0.f), fmaxf(tb.y, 0.f)) : make_float2(0.f, 0.f);
-          cc[j] = (row_ok && r_ok) ? make_float2(fmaxf(tc.x, 0.f), fmaxf(tc.y, 0.f)) : make_float2(0.f, 0.f);
+      for (int q = 0; q < NQ; ++q) unpack8<T>(raw[rr][q], v[q]);
+      if (AFFINE) {
+        if ((unsigned)r_in < (unsigned)H) {       // uniform over the CTA
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+              const float2 t = fma2(v[q][j], asc[j], ash[j]);
+              v[q][j] = make_float2(fmaxf(t.x, 0.f), fmaxf(t.y, 0.f));
+            }
+#pragma unroll
+          for (int j = 0; j < NP; ++j) { v[0][j] = mul2(v[0][j], lm2); v[NQ - 1][j] = mul2(v[NQ - 1][j], rm2); }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) v[q][j] = make_float2(0.f, 0.f);
         }
       }
       if (r_in > h0 && r_in <= h1 && live) {   // output row r_in-1 is complete once kernel row 2 has seen input row r_in
-        float o[NV];
+#pragma unroll
+        for (int q = 0; q < CW; ++q) {
+          float o[NV];
+#pragma unroll
+          for (int j = 0; j < NP; ++j) {
+            const float2 r = fma2(k9[8][j], v[q + 2][j], fma2(k9[7][j], v[q + 1][j], fma2(k9[6][j], v[q][j], prev[q][j])));
+            o[2 * j] = r.x; o[2 * j + 1] = r.y;
+          }
+          if (DROP) {
+            const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (col0 + q)) * dp.ctot + dp.c0 + c;
+            dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
+          }
+          const uint2 packed = pack8(o, (T*)nullptr);
+          *reinterpret_cast<uint2*>(yptr + q * ldy) = packed;
+          if (SUMS) {                               // column sums of the values as stored (what the pointwise GEMM reads)
+            float2 st2[NP];
+            unpack8<T>(packed, st2);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { csum[j].x += st2[j].x; csum[j].y += st2[j].y; }
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < CW; ++q)
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          const float2 v = fma2(k9[8][j], cc[j], fma2(k9[7][j], b[j], fma2(k9[6][j], a[j], prev[j])));
-          o[2 * j] = v.x; o[2 * j + 1] = v.y;
+          prev[q][j] = fma2(k9[5][j], v[q + 2][j], fma2(k9[4][j], v[q + 1][j], fma2(k9[3][j], v[q][j], cur[q][j])));
+          cur[q][j]  = fma2(k9[2][j], v[q + 2][j], fma2(k9[1][j], v[q + 1][j], mul2(k9[0][j], v[q][j])));
         }
-        if (DROP) {
-          const uint64_t base = (uint64_t)(((int64_t)n * H + (r_in - 1)) * W + (w0 + px)) * dp.ctot + dp.c0 + c;
-          dropout_apply(o, base, seed, dp.keep, dp.inv_keep);
-        }
-        const uint2 packed = pack8(o, (T*)nullptr);
-        *reinterpret_cast<uint2*>(yptr) = packed;
-        if (SUMS) {                               // column sums of the values as stored (what the pointwise GEMM reads)
-          float2 st2[NP];
-          unpack8<T>(packed, st2);
-#pragma unroll
-          for (int j = 0; j < NP; ++j) { csum[j].x += st2[j].x; csum[j].y += st2[j].y; }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < NP; ++j) {
-        prev[j] = fma2(k9[5][j], cc[j], fma2(k9[4][j], b[j], fma2(k9[3][j], a[j], cur[j])));
-        cur[j]  = fma2(k9[2][j], cc[j], fma2(k9[1][j], b[j], mul2(k9[0][j], a[j])));
-      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -314,27 +337,25 @@ static int pick_seg_rows(int N, int H, int ntw, int ncb, int min_rows, int64_t w
   return seg;
 }
 
-template <typename T>
-static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
-                               int flip, DropArgs dp, float* colsum, const float* in_scale, const float* in_shift, cudaStream_t st) {
-  using Cfg = StripCfg<T>;
-  UNET_REQUIRE(!(colsum && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum and dropout cannot be combined");
-  UNET_REQUIRE(!(in_scale && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: input affine and dropout cannot be combined");
+template <typename T, int CW, int PXT>
+static int dw_fwd_strip_launch_cfg(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
+                                   int flip, DropArgs dp, float* colsum, const float* in_scale, const float* in_shift, cudaStream_t st) {
+  using Cfg = StripCfg<T, CW, PXT>;
   CUtensorMap tm;
   if (int e = make_nhwc_tmap<T>(&tm, x, ldx, N, H, W, C, Cfg::TW + 2, Cfg::RH, "dwconv3x3_fwd")) return e;
   static SmemAttrOnce once_plain, once_drop, once_sums, once_aff, once_aff_sums;
-  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, false, false, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, true, false, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_sums, dwconv3x3_strip_kernel<T, false, true, false>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff, dwconv3x3_strip_kernel<T, false, false, true>, Cfg::kSmemBytes);
-  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff_sums, dwconv3x3_strip_kernel<T, false, true, true>, Cfg::kSmemBytes);
+  cudaError_t ea = ensure_dynamic_smem(once_plain, dwconv3x3_strip_kernel<T, CW, PXT, false, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_drop, dwconv3x3_strip_kernel<T, CW, PXT, true, false, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_sums, dwconv3x3_strip_kernel<T, CW, PXT, false, true, false>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff, dwconv3x3_strip_kernel<T, CW, PXT, false, false, true>, Cfg::kSmemBytes);
+  if (ea == cudaSuccess) ea = ensure_dynamic_smem(once_aff_sums, dwconv3x3_strip_kernel<T, CW, PXT, false, true, true>, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_fwd: cudaFuncSetAttribute");
   const int ntw = (int)ceil_div(W, Cfg::TW), ncb = (int)ceil_div(C, Cfg::CB);
-  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6);
+  const int seg = pick_seg_rows(N, H, ntw, ncb, 32, (int64_t)sm_count() * 6 * Cfg::kMinBlocks);
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
-#define UNET_DWF(D_, S_, A_) dwconv3x3_strip_kernel<T, D_, S_, A_><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+#define UNET_DWF(D_, S_, A_) dwconv3x3_strip_kernel<T, CW, PXT, D_, S_, A_><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
       tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, colsum, in_scale, in_shift)
   if (dp.on) UNET_DWF(true, false, false);
   else if (in_scale) { if (colsum) UNET_DWF(false, true, true); else UNET_DWF(false, false, true); }
@@ -343,6 +364,20 @@ static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, voi
 #undef UNET_DWF
   UNET_LAUNCH_CHECK("dwconv3x3_fwd(strip)");
   return UNET_OK;
+}
+
+template <typename T>
+static int dw_fwd_strip_launch(const void* x, int64_t ldx, const float* w9c, void* y, int64_t ldy, int N, int H, int W, int C,
+                               int flip, DropArgs dp, float* colsum, const float* in_scale, const float* in_shift, cudaStream_t st) {
+  UNET_REQUIRE(!(colsum && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: colsum and dropout cannot be combined");
+  UNET_REQUIRE(!(in_scale && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_fwd: input affine and dropout cannot be combined");
+  // 4 output columns per thread (6 loaded: half the shared loads / unpacks / on-load transforms of the 1-column form) when
+  // the row splits into whole groups of 4; 2 per thread for other even widths; 1 per thread otherwise and for narrow rows
+  if (W % 4 == 0 && W >= 32)
+    return dw_fwd_strip_launch_cfg<T, 4, 8>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, in_scale, in_shift, st);
+  if (W % 2 == 0 && W >= 32)
+    return dw_fwd_strip_launch_cfg<T, 2, 16>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, in_scale, in_shift, st);
+  return dw_fwd_strip_launch_cfg<T, 1, 32>(x, ldx, w9c, y, ldy, N, H, W, C, flip, dp, colsum, in_scale, in_shift, st);
 }
 
 // any channel count (used for the 3-channel input image)

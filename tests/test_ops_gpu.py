@@ -110,7 +110,8 @@ def test_dwconv_bwd_weight(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (1, 70, 12, 128), (2, 8, 8, 1024), (2, 33, 40, 16), (1, 67, 35, 32)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 5, 7, 8), (1, 70, 12, 128), (2, 8, 8, 1024), (2, 33, 40, 16), (1, 67, 35, 32),
+                                   (1, 21, 96, 64), (2, 9, 50, 72)])
 @pytest.mark.parametrize("mode", ["plain", "mask", "drop"])
 def test_dwconv_bwd_fused(dtype, shape, mode):
     """one pass over dy: dx (+ReLU mask from x>0, BN-backward sums, or dropout on dx) and dw; ragged strips, views"""
@@ -180,9 +181,10 @@ def test_dwconv_fwd_affine_on_load(dtype, shape):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mask", [False, True])
-def test_dwconv_bwd_fused_affine_on_load(dtype, mask):
+@pytest.mark.parametrize("shape", [(2, 37, 45, 72), (2, 37, 50, 72), (1, 19, 64, 128)])
+def test_dwconv_bwd_fused_affine_on_load(dtype, mask, shape):
     """fused depthwise backward whose x stream is the producer's pre-BN tensor: y = relu(z*scale+shift) formed on load"""
-    n, h, w, c = 2, 37, 45, 72
+    n, h, w, c = shape
     z = RNG.standard_normal((n, h, w, c)).astype(np.float32); dy = RNG.standard_normal((n, h, w, c)).astype(np.float32)
     wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
     sc = RNG.uniform(0.5, 1.5, c).astype(np.float32); sh = (RNG.standard_normal(c) * 0.5).astype(np.float32)

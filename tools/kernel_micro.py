@@ -76,6 +76,19 @@ elif name == "gemm_fold_wgrad":   # its weight gradient: G = d^T [g | z]
     d_, g_, z_ = rnd(M, 128), rnd(M, 64), rnd(M, 64)
     G = torch.zeros((128, 128), device=dev)
     run(lambda: ops.gemm(d_, g_, G, a_trans=True, accumulate=True, B2=z_), M * (128 + 64 + 64) * 2)
+elif name in ("dw_bwd_aff", "dw_bwd128", "dw_bwd_drop256", "dw_bwd_aff128_256"):
+    cc, hh = {"dw_bwd_aff": (64, 512), "dw_bwd128": (128, 512), "dw_bwd_drop256": (256, 256), "dw_bwd_aff128_256": (128, 256)}[name]
+    x, dy, dw = rnd(B, hh, hh, cc), rnd(B, hh, hh, cc), torch.zeros((9, cc), device=dev)
+    dx, w, sums = torch.empty_like(x), torch.rand((9, cc), device=dev), torch.zeros((2, cc), device=dev)
+    sc, sh = torch.rand(cc, device=dev) + 0.5, torch.rand(cc, device=dev) - 0.5
+    nb = 3 * B * hh * hh * cc * 2
+    if "aff" in name:
+        run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, relu_mask=True, bn_sums=sums, x_scale=sc, x_shift=sh), nb)
+    elif "drop" in name:
+        drop = ops.make_dropout(0.2, 5, ctot=cc, c0=0)
+        run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, drop=drop, drop_c_from=cc // 2), nb)
+    else:
+        run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw), nb)
 elif name in ("dw_bwd", "dw_bwd_mask"):
     x, dy, dw = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.zeros((9, 64), device=dev)
     dx, w, sums = torch.empty_like(x), torch.rand((9, 64), device=dev), torch.zeros((2, 64), device=dev)

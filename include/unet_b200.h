@@ -209,6 +209,13 @@ int unet_bn_bwd_coef(const float* sums, const float* gamma, const float* beta, c
                      const float* w, int Cin, int C, void* wab, float* bias, void* stream);
 /* dw[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c];  G fp32 [Cin,2C] = d^T [g | z], coef = [A|B|K], sd[i] = sum_m d[m,i] */
 int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd, float* dw, int Cin, int C, void* stream);
+/* Both contractions above from ONE pass over [g | z] and d (tcgen05; bf16; C == 64, Cin in {64,128}; else UNET_EUNSUPPORTED
+   and the caller issues the two unet_gemm_tc calls):  dd[P,Cin] = [g | z] * wab^T + bias  and  G[Cin,2C] += d^T [g | z].
+   The same TMA-staged 128-pixel x 64-channel tiles serve as the K-major operand of the first product and the MN-major
+   operands of the second, so [g | z] is read from HBM once (SeparableConv2D pointwise backward, u_net.py:14-23). */
+int unet_pw_bwd_fused(const void* g, int64_t ldg, const void* z, int64_t ldz, const void* d, int64_t ldd,
+                      const void* wab, int64_t ldw, const float* bias, void* dd, int64_t lddd,
+                      float* G, int64_t ldG, int64_t P, int Cin, int C, void* stream);
 
 /* ---- MaxPooling2D((2,2)) (u_net.py:69) ---- */
 int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, int H, int W, int C, int dtype, void* stream);

@@ -236,6 +236,34 @@ def test_gemm_tc_operand_concatenation():
     np.testing.assert_allclose(host(got), want, rtol=1e-3, atol=5e-2)
 
 
+@pytest.mark.parametrize("cfg", [(1000, 64), (128 * 300 + 77, 128), (50, 64), (4096, 128)])
+def test_pw_bwd_fused(cfg):
+    """dd = [g | z] wab^T + bias and G += d^T [g | z] from one pass == the two tensor-core GEMMs (bit-exact dd) and NumPy"""
+    bf = torch.bfloat16
+    P, cin = cfg
+    c = 64
+    g, z = dev(RNG.standard_normal((P, c)), bf), dev(RNG.standard_normal((P, c)), bf)
+    d = dev(RNG.standard_normal((P, cin)), bf)
+    wab = dev(RNG.standard_normal((cin, 2 * c)) / np.sqrt(2 * c), bf)
+    bias = dev(RNG.standard_normal(cin))
+    dd_ref = torch.empty((P, cin), device="cuda", dtype=bf); G_ref = torch.zeros((cin, 2 * c), device="cuda")
+    ops.gemm(g, wab, dd_ref, b_trans=True, A2=z, epilogue=ops.EPI_AFFINE, shift=bias, tensor_core=True)
+    ops.gemm(d, g, G_ref, a_trans=True, accumulate=True, B2=z, tensor_core=True)
+    assert ops.pw_bwd_fused_supported(g, z, d, dd_ref)
+    # operands as column views of wider buffers (how the engine holds them), dd into a view as well
+    gbuf = torch.zeros((P, c + 8), device="cuda", dtype=bf); gbuf[:, :c] = g
+    ddbuf = torch.full((P, cin + 16), 7.0, device="cuda", dtype=bf)
+    G = torch.zeros((cin, 2 * c), device="cuda")
+    ops.pw_bwd_fused(gbuf[:, :c], z, d, wab, bias, ddbuf[:, 8:8 + cin], G)
+    assert torch.equal(ddbuf[:, 8:8 + cin], dd_ref)
+    assert bool((ddbuf[:, :8] == 7.0).all()) and bool((ddbuf[:, 8 + cin:] == 7.0).all())
+    np.testing.assert_allclose(host(G), host(G_ref), rtol=1e-4, atol=1e-3 * np.sqrt(P))
+    want = host(d).T @ np.concatenate([host(g), host(z)], 1)
+    np.testing.assert_allclose(host(G), want, rtol=1e-3, atol=2e-3 * np.sqrt(P))
+    ops.pw_bwd_fused(g, z, d, wab, bias, dd_ref, G)              # accumulates
+    np.testing.assert_allclose(host(G), 2 * want, rtol=1e-3, atol=4e-3 * np.sqrt(P))
+
+
 def test_bn_bwd_folded_into_gemms():
     """dz = A*g + B*z + K from the sums (sum g, sum g*y): folded data / weight gradients == explicit BatchNormalization backward"""
     bf = torch.bfloat16

@@ -11,6 +11,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 B, H, W = 64, 512, 512
 VARIANTS = {
     "all on": {},
+    "no fuse_pw_bwd": {"fuse_pw_bwd": False},
     "no fold_bn_bwd": {"fold_bn_bwd": False},
     "no fuse_bn_act": {"fuse_bn_act": False},
     "no defer_dropout": {"defer_dropout": False},
@@ -24,7 +25,7 @@ eng.use_graphs = True
 res = {k: [] for k in VARIANTS}
 for rnd in range(3):
     for name, flags in VARIANTS.items():
-        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act"):
+        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act", "fuse_pw_bwd"):
             setattr(eng, k, flags.get(k, True))
         eng.release_plans()
         for _ in range(3):

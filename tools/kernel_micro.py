@@ -76,6 +76,12 @@ elif name == "gemm_fold_wgrad":   # its weight gradient: G = d^T [g | z]
     d_, g_, z_ = rnd(M, 128), rnd(M, 64), rnd(M, 64)
     G = torch.zeros((128, 128), device=dev)
     run(lambda: ops.gemm(d_, g_, G, a_trans=True, accumulate=True, B2=z_), M * (128 + 64 + 64) * 2)
+elif name in ("pw_bwd_fused64", "pw_bwd_fused128"):   # folded pointwise backward, both contractions from one pass (level 0)
+    cin = 64 if name.endswith("64") else 128
+    g_, z_, d_ = rnd(M, 64), rnd(M, 64), rnd(M, cin)
+    wab, bias = rnd(cin, 128), torch.rand(cin, device=dev)
+    dd, G = torch.empty((M, cin), device=dev, dtype=bf), torch.zeros((cin, 128), device=dev)
+    run(lambda: ops.pw_bwd_fused(g_, z_, d_, wab, bias, dd, G), M * (128 + 2 * cin) * 2)
 elif name in ("dw_bwd_aff", "dw_bwd128", "dw_bwd_drop256", "dw_bwd_aff128_256"):
     cc, hh = {"dw_bwd_aff": (64, 512), "dw_bwd128": (128, 512), "dw_bwd_drop256": (256, 256), "dw_bwd_aff128_256": (128, 256)}[name]
     x, dy, dw = rnd(B, hh, hh, cc), rnd(B, hh, hh, cc), torch.zeros((9, cc), device=dev)

@@ -285,7 +285,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
             float2 st2[NP];
             unpack8<T>(packed, st2);
 #pragma unroll
-            for (int j = 0; j < NP; ++j) { csum[j].x += st2[j].x; csum[j].y += st2[j].y; }
+            for (int j = 0; j < NP; ++j) csum[j] = add2(csum[j], st2[j]);
           }
         }
       }
@@ -896,7 +896,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
             unpack8<T>(packed, g);
 #pragma unroll
             for (int j = 0; j < NP; ++j) {
-              s1[j].x += g[j].x; s1[j].y += g[j].y;
+              s1[j] = add2(s1[j], g[j]);
               s2[j] = fma2(g[j], xm[q][j], s2[j]);
             }
           }

@@ -615,6 +615,190 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused pointwise backward
+// Both contractions of the folded pointwise backward (engine.py, SeparableConv2D pointwise half + BatchNormalization backward)
+// from ONE pass over [g | z] and d:
+//   dd[P,Cin]     = [g | z] * wab^T + bias       (data gradient;   unet_gemm_tc a_trans=0 with A2)
+//   G [Cin,2C]   += d^T [g | z]                  (weight gradient; unet_gemm_tc a_trans=1 with B2)
+// A 128-pixel x 64-channel bf16 box landed by TMA with SWIZZLE_128B is at once a K-major operand (rows = pixels, K = channels:
+// the data gradient's A) and an MN-major operand (K = pixels, MN = channels: both operands of the weight gradient), so each
+// stage {g, z, d chunks} feeds both MMAs and [g | z] is read from HBM once instead of twice.  C = 64 (2C = 128 = the MMA's M
+// for the weight gradient, computed transposed: G^T[2C,Cin] = [g | z]^T d), Cin in {64, 128}.
+//   warp 0   TMA producer (wab once, then one stage per 128 pixels)      warp 1   MMA issuer (8 + 8 tcgen05.mma per stage)
+//   warp 2   TMEM allocator                                              warps 4-7  epilogue: dd tile per stage (TMEM -> +bias ->
+//   bf16 -> swizzled staging -> TMA store), and once at the end G^T (TMEM -> fp32 atomics, coalesced along 2C)
+template <int CIN> struct PbCfg {
+  static constexpr int kPix = 128;
+  static constexpr int kChunk = kPix * 128;                        // 128 pixel rows x 64 bf16
+  static constexpr int kDChunks = CIN / 64;
+  static constexpr int kStageBytes = (2 + kDChunks) * kChunk;      // g | z | d
+  static constexpr int kStages = CIN == 64 ? 3 : 2;
+  static constexpr int kWBytes = 2 * CIN * 128;                    // wab: two K-major chunks of [CIN rows x 64 k]
+  static constexpr int kOutBytes = kDChunks * kChunk;              // dd staging
+  static constexpr int kTmemCols = CIN == 64 ? 256 : 512;          // G^T: CIN columns, dd: 2 x CIN columns
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kWBytes + kOutBytes + CIN * 4 + 256;
+};
+
+struct PbParams { int64_t P; const float* bias; float* G; int64_t ldG; int num_blocks; };
+
+template <int CIN>
+__global__ void __launch_bounds__(256, 1)
+pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmZ,
+                    const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmO, const PbParams p) {
+  using Cfg = PbCfg<CIN>;
+  constexpr int S = Cfg::kStages, kChunk = Cfg::kChunk, DC = Cfg::kDChunks;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stages = smem;
+  uint8_t* smem_w = stages + S * Cfg::kStageBytes;
+  uint8_t* out_tile = smem_w + Cfg::kWBytes;
+  float* s_bias = reinterpret_cast<float*>(out_tile + Cfg::kOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + CIN);
+  uint64_t* full_bar = bars;             // [S]
+  uint64_t* empty_bar = bars + S;        // [S]
+  uint64_t* w_full = bars + 2 * S;
+  uint64_t* d2_full = bars + 2 * S + 1;  // [2]
+  uint64_t* d2_empty = bars + 2 * S + 3; // [2]
+  uint64_t* d1_full = bars + 2 * S + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmG); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmD); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(w_full, 1); mbar_init(d1_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(tmem_ptr, Cfg::kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t d1_tmem = tmem_base;                    // G^T accumulator [128 x CIN]
+  const uint32_t d2_tmem = tmem_base + CIN;              // dd accumulators [2][128 x CIN]
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, Cfg::kWBytes);
+      for (int c = 0; c < 2; ++c) tma_load_2d(smem_w + c * (CIN * 128), &tmW, w_full, c * 64, 0, kEvictLast);
+      int s = 0; uint32_t ph = 0;
+      for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        uint8_t* st = stages + s * Cfg::kStageBytes;
+        const int row = blk * Cfg::kPix;
+        tma_load_2d(st, &tmG, &full_bar[s], 0, row, kEvictFirst);
+        tma_load_2d(st + kChunk, &tmZ, &full_bar[s], 0, row, kEvictFirst);
+        for (int c = 0; c < DC; ++c) tma_load_2d(st + (2 + c) * kChunk, &tmD, &full_bar[s], c * 64, row, kEvictFirst);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_nt = make_idesc(CIN, false, false);    // dd:  A K-major (pixels x channels), B K-major (wab)
+      constexpr uint32_t idesc_tn = make_idesc(CIN, true, true);      // G^T: A MN-major ([g|z]), B MN-major (d)
+      mbar_wait(w_full, 0);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x, ++it) {
+        const int buf = it & 1; const uint32_t bph = (it >> 1) & 1;
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&d2_empty[buf], bph ^ 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stages + s * Cfg::kStageBytes);
+        const uint32_t dd_t = d2_tmem + buf * CIN;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                  // K = [g channels | z channels]
+          const uint64_t adesc = make_smem_desc(st + c * kChunk, 0, 1024);
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_w) + c * (CIN * 128), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(dd_t, adesc + 2 * k, bdesc + 2 * k, idesc_nt, (c | k) != 0);
+        }
+        umma_commit(&d2_full[buf]);
+        const uint64_t gz = make_smem_desc(st, kChunk, 1024);                  // M = 2C = 128: chunks g, z
+        const uint64_t dm = make_smem_desc(st + 2 * kChunk, kChunk, 1024);     // N = CIN: chunks of d
+#pragma unroll
+        for (int k = 0; k < Cfg::kPix / 16; ++k)       // 16 pixel rows x 128 B = 2048 B per UMMA_K
+          umma_bf16(d1_tmem, gz + (uint64_t)(k * 128), dm + (uint64_t)(k * 128), idesc_tn, (it | k) != 0);
+        umma_commit(&empty_bar[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      umma_commit(d1_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;                            // TMEM lane quarter
+    const int row = q * 32 + lane;
+    const int gtid = (warp - 4) * 32 + lane;
+    const bool issuer = gtid == 0;
+    for (int i = gtid; i < CIN; i += 128) s_bias[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+    named_bar_sync(1, 128);
+    const uint32_t sw = (uint32_t)(row & 7);
+    const uint32_t my_row_s = smem_u32(out_tile) + (uint32_t)row * 128u;
+    int it = 0;
+    for (int blk = blockIdx.x; blk < p.num_blocks; blk += gridDim.x, ++it) {
+      const int buf = it & 1; const uint32_t bph = (it >> 1) & 1;
+      mbar_wait(&d2_full[buf], bph);
+      tc_fence_after();
+      if (issuer) bulk_wait_read<0>();                 // the previous store has read the staging tile
+      named_bar_sync(1, 128);
+      const uint32_t t_addr = d2_tmem + buf * CIN + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < DC; ++c) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c * 64 + half * 32, r);
+          tmem_ld_wait();
+          float v[32];
+          const uint32_t pb_s = smem_u32(s_bias + c * 64 + half * 32);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 h4 = lds128f(pb_s + i * 4);
+            v[i] = __uint_as_float(r[i]) + h4.x; v[i + 1] = __uint_as_float(r[i + 1]) + h4.y;
+            v[i + 2] = __uint_as_float(r[i + 2]) + h4.z; v[i + 3] = __uint_as_float(r[i + 3]) + h4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            sts128(my_row_s + c * kChunk + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), o);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d2_empty[buf]);
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (issuer) {
+        for (int c = 0; c < DC; ++c) tma_store_2d(&tmO, out_tile + c * kChunk, c * 64, blk * Cfg::kPix);
+        bulk_commit();
+      }
+    }
+    // G^T[r, ci] (r = column of [g | z], ci = input channel) -> G[ci, r]: a warp's 32 lanes hit 32 consecutive floats
+    mbar_wait(d1_full, 0);
+    tc_fence_after();
+    if (blockIdx.x < p.num_blocks) {
+#pragma unroll
+      for (int half = 0; half < CIN / 32; ++half) {
+        uint32_t r[32];
+        tmem_ld_32x32(d1_tmem + ((uint32_t)(q * 32) << 16) + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(p.G + (int64_t)(half * 32 + i) * p.ldG + row, __uint_as_float(r[i]));
+      }
+    }
+    if (issuer) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 // ================================================================================================ host side
 // bf16 2-D tensor [outer, inner] with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B; OOB reads give zero
 static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, const char* who) {
@@ -716,9 +900,52 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
 
 static int pick_block_n(int64_t N) { return N >= 256 ? 256 : (N > 64 ? 128 : 64); }
 
+template <int CIN>
+static int launch_pw_bwd_fused(const CUtensorMap& tmG, const CUtensorMap& tmZ, const CUtensorMap& tmD, const CUtensorMap& tmW,
+                               const CUtensorMap& tmO, PbParams& p, cudaStream_t st) {
+  using Cfg = PbCfg<CIN>;
+  static SmemAttrOnce once;
+  if (cudaError_t e = ensure_dynamic_smem(once, pw_bwd_fused_kernel<CIN>, Cfg::kSmemBytes))
+    return set_cuda_error(e, "pw_bwd_fused: cudaFuncSetAttribute");
+  const unsigned grid = (unsigned)i64min(p.num_blocks, sm_count());
+  pw_bwd_fused_kernel<CIN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmG, tmZ, tmD, tmW, tmO, p);
+  UNET_LAUNCH_CHECK("pw_bwd_fused");
+  return UNET_OK;
+}
+
 }  // namespace unet
 
 using namespace unet;
+
+extern "C" int unet_pw_bwd_fused(const void* g, int64_t ldg, const void* z, int64_t ldz, const void* d, int64_t ldd,
+                                 const void* wab, int64_t ldw, const float* bias, void* dd, int64_t lddd,
+                                 float* G, int64_t ldG, int64_t P, int Cin, int C, void* stream) {
+  UNET_REQUIRE(g && z && d && wab && dd && G, UNET_EINVAL, "pw_bwd_fused: null pointer");
+  UNET_REQUIRE(P > 0 && P < ((int64_t)1 << 31) - 128, UNET_EINVAL, "pw_bwd_fused: bad P %lld", (long long)P);
+  UNET_REQUIRE(C == 64 && (Cin == 64 || Cin == 128), UNET_EUNSUPPORTED,
+               "pw_bwd_fused: needs C == 64 and Cin in {64, 128} (got C=%d Cin=%d); use unet_gemm_tc twice", C, Cin);
+  UNET_REQUIRE(ldg >= C && ldz >= C && ldd >= Cin && ldw >= 2 * C && lddd >= Cin && ldG >= 2 * C, UNET_EINVAL, "pw_bwd_fused: ld too small");
+  UNET_REQUIRE((lddd * 2) % 16 == 0 && aligned16(dd) && aligned16(G), UNET_EALIGN, "pw_bwd_fused: dd / G need 16B alignment");
+  CUtensorMap tmG, tmZ, tmD, tmW, tmO;
+  if (int e = make_tmap(&tmG, g, C, P, ldg, 128, "pw_bwd_fused(g)")) return e;
+  if (int e = make_tmap(&tmZ, z, C, P, ldz, 128, "pw_bwd_fused(z)")) return e;
+  if (int e = make_tmap(&tmD, d, Cin, P, ldd, 128, "pw_bwd_fused(d)")) return e;
+  if (int e = make_tmap(&tmW, wab, 2 * C, Cin, ldw, Cin, "pw_bwd_fused(wab)")) return e;
+  {
+    PFN_encodeTiled fn = get_encode_fn();
+    cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)P};
+    cuuint64_t strides[1] = {(cuuint64_t)lddd * 2};
+    cuuint32_t box[2] = {64u, 128u};
+    cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, dd, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "pw_bwd_fused: cuTensorMapEncodeTiled(dd) failed with CUresult %d", (int)r);
+  }
+  PbParams p{};
+  p.P = P; p.bias = bias; p.G = G; p.ldG = ldG; p.num_blocks = (int)ceil_div(P, 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  return Cin == 64 ? launch_pw_bwd_fused<64>(tmG, tmZ, tmD, tmW, tmO, p, st) : launch_pw_bwd_fused<128>(tmG, tmZ, tmD, tmW, tmO, p, st);
+}
 
 extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;

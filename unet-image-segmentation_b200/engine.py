@@ -105,6 +105,7 @@ class UNetEngine:
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
+        self.fuse_pw_bwd = True                 # training: folded data + weight gradient of a 64-channel pointwise from one pass
         self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward folded into the block's pointwise
                                                 # data / weight gradient GEMMs (no reduce / apply passes, no dz tensor) wherever the
                                                 # producer of dy has the block's activation in registers: every *_block1 (depthwise
@@ -495,9 +496,13 @@ class UNetEngine:
                 ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef,
                                 w=self._mat(f"{prefix}_sepconv/pointwise_kernel"), wab=wab, bias=bias)
                 d = pl.t[prefix + "/d"]
-                ops.gemm(d, dy, G, a_trans=True, accumulate=True, B2=z)
-                ops.bn_bwd_wgrad_combine(G, coef, sd, gwp)
-                ops.gemm(dy, wab, dd, b_trans=True, A2=z, epilogue=ops.EPI_AFFINE, shift=bias)
+                if self.fuse_pw_bwd and ops.pw_bwd_fused_supported(dy, z, d, dd):
+                    ops.pw_bwd_fused(dy, z, d, wab, bias, dd, G)    # both contractions from one pass over [g | z] and d
+                    ops.bn_bwd_wgrad_combine(G, coef, sd, gwp)
+                else:
+                    ops.gemm(d, dy, G, a_trans=True, accumulate=True, B2=z)
+                    ops.bn_bwd_wgrad_combine(G, coef, sd, gwp)
+                    ops.gemm(dy, wab, dd, b_trans=True, A2=z, epilogue=ops.EPI_AFFINE, shift=bias)
         else:
             ops.bn_bwd_reduce(dy, z, scale, shift, smean, srstd, dgamma, dbeta, relu=True, drop=ydrop)
             ops.bn_bwd_apply(dy, z, scale, shift, smean, srstd, dgamma, dbeta, dz, relu=True, drop=ydrop)

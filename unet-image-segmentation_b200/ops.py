@@ -343,6 +343,32 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
           flops=2 * M * N * K)
 
 
+def pw_bwd_fused_supported(g, z, d, dd) -> bool:
+    """unet_pw_bwd_fused takes bf16 row views with C == 64 and Cin in {64, 128}."""
+    if any(t.dtype != torch.bfloat16 for t in (g, z, d, dd)):
+        return False
+    c, cin = g.shape[-1], d.shape[-1]
+    return c == 64 and cin in (64, 128) and z.shape[-1] == c and dd.shape[-1] == cin
+
+
+def pw_bwd_fused(g, z, d, wab, bias, dd, G) -> None:
+    """Folded pointwise backward in one pass over [g | z] and d:  dd = [g | z] wab^T + bias  and  G += d^T [g | z]
+    (g, z: [P,C]; d, dd: [P,Cin]; wab bf16 [Cin,2C]; bias fp32 [Cin]; G fp32 [Cin,2C], accumulated)."""
+    P, c, ldg = _rows(g, "g")
+    pz, cz, ldz = _rows(z, "z")
+    pd, cin, ldd = _rows(d, "d")
+    po, co, ldo = _rows(dd, "dd")
+    if not (P == pz == pd == po) or cz != c or co != cin:
+        raise ValueError("pw_bwd_fused: g, z [P,C] and d, dd [P,Cin] must agree")
+    if wab.dtype != torch.bfloat16 or tuple(wab.shape) != (cin, 2 * c) or not wab.is_contiguous():
+        raise ValueError("pw_bwd_fused: wab must be a contiguous bf16 [Cin, 2C]")
+    _f32(bias, "bias"); _f32(G, "G")
+    if tuple(G.shape) != (cin, 2 * c) or not G.is_contiguous() or bias.numel() != cin:
+        raise ValueError("pw_bwd_fused: G must be a contiguous fp32 [Cin, 2C] and bias [Cin]")
+    _call("unet_pw_bwd_fused", _p(g), ldg, _p(z), ldz, _p(d), ldd, _p(wab), 2 * c, _p(bias), _p(dd), ldo, _p(G), 2 * c,
+          P, cin, c, _stream(), tag=f"{P}x{cin}x{2 * c}", nbytes=_nbytes(g, z, d, dd), flops=2 * 2 * P * cin * 2 * c)
+
+
 # ------------------------------------------------------------------------------------------------ batch normalisation
 def bn_bwd_coef(sums, gamma, beta, save_mean, save_rstd, count: int, dgamma, dbeta, coef=None, w=None, wab=None, bias=None) -> None:
     """BatchNormalization backward as per-channel coefficients dz = A*g + B*z + K (coef fp32 [3,C]); accumulates dgamma/dbeta;

@@ -125,11 +125,17 @@ int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void* dy, int64_
    the channels below are left to another reader of dx, e.g. unet_convt_bwd_gather).
    x_scale/x_shift (fp32 [C], may be NULL): x is the producer's PRE-BatchNormalization output z and the activation
    y = max(z*x_scale + x_shift, 0) is formed on load (the producer's BN+ReLU pass never materialises y); not with dropout.
+   up_out (may be NULL; relu_mask=0, even H and W): dx is the gradient of a skip-concat buffer whose first up_c channels
+   came out of Conv2DTranspose(k=2,s=2) (u_net.py:88-96).  Those channels are stored un-pixel-shuffled into up_out
+   [N*H/2*W/2, 4*up_c] — row (n, i/2, j/2), column block (i%2, j%2): the operand of the transposed convolution's weight /
+   data gradient GEMMs, i.e. what unet_convt_bwd_gather would produce from dx — instead of into dx, and up_colsum
+   (fp32 [up_c], accumulated, may be NULL) receives their per-channel sums (the Conv2DTranspose bias gradient).
    UNET_EUNSUPPORTED unless C % (8/sizeof(T)) == 0, C >= 8 and all views are 16-byte aligned. */
 int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                        void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
                        int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from,
-                       const float* x_scale, const float* x_shift, void* stream);
+                       const float* x_scale, const float* x_shift,
+                       void* up_out, int up_c, float* up_colsum, void* stream);
 
 /* ---- first conv_block, fused (enc1_block1_sepconv on the RGB image, u_net.py:14-20,63-66; Cin = 3, Cout = 64 only) ---- */
 /* out = pw(dw(x)) [* scale + shift, ReLU if relu]; x contiguous [N,H,W,3]; with colsum/colsq also the BN batch statistics

@@ -147,6 +147,30 @@ def test_dwconv_bwd_fused(dtype, shape, mode):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("shape,drop", [((2, 16, 32, 128), False), ((1, 10, 22, 256), True), ((2, 8, 6, 128), True), ((1, 34, 48, 256), False)])
+def test_dwconv_bwd_fused_up_redirect(dtype, shape, drop):
+    """the upsampled half of a concat gradient leaves un-pixel-shuffled (the Conv2DTranspose gradient operand) with its bias
+    gradient: == the plain kernel followed by unet_convt_bwd_gather; the skip half still lands in dx"""
+    n, h, w, c = shape
+    f = c // 2
+    x = RNG.standard_normal(shape).astype(np.float32); dy = RNG.standard_normal(shape).astype(np.float32)
+    wk = RNG.standard_normal((3, 3, c)).astype(np.float32)
+    xd, dyd, wd = dev(x, dtype), dev(dy, dtype), dev(wk.reshape(9, -1))
+    dp = ops.make_dropout(0.25, 91, ctot=c, c0=0) if drop else None
+    dx_ref = torch.empty(shape, device="cuda", dtype=dtype); dw_ref = torch.zeros((9, c), device="cuda")
+    ops.dwconv3x3_bwd(xd, dyd, wd, dx_ref, dw_ref, drop=dp)
+    g_ref = torch.empty((n * h * w // 4, 4 * f), device="cuda", dtype=dtype); db_ref = torch.zeros(f, device="cuda")
+    ops.convt_bwd_gather(dx_ref[..., :f], g_ref, db_ref)
+    dx = torch.full(shape, 7.0, device="cuda", dtype=dtype); dw = torch.zeros((9, c), device="cuda")
+    g = torch.full_like(g_ref, 3.0); db = torch.zeros(f, device="cuda")
+    ops.dwconv3x3_bwd(xd, dyd, wd, dx, dw, drop=dp, up_out=g, up_colsum=db)
+    assert torch.equal(g, g_ref)
+    assert torch.equal(dx[..., f:], dx_ref[..., f:]) and bool((dx[..., :f] == 7.0).all())
+    np.testing.assert_allclose(host(dw), host(dw_ref), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+    np.testing.assert_allclose(host(db), host(db_ref), rtol=1e-4, atol=1e-3 * np.sqrt(n * h * w))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_dwconv_bwd_fused_partial_dropout(dtype):
     """the Dropout mask is applied to channels >= drop_c_from only (the other half is masked by the reader of dx)"""
     n, h, w, c = 2, 9, 30, 128

@@ -12,6 +12,7 @@ B, H, W = 64, 512, 512
 VARIANTS = {
     "all on": {},
     "no fuse_pw_bwd": {"fuse_pw_bwd": False},
+    "no convt_bwd_direct": {"convt_bwd_direct": False},
     "no fold_bn_bwd": {"fold_bn_bwd": False},
     "no fuse_bn_act": {"fuse_bn_act": False},
     "no defer_dropout": {"defer_dropout": False},
@@ -25,7 +26,7 @@ eng.use_graphs = True
 res = {k: [] for k in VARIANTS}
 for rnd in range(3):
     for name, flags in VARIANTS.items():
-        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act", "fuse_pw_bwd"):
+        for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act", "fuse_pw_bwd", "convt_bwd_direct"):
             setattr(eng, k, flags.get(k, True))
         eng.release_plans()
         for _ in range(3):

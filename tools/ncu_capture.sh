@@ -11,4 +11,7 @@ for spec in "dw_fwd128:dwconv3x3_strip" "dw_fwd_aff:dwconv3x3_strip" "gemm64:gem
   python tools/kernel_micro.py $name 2 > gpurun_out/plain_$name.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 -o gpurun_out/prof_$name python tools/kernel_micro.py $name 2 > gpurun_out/ncu_$name.log 2>&1
 done
+# summarise on the box (gpurun merges at most 64 MiB back): tables into gpurun_out/profiles_out/, then keep only three reports
+UNET_PROFILES_OUT=gpurun_out/profiles_out python tools/ncu_summarize.py r01
 ls -la gpurun_out/*.ncu-rep
+for f in gpurun_out/prof_*.ncu-rep; do case "$f" in *pw_bwd_fused64*|*dw_bwd_aff*|*dw_fwd_aff*) ;; *) rm -f "$f";; esac; done

@@ -2,7 +2,8 @@
 """Summarise gpurun_out/*.ncu-rep and launches.csv into tracked files under profiles/ (run here, no GPU needed)."""
 import csv, io, json, os, subprocess, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("UNET_PROFILES_OUT") or os.path.join(ROOT, "profiles")
+os.makedirs(OUT, exist_ok=True)
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -29,6 +30,24 @@ for f in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
                 rec[h] = f"{v} {u}".strip()
         summary[f[:-8]] = rec
 json.dump(summary, open(os.path.join(OUT, f"ncu_full_{tag}.json"), "w"), indent=1)
+# DRAM bytes (read + write) per launch of each captured kernel, keyed by bench.py's per-kernel table tag (roofline.traffic)
+BENCH_KEY = {"prof_dw_fwd128": "dwconv3x3_fwd[64x512x512x128]", "prof_dw_fwd_aff": "dwconv3x3_fwd[64x512x512x64]",
+             "prof_gemm64": "gemm_tc[nt:16777216x64x64:e3]", "prof_dw_bwd_aff": "dwconv3x3_bwd[64x512x512x64+mask]",
+             "prof_dw_bwd_mask": "dwconv3x3_bwd[64x512x512x64+mask,noaffine]",
+             "prof_pw_bwd_fused64": "pw_bwd_fused[16777216x64x128]", "prof_pw_bwd_fused128": "pw_bwd_fused[16777216x128x128]",
+             "prof_gemm_fold_dgrad": "gemm_tc[nt:16777216x128x128:e1]", "prof_gemm_fold_wgrad": "gemm_tc[wgrad:128x128x16777216:e0]",
+             "prof_bn_bwd_apply": "bn_bwd_apply[16777216x64]", "prof_fused64": "sepconv_fused_fwd[64x512x512x64->64]",
+             "prof_bn_act": "bn_act[64x512x512x64]"}
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+def _bytes(v):
+    num, unit = v.split()[0], (v.split() + ["byte"])[1]
+    return float(num.replace(",", "")) * UNIT.get(unit, 1)
+traffic = {}
+for k, rec in summary.items():
+    if k in BENCH_KEY and "dram__bytes_read.sum" in rec and "dram__bytes_write.sum" in rec:
+        traffic[BENCH_KEY[k]] = int(_bytes(rec["dram__bytes_read.sum"]) + _bytes(rec["dram__bytes_write.sum"]))
+if traffic:
+    json.dump(traffic, open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1)
 with open(os.path.join(OUT, f"ncu_full_{tag}.md"), "w") as o:
     o.write(f"# ncu --set full --clock-control none summaries ({tag}); source: tools/ncu_capture.sh, shapes = train512 level 0 (batch 64, 512x512)\n\n")
     for k, rec in summary.items():

@@ -739,12 +739,18 @@ template <typename T, int CW_ = 1, int PXT_ = 24> struct BwCfg {
   static constexpr int kSmemBytes = S * kStageBytes + 11 * CB * 4 + 2 * S * 8 + 128;
 };
 
-template <typename T, int CW, int PXT, bool DROP, bool RELU_MASK, bool AFFINE>
+// Conv2DTranspose(k=2,s=2) consumer of the first `c_end` channels of dx (the upsampled half of a skip-concat gradient,
+// u_net.py:88-96): those channel blocks are stored un-pixel-shuffled, row (n, i/2, j/2), column block (i%2, j%2), as the
+// [N*H/2*W/2, 4*c_end] operand of the transposed convolution's weight / data gradient GEMMs (what unet_convt_bwd_gather
+// would produce from dx), and their per-channel sums (the bias gradient) are accumulated into `colsum`.
+struct UpArgs { void* out; int c_end; float* colsum; };
+
+template <typename T, int CW, int PXT, bool DROP, bool RELU_MASK, bool AFFINE, bool UP = false>
 __global__ void __launch_bounds__((BwCfg<T, CW, PXT>::kThreads), (BwCfg<T, CW, PXT>::kMinBlocks))
 dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmX,
                            const float* __restrict__ w9c, T* __restrict__ dx, int64_t lddx, float* __restrict__ dw9c,
                            float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp,
-                           int drop_c_from, const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
+                           int drop_c_from, const float* __restrict__ x_scale, const float* __restrict__ x_shift, UpArgs up) {
   using Cfg = BwCfg<T, CW, PXT>;
   constexpr int NV = Cfg::NV, NP = NV / 2, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S, NQ = CW + 2;
   extern __shared__ uint8_t smem_raw[];
@@ -830,6 +836,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
   }
   T* optr = dx + (((int64_t)n * H + (h0 - 2)) * W + col0) * lddx + c;   // advanced one row per dy row
   const int64_t orow = (int64_t)W * lddx;
+  const bool redirect = UP && c0 < up.c_end;      // CTA-uniform
   const uint32_t off = (uint32_t)(px * CW) * 128u + (uint32_t)cg * 8u;
   const uint32_t smem_base = smem_u32(smem);
   int t = h0 - 1;                                   // dy row being consumed; the x row of the same stage slot is t + 1
@@ -900,7 +907,18 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
               s2[j] = fma2(g[j], xm[q][j], s2[j]);
             }
           }
-          *reinterpret_cast<uint2*>(optr + q * lddx) = packed;
+          if (UP && redirect) {                     // un-pixel-shuffled store + bias-gradient sums (see UpArgs)
+            const int hh = t - 1, ww = col0 + q;
+            const int64_t m = ((int64_t)n * (H >> 1) + (hh >> 1)) * (W >> 1) + (ww >> 1);
+            T* dst = reinterpret_cast<T*>(up.out) + (m * 4 + ((hh & 1) * 2 + (ww & 1))) * up.c_end + c;
+            *reinterpret_cast<uint2*>(dst) = packed;
+            float2 g[NP];
+            unpack8<T>(packed, g);
+#pragma unroll
+            for (int j = 0; j < NP; ++j) s1[j] = add2(s1[j], g[j]);
+          } else {
+            *reinterpret_cast<uint2*>(optr + q * lddx) = packed;
+          }
         }
       }
 #pragma unroll
@@ -947,6 +965,14 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
     const int tap = i / Cfg::CB, ch = c0 + i % Cfg::CB;
     if (ch < C) atomicAdd(&dw9c[(int64_t)tap * C + ch], s_acc[i]);
   }
+  if (UP && redirect && up.colsum) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; ++j) fold((j & 1) ? s1[j / 2].y : s1[j / 2].x, 9, j);
+    __syncthreads();
+    for (int i = threadIdx.x; i < Cfg::CB; i += blockDim.x)
+      if (c0 + i < up.c_end) atomicAdd(&up.colsum[c0 + i], s_acc[9 * Cfg::CB + i]);
+  }
   if (RELU_MASK && bn_sums) {
     for (int i = threadIdx.x; i < 2 * Cfg::CB; i += blockDim.x) {
       const int which = i / Cfg::CB, ch = c0 + i % Cfg::CB;
@@ -963,7 +989,7 @@ template <typename T> static bool dw_strip_ok(const void* a, int64_t lda, const 
 template <typename T, int CW, int PXT>
 static int dw_bwd_strip_launch_cfg(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c, void* dx, int64_t lddx,
                                    float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, int drop_c_from,
-                                   const float* x_scale, const float* x_shift, cudaStream_t st) {
+                                   const float* x_scale, const float* x_shift, UpArgs up, cudaStream_t st) {
   using Cfg = BwCfg<T, CW, PXT>;
   static_assert(Cfg::S >= 3, "dwconv3x3_bwd: the stage ring needs at least 3 stages");
   CUtensorMap tmD, tmX;
@@ -983,8 +1009,18 @@ static int dw_bwd_strip_launch_cfg(const void* x, int64_t ldx, const void* dy, i
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd: too many strips");
 #define UNET_BW_LAUNCH(D, M, A) dwconv3x3_bwd_strip_kernel<T, CW, PXT, D, M, A><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
-      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift)
-  if (x_scale) { if (relu_mask) UNET_BW_LAUNCH(false, true, true); else UNET_BW_LAUNCH(false, false, true); }
+      tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up)
+  if (up.out) {       // validated by the caller: no ReLU mask, no x affine
+    static SmemAttrOnce u0, u1;
+    ea = ensure_dynamic_smem(u0, dwconv3x3_bwd_strip_kernel<T, CW, PXT, false, false, false, true>, Cfg::kSmemBytes);
+    if (ea == cudaSuccess) ea = ensure_dynamic_smem(u1, dwconv3x3_bwd_strip_kernel<T, CW, PXT, true, false, false, true>, Cfg::kSmemBytes);
+    if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_bwd: cudaFuncSetAttribute");
+    if (dp.on) dwconv3x3_bwd_strip_kernel<T, CW, PXT, true, false, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
+        tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
+    else dwconv3x3_bwd_strip_kernel<T, CW, PXT, false, false, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
+        tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
+  }
+  else if (x_scale) { if (relu_mask) UNET_BW_LAUNCH(false, true, true); else UNET_BW_LAUNCH(false, false, true); }
   else if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true, false); else UNET_BW_LAUNCH(true, false, false); }
   else            { if (relu_mask) UNET_BW_LAUNCH(false, true, false); else UNET_BW_LAUNCH(false, false, false); }
 #undef UNET_BW_LAUNCH
@@ -995,10 +1031,10 @@ static int dw_bwd_strip_launch_cfg(const void* x, int64_t ldx, const void* dy, i
 template <typename T>
 static int dw_bwd_strip_launch(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c, void* dx, int64_t lddx,
                                float* dw9c, float* bn_sums, int relu_mask, int N, int H, int W, int C, DropArgs dp, int drop_c_from,
-                               const float* x_scale, const float* x_shift, cudaStream_t st) {
+                               const float* x_scale, const float* x_shift, UpArgs up, cudaStream_t st) {
   UNET_REQUIRE(!(x_scale && dp.on), UNET_EUNSUPPORTED, "dwconv3x3_bwd: x affine and dropout cannot be combined");
 #define UNET_BW_CFG(CW_, PXT_) dw_bwd_strip_launch_cfg<T, CW_, PXT_>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, \
-                                                                   dp, drop_c_from, x_scale, x_shift, st)
+                                                                   dp, drop_c_from, x_scale, x_shift, up, st)
   // even widths: 2 columns per thread, strips of 16 columns, 3 CTAs of 128 threads per SM (measured best of {1,2} columns x
   // {128,192,384} threads: 5.1 -> 6.5 TB/s plain, 4.4 -> 5.4 masked at 64 x 512 x 512 x 64); otherwise 1 column, 384 threads
   if (W % 2 == 0 && W >= 16) return UNET_BW_CFG(2, 8);
@@ -1142,8 +1178,14 @@ extern "C" int unet_dwconv3x3_bwd_weight(const void* x, int64_t ldx, const void*
 extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, int64_t lddy, const float* w9c,
                                   void* dx, int64_t lddx, float* dw9c, int N, int H, int W, int C, int dtype,
                                   int relu_mask, float* bn_sums, const unet_dropout* drop, int drop_c_from,
-                                  const float* x_scale, const float* x_shift, void* stream) {
+                                  const float* x_scale, const float* x_shift,
+                                  void* up_out, int up_c, float* up_colsum, void* stream) {
   UNET_REQUIRE(x && dy && w9c && dx && dw9c, UNET_EINVAL, "dwconv3x3_bwd: null pointer");
+  const int cblk = 128 / (dtype == UNET_F32 ? 4 : 2);
+  UNET_REQUIRE(!up_out || (!relu_mask && !x_scale && up_c > 0 && up_c <= C && up_c % cblk == 0 && H % 2 == 0 && W % 2 == 0 && aligned16(up_out)), UNET_EINVAL,
+               "dwconv3x3_bwd: up_out needs relu_mask=0, no x affine, even H and W, and up_c a multiple of the 128-byte channel block inside C");
+  UNET_REQUIRE(up_out || !up_colsum, UNET_EINVAL, "dwconv3x3_bwd: up_colsum needs up_out");
+  const UpArgs up{up_out, up_out ? up_c : 0, up_colsum};
   UNET_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), UNET_EINVAL, "dwconv3x3_bwd: x_scale/x_shift must come together");
   UNET_REQUIRE(!x_scale || (aligned16(x_scale) && aligned16(x_shift)), UNET_EALIGN, "dwconv3x3_bwd: x_scale/x_shift must be 16B aligned");
   UNET_REQUIRE(drop_c_from >= 0 && drop_c_from % (128 / (dtype == UNET_F32 ? 4 : 2)) == 0, UNET_EINVAL,
@@ -1156,12 +1198,12 @@ extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, in
   if (dtype == UNET_F32) {
     UNET_REQUIRE(dw_strip_ok<float>(x, ldx, dy, lddy, C) && dw_strip_ok<float>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%2==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, st);
+    return dw_bwd_strip_launch<float>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, up, st);
   }
   if (dtype == UNET_BF16) {
     UNET_REQUIRE(dw_strip_ok<__nv_bfloat16>(x, ldx, dy, lddy, C) && dw_strip_ok<__nv_bfloat16>(dx, lddx, dy, lddy, C), UNET_EUNSUPPORTED,
                  "dwconv3x3_bwd: needs C%%4==0, C>=8 and 16B-aligned views (use dwconv3x3_fwd(flip) + dwconv3x3_bwd_weight)");
-    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, st);
+    return dw_bwd_strip_launch<__nv_bfloat16>(x, ldx, dy, lddy, w9c, dx, lddx, dw9c, bn_sums, relu_mask, N, H, W, C, dp, drop_c_from, x_scale, x_shift, up, st);
   }
   return set_error(UNET_EINVAL, "dwconv3x3_bwd: bad dtype %d", dtype);
 }

@@ -105,6 +105,7 @@ class UNetEngine:
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
+        self.convt_bwd_direct = True            # training: no un-pixel-shuffle gather pass (the depthwise backward stores that layout)
         self.fuse_pw_bwd = True                 # training: folded data + weight gradient of a 64-channel pointwise from one pass
         self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward folded into the block's pointwise
                                                 # data / weight gradient GEMMs (no reduce / apply passes, no dz tensor) wherever the
@@ -463,7 +464,7 @@ class UNetEngine:
         return y
 
     def _block_train_bwd(self, pl, prefix, x, dy, scr, dx_out=None, ydrop=None, dx_drop=None, mask_for=None, folded=False,
-                         dx_drop_from=0, x_affine=None):
+                         dx_drop_from=0, x_affine=None, up_out=None):
         """dy: gradient w.r.t. the block output (as stored).  scr: two scratch tensors (flat).  Returns dx_out.
         mask_for: prefix of the block that produced x (= its post-ReLU output): dx_out then is the ReLU-masked gradient
         w.r.t. that block's BatchNormalization output and its two BN-backward reductions are accumulated on the way.
@@ -519,9 +520,10 @@ class UNetEngine:
             # both gradients from one pass over dd (+ the producer's ReLU mask and BN-backward reductions)
             ops.dwconv3x3_bwd(x, dd, wd, dx_out, gwd, drop=dx_drop, drop_c_from=dx_drop_from, relu_mask=mask_for is not None,
                               bn_sums=self._fold_bufs(mask_for)[0] if mask_for is not None else None,
-                              x_scale=x_affine[0] if x_affine else None, x_shift=x_affine[1] if x_affine else None)
+                              x_scale=x_affine[0] if x_affine else None, x_shift=x_affine[1] if x_affine else None,
+                              up_out=up_out[0] if up_out else None, up_colsum=up_out[1] if up_out else None)
             return dx_out
-        if mask_for is not None or x_affine is not None:
+        if mask_for is not None or x_affine is not None or up_out is not None:
             raise RuntimeError(f"{prefix}: folded BN backward / BN+ReLU on load need the fused depthwise backward kernel")
         ops.dwconv3x3_bwd_weight(x, dd, gwd)
         if dx_out is not None:
@@ -620,16 +622,22 @@ class UNetEngine:
             dcat[s] = pl.buf(f"dcat{s}", (B, h, w, 2 * f))
             # the Dropout mask of the upsampled half of the concat gradient is applied by its reader (the un-pixel-shuffle
             # gather, a memory-bound kernel with ALU to spare); the depthwise backward kernel masks only the skip half
-            defer = self.defer_dropout and s > 1 and f % 64 == 0
-            self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
-                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None,
-                                  dx_drop_from=f if defer else 0, folded=fold)
-            # Conv2DTranspose backward
             xi = convt_in[s]
             Mi = xi.shape[0] * xi.shape[1] * xi.shape[2]
-            gth = S[o1][: Mi * 4 * f].view(Mi, 4 * f)
-            ops.convt_bwd_gather(dcat[s][..., :f], gth, self.wview(f"dec{s}_upsample/bias", self.g),
-                                 drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
+            gth = S[o1][: Mi * 4 * f].view(Mi, 4 * f)            # S[o1] held dz, dead once dd exists
+            dbias = self.wview(f"dec{s}_upsample/bias", self.g)
+            # gather-free: the depthwise backward kernel stores the upsampled half of the concat gradient un-pixel-shuffled
+            # (the operand of the Conv2DTranspose gradient GEMMs) and accumulates the bias gradient; it then masks both halves
+            direct = (self.convt_bwd_direct and self.fuse_dw_bwd and f % (64 if self.act_dtype == torch.bfloat16 else 32) == 0
+                      and ops.dwconv3x3_bwd_supported(cats[s], dx, dcat[s]))
+            defer = (not direct) and self.defer_dropout and s > 1 and f % 64 == 0
+            self._block_train_bwd(pl, f"dec{s}_block1", cats[s], dx, (S[o1], S[o2]), dx_out=dcat[s],
+                                  dx_drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None,
+                                  dx_drop_from=f if defer else 0, folded=fold, up_out=(gth, dbias) if direct else None)
+            # Conv2DTranspose backward
+            if not direct:
+                ops.convt_bwd_gather(dcat[s][..., :f], gth, dbias,
+                                     drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
             ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True)
             dy = S[ci][: Mi * 2 * f].view(xi.shape)
             self._convt_dgrad(s, gth, dy)

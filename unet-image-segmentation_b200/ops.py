@@ -159,9 +159,12 @@ def dwconv3x3_bwd_supported(x: torch.Tensor, dy: torch.Tensor, dx: torch.Tensor)
 
 def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torch.Tensor, dw9c: torch.Tensor,
                   relu_mask: bool = False, bn_sums: Optional[torch.Tensor] = None, drop: Optional[Dropout] = None,
-                  drop_c_from: int = 0, x_scale: Optional[torch.Tensor] = None, x_shift: Optional[torch.Tensor] = None) -> None:
+                  drop_c_from: int = 0, x_scale: Optional[torch.Tensor] = None, x_shift: Optional[torch.Tensor] = None,
+                  up_out: Optional[torch.Tensor] = None, up_colsum: Optional[torch.Tensor] = None) -> None:
     """SeparableConv2D depthwise backward in one pass over dy: input gradient (optionally ReLU-masked by x > 0, with the
-    BatchNormalization-backward reductions sum(g), sum(g*x) accumulated into bn_sums [2,C]) + weight gradient."""
+    BatchNormalization-backward reductions sum(g), sum(g*x) accumulated into bn_sums [2,C]) + weight gradient.
+    up_out [N*H/2*W/2, 4*up_c] (contiguous): the first up_c channels of dx are stored un-pixel-shuffled there (the operand of
+    the Conv2DTranspose gradient GEMMs) instead of into dx; up_colsum (fp32 [up_c], accumulated): their per-channel sums."""
     n, h, w, c, ldx = _nhwc(x, "x")
     n2, h2, w2, c2, lddy = _nhwc(dy, "dy")
     n3, h3, w3, c3, lddx = _nhwc(dx, "dx")
@@ -170,8 +173,20 @@ def dwconv3x3_bwd(x: torch.Tensor, dy: torch.Tensor, w9c: torch.Tensor, dx: torc
     _f32(w9c, "w9c"); _f32(dw9c, "dw9c"); _f32(bn_sums, "bn_sums"); _f32(x_scale, "x_scale"); _f32(x_shift, "x_shift")
     if w9c.numel() != 9 * c or dw9c.numel() != 9 * c or (bn_sums is not None and bn_sums.numel() != 2 * c):
         raise ValueError("dwconv3x3_bwd: w9c / dw9c must hold 9*C floats and bn_sums 2*C")
+    up_c = 0
+    if up_out is not None:
+        if up_out.dtype != x.dtype or up_out.dim() != 2 or not up_out.is_contiguous() or up_out.shape[1] % 4 != 0 \
+                or up_out.shape[0] * 4 != n * h * w:
+            raise ValueError("dwconv3x3_bwd: up_out must be a contiguous [N*H/2*W/2, 4*up_c] tensor of x's dtype")
+        up_c = up_out.shape[1] // 4
+        _f32(up_colsum, "up_colsum")
+        if up_colsum is not None and up_colsum.numel() != up_c:
+            raise ValueError("dwconv3x3_bwd: up_colsum must hold up_c floats")
+    elif up_colsum is not None:
+        raise ValueError("dwconv3x3_bwd: up_colsum needs up_out")
     _call("unet_dwconv3x3_bwd", _p(x), ldx, _p(dy), lddy, _p(w9c), _p(dx), lddx, _p(dw9c), n, h, w, c, _dt(x),
-          int(relu_mask), _p(bn_sums), _dref(drop), int(drop_c_from), _p(x_scale), _p(x_shift), _stream(),
+          int(relu_mask), _p(bn_sums), _dref(drop), int(drop_c_from), _p(x_scale), _p(x_shift),
+          _p(up_out), up_c, _p(up_colsum), _stream(),
           tag=f"{n}x{h}x{w}x{c}" + ("+mask" if relu_mask else "") + ("+drop" if drop is not None else ""), nbytes=_nbytes(x, dy, dx, w9c), flops=36 * x.numel())
 
 

@@ -82,13 +82,18 @@ elif name in ("pw_bwd_fused64", "pw_bwd_fused128"):   # folded pointwise backwar
     wab, bias = rnd(cin, 128), torch.rand(cin, device=dev)
     dd, G = torch.empty((M, cin), device=dev, dtype=bf), torch.zeros((cin, 128), device=dev)
     run(lambda: ops.pw_bwd_fused(g_, z_, d_, wab, bias, dd, G), M * (128 + 2 * cin) * 2)
-elif name in ("dw_bwd_aff", "dw_bwd128", "dw_bwd_drop256", "dw_bwd_aff128_256"):
-    cc, hh = {"dw_bwd_aff": (64, 512), "dw_bwd128": (128, 512), "dw_bwd_drop256": (256, 256), "dw_bwd_aff128_256": (128, 256)}[name]
+elif name in ("dw_bwd_aff", "dw_bwd128", "dw_bwd_drop256", "dw_bwd_aff128_256", "dw_bwd128_up", "dw_bwd_drop256_up"):
+    cc, hh = {"dw_bwd_aff": (64, 512), "dw_bwd128": (128, 512), "dw_bwd_drop256": (256, 256), "dw_bwd_aff128_256": (128, 256),
+              "dw_bwd128_up": (128, 512), "dw_bwd_drop256_up": (256, 256)}[name]
     x, dy, dw = rnd(B, hh, hh, cc), rnd(B, hh, hh, cc), torch.zeros((9, cc), device=dev)
     dx, w, sums = torch.empty_like(x), torch.rand((9, cc), device=dev), torch.zeros((2, cc), device=dev)
     sc, sh = torch.rand(cc, device=dev) + 0.5, torch.rand(cc, device=dev) - 0.5
     nb = 3 * B * hh * hh * cc * 2
-    if "aff" in name:
+    if name.endswith("_up"):     # dec*_block1: upsampled half of the concat gradient stored un-pixel-shuffled + bias gradient
+        gth, db = torch.empty((B * hh * hh // 4, 2 * cc), device=dev, dtype=bf), torch.zeros(cc // 2, device=dev)
+        drop = ops.make_dropout(0.2, 5, ctot=cc, c0=0) if "drop" in name else None
+        run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, drop=drop, up_out=gth, up_colsum=db), nb)
+    elif "aff" in name:
         run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, relu_mask=True, bn_sums=sums, x_scale=sc, x_shift=sh), nb)
     elif "drop" in name:
         drop = ops.make_dropout(0.2, 5, ctot=cc, c0=0)

@@ -837,6 +837,12 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
   T* optr = dx + (((int64_t)n * H + (h0 - 2)) * W + col0) * lddx + c;   // advanced one row per dy row
   const int64_t orow = (int64_t)W * lddx;
   const bool redirect = UP && c0 < up.c_end;      // CTA-uniform
+  // un-pixel-shuffled destination of pixel (n, hh, ww), channel c: ((n*H/2 + hh/2) * W/2 + ww/2) * 4F + ((hh%2)*2 + ww%2) * F + c
+  T* const up_base = reinterpret_cast<T*>(up.out);
+  const int up_nh = n * (H >> 1), up_rowstride = (W >> 1) * 4 * up.c_end;        // 2*W*F < 2^31 (checked by the launcher)
+  int up_col[CW];
+#pragma unroll
+  for (int q = 0; q < CW; ++q) up_col[q] = ((col0 + q) >> 1) * 4 * up.c_end + ((col0 + q) & 1) * up.c_end + c;
   const uint32_t off = (uint32_t)(px * CW) * 128u + (uint32_t)cg * 8u;
   const uint32_t smem_base = smem_u32(smem);
   int t = h0 - 1;                                   // dy row being consumed; the x row of the same stage slot is t + 1
@@ -884,6 +890,9 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
           acc[6][j] = fma2(xp[q][j], d[q + 2][j], acc[6][j]); acc[7][j] = fma2(xp[q][j], d[q + 1][j], acc[7][j]); acc[8][j] = fma2(xp[q][j], d[q][j], acc[8][j]);
         }
       if ((!EDGE || (t > h0 && t <= h1)) && live) {   // dx row t-1 is complete once flipped-kernel row 2 has seen dy row t
+        T* up_row = nullptr;
+        if (UP && redirect)     // row (n, (t-1)/2) of the un-pixel-shuffled operand, column block ((t-1)%2, .): one wide multiply per row
+          up_row = up_base + (int64_t)(up_nh + ((t - 1) >> 1)) * up_rowstride + ((t - 1) & 1) * 2 * up.c_end;
 #pragma unroll
         for (int q = 0; q < CW; ++q) {
           float o[NV];
@@ -908,14 +917,9 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
             }
           }
           if (UP && redirect) {                     // un-pixel-shuffled store + bias-gradient sums (see UpArgs)
-            const int hh = t - 1, ww = col0 + q;
-            const int64_t m = ((int64_t)n * (H >> 1) + (hh >> 1)) * (W >> 1) + (ww >> 1);
-            T* dst = reinterpret_cast<T*>(up.out) + (m * 4 + ((hh & 1) * 2 + (ww & 1))) * up.c_end + c;
-            *reinterpret_cast<uint2*>(dst) = packed;
-            float2 g[NP];
-            unpack8<T>(packed, g);
+            *reinterpret_cast<uint2*>(up_row + up_col[q]) = packed;
 #pragma unroll
-            for (int j = 0; j < NP; ++j) s1[j] = add2(s1[j], g[j]);
+            for (int j = 0; j < NP; ++j) s1[j] = add2(s1[j], make_float2(o[2 * j], o[2 * j + 1]));   // fp32 values before rounding
           } else {
             *reinterpret_cast<uint2*>(optr + q * lddx) = packed;
           }
@@ -1185,6 +1189,8 @@ extern "C" int unet_dwconv3x3_bwd(const void* x, int64_t ldx, const void* dy, in
   UNET_REQUIRE(!up_out || (!relu_mask && !x_scale && up_c > 0 && up_c <= C && up_c % cblk == 0 && H % 2 == 0 && W % 2 == 0 && aligned16(up_out)), UNET_EINVAL,
                "dwconv3x3_bwd: up_out needs relu_mask=0, no x affine, even H and W, and up_c a multiple of the 128-byte channel block inside C");
   UNET_REQUIRE(up_out || !up_colsum, UNET_EINVAL, "dwconv3x3_bwd: up_colsum needs up_out");
+  UNET_REQUIRE(!up_out || ((int64_t)2 * W * up_c < ((int64_t)1 << 31) && (int64_t)N * (H / 2) < ((int64_t)1 << 31)), UNET_EUNSUPPORTED,
+               "dwconv3x3_bwd: up_out row stride overflows 32 bits");
   const UpArgs up{up_out, up_out ? up_c : 0, up_colsum};
   UNET_REQUIRE((x_scale == nullptr) == (x_shift == nullptr), UNET_EINVAL, "dwconv3x3_bwd: x_scale/x_shift must come together");
   UNET_REQUIRE(!x_scale || (aligned16(x_scale) && aligned16(x_shift)), UNET_EALIGN, "dwconv3x3_bwd: x_scale/x_shift must be 16B aligned");

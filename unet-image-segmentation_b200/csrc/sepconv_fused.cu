@@ -180,12 +180,18 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         const uint32_t xs = smem_u32(stages + s * Cfg::kStageBytes) + x_off;
         const float2 z2 = make_float2(0.f, 0.f);
         float2 prev0[2] = {z2, z2}, cur0[2] = {z2, z2}, prev1[2] = {z2, z2}, cur1[2] = {z2, z2};
+        // software-pipelined by one row: the shared loads of row r+1 are issued before the FMAs and the A-tile stores of row r
+        // (the explicit ld/st.shared keep program order, so without this every row pays the full shared-load latency)
+        uint2 n0 = lds64(xs), n1 = lds64(xs + 128), n2 = lds64(xs + 256), n3 = lds64(xs + 384);
 #pragma unroll
         for (int r = 0; r < kXRows; ++r) {
-          const uint2 r0 = lds64(xs + r * kXCols * 128);           // halo columns 2cp .. 2cp+3 of this row
-          const uint2 r1 = lds64(xs + r * kXCols * 128 + 128);
-          const uint2 r2 = lds64(xs + r * kXCols * 128 + 256);
-          const uint2 r3 = lds64(xs + r * kXCols * 128 + 384);
+          const uint2 r0 = n0, r1 = n1, r2 = n2, r3 = n3;          // halo columns 2cp .. 2cp+3 of this row
+          if (r + 1 < kXRows) {
+            n0 = lds64(xs + (r + 1) * kXCols * 128);
+            n1 = lds64(xs + (r + 1) * kXCols * 128 + 128);
+            n2 = lds64(xs + (r + 1) * kXCols * 128 + 256);
+            n3 = lds64(xs + (r + 1) * kXCols * 128 + 384);
+          }
           float2 q0[2], q1[2], q2[2], q3[2];
           q0[0] = make_float2(__uint_as_float(r0.x << 16), __uint_as_float(r0.x & 0xffff0000u)); q0[1] = make_float2(__uint_as_float(r0.y << 16), __uint_as_float(r0.y & 0xffff0000u));
           q1[0] = make_float2(__uint_as_float(r1.x << 16), __uint_as_float(r1.x & 0xffff0000u)); q1[1] = make_float2(__uint_as_float(r1.y << 16), __uint_as_float(r1.y & 0xffff0000u));

@@ -157,7 +157,7 @@ int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, const float*
 
 /* ---- whole conv_block for inference (u_net.py:5-26): y = act((dw3x3(x) . Wp) * scale + shift), depthwise result kept on chip ---- */
 /* bf16 only.  x: [N,H,W,Cin] view (ldx); wp_t: pointwise kernel TRANSPOSED, bf16 [Cout, Cin] (ldw); scale/shift: folded
-   BatchNormalization (or NULL / bias); y: [N,H,W,Cout] view (ldy).  Cin <= 512, Cout <= 128, both multiples of 8.
+   BatchNormalization (or NULL / bias); y: [N,H,W,Cout] view (ldy).  Cin <= 256, Cout <= 128, both multiples of 8.
    Optional fused output head (Cout <= 64; u_net.py:105-112): head_out[N*H*W, classes] = sigmoid|softmax(y . head_w + head_b);
    y may then be NULL (the last activation of the network is never written). */
 int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* wd9c, const void* wp_t, int64_t ldw,

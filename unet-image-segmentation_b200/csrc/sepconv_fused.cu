@@ -42,12 +42,14 @@ constexpr int kXRows = kPH + 2, kXCols = kPW + 2;
 constexpr int kXBytes = kXRows * kXCols * 128;          // 23040
 constexpr int kXStage = 23 * 1024;                      // padded so that the B tile behind it is 1024 B aligned
 constexpr int kTileBytes = 128 * 128;
-constexpr int kMaxCin = 512;
+constexpr int kMaxCin = 256;
 
 template <int BLOCK_N> struct FsCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kXStage + kBBytes;
-  static constexpr int kStages = 3;
+  // the stage ring bounds the number of patches in flight per SM (a stage is held from its TMA until the MMA that read its
+  // pointwise-kernel slice retires): 4 stages where they fit in 227 KB
+  static constexpr int kStages = BLOCK_N == 64 ? 4 : 3;
   static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;     // fused output head: w[class][64] + bias[8], per group
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
                                     2 * (2 * BLOCK_N + kHeadFloats) * 4 /*scale,shift[,head] per group*/ +

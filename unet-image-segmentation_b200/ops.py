@@ -239,7 +239,7 @@ def stem_bwd_folded(g: torch.Tensor, z: torch.Tensor, coef: torch.Tensor, d3: to
 # ------------------------------------------------------------------------------------------------ fused conv_block (inference)
 def sepconv_fused_supported(x: torch.Tensor, cout: int) -> bool:
     cin = x.shape[-1]
-    return x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and cin <= 512 and cout <= 128
+    return x.dtype == torch.bfloat16 and cin % 8 == 0 and cout % 8 == 0 and cin <= 256 and cout <= 128
 
 
 def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Optional[torch.Tensor],

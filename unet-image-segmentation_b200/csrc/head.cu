@@ -434,9 +434,9 @@ head_fwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
   const int64_t p_begin = (int64_t)blockIdx.x * pix_per_block;
   const int64_t p_end = i64min(hw, p_begin + pix_per_block);
   float si = 0.f, st = 0.f, sp = 0.f;
-  constexpr int U = 2;
+  constexpr int U = 4;                    // pixels per thread in flight: 4 x 16-byte loads before the first FMA
   for (int64_t p0 = p_begin; p0 < p_end; p0 += 32 * U) {
-    float acc[U][8];
+    float2 acc2[U][4];                     // class pairs: every FMA below is a packed FFMA2
     int64_t mrow[U]; bool live[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -444,7 +444,7 @@ head_fwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
       live[u] = p < p_end;
       mrow[u] = n * hw + (live[u] ? p : p_begin);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) acc[u][c] = 0.f;
+      for (int c = 0; c < 4; ++c) acc2[u][c] = make_float2(0.f, 0.f);
     }
     for (int k0 = sub * 8; k0 < K; k0 += 64) {
       float v[U][8];
@@ -456,22 +456,24 @@ head_fwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
         const float4 w1 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j) + 4]);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          acc[u][0] = fmaf(v[u][j], w0.x, acc[u][0]); acc[u][1] = fmaf(v[u][j], w0.y, acc[u][1]);
-          acc[u][2] = fmaf(v[u][j], w0.z, acc[u][2]); acc[u][3] = fmaf(v[u][j], w0.w, acc[u][3]);
-          acc[u][4] = fmaf(v[u][j], w1.x, acc[u][4]); acc[u][5] = fmaf(v[u][j], w1.y, acc[u][5]);
-          acc[u][6] = fmaf(v[u][j], w1.z, acc[u][6]); acc[u][7] = fmaf(v[u][j], w1.w, acc[u][7]);
+          const float2 vv = make_float2(v[u][j], v[u][j]);
+          acc2[u][0] = fma2(vv, make_float2(w0.x, w0.y), acc2[u][0]); acc2[u][1] = fma2(vv, make_float2(w0.z, w0.w), acc2[u][1]);
+          acc2[u][2] = fma2(vv, make_float2(w1.x, w1.y), acc2[u][2]); acc2[u][3] = fma2(vv, make_float2(w1.z, w1.w), acc2[u][3]);
         }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      float acc[1][8];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { acc[0][2 * c] = acc2[u][c].x; acc[0][2 * c + 1] = acc2[u][c].y; }
       // reduce-scatter over the 8 lanes of the pixel: lane `sub` ends with the full logit of class `sub`
       float r4[4], r2[2], logit;
       const bool hi4 = sub & 4, hi2 = sub & 2, hi1 = sub & 1;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float send = hi4 ? acc[u][i] : acc[u][i + 4];
-        const float keep = hi4 ? acc[u][i + 4] : acc[u][i];
+        const float send = hi4 ? acc[0][i] : acc[0][i + 4];
+        const float keep = hi4 ? acc[0][i + 4] : acc[0][i];
         r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
 #pragma unroll
@@ -536,39 +538,57 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
   const float ca = sub < C ? coef[(n * C + sub) * 2] : 0.f, cb = sub < C ? coef[(n * C + sub) * 2 + 1] : 0.f;
   float dbs = 0.f;
   for (int k0 = sub * 8; k0 < K; k0 += 64) {
-    float dwacc[8][8];
+    float2 dwacc[8][4];                    // [channel][class pair]: packed FFMA2
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dwacc[j][c] = 0.f;
+      for (int c = 0; c < 4; ++c) dwacc[j][c] = make_float2(0.f, 0.f);
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+    // software-pipelined by one pixel: the loads of the next pixel are issued before the 128 FMAs of the current one
+    float vn[8], prn = 0.f, ytn = 0.f;
+    {
+      const int64_t p = p_begin + slot;
+      const int64_t m = n * hw + (p < p_end ? p : p_begin);
+      load8(x + m * ldx + k0, vn);
+      if (sub < C) { prn = __ldg(probs + m * C + sub); ytn = __ldg(y_true + m * C + sub); }
+    }
     for (int64_t p0 = p_begin; p0 < p_end; p0 += 32) {
       const int64_t p = p0 + slot;
       const bool live = p < p_end;
       const int64_t m = n * hw + (live ? p : p_begin);
       float v[8];
-      load8(x + m * ldx + k0, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = vn[j];
       // lane `sub` owns class `sub`: dz_c = p_c (g_c - sum_c' g_c' p_c')
-      float pr = 0.f, g = 0.f;
-      if (sub < C) { pr = __ldg(probs + m * C + sub); g = fmaf(ca, __ldg(y_true + m * C + sub), cb); }
+      const float pr = prn, g = sub < C ? fmaf(ca, ytn, cb) : 0.f;
+      if (p0 + 32 < p_end) {
+        const int64_t pn = p0 + 32 + slot;
+        const int64_t mn = n * hw + (pn < p_end ? pn : p_begin);
+        load8(x + mn * ldx + k0, vn);
+        if (sub < C) { prn = __ldg(probs + mn * C + sub); ytn = __ldg(y_true + mn * C + sub); }
+      }
       float dot = g * pr;
       dot += __shfl_xor_sync(0xffffffffu, dot, 1); dot += __shfl_xor_sync(0xffffffffu, dot, 2); dot += __shfl_xor_sync(0xffffffffu, dot, 4);
       const float dz_own = live ? pr * (g - dot) : 0.f;
-      float dz[8];
+      float2 dz2[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) dz[c] = __shfl_sync(0xffffffffu, dz_own, (lane & ~7) + c);
+      for (int c = 0; c < 4; ++c)
+        dz2[c] = make_float2(__shfl_sync(0xffffffffu, dz_own, (lane & ~7) + 2 * c), __shfl_sync(0xffffffffu, dz_own, (lane & ~7) + 2 * c + 1));
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 w0 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j)]);      // 16-byte shared loads, 8 distinct rows per warp
         const float4 w1 = *reinterpret_cast<const float4*>(&s_w[mc_row(k0 + j) + 4]);
-        const float wk[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        float sacc = 0.f;
+        float2 sacc = mul2(dz2[0], make_float2(w0.x, w0.y));
+        sacc = fma2(dz2[1], make_float2(w0.z, w0.w), sacc);
+        sacc = fma2(dz2[2], make_float2(w1.x, w1.y), sacc);
+        sacc = fma2(dz2[3], make_float2(w1.z, w1.w), sacc);
+        const float2 vv = make_float2(v[j], v[j]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { sacc = fmaf(dz[c], wk[c], sacc); dwacc[j][c] = fmaf(v[j], dz[c], dwacc[j][c]); }
-        o[j] = sacc;
+        for (int c = 0; c < 4; ++c) dwacc[j][c] = fma2(vv, dz2[c], dwacc[j][c]);
+        o[j] = sacc.x + sacc.y;
       }
       if (bn_sums && live) {
 #pragma unroll
@@ -593,7 +613,7 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        float sacc = dwacc[j][c];
+        float sacc = (c & 1) ? dwacc[j][c >> 1].y : dwacc[j][c >> 1].x;
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 8);
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
         if (lane < 8) atomicAdd(&s_dw[(k0 + j) * 8 + c], sacc);

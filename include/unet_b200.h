@@ -159,11 +159,14 @@ int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, const float*
 /* bf16 only.  x: [N,H,W,Cin] view (ldx); wp_t: pointwise kernel TRANSPOSED, bf16 [Cout, Cin] (ldw); scale/shift: folded
    BatchNormalization (or NULL / bias); y: [N,H,W,Cout] view (ldy).  Cin <= 256, Cout <= 128, both multiples of 8.
    Optional fused output head (Cout <= 64; u_net.py:105-112): head_out[N*H*W, classes] = sigmoid|softmax(y . head_w + head_b);
-   y may then be NULL (the last activation of the network is never written). */
+   y may then be NULL (the last activation of the network is never written).
+   pooled (may be NULL; needs y, even H and W): additionally MaxPooling2D((2,2)) (u_net.py:69) of the stored activation,
+   [N,H/2,W/2,Cout] view (ldp) — the encoder's skip tensor is then not read back by unet_maxpool2x2_fwd. */
 int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* wd9c, const void* wp_t, int64_t ldw,
                            const float* scale, const float* shift, int relu, void* y, int64_t ldy,
                            int N, int H, int W, int Cin, int Cout,
-                           const float* head_w, const float* head_b, float* head_out, int head_classes, void* stream);
+                           const float* head_w, const float* head_b, float* head_out, int head_classes,
+                           void* pooled, int64_t ldp, void* stream);
 
 /* ---- dense contractions: SeparableConv2D pointwise half, Conv2DTranspose, their gradients ---- */
 /* fp32-exact CUDA-core path (any shape, either dtype) */

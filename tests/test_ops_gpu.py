@@ -881,6 +881,25 @@ def test_sepconv_fused(cfg):
     assert np.all(got[..., :64] == 0)
 
 
+@pytest.mark.parametrize("cfg", [(2, 16, 32, 64, 64), (1, 24, 20, 128, 64), (2, 10, 38, 64, 128), (1, 64, 64, 128, 128)])
+def test_sepconv_fused_with_pool(cfg):
+    """MaxPooling2D((2,2)) from the staged tile of the fused conv_block kernel == max over the stored activation, bit-exact;
+    ragged patches, channel-sliced destinations"""
+    n, h, w, cin, cout = cfg
+    x = dev(RNG.standard_normal((n, h, w, cin)), torch.bfloat16)
+    wd = dev(RNG.standard_normal((9, cin)) / 3)
+    wpt = dev(RNG.standard_normal((cout, cin)) / np.sqrt(cin), torch.bfloat16)
+    sh = dev(RNG.standard_normal(cout) * 0.3)
+    ybuf = torch.zeros((n, h, w, 2 * cout), device="cuda", dtype=torch.bfloat16)
+    y_ref = torch.empty((n, h, w, cout), device="cuda", dtype=torch.bfloat16)
+    pbuf = torch.full((n, h // 2, w // 2, cout + 8), 5.0, device="cuda", dtype=torch.bfloat16)
+    ops.sepconv_fused(x, wd, wpt, y_ref, shift=sh)
+    ops.sepconv_fused(x, wd, wpt, ybuf[..., cout:], shift=sh, pooled=pbuf[..., :cout])
+    assert torch.equal(ybuf[..., cout:], y_ref) and bool((ybuf[..., :cout] == 0).all())
+    want = y_ref.float().view(n, h // 2, 2, w // 2, 2, cout).amax(dim=(2, 4))
+    assert torch.equal(pbuf[..., :cout].float(), want) and bool((pbuf[..., cout:] == 5.0).all())
+
+
 @pytest.mark.parametrize("classes", [1, 8])
 def test_sepconv_fused_with_head(classes):
     n, h, w, cin, cout = 2, 19, 37, 64, 64

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "unet_stem_fwd": [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "unet_stem_bwd_folded": [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp],
     "unet_stem_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
-    "unet_sepconv_fused_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "unet_sepconv_fused_fwd": [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i64, _vp],
     "unet_gemm_simt": [C.POINTER(GemmArgs), _vp],
     "unet_gemm_tc": [C.POINTER(GemmArgs), _vp],
     "unet_bn_fold": [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],

@@ -12,7 +12,9 @@
 //                 partial sums per output in registers (4 conflict-free 8-byte shared loads + 2 x 9 packed FFMA2 per row),
 //                 packs bf16 and stores into the A tile (K-major, SWIZZLE_128B) -> fence.proxy.async -> mbarrier
 //   warps 12-19   two epilogue groups (one per accumulator stage): tcgen05.ld -> scale/shift/ReLU -> bf16 -> swizzled staging
-//                 tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC destination
+//                 tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC destination;
+//                 optionally MaxPooling2D((2,2)) (u_net.py:69) of the staged tile -> a second 4-D TMA store of the 4x8 pooled
+//                 patch, so the encoder's skip tensor is not read back for pooling
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,6 +32,11 @@ __device__ __forceinline__ uint64_t fs_smem_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t fs_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+__device__ __forceinline__ uint32_t fs_max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
 __device__ __forceinline__ void fs_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void fs_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fs_tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
@@ -43,6 +50,7 @@ constexpr int kXBytes = kXRows * kXCols * 128;          // 23040
 constexpr int kXStage = 23 * 1024;                      // padded so that the B tile behind it is 1024 B aligned
 constexpr int kTileBytes = 128 * 128;
 constexpr int kMaxCin = 256;
+constexpr int kPoolBytes = (kPH / 2) * (kPW / 2) * 128;   // pooled patch: 32 pixels x 128 B
 
 template <int BLOCK_N> struct FsCfg {
   static constexpr int kBBytes = BLOCK_N * 128;
@@ -52,6 +60,7 @@ template <int BLOCK_N> struct FsCfg {
   static constexpr int kStages = BLOCK_N == 64 ? 4 : 3;
   static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;     // fused output head: w[class][64] + bias[8], per group
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
+                                    2 * kPoolBytes /*pooled staging*/ +
                                     2 * (2 * BLOCK_N + kHeadFloats) * 4 /*scale,shift[,head] per group*/ +
                                     9 * kMaxCin * 4 /*dw weights*/ + 256;
 };
@@ -61,13 +70,14 @@ struct FsParams {
   int tiles_h, tiles_w, total_tiles, num_k;
   const float* wd9c; const float* scale; const float* shift;
   int store_y;                                                       // 0: the activation itself is not needed (head only)
+  int store_pool;                                                    // also store the 2x2 max-pooled activation (tmP)
   const float* head_w; const float* head_b; float* head_out; int head_classes;   // optional fused 1x1 output head (Cout <= 64)
 };
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(640, 1)
 sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmY, const FsParams p) {
+                     const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP, const FsParams p) {
   using Cfg = FsCfg<BLOCK_N>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -75,7 +85,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   uint8_t* stages = smem;
   uint8_t* a_tiles = stages + S * Cfg::kStageBytes;                  // [2][16 KB]
   uint8_t* out_tiles = a_tiles + 2 * kTileBytes;                     // [group][16 KB]
-  float* s_par = reinterpret_cast<float*>(out_tiles + 2 * kTileBytes);   // [group][2][BLOCK_N]
+  uint8_t* pool_tiles = out_tiles + 2 * kTileBytes;                  // [group][4 KB]
+  float* s_par = reinterpret_cast<float*>(pool_tiles + 2 * kPoolBytes);  // [group][2][BLOCK_N]
   float* s_wd = s_par + 2 * (2 * BLOCK_N + Cfg::kHeadFloats);        // [9][Cin]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_wd + 9 * kMaxCin);
   uint64_t* ld_full = bars;              // [S]
@@ -90,7 +101,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int num_k = p.num_k;
 
   for (int i = threadIdx.x; i < 9 * p.Cin; i += blockDim.x) s_wd[i] = p.wd9c[i];
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 5); }   // 4 producer warps + the MMA commit
     for (int i = 0; i < 2; ++i) {
@@ -328,8 +339,31 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         fs_fence_proxy_async();
         fs_bar_sync(1 + g, 128);
-        if (issuer && p.store_y) {
-          fs_tma_store_4d(&tmY, buf, c * 64, wb * kPW, hb * kPH, n);
+        if (p.store_pool) {
+          // 2x2 max over the staged tile (row = h*16 + w, 16-byte chunk j of row r at ((j ^ (r & 7)) << 4)): 32 pooled pixels
+          // x 8 chunks = 2 items per thread, bf16x2 max, into the swizzled pooled tile
+          const uint32_t ps = smem_u32(pool_tiles + g * kPoolBytes);
+#pragma unroll
+          for (int it2 = 0; it2 < 2; ++it2) {
+            const int item = gtid + it2 * 128;
+            const int pp = item >> 3, j = item & 7;                 // pooled pixel (4 x 8), chunk
+            const int r00 = ((pp >> 3) * 2) * kPW + (pp & 7) * 2;
+            uint4 m4 = lds128u(smem_u32(buf) + (uint32_t)r00 * 128u + (((uint32_t)j ^ ((uint32_t)r00 & 7u)) << 4));
+#pragma unroll
+            for (int q = 1; q < 4; ++q) {
+              const int rr = r00 + (q & 1) + (q >> 1) * kPW;
+              const uint4 v4 = lds128u(smem_u32(buf) + (uint32_t)rr * 128u + (((uint32_t)j ^ ((uint32_t)rr & 7u)) << 4));
+              m4.x = fs_max_bf16x2(m4.x, v4.x); m4.y = fs_max_bf16x2(m4.y, v4.y);
+              m4.z = fs_max_bf16x2(m4.z, v4.z); m4.w = fs_max_bf16x2(m4.w, v4.w);
+            }
+            sts128(ps + (uint32_t)pp * 128u + (((uint32_t)j ^ ((uint32_t)pp & 7u)) << 4), m4);
+          }
+          fs_fence_proxy_async();
+          fs_bar_sync(1 + g, 128);
+        }
+        if (issuer && (p.store_y || p.store_pool)) {
+          if (p.store_y) fs_tma_store_4d(&tmY, buf, c * 64, wb * kPW, hb * kPH, n);
+          if (p.store_pool) fs_tma_store_4d(&tmP, pool_tiles + g * kPoolBytes, c * 64, wb * (kPW / 2), hb * (kPH / 2), n);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -375,13 +409,13 @@ static int fs_tmap_4d(CUtensorMap* map, const void* base, int64_t ld, int N, int
 }
 
 template <int BLOCK_N>
-static int fs_launch(const CUtensorMap& tmX, const CUtensorMap& tmB, const CUtensorMap& tmY, const FsParams& p, cudaStream_t st) {
+static int fs_launch(const CUtensorMap& tmX, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmP, const FsParams& p, cudaStream_t st) {
   using Cfg = FsCfg<BLOCK_N>;
   static SmemAttrOnce once;
   if (cudaError_t e = ensure_dynamic_smem(once, sepconv_fused_kernel<BLOCK_N>, Cfg::kSmemBytes))
     return set_cuda_error(e, "sepconv_fused: cudaFuncSetAttribute");
   const unsigned grid = (unsigned)i64min(p.total_tiles, sm_count());
-  sepconv_fused_kernel<BLOCK_N><<<grid, 640, Cfg::kSmemBytes, st>>>(tmX, tmB, tmY, p);
+  sepconv_fused_kernel<BLOCK_N><<<grid, 640, Cfg::kSmemBytes, st>>>(tmX, tmB, tmY, tmP, p);
   UNET_LAUNCH_CHECK("sepconv_fused");
   return UNET_OK;
 }
@@ -393,7 +427,10 @@ using namespace unet;
 extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* wd9c, const void* wp_t, int64_t ldw,
                                       const float* scale, const float* shift, int relu, void* y, int64_t ldy,
                                       int N, int H, int W, int Cin, int Cout,
-                                      const float* head_w, const float* head_b, float* head_out, int head_classes, void* stream) {
+                                      const float* head_w, const float* head_b, float* head_out, int head_classes,
+                                      void* pooled, int64_t ldp, void* stream) {
+  UNET_REQUIRE(!pooled || (y && H % 2 == 0 && W % 2 == 0 && ldp >= Cout && ldp % 8 == 0 && aligned16(pooled)), UNET_EINVAL,
+               "sepconv_fused: pooled needs y, even H and W, ldp >= Cout, ldp%%8==0 and a 16B-aligned base");
   UNET_REQUIRE(x && wd9c && wp_t && (y || head_out) && N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, UNET_EINVAL, "sepconv_fused: bad argument");
   UNET_REQUIRE(ldx >= Cin && (!y || ldy >= Cout) && ldw >= Cin, UNET_EINVAL, "sepconv_fused: leading dimension too small");
   UNET_REQUIRE(!head_out || (head_w && head_classes >= 1 && head_classes <= 8 && Cout <= 64), UNET_EINVAL,
@@ -403,10 +440,12 @@ extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* w
   UNET_REQUIRE(ldx % 8 == 0 && (!y || (ldy % 8 == 0 && aligned16(y))) && ldw % 8 == 0 && aligned16(x) && aligned16(wp_t) && aligned16(wd9c),
                UNET_EALIGN, "sepconv_fused: operands need 16B-aligned bases and ld%%8==0");
   UNET_REQUIRE((!scale || aligned16(scale)) && (!shift || aligned16(shift)), UNET_EALIGN, "sepconv_fused: scale/shift must be 16B aligned");
-  CUtensorMap tmX, tmB, tmY;
+  CUtensorMap tmX, tmB, tmY, tmP;
   if (int e = fs_tmap_4d(&tmX, x, ldx, N, H, W, Cin, kXCols, kXRows, CU_TENSOR_MAP_SWIZZLE_NONE, "sepconv_fused(x)")) return e;
   if (y) { if (int e = fs_tmap_4d(&tmY, y, ldy, N, H, W, Cout, kPW, kPH, CU_TENSOR_MAP_SWIZZLE_128B, "sepconv_fused(y)")) return e; }
   else tmY = tmX;        // placeholder descriptor: nothing is stored through it
+  if (pooled) { if (int e = fs_tmap_4d(&tmP, pooled, ldp, N, H / 2, W / 2, Cout, kPW / 2, kPH / 2, CU_TENSOR_MAP_SWIZZLE_128B, "sepconv_fused(pooled)")) return e; }
+  else tmP = tmX;
   const int bn = Cout > 64 ? 128 : 64;
   {
     PFN_encodeTiled fn = get_encode_fn();
@@ -427,7 +466,8 @@ extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* w
   p.total_tiles = (int)tiles; p.num_k = (int)ceil_div(Cin, 64);
   p.wd9c = wd9c; p.scale = scale; p.shift = shift;
   p.store_y = y != nullptr;
+  p.store_pool = pooled != nullptr;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_classes = head_classes;
   cudaStream_t st = (cudaStream_t)stream;
-  return bn == 128 ? fs_launch<128>(tmX, tmB, tmY, p, st) : fs_launch<64>(tmX, tmB, tmY, p, st);
+  return bn == 128 ? fs_launch<128>(tmX, tmB, tmY, tmP, p, st) : fs_launch<64>(tmX, tmB, tmY, tmP, p, st);
 }

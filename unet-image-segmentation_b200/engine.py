@@ -105,6 +105,7 @@ class UNetEngine:
         self.dropout_masks_from_step = True     # False: masks depend only on the seeds (parity tests)
         self.fuse_sepconv = True                # inference: levels with <= 128 output channels run the fused conv_block kernel
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
+        self.fuse_pool = True                   # inference: MaxPooling2D from the fused conv_block kernel's staged tile
         self.convt_bwd_direct = True            # training: no un-pixel-shuffle gather pass (the depthwise backward stores that layout)
         self.fuse_pw_bwd = True                 # training: folded data + weight gradient of a 64-channel pointwise from one pass
         self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward folded into the block's pointwise
@@ -281,7 +282,8 @@ class UNetEngine:
             return self._stage_fold[name], None, self.fold[1, o:o + c]
         return self._stage[name + "^T"], self.fold[0, o:o + c], self.fold[1, o:o + c]
 
-    def _block_infer(self, pl: _Plan, prefix: str, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    def _block_infer(self, pl: _Plan, prefix: str, x: torch.Tensor, y: torch.Tensor, pooled: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pooled: also produce MaxPooling2D((2,2)) of y (from the fused kernel's staged tile where that kernel runs)."""
         B, h, w, cin = x.shape
         if ops.stem_supported(cin, y.shape[-1]) and x.is_contiguous():
             o, c = self._bn_off[prefix]
@@ -293,7 +295,11 @@ class UNetEngine:
         if self.fuse_sepconv and ops.sepconv_fused_supported(x, y.shape[-1]):
             # whole conv_block in one kernel: the depthwise result is produced on chip as the GEMM's A operand
             wpt, sc, sh = self._infer_pw(prefix)
-            ops.sepconv_fused(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), wpt, y, scale=sc, shift=sh, relu=True)
+            fuse_pool = pooled is not None and self.fuse_pool and h % 2 == 0 and w % 2 == 0
+            ops.sepconv_fused(x, self._mat(f"{prefix}_sepconv/depthwise_kernel"), wpt, y, scale=sc, shift=sh, relu=True,
+                              pooled=pooled if fuse_pool else None)
+            if pooled is not None and not fuse_pool:
+                ops.maxpool2x2(y, pooled)
             return y
         level = (self.spec.input_size[0] // h).bit_length() - 1
         max_cin = 1024 if level == 4 else 2 * FILTERS[level]
@@ -307,6 +313,8 @@ class UNetEngine:
             self._pw_fwd(prefix, d, y, epilogue=ops.EPI_AFFINE_RELU, scale=self.fold[0, o:o + c], shift=self.fold[1, o:o + c])
         else:
             self._pw_fwd(prefix, d, y, epilogue=ops.EPI_AFFINE_RELU, shift=self.wview(f"{prefix}_sepconv/bias"))
+        if pooled is not None:
+            ops.maxpool2x2(y, pooled)
         return y
 
     def forward_inference(self, x: torch.Tensor) -> torch.Tensor:
@@ -352,9 +360,9 @@ class UNetEngine:
             h, w = self._dims(s - 1)
             cat = cats[s] = pl.buf(f"cat{s}", (B, h, w, 2 * f))
             cur = self._block_infer(pl, f"enc{s}_block1", cur, pl.buf(f"ya{s}", (B, h, w, f)))
-            skip = self._block_infer(pl, f"enc{s}_block2", cur, cat[..., f:])
-            cur = pl.buf(f"pool{s}", (B, h // 2, w // 2, f))
-            ops.maxpool2x2(skip, cur)
+            nxt = pl.buf(f"pool{s}", (B, h // 2, w // 2, f))
+            self._block_infer(pl, f"enc{s}_block2", cur, cat[..., f:], pooled=nxt)
+            cur = nxt
         h, w = self._dims(4)
         cur = self._block_infer(pl, "bneck_block1", cur, pl.buf("ya5", (B, h, w, 1024)))
         cur = self._block_infer(pl, "bneck_block2", cur, pl.buf("yb5", (B, h, w, 1024)))

@@ -245,7 +245,7 @@ def sepconv_fused_supported(x: torch.Tensor, cout: int) -> bool:
 def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Optional[torch.Tensor],
                   scale: Optional[torch.Tensor] = None, shift: Optional[torch.Tensor] = None, relu: bool = True,
                   head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
-                  head_out: Optional[torch.Tensor] = None) -> None:
+                  head_out: Optional[torch.Tensor] = None, pooled: Optional[torch.Tensor] = None) -> None:
     """conv_block for inference in one kernel: depthwise 3x3 produced on chip as the tcgen05 A operand, pointwise GEMM,
     folded BN + ReLU epilogue, TMA store into the (possibly channel-sliced) destination; optionally the 1x1 output head
     (sigmoid / softmax) from the same registers, in which case `y` may be None."""
@@ -266,10 +266,15 @@ def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Op
         classes = head_w.shape[1]
     elif y is None:
         raise ValueError("sepconv_fused: nothing to produce")
+    ldp = 0
+    if pooled is not None:     # MaxPooling2D((2,2)) of the stored activation from the same staged tile
+        n3, h3, w3, c3, ldp = _nhwc(pooled, "pooled")
+        if y is None or (n3, h3 * 2, w3 * 2, c3) != (n, h, w, cout) or pooled.dtype != torch.bfloat16:
+            raise ValueError("sepconv_fused: pooled must be a bf16 [N,H/2,W/2,Cout] view and needs y")
     _call("unet_sepconv_fused_fwd", _p(x), ldx, _p(wd9c), _p(wp_t), wp_t.stride(0), _p(scale), _p(shift), int(relu), _p(y), ldy,
-          n, h, w, cin, cout, _p(head_w), _p(head_b), _p(head_out), classes, _stream(),
-          tag=f"{n}x{h}x{w}x{cin}->{cout}{'+head' if head_out is not None else ''}",
-          nbytes=_nbytes(x, y, wp_t, head_out), flops=(18 * cin + 2 * cin * cout) * n * h * w)
+          n, h, w, cin, cout, _p(head_w), _p(head_b), _p(head_out), classes, _p(pooled), ldp, _stream(),
+          tag=f"{n}x{h}x{w}x{cin}->{cout}{'+head' if head_out is not None else ''}{'+pool' if pooled is not None else ''}",
+          nbytes=_nbytes(x, y, wp_t, head_out, pooled), flops=(18 * cin + 2 * cin * cout) * n * h * w)
 
 
 # ------------------------------------------------------------------------------------------------ dense contractions

@@ -316,6 +316,24 @@ class Layer:
 
 
 # ====================================================================================================== input prefetch
+def _host_copy(dst, src) -> None:
+    """Host-to-host copy (with dtype conversion) between NumPy arrays / CPU tensors on all of torch's CPU threads: one thread
+    moves ~10 GB/s, which would cap `predict` of 512x512 batches below what the GPU and PCIe sustain."""
+    import torch
+    nbytes = src.numel() * src.element_size() if isinstance(src, torch.Tensor) else src.nbytes
+    if nbytes < (8 << 20):                             # small batches: the thread fan-out costs more than it saves
+        np.copyto(dst.numpy() if isinstance(dst, torch.Tensor) else dst, src.numpy() if isinstance(src, torch.Tensor) else src,
+                  casting="unsafe")
+        return
+    try:
+        d = dst if isinstance(dst, torch.Tensor) else torch.from_numpy(dst)
+        s_ = src if isinstance(src, torch.Tensor) else torch.from_numpy(src if src.flags.writeable else src.copy())
+        d.copy_(s_)
+    except (TypeError, ValueError, RuntimeError):      # dtypes / layouts torch cannot wrap: NumPy does it on one thread
+        np.copyto(dst.numpy() if isinstance(dst, torch.Tensor) else dst, src.numpy() if isinstance(src, torch.Tensor) else src,
+                  casting="unsafe")
+
+
 class _Prefetcher:
     """Host -> device staging for `fit`: batch i+1 is uploaded on a copy stream (from pinned memory) while batch i
     computes.  Two device slots; a slot is rewritten only after the step that read it has been enqueued and has
@@ -352,7 +370,7 @@ class _Prefetcher:
                         host = slot["pin"][(key, a.shape)] = torch.empty(a.shape, dtype=torch.float32).pin_memory()
                     if slot["ready"] is not None:
                         slot["ready"].synchronize()          # the previous DMA out of this pinned buffer has finished
-                    np.copyto(host.numpy(), a, casting="unsafe")
+                    _host_copy(host, a)
                 dev = slot["dev"].get((key, tuple(host.shape)))
                 if dev is None:
                     dev = slot["dev"][(key, tuple(host.shape))] = torch.empty(host.shape, dtype=torch.float32, device="cuda")
@@ -557,7 +575,7 @@ class Model:
             if pending[slot] is not None:
                 ev, lo, hi = pending[slot]
                 ev.synchronize()
-                out[lo:hi] = cache["pin_out"][slot][: hi - lo].numpy()
+                _host_copy(out[lo:hi], cache["pin_out"][slot][: hi - lo])
                 pending[slot] = None
 
         chunks = ((x[lo:lo + bs], None) for lo in range(0, n, bs))

@@ -546,8 +546,8 @@ class Model:
     def predict(self, x, batch_size: Optional[int] = 32, verbose=0, steps=None) -> np.ndarray:
         """model.predict (inference.py:116, benchmark.py:254): NHWC float array in, NHWC fp32 probabilities out.
         Chunks of `batch_size` are pipelined: upload of chunk i+1 (copy stream), forward of chunk i (compute stream) and
-        download of chunk i-1 (second copy stream, into pinned memory) overlap; the host copies finished chunks into the
-        result array while the GPU works."""
+        download of chunk i-1 (second copy stream, into pinned memory) overlap; a worker thread copies finished chunks into
+        the result array while the calling thread stages the next input."""
         import torch
         x = np.asarray(x) if not isinstance(x, torch.Tensor) else x
         if x.ndim != 4 or tuple(x.shape[1:]) != tuple(self.spec.input_size):
@@ -567,15 +567,22 @@ class Model:
             cache["dev_out"] = [torch.empty((bs, H, W, NC), dtype=torch.float32, device="cuda") for _ in range(2)]
             cache["pin_out"] = [torch.empty((bs, H, W, NC), dtype=torch.float32).pin_memory() for _ in range(2)]
             cache["pf"] = {}
+        if "worker" not in cache:
+            from concurrent.futures import ThreadPoolExecutor
+            cache["worker"] = ThreadPoolExecutor(1, thread_name_prefix="unet_predict_out")
         s_out = cache["out"]
         compute = torch.cuda.current_stream()
-        pending = [None, None]                       # per output slot: (event, lo, hi)
+        dev_idx = torch.cuda.current_device()
+        pending = [None, None]                       # per output slot: future of its copy-out job
+
+        def copy_out(ev, slot, lo, hi):              # worker thread: the result array's first-touch page faults and the
+            with torch.cuda.device(dev_idx):         # copy out of pinned memory stay off the thread that feeds the GPU
+                ev.synchronize()
+            _host_copy(out[lo:hi], cache["pin_out"][slot][: hi - lo])
 
         def retire(slot):
             if pending[slot] is not None:
-                ev, lo, hi = pending[slot]
-                ev.synchronize()
-                _host_copy(out[lo:hi], cache["pin_out"][slot][: hi - lo])
+                pending[slot].result()
                 pending[slot] = None
 
         chunks = ((x[lo:lo + bs], None) for lo in range(0, n, bs))
@@ -592,8 +599,7 @@ class Model:
                 s_out.wait_event(ev_c)
                 cache["pin_out"][slot][:k].copy_(dev_out[:k], non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(s_out)
-            pending[slot] = (ev, lo, lo + k)
-            retire(1 - slot)                         # copy the previous chunk out while this one computes
+            pending[slot] = cache["worker"].submit(copy_out, ev, slot, lo, lo + k)
             lo += k
         retire(0); retire(1)
         return out

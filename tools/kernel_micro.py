@@ -48,6 +48,11 @@ elif name == "convt":         # dec1_upsample
     bias = torch.zeros(64, device=dev)
     run(lambda: ops.gemm(x, Bt, cat[..., :64], b_trans=True, epilogue=ops.EPI_CONVT, shift=bias, convt_hw=(256, 256)),
         (x.numel() + M * 64) * 2)
+elif name == "gemm_convt_shape":   # the dec1_upsample contraction with a plain row-major store (isolates the 5-D pixel-shuffle store)
+    x, Bt = rnd(B * 256 * 256, 128), rnd(256, 128)
+    C = torch.empty((B * 256 * 256, 256), device=dev, dtype=bf)
+    bias = torch.zeros(256, device=dev)
+    run(lambda: ops.gemm(x, Bt, C, b_trans=True, epilogue=ops.EPI_AFFINE, shift=bias), (x.numel() + C.numel()) * 2)
 elif name == "wgrad64":
     A, Bm, C = rnd(M, 64), rnd(M, 64), torch.zeros((64, 64), device=dev)
     run(lambda: ops.gemm(A, Bm, C, a_trans=True, accumulate=True), 2 * M * 64 * 2)

@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "TensorFlow is not installable in this image (no wheel, no network): the CPU arm is the oracle's torch port",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ====================================================================================================== B200 arm
@@ -400,13 +400,34 @@ def run_b200(args):
                      "TFLOP_per_step": round(tot_flops / 1e12, 2)},
         "kernels": table[:12],
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         pass
 
 
+_JSON_FD = None
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner to fd 1) are sent to stderr for
+    the whole run and the line is written to the original stdout at the end."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)
         return

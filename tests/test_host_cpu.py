@@ -267,3 +267,25 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_host_copy_paths():
+    """predict()'s staging copy: NumPy path below 8 MB, torch (all CPU threads) above, dtype conversion, tensor/array mixes"""
+    import torch
+    from unet_b200.keras_api import _host_copy
+    rng = np.random.default_rng(3)
+    small = rng.integers(0, 255, (2, 16, 16, 3)).astype(np.uint8)
+    dst = torch.empty(small.shape, dtype=torch.float32)
+    _host_copy(dst, small)
+    assert np.array_equal(dst.numpy(), small.astype(np.float32))
+    big = rng.random((3, 512, 512, 3)).astype(np.float64)            # 18.9 MB: the threaded path, with a down-cast
+    dstb = torch.empty(big.shape, dtype=torch.float32)
+    _host_copy(dstb, big)
+    assert np.array_equal(dstb.numpy(), big.astype(np.float32))
+    out = np.zeros((4, 512, 512, 2), np.float32)
+    src = torch.arange(2 * 512 * 512 * 2, dtype=torch.float32).view(2, 512, 512, 2)
+    _host_copy(out[1:3], src)                                          # into a slice of the result array
+    assert np.array_equal(out[1:3], src.numpy()) and out[0].sum() == 0 and out[3].sum() == 0
+    ro = rng.random((3, 512, 512, 3)).astype(np.float32); ro.setflags(write=False)
+    _host_copy(dstb, ro)                                               # read-only source array
+    assert np.array_equal(dstb.numpy(), ro)

@@ -316,8 +316,8 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     const bool stats = epi == UNET_EPI_STATS;
     const uint32_t seed = p.drop_on ? p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u) : 0u;
-    // Conv2DTranspose: tile rows are input pixels (q = image*H + i, j); the box covers bj columns x bq rows of them
-    const int cw = p.convt_W, bj = cw < kBlockM ? cw : kBlockM;
+    // Conv2DTranspose: tile rows are input pixels (q = image*H + i, j); the box covers min(W,128) columns x 128/min(W,128) rows
+    const int cw = p.convt_W;
     float st_sum[kChunks][CPL], st_sq[kChunks][CPL];
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)

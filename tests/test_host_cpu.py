@@ -209,6 +209,24 @@ def test_paired_directory_iterator(tmp_path):
     assert a == b
     xs, ys = next(synthetic_batches(3, 32, 32, classes=8))
     assert xs.shape == (3, 32, 32, 3) and ys.shape == (3, 32, 32, 8) and np.all(ys.sum(-1) == 1)
+    # threaded decode + background prefetch yields the very same stream as the synchronous path
+    kw = dict(target_size=(16, 16), batch_size=2, shuffle=True, horizontal_flip=True, seed=7)
+    sync = [b for b, _ in zip(iter(PairedDirectoryIterator(str(fd), str(md), workers=0, **kw)), range(7))]
+    gen_t = iter(PairedDirectoryIterator(str(fd), str(md), workers=4, prefetch=3, **kw))
+    thr = [next(gen_t) for _ in range(7)]
+    gen_t.close()                                # stops the producer thread and the pool
+    for (xa, ya), (xb, yb) in zip(sync, thr):
+        assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    # same values as the plain recipe: float32(image) * float32(1/255)
+    first = cv2.cvtColor(cv2.imread(str(fd / "0.png")), cv2.COLOR_BGR2RGB)
+    ref0 = cv2.resize(first, (16, 16), interpolation=cv2.INTER_LINEAR).astype(np.float32) * np.float32(1.0 / 255.0)
+    x0, _ = next(iter(PairedDirectoryIterator(str(fd), str(md), (16, 16), 1, shuffle=False, workers=2)))
+    assert np.array_equal(x0[0], ref0)
+    # a decode error surfaces in the consumer
+    (md / "4.png").write_bytes(b"not an image")
+    with pytest.raises(OSError):
+        for _ in zip(iter(PairedDirectoryIterator(str(fd), str(md), (16, 16), 2, shuffle=False, workers=2)), range(5)):
+            pass
 
 
 def test_postprocessing_known_answer(tmp_path):

@@ -214,6 +214,8 @@ def run_b200(args):
     if world != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
     torch.cuda.set_device(local_rank)
+    if world > 1:       # torchrun pins OMP_NUM_THREADS=1: give each rank its share of the host cores for the staging copies
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     mode, H, W, classes, batch, desc = WORKLOADS[args.workload]
     batch = args.batch or batch
     hbm_peak, tc_peak, peak_kind = peaks()

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="print the per-kernel table to stderr")
     ap.add_argument("--no-graphs", action="store_true", help="launch every step eagerly (no CUDA-graph replay)")
+    ap.add_argument("--no-infer", action="store_true", help="training workloads: skip the inference record (`infer`) of the same shape")
+    ap.add_argument("--check", action="store_true", help="N > 1: data-parallel correctness leg (gradient == mean of shard gradients; "
+                    "weights identical across ranks after steps) before the timed runs")
     return ap.parse_args()
 
 
@@ -201,39 +204,9 @@ def run_reference(args):
 
 
 # ====================================================================================================== B200 arm
-def run_b200(args):
-    import numpy as np
+def synthetic_shard(batch, H, W, classes, rank):
+    """synthetic shard of the global batch: uniform images, filled-rectangle masks (oracle generator's recipe restated)"""
     import torch
-    import torch.distributed as dist
-    from unet_b200 import dist as D
-    from unet_b200 import ops
-    from unet_b200.keras_api import AdamW, MeanIoU, Model
-
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
-    rank, local_rank, world = D.init_from_env("nccl")
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
-    torch.cuda.set_device(local_rank)
-    if world > 1:       # torchrun pins OMP_NUM_THREADS=1: give each rank its share of the host cores for the staging copies
-        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
-    mode, H, W, classes, batch, desc = WORKLOADS[args.workload]
-    batch = args.batch or batch
-    hbm_peak, tc_peak, peak_kind = peaks()
-
-    model = Model((H, W, 3), num_classes=classes, dropout_rate=0.2, use_batch_norm=True, dtype=args.dtype,
-                  seed=2301)
-    model.compile(optimizer=AdamW(learning_rate=2e-3, weight_decay=1e-4), loss="dice_loss", metrics=[])
-    eng = model.engine
-    if args.no_graphs:
-        eng.use_graphs = False
-    if world > 1:
-        dist.broadcast(eng.w, src=0)
-        dist.broadcast(eng.state, src=0)
-        eng._stage_dirty = True
-        if mode == "train":
-            model.enable_data_parallel()
-
-    # synthetic shard of the global batch: uniform images, filled-quadrilateral masks (oracle generator's recipe restated)
     g = torch.Generator(device="cuda"); g.manual_seed(2301 + rank)
     x_dev = torch.rand((batch, H, W, 3), device="cuda", generator=g)
     yy, xx = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
@@ -247,17 +220,75 @@ def run_b200(args):
     else:
         lab = (inside.long() * (1 + (xx[None] // 32 + yy[None] // 32) % (classes - 1)))
         y_dev = torch.nn.functional.one_hot(lab, classes).float().contiguous()
-    x_pin, y_pin = x_dev.cpu().pin_memory(), y_dev.cpu().pin_memory()
+    return x_dev, y_dev
+
+
+def roofline_of(prof, steps, hbm_peak, tc_peak, peak_kind):
+    """roofline of the dominant kernel: the C-ABI entry point (one CUDA kernel, all its shapes) with the largest share of
+    the step; achieved = its algorithmic bytes (or flops) over all launches / its summed launch time.  Also the per-kernel
+    table and the whole-step totals."""
+    rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    kernel_ms = sum(r["ms"] for _, r in rows)
+    byname = {}
+    for k, r in rows:
+        nm = k.split("[")[0]
+        if nm == "gemm_tc":
+            nm = "gemm_tc(" + k.split("[")[1].split(":")[0] + ")"      # nt / convt / wgrad are different kernels
+        a = byname.setdefault(nm, dict(ms=0.0, calls=0, bytes=0, flops=0, top=k, top_ms=0.0))
+        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]
+        if r["ms"] > a["top_ms"]:
+            a["top"], a["top_ms"] = k, r["ms"]
+    top_name, top = max(byname.items(), key=lambda kv: kv[1]["ms"])
+    ai = top["flops"] / max(top["bytes"], 1)
+    if top_name.startswith("gemm_tc") and ai > RIDGE_FLOP_PER_BYTE:
+        roof = {"bound": "tensor", "achieved": round(top["flops"] / (top["ms"] * 1e-3) / 1e12, 2), "peak": tc_peak, "unit": "TFLOP/s"}
+    else:
+        roof = {"bound": "hbm", "achieved": round(top["bytes"] / (top["ms"] * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s"}
+    roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
+    roof["kernel"] = top_name
+    roof["launches_per_step"] = round(top["calls"] / steps, 1)
+    roof["avg_launch_ms"] = round(top["ms"] / top["calls"], 4)
+    roof["algorithmic_bytes_per_launch"] = int(top["bytes"] / top["calls"])
+    roof["share_of_step"] = round(top["ms"] / kernel_ms, 4)
+    roof["peak_source"] = f"{peak_kind} ({'MEASURED_PEAKS.json' if peak_kind == 'measured' else 'B200_PROFILING.md fallback'}, sustained)"
+    roof["traffic"] = None
+    try:        # ncu --set full dram bytes of this kernel's largest shape, scaled to the average launch of the step
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        shape_key = top["top"]
+        if shape_key not in tr:     # another shape of the same kernel was captured
+            cands = [k for k in tr if k.split("[")[0] == shape_key.split("[")[0] and k in prof]
+            shape_key = cands[0] if cands else shape_key
+        if shape_key in tr and shape_key in prof:
+            ratio = tr[shape_key] / (prof[shape_key]["bytes"] / prof[shape_key]["calls"])
+            roof["traffic"] = int(ratio * top["bytes"] / top["calls"])
+            roof["traffic_over_algorithmic"] = round(ratio, 4)
+            roof["traffic_shape"] = shape_key
+    except Exception:
+        pass
+    tot_bytes = sum(r["bytes"] for _, r in rows) / steps
+    tot_flops = sum(r["flops"] for _, r in rows) / steps
+    table = [{"kernel": k, "calls_per_step": r["calls"] / steps, "ms_per_step": round(r["ms"] / steps, 3),
+              "GBps": round(r["bytes"] / max(r["ms"], 1e-9) / 1e6, 1), "TFLOPs": round(r["flops"] / max(r["ms"], 1e-9) / 1e9, 2)}
+             for k, r in rows]
+    return roof, table, tot_bytes, tot_flops
+
+
+def measure(model, mode, batch, H, W, classes, args, rank, local_rank, world, peaks3):
+    """One workload on this rank's GPU: device-resident throughput (`value`), the live per-kernel table, and the end-to-end
+    throughput through the Keras-shaped API from PAGEABLE NumPy arrays (what a user of the reference passes) and, separately,
+    from caller-pinned buffers."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from unet_b200 import ops
+    hbm_peak, tc_peak, peak_kind = peaks3
+    eng = model.engine
+    x_dev, y_dev = synthetic_shard(batch, H, W, classes, rank)
 
     def device_step():
-        if mode == "train":
-            if model._grad_sync is None:
-                return eng.train_step(x_dev, y_dev, "dice")          # CUDA-graph replay unless per-launch timing is on
-            out3 = eng.train_forward_backward(x_dev, y_dev, "dice")
-            model._grad_sync.finish()
-            D.average_(eng.state)
-            eng.apply_gradients()
-            return out3
+        if mode == "train":      # forward + backward + (NCCL exchange) + AdamW + the compiled metrics' update (train.py:227-234)
+            return model._train_step_device(x_dev, y_dev)[0]
         return eng.forward_inference(x_dev)
 
     def barrier():
@@ -269,7 +300,7 @@ def run_b200(args):
         device_step()
     barrier()
 
-    # ---------------- timed region 1: inputs resident in HBM (the step as shipped: CUDA-graph replay on one GPU)
+    # ---------------- timed region 1: inputs resident in HBM (the step as shipped: CUDA-graph replay)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         barrier()
@@ -294,91 +325,163 @@ def run_b200(args):
     launches = ops.launches - launches0
     barrier()
 
-    # ---------------- timed region 2: end to end through the public (Keras-shaped) API with pinned host buffers
-    e2e = None
+    # ---------------- timed region 2: end to end through the public (Keras-shaped) API, host buffers in, host result out
+    e2e = e2e_pinned = None
     if not args.no_e2e:
-        def api_run(k):
-            if mode == "train":
-                # the call a user of the reference makes (scripts/train.py:308): model.fit(generator, steps_per_epoch=k).
-                # Every step uploads its (x, y) from pinned host memory and reads its loss back to the host.
-                gen = ((x_pin, y_pin) for _ in range(k))
-                model.fit(gen, epochs=1, steps_per_epoch=k, verbose=0)
-            else:
-                # model.predict over k batches in ONE call (pinned input): per batch H2D of the images, D2H of the probabilities
-                model.predict(x_pin_rep[: k * batch], batch_size=batch)
-        if mode != "train":
-            reps = max(args.steps, 2)
-            x_pin_rep = torch.empty((reps * batch, H, W, 3), dtype=torch.float32).pin_memory()
+        x_np, y_np = x_dev.cpu().numpy(), y_dev.cpu().numpy()                   # pageable host memory, as a generator yields
+        reps = max(args.steps, 2)
+
+        def timed(fn):
+            fn(2)
+            barrier()
+            e0.record()
+            fn(args.steps)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return batch * world * args.steps / (float(t.item()) / 1e3)
+
+        if mode == "train":
+            # the call a user of the reference makes (scripts/train.py:308): model.fit(generator, steps_per_epoch=k); every
+            # step stages its (x, y) NumPy batch into pinned memory, uploads it, and reads its loss back to the host
+            v_page = timed(lambda k: model.fit(((x_np, y_np) for _ in range(k)), epochs=1, steps_per_epoch=k, verbose=0))
+            x_pin, y_pin = torch.from_numpy(x_np).pin_memory(), torch.from_numpy(y_np).pin_memory()
+            v_pin = timed(lambda k: model.fit(((x_pin, y_pin) for _ in range(k)), epochs=1, steps_per_epoch=k, verbose=0))
+            h2d, d2h = x_np.nbytes + y_np.nbytes, 12
+        else:
+            # model.predict over k batches in ONE call (inference.py:116): per batch H2D of the images, D2H of the probabilities
+            x_rep = np.empty((reps * batch, H, W, 3), np.float32)
             for r in range(reps):
-                x_pin_rep[r * batch:(r + 1) * batch].copy_(x_pin)
-        api_run(2)
-        barrier()
-        e0.record()
-        api_run(args.steps)
-        e1.record()
-        barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+                x_rep[r * batch:(r + 1) * batch] = x_np
+            v_page = timed(lambda k: model.predict(x_rep[: k * batch], batch_size=batch))
+            x_pin = torch.from_numpy(x_rep).pin_memory()
+            v_pin = timed(lambda k: model.predict(x_pin[: k * batch], batch_size=batch))
+            del x_pin
+            h2d, d2h = x_np.nbytes, batch * H * W * classes * 4
+        e2e = {"value": round(v_page, 2), "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "host_buffers": "pageable NumPy (staged through pinned memory inside the timed region)"}
+        e2e_pinned = {"value": round(v_pin, 2), "unit": "img/s", "host_buffers": "caller-pinned"}
+
+    rec = {"metric": f"{mode} img/s", "value": round(value, 2), "unit": "img/s", "ms_per_step": round(ms_total / args.steps, 3),
+           "e2e": e2e, "e2e_pinned": e2e_pinned, "gpu_launches": launches, "clocks": clk.summary()}
+    if rank == 0:
+        roof, table, tot_bytes, tot_flops = roofline_of(prof, args.steps, hbm_peak, tc_peak, peak_kind)
+        rec["roofline"] = roof
+        rec["step_hbm"] = {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 2), "GBps": round(tot_bytes / (ms_total / args.steps) / 1e6, 1),
+                           "frac_of_peak": round(tot_bytes / (ms_total / args.steps) / 1e6 / hbm_peak, 4),
+                           "TFLOP_per_step": round(tot_flops / 1e12, 2)}
+        rec["kernels"] = table
+        if args.breakdown:
+            for t in table:
+                print(f"{t['kernel']:58s} {t['calls_per_step']:5.1f} {t['ms_per_step']:9.3f} ms {t['GBps']:8.1f} GB/s {t['TFLOPs']:8.2f} TF/s",
+                      file=sys.stderr)
+    return rec
+
+
+def dp_check(model, H, W, classes, rank, world):
+    """SURVEY 8e's definition of data-parallel correctness, on NCCL: (1) the exchanged gradient == mean of the per-shard
+    single-GPU gradients; (2) after K optimizer steps every rank holds bit-identical weights and BN statistics."""
+    import torch
+    import torch.distributed as dist
+    eng = model.engine
+    b = 4
+    shards = [synthetic_shard(b, H, W, classes, 1000 + r) for r in range(world)]
+    keep_graphs, keep_drop = eng.use_graphs, eng.dropout_masks_from_step
+    eng.use_graphs, eng.dropout_masks_from_step = False, False
+    w0, s0 = eng.w.clone(), eng.state.clone()
+    # (1) every rank computes every shard's gradient locally (no exchange), then its own shard's with the exchange
+    hook, eng.grad_hook = eng.grad_hook, None
+    acc = torch.zeros_like(eng.g, dtype=torch.float64)
+    for xs, ys in shards:
+        eng.state.copy_(s0)
+        eng.train_forward_backward(xs, ys, "dice")
+        acc += eng.g.double()
+    mean_local = acc / world
+    eng.grad_hook = hook
+    eng.state.copy_(s0)
+    eng.train_forward_backward(*shards[rank], "dice")
+    model._grad_sync.finish()
+    torch.cuda.synchronize()
+    synced = eng.g.double() / world
+    rel = float((synced - mean_local).norm() / (mean_local.norm() + 1e-300))
+    # (2) K real steps, then compare bit patterns across ranks
+    eng.state.copy_(s0); eng.w.copy_(w0); eng._stage_dirty = True
+    eng.use_graphs, eng.dropout_masks_from_step = keep_graphs, keep_drop
+    for _ in range(4):
+        model._train_step_device(*shards[rank])
+    torch.cuda.synchronize()
+    sig = torch.stack([eng.w.view(torch.int32).long().sum(), eng.state.view(torch.int32).long().sum(),
+                       eng.w.double().abs().sum().view(torch.int64)])
+    allsig = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(allsig, sig)
+    same = all(bool((a == allsig[0]).all()) for a in allsig)
+    moved = bool((eng.w != w0).any())
+    eng.w.copy_(w0); eng.state.copy_(s0); eng._stage_dirty = True
+    eng.reset_optimizer()
+    return {"grad_equals_mean_of_shard_grads_rel_err": rel, "grad_ok": rel < 2e-3,
+            "weights_identical_across_ranks_after_4_steps": same, "weights_moved": moved, "world": world,
+            "shard_batch": b}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from unet_b200 import dist as D
+    from unet_b200.keras_api import AdamW, MeanIoU, Model
+    from utils.metrics import dice_coef
+
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the one JSON line
+    rank, local_rank, world = D.init_from_env("nccl")
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}", file=sys.stderr)
+    torch.cuda.set_device(local_rank)
+    if world > 1:       # torchrun pins OMP_NUM_THREADS=1: give each rank its share of the host cores for the staging copies
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+    mode, H, W, classes, batch, desc = WORKLOADS[args.workload]
+    batch = args.batch or batch
+    P3 = peaks()
+
+    def build(mode_):
+        m = Model((H, W, 3), num_classes=classes, dropout_rate=0.2, use_batch_norm=True, dtype=args.dtype, seed=2301)
+        # the reference's compile call (scripts/train.py:226-234): AdamW + dice_loss + [MeanIoU(2, 'mean_io_u'), dice_coef]
+        m.compile(optimizer=AdamW(learning_rate=2e-3, weight_decay=1e-4), loss="dice_loss",
+                  metrics=[MeanIoU(num_classes=max(2, classes), name="mean_io_u"), dice_coef])
+        if args.no_graphs:
+            m.engine.use_graphs = False
         if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        h2d = x_pin.numel() * 4 + (y_pin.numel() * 4 if mode == "train" else 0)
-        d2h = 12 if mode == "train" else batch * H * W * classes * 4
-        e2e = {"value": round(batch * world * args.steps / (float(ms2.item()) / 1e3), 2), "unit": "img/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+            dist.broadcast(m.engine.w, src=0)
+            dist.broadcast(m.engine.state, src=0)
+            m.engine._stage_dirty = True
+            if mode_ == "train":
+                m.enable_data_parallel()
+        return m
+
+    model = build(mode)
+    check = None
+    if args.check and world > 1 and mode == "train":
+        check = dp_check(model, H, W, classes, rank, world)
+    rec = measure(model, mode, batch, H, W, classes, args, rank, local_rank, world, P3)
+    eng = model.engine
+    graph = bool(eng.use_graphs and (model._grad_sync is None or getattr(eng, "graph_collectives", False)))
+
+    infer = None
+    if mode == "train" and not args.no_infer:
+        # the other half of BASELINE.json's metric ("train & infer img/s"): inference at the same resolution and batch, on
+        # the same model object (weights as trained so far), no communication (each rank serves its shard)
+        eng.release_plans()
+        torch.cuda.empty_cache()
+        hook, eng.grad_hook = eng.grad_hook, None
+        infer = measure(model, "infer", batch, H, W, classes, args, rank, local_rank, world, P3)
+        eng.grad_hook = hook
+        infer["config"] = {"workload": f"U-Net {H}x{W} inference, batch {batch}/GPU (model.predict, scripts/inference.py:116)",
+                           "batch_per_gpu": batch, "parallelism": f"batch sharded over {world} GPU(s), no communication"}
+        if rank == 0:
+            infer["kernels"] = infer["kernels"][:6]
 
     if rank != 0:
         return
-    # ---------------- roofline of the dominant kernel: the C-ABI entry point (one CUDA kernel, all its shapes) with the
-    # largest share of the step; achieved = its algorithmic bytes (or flops) over all launches / its summed launch time
-    rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
-    kernel_ms = sum(r["ms"] for _, r in rows)
-    byname = {}
-    for k, r in rows:
-        nm = k.split("[")[0]
-        if nm == "gemm_tc":
-            nm = "gemm_tc(" + k.split("[")[1].split(":")[0] + ")"      # nt / convt / wgrad are different kernels
-        a = byname.setdefault(nm, dict(ms=0.0, calls=0, bytes=0, flops=0, top=k, top_ms=0.0))
-        a["ms"] += r["ms"]; a["calls"] += r["calls"]; a["bytes"] += r["bytes"]; a["flops"] += r["flops"]
-        if r["ms"] > a["top_ms"]:
-            a["top"], a["top_ms"] = k, r["ms"]
-    top_name, top = max(byname.items(), key=lambda kv: kv[1]["ms"])
-    ai = top["flops"] / max(top["bytes"], 1)
-    if top_name.startswith("gemm_tc") and ai > RIDGE_FLOP_PER_BYTE:
-        roof = {"bound": "tensor", "achieved": round(top["flops"] / (top["ms"] * 1e-3) / 1e12, 2), "peak": tc_peak, "unit": "TFLOP/s"}
-    else:
-        roof = {"bound": "hbm", "achieved": round(top["bytes"] / (top["ms"] * 1e-3) / 1e9, 1), "peak": hbm_peak, "unit": "GB/s"}
-    roof["frac"] = round(roof["achieved"] / roof["peak"], 4)
-    roof["kernel"] = top_name
-    roof["launches_per_step"] = round(top["calls"] / args.steps, 1)
-    roof["avg_launch_ms"] = round(top["ms"] / top["calls"], 4)
-    roof["algorithmic_bytes_per_launch"] = int(top["bytes"] / top["calls"])
-    roof["share_of_step"] = round(top["ms"] / kernel_ms, 4)
-    roof["peak_source"] = f"{peak_kind} ({'MEASURED_PEAKS.json' if peak_kind == 'measured' else 'B200_PROFILING.md fallback'}, sustained)"
-    roof["traffic"] = None
-    try:        # ncu --set full dram bytes of this kernel's largest shape, scaled to the average launch of the step
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            tr = json.load(f)
-        shape_key = top["top"]
-        if shape_key not in tr:     # another shape of the same kernel was captured
-            cands = [k for k in tr if k.split("[")[0] == shape_key.split("[")[0] and k in prof]
-            shape_key = cands[0] if cands else shape_key
-        if shape_key in tr and shape_key in prof:
-            ratio = tr[shape_key] / (prof[shape_key]["bytes"] / prof[shape_key]["calls"])
-            roof["traffic"] = int(ratio * top["bytes"] / top["calls"])
-            roof["traffic_over_algorithmic"] = round(ratio, 4)
-            roof["traffic_shape"] = shape_key
-    except Exception:
-        pass
-    # whole-step HBM view: algorithmic bytes of every launch / step time
-    tot_bytes = sum(r["bytes"] for _, r in rows) / args.steps
-    tot_flops = sum(r["flops"] for _, r in rows) / args.steps
-    table = [{"kernel": k, "calls_per_step": r["calls"] / args.steps, "ms_per_step": round(r["ms"] / args.steps, 3),
-              "GBps": round(r["bytes"] / max(r["ms"], 1e-9) / 1e6, 1), "TFLOPs": round(r["flops"] / max(r["ms"], 1e-9) / 1e9, 2)}
-             for k, r in rows]
-    if args.breakdown:
-        for t in table:
-            print(f"{t['kernel']:58s} {t['calls_per_step']:5.1f} {t['ms_per_step']:9.3f} ms {t['GBps']:8.1f} GB/s {t['TFLOPs']:8.2f} TF/s",
-                  file=sys.stderr)
-
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(host_threads())
@@ -389,22 +492,22 @@ def run_b200(args):
                "sample": f"2 steps of batch {b} at {H}x{W}, torch-CPU fp32 port of the reference's TF path ({sec:.1f} s/step)"}
 
     line = {
-        "metric": f"{mode} img/s", "value": round(value, 2), "unit": "img/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "metric": rec["metric"], "value": rec["value"], "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": desc, "H": H, "W": W, "classes": classes, "batch_per_gpu": batch,
                    "global_batch": batch * world, "dropout": 0.2, "optimizer": "AdamW(2e-3, wd 1e-4)" if mode == "train" else None,
-                   "parallelism": f"dp{world}", "cuda_graph": bool(eng.use_graphs and model._grad_sync is None), "l2": "inputs and activations exceed L2 (126 MB) many times over; no flush needed"},
-        "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
-        "roofline": roof, "cpu_baseline": cpu,
-        "step_hbm": {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 2), "GBps": round(tot_bytes / (ms_total / args.steps) / 1e6, 1),
-                     "frac_of_peak": round(tot_bytes / (ms_total / args.steps) / 1e6 / hbm_peak, 4),
-                     "TFLOP_per_step": round(tot_flops / 1e12, 2)},
-        "kernels": table[:12],
+                   "metrics": "[MeanIoU(2,'mean_io_u'), dice_coef] updated every step" if mode == "train" else None,
+                   "parallelism": f"dp{world}", "cuda_graph": graph,
+                   "l2": "inputs and activations exceed L2 (126 MB) many times over; no flush needed"},
+        "clocks": rec["clocks"], "e2e": rec["e2e"], "e2e_pinned": rec["e2e_pinned"], "gpu_launches": rec["gpu_launches"],
+        "roofline": rec["roofline"], "cpu_baseline": cpu, "step_hbm": rec["step_hbm"], "kernels": rec["kernels"][:12],
     }
+    if check is not None:
+        line["check"] = check
+    if infer is not None:
+        line["infer"] = infer          # last key: the end of the line is what a log tail shows
     _emit(line)
-    if world > 1:
-        pass
 
 
 _JSON_FD = None

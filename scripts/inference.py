@@ -49,6 +49,37 @@ def _write(path: str, img, what: str) -> None:
         print(f"Error saving {what}: {e}")
 
 
+def postprocess_and_save_results(prob_mask_pred, original_bgr, orig_height: int, orig_width: int, output_mask_path: str,
+                                 output_cropped_path: str, binary_threshold: float = 0.5,
+                                 min_contour_area: float = 100.0) -> None:
+    """Same name, arguments and printed messages as the reference's function (scripts/inference.py:127-201): bilinear
+    resize of the (h, w, 1) probabilities to the original size, threshold -> {0,255} mask PNG, largest external contour ->
+    bounding-box crop of the original BGR image.  `prob_mask_pred` may be a host array (cv2 resize, as the reference) or a
+    CUDA tensor (the --gpu-prepost path: unet_postprocess_mask does the resize + threshold on the device)."""
+    from unet_b200 import imaging
+    if prob_mask_pred is None or original_bgr is None:
+        print("Error: Invalid input provided for postprocessing.")
+        return
+    print("Processing predicted mask...")
+    if hasattr(prob_mask_pred, "is_cuda") and prob_mask_pred.is_cuda:
+        mask = imaging.gpu_probability_to_mask(prob_mask_pred, orig_height, orig_width, binary_threshold)
+    else:
+        mask = imaging.probability_to_mask(prob_mask_pred, orig_height, orig_width, binary_threshold)
+    print(f"Saving binary mask to {output_mask_path} ...")
+    _write(output_mask_path, mask, "mask")
+    print("Finding largest contour for cropping...")
+    crop, area, rect = imaging.largest_region_crop(mask, original_bgr, min_contour_area)
+    if area is None:
+        print("No contours found in the binary mask. Cropped image not saved.")
+    elif crop is None:
+        print(f"Largest contour area ({area:.0f}) is below minimum threshold ({min_contour_area:.0f}). Cropped image not saved.")
+    else:
+        x0, y0, cw, ch = rect
+        print(f"Largest contour area: {area:.0f} > {min_contour_area:.0f}. Cropping region: (x={x0}, y={y0}, w={cw}, h={ch})")
+        print(f"Saving cropped image to {output_cropped_path} ...")
+        _write(output_cropped_path, crop, "cropped image")
+
+
 def main(argv=None):
     args = parse_args(argv)
     if not os.path.isfile(args.input):
@@ -102,24 +133,8 @@ def main(argv=None):
         sys.exit(1)
 
     print("Postprocessing results...")
-    print("Processing predicted mask...")
-    if args.gpu_prepost:
-        mask = imaging.gpu_probability_to_mask(pred[0], bgr.shape[0], bgr.shape[1], args.threshold)
-    else:
-        mask = imaging.probability_to_mask(pred[0], bgr.shape[0], bgr.shape[1], args.threshold)
-    print(f"Saving binary mask to {args.output_mask} ...")
-    _write(args.output_mask, mask, "mask")
-    print("Finding largest contour for cropping...")
-    crop, area, rect = imaging.largest_region_crop(mask, bgr, args.min_area)
-    if area is None:
-        print("No contours found in the binary mask. Cropped image not saved.")
-    elif crop is None:
-        print(f"Largest contour area ({area:.0f}) is below minimum threshold ({args.min_area:.0f}). Cropped image not saved.")
-    else:
-        x0, y0, cw, ch = rect
-        print(f"Largest contour area: {area:.0f} > {args.min_area:.0f}. Cropping region: (x={x0}, y={y0}, w={cw}, h={ch})")
-        print(f"Saving cropped image to {args.output_cropped} ...")
-        _write(args.output_cropped, crop, "cropped image")
+    postprocess_and_save_results(pred[0], bgr, bgr.shape[0], bgr.shape[1], args.output_mask, args.output_cropped,
+                                 binary_threshold=args.threshold, min_contour_area=args.min_area)
     print("Inference script finished.")
 
 

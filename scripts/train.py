@@ -72,6 +72,11 @@ def main(argv=None):
     rank, local_rank, world = D.init_from_env()
     size = (args.image_size, args.image_size)
     bs = args.batch_size
+    if world > 1 and (bs < world or bs % world != 0):
+        # every rank must get the same, non-empty share of every batch: an empty shard cannot run a step (the other ranks
+        # would wait for it in the gradient all-reduce) and unequal shards would be mis-weighted by the 1/world average
+        print(f"Error: --batch-size ({bs}) must be a positive multiple of the number of GPUs ({world}) for data-parallel training.")
+        sys.exit(1)
     try:
         if args.synthetic:
             n_train, n_val = args.synthetic, max(bs, args.synthetic // 5)
@@ -88,8 +93,11 @@ def main(argv=None):
             val_it = PairedDirectoryIterator(VAL_FRAMES_DIR, VAL_MASKS_DIR, size, bs, shuffle=False, seed=SEED)
             n_train, n_val = train_it.samples, val_it.samples
             lo, hi = D.shard_range(bs, rank, world)
-            train_gen = ((x[lo:hi], y[lo:hi]) for x, y in train_it)
-            val_gen = ((x[lo:hi], y[lo:hi]) for x, y in val_it)
+            # Keras' iterator yields the short last batch of each pass; data parallel only takes full batches (see above),
+            # and every rank skips the same ones, so the ranks stay in lock-step
+            full = (lambda it: it) if world == 1 else (lambda it: (b for b in it if len(b[0]) == bs))
+            train_gen = ((x[lo:hi], y[lo:hi]) for x, y in full(train_it))
+            val_gen = ((x[lo:hi], y[lo:hi]) for x, y in full(val_it))
     except Exception as e:
         print("\n--- Error setting up data generators ---")
         print(f"{e}")
@@ -99,6 +107,9 @@ def main(argv=None):
         sys.exit(1)
     if n_val == 0:
         print(f"Error: No validation images found in {VAL_FRAMES_DIR}")
+        sys.exit(1)
+    if world > 1 and (n_train < bs or n_val < bs):
+        print(f"Error: data-parallel training needs at least one full batch ({bs}) of training ({n_train}) and validation ({n_val}) images.")
         sys.exit(1)
 
     print("Building U-Net model...")
@@ -112,6 +123,7 @@ def main(argv=None):
     if world > 1:
         import torch.distributed as dist
         dist.broadcast(model.engine.w, src=0)
+        dist.broadcast(model.engine.state, src=0)
         model.engine._stage_dirty = True
         model.enable_data_parallel()
 

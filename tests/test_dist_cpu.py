@@ -23,11 +23,13 @@ def _worker(rank, world, port, out):
     regions = D.grad_regions(spec)
     g = torch.full((spec.n_trainable_flat,), float(rank + 1))
     g[:: 7] = rank * 10.0
-    sync = D.GradSync(g, regions)
+    moving = torch.tensor([float(rank), 4.0])               # rides with the first region, averaged (BN moving statistics)
+    sync = D.GradSync(g, regions, mean_with_first=moving)
     order = []
     for name in ("decoder", "bottleneck", "encoder"):        # the order backward completes them
         sync.ready(name); order.append(name)
     sync.finish()
+    assert moving.tolist() == [0.5, 4.0]
     stats = torch.tensor([float(rank), 2.0 * rank])
     D.average_(stats)
     lo, hi = D.shard_range(10, rank, world)
@@ -53,7 +55,7 @@ def test_two_rank_gradient_exchange():
         np.testing.assert_allclose(head, expect[:16])
         assert total == pytest.approx(expect.sum())
         assert stats == [0.5, 1.0]
-        assert nbytes == n * 4                              # every parameter crossed the wire exactly once
+        assert nbytes == n * 4 + 8                          # every parameter (and the 2 statistics) crossed the wire exactly once
     assert [r[5] for r in res] == [(0, 5), (5, 10)]
 
 

@@ -248,6 +248,32 @@ def test_postprocessing_known_answer(tmp_path):
     assert imaging.sample_iou(np.ones((4, 4, 1)), np.zeros((4, 4))) == pytest.approx(1e-7 / (16 + 1e-7), rel=1e-2)
 
 
+def test_chile_id_card_known_answer(tmp_path):
+    """The one byte-exact fixture the reference holds: samples/test_images/chile_id_card.png with
+    samples/usage/chile_id_card/output_{mask,cropped}.png — the reference's own post-processing output
+    (scripts/inference.py:173-187).  Copied unmodified into tests/golden/chile_id_card/."""
+    import cv2
+    from unet_b200 import imaging
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import importlib
+    inference = importlib.import_module("inference")
+    gold = os.path.join(ROOT, "tests", "golden", "chile_id_card")
+    bgr = cv2.imread(os.path.join(gold, "input.png"), cv2.IMREAD_COLOR)
+    mask = cv2.imread(os.path.join(gold, "output_mask.png"), cv2.IMREAD_GRAYSCALE)
+    want = cv2.imread(os.path.join(gold, "output_cropped.png"), cv2.IMREAD_COLOR)
+    assert bgr.shape == (960, 540, 3) and mask.shape == (960, 540) and set(np.unique(mask).tolist()) == {0, 255}
+    crop, area, rect = imaging.largest_region_crop(mask, bgr, 100.0)
+    assert rect == (38, 296, 466, 300) and area == 128625.0
+    np.testing.assert_array_equal(crop, want)                      # byte-exact
+    # ... and through the script's own post-processing entry point (same name and arguments as the reference's), from a
+    # probability map: one at the original size (identity resize) and one at the model's 256x256 that upsamples to the mask
+    prob_full = (mask.astype(np.float32) / 255.0)[..., None]
+    out_m, out_c = str(tmp_path / "m.png"), str(tmp_path / "c.png")
+    inference.postprocess_and_save_results(prob_full, bgr, 960, 540, out_m, out_c, binary_threshold=0.5, min_contour_area=100.0)
+    np.testing.assert_array_equal(cv2.imread(out_m, cv2.IMREAD_GRAYSCALE), mask)
+    np.testing.assert_array_equal(cv2.imread(out_c, cv2.IMREAD_COLOR), want)
+
+
 def test_quad_mask(tmp_path):
     import cv2
     from unet_b200 import imaging

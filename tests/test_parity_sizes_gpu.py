@@ -1,0 +1,336 @@
+"""Parity at the BENCHMARKED configurations (BASELINE.json configs[0..4]) — the sizes at which the 512-wide strip kernels,
+4-stage TMA rings, `pw_bwd_fused` and > 2^31-element index arithmetic actually engage.
+
+Oracle = the torch-CPU restatement (oracle/torch_ref.py: model/u_net.py:5-116 + SURVEY Appendix A) run on the SAME seeded
+inputs and weights; where a full-size oracle run does not fit a CPU (batch 64 at 512x512) the comparison uses properties that
+do not depend on size: inference is per-image independent (oracle on sampled images), and a batch made of r copies of a
+smaller batch has the same BatchNormalization statistics, loss and mean gradient as the smaller batch.
+Tolerances are BASELINE.json's north_star: fp32 probabilities <= 1e-4 max abs; bf16 <= 2e-2 max abs and >= 99.9 % agreement of
+the thresholded mask; loss and MeanIoU within 1e-3.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import torch_ref as TR
+from oracle import unet_ref as R
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def dev(a):
+    return torch.tensor(np.asarray(a, dtype=np.float32), device="cuda")
+
+
+def _params(shape, nc, rate=0.2, seed=3, decisive=True):
+    P = R.init_params(R.layer_specs(shape, nc, rate, True), seed=seed, trained_like=True)
+    if decisive:                 # decisive logits, as a trained model has (otherwise every pixel sits at p ~ 0.5)
+        P["output_mask/kernel"] = P["output_mask/kernel"] * 8.0
+    return P
+
+
+def _engine(shape, nc, rate, dtype, P):
+    from unet_b200.engine import UNetEngine
+    eng = UNetEngine(shape, num_classes=nc, dropout_rate=rate, use_batch_norm=True, dtype=dtype)
+    eng.dropout_masks_from_step = False
+    eng.set_weights(P)
+    return eng
+
+
+def _oracle_infer(P, x, nc):
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    Pt = TR.to_torch(P, dtype=torch.float64)
+    with torch.no_grad():
+        return TR.forward(Pt, torch.tensor(x, dtype=torch.float64), nc, 0.2, True, training=False).numpy()
+
+
+def _check_probs(got, ref, dtype, nc):
+    err = float(np.abs(got - ref).max())
+    if dtype == "fp32":
+        assert err <= 1e-4, err
+        return err
+    assert err <= 2e-2, err
+    agree = np.mean((got > 0.5) == (ref > 0.5)) if nc == 1 else np.mean(got.argmax(-1) == ref.argmax(-1))
+    assert agree >= 0.999, agree
+    return err
+
+
+def _mean_iou(y, p, nc):
+    m = R.MeanIoU(max(nc, 2))
+    if nc == 1:
+        m.update_state(y, (p > 0.5).astype(np.float32))
+    else:
+        m.update_state(y.argmax(-1), p.argmax(-1))
+    return m.result()
+
+
+# ------------------------------------------------------------------------------------------ configs[0]: 256x256, batch 8
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_config0_infer_256_batch8(dtype):
+    shape = (256, 256, 3)
+    P = _params(shape, 1)
+    x, y = R.synthetic_batch(8, 256, 256, 3, 1, seed=2301)
+    ref = _oracle_infer(P, x, 1)
+    eng = _engine(shape, 1, 0.2, dtype, P)
+    got = eng.forward_inference(dev(x)).cpu().numpy()
+    _check_probs(got, ref, dtype, 1)
+    assert abs(_mean_iou(y, got, 1) - _mean_iou(y, ref, 1)) <= 1e-3
+    out3 = eng.evaluate_batch(dev(x), dev(y)).cpu().numpy()
+    assert abs(out3[1] - R.dice_coef(y, ref, dtype=np.float64)) <= 1e-3
+    assert abs(out3[2] - R.iou_coef(y, ref, dtype=np.float64)) <= 1e-3
+    # the same through the public surface with CUDA-graph replay (what bench.py and the CLIs run)
+    eng.use_graphs = True
+    for _ in range(2):
+        _check_probs(eng.forward_inference(dev(x)).cpu().numpy(), ref, dtype, 1)
+
+
+# ------------------------------------------------------------------------------------------ configs[1]: 256x256 training, batch 32
+def test_config1_train_256_batch32_replicated():
+    """batch 32 = 4 copies of 8 distinct samples: BatchNormalization statistics, Dice loss and mean gradient equal those of
+    the 8-sample batch, which the oracle runs in fp64 with autograd."""
+    shape = (256, 256, 3)
+    P = _params(shape, 1, rate=0.0, decisive=False)
+    x, y = R.synthetic_batch(8, 256, 256, 3, 1, seed=77)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    loss_ref, _, grads_ref = TR.loss_and_grads(P, x, y, 1, 0.0, True, dtype=torch.float32)
+    eng = _engine(shape, 1, 0.0, "bf16", P)
+    out3 = eng.train_forward_backward(dev(np.tile(x, (4, 1, 1, 1))), dev(np.tile(y, (4, 1, 1, 1)))).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= 1e-3
+    _grad_cosines(eng, grads_ref, per_tensor=0.8, overall=0.95)
+
+
+def _grad_cosines(eng, grads_ref, per_tensor, overall):
+    num = da = db = 0.0
+    worst = (1.0, "")
+    for name, gr in grads_ref.items():
+        g = eng.wview(name, eng.g).cpu().numpy().reshape(gr.shape).astype(np.float64)
+        gr = gr.astype(np.float64)
+        a, b, c = float((g * gr).sum()), float((g * g).sum()), float((gr * gr).sum())
+        cos = a / np.sqrt(b * c + 1e-300)
+        worst = min(worst, (cos, name))
+        num += a; da += b; db += c
+    cos_all = num / np.sqrt(da * db)
+    assert worst[0] > per_tensor, worst
+    assert cos_all > overall, cos_all
+    assert 0.9 < np.sqrt(da / db) < 1.1
+    return cos_all, worst
+
+
+# ------------------------------------------------------------------------------------------ configs[2]: 512x512
+def test_config2_infer_512_batch64_sampled():
+    """The BENCH configuration's forward at batch 64 (level-0 tensors hold 2^31 elements): inference is per-image
+    independent, so the oracle runs on sampled images (first, middle, last: the last one sits above the 2^31 offset)."""
+    shape = (512, 512, 3)
+    P = _params(shape, 1)
+    x, y = R.synthetic_batch(64, 512, 512, 3, 1, seed=2301)
+    eng = _engine(shape, 1, 0.2, "bf16", P)
+    eng.use_graphs = True
+    got = eng.forward_inference(dev(x)).cpu().numpy()
+    pick = [0, 31, 63]
+    ref = _oracle_infer(P, x[pick], 1)
+    _check_probs(got[pick], ref, "bf16", 1)
+    assert abs(_mean_iou(y[pick], got[pick], 1) - _mean_iou(y[pick], ref, 1)) <= 1e-3
+    # every image must have been produced by the same arithmetic: per-image Dice against its own truth is finite and the
+    # batch's images are all distinct inputs -> distinct outputs
+    assert np.isfinite(got).all() and got.min() >= 0.0 and got.max() <= 1.0
+    sums = got.reshape(64, -1).sum(1)
+    assert len(np.unique(np.round(sums, 3))) == 64
+
+
+def test_config2_train_512_batch8_vs_oracle():
+    """512x512 training step, Dropout(0.2) on, batch 8: loss within 1e-3, per-tensor gradient direction, new BN moving
+    statistics — against the torch-CPU oracle (fp32 autograd; the dropout masks are the oracle's restatement of the hash)."""
+    import psutil
+    nb = 8 if psutil.virtual_memory().available > 56e9 else 4      # the fp32 autograd oracle keeps ~3.4 GB per 512x512 sample
+    shape = (512, 512, 3)
+    P = _params(shape, 1, decisive=False)
+    x, y = R.synthetic_batch(nb, 512, 512, 3, 1, seed=512)
+    eng = _engine(shape, 1, 0.2, "bf16", P)
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    loss_ref, probs_ref, grads_ref = TR.loss_and_grads(P, x, y, 1, 0.2, True, drop_seeds=eng._drop_seed, dtype=torch.float32)
+    out3 = eng.train_forward_backward(dev(x), dev(y)).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= 1e-3, (out3[0], loss_ref)
+    probs = eng._plans[(nb, True)].t["probs"].cpu().numpy()
+    assert np.abs(probs - probs_ref).max() <= 2e-2
+    _grad_cosines(eng, grads_ref, per_tensor=0.8, overall=0.95)
+
+
+def test_config2_train_512_batch64_replicated():
+    """The BENCH configuration itself (batch 64, 512x512, 2^31-element level-0 tensors, every large-shape kernel path): the
+    batch is 8 copies of the 8 samples above, so loss / BN statistics / mean gradients must equal the batch-8 step's (both on
+    the engine; the batch-8 step is checked against the oracle by the test above), Dropout off so the masks do not depend on
+    the sample index.  Then CUDA-graph replayed steps must keep reducing the loss."""
+    shape = (512, 512, 3)
+    P = _params(shape, 1, rate=0.0, decisive=False)
+    x, y = R.synthetic_batch(8, 512, 512, 3, 1, seed=512)
+    e8 = _engine(shape, 1, 0.0, "bf16", P)
+    l8 = e8.train_forward_backward(dev(x), dev(y)).cpu().numpy()
+    g8 = e8.g.clone()
+    mm8 = e8.wview("bneck_block2_bn/moving_variance").clone()
+    e8.release_plans(); del e8
+    torch.cuda.empty_cache()
+    e64 = _engine(shape, 1, 0.0, "bf16", P)
+    xd, yd = dev(np.tile(x, (8, 1, 1, 1))), dev(np.tile(y, (8, 1, 1, 1)))
+    l64 = e64.train_forward_backward(xd, yd).cpu().numpy()
+    np.testing.assert_allclose(l64, l8, atol=2e-4)
+    a, b = e64.g.double(), g8.double()
+    cos = float((a * b).sum() / (a.norm() * b.norm()))
+    assert cos > 0.995, cos                         # same arithmetic up to summation order / split-K partition of bf16 data
+    assert 0.98 < float(a.norm() / b.norm()) < 1.02
+    np.testing.assert_allclose(e64.wview("bneck_block2_bn/moving_variance").cpu().numpy(), mm8.cpu().numpy(), rtol=2e-3, atol=1e-6)
+    for name in ("output_mask/kernel", "dec1_block2_sepconv/depthwise_kernel", "dec1_upsample/kernel", "enc1_block2_sepconv/pointwise_kernel",
+                 "enc1_block1_sepconv/depthwise_kernel", "bneck_block2_sepconv/pointwise_kernel"):
+        u, v = e64.wview(name, e64.g).double(), e64.wview(name, g8).double()
+        assert float((u * v).sum() / (u.norm() * v.norm() + 1e-300)) > 0.98, name
+    e64.use_graphs = True
+    e64.apply_gradients()
+    losses = [float(e64.train_step(xd, yd)[0]) for _ in range(6)]
+    assert losses[-1] < float(l64[0]), (losses, l64)
+
+
+# ------------------------------------------------------------------------------------------ configs[3]: 1024x1024 inference
+def test_config3_infer_1024_batch2():
+    shape = (1024, 1024, 3)
+    P = _params(shape, 1)
+    x, y = R.synthetic_batch(2, 1024, 1024, 3, 1, seed=1024)
+    ref = _oracle_infer(P, x, 1)
+    got = _engine(shape, 1, 0.2, "bf16", P).forward_inference(dev(x)).cpu().numpy()
+    _check_probs(got, ref, "bf16", 1)
+    assert abs(_mean_iou(y, got, 1) - _mean_iou(y, ref, 1)) <= 1e-3
+
+
+# ------------------------------------------------------------------------------------------ configs[4]: 8 classes, 512x512
+def test_config4_8class_512_infer_and_train():
+    shape = (512, 512, 3)
+    P = _params(shape, 8)
+    x, y = R.synthetic_batch(2, 512, 512, 3, 8, seed=8)
+    ref = _oracle_infer(P, x, 8)
+    eng = _engine(shape, 8, 0.2, "bf16", P)
+    got = eng.forward_inference(dev(x)).cpu().numpy()
+    _check_probs(got, ref, "bf16", 8)
+    assert abs(_mean_iou(y, got, 8) - _mean_iou(y, ref, 8)) <= 1e-3
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    loss_ref, _, grads_ref = TR.loss_and_grads(P, x, y, 8, 0.2, True, drop_seeds=eng._drop_seed, dtype=torch.float32)
+    out3 = eng.train_forward_backward(dev(x), dev(y)).cpu().numpy()
+    assert abs(out3[0] - loss_ref) <= 1e-3
+    _grad_cosines(eng, grads_ref, per_tensor=0.7, overall=0.93)
+    # MeanIoU(8) on device (argmax labels), the benchmark.py flow of configs[4]
+    from unet_b200.keras_api import MeanIoU
+    m = MeanIoU(8)
+    m.update_state(y.argmax(-1).astype(np.float32), got.argmax(-1).astype(np.float32))
+    assert abs(float(m.result()) - _mean_iou(y, got, 8)) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------ 2^31-element operands
+def _rows_ref_dwbwd(x, dy, wk, n, r0, r1):
+    """oracle depthwise backward (dx) for rows [r0, r1) of image n, computed from a slab with one halo row either side"""
+    H = x.shape[1]
+    lo, hi = max(r0 - 1, 0), min(r1 + 1, H)
+    xs = x[n:n + 1, lo:hi].float().cpu().numpy().astype(np.float64)
+    dys = dy[n:n + 1, lo:hi].float().cpu().numpy().astype(np.float64)
+    dx, _ = R.dwconv3x3_bwd(xs, wk.astype(np.float64), dys)
+    return dx[0, r0 - lo:r1 - lo], xs[0, r0 - lo:r1 - lo]
+
+
+def test_dwconv_bwd_on_2pow31_elements():
+    """dec1_block1's fused depthwise backward at the BENCH shape: 64 x 512 x 512 x 128 = 2^31 elements per tensor.  dx checked
+    on sampled rows (incl. the last image, above the 2^31 offset, and image borders); dw and the BN reductions checked
+    exactly through sparsity: dy is non-zero only inside a few slabs, so the full-tensor sums equal the slab sums."""
+    N, H, W, C = 64, 512, 512, 128
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    x = torch.empty((N, H, W, C), device="cuda", dtype=torch.bfloat16)
+    for i in range(0, N, 8):                      # fill in chunks: randn at fp32 for the whole tensor would need 8 GB
+        x[i:i + 8] = torch.randn((8, H, W, C), device="cuda", generator=g).clamp_(min=0).to(torch.bfloat16)
+    dy = torch.zeros((N, H, W, C), device="cuda", dtype=torch.bfloat16)
+    slabs = [(0, 0, 6), (17, 250, 262), (63, 500, 512), (63, 0, 5)]
+    for n, r0, r1 in slabs:
+        dy[n, r0:r1] = torch.randn((r1 - r0, W, C), device="cuda", generator=g).to(torch.bfloat16)
+    wk = np.random.default_rng(1).standard_normal((3, 3, C)).astype(np.float32)
+    dx = torch.empty_like(x)
+    dw = torch.zeros((9, C), device="cuda")
+    sums = torch.zeros((2, C), device="cuda")
+    from unet_b200 import ops
+    ops.dwconv3x3_bwd(x, dy, dev(wk.reshape(9, C)), dx, dw, relu_mask=True, bn_sums=sums)
+    torch.cuda.synchronize()
+    dw_ref = np.zeros((3, 3, C)); s0 = np.zeros(C); s1 = np.zeros(C)
+    for n, r0, r1 in slabs:
+        a, b = max(r0 - 2, 0), min(r1 + 2, H)      # dx is non-zero one row beyond the slab; take two for the halo
+        ref, xs = _rows_ref_dwbwd(x, dy, wk, n, a, b)
+        ref = ref * (xs > 0)
+        got = dx[n, a:b].float().cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(got, ref, rtol=1.0 / 128, atol=1e-2)
+        s0 += got.sum((0, 1)); s1 += (got * xs).sum((0, 1))
+        lo, hi = max(a - 1, 0), min(b + 1, H)
+        _, dwn = R.dwconv3x3_bwd(x[n:n + 1, lo:hi].float().cpu().numpy().astype(np.float64), wk.astype(np.float64),
+                                 dy[n:n + 1, lo:hi].float().cpu().numpy().astype(np.float64))
+        dw_ref += dwn
+    # rows far from every slab must be exactly zero (also above the 2^31 offset)
+    assert float(dx[40].abs().max()) == 0.0 and float(dx[63, 100:400].abs().max()) == 0.0
+    np.testing.assert_allclose(dw.cpu().numpy().reshape(3, 3, C), dw_ref, rtol=2e-3, atol=0.5)
+    np.testing.assert_allclose(sums[0].cpu().numpy(), s0, rtol=2e-3, atol=0.5)
+    np.testing.assert_allclose(sums[1].cpu().numpy(), s1, rtol=2e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("cfg", [(64, 256, 256, 128, 64, 0.0), (64, 128, 128, 256, 128, 0.2)])
+def test_convt_gemm_at_bench_shapes(cfg):
+    """Conv2DTranspose as a tcgen05 GEMM with the 5-D TMA pixel-shuffle store at the BENCH shapes: dec1_upsample (the concat
+    buffer holds 2^31 elements) and dec2_upsample with Dropout in the epilogue.  Checked on sampled input rows."""
+    from unet_b200 import ops
+    n, h, w, cin, cout, rate = cfg
+    g = torch.Generator(device="cuda"); g.manual_seed(9)
+    x = torch.randn((n, h, w, cin), device="cuda", generator=g).to(torch.bfloat16)
+    rng = np.random.default_rng(4)
+    k = (rng.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = rng.standard_normal(cout).astype(np.float32)
+    Bnk = torch.tensor(k.reshape(4 * cout, cin), device="cuda").to(torch.bfloat16)         # [(a,b,co), Cin]
+    concat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), device="cuda", dtype=torch.bfloat16)
+    drop = ops.make_dropout(rate, 5, ctot=2 * cout, c0=0)
+    ops.gemm(x, Bnk, concat[..., :cout], b_trans=True, epilogue=ops.EPI_CONVT, shift=dev(b), convt_hw=(h, w), drop=drop)
+    torch.cuda.synchronize()
+    kr = Bnk.float().cpu().numpy().astype(np.float64).reshape(2, 2, cout, cin)
+    for img, i in [(0, 0), (n // 2, h // 2), (n - 1, h - 1), (n - 1, 0)]:
+        xs = x[img:img + 1, i:i + 1].float().cpu().numpy().astype(np.float64)              # one input row -> two output rows
+        ref = R.convt2x2(xs, kr, b.astype(np.float64))[0]
+        if rate > 0:
+            base = ((img * 2 * h + 2 * i) * 2 * w) * 2 * cout
+            idx = (np.uint64(base) + np.arange(2 * 2 * w * 2 * cout, dtype=np.uint64))
+            hsh = R.dropout_hash(idx >> np.uint64(1), 5)
+            r = np.where((idx & np.uint64(1)) == 1, hsh >> np.uint32(16), hsh & np.uint32(0xFFFF)).astype(np.uint32)
+            keep = np.float32(1.0 - rate)
+            mult = np.where(r < np.uint32(keep * np.float32(65536.0)), np.float32(1.0) / keep, np.float32(0)).reshape(2, 2 * w, 2 * cout)
+            ref = ref * mult[..., :cout]
+        got = concat[img, 2 * i:2 * i + 2, :, :cout].float().cpu().numpy().astype(np.float64)
+        np.testing.assert_allclose(got, ref, rtol=1.0 / 128, atol=1e-2)
+    assert float(concat[..., cout:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------ the reference-held fixture, on the GPU path
+def test_chile_id_card_through_gpu_postprocess(tmp_path):
+    """samples/usage/chile_id_card (scripts/inference.py:173-187): unet_postprocess_mask (resize + threshold on the device)
+    reproduces the reference's mask, and the crop is byte-exact."""
+    import cv2
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import importlib
+    inference = importlib.import_module("inference")
+    gold = os.path.join(ROOT, "tests", "golden", "chile_id_card")
+    bgr = cv2.imread(os.path.join(gold, "input.png"), cv2.IMREAD_COLOR)
+    mask = cv2.imread(os.path.join(gold, "output_mask.png"), cv2.IMREAD_GRAYSCALE)
+    want = cv2.imread(os.path.join(gold, "output_cropped.png"), cv2.IMREAD_COLOR)
+    prob = torch.tensor(mask.astype(np.float32) / 255.0, device="cuda")[..., None].contiguous()
+    out_m, out_c = str(tmp_path / "m.png"), str(tmp_path / "c.png")
+    inference.postprocess_and_save_results(prob, bgr, bgr.shape[0], bgr.shape[1], out_m, out_c, 0.5, 100.0)
+    np.testing.assert_array_equal(cv2.imread(out_m, cv2.IMREAD_GRAYSCALE), mask)
+    np.testing.assert_array_equal(cv2.imread(out_c, cv2.IMREAD_COLOR), want)
+    # a 256x256 probability map (the model's output size), upsampled on the device, must equal cv2's upsample + threshold
+    small = cv2.resize(mask.astype(np.float32) / 255.0, (256, 256), interpolation=cv2.INTER_LINEAR)[..., None]
+    from unet_b200 import imaging
+    m_cv = imaging.probability_to_mask(small, bgr.shape[0], bgr.shape[1], 0.5)
+    m_gpu = imaging.gpu_probability_to_mask(torch.tensor(small, device="cuda"), bgr.shape[0], bgr.shape[1], 0.5)
+    assert np.mean(m_cv != m_gpu) <= 1e-5          # identical up to fp32 rounding exactly at the threshold
+    c1, a1, r1 = imaging.largest_region_crop(m_gpu, bgr, 100.0)
+    c2, a2, r2 = imaging.largest_region_crop(m_cv, bgr, 100.0)
+    assert r1 == r2

@@ -52,36 +52,52 @@ def grad_regions(spec) -> List[Tuple[str, int, int]]:
 
 class GradSync:
     """Sums `flat` across ranks region by region.  `ready(name)` is called by the engine when backward has finished
-    a region; `finish()` makes the compute stream wait for all exchanges.  Works on CPU tensors (gloo) for tests."""
+    a region; `finish()` makes the compute stream wait for all exchanges.  `mean_with_first`: a tensor averaged across ranks
+    together with the first region (the BatchNormalization moving statistics: final once the forward pass is over, so their
+    exchange hides behind backward instead of being a second, serialised collective at the end of the step).
+    Fork/join structure only (events and stream waits, no host blocking), so a whole training step including its
+    collectives can be captured into a CUDA graph.  Works on CPU tensors (gloo) for tests."""
 
-    def __init__(self, flat: torch.Tensor, regions: List[Tuple[str, int, int]], group=None):
+    def __init__(self, flat: torch.Tensor, regions: List[Tuple[str, int, int]], group=None,
+                 mean_with_first: Optional[torch.Tensor] = None):
         self.flat, self.group = flat, group
         self.regions = {name: (lo, hi) for name, lo, hi in regions}
+        self.first = regions[0][0]
+        self.mean_with_first = mean_with_first
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.cuda = flat.is_cuda
         self.comm_stream = torch.cuda.Stream(device=flat.device) if self.cuda and self.world > 1 else None
-        self._pending = []
         self.bytes_exchanged = 0
+
+    def _exchange(self, name: str) -> None:
+        lo, hi = self.regions[name]
+        view = self.flat[lo:hi]
+        self.bytes_exchanged += view.numel() * view.element_size()
+        dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        t = self.mean_with_first
+        if t is not None and name == self.first:
+            self.bytes_exchanged += t.numel() * t.element_size()
+            if self.cuda:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)        # ncclAvg: no separate scaling kernel
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.div_(self.world)
 
     def ready(self, name: str) -> None:
         if self.world == 1:
             return
-        lo, hi = self.regions[name]
-        view = self.flat[lo:hi]
-        self.bytes_exchanged += view.numel() * view.element_size()
-        if self.cuda:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream())
-            with torch.cuda.stream(self.comm_stream):
-                self.comm_stream.wait_event(ev)
-                self._pending.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        else:
-            self._pending.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if not self.cuda:
+            self._exchange(name)
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ev)          # fork: the collective starts when backward has written the region
+            self._exchange(name)                     # NCCL runs on its own stream; comm_stream waits for it (no host block)
 
     def finish(self) -> None:
-        for w in self._pending:
-            w.wait()          # CUDA: the current stream waits for the collective; no host block
-        self._pending.clear()
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)              # join
 
 
 def average_(t: torch.Tensor, group=None) -> None:

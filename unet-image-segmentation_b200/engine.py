@@ -119,6 +119,8 @@ class UNetEngine:
         self.use_graphs = False                 # replay inference / single-GPU training steps from CUDA graphs
         self._graphs: Dict[tuple, tuple] = {}
         self.grad_hook = None                   # callable(region) — dist.GradSync.ready; regions: decoder, bottleneck, encoder
+        self.grad_finish = None                 # callable() — dist.GradSync.finish: the compute stream joins the exchanges
+        self.graph_collectives = True           # data parallel: capture the step INCLUDING its NCCL exchanges into the CUDA graph
         self.init_weights(seed)
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -703,13 +705,20 @@ class UNetEngine:
         self._stage_dirty = True
         self._restage()
 
+    def _step_eager(self, x, y_true, loss):
+        out3 = self.train_forward_backward(x, y_true, loss)
+        if self.grad_finish is not None:
+            self.grad_finish()
+        self.apply_gradients()
+        return out3
+
     def train_step(self, x: torch.Tensor, y_true: torch.Tensor, loss: str = "dice") -> torch.Tensor:
-        """forward + backward + AdamW.  Single-GPU steps are replayed from a CUDA graph when `use_graphs` is set (the
-        learning rate, the Adam step count and the dropout seed word live in device memory, so a replay is a new step)."""
-        if not self.use_graphs or self.grad_hook is not None or ops._prof is not None:
-            out3 = self.train_forward_backward(x, y_true, loss)
-            self.apply_gradients()
-            return out3
+        """forward + backward (+ data-parallel gradient exchange) + AdamW.  Steps are replayed from a CUDA graph when
+        `use_graphs` is set (the learning rate, the Adam step count and the dropout seed word live in device memory, so a
+        replay is a new step); under data parallel the NCCL exchanges are part of the graph (`graph_collectives`)."""
+        if (not self.use_graphs or ops._prof is not None
+                or (self.grad_hook is not None and not self.graph_collectives)):
+            return self._step_eager(x, y_true, loss)
         B = x.shape[0]
         key = ("train", B, loss)
         ent = self._graphs.get(key)
@@ -718,16 +727,26 @@ class UNetEngine:
             gx = pl.buf("graph_x", tuple(x.shape), torch.float32)
             gy = pl.buf("graph_y", tuple(y_true.shape), torch.float32)
             gx.copy_(x); gy.copy_(y_true)
-            out3 = self.train_forward_backward(gx, gy, loss)     # a real (eager) step doubles as the warm-up
-            self.apply_gradients()
+            out3 = self._step_eager(gx, gy, loss)                # a real (eager) step doubles as the warm-up
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                cap = self.train_forward_backward(gx, gy, loss)
-                self.apply_gradients()
+            try:
+                with torch.cuda.graph(g):
+                    cap = self._step_eager(gx, gy, loss)
+            except Exception as e:
+                if self.grad_hook is None:
+                    raise
+                # collectives could not be captured on this NCCL / driver combination: keep launching eagerly
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the data-parallel step failed ({e}); running eagerly")
+                self.graph_collectives = False
+                torch.cuda.synchronize()
+                return out3
             self._graphs[key] = (g, gx, gy, cap)
             return out3
         g, gx, gy, out3 = ent
+        self._restage()          # set_weights / load_weights since the last step: refresh the bf16 operand copies (conditional,
+                                 # so it lives outside the graph; the graph itself restages after its own AdamW step)
         if x.data_ptr() != gx.data_ptr():
             gx.copy_(x)
         if y_true.data_ptr() != gy.data_ptr():

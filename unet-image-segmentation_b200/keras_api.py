@@ -618,8 +618,10 @@ class Model:
         """Sum gradients across ranks (dist.GradSync) and scale by 1/world; average BN moving statistics."""
         from . import dist as D
         eng = self.engine
-        self._grad_sync = D.GradSync(eng.g, D.grad_regions(eng.spec), group)
+        self._grad_sync = D.GradSync(eng.g, D.grad_regions(eng.spec), group, mean_with_first=eng.state)
         eng.grad_hook = self._grad_sync.ready
+        eng.grad_finish = self._grad_sync.finish
+        eng.graph_collectives = os.environ.get("UNET_B200_GRAPH_NCCL", "1") != "0"
         eng.set_hyper(grad_scale=1.0 / self._grad_sync.world)
 
     def train_on_batch(self, x, y, return_dict=False):
@@ -639,14 +641,7 @@ class Model:
             raise RuntimeError("You must call `compile()` before using the model for training.")
         eng = self.engine
         xd, yd = self._stage_in(x, "tx"), self._stage_in(y, "ty")
-        if self._grad_sync is None:
-            out3 = eng.train_step(xd, yd, self._loss_kind)
-        else:
-            out3 = eng.train_forward_backward(xd, yd, self._loss_kind)
-            self._grad_sync.finish()
-            from . import dist as D
-            D.average_(eng.state)
-            eng.apply_gradients()
+        out3 = eng.train_step(xd, yd, self._loss_kind)     # under data parallel the gradient / BN-statistics exchange is inside
         for m in self.metrics:
             if isinstance(m, MeanIoU):
                 m.update_state(yd, eng._plans[(xd.shape[0], True)].t["probs"])
@@ -665,6 +660,23 @@ class Model:
         probs = eng._plans[(xd.shape[0], False)].t["probs"]
         return out3, yd, probs
 
+    def _dp_reduce(self, acc, n, metrics):
+        """Under data parallel every rank sees only its shard of each batch.  Sum the (loss, dice, iou) accumulators, the
+        batch count and the MeanIoU confusion counts over the ranks, so that logs — and with them ModelCheckpoint,
+        EarlyStopping and ReduceLROnPlateau decisions — are identical on every rank (ranks that disagreed about the learning
+        rate would silently diverge; ranks that disagreed about stopping would hang in the next all-reduce)."""
+        if self._grad_sync is None or self._grad_sync.world == 1:
+            return acc, n
+        import torch
+        import torch.distributed as dist
+        grp = self._grad_sync.group
+        t = torch.cat([acc.double().to("cuda"), torch.tensor([float(n)], device="cuda", dtype=torch.float64)])
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=grp)
+        for m in metrics:
+            if isinstance(m, MeanIoU):
+                dist.all_reduce(m._dev_counts(), op=dist.ReduceOp.SUM, group=grp)
+        return t[:3], int(round(float(t[3].item())))
+
     def evaluate(self, x, y=None, steps=None, verbose=0, return_dict=False, _metrics=None):
         """Inference-mode loss / metrics over a generator of (x, y) batches (or arrays x, y)."""
         import torch
@@ -682,6 +694,7 @@ class Model:
             for m in metrics:
                 if isinstance(m, MeanIoU):
                     m.update_state(yd, probs)
+        acc, n = self._dp_reduce(acc, n, metrics)      # data parallel: every rank reports the metrics of the WHOLE validation set
         vals = (acc / max(n, 1)).cpu().numpy()
         res = {"loss": float(vals[0])}
         for m in metrics:
@@ -742,7 +755,12 @@ class Model:
             for k, ev in pending:
                 ev.synchronize(); host_sum += ring[k].numpy()
             self.last_h2d_bytes = pf.h2d_bytes
-            vals = host_sum / max(n, 1)
+            if self._grad_sync is not None and self._grad_sync.world > 1:
+                acc, n_all = self._dp_reduce(torch.tensor(host_sum, device="cuda", dtype=torch.float64), n, self.metrics)
+                host_sum, n_red = acc.cpu().numpy(), n_all
+            else:
+                n_red = n
+            vals = host_sum / max(n_red, 1)
             logs: Dict[str, float] = {"loss": float(vals[0])}
             for m in self.metrics:
                 if isinstance(m, MeanIoU):

@@ -272,6 +272,11 @@ int unet_confusion_matrix_update(const float* y_true, const float* y_pred, int64
 /* thresholded variant used by benchmark.py:260: p = (prob > thr) */
 int unet_confusion_matrix_update_thr(const float* y_true, const float* prob, float thr, int64_t n,
                                      unsigned long long* counts /*[4]*/, void* stream);
+/* calculate_sample_iou (benchmark.py:159-170) on thresholded predictions (:260): per-sample 2x2 counts in one launch,
+ * counts[nb*4 + t*2 + p] += 1; I = counts[3], T = counts[2]+counts[3], P = counts[1]+counts[3] per sample, and the sum over
+ * samples is the MeanIoU(2) confusion matrix of the batch (:269) */
+int unet_sample_confusion_thr(const float* y_true, const float* prob, float thr, int64_t NB, int64_t per_sample,
+                              unsigned long long* counts /*[NB][4]*/, void* stream);
 
 /* ---- AdamW, Keras form (train.py:226): w -= lr*wd*w; m,v update; w -= alpha*m/(sqrt(v)+eps) ---- */
 /* hyper (device, fp32[8]): lr, wd, beta1, beta2, eps, step t (as float), grad_scale, unused — read on device so a

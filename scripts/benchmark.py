@@ -31,6 +31,8 @@ _ARGS = [
     (("--pred_threshold",), dict(type=float, default=0.5, help="probability above which a pixel counts as foreground")),
     (("--low_score_log",), dict(type=str, default=None, help="CSV file for the samples below --iou_threshold")),
     (("--batch",), dict(type=int, default=1, help="images per predict call (extension; the reference uses 1)")),
+    (("--host-metrics",), dict(action="store_true", help="threshold and score on the host with NumPy, as the reference does "
+                                                         "(default: integer confusion counts on the GPU; identical numbers)")),
 ]
 
 
@@ -107,15 +109,21 @@ def _evaluate(model, pairs, args):
             images.append(image); truths.append(truth); ids.append(sample_id)
         if not images:
             continue
-        probs = model.predict(np.concatenate(images, 0), batch_size=len(images), verbose=0)
-        masks = (probs > args.pred_threshold).astype(np.uint8)   # reference :260
         truth_batch = np.concatenate(truths, 0)
-        for k, sample_id in enumerate(ids):
-            score = imaging.sample_iou(truth_batch[k], masks[k])
+        if args.host_metrics:      # the reference's order of operations: probabilities to the host, NumPy threshold and sums
+            probs = model.predict(np.concatenate(images, 0), batch_size=len(images), verbose=0)
+            masks = (probs > args.pred_threshold).astype(np.uint8)   # reference :260
+            scores = [imaging.sample_iou(truth_batch[k], masks[k]) for k in range(len(ids))]
+            overall.update_state(truth_batch, masks)
+        else:                      # same numbers from integer counts made on the device: only 32 bytes per sample come back
+            prob_dev = model.predict_on_device(model._stage_in(np.concatenate(images, 0), "bench_x"))
+            counts = imaging.gpu_batch_sample_counts(truth_batch, prob_dev, args.pred_threshold)
+            scores = [imaging.sample_iou_from_counts(counts[k]) for k in range(len(ids))]
+            overall.add_confusion(counts.sum(0))
+        for sample_id, score in zip(ids, scores):
             if score < args.iou_threshold:
                 below.append((sample_id, score))
                 print(f"\n  IoU {score:.3f} < {args.iou_threshold:.2f}: {sample_id}")
-        overall.update_state(truth_batch, masks)
     print()
     return float(overall.result().numpy()), below
 

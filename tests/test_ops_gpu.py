@@ -794,6 +794,30 @@ def test_confusion_matrix():
     np.testing.assert_array_equal(c8.cpu().numpy().reshape(8, 8), m.cm)
 
 
+def test_sample_confusion_thr_matches_calculate_sample_iou():
+    """a13: calculate_sample_iou (scripts/benchmark.py:159-170) of thresholded predictions (:260) from per-sample integer counts
+    made on the device equals the oracle's float32 restatement bit for bit, and the counts sum to MeanIoU(2)'s matrix (:269)."""
+    from unet_b200 import imaging
+    rng = np.random.default_rng(3)
+    B, h, w = 5, 64, 48
+    prob = rng.random((B, h, w, 1)).astype(np.float32)
+    prob[3] = 0.1                                                  # empty prediction
+    truth = (rng.random((B, h, w, 1)) > 0.6).astype(np.uint8)
+    truth[4] = 0                                                   # empty truth
+    counts = imaging.gpu_batch_sample_counts(truth, dev(prob), 0.5)
+    masks = (prob > 0.5).astype(np.uint8)
+    m = R.MeanIoU(2)
+    for k in range(B):
+        assert imaging.sample_iou_from_counts(counts[k]) == R.sample_iou(truth[k], masks[k])
+        assert imaging.sample_iou_from_counts(counts[k]) == imaging.sample_iou(truth[k], masks[k])
+        m.update_state(truth[k], masks[k])
+    np.testing.assert_array_equal(counts.sum(0).reshape(2, 2), m.cm)
+    from unet_b200.keras_api import MeanIoU
+    mm = MeanIoU(2)
+    mm.add_confusion(counts.sum(0))
+    assert float(mm.result()) == pytest.approx(m.result(), abs=1e-12)
+
+
 def test_adamw_keras_form():
     n = 10007
     w = RNG.standard_normal(n).astype(np.float32)

@@ -80,6 +80,7 @@ _SIGNATURES = {
     "unet_seg_sums": [_vp, _vp, _vp, _i64, _i64, _i, _vp],
     "unet_confusion_matrix_update": [_vp, _vp, _i64, _i, _vp, _vp],
     "unet_confusion_matrix_update_thr": [_vp, _vp, _f, _i64, _vp, _vp],
+    "unet_sample_confusion_thr": [_vp, _vp, _f, _i64, _i64, _vp, _vp],
     "unet_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "unet_step_advance": [_vp, _vp, _vp],
     "unet_cast_transpose_bf16": [_vp, _vp, _vp, _i, _i, _vp, _vp],

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <string.h>
+#include <stdlib.h>
 
 namespace unet {
 
@@ -30,6 +31,15 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("UNET_B200_PDL");
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
 }
 
 PFN_encodeTiled get_encode_fn() {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <utility>
 #include "../../include/unet_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -29,6 +30,31 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t i64min(int64_t a, int64_t b) { return a < b ? a : b; }
 __host__ __device__ inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 int sm_count();
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with the programmatic-stream-serialization attribute and begins with pdl_enter():
+// `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be scheduled as soon as every CTA of this one has
+// started (its CTAs fill the SMs that this kernel's tail leaves idle and run their prologue: barrier init, descriptor
+// prefetch, TMEM allocation), and `griddepcontrol.wait` holds this kernel's first global-memory access until the PREVIOUS
+// kernel of the stream has completed and flushed.  Kernel boundaries of the ~195-launch training step (or its CUDA graph:
+// the attribute is captured as a programmatic edge) then cost a CTA hand-over instead of a drain + launch + ramp.
+// UNET_B200_PDL=0 turns the attribute off (the device instructions are then no-ops).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per (kernel instantiation, device)
 struct SmemAttrOnce { bool done[64] = {}; };
 template <typename F>

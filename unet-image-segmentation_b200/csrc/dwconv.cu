@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256)
 dwconv3x3_vec8_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w9c,
                       T* __restrict__ y, int64_t ldy, int N, int H, int W, int C, int R, int nseg, int flip,
                       const float* __restrict__ in_scale, const float* __restrict__ in_shift, DropArgs dp) {
+  pdl_enter();
   const int cv = C >> 3;
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int c8 = (int)(t % cv); t /= cv;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__((StripCfg<T, CW, PXT>::kThreads), (StripCfg<T,
 dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ w9c, T* __restrict__ y, int64_t ldy,
                        int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, int flip, DropArgs dp,
                        float* __restrict__ colsum, const float* __restrict__ in_scale, const float* __restrict__ in_shift) {
+  pdl_launch_dependents();
   using Cfg = StripCfg<T, CW, PXT>;
   constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S, NQ = CW + 2;
   extern __shared__ uint8_t smem_raw[];
@@ -168,6 +170,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();            // above: shared memory and kernel parameters only
 
   // thread 0 doubles as the TMA producer: it keeps S-1 stages in flight ahead of the stage being consumed
   auto issue = [&](int k) {
@@ -355,7 +358,7 @@ static int dw_fwd_strip_launch_cfg(const void* x, int64_t ldx, const float* w9c,
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_fwd: too many strips");
-#define UNET_DWF(D_, S_, A_) dwconv3x3_strip_kernel<T, CW, PXT, D_, S_, A_><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+#define UNET_DWF(D_, S_, A_) launch_pdl(dwconv3x3_strip_kernel<T, CW, PXT, D_, S_, A_>, (unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st, \
       tm, w9c, (T*)y, ldy, H, W, C, seg, nseg, ntw, ncb, flip, dp, colsum, in_scale, in_shift)
   if (dp.on) UNET_DWF(true, false, false);
   else if (in_scale) { if (colsum) UNET_DWF(false, true, true); else UNET_DWF(false, false, true); }
@@ -386,6 +389,7 @@ __global__ void dwconv3x3_scalar_kernel(const T* __restrict__ x, int64_t ldx, co
                                         T* __restrict__ y, int64_t ldy, int N, int H, int W, int C, int flip,
                                         const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                                         DropArgs dp) {
+  pdl_enter();
   const int64_t total = (int64_t)N * H * W * C;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(t % C); int64_t p = t / C;
@@ -429,19 +433,19 @@ static int dw_fwd_launch(const void* x, int64_t ldx, const float* w9c, void* y, 
     const int64_t threads = cols * nseg;
     const unsigned grid = (unsigned)ceil_div(threads, 256);
     if (in_scale)
-      dwconv3x3_vec8_kernel<T, true><<<grid, 256, 0, st>>>((const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, R, nseg, flip,
+      launch_pdl(dwconv3x3_vec8_kernel<T, true>, grid, 256, 0, st, (const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, R, nseg, flip,
                                                           in_scale, in_shift, dp);
     else
-      dwconv3x3_vec8_kernel<T, false><<<grid, 256, 0, st>>>((const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, R, nseg, flip,
+      launch_pdl(dwconv3x3_vec8_kernel<T, false>, grid, 256, 0, st, (const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, R, nseg, flip,
                                                            nullptr, nullptr, dp);
   } else {
     const int64_t total = (int64_t)N * H * W * C;
     const unsigned grid = (unsigned)i64min(ceil_div(total, 256), (int64_t)sm_count() * 32);
     if (in_scale)
-      dwconv3x3_scalar_kernel<T, true><<<grid, 256, 0, st>>>((const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, flip,
+      launch_pdl(dwconv3x3_scalar_kernel<T, true>, grid, 256, 0, st, (const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, flip,
                                                             in_scale, in_shift, dp);
     else
-      dwconv3x3_scalar_kernel<T, false><<<grid, 256, 0, st>>>((const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, flip,
+      launch_pdl(dwconv3x3_scalar_kernel<T, false>, grid, 256, 0, st, (const T*)x, ldx, w9c, (T*)y, ldy, N, H, W, C, flip,
                                                              nullptr, nullptr, dp);
   }
   UNET_LAUNCH_CHECK("dwconv3x3_fwd");
@@ -466,6 +470,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 dwconv3x3_bwd_weight_vec4_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                                  float* __restrict__ dw9c, int N, int H, int W, int C, int R, int nseg) {
+  pdl_enter();
   extern __shared__ float s_acc[];   // [9][C]
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) s_acc[i] = 0.f;
   __syncthreads();
@@ -543,6 +548,7 @@ dwconv3x3_bwd_weight_vec4_kernel(const T* __restrict__ x, int64_t ldx, const T* 
 template <typename T>
 __global__ void dwconv3x3_bwd_weight_scalar_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy,
                                                    int64_t lddy, float* __restrict__ dw9c, int N, int H, int W, int C) {
+  pdl_enter();
   // one block per (tap, channel); small C only
   const int tap = blockIdx.x / C, c = blockIdx.x % C;
   const int a = tap / 3, b = tap % 3;
@@ -588,6 +594,7 @@ template <typename T>
 __global__ void __launch_bounds__(512, 1)
 dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmD,
                              float* __restrict__ dw9c, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb) {
+  pdl_launch_dependents();
   using Cfg = WgCfg<T>;
   constexpr int NV = Cfg::NV, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S;
   extern __shared__ uint8_t smem_raw[];
@@ -612,6 +619,7 @@ dwconv3x3_wgrad_strip_kernel(const __grid_constant__ CUtensorMap tmX, const __gr
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();            // above: shared memory and kernel parameters only
 
   auto issue = [&](int k) {
     const int s = k % S;
@@ -704,7 +712,7 @@ static int dw_wgrad_strip_launch(const void* x, int64_t ldx, const void* dy, int
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd_weight: too many strips");
-  dwconv3x3_wgrad_strip_kernel<T><<<(unsigned)items, 512, Cfg::kSmemBytes, st>>>(tmX, tmD, dw9c, H, W, C, seg, nseg, ntw, ncb);
+  launch_pdl(dwconv3x3_wgrad_strip_kernel<T>, (unsigned)items, 512, Cfg::kSmemBytes, st, tmX, tmD, dw9c, H, W, C, seg, nseg, ntw, ncb);
   UNET_LAUNCH_CHECK("dwconv3x3_bwd_weight(strip)");
   return UNET_OK;
 }
@@ -751,6 +759,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
                            const float* __restrict__ w9c, T* __restrict__ dx, int64_t lddx, float* __restrict__ dw9c,
                            float* __restrict__ bn_sums, int H, int W, int C, int seg_rows, int nseg, int ntw, int ncb, DropArgs dp,
                            int drop_c_from, const float* __restrict__ x_scale, const float* __restrict__ x_shift, UpArgs up) {
+  pdl_launch_dependents();
   using Cfg = BwCfg<T, CW, PXT>;
   constexpr int NV = Cfg::NV, NP = NV / 2, TW = Cfg::TW, RH = Cfg::RH, S = Cfg::S, NQ = CW + 2;
   extern __shared__ uint8_t smem_raw[];
@@ -775,6 +784,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
     fence_barrier_init();
   }
   __syncthreads();
+  pdl_wait();            // above: shared memory and kernel parameters only
 
   auto issue = [&](int k) {
     const int s = k % S;
@@ -1012,17 +1022,15 @@ static int dw_bwd_strip_launch_cfg(const void* x, int64_t ldx, const void* dy, i
   const int nseg = (int)ceil_div(H, seg);
   const int64_t items = (int64_t)N * nseg * ntw * ncb;
   UNET_REQUIRE(items < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "dwconv3x3_bwd: too many strips");
-#define UNET_BW_LAUNCH(D, M, A) dwconv3x3_bwd_strip_kernel<T, CW, PXT, D, M, A><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>( \
+#define UNET_BW_LAUNCH(D, M, A) launch_pdl(dwconv3x3_bwd_strip_kernel<T, CW, PXT, D, M, A>, (unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st, \
       tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up)
   if (up.out) {       // validated by the caller: no ReLU mask, no x affine
     static SmemAttrOnce u0, u1;
     ea = ensure_dynamic_smem(u0, dwconv3x3_bwd_strip_kernel<T, CW, PXT, false, false, false, true>, Cfg::kSmemBytes);
     if (ea == cudaSuccess) ea = ensure_dynamic_smem(u1, dwconv3x3_bwd_strip_kernel<T, CW, PXT, true, false, false, true>, Cfg::kSmemBytes);
     if (ea != cudaSuccess) return set_cuda_error(ea, "dwconv3x3_bwd: cudaFuncSetAttribute");
-    if (dp.on) dwconv3x3_bwd_strip_kernel<T, CW, PXT, true, false, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
-        tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
-    else dwconv3x3_bwd_strip_kernel<T, CW, PXT, false, false, false, true><<<(unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st>>>(
-        tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
+    if (dp.on) launch_pdl(dwconv3x3_bwd_strip_kernel<T, CW, PXT, true, false, false, true>, (unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st, tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
+    else launch_pdl(dwconv3x3_bwd_strip_kernel<T, CW, PXT, false, false, false, true>, (unsigned)items, Cfg::kThreads, Cfg::kSmemBytes, st, tmD, tmX, w9c, (T*)dx, lddx, dw9c, bn_sums, H, W, C, seg, nseg, ntw, ncb, dp, drop_c_from, x_scale, x_shift, up);
   }
   else if (x_scale) { if (relu_mask) UNET_BW_LAUNCH(false, true, true); else UNET_BW_LAUNCH(false, false, true); }
   else if (dp.on) { if (relu_mask) UNET_BW_LAUNCH(true, true, false); else UNET_BW_LAUNCH(true, false, false); }
@@ -1052,6 +1060,7 @@ template <typename T, int CC>
 __global__ void __launch_bounds__(256)
 dwconv3x3_bwd_weight_smallc_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ dy, int64_t lddy,
                                    float* __restrict__ dw9c, int N, int H, int W, int R, int nseg) {
+  pdl_enter();
   __shared__ float s_acc[9 * CC];
   if (threadIdx.x < 9 * CC) s_acc[threadIdx.x] = 0.f;
   __syncthreads();
@@ -1110,7 +1119,7 @@ static void dw_bwd_weight_smallc_launch(const void* x, int64_t ldx, const void* 
   const int nseg = (int)ceil_div(H, R);
   const int64_t items = (int64_t)N * nseg * W;
   const unsigned grid = (unsigned)i64min(ceil_div(items, 256), (int64_t)sm_count() * 8);
-  dwconv3x3_bwd_weight_smallc_kernel<T, CC><<<grid, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, R, nseg);
+  launch_pdl(dwconv3x3_bwd_weight_smallc_kernel<T, CC>, grid, 256, 0, st, (const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, R, nseg);
 }
 
 template <typename T>
@@ -1132,7 +1141,7 @@ static int dw_bwd_weight_launch(const void* x, int64_t ldx, const void* dy, int6
     const size_t smem = (size_t)9 * C * sizeof(float);
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(dwconv3x3_bwd_weight_vec4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dwconv3x3_bwd_weight_vec4_kernel<T><<<(unsigned)grid, 256, smem, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c,
+    launch_pdl(dwconv3x3_bwd_weight_vec4_kernel<T>, (unsigned)grid, 256, smem, st, (const T*)x, ldx, (const T*)dy, lddy, dw9c,
                                                                            N, H, W, C, R, nseg);
   } else if (C <= 4) {
     switch (C) {
@@ -1143,7 +1152,7 @@ static int dw_bwd_weight_launch(const void* x, int64_t ldx, const void* dy, int6
     }
   } else {
     UNET_REQUIRE(C <= 64, UNET_EUNSUPPORTED, "dwconv3x3_bwd_weight: C=%d needs C%%4==0 and 16B-aligned views", C);
-    dwconv3x3_bwd_weight_scalar_kernel<T><<<9 * C, 256, 0, st>>>((const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, C);
+    launch_pdl(dwconv3x3_bwd_weight_scalar_kernel<T>, 9 * C, 256, 0, st, (const T*)x, ldx, (const T*)dy, lddy, dw9c, N, H, W, C);
   }
   UNET_LAUNCH_CHECK("dwconv3x3_bwd_weight");
   return UNET_OK;

@@ -23,6 +23,7 @@ static unsigned grid_for(int64_t threads, int block = 256) { return (unsigned)ce
 // ------------------------------------------------------------------------------------------------ BN fold / finalize
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                                float* scale, float* shift, int C) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
@@ -35,6 +36,7 @@ __global__ void bn_finalize_kernel(const double* colsum, const double* colsq, do
                                    const float* gamma, const float* beta, float eps, float momentum,
                                    float* moving_mean, float* moving_var, float* scale, float* shift,
                                    float* save_mean, float* save_rstd, int C) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = colsum[c] * inv_count;
@@ -64,6 +66,7 @@ bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gam
                    const float* __restrict__ mean, const float* __restrict__ rstd, float inv_count,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
                    const float* __restrict__ w, int Cin, int C, __nv_bfloat16* __restrict__ wab, float* __restrict__ bias) {
+  pdl_enter();
   __shared__ float s_red[8];
   const int i = blockIdx.x;
   float part = 0.f;
@@ -102,6 +105,7 @@ bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gam
 // dW[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c]     (G = d^T [g | z], sd = column sums of d)
 __global__ void bn_bwd_wgrad_combine_kernel(const float* __restrict__ G, const float* __restrict__ coef, const float* __restrict__ sd,
                                             float* __restrict__ dw, int Cin, int C) {
+  pdl_enter();
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (idx >= (int64_t)Cin * C) return;
   const int i = (int)(idx / C), c = (int)(idx % C);
@@ -115,6 +119,7 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(256)
 bn_act_kernel(const T* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
               T* __restrict__ y, int64_t ldy, T* __restrict__ pooled, int N, int H, int W, int C, DropArgs dp) {
+  pdl_enter();
   const int cv = C >> 3;
   const int slots = blockDim.x / cv;
   const int c0 = (threadIdx.x % cv) << 3;
@@ -199,6 +204,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t M, int C, int relu, DropArgs dp) {
+  pdl_enter();
   extern __shared__ float s_red[];   // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
@@ -259,6 +265,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict_
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, T* __restrict__ dz,
                     int64_t M, int C, int relu, float inv_m, DropArgs dp) {
+  pdl_enter();
   const int cv = C >> 3;
   const int rows_per_block = blockDim.x / cv;
   const int c0 = (threadIdx.x % cv) << 3;
@@ -315,6 +322,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict_
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ y, int N, int H, int W, int C) {
+  pdl_enter();
   const int cv = C >> 3, W2 = W >> 1, H2 = H >> 1;
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int c0 = (int)(t % cv) << 3; t /= cv;
@@ -338,6 +346,7 @@ __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const T* __restrict__ z, int64_t ldz, const float* __restrict__ scale, const float* __restrict__ shift,
                    const T* __restrict__ dpool, const T* __restrict__ dskip, int64_t lddskip, T* __restrict__ dy,
                    int N, int H, int W, int C, float* __restrict__ bn_sums, DropArgs drp) {
+  pdl_enter();
   extern __shared__ float s_bn[];      // [2][C] when bn_sums
   const uint32_t seed = DROP ? drop_seed(drp) : 0u;
   if (SUMS) {
@@ -407,6 +416,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ g, float* __restrict__ dbias,
                         int N, int H, int W, int Cout, DropArgs dp) {
+  pdl_enter();
   extern __shared__ float s_red[];   // [Cout]
   const uint32_t seed = dp.on ? drop_seed(dp) : 0u;
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_red[i] = 0.f;
@@ -445,6 +455,7 @@ convt_bwd_gather_kernel(const T* __restrict__ du, int64_t lddu, T* __restrict__ 
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              int64_t n, const float* __restrict__ hyper) {
+  pdl_enter();
   const float lr = hyper[0], wd = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4], t = hyper[5], gs = hyper[6];
   // alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
   const float alpha = lr * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
@@ -481,6 +492,7 @@ adamw_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restri
 }
 
 __global__ void step_advance_kernel(float* hyper, uint32_t* counter) {
+  pdl_enter();
   if (hyper) hyper[5] += 1.f;
   if (counter) *counter += 1u;
 }
@@ -488,6 +500,7 @@ __global__ void step_advance_kernel(float* hyper, uint32_t* counter) {
 // ------------------------------------------------------------------------------------------------ casts
 __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                            __nv_bfloat16* __restrict__ dst_t, int R, int C, const float* __restrict__ col_scale) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -511,6 +524,7 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
 
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
+  pdl_enter();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     d[i] = from_f32<D>(to_f32(s[i]));
 }
@@ -518,6 +532,7 @@ __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t 
 // ------------------------------------------------------------------------------------------------ MeanIoU confusion counts
 __global__ void confusion_kernel(const float* __restrict__ yt, const float* __restrict__ yp, int64_t n, int C,
                                  unsigned long long* __restrict__ counts, int use_thr, float thr) {
+  pdl_enter();
   extern __shared__ unsigned int s_cnt[];   // [C*C]
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) s_cnt[i] = 0u;
   __syncthreads();
@@ -531,10 +546,38 @@ __global__ void confusion_kernel(const float* __restrict__ yt, const float* __re
     if (s_cnt[i]) atomicAdd(&counts[i], (unsigned long long)s_cnt[i]);
 }
 
+// per-sample 2x2 confusion counts of thresholded probabilities (scripts/benchmark.py:159-170,260): counts[nb][t*2+p]
+__global__ void sample_confusion_thr_kernel(const float* __restrict__ yt, const float* __restrict__ yp, int64_t per_sample,
+                                            unsigned long long* __restrict__ counts, float thr) {
+  pdl_enter();
+  __shared__ unsigned int s_cnt[4];
+  if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t nb = blockIdx.y;
+  const float* t = yt + nb * per_sample;
+  const float* p = yp + nb * per_sample;
+  unsigned c[4] = {0u, 0u, 0u, 0u};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < per_sample; i += (int64_t)gridDim.x * blockDim.x) {
+    const int tv = (int)t[i];
+    const int pv = p[i] > thr ? 1 : 0;
+    if (tv >= 0 && tv < 2) c[tv * 2 + pv] += 1u;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned v = c[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(&counts[nb * 4 + threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+}
+
 // ------------------------------------------------------------------------------------------------ (I,T,P) sums
 // sums[nb][c][0..2] += (sum t*p, sum t, sum p) over hw pixels.  blockDim is a multiple of C so that a thread's class is fixed.
 __global__ void seg_sums_kernel(const float* __restrict__ yt, const float* __restrict__ yp, double* __restrict__ sums,
                                 int64_t hw, int C) {
+  pdl_enter();
   extern __shared__ double s_sum[];   // [C][3]
   for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) s_sum[i] = 0.0;
   __syncthreads();
@@ -558,6 +601,7 @@ __global__ void seg_sums_kernel(const float* __restrict__ yt, const float* __res
 // loss finalize: one block
 __global__ void seg_loss_finalize_kernel(const double* __restrict__ sums, int npairs, float smooth, int kind,
                                          float grad_scale, float* __restrict__ out3, float* __restrict__ coef) {
+  pdl_enter();
   __shared__ double s_d[32], s_i[32];
   double dsum = 0.0, isum = 0.0;
   const double s = (double)smooth, inv = 1.0 / (double)npairs;
@@ -596,7 +640,7 @@ using namespace unet;
 extern "C" int unet_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                             float* scale, float* shift, int C, void* stream) {
   UNET_REQUIRE(mean && var && scale && shift && C > 0, UNET_EINVAL, "bn_fold: bad argument");
-  bn_fold_kernel<<<grid_for(C, 128), 128, 0, ST>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  launch_pdl(bn_fold_kernel, grid_for(C, 128), 128, 0, ST, gamma, beta, mean, var, eps, scale, shift, C);
   UNET_LAUNCH_CHECK("bn_fold");
   return UNET_OK;
 }
@@ -606,7 +650,7 @@ extern "C" int unet_bn_finalize(const double* colsum, const double* colsq, int64
                                 float* moving_mean, float* moving_var,
                                 float* scale, float* shift, float* save_mean, float* save_rstd, int C, void* stream) {
   UNET_REQUIRE(colsum && colsq && scale && shift && C > 0 && count > 0, UNET_EINVAL, "bn_finalize: bad argument");
-  bn_finalize_kernel<<<grid_for(C, 128), 128, 0, ST>>>(colsum, colsq, 1.0 / (double)count, gamma, beta, eps, momentum,
+  launch_pdl(bn_finalize_kernel, grid_for(C, 128), 128, 0, ST, colsum, colsq, 1.0 / (double)count, gamma, beta, eps, momentum,
                                                       moving_mean, moving_var, scale, shift, save_mean, save_rstd, C);
   UNET_LAUNCH_CHECK("bn_finalize");
   return UNET_OK;
@@ -619,11 +663,11 @@ static int bn_act_launch(const void* z, const float* scale, const float* shift, 
   if (pooled) {
     const int64_t items = (int64_t)N * (H / 2) * (W / 2);
     const unsigned grid = (unsigned)i64min(ceil_div(items, slots), (int64_t)sm_count() * 16);
-    bn_act_kernel<T, true><<<grid, 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, (T*)pooled, N, H, W, C, dp);
+    launch_pdl(bn_act_kernel<T, true>, grid, 256, 0, st, (const T*)z, scale, shift, relu, (T*)y, ldy, (T*)pooled, N, H, W, C, dp);
   } else {
     const int64_t items = (int64_t)N * H * W;
     const unsigned grid = (unsigned)i64min(ceil_div(items, (int64_t)slots * 4), (int64_t)sm_count() * 16);
-    bn_act_kernel<T, false><<<grid, 256, 0, st>>>((const T*)z, scale, shift, relu, (T*)y, ldy, nullptr, N, H, W, C, dp);
+    launch_pdl(bn_act_kernel<T, false>, grid, 256, 0, st, (const T*)z, scale, shift, relu, (T*)y, ldy, nullptr, N, H, W, C, dp);
   }
   UNET_LAUNCH_CHECK("bn_act");
   return UNET_OK;
@@ -662,10 +706,10 @@ extern "C" int unet_bn_bwd_reduce(const void* dy, int64_t lddy, const void* z,
   const unsigned grid = (unsigned)i64min(ceil_div(M, (int64_t)rows_per_block * kBnUnroll), (int64_t)sm_count() * 8);
   const size_t smem = (size_t)2 * C * sizeof(float);
   if (dtype == UNET_F32)
-    bn_bwd_reduce_kernel<float><<<grid, 256, smem, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift, save_mean,
+    launch_pdl(bn_bwd_reduce_kernel<float>, grid, 256, smem, ST, (const float*)dy, lddy, (const float*)z, scale, shift, save_mean,
                                                         save_rstd, dgamma, dbeta, M, C, relu, dp);
   else if (dtype == UNET_BF16)
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+    launch_pdl(bn_bwd_reduce_kernel<__nv_bfloat16>, grid, 256, smem, ST, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
                                                                 scale, shift, save_mean, save_rstd, dgamma, dbeta, M, C, relu, dp);
   else return set_error(UNET_EINVAL, "bn_bwd_reduce: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("bn_bwd_reduce");
@@ -684,10 +728,10 @@ extern "C" int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
   const int rows_per_block = 256 / (C / 8);
   const unsigned grid = (unsigned)i64min(ceil_div(M, (int64_t)rows_per_block * kBnUnroll), (int64_t)sm_count() * 16);
   if (dtype == UNET_F32)
-    bn_bwd_apply_kernel<float><<<grid, 256, 0, ST>>>((const float*)dy, lddy, (const float*)z, scale, shift,
+    launch_pdl(bn_bwd_apply_kernel<float>, grid, 256, 0, ST, (const float*)dy, lddy, (const float*)z, scale, shift,
                                                     save_mean, save_rstd, dgamma, dbeta, (float*)dz, M, C, relu, inv_m, dp);
   else if (dtype == UNET_BF16)
-    bn_bwd_apply_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
+    launch_pdl(bn_bwd_apply_kernel<__nv_bfloat16>, grid, 256, 0, ST, (const __nv_bfloat16*)dy, lddy, (const __nv_bfloat16*)z,
                                                             scale, shift, save_mean, save_rstd, dgamma, dbeta,
                                                             (__nv_bfloat16*)dz, M, C, relu, inv_m, dp);
   else return set_error(UNET_EINVAL, "bn_bwd_apply: bad dtype %d", dtype);
@@ -700,9 +744,9 @@ extern "C" int unet_maxpool2x2_fwd(const void* x, int64_t ldx, void* y, int N, i
   UNET_REQUIRE(C % 8 == 0 && ldx % 8 == 0 && aligned16(x) && aligned16(y), UNET_EALIGN, "maxpool2x2_fwd: needs C%%8==0, ld%%8==0");
   const int64_t threads = (int64_t)N * (H / 2) * (W / 2) * (C / 8);
   if (dtype == UNET_F32)
-    maxpool_fwd_kernel<float><<<grid_for(threads), 256, 0, ST>>>((const float*)x, ldx, (float*)y, N, H, W, C);
+    launch_pdl(maxpool_fwd_kernel<float>, grid_for(threads), 256, 0, ST, (const float*)x, ldx, (float*)y, N, H, W, C);
   else if (dtype == UNET_BF16)
-    maxpool_fwd_kernel<__nv_bfloat16><<<grid_for(threads), 256, 0, ST>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, N, H, W, C);
+    launch_pdl(maxpool_fwd_kernel<__nv_bfloat16>, grid_for(threads), 256, 0, ST, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, N, H, W, C);
   else return set_error(UNET_EINVAL, "maxpool2x2_fwd: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("maxpool2x2_fwd");
   return UNET_OK;
@@ -721,7 +765,7 @@ extern "C" int unet_maxpool2x2_bwd(const void* z, int64_t ldz, const float* scal
   const unsigned grid = (unsigned)i64min(ceil_div(items, 256 / (C / 8)), (int64_t)sm_count() * 16);
   UNET_REQUIRE(!bn_sums || scale, UNET_EINVAL, "maxpool2x2_bwd: bn_sums needs the activation recomputed from z (scale/shift)");
   const size_t smem = bn_sums ? (size_t)2 * C * sizeof(float) : 0;
-#define UNET_MPB(T, S_, D_) maxpool_bwd_kernel<T, S_, D_><<<grid, 256, smem, ST>>>((const T*)z, ldz, scale, shift, (const T*)dpool, \
+#define UNET_MPB(T, S_, D_) launch_pdl(maxpool_bwd_kernel<T, S_, D_>, grid, 256, smem, ST, (const T*)z, ldz, scale, shift, (const T*)dpool, \
                                                                           (const T*)dskip, lddskip, (T*)dy, N, H, W, C, bn_sums, dp)
 #define UNET_MPB4(T) do { if (bn_sums) { if (dp.on) UNET_MPB(T, true, true); else UNET_MPB(T, true, false); } \
                           else { if (dp.on) UNET_MPB(T, false, true); else UNET_MPB(T, false, false); } } while (0)
@@ -743,9 +787,9 @@ extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, floa
   const unsigned grid = (unsigned)i64min((int64_t)N * H * 2, (int64_t)sm_count() * 8);
   const size_t smem = (size_t)Cout * sizeof(float);
   if (dtype == UNET_F32)
-    convt_bwd_gather_kernel<float><<<grid, 256, smem, ST>>>((const float*)du, lddu, (float*)g, dbias, N, H, W, Cout, dp);
+    launch_pdl(convt_bwd_gather_kernel<float>, grid, 256, smem, ST, (const float*)du, lddu, (float*)g, dbias, N, H, W, Cout, dp);
   else if (dtype == UNET_BF16)
-    convt_bwd_gather_kernel<__nv_bfloat16><<<grid, 256, smem, ST>>>((const __nv_bfloat16*)du, lddu, (__nv_bfloat16*)g, dbias, N, H, W, Cout, dp);
+    launch_pdl(convt_bwd_gather_kernel<__nv_bfloat16>, grid, 256, smem, ST, (const __nv_bfloat16*)du, lddu, (__nv_bfloat16*)g, dbias, N, H, W, Cout, dp);
   else return set_error(UNET_EINVAL, "convt_bwd_gather: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("convt_bwd_gather");
   return UNET_OK;
@@ -754,13 +798,13 @@ extern "C" int unet_convt_bwd_gather(const void* du, int64_t lddu, void* g, floa
 extern "C" int unet_adamw_step(float* w, const float* g, float* m, float* v, int64_t n, const float* hyper, void* stream) {
   UNET_REQUIRE(w && g && m && v && hyper && n > 0, UNET_EINVAL, "adamw_step: bad argument");
   UNET_REQUIRE(aligned16(w) && aligned16(g) && aligned16(m) && aligned16(v), UNET_EALIGN, "adamw_step: buffers must be 16B aligned");
-  adamw_kernel<<<grid_for(ceil_div(n, 4)), 256, 0, ST>>>(w, g, m, v, n, hyper);
+  launch_pdl(adamw_kernel, grid_for(ceil_div(n, 4)), 256, 0, ST, w, g, m, v, n, hyper);
   UNET_LAUNCH_CHECK("adamw_step");
   return UNET_OK;
 }
 
 extern "C" int unet_step_advance(float* hyper, uint32_t* counter, void* stream) {
-  step_advance_kernel<<<1, 1, 0, ST>>>(hyper, counter);
+  launch_pdl(step_advance_kernel, 1, 1, 0, ST, hyper, counter);
   UNET_LAUNCH_CHECK("step_advance");
   return UNET_OK;
 }
@@ -768,7 +812,7 @@ extern "C" int unet_step_advance(float* hyper, uint32_t* counter, void* stream) 
 extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, const float* col_scale, void* stream) {
   UNET_REQUIRE(src && (dst || dst_t) && R > 0 && C > 0, UNET_EINVAL, "cast_transpose_bf16: bad argument");
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(R, 32));
-  cast_transpose_bf16_kernel<<<grid, dim3(32, 8), 0, ST>>>(src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C, col_scale);
+  launch_pdl(cast_transpose_bf16_kernel, grid, dim3(32, 8), 0, ST, src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C, col_scale);
   UNET_LAUNCH_CHECK("cast_transpose_bf16");
   return UNET_OK;
 }
@@ -777,13 +821,13 @@ extern "C" int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtyp
   UNET_REQUIRE(src && dst && n > 0, UNET_EINVAL, "cast: bad argument");
   const unsigned grid = (unsigned)i64min(ceil_div(n, 256), (int64_t)sm_count() * 16);
   if (src_dtype == UNET_F32 && dst_dtype == UNET_BF16)
-    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, ST>>>((const float*)src, (__nv_bfloat16*)dst, n);
+    launch_pdl(cast_kernel<float, __nv_bfloat16>, grid, 256, 0, ST, (const float*)src, (__nv_bfloat16*)dst, n);
   else if (src_dtype == UNET_BF16 && dst_dtype == UNET_F32)
-    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)src, (float*)dst, n);
+    launch_pdl(cast_kernel<__nv_bfloat16, float>, grid, 256, 0, ST, (const __nv_bfloat16*)src, (float*)dst, n);
   else if (src_dtype == UNET_F32 && dst_dtype == UNET_F32)
-    cast_kernel<float, float><<<grid, 256, 0, ST>>>((const float*)src, (float*)dst, n);
+    launch_pdl(cast_kernel<float, float>, grid, 256, 0, ST, (const float*)src, (float*)dst, n);
   else if (src_dtype == UNET_BF16 && dst_dtype == UNET_BF16)
-    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, ST>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+    launch_pdl(cast_kernel<__nv_bfloat16, __nv_bfloat16>, grid, 256, 0, ST, (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
   else return set_error(UNET_EINVAL, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
   UNET_LAUNCH_CHECK("cast");
   return UNET_OK;
@@ -794,7 +838,7 @@ extern "C" int unet_confusion_matrix_update(const float* y_true, const float* y_
   UNET_REQUIRE(y_true && y_pred && counts && n > 0, UNET_EINVAL, "confusion_matrix_update: bad argument");
   UNET_REQUIRE(num_classes >= 1 && num_classes <= 64, UNET_EUNSUPPORTED, "confusion_matrix_update: 1 <= num_classes <= 64");
   const unsigned grid = (unsigned)i64min(ceil_div(n, 256 * 8), (int64_t)sm_count() * 8);
-  confusion_kernel<<<grid, 256, (size_t)num_classes * num_classes * sizeof(unsigned), ST>>>(y_true, y_pred, n, num_classes, counts, 0, 0.f);
+  launch_pdl(confusion_kernel, grid, 256, (size_t)num_classes * num_classes * sizeof(unsigned), ST, y_true, y_pred, n, num_classes, counts, 0, 0.f);
   UNET_LAUNCH_CHECK("confusion_matrix_update");
   return UNET_OK;
 }
@@ -803,8 +847,18 @@ extern "C" int unet_confusion_matrix_update_thr(const float* y_true, const float
                                                 unsigned long long* counts, void* stream) {
   UNET_REQUIRE(y_true && prob && counts && n > 0, UNET_EINVAL, "confusion_matrix_update_thr: bad argument");
   const unsigned grid = (unsigned)i64min(ceil_div(n, 256 * 8), (int64_t)sm_count() * 8);
-  confusion_kernel<<<grid, 256, 4 * sizeof(unsigned), ST>>>(y_true, prob, n, 2, counts, 1, thr);
+  launch_pdl(confusion_kernel, grid, 256, 4 * sizeof(unsigned), ST, y_true, prob, n, 2, counts, 1, thr);
   UNET_LAUNCH_CHECK("confusion_matrix_update_thr");
+  return UNET_OK;
+}
+
+extern "C" int unet_sample_confusion_thr(const float* y_true, const float* prob, float thr, int64_t NB, int64_t per_sample,
+                                         unsigned long long* counts, void* stream) {
+  UNET_REQUIRE(y_true && prob && counts && NB > 0 && per_sample > 0, UNET_EINVAL, "sample_confusion_thr: bad argument");
+  UNET_REQUIRE(NB <= 65535, UNET_EUNSUPPORTED, "sample_confusion_thr: NB <= 65535");
+  const unsigned gx = (unsigned)i64max(1, i64min(ceil_div(per_sample, 256 * 8), ceil_div((int64_t)sm_count() * 8, NB)));
+  launch_pdl(sample_confusion_thr_kernel, dim3(gx, (unsigned)NB), 256, 0, ST, y_true, prob, per_sample, counts, thr);
+  UNET_LAUNCH_CHECK("sample_confusion_thr");
   return UNET_OK;
 }
 
@@ -813,7 +867,7 @@ extern "C" int unet_seg_sums(const float* y_true, const float* y_pred, double* s
   UNET_REQUIRE(C <= 256 && NB <= 65535, UNET_EUNSUPPORTED, "seg_sums: C <= 256, NB <= 65535");
   const int block = (256 / C) * C;
   const unsigned gx = (unsigned)i64max(1, i64min(ceil_div(hw * C, (int64_t)block * 16), ceil_div((int64_t)sm_count() * 8, NB)));
-  seg_sums_kernel<<<dim3(gx, (unsigned)NB), block, (size_t)3 * C * sizeof(double), ST>>>(y_true, y_pred, sums, hw, C);
+  launch_pdl(seg_sums_kernel, dim3(gx, (unsigned)NB), block, (size_t)3 * C * sizeof(double), ST, y_true, y_pred, sums, hw, C);
   UNET_LAUNCH_CHECK("seg_sums");
   return UNET_OK;
 }
@@ -821,7 +875,7 @@ extern "C" int unet_seg_sums(const float* y_true, const float* y_pred, double* s
 extern "C" int unet_seg_loss_finalize(const double* sums, int NC_pairs, float smooth, int kind, float grad_scale,
                                       float* out3, float* coef, void* stream) {
   UNET_REQUIRE(sums && out3 && NC_pairs > 0 && (kind == 0 || kind == 1), UNET_EINVAL, "seg_loss_finalize: bad argument");
-  seg_loss_finalize_kernel<<<1, 256, 0, ST>>>(sums, NC_pairs, smooth, kind, grad_scale, out3, coef);
+  launch_pdl(seg_loss_finalize_kernel, 1, 256, 0, ST, sums, NC_pairs, smooth, kind, grad_scale, out3, coef);
   UNET_LAUNCH_CHECK("seg_loss_finalize");
   return UNET_OK;
 }
@@ -831,7 +885,7 @@ extern "C" int unet_bn_bwd_coef(const float* sums, const float* gamma, const flo
                                 const float* w, int Cin, int C, void* wab, float* bias, void* stream) {
   UNET_REQUIRE(sums && gamma && beta && save_mean && save_rstd && C > 0 && count > 0, UNET_EINVAL, "bn_bwd_coef: bad argument");
   UNET_REQUIRE(!w || (wab && bias && Cin > 0), UNET_EINVAL, "bn_bwd_coef: w needs wab, bias and Cin");
-  bn_bwd_coef_kernel<<<w ? Cin : 1, 256, 0, ST>>>(sums, gamma, beta, save_mean, save_rstd, 1.f / (float)count, dgamma, dbeta, coef,
+  launch_pdl(bn_bwd_coef_kernel, w ? Cin : 1, 256, 0, ST, sums, gamma, beta, save_mean, save_rstd, 1.f / (float)count, dgamma, dbeta, coef,
                                                  w, Cin, C, (__nv_bfloat16*)wab, bias);
   UNET_LAUNCH_CHECK("bn_bwd_coef");
   return UNET_OK;
@@ -839,7 +893,7 @@ extern "C" int unet_bn_bwd_coef(const float* sums, const float* gamma, const flo
 
 extern "C" int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd, float* dw, int Cin, int C, void* stream) {
   UNET_REQUIRE(G && coef && sd && dw && Cin > 0 && C > 0, UNET_EINVAL, "bn_bwd_wgrad_combine: bad argument");
-  bn_bwd_wgrad_combine_kernel<<<grid_for((int64_t)Cin * C), 256, 0, ST>>>(G, coef, sd, dw, Cin, C);
+  launch_pdl(bn_bwd_wgrad_combine_kernel, grid_for((int64_t)Cin * C), 256, 0, ST, G, coef, sd, dw, Cin, C);
   UNET_LAUNCH_CHECK("bn_bwd_wgrad_combine");
   return UNET_OK;
 }

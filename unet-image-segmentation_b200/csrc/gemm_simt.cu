@@ -26,6 +26,7 @@ struct SimtParams {
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const SimtParams p) {
+  pdl_enter();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   __shared__ float s_cs[BN], s_cq[BN];
@@ -189,10 +190,10 @@ extern "C" int unet_gemm_simt(const unet_gemm_args* a, void* stream) {
   UNET_REQUIRE(ceil_div(a->N, BN) <= 65535, UNET_EUNSUPPORTED, "gemm_simt: N too large for grid.y");
   dim3 grid((unsigned)ceil_div(a->M, BM), (unsigned)ceil_div(a->N, BN), (unsigned)splits);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->in_dtype == UNET_F32 && a->out_dtype == UNET_F32)        gemm_simt_kernel<float, float><<<grid, 256, 0, st>>>(p);
-  else if (a->in_dtype == UNET_BF16 && a->out_dtype == UNET_BF16) gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else if (a->in_dtype == UNET_BF16 && a->out_dtype == UNET_F32)  gemm_simt_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>(p);
-  else                                                            gemm_simt_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>(p);
+  if (a->in_dtype == UNET_F32 && a->out_dtype == UNET_F32)        launch_pdl(gemm_simt_kernel<float, float>, grid, 256, 0, st, p);
+  else if (a->in_dtype == UNET_BF16 && a->out_dtype == UNET_BF16) launch_pdl(gemm_simt_kernel<__nv_bfloat16, __nv_bfloat16>, grid, 256, 0, st, p);
+  else if (a->in_dtype == UNET_BF16 && a->out_dtype == UNET_F32)  launch_pdl(gemm_simt_kernel<__nv_bfloat16, float>, grid, 256, 0, st, p);
+  else                                                            launch_pdl(gemm_simt_kernel<float, __nv_bfloat16>, grid, 256, 0, st, p);
   UNET_LAUNCH_CHECK("gemm_simt");
   return UNET_OK;
 }

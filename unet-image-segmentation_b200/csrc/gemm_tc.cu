@@ -219,6 +219,7 @@ template <int BLOCK_N, bool OUT_BF16>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  pdl_launch_dependents();
   using Cfg = NtCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CW = OUT_BF16 ? 64 : 32;          // output columns per 128-byte staging row
@@ -251,6 +252,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
@@ -525,6 +527,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
+  pdl_launch_dependents();
   using Cfg = TcCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kChunks = BLOCK_N / 64;
@@ -558,6 +561,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = *tmem_ptr;
 
   if (num_k > 0) {
@@ -647,6 +651,7 @@ __global__ void __launch_bounds__(256, 1)
 pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmZ,
                     const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmO, const PbParams p) {
+  pdl_launch_dependents();
   using Cfg = PbCfg<CIN>;
   constexpr int S = Cfg::kStages, kChunk = Cfg::kChunk, DC = Cfg::kDChunks;
   extern __shared__ uint8_t smem_raw[];
@@ -678,6 +683,7 @@ pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();            // everything above touched only shared memory / TMEM / kernel parameters
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t d1_tmem = tmem_base;                    // G^T accumulator [128 x CIN]
   const uint32_t d2_tmem = tmem_base + CIN;              // dd accumulators [2][128 x CIN]
@@ -872,7 +878,7 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   const unsigned grid = (unsigned)i64min(tiles, sm_count());
-  gemm_tc_nt_kernel<BLOCK_N, OUT_BF16><<<grid, 384, Cfg::kSmemBytes, st>>>(tmA, tmA2, tmB, tmC, p);
+  launch_pdl(gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, grid, 384, Cfg::kSmemBytes, st, tmA, tmA2, tmB, tmC, p);
   UNET_LAUNCH_CHECK("gemm_tc_nt");
   return UNET_OK;
 }
@@ -893,7 +899,7 @@ static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   p.kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, p.kb_per_split);
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  gemm_tc_wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, st>>>(tmA, tmB, tmB2, p);
+  launch_pdl(gemm_tc_wgrad_kernel<BLOCK_N>, grid, 256, Cfg::kSmemBytes, st, tmA, tmB, tmB2, p);
   UNET_LAUNCH_CHECK("gemm_tc_wgrad");
   return UNET_OK;
 }
@@ -908,7 +914,7 @@ static int launch_pw_bwd_fused(const CUtensorMap& tmG, const CUtensorMap& tmZ, c
   if (cudaError_t e = ensure_dynamic_smem(once, pw_bwd_fused_kernel<CIN>, Cfg::kSmemBytes))
     return set_cuda_error(e, "pw_bwd_fused: cudaFuncSetAttribute");
   const unsigned grid = (unsigned)i64min(p.num_blocks, sm_count());
-  pw_bwd_fused_kernel<CIN><<<grid, 256, Cfg::kSmemBytes, st>>>(tmG, tmZ, tmD, tmW, tmO, p);
+  launch_pdl(pw_bwd_fused_kernel<CIN>, grid, 256, Cfg::kSmemBytes, st, tmG, tmZ, tmD, tmW, tmO, p);
   UNET_LAUNCH_CHECK("pw_bwd_fused");
   return UNET_OK;
 }

@@ -18,6 +18,7 @@ __global__ void __launch_bounds__(256, MAXC == 1 ? 4 : 1)
 head_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                 float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
                 int64_t hw, int K, int C, int pix_per_block) {
+  pdl_enter();
   __shared__ float s_w[kHeadMaxK * MAXC];
   __shared__ float s_b[MAXC];
   __shared__ double s_sum[MAXC * 3];
@@ -124,6 +125,7 @@ head_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ 
                 const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
                 float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block,
                 float* __restrict__ bn_sums) {
+  pdl_enter();
   __shared__ float s_w[kHeadMaxK * MAXC];
   __shared__ float s_dw[kHeadMaxK * MAXC];
   __shared__ float s_db[MAXC];
@@ -262,6 +264,7 @@ __global__ void __launch_bounds__(256, 4)
 head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                         float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
                         int64_t hw, int pix_per_block, const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
+  pdl_enter();
   __shared__ uint4 ring_x[kH1FD][256];
   __shared__ float ring_t[kH1FD][256];
   __shared__ double s_sum[3];
@@ -335,6 +338,7 @@ head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
                         const float* __restrict__ y_true, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dx,
                         float* __restrict__ dw, float* __restrict__ db, int64_t hw, int pix_per_block, float* __restrict__ bn_sums,
                         const float* __restrict__ x_scale, const float* __restrict__ x_shift) {
+  pdl_enter();
   __shared__ uint4 ring_x[kH1D][256];
   __shared__ float ring_p[kH1D][256], ring_t[kH1D][256];
   __shared__ float s_red[3 * 64 + 1];              // dw | sum g | (unused) | db
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(256, 2)
 head_fwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
                    float* __restrict__ probs, const float* __restrict__ y_true, double* __restrict__ sums,
                    int64_t hw, int K, int C, int pix_per_block) {
+  pdl_enter();
   __shared__ __align__(16) float s_w[kMcWeightFloats];
   __shared__ double s_sum[8 * 3];
   for (int i = threadIdx.x; i < K * 8; i += blockDim.x) s_w[mc_row(i >> 3) + (i & 7)] = (i & 7) < C ? w[(i >> 3) * C + (i & 7)] : 0.f;
@@ -523,6 +528,7 @@ head_bwd_mc_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict
                    const float* __restrict__ y_true, const float* __restrict__ coef, T* __restrict__ dx, int64_t lddx,
                    float* __restrict__ dw, float* __restrict__ db, int64_t hw, int K, int C, int pix_per_block,
                    float* __restrict__ bn_sums) {
+  pdl_enter();
   __shared__ __align__(16) float s_w[kMcWeightFloats];
   __shared__ float s_dw[kHeadMaxK * 8];
   __shared__ float s_db[8];
@@ -657,12 +663,12 @@ extern "C" int unet_head_fwd(const void* x, int64_t ldx, const float* w, const f
   head_grid(M / hw, hw, &grid, &ppb);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64) {     // the reference head: streamed kernel
-    head1_fwd_stream_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, b, probs, y_true, sums, hw, ppb, x_scale, x_shift);
+    launch_pdl(head1_fwd_stream_kernel, grid, 256, 0, st, (const __nv_bfloat16*)x, w, b, probs, y_true, sums, hw, ppb, x_scale, x_shift);
     UNET_LAUNCH_CHECK("head_fwd(stream)");
     return UNET_OK;
   }
-#define LAUNCH(T, MC) head_fwd_kernel<T, MC><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
-#define LAUNCH_MC(T) head_fwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
+#define LAUNCH(T, MC) launch_pdl(head_fwd_kernel<T, MC>, grid, 256, 0, st, (const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
+#define LAUNCH_MC(T) launch_pdl(head_fwd_mc_kernel<T>, grid, 256, 0, st, (const T*)x, ldx, w, b, probs, y_true, sums, hw, K, C, ppb)
   if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }
   else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH_MC(__nv_bfloat16); }
 #undef LAUNCH_MC
@@ -691,14 +697,14 @@ extern "C" int unet_head_bwd(const void* x, int64_t ldx, const float* w, const f
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_BF16 && C == 1 && K == 64 && ldx == 64 && dx && lddx == 64) {     // the reference head: streamed kernel
     head_grid(M / hw, hw, &grid, &ppb, 16);
-    if (bn_sums) head1_bwd_stream_kernel<true><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
-    else head1_bwd_stream_kernel<false><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
+    if (bn_sums) launch_pdl(head1_bwd_stream_kernel<true>, grid, 256, 0, st, (const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
+    else launch_pdl(head1_bwd_stream_kernel<false>, grid, 256, 0, st, (const __nv_bfloat16*)x, w, probs, y_true, coef, (__nv_bfloat16*)dx, dw, db, hw, ppb, bn_sums, x_scale, x_shift);
     UNET_LAUNCH_CHECK("head_bwd(stream)");
     return UNET_OK;
   }
-#define LAUNCH(T, MC) do { if (bn_sums) head_bwd_kernel<T, MC, true><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); \
-                           else head_bwd_kernel<T, MC, false><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); } while (0)
-#define LAUNCH_MC(T) head_bwd_mc_kernel<T><<<grid, 256, 0, st>>>((const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums)
+#define LAUNCH(T, MC) do { if (bn_sums) launch_pdl(head_bwd_kernel<T, MC, true>, grid, 256, 0, st, (const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); \
+                           else launch_pdl(head_bwd_kernel<T, MC, false>, grid, 256, 0, st, (const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums); } while (0)
+#define LAUNCH_MC(T) launch_pdl(head_bwd_mc_kernel<T>, grid, 256, 0, st, (const T*)x, ldx, w, probs, y_true, coef, (T*)dx, lddx, dw, db, hw, K, C, ppb, bn_sums)
   if (dtype == UNET_F32)       { if (C == 1) LAUNCH(float, 1); else LAUNCH_MC(float); }
   else if (dtype == UNET_BF16) { if (C == 1) LAUNCH(__nv_bfloat16, 1); else LAUNCH_MC(__nv_bfloat16); }
 #undef LAUNCH_MC

@@ -26,6 +26,7 @@ template <int CH>
 __global__ void __launch_bounds__(256)
 preprocess_u8_kernel(const uint8_t* __restrict__ img, int H0, int W0, int64_t row_stride, float* __restrict__ out, int h, int w,
                      float divisor, double sy, double sx) {
+  pdl_enter();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)h * w) return;
   const int y = (int)(t / w), x = (int)(t % w);
@@ -45,6 +46,7 @@ preprocess_u8_kernel(const uint8_t* __restrict__ img, int H0, int W0, int64_t ro
 __global__ void __launch_bounds__(256)
 postprocess_mask_kernel(const float* __restrict__ prob, int h, int w, int64_t ldp, uint8_t* __restrict__ mask, int H0, int W0,
                         float threshold, double sy, double sx) {
+  pdl_enter();
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (t >= (int64_t)H0 * W0) return;
   const int y = (int)(t / W0), x = (int)(t % W0);
@@ -69,9 +71,9 @@ extern "C" int unet_preprocess_u8(const uint8_t* img, int H0, int W0, int C, int
   const unsigned grid = (unsigned)ceil_div((int64_t)h * w, 256);
   const double sy = (double)H0 / h, sx = (double)W0 / w;
   cudaStream_t st = (cudaStream_t)stream;
-  if (C == 1) preprocess_u8_kernel<1><<<grid, 256, 0, st>>>(img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
-  else if (C == 3) preprocess_u8_kernel<3><<<grid, 256, 0, st>>>(img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
-  else preprocess_u8_kernel<4><<<grid, 256, 0, st>>>(img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
+  if (C == 1) launch_pdl(preprocess_u8_kernel<1>, grid, 256, 0, st, img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
+  else if (C == 3) launch_pdl(preprocess_u8_kernel<3>, grid, 256, 0, st, img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
+  else launch_pdl(preprocess_u8_kernel<4>, grid, 256, 0, st, img, H0, W0, row_stride_bytes, out, h, w, divisor, sy, sx);
   UNET_LAUNCH_CHECK("preprocess_u8");
   return UNET_OK;
 }
@@ -80,7 +82,7 @@ extern "C" int unet_postprocess_mask(const float* prob, int h, int w, int64_t ld
                                      void* stream) {
   UNET_REQUIRE(prob && mask && h > 0 && w > 0 && H0 > 0 && W0 > 0 && ld >= 1, UNET_EINVAL, "postprocess_mask: bad argument");
   const unsigned grid = (unsigned)ceil_div((int64_t)H0 * W0, 256);
-  postprocess_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(prob, h, w, ld, mask, H0, W0, threshold, (double)h / H0, (double)w / W0);
+  launch_pdl(postprocess_mask_kernel, grid, 256, 0, (cudaStream_t)stream, prob, h, w, ld, mask, H0, W0, threshold, (double)h / H0, (double)w / W0);
   UNET_LAUNCH_CHECK("postprocess_mask");
   return UNET_OK;
 }

@@ -78,6 +78,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(640, 1)
 sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP, const FsParams p) {
+  pdl_launch_dependents();
   using Cfg = FsCfg<BLOCK_N>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +101,6 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.num_k;
 
-  for (int i = threadIdx.x; i < 9 * p.Cin; i += blockDim.x) s_wd[i] = p.wd9c[i];
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 5); }   // 4 producer warps + the MMA commit
@@ -111,6 +111,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr, 2 * BLOCK_N); tmem_relinquish(); }
+  pdl_wait();            // above: shared memory, TMEM and kernel parameters only
+  for (int i = threadIdx.x; i < 9 * p.Cin; i += blockDim.x) s_wd[i] = p.wd9c[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -415,7 +417,7 @@ static int fs_launch(const CUtensorMap& tmX, const CUtensorMap& tmB, const CUten
   if (cudaError_t e = ensure_dynamic_smem(once, sepconv_fused_kernel<BLOCK_N>, Cfg::kSmemBytes))
     return set_cuda_error(e, "sepconv_fused: cudaFuncSetAttribute");
   const unsigned grid = (unsigned)i64min(p.total_tiles, sm_count());
-  sepconv_fused_kernel<BLOCK_N><<<grid, 640, Cfg::kSmemBytes, st>>>(tmX, tmB, tmY, tmP, p);
+  launch_pdl(sepconv_fused_kernel<BLOCK_N>, grid, 640, Cfg::kSmemBytes, st, tmX, tmB, tmY, tmP, p);
   UNET_LAUNCH_CHECK("sepconv_fused");
   return UNET_OK;
 }

@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256, 4)
 stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const float* __restrict__ wp, T* __restrict__ out,
                 int64_t ldo, int N, int H, int W, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                 double* __restrict__ colsum, double* __restrict__ colsq, int tiles_h, int tiles_w, float* __restrict__ d_out) {
+  pdl_enter();
   __shared__ float s_x[(kTH + 2) * (kTW + 2) * kStemCin];
   __shared__ float s_d[kTH * kTW * kStemCin];
   __shared__ float s_wd[9 * kStemCin];
@@ -127,6 +128,7 @@ stem_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, const f
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_dw_kernel(const T* __restrict__ x, const float* __restrict__ wd9c, float* __restrict__ d3, int N, int H, int W) {
+  pdl_enter();
   __shared__ float s_wd[9 * kStemCin];
   if (threadIdx.x < 9 * kStemCin) s_wd[threadIdx.x] = wd9c[threadIdx.x];
   __syncthreads();
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(256, 4)
 stem_pw_kernel(const float* __restrict__ d3, const float* __restrict__ wp, T* __restrict__ out, int64_t ldo, int64_t M,
                const float* __restrict__ scale, const float* __restrict__ shift, int relu,
                double* __restrict__ colsum, double* __restrict__ colsq) {
+  pdl_enter();
   __shared__ float s_stat[2 * kStemCout];
   if (threadIdx.x < 2 * kStemCout) s_stat[threadIdx.x] = 0.f;
   const int cg = threadIdx.x & 7, slot = threadIdx.x >> 3;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256, 2)
 stem_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dz, int64_t lddz, const float* __restrict__ wd9c,
                 const float* __restrict__ wp, float* __restrict__ dwd9c, float* __restrict__ dwp, int N, int H, int W,
                 int tiles_h, int tiles_w) {
+  pdl_enter();
   __shared__ float s_x[(kTH + 2) * (kTW + 2) * kStemCin];
   __shared__ float s_d[kTH * kTW * kStemCin];
   __shared__ float s_dd[kTH * kTW * kStemCin];
@@ -345,6 +349,7 @@ __global__ void __launch_bounds__(256, 2)
 stem_bwd_folded_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict__ z, const float* __restrict__ coef,
                        const float* __restrict__ d3, const float* __restrict__ wp, float* __restrict__ dwp, T* __restrict__ dd,
                        int64_t M) {
+  pdl_enter();
   constexpr int kRaw = 8 * (int)sizeof(T);          // bytes of 8 channels
   constexpr int kSbD = sizeof(T) == 2 ? 4 : 2;
   __shared__ __align__(16) uint8_t ring_g[kSbD][256 * kRaw];
@@ -463,9 +468,9 @@ extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, 
     const int64_t M = (int64_t)N * H * W;
     const unsigned g1 = (unsigned)i64min(ceil_div(M, 256), (int64_t)sm_count() * 32);
     const unsigned g2 = (unsigned)i64min(ceil_div(M, 256), (int64_t)sm_count() * 16);
-#define STEM_STREAM(T) do { stem_dw_kernel<T><<<g1, 256, 0, st>>>((const T*)x, wd9c, d_out, N, H, W); \
-      if (colsum) stem_pw_kernel<T, true><<<g2, 256, 0, st>>>(d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); \
-      else stem_pw_kernel<T, false><<<g2, 256, 0, st>>>(d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); } while (0)
+#define STEM_STREAM(T) do { launch_pdl(stem_dw_kernel<T>, g1, 256, 0, st, (const T*)x, wd9c, d_out, N, H, W); \
+      if (colsum) launch_pdl(stem_pw_kernel<T, true>, g2, 256, 0, st, d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); \
+      else launch_pdl(stem_pw_kernel<T, false>, g2, 256, 0, st, d_out, wp, (T*)out, ldo, M, scale, shift, relu, colsum, colsq); } while (0)
     if (dtype == UNET_F32) STEM_STREAM(float);
     else if (dtype == UNET_BF16) STEM_STREAM(__nv_bfloat16);
     else return set_error(UNET_EINVAL, "stem_fwd: bad dtype %d", dtype);
@@ -473,7 +478,7 @@ extern "C" int unet_stem_fwd(const void* x, const float* wd9c, const float* wp, 
     UNET_LAUNCH_CHECK("stem_fwd(stream)");
     return UNET_OK;
   }
-#define STEM_FWD(T, S) stem_fwd_kernel<T, S><<<grid, 256, 0, st>>>((const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw, d_out)
+#define STEM_FWD(T, S) launch_pdl(stem_fwd_kernel<T, S>, grid, 256, 0, st, (const T*)x, wd9c, wp, (T*)out, ldo, N, H, W, scale, shift, relu, colsum, colsq, th, tw, d_out)
   if (dtype == UNET_F32) { if (colsum) STEM_FWD(float, true); else STEM_FWD(float, false); }
   else if (dtype == UNET_BF16) { if (colsum) STEM_FWD(__nv_bfloat16, true); else STEM_FWD(__nv_bfloat16, false); }
 #undef STEM_FWD
@@ -492,9 +497,9 @@ extern "C" int unet_stem_bwd(const void* x, const void* dz, int64_t lddz, const 
   const unsigned grid = (unsigned)i64min(tiles, (int64_t)sm_count() * 4);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_F32)
-    stem_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)x, (const float*)dz, lddz, wd9c, wp, dwd9c, dwp, N, H, W, th, tw);
+    launch_pdl(stem_bwd_kernel<float>, grid, 256, 0, st, (const float*)x, (const float*)dz, lddz, wd9c, wp, dwd9c, dwp, N, H, W, th, tw);
   else if (dtype == UNET_BF16)
-    stem_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, lddz, wd9c, wp, dwd9c, dwp,
+    launch_pdl(stem_bwd_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dz, lddz, wd9c, wp, dwd9c, dwp,
                                                         N, H, W, th, tw);
   else return set_error(UNET_EINVAL, "stem_bwd: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("stem_bwd");
@@ -509,9 +514,9 @@ extern "C" int unet_stem_bwd_folded(const void* g, int64_t ldg, const void* z, c
   const unsigned grid = (unsigned)i64min(ceil_div(M, 32 * 64), (int64_t)sm_count() * 12);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == UNET_F32)
-    stem_bwd_folded_kernel<float><<<grid, 256, 0, st>>>((const float*)g, ldg, (const float*)z, coef, d3, wp, dwp, (float*)dd, M);
+    launch_pdl(stem_bwd_folded_kernel<float>, grid, 256, 0, st, (const float*)g, ldg, (const float*)z, coef, d3, wp, dwp, (float*)dd, M);
   else if (dtype == UNET_BF16)
-    stem_bwd_folded_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g, ldg, (const __nv_bfloat16*)z, coef, d3, wp, dwp,
+    launch_pdl(stem_bwd_folded_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)g, ldg, (const __nv_bfloat16*)z, coef, d3, wp, dwp,
                                                                (__nv_bfloat16*)dd, M);
   else return set_error(UNET_EINVAL, "stem_bwd_folded: bad dtype %d", dtype);
   UNET_LAUNCH_CHECK("stem_bwd_folded");

@@ -83,6 +83,14 @@ def sample_iou(y_true: np.ndarray, y_pred: np.ndarray, smooth: float = SMOOTH) -
     return float((inter + np.float32(smooth)) / (union + np.float32(smooth)))
 
 
+def sample_iou_from_counts(cm4, smooth: float = SMOOTH) -> float:
+    """calculate_sample_iou (scripts/benchmark.py:159-170) from a sample's 2x2 confusion counts [t*2+p]: for {0,1} arrays
+    I = #(t=1,p=1), T = #(t=1), P = #(p=1); same float32 arithmetic as sample_iou, so the value is identical."""
+    inter = np.float32(cm4[3])
+    union = np.float32(cm4[2] + cm4[3]) + np.float32(cm4[1] + cm4[3]) - inter
+    return float((inter + np.float32(smooth)) / (union + np.float32(smooth)))
+
+
 # ------------------------------------------------------------------------------------------------ GPU variants (opt-in)
 def gpu_preprocess(images_bgr, height: int, width: int):
     """uint8 BGR images (any sizes) -> one CUDA fp32 batch [B, height, width, 3]: the same /255 + INTER_LINEAR resize as
@@ -104,3 +112,15 @@ def gpu_probability_to_mask(prob_dev, out_height: int, out_width: int, threshold
     mask = torch.empty((out_height, out_width), dtype=torch.uint8, device="cuda")
     ops.postprocess_mask(prob_dev[..., 0], mask, threshold)
     return mask.cpu().numpy()
+
+
+def gpu_batch_sample_counts(truth, prob_dev, threshold: float) -> np.ndarray:
+    """truth: host uint8/float {0,1} [B,h,w,1]; prob_dev: CUDA fp32 [B,h,w,1] (model.predict_on_device).  Returns the
+    per-sample 2x2 confusion counts [B,4] (int64, host) of (prob > threshold) — one kernel launch, one 32*B-byte read-back
+    instead of the probabilities' trip to the host."""
+    import torch
+    from . import ops
+    t = torch.from_numpy(np.ascontiguousarray(truth, dtype=np.float32)).cuda()
+    counts = torch.zeros((t.shape[0], 4), dtype=torch.int64, device="cuda")
+    ops.sample_confusion_thr(t, prob_dev, threshold, counts)
+    return counts.cpu().numpy()

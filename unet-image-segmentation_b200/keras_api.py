@@ -93,6 +93,14 @@ class MeanIoU:
             raise ValueError(f"y_true and y_pred differ in size: {tuple(t.shape)} vs {tuple(p.shape)}")
         ops.confusion_matrix_update(t.view(-1), p.view(-1), self.num_classes, self._dev_counts())
 
+    def add_confusion(self, cm) -> None:
+        """Accumulate a confusion matrix computed elsewhere (benchmark.py's device path sums per-sample counts)."""
+        import torch
+        c = torch.from_numpy(np.ascontiguousarray(np.asarray(cm, dtype=np.int64).reshape(-1))).cuda()
+        if c.numel() != self.num_classes * self.num_classes:
+            raise ValueError("confusion matrix has the wrong size")
+        self._dev_counts().add_(c)
+
     def confusion_matrix(self) -> np.ndarray:
         c = self.num_classes
         return np.zeros((c, c), np.int64) if self._counts is None else self._counts.cpu().numpy().reshape(c, c)

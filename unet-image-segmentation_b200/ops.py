@@ -563,6 +563,18 @@ def confusion_matrix_update(y_true, y_pred, num_classes: int, counts: torch.Tens
               _p(counts), _stream())
 
 
+def sample_confusion_thr(y_true: torch.Tensor, prob: torch.Tensor, threshold: float, counts: torch.Tensor) -> None:
+    """Per-sample 2x2 confusion counts of (prob > threshold) against a {0,1} truth: counts [NB,4] int64, accumulated
+    (calculate_sample_iou + MeanIoU(2) of scripts/benchmark.py:159-170,260,269 from one pass over the batch)."""
+    _f32(y_true, "y_true"); _f32(prob, "prob")
+    nb = y_true.shape[0]
+    if y_true.numel() != prob.numel() or prob.shape[0] != nb:
+        raise ValueError("sample_confusion_thr: y_true and prob disagree")
+    if counts.dtype != torch.int64 or not counts.is_contiguous() or tuple(counts.shape) != (nb, 4) or not counts.is_cuda:
+        raise TypeError("counts must be a contiguous CUDA int64 [NB,4] tensor")
+    _call("unet_sample_confusion_thr", _p(y_true), _p(prob), float(threshold), nb, y_true.numel() // nb, _p(counts), _stream())
+
+
 # ------------------------------------------------------------------------------------------------ optimiser, staging
 def adamw_step(w, g, m, v, hyper) -> None:
     for t, nm in ((w, "w"), (g, "g"), (m, "m"), (v, "v"), (hyper, "hyper")):

@@ -51,8 +51,9 @@ typedef enum {
                              Inference only; tensor-core path only; needs N <= 64 (one column tile) and classes <= 8. */
 } unet_epilogue;
 
-/* stateless dropout mask: elements 2k and 2k+1 (linear NHWC offsets in the ctot-wide tensor) share h = lowbias32(k ^ seed-mix);
-   element e keeps iff its 16-bit half of h (low half for even e) < floor((1-rate) * 65536).  rate == 0 disables. */
+/* stateless dropout mask: elements 4k .. 4k+3 (linear NHWC offsets in the ctot-wide tensor) share two 32-bit words
+   a = mix(k ^ seed-mix), b = a * 0xC2B2AE3D; b ^= b >> 16 (csrc/common.cuh::dropout_words); element 4k+j keeps iff its 16-bit
+   field (a.lo, a.hi, b.lo, b.hi) < floor((1-rate) * 65536).  rate == 0 disables.  Tensors of up to 2^34 elements. */
 typedef struct {
   float    rate;      /* Dropout(rate), u_net.py:78,98 */
   uint32_t seed;
@@ -212,10 +213,12 @@ int unet_bn_bwd_apply(const void* dy, int64_t lddy, const void* z,
    and, when w (pointwise kernel, fp32 [Cin,C]) is given, the operands of the folded data gradient
      wab (bf16 [Cin,2C]) = [w diag(A) | w diag(B)],  bias[i] = sum_c K[c]*w[i,c]
    so that  dd = [g | z] * wab^T + bias  (unet_gemm_tc, A2 = z, UNET_EPI_AFFINE)  and
-            dW += combine(d^T [g | z], coef, colsum(d))  (unet_gemm_tc a_trans, B2 = z;  unet_bn_bwd_wgrad_combine). */
+            dW += combine(d^T [g | z], coef, colsum(d))  (unet_gemm_tc a_trans, B2 = z;  unet_bn_bwd_wgrad_combine).
+   ill_conditioned (device int, optional): set to 1 when some |gamma[c]| < |beta[c]|/16 (incl. gamma == 0), where recovering
+   sum(g*xhat) from bf16-rounded activations loses precision; the caller then uses unet_bn_bwd_reduce/_apply instead. */
 int unet_bn_bwd_coef(const float* sums, const float* gamma, const float* beta, const float* save_mean,
                      const float* save_rstd, int64_t count, float* dgamma, float* dbeta, float* coef,
-                     const float* w, int Cin, int C, void* wab, float* bias, void* stream);
+                     const float* w, int Cin, int C, void* wab, float* bias, int* ill_conditioned, void* stream);
 /* dw[i,c] += G[i,c]*A[c] + G[i,C+c]*B[c] + sd[i]*K[c];  G fp32 [Cin,2C] = d^T [g | z], coef = [A|B|K], sd[i] = sum_m d[m,i] */
 int unet_bn_bwd_wgrad_combine(const float* G, const float* coef, const float* sd, float* dw, int Cin, int C, void* stream);
 /* Both contractions above from ONE pass over [g | z] and d (tcgen05; bf16; C == 64, Cin in {64,128}; else UNET_EUNSUPPORTED
@@ -300,7 +303,8 @@ int unet_preprocess_u8(const uint8_t* img, int H0, int W0, int C, int64_t row_st
 int unet_postprocess_mask(const float* prob, int h, int w, int64_t ld, uint8_t* mask, int H0, int W0, float threshold,
                           void* stream);
 
-/* host helper: the mask bit the kernels use, for reproducing dropout on the host in tests */
+/* host helper: the 32-bit word holding element idx's 16-bit mask field (idx & 1 selects the half), for reproducing dropout on
+   the host in tests */
 uint32_t unet_host_dropout_hash(uint64_t idx, uint32_t seed);
 
 #ifdef __cplusplus

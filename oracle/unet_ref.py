@@ -127,32 +127,45 @@ def init_params(specs: List[dict], seed: int = 2301, trained_like: bool = False)
 
 
 # ----------------------------------------------------------------------------------------------- dropout mask
-def dropout_hash(idx: np.ndarray, seed: int) -> np.ndarray:
-    """Restatement of dropout_hash() in csrc/common.cuh (lowbias32 over a 64-bit element index)."""
-    idx = idx.astype(np.uint64)
-    lo = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint64)
-    hi = (idx >> np.uint64(32)).astype(np.uint64)
+def dropout_words(group: np.ndarray, seed: int):
+    """Restatement of dropout_words() in csrc/common.cuh: the two 32-bit words (a, b) a group of four consecutive elements
+    draws from its index and the seed (uint32 arithmetic, wrapping)."""
     m32 = np.uint64(0xFFFFFFFF)
-    s = (np.uint64(seed) * np.uint64(0x85EBCA6B) + np.uint64(0xC2B2AE35)) & m32
-    x = (lo ^ ((hi * np.uint64(0x9E3779B1)) & m32) ^ s) & m32
-    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m32
-    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m32
-    x ^= x >> np.uint64(16)
-    return x.astype(np.uint32)
+    g = group.astype(np.uint64) & m32
+    s = (np.uint64(seed & 0xFFFFFFFF) * np.uint64(0x85EBCA6B) + np.uint64(0xC2B2AE35)) & m32
+    x = ((g ^ s) * np.uint64(0x9E3779B1)) & m32
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x85EBCA77)) & m32
+    x ^= x >> np.uint64(13)
+    y = (x * np.uint64(0xC2B2AE3D)) & m32
+    y ^= y >> np.uint64(16)
+    return x.astype(np.uint32), y.astype(np.uint32)
 
 
-def dropout_multiplier(shape: Tuple[int, int, int, int], rate: float, seed: int) -> np.ndarray:
+def dropout_hash(idx: np.ndarray, seed: int) -> np.ndarray:
+    """The 32-bit word that holds element idx's 16-bit field (dropout_hash() of csrc/common.cuh; unet_host_dropout_hash)."""
+    idx = np.asarray(idx).astype(np.uint64)
+    a, b = dropout_words(idx >> np.uint64(2), seed)
+    return np.where((idx & np.uint64(2)) != 0, b, a).astype(np.uint32)
+
+
+def dropout_fields(idx: np.ndarray, seed: int) -> np.ndarray:
+    """16-bit field of every element: a.lo, a.hi, b.lo, b.hi for elements 4k .. 4k+3."""
+    idx = np.asarray(idx).astype(np.uint64)
+    h = dropout_hash(idx, seed)
+    return np.where((idx & np.uint64(1)) == 1, h >> np.uint32(16), h & np.uint32(0xFFFF)).astype(np.uint32)
+
+
+def dropout_multiplier(shape: Tuple[int, int, int, int], rate: float, seed: int, offset: int = 0) -> np.ndarray:
     """Mask * 1/(1-rate) over an NHWC tensor, indexed by the element's linear offset (Dropout, u_net.py:78,98).
-    Restates dropout_mult() of csrc/common.cuh: one hash per pair of adjacent elements (2k, 2k+1); element e keeps iff
-    its 16-bit half (low half for even e) is below floor(keep_prob * 65536)."""
+    Restates dropout_mult() of csrc/common.cuh: element e keeps iff its 16-bit field is below floor(keep_prob * 65536).
+    `offset`: linear offset of the first element (to evaluate a slab of a larger tensor)."""
     n = int(np.prod(shape))
-    idx = np.arange(n, dtype=np.uint64)
-    h = dropout_hash(idx >> np.uint64(1), seed)
-    r = np.where((idx & np.uint64(1)) == 1, h >> np.uint32(16), h & np.uint32(0xFFFF)).astype(np.uint32)
+    idx = np.uint64(offset) + np.arange(n, dtype=np.uint64)
+    r = dropout_fields(idx, seed)
     keep = np.float32(1.0 - rate)
-    thr = np.uint32(np.float32(keep) * np.float32(65536.0))
+    thr = min(int(np.float32(keep) * np.float32(65536.0)), 65535)
     inv = np.float32(1.0) / keep
-    return np.where(r < thr, inv, np.float32(0)).astype(np.float32).reshape(shape)
+    return np.where(r < np.uint32(thr), inv, np.float32(0)).astype(np.float32).reshape(shape)
 
 
 # ----------------------------------------------------------------------------------------------- primitive ops

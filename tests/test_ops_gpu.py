@@ -313,7 +313,9 @@ def test_bn_bwd_folded_into_gemms():
     sums = dev(np.stack([g.sum(0), (g * y).sum(0)]))
     dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
     coef = torch.empty((3, c), device="cuda"); wab = torch.empty((cin, 2 * c), device="cuda", dtype=bf); bias = torch.empty(cin, device="cuda")
-    ops.bn_bwd_coef(sums, dev(gamma), dev(beta), dev(mean), dev(rstd), M, dg, db, coef, w=dev(w), wab=wab, bias=bias)
+    guard = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ops.bn_bwd_coef(sums, dev(gamma), dev(beta), dev(mean), dev(rstd), M, dg, db, coef, w=dev(w), wab=wab, bias=bias, guard=guard)
+    assert int(guard.item()) == int(np.any(np.abs(gamma) < np.abs(beta) / 16))
     np.testing.assert_allclose(host(db), dbeta, rtol=1e-5, atol=1e-4)
     np.testing.assert_allclose(host(dg), dgamma, rtol=2e-2, atol=0.5)        # xhat recovered from the bf16 activation
     gd, zd, dd_ = dev(g, bf), dev(z, bf), dev(d, bf)

@@ -53,6 +53,31 @@ elif name == "gemm_convt_shape":   # the dec1_upsample contraction with a plain 
     C = torch.empty((B * 256 * 256, 256), device=dev, dtype=bf)
     bias = torch.zeros(256, device=dev)
     run(lambda: ops.gemm(x, Bt, C, b_trans=True, epilogue=ops.EPI_AFFINE, shift=bias), (x.numel() + C.numel()) * 2)
+elif name in ("pw_bneck2", "pw_dec4b1", "pw_enc4b2", "dgrad_bneck2"):
+    # tensor-bound pointwise GEMMs of train512: bneck_block2.pw 1024->1024 at 32x32, dec4_block1.pw 1024->512 and
+    # enc4_block2.pw 512->512 at 64x64 (forward with BatchNormalization statistics), and bneck_block2's data gradient
+    m, k, n = {"pw_bneck2": (B * 32 * 32, 1024, 1024), "pw_dec4b1": (B * 64 * 64, 1024, 512), "pw_enc4b2": (B * 64 * 64, 512, 512),
+               "dgrad_bneck2": (B * 32 * 32, 1024, 1024)}[name]
+    A, Bt, C = rnd(m, k), rnd(n, k), torch.empty((m, n), device=dev, dtype=bf)
+    cs = torch.zeros(n, device=dev, dtype=torch.float64); cq = torch.zeros_like(cs)
+    flops = 2 * m * k * n
+    if name.startswith("dgrad"):
+        fn = lambda: ops.gemm(A, Bt, C, b_trans=True)
+    else:
+        fn = lambda: ops.gemm(A, Bt, C, b_trans=True, epilogue=ops.EPI_STATS, colsum=cs, colsq=cq)
+    run(fn, (m * k + m * n + n * k) * 2)
+    print(f"{name}: {flops / 1e12:.3f} TFLOP per launch")
+elif name in ("convt_dec4", "convt_dec3", "convt_dec2", "convt_dec4_nodrop", "convt_dec3_nodrop", "convt_dec2_nodrop"):
+    # Conv2DTranspose GEMMs with the 5-D pixel-shuffle store into the concat buffer (+ Dropout in the epilogue, as trained)
+    hh, cin = {"convt_dec4": (32, 1024), "convt_dec3": (64, 512), "convt_dec2": (128, 256)}[name.replace("_nodrop", "")]
+    cout = cin // 2
+    x, Bt = rnd(B, hh, hh, cin), rnd(4 * cout, cin)
+    cat = torch.empty((B, 2 * hh, 2 * hh, 2 * cout), device=dev, dtype=bf)
+    bias = torch.zeros(cout, device=dev)
+    drop = None if name.endswith("_nodrop") else ops.make_dropout(0.2, 5, ctot=2 * cout, c0=0)
+    run(lambda: ops.gemm(x, Bt, cat[..., :cout], b_trans=True, epilogue=ops.EPI_CONVT, shift=bias, convt_hw=(hh, hh), drop=drop),
+        (x.numel() + B * 4 * hh * hh * cout + Bt.numel()) * 2)
+    print(f"{name}: {2 * B * hh * hh * cin * 4 * cout / 1e12:.3f} TFLOP per launch")
 elif name == "wgrad64":
     A, Bm, C = rnd(M, 64), rnd(M, 64), torch.zeros((64, 64), device=dev)
     run(lambda: ops.gemm(A, Bm, C, a_trans=True, accumulate=True), 2 * M * 64 * 2)

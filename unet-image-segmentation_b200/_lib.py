@@ -56,7 +56,7 @@ _SIGNATURES = {
     "unet_device_check": [_i],
     "unet_dwconv3x3_fwd": [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp, _vp, _dp, _vp, _vp],
     "unet_dwconv3x3_bwd_weight": [_vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp],
-    "unet_bn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+    "unet_bn_bwd_coef": [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "unet_bn_bwd_wgrad_combine": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "unet_pw_bwd_fused": [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _vp],
     "unet_dwconv3x3_bwd": [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp, _dp, _i, _vp, _vp, _vp, _i, _vp, _vp],

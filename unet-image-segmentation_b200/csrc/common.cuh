@@ -183,35 +183,66 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32(from_f32<T>(v)); }
 
 // ---------------------------------------------------------------- dropout mask (stateless, reproducible on host)
-// One 32-bit hash serves TWO adjacent elements (indices 2k, 2k+1): element e keeps iff its 16-bit half of the hash of
-// pair k is below floor(keep_prob * 65536).  (16 bits: |P(keep) - keep_prob| < 2^-16.)
-__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t idx, uint32_t seed) {
-  uint32_t x = static_cast<uint32_t>(idx) ^ (static_cast<uint32_t>(idx >> 32) * 0x9E3779B1u) ^ (seed * 0x85EBCA6Bu + 0xC2B2AE35u);
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;   // lowbias32
-  return x;
+// Elements are taken in GROUPS OF FOUR consecutive linear offsets (4k .. 4k+3; one 8-byte bf16 vector).  A group draws two
+// 32-bit words from its index and the seed,
+//     a = mix(k ^ seedmix),   b = a * 0xC2B2AE3D; b ^= b >> 16,        mix(x): x *= 0x9E3779B1; x ^= x >> 15; x *= 0x85EBCA77; x ^= x >> 13
+// and element 4k+j keeps iff its 16-bit field (a.lo, a.hi, b.lo, b.hi for j = 0..3) is below floor(keep_prob * 65536)
+// (|P(keep) - keep_prob| < 2^-16).  10 integer instructions per four elements instead of one full avalanche hash per pair:
+// the mask is recomputed by every producer and consumer of a dropped tensor (never stored), so it sits on the critical path
+// of issue-bound kernels.  Group indices are 32-bit: tensors of up to 2^34 elements (the mask repeats beyond).
+// oracle/unet_ref.py::dropout_multiplier restates this on the host.
+__host__ __device__ __forceinline__ uint32_t dropout_seedmix(uint32_t seed) { return seed * 0x85EBCA6Bu + 0xC2B2AE35u; }
+__host__ __device__ __forceinline__ void dropout_words(uint32_t group, uint32_t seedmix, uint32_t& a, uint32_t& b) {
+  uint32_t x = (group ^ seedmix) * 0x9E3779B1u;
+  x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
+  a = x;
+  uint32_t y = x * 0xC2B2AE3Du;
+  y ^= y >> 16;
+  b = y;
 }
-__host__ __device__ __forceinline__ uint32_t dropout_threshold(float keep_prob) { return static_cast<uint32_t>(keep_prob * 65536.0f); }
+// threshold in the HIGH half of a word: field < thr  <=>  (field << 16) < (thr << 16), so the high field compares in one instruction
+__host__ __device__ __forceinline__ uint32_t dropout_threshold(float keep_prob) {
+  uint32_t t = static_cast<uint32_t>(keep_prob * 65536.0f);
+  return (t > 65535u ? 65535u : t) << 16;
+}
+// the 32-bit word holding element idx's field (host helper / tests)
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint64_t idx, uint32_t seed) {
+  uint32_t a, b;
+  dropout_words(static_cast<uint32_t>(idx >> 2), dropout_seedmix(seed), a, b);
+  return (idx & 2) ? b : a;
+}
 // multiplier for element idx: 0 if dropped, 1/(1-rate) if kept
 __host__ __device__ __forceinline__ float dropout_mult(uint64_t idx, uint32_t seed, float keep_prob, float inv_keep) {
-  const uint32_t h = dropout_hash(idx >> 1, seed);
-  const uint32_t r = (idx & 1) ? (h >> 16) : (h & 0xffffu);
-  return r < dropout_threshold(keep_prob) ? inv_keep : 0.0f;
+  const uint32_t h = dropout_hash(idx, seed);
+  const uint32_t f = (idx & 1) ? h : (h << 16);
+  return f < dropout_threshold(keep_prob) ? inv_keep : 0.0f;
 }
-// multipliers of elements even_idx and even_idx + 1 from one hash
-__host__ __device__ __forceinline__ void dropout_mult2(uint64_t even_idx, uint32_t seed, uint32_t thr, float inv_keep, float& m0, float& m1) {
-  const uint32_t h = dropout_hash(even_idx >> 1, seed);
-  m0 = (h & 0xffffu) < thr ? inv_keep : 0.0f;
-  m1 = (h >> 16) < thr ? inv_keep : 0.0f;
-}
-// n consecutive elements starting at an EVEN index (n even)
-template <int N>
+// n consecutive elements starting at an EVEN index (n even); runs that start on a multiple of 4 with n % 4 == 0 (every bf16
+// kernel: a thread owns 4, 8 or 32 channels) draw one pair of words per four elements
+// PRESCALED: the caller has already multiplied the kept values by 1/keep_prob (folded into an FMA it does anyway); only zero the rest
+template <int N, bool PRESCALED = false>
 __device__ __forceinline__ void dropout_apply(float (&v)[N], uint64_t even_base, uint32_t seed, float keep_prob, float inv_keep) {
   const uint32_t thr = dropout_threshold(keep_prob);
+  const uint32_t sm = dropout_seedmix(seed);
+  const float m = PRESCALED ? 1.0f : inv_keep;
+  if (N % 4 == 0 && (even_base & 2) == 0) {
+    const uint32_t g0 = static_cast<uint32_t>(even_base >> 2);
 #pragma unroll
-  for (int j = 0; j < N; j += 2) {
-    float m0, m1;
-    dropout_mult2(even_base + j, seed, thr, inv_keep, m0, m1);
-    v[j] *= m0; v[j + 1] *= m1;
+    for (int j = 0; j < N / 4; ++j) {
+      uint32_t a, b;
+      dropout_words(g0 + j, sm, a, b);
+      v[4 * j]     = (a << 16) < thr ? (PRESCALED ? v[4 * j] : v[4 * j] * m) : 0.0f;
+      v[4 * j + 1] = a < thr ? (PRESCALED ? v[4 * j + 1] : v[4 * j + 1] * m) : 0.0f;
+      v[4 * j + 2] = (b << 16) < thr ? (PRESCALED ? v[4 * j + 2] : v[4 * j + 2] * m) : 0.0f;
+      v[4 * j + 3] = b < thr ? (PRESCALED ? v[4 * j + 3] : v[4 * j + 3] * m) : 0.0f;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      const uint32_t h = dropout_hash(even_base + j, seed);
+      v[j]     = (h << 16) < thr ? (PRESCALED ? v[j] : v[j] * m) : 0.0f;
+      v[j + 1] = h < thr ? (PRESCALED ? v[j + 1] : v[j + 1] * m) : 0.0f;
+    }
   }
 }
 

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ rstd, float inv_count,
                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef,
-                   const float* __restrict__ w, int Cin, int C, __nv_bfloat16* __restrict__ wab, float* __restrict__ bias) {
+                   const float* __restrict__ w, int Cin, int C, __nv_bfloat16* __restrict__ wab, float* __restrict__ bias,
+                   int* __restrict__ ill_conditioned) {
   pdl_enter();
   __shared__ float s_red[8];
   const int i = blockIdx.x;
@@ -74,6 +75,10 @@ bn_bwd_coef_kernel(const float* __restrict__ sums, const float* __restrict__ gam
     const float g = gamma[c], b = beta[c];
     const float s1 = sums[c], s2 = sums[C + c];
     const float dg = g != 0.f ? (s2 - b * s1) / g : 0.f;     // sum(g * xhat)
+    // (s2 - b*s1)/g is formed from bf16-rounded activations y = g*xhat + b: once |g| << |b| the rounding of y (2^-9 |b|) swamps
+    // g*xhat and dividing by g amplifies it (and g == 0 loses dgamma altogether).  Tell the host, which then takes the
+    // explicit reduce/apply schedule (sum(g*xhat) straight from z) for the rest of training.
+    if (i == 0 && ill_conditioned && fabsf(g) < 0.0625f * fabsf(b)) *ill_conditioned = 1;
     const float c1 = s1 * inv_count, c2 = dg * inv_count;
     const float A = g * rstd[c];
     const float B = -A * c2 * rstd[c];
@@ -882,11 +887,11 @@ extern "C" int unet_seg_loss_finalize(const double* sums, int NC_pairs, float sm
 
 extern "C" int unet_bn_bwd_coef(const float* sums, const float* gamma, const float* beta, const float* save_mean,
                                 const float* save_rstd, int64_t count, float* dgamma, float* dbeta, float* coef,
-                                const float* w, int Cin, int C, void* wab, float* bias, void* stream) {
+                                const float* w, int Cin, int C, void* wab, float* bias, int* ill_conditioned, void* stream) {
   UNET_REQUIRE(sums && gamma && beta && save_mean && save_rstd && C > 0 && count > 0, UNET_EINVAL, "bn_bwd_coef: bad argument");
   UNET_REQUIRE(!w || (wab && bias && Cin > 0), UNET_EINVAL, "bn_bwd_coef: w needs wab, bias and Cin");
   launch_pdl(bn_bwd_coef_kernel, w ? Cin : 1, 256, 0, ST, sums, gamma, beta, save_mean, save_rstd, 1.f / (float)count, dgamma, dbeta, coef,
-                                                 w, Cin, C, (__nv_bfloat16*)wab, bias);
+                                                 w, Cin, C, (__nv_bfloat16*)wab, bias, ill_conditioned);
   UNET_LAUNCH_CHECK("bn_bwd_coef");
   return UNET_OK;
 }

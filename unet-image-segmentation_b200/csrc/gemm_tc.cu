@@ -353,7 +353,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int64_t n = (int64_t)n_blk * BLOCK_N + i;
             float sc = 1.f, sh = 0.f;
             if (n < p.N) {
-              if (epi == UNET_EPI_CONVT) { if (p.shift) sh = __ldg(p.shift + (n % p.convt_cout)); }
+              if (epi == UNET_EPI_CONVT) { if (p.shift) sh = __ldg(p.shift + (n % p.convt_cout)); if (p.drop_on) sh *= p.inv_keep; }
               else { if (p.scale) sc = __ldg(p.scale + n); if (p.shift) sh = __ldg(p.shift + n); }
             }
             par_scale[i] = sc; par_shift[i] = sh;
@@ -410,6 +410,14 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
                 v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
               }
+            } else if (p.drop_on) {               // Conv2DTranspose + Dropout: (acc + bias) / keep as one FMA (the staged bias is pre-divided)
+              const float ik = p.inv_keep;
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 h4 = lds128f(ph_s + i * 4);
+                v[i] = fmaf(v[i], ik, h4.x); v[i + 1] = fmaf(v[i + 1], ik, h4.y);
+                v[i + 2] = fmaf(v[i + 2], ik, h4.z); v[i + 3] = fmaf(v[i + 3], ik, h4.w);
+              }
             } else {                              // bias only (Conv2DTranspose, folded BN scale, folded BN backward)
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
@@ -421,7 +429,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.drop_on) dropout_apply(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
+            if (p.drop_on) dropout_apply<32, true>(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
           }
           if (kHeadCapable && head) {             // 1x1 output convolution from the activations as they will be stored (bf16)
             const int ncls = p.head_classes;

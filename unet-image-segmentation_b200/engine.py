@@ -84,6 +84,7 @@ class UNetEngine:
             # lr, wd, beta1, beta2, eps, t, grad_scale, unused
             self.hyper = torch.tensor([2e-3, 1e-4, 0.9, 0.999, 1e-7, 1.0, 1.0, 0.0], device=dev)
             self.step_word = torch.zeros(1, device=dev, dtype=torch.int32)
+            self.fold_guard = torch.zeros(1, device=dev, dtype=torch.int32)    # set by bn_bwd_coef: the fold is ill-conditioned
             # folded BN backward (per block): sums [2,Cout] | sd [Cin] | G [Cin,2Cout] live in ONE fp32 buffer zeroed per step
             self._fz_off: Dict[str, Tuple[int, int, int]] = {}
             tot = 0
@@ -498,14 +499,14 @@ class UNetEngine:
             sums, sd, G, coef, wab, bias = self._fold_bufs(prefix)
             gamma, beta = self.wview(f"{prefix}_bn/gamma"), self.wview(f"{prefix}_bn/beta")
             if stem:   # streaming first-block backward: dz = A*g + B*z + K in registers, then a 3-channel depthwise weight gradient
-                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef)
+                ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef, guard=self.fold_guard)
                 dd3 = pl.buf(prefix + "/dd3", (B, h, w, cin))
                 ops.stem_bwd_folded(dy, z, coef, pl.t[prefix + "/d3"], self._mat(f"{prefix}_sepconv/pointwise_kernel"), gwp, dd3)
                 ops.dwconv3x3_bwd_weight(x, dd3, self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g))
                 return None
             else:      # dz = A*g + B*z + K never exists: both contractions read [g | z]
                 ops.bn_bwd_coef(sums, gamma, beta, smean, srstd, M, dgamma, dbeta, coef,
-                                w=self._mat(f"{prefix}_sepconv/pointwise_kernel"), wab=wab, bias=bias)
+                                w=self._mat(f"{prefix}_sepconv/pointwise_kernel"), wab=wab, bias=bias, guard=self.fold_guard)
                 d = pl.t[prefix + "/d"]
                 if self.fuse_pw_bwd and ops.pw_bwd_fused_supported(dy, z, d, dd):
                     ops.pw_bwd_fused(dy, z, d, wab, bias, dd, G)    # both contractions from one pass over [g | z] and d
@@ -767,6 +768,19 @@ class UNetEngine:
         out3 = pl.buf("out3", (3,), torch.float32)
         ops.seg_loss_finalize(sums, B * NC, SMOOTH, {"dice": 0, "iou": 1}[loss], 1.0, out3, None)
         return out3
+
+    def check_fold_guard(self) -> bool:
+        """Host read of the conditioning flag of the folded BatchNormalization backward (call at a point that synchronises
+        anyway, e.g. the end of an epoch).  When some |gamma| has fallen below |beta|/16 the engine switches to the explicit
+        reduce / apply schedule — which forms sum(g*xhat) from z directly — for the rest of training.  Returns True if it did."""
+        if not self.fold_bn_bwd or int(self.fold_guard.item()) == 0:
+            return False
+        import warnings
+        warnings.warn("BatchNormalization backward: a gamma fell below |beta|/16; switching from the folded to the two-pass schedule")
+        self.fold_bn_bwd = False
+        self.fold_guard.zero_()
+        self._graphs = {k: v for k, v in self._graphs.items() if k[0] != "train"}
+        return True
 
     def plan_bytes(self) -> int:
         return sum(p.bytes() for p in self._plans.values())

@@ -763,6 +763,7 @@ class Model:
             for k, ev in pending:
                 ev.synchronize(); host_sum += ring[k].numpy()
             self.last_h2d_bytes = pf.h2d_bytes
+            self.engine.check_fold_guard()          # epoch end synchronises anyway (the logs are read back)
             if self._grad_sync is not None and self._grad_sync.world > 1:
                 acc, n_all = self._dp_reduce(torch.tensor(host_sum, device="cuda", dtype=torch.float64), n, self.metrics)
                 host_sum, n_red = acc.cpu().numpy(), n_all

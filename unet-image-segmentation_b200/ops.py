@@ -390,9 +390,13 @@ def pw_bwd_fused(g, z, d, wab, bias, dd, G) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ batch normalisation
-def bn_bwd_coef(sums, gamma, beta, save_mean, save_rstd, count: int, dgamma, dbeta, coef=None, w=None, wab=None, bias=None) -> None:
+def bn_bwd_coef(sums, gamma, beta, save_mean, save_rstd, count: int, dgamma, dbeta, coef=None, w=None, wab=None, bias=None,
+                guard: Optional[torch.Tensor] = None) -> None:
     """BatchNormalization backward as per-channel coefficients dz = A*g + B*z + K (coef fp32 [3,C]); accumulates dgamma/dbeta;
-    with the pointwise kernel w [Cin,C] also the folded data-gradient operands wab (bf16 [Cin,2C]) and bias [Cin]."""
+    with the pointwise kernel w [Cin,C] also the folded data-gradient operands wab (bf16 [Cin,2C]) and bias [Cin].
+    guard (CUDA int32 [1], optional): set to 1 by the kernel when the fold is ill-conditioned (|gamma| < |beta|/16)."""
+    if guard is not None and (guard.dtype != torch.int32 or not guard.is_cuda):
+        raise TypeError("guard must be a CUDA int32 tensor")
     for t, nm in ((sums, "sums"), (gamma, "gamma"), (beta, "beta"), (save_mean, "save_mean"), (save_rstd, "save_rstd"),
                   (dgamma, "dgamma"), (dbeta, "dbeta"), (coef, "coef"), (w, "w"), (bias, "bias")):
         _f32(t, nm)
@@ -406,7 +410,7 @@ def bn_bwd_coef(sums, gamma, beta, save_mean, save_rstd, count: int, dgamma, dbe
     if sums.numel() != 2 * c or (coef is not None and coef.numel() != 3 * c):
         raise ValueError("bn_bwd_coef: sums must hold 2*C and coef 3*C floats")
     _call("unet_bn_bwd_coef", _p(sums), _p(gamma), _p(beta), _p(save_mean), _p(save_rstd), int(count), _p(dgamma), _p(dbeta),
-          _p(coef), _p(w), cin, c, _p(wab), _p(bias), _stream())
+          _p(coef), _p(w), cin, c, _p(wab), _p(bias), _p(guard), _stream())
 
 
 def bn_bwd_wgrad_combine(G, coef, sd, dw) -> None:

@@ -37,7 +37,7 @@ bool pdl_enabled() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("UNET_B200_PDL");
-    cached = (e && e[0] == '0') ? 0 : 1;
+    cached = (e && e[0] == '1') ? 1 : 0;     // opt-in: measured slower under CUDA-graph replay (common.cuh)
   }
   return cached == 1;
 }

@@ -31,14 +31,18 @@ __host__ __device__ inline int64_t i64min(int64_t a, int64_t b) { return a < b ?
 __host__ __device__ inline int64_t i64max(int64_t a, int64_t b) { return a > b ? a : b; }
 int sm_count();
 
-// ---------------------------------------------------------------- programmatic dependent launch
-// Every kernel of the library is launched with the programmatic-stream-serialization attribute and begins with pdl_enter():
-// `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be scheduled as soon as every CTA of this one has
-// started (its CTAs fill the SMs that this kernel's tail leaves idle and run their prologue: barrier init, descriptor
-// prefetch, TMEM allocation), and `griddepcontrol.wait` holds this kernel's first global-memory access until the PREVIOUS
-// kernel of the stream has completed and flushed.  Kernel boundaries of the ~195-launch training step (or its CUDA graph:
-// the attribute is captured as a programmatic edge) then cost a CTA hand-over instead of a drain + launch + ramp.
-// UNET_B200_PDL=0 turns the attribute off (the device instructions are then no-ops).
+// ---------------------------------------------------------------- programmatic dependent launch (opt-in: UNET_B200_PDL=1)
+// Every kernel begins with pdl_enter() (or its two halves around a prologue that touches only shared memory / TMEM / kernel
+// parameters): `griddepcontrol.wait` holds the first global-memory access until the PREVIOUS kernel of the stream has completed
+// and flushed, so a kernel launched with the programmatic-stream-serialization attribute may be scheduled before its
+// predecessor has drained; `griddepcontrol.launch_dependents` lets the NEXT kernel be scheduled as soon as every CTA of this one
+// has started.  Without the attribute both instructions are no-ops.
+//   UNET_B200_PDL=0 (default)  plain launches.  MEASURED on B200, train512 CUDA-graph replay, same box, alternating runs:
+//                              55.11 / 55.02 ms per step.
+//   UNET_B200_PDL=1            attribute + early trigger: 56.03 / 55.95 ms per step (-1.7 %): programmatic edges cost more per
+//                              graph node than the ~195 kernel boundaries of the step give back; inference 512x512 is unchanged
+//                              within run-to-run noise (11.45 / 11.63 vs 11.88 / 11.60 ms).
+// Kept because eager (non-graph) launch sequences can profit; off where it was measured to lose.
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -732,7 +732,10 @@ class UNetEngine:
             torch.cuda.current_stream().synchronize()
             g = torch.cuda.CUDAGraph()
             try:
-                with torch.cuda.graph(g):
+                # data parallel: NCCL's watchdog thread polls CUDA events concurrently, which the default (global) capture
+                # mode would turn into a capture error; only this thread's calls belong to the capture
+                mode = "thread_local" if self.grad_hook is not None else "global"
+                with torch.cuda.graph(g, capture_error_mode=mode):
                     cap = self._step_eager(gx, gy, loss)
             except Exception as e:
                 if self.grad_hook is None:

@@ -534,6 +534,9 @@ def _emit(line: dict):
 
 def main():
     args = parse()
+    if os.environ.get("BENCH_FAULT_TIMEOUT"):      # debugging aid: dump every thread's Python stack if the run is still going
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_FAULT_TIMEOUT"]), exit=True, file=sys.stderr)
     _reserve_stdout()
     if args.impl == "reference":
         run_reference(args)

@@ -112,6 +112,14 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
   a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(p) = a;
 }
+// bf16 -> fp32 of the low half is `u << 16`; written as a byte permute so that it stays on the ALU pipe: ptxas turns the shift
+// into IMAD.U32 (x * 65536), which lands on the FMA pipe — the one these kernels saturate (ncu r02: IMAD.U32 carried 11 % of
+// the stall samples of the fused depthwise backward, almost all of them math-pipe throttle)
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t u) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(d) : "r"(u));     // bytes (lsb first): 0, 0, u.b0, u.b1
+  return __uint_as_float(d);
+}
 // 8-byte shared-memory load through an explicit shared-window address (pointer arithmetic on the dynamic-smem base
 // otherwise degrades to generic LD)
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {

@@ -122,14 +122,6 @@ template <typename T, int CW_ = 1, int PXT_ = 32> struct StripCfg {
 
 // 8 bytes of channels -> fp32 pairs (the operands of the packed FFMA2 path)
 template <typename T> __device__ __forceinline__ void unpack8(const uint2& r, float2 (&v)[4 / sizeof(T)]);
-// bf16 -> fp32 of the low half is `u << 16`; written as a byte permute so that it stays on the ALU pipe: ptxas turns the shift
-// into IMAD.U32 (x * 65536), which lands on the FMA pipe — the one these kernels saturate (ncu r02: IMAD.U32 carried 11 % of
-// the stall samples of the fused depthwise backward, almost all of them math-pipe throttle)
-__device__ __forceinline__ float bf16lo_to_f32(uint32_t u) {
-  uint32_t d;
-  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(d) : "r"(u));     // bytes (lsb first): 0, 0, u.b0, u.b1
-  return __uint_as_float(d);
-}
 template <> __device__ __forceinline__ void unpack8<__nv_bfloat16>(const uint2& r, float2 (&v)[2]) {
   v[0] = make_float2(bf16lo_to_f32(r.x), __uint_as_float(r.x & 0xffff0000u));
   v[1] = make_float2(bf16lo_to_f32(r.y), __uint_as_float(r.y & 0xffff0000u));

@@ -208,10 +208,10 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             n3 = lds64(xs + (r + 1) * kXCols * 128 + 384);
           }
           float2 q0[2], q1[2], q2[2], q3[2];
-          q0[0] = make_float2(__uint_as_float(r0.x << 16), __uint_as_float(r0.x & 0xffff0000u)); q0[1] = make_float2(__uint_as_float(r0.y << 16), __uint_as_float(r0.y & 0xffff0000u));
-          q1[0] = make_float2(__uint_as_float(r1.x << 16), __uint_as_float(r1.x & 0xffff0000u)); q1[1] = make_float2(__uint_as_float(r1.y << 16), __uint_as_float(r1.y & 0xffff0000u));
-          q2[0] = make_float2(__uint_as_float(r2.x << 16), __uint_as_float(r2.x & 0xffff0000u)); q2[1] = make_float2(__uint_as_float(r2.y << 16), __uint_as_float(r2.y & 0xffff0000u));
-          q3[0] = make_float2(__uint_as_float(r3.x << 16), __uint_as_float(r3.x & 0xffff0000u)); q3[1] = make_float2(__uint_as_float(r3.y << 16), __uint_as_float(r3.y & 0xffff0000u));
+          q0[0] = make_float2(bf16lo_to_f32(r0.x), __uint_as_float(r0.x & 0xffff0000u)); q0[1] = make_float2(bf16lo_to_f32(r0.y), __uint_as_float(r0.y & 0xffff0000u));
+          q1[0] = make_float2(bf16lo_to_f32(r1.x), __uint_as_float(r1.x & 0xffff0000u)); q1[1] = make_float2(bf16lo_to_f32(r1.y), __uint_as_float(r1.y & 0xffff0000u));
+          q2[0] = make_float2(bf16lo_to_f32(r2.x), __uint_as_float(r2.x & 0xffff0000u)); q2[1] = make_float2(bf16lo_to_f32(r2.y), __uint_as_float(r2.y & 0xffff0000u));
+          q3[0] = make_float2(bf16lo_to_f32(r3.x), __uint_as_float(r3.x & 0xffff0000u)); q3[1] = make_float2(bf16lo_to_f32(r3.y), __uint_as_float(r3.y & 0xffff0000u));
           if (r >= 2) {
             float2 o0[2], o1[2];
 #pragma unroll

@@ -232,12 +232,14 @@ __host__ __device__ __forceinline__ float dropout_mult(uint64_t idx, uint32_t se
 // n consecutive elements starting at an EVEN index (n even); runs that start on a multiple of 4 with n % 4 == 0 (every bf16
 // kernel: a thread owns 4, 8 or 32 channels) draw one pair of words per four elements
 // PRESCALED: the caller has already multiplied the kept values by 1/keep_prob (folded into an FMA it does anyway); only zero the rest
-template <int N, bool PRESCALED = false>
+// ALIGNED4: the caller guarantees even_base % 4 == 0 (no code for the generic path: the tensor-core epilogues are large enough to
+// feel every duplicated loop in the instruction cache)
+template <int N, bool PRESCALED = false, bool ALIGNED4 = false>
 __device__ __forceinline__ void dropout_apply(float (&v)[N], uint64_t even_base, uint32_t seed, float keep_prob, float inv_keep) {
   const uint32_t thr = dropout_threshold(keep_prob);
   const uint32_t sm = dropout_seedmix(seed);
   const float m = PRESCALED ? 1.0f : inv_keep;
-  if (N % 4 == 0 && (even_base & 2) == 0) {
+  if (N % 4 == 0 && (ALIGNED4 || (even_base & 2) == 0)) {
     const uint32_t g0 = static_cast<uint32_t>(even_base >> 2);
 #pragma unroll
     for (int j = 0; j < N / 4; ++j) {

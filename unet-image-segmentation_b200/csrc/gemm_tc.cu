@@ -65,8 +65,9 @@ template <int BLOCK_N> struct TcCfg {
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kNumEpiWarps * kSlabBytes + 256;
 };
 
-// ------------------------------------------------------------------------------------------------ shared epilogue
-// One 64-column chunk of one warp's 32 accumulator rows: TMEM -> slab -> (lane owns 4 fixed columns) -> global.
+// ------------------------------------------------------------------------------------------------ weight-gradient epilogue
+// One 64-column chunk of one warp's 32 accumulator rows: TMEM -> slab -> (lane owns 4 fixed columns) -> fp32 atomics into C.
+// (The weight-gradient kernel is the only user: accumulate == 1, no fused epilogue — validated on the host.)
 template <bool OUT_BF16>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_addr, uint8_t* slab, int lane,
                                                int64_t row0 /*global row of slab row 0*/, int64_t n_base /*global col of chunk*/,
@@ -87,67 +88,14 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, uint32_t tmem_
   const int seg = lane & 15, rsub = lane >> 4;
   const int64_t n = n_base + seg * 4;
   const bool col_ok = n < p.N;     // N is a multiple of 8: a 4-column group is all-or-nothing
-  float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-  uint32_t cv_ab = 0, cv_co = 0;
-  if (col_ok) {
-    if (p.epilogue == UNET_EPI_AFFINE || p.epilogue == UNET_EPI_AFFINE_RELU) {
-      if (p.scale) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.scale + n)); sc[0] = t.x; sc[1] = t.y; sc[2] = t.z; sc[3] = t.w; }
-      if (p.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + n)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
-    } else if (p.epilogue == UNET_EPI_CONVT) {
-      cv_ab = (uint32_t)n / (uint32_t)p.convt_cout; cv_co = (uint32_t)n % (uint32_t)p.convt_cout;
-      if (p.shift) { const float4 t = __ldg(reinterpret_cast<const float4*>(p.shift + cv_co)); sh[0] = t.x; sh[1] = t.y; sh[2] = t.z; sh[3] = t.w; }
-    }
-  }
-  const bool relu = p.epilogue == UNET_EPI_AFFINE_RELU;
-  const bool stats = p.epilogue == UNET_EPI_STATS;
 #pragma unroll 4
   for (int it = 0; it < 16; ++it) {
     const int r = it * 2 + rsub;
     const int64_t m = row0 + r;
     const float4 a = lds128f(smem_u32(slab) + (uint32_t)(r * kSlabPitch + seg * 16));
     if (!col_ok || m >= p.M) continue;
-    float v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j] = fmaf(v[j], sc[j], sh[j]);
-      if (relu) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (p.accumulate) {
-      float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(dst + j, v[j]);
-      continue;
-    }
-    int64_t off;
-    if (p.epilogue == UNET_EPI_CONVT) {
-      // 32-bit index arithmetic (M < 2^31 is checked on the host): 64-bit div/mod here cost more than the tile's MMA
-      const uint32_t m32 = (uint32_t)m, cw = (uint32_t)p.convt_W, ch = (uint32_t)p.convt_H;
-      const uint32_t q = m32 / cw, jj = m32 - q * cw;
-      const uint32_t img = q / ch, ii = q - img * ch;
-      const int64_t pix = ((int64_t)img * 2 * ch + 2 * ii + (cv_ab >> 1)) * (2 * cw) + 2 * jj + (cv_ab & 1);
-      if (p.drop_on) {
-        const uint64_t base = (uint64_t)pix * p.ctot + p.c0 + cv_co;
-        dropout_apply(v, base, p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u), p.keep, p.inv_keep);
-      }
-      off = pix * p.ldc + cv_co;
-    } else {
-      off = m * p.ldc + n;
-    }
-    if (OUT_BF16) {
-      uint2 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + off) = o;
-      if (stats) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float rr = round_to<__nv_bfloat16>(v[j]); st_sum[j] += rr; st_sq[j] = fmaf(rr, rr, st_sq[j]); }
-      }
-    } else {
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off) = make_float4(v[0], v[1], v[2], v[3]);
-      if (stats) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { st_sum[j] += v[j]; st_sq[j] = fmaf(v[j], v[j], st_sq[j]); }
-      }
-    }
+    float* dst = reinterpret_cast<float*>(p.C) + m * p.ldc + n;
+    atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
   }
   __syncwarp();   // slab is overwritten by the next chunk
 }
@@ -318,6 +266,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     const bool stats = epi == UNET_EPI_STATS;
     const uint32_t seed = p.drop_on ? p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0u) : 0u;
+    const float drop_ik = p.drop_on ? p.inv_keep : 1.0f;
     // Conv2DTranspose: tile rows are input pixels (q = image*H + i, j); the box covers min(W,128) columns x 128/min(W,128) rows
     const int cw = p.convt_W;
     float st_sum[kChunks][CPL], st_sq[kChunks][CPL];
@@ -410,26 +359,20 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 v[i] = fmaf(v[i], s4.x, h4.x); v[i + 1] = fmaf(v[i + 1], s4.y, h4.y);
                 v[i + 2] = fmaf(v[i + 2], s4.z, h4.z); v[i + 3] = fmaf(v[i + 3], s4.w, h4.w);
               }
-            } else if (p.drop_on) {               // Conv2DTranspose + Dropout: (acc + bias) / keep as one FMA (the staged bias is pre-divided)
-              const float ik = p.inv_keep;
+            } else {                              // bias only (Conv2DTranspose, folded BN scale, folded BN backward); with Dropout
+              const float ik = drop_ik;           // the kept values' 1/keep rides in the same FMA (the staged bias is pre-divided)
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 h4 = lds128f(ph_s + i * 4);
                 v[i] = fmaf(v[i], ik, h4.x); v[i + 1] = fmaf(v[i + 1], ik, h4.y);
                 v[i + 2] = fmaf(v[i + 2], ik, h4.z); v[i + 3] = fmaf(v[i + 3], ik, h4.w);
               }
-            } else {                              // bias only (Conv2DTranspose, folded BN scale, folded BN backward)
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 h4 = lds128f(ph_s + i * 4);
-                v[i] += h4.x; v[i + 1] += h4.y; v[i + 2] += h4.z; v[i + 3] += h4.w;
-              }
             }
             if (relu) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (p.drop_on) dropout_apply<32, true>(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
+            if (p.drop_on) dropout_apply<32, true, true>(v, drop_base + half * 32, seed, p.keep, p.inv_keep);
           }
           if (kHeadCapable && head) {             // 1x1 output convolution from the activations as they will be stored (bf16)
             const int ncls = p.head_classes;
@@ -973,6 +916,9 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   UNET_REQUIRE(!a->shift || aligned16(a->shift), UNET_EALIGN, "gemm_tc: shift must be 16B aligned");
   if (a->epilogue == UNET_EPI_CONVT)
     UNET_REQUIRE(a->M < (int64_t)1 << 31, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs M < 2^31");
+  if (a->epilogue == UNET_EPI_CONVT && a->drop.rate > 0.f)
+    UNET_REQUIRE(a->drop.ctot % 4 == 0 && a->drop.c0 % 4 == 0, UNET_EUNSUPPORTED,
+                 "gemm_tc: CONVT dropout needs ctot and c0 to be multiples of 4 (mask groups of four elements)");
   if (a->epilogue == UNET_EPI_CONVT) {
     UNET_REQUIRE((a->N / 4) % 64 == 0, UNET_EUNSUPPORTED, "gemm_tc: CONVT needs Cout%%64==0 (got %lld)", (long long)(a->N / 4));
     const int w = a->convt_W;   // a 128-row tile must be a whole box of input pixels: W | 128 or 128 | W

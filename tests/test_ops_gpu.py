@@ -513,6 +513,62 @@ def test_gemm_tc_fused_head(classes, store_y):
         np.testing.assert_allclose(host(Cm), y, **tol(torch.bfloat16))
 
 
+@pytest.mark.parametrize("mkn", [(128, 32, 64), (1000, 64, 64), (300, 72, 128), (4096, 512, 512), (257, 1024, 256), (129, 8, 64), (96, 36, 1024)])
+def test_gemm_tc_fp32_tf32x3(mkn):
+    """fp32 mode on the tensor cores: operands split into tf32 (hi, lo) parts, three kind::tf32 MMAs per k-step.  Against fp64:
+    the error must be fp32-grade (a single tf32 product would be off by ~5e-4 relative), incl. strided A views and ragged tiles."""
+    M, K, N = mkn
+    a = RNG.standard_normal((M, K)).astype(np.float32)
+    b = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T
+    abuf = torch.zeros((M, K + 8), device="cuda"); abuf[:, 4:4 + K] = dev(a)
+    bh, bl = torch.empty((N, K), device="cuda"), torch.empty((N, K), device="cuda")
+    ops.split_tf32(dev(b), bh, bl)
+    np.testing.assert_array_equal(host(bh) + host(bl), b.astype(np.float64))          # the split is exact
+    assert np.all((bh.view(torch.int32) & 0x1FFF) == 0)                                # hi is a tf32 value
+    c = torch.zeros((M, N + 4), device="cuda")
+    ops.gemm(abuf[:, 4:4 + K], bh, c[:, :N], b_trans=True, B_lo=bl, tensor_core=True)
+    got = host(c)
+    err = np.abs(got[:, :N] - ref).max()
+    assert err <= 2e-5 * np.abs(ref).max() + 1e-6, err
+    assert np.all(got[:, N:] == 0)
+    # transposed split (weights kept as [K, N] in Keras order)
+    bth, btl = torch.empty((N, K), device="cuda"), torch.empty((N, K), device="cuda")
+    ops.split_tf32(dev(b.T.copy()), bth, btl, transpose=True)
+    np.testing.assert_array_equal(host(bth), host(bh)); np.testing.assert_array_equal(host(btl), host(bl))
+    # epilogues: scale/shift + ReLU, batch statistics
+    sc, sh = RNG.uniform(0.5, 1.5, N).astype(np.float32), RNG.standard_normal(N).astype(np.float32)
+    c2 = torch.empty((M, N), device="cuda")
+    ops.gemm(dev(a), bh, c2, b_trans=True, B_lo=bl, epilogue=ops.EPI_AFFINE_RELU, scale=dev(sc), shift=dev(sh))
+    np.testing.assert_allclose(host(c2), np.maximum(ref * sc + sh, 0), rtol=1e-5, atol=2e-5 * np.abs(ref).max())
+    cs, cq = torch.zeros(N, device="cuda", dtype=torch.float64), torch.zeros(N, device="cuda", dtype=torch.float64)
+    ops.gemm(dev(a), bh, c2, b_trans=True, B_lo=bl, epilogue=ops.EPI_STATS, colsum=cs, colsq=cq)
+    np.testing.assert_allclose(cs.cpu().numpy(), ref.sum(0), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(cq.cpu().numpy(), (ref ** 2).sum(0), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("rate", [0.0, 0.2])
+@pytest.mark.parametrize("cfg", [(2, 4, 4, 128, 64), (1, 8, 16, 256, 32), (3, 6, 128, 64, 64)])
+def test_convt_tc_fp32_tf32x3(cfg, rate):
+    n, h, w, cin, cout = cfg
+    x = RNG.standard_normal((n, h, w, cin)).astype(np.float32)
+    k = (RNG.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
+    b = RNG.standard_normal(cout).astype(np.float32)
+    ref = R.convt2x2(x.astype(np.float64), k.astype(np.float64), b.astype(np.float64))
+    Bnk = dev(k.reshape(4 * cout, cin))
+    bh, bl = torch.empty_like(Bnk), torch.empty_like(Bnk)
+    ops.split_tf32(Bnk, bh, bl)
+    concat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), device="cuda")
+    drop = ops.make_dropout(rate, 5, ctot=2 * cout, c0=0)
+    ops.gemm(dev(x), bh, concat[..., :cout], b_trans=True, B_lo=bl, epilogue=ops.EPI_CONVT, shift=dev(b), convt_hw=(h, w), drop=drop,
+             tensor_core=True)
+    if rate > 0:
+        ref = ref * R.dropout_multiplier((n, 2 * h, 2 * w, 2 * cout), rate, 5)[..., :cout]
+    got = host(concat)
+    np.testing.assert_allclose(got[..., :cout], ref, rtol=2e-5, atol=3e-5)
+    assert np.all(got[..., cout:] == 0)
+
+
 @pytest.mark.parametrize("mkn", [(1000, 64, 64), (5000, 256, 512), (333, 128, 192)])
 @pytest.mark.parametrize("out_dtype", DTYPES)
 def test_gemm_tc_stats(mkn, out_dtype):

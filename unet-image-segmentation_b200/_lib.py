@@ -42,6 +42,7 @@ class GemmArgs(C.Structure):
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_classes", C.c_int),
         ("A2", C.c_void_p), ("lda2", C.c_int64), ("k_split", C.c_int64),
         ("B2", C.c_void_p), ("ldb2", C.c_int64), ("n_split", C.c_int64),
+        ("A_lo", C.c_void_p), ("B_lo", C.c_void_p),
     ]
 
 
@@ -81,6 +82,7 @@ _SIGNATURES = {
     "unet_confusion_matrix_update": [_vp, _vp, _i64, _i, _vp, _vp],
     "unet_confusion_matrix_update_thr": [_vp, _vp, _f, _i64, _vp, _vp],
     "unet_sample_confusion_thr": [_vp, _vp, _f, _i64, _i64, _vp, _vp],
+    "unet_split_tf32": [_vp, _i64, _i64, _i64, _vp, _vp, _i, _vp],
     "unet_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "unet_step_advance": [_vp, _vp, _vp],
     "unet_cast_transpose_bf16": [_vp, _vp, _vp, _i, _i, _vp, _vp],

@@ -527,6 +527,45 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
   }
 }
 
+// tf32 (hi, lo) split (fp32 mode on the tensor cores): hi = cvt.rna.tf32(x), lo = x - hi
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
+                                  float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_enter();
+  const int64_t cv = cols >> 2;                   // cols % 4 == 0 (checked on the host)
+  const int64_t n4 = rows * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv, c = (i - r * cv) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * ld + c));
+    const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+    *reinterpret_cast<float4*>(hi + r * cols + c) = h;
+    *reinterpret_cast<float4*>(lo + r * cols + c) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  }
+}
+__global__ void split_tf32_t_kernel(const float* __restrict__ src, int64_t ld, int R, int C, float* __restrict__ hi_t, float* __restrict__ lo_t) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = blockIdx.y * 32 + i;
+    tile[i][threadIdx.x] = (r < R && c < C) ? src[(int64_t)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  const int r2 = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c2 = blockIdx.x * 32 + i;
+    if (r2 < R && c2 < C) {
+      const float v = tile[threadIdx.x][i], h = tf32_rna(v);
+      hi_t[(int64_t)c2 * R + r2] = h;
+      lo_t[(int64_t)c2 * R + r2] = v - h;
+    }
+  }
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ s, D* __restrict__ d, int64_t n) {
   pdl_enter();
@@ -819,6 +858,22 @@ extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(R, 32));
   launch_pdl(cast_transpose_bf16_kernel, grid, dim3(32, 8), 0, ST, src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C, col_scale);
   UNET_LAUNCH_CHECK("cast_transpose_bf16");
+  return UNET_OK;
+}
+
+extern "C" int unet_split_tf32(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo, int transpose, void* stream) {
+  UNET_REQUIRE(src && hi && lo && rows > 0 && cols > 0 && ld >= cols, UNET_EINVAL, "split_tf32: bad argument");
+  if (transpose) {
+    UNET_REQUIRE(rows < ((int64_t)1 << 31) && cols < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "split_tf32: transposed split is for weight matrices");
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    launch_pdl(split_tf32_t_kernel, grid, dim3(32, 8), 0, ST, src, ld, (int)rows, (int)cols, hi, lo);
+  } else {
+    UNET_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && aligned16(src) && aligned16(hi) && aligned16(lo), UNET_EALIGN,
+                 "split_tf32: needs cols%%4==0, ld%%4==0 and 16B-aligned pointers");
+    const unsigned grid = (unsigned)i64min(ceil_div(rows * (cols / 4), 256), (int64_t)sm_count() * 16);
+    launch_pdl(split_tf32_kernel, grid, 256, 0, ST, src, ld, rows, cols, hi, lo);
+  }
+  UNET_LAUNCH_CHECK("split_tf32");
   return UNET_OK;
 }
 

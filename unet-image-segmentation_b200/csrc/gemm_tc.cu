@@ -36,6 +36,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// kind::tf32: D fp32, A/B fp32 words read as tf32 (8 k per instruction = the same 32 bytes per row as 16 bf16), M = 128, K-major.
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
 // ================================================================================================ kernel parameters
 struct TcParams {
   int64_t M, N, K;
@@ -138,11 +143,17 @@ __device__ __forceinline__ void stats_flush(const TcParams& p, int lane, int64_t
 constexpr int kNumEpiGroups = 2;
 constexpr int kStageTileBytes = 128 * 128;       // 128 rows x 128 B
 
-template <int BLOCK_N> struct NtCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+// X3 (fp32 mode): operands are fp32, each given as a (hi, lo) pair of tensors with hi = tf32(x), lo = x - hi (unet_split_tf32);
+// a stage holds [A_hi | A_lo] and [B_hi | B_lo] tiles of 32 k (128 B rows) and every k-step issues three kind::tf32 MMAs
+// (hi*hi + lo*hi + hi*lo): fp32-grade products (error ~2^-21 of |a||b|) at a third of the tf32 rate.
+template <int BLOCK_N, bool X3 = false> struct NtCfg {
+  static constexpr int kTileA = kBlockM * 128;          // 128 rows x 128 B: 64 bf16 or 32 fp32 per row
+  static constexpr int kTileB = BLOCK_N * 128;
+  static constexpr int kABytes = kTileA * (X3 ? 2 : 1);
+  static constexpr int kBBytes = kTileB * (X3 ? 2 : 1);
+  static constexpr int kKElems = X3 ? 32 : 64;          // k per stage
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5);
+  static constexpr int kStages = X3 ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5));
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;        // fused output head: w[class][64] + bias[8]
   static constexpr int kParBytes = kNumEpiGroups * (2 * BLOCK_N + kHeadFloats) * 4;   // per group: scale, shift[, head]
@@ -163,12 +174,14 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void*
                ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
-template <int BLOCK_N, bool OUT_BF16>
+template <int BLOCK_N, bool OUT_BF16, bool X3 = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  static_assert(!X3 || (!OUT_BF16 && BLOCK_N <= 128), "the tf32x3 variant serves fp32 mode: fp32 output, tiles up to 128 x 128");
   pdl_launch_dependents();
-  using Cfg = NtCfg<BLOCK_N>;
+  using Cfg = NtCfg<BLOCK_N, X3>;
   constexpr int kStages = Cfg::kStages;
   constexpr int CW = OUT_BF16 ? 64 : 32;          // output columns per 128-byte staging row
   constexpr int kChunks = BLOCK_N / CW;
@@ -187,10 +200,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_k = (int)((p.K + kBlockK - 1) / kBlockK);
+  const int num_k = (int)((p.K + Cfg::kKElems - 1) / Cfg::kKElems);
   const int total_tiles = p.num_m_tiles * p.num_n_tiles;
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmC); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmB2); tma_prefetch_desc(&tmC); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
@@ -211,6 +224,14 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (X3) {          // (hi, lo) pairs of both operands: tmA2 / tmB2 are the lo tensors
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * Cfg::kKElems, m_blk * kBlockM, kEvictFirst);
+            tma_load_2d(smem_a + stage * Cfg::kABytes + Cfg::kTileA, &tmA2, &full_bar[stage], kb * Cfg::kKElems, m_blk * kBlockM, kEvictFirst);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * Cfg::kKElems, n_blk * BLOCK_N, kEvictLast);
+            tma_load_2d(smem_b + stage * Cfg::kBBytes + Cfg::kTileB, &tmB2, &full_bar[stage], kb * Cfg::kKElems, n_blk * BLOCK_N, kEvictLast);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (kb < p.split_kb) tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full_bar[stage], kb * kBlockK, m_blk * kBlockM, kEvictFirst);
           else tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA2, &full_bar[stage], (kb - p.split_kb) * kBlockK, m_blk * kBlockM, kEvictFirst);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full_bar[stage], kb * kBlockK, n_blk * BLOCK_N, kEvictLast);
@@ -220,7 +241,7 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N, false, false);
+      constexpr uint32_t idesc = X3 ? make_idesc_tf32(BLOCK_N) : make_idesc(BLOCK_N, false, false);
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1; const uint32_t acc_phase = (it >> 1) & 1;
@@ -232,9 +253,20 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 0, 1024);
           const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 0, 1024);
+          if (X3) {
+            const uint64_t alo = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes + Cfg::kTileA), 0, 1024);
+            const uint64_t blo = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes + Cfg::kTileB), 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per UMMA_K inside the 128 B swizzle atom
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            for (int k = 0; k < 4; ++k) {          // 8 k (32 B) per kind::tf32 instruction; small terms first
+              umma_tf32(d_tmem, alo + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+              umma_tf32(d_tmem, adesc + 2 * k, blo + 2 * k, idesc, 1);
+              umma_tf32(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per UMMA_K inside the 128 B swizzle atom
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);
           if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -758,15 +790,18 @@ pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
 
 // ================================================================================================ host side
 // bf16 2-D tensor [outer, inner] with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B; OOB reads give zero
-static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, const char* who) {
+// (f32: fp32 elements, box = {32, box_rows} — the same 128-byte rows)
+static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, const char* who,
+                     bool f32 = false) {
   PFN_encodeTiled fn = get_encode_fn();
   UNET_REQUIRE(fn, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
-  UNET_REQUIRE(aligned16(base) && (ld % 8 == 0), UNET_EALIGN, "%s: TMA operand needs a 16B-aligned base and ld%%8==0", who);
+  const int es = f32 ? 4 : 2;
+  UNET_REQUIRE(aligned16(base) && ((ld * es) % 16 == 0), UNET_EALIGN, "%s: TMA operand needs a 16B-aligned base and a 16B-multiple row pitch", who);
   cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
@@ -819,17 +854,19 @@ static int make_c_tmap(CUtensorMap* map, const unet_gemm_args* a, const char* wh
   return UNET_OK;
 }
 
-template <int BLOCK_N, bool OUT_BF16>
-static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st) {
-  using Cfg = NtCfg<BLOCK_N>;
+template <int BLOCK_N, bool OUT_BF16, bool X3 = false>
+static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmC, TcParams& p, cudaStream_t st,
+                     const CUtensorMap* tmB2p = nullptr) {
+  using Cfg = NtCfg<BLOCK_N, X3>;
+  const CUtensorMap& tmB2 = tmB2p ? *tmB2p : tmB;
   static SmemAttrOnce once;
-  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, Cfg::kSmemBytes))
+  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_nt_kernel<BLOCK_N, OUT_BF16, X3>, Cfg::kSmemBytes))
     return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
   p.num_m_tiles = (int)ceil_div(p.M, kBlockM);
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
   const unsigned grid = (unsigned)i64min(tiles, sm_count());
-  launch_pdl(gemm_tc_nt_kernel<BLOCK_N, OUT_BF16>, grid, 384, Cfg::kSmemBytes, st, tmA, tmA2, tmB, tmC, p);
+  launch_pdl(gemm_tc_nt_kernel<BLOCK_N, OUT_BF16, X3>, grid, 384, Cfg::kSmemBytes, st, tmA, tmA2, tmB, tmB2, tmC, p);
   UNET_LAUNCH_CHECK("gemm_tc_nt");
   return UNET_OK;
 }
@@ -906,7 +943,37 @@ extern "C" int unet_pw_bwd_fused(const void* g, int64_t ldg, const void* z, int6
 
 extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;
-  UNET_REQUIRE(a->in_dtype == UNET_BF16, UNET_EUNSUPPORTED, "gemm_tc: operands must be bf16 (fp32 mode uses gemm_simt)");
+  if (a->in_dtype == UNET_F32) {
+    // fp32 mode on the tensor cores: every operand is a (hi, lo) pair from unet_split_tf32, three kind::tf32 MMAs per k-step
+    UNET_REQUIRE(a->A_lo && a->B_lo, UNET_EUNSUPPORTED, "gemm_tc: fp32 operands need their tf32 (hi, lo) split: A/B = hi parts, A_lo/B_lo = lo parts");
+    UNET_REQUIRE(!a->a_trans && a->b_trans == 1 && !a->accumulate && !a->A2 && !a->B2, UNET_EUNSUPPORTED,
+                 "gemm_tc: the fp32 (tf32x3) path takes C = A * B^T with B given as [N,K] and no operand concatenation");
+    UNET_REQUIRE(a->out_dtype == UNET_F32 && a->epilogue != UNET_EPI_HEAD, UNET_EUNSUPPORTED, "gemm_tc: the fp32 path writes fp32 and has no fused head");
+    UNET_REQUIRE(a->N % 8 == 0 && a->K % 4 == 0, UNET_EUNSUPPORTED, "gemm_tc(fp32): N must be a multiple of 8 and K of 4");
+    UNET_REQUIRE(a->ldc % 4 == 0 && aligned16(a->C), UNET_EALIGN, "gemm_tc: C needs a 16B-aligned base and ldc%%4==0");
+    UNET_REQUIRE((!a->scale || aligned16(a->scale)) && (!a->shift || aligned16(a->shift)), UNET_EALIGN, "gemm_tc: scale / shift must be 16B aligned");
+    if (a->epilogue == UNET_EPI_CONVT) {
+      UNET_REQUIRE(a->M < (int64_t)1 << 31 && (a->N / 4) % 32 == 0, UNET_EUNSUPPORTED, "gemm_tc(fp32): CONVT needs M < 2^31 and Cout%%32==0");
+      const int w = a->convt_W;
+      UNET_REQUIRE(w > 0 && (w >= kBlockM ? w % kBlockM == 0 : kBlockM % w == 0), UNET_EUNSUPPORTED,
+                   "gemm_tc: CONVT needs the input width to divide 128 or be a multiple of it (got %d)", w);
+      if (a->drop.rate > 0.f)
+        UNET_REQUIRE(a->drop.ctot % 4 == 0 && a->drop.c0 % 4 == 0, UNET_EUNSUPPORTED, "gemm_tc: CONVT dropout needs ctot and c0 to be multiples of 4");
+    }
+    TcParams p{};
+    fill_params(p, a);
+    p.split_kb = 1 << 30;
+    const int bn = a->N > 64 ? 128 : 64;
+    CUtensorMap tmA, tmAl, tmB, tmBl, tmC;
+    if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A hi)", true)) return e;
+    if (int e = make_tmap(&tmAl, a->A_lo, a->K, a->M, a->lda, kBlockM, "gemm_tc(A lo)", true)) return e;
+    if (int e = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, bn, "gemm_tc(B hi)", true)) return e;
+    if (int e = make_tmap(&tmBl, a->B_lo, a->K, a->N, a->ldb, bn, "gemm_tc(B lo)", true)) return e;
+    if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    return bn == 128 ? launch_nt<128, false, true>(tmA, tmAl, tmB, tmC, p, st, &tmBl) : launch_nt<64, false, true>(tmA, tmAl, tmB, tmC, p, st, &tmBl);
+  }
+  UNET_REQUIRE(a->in_dtype == UNET_BF16, UNET_EUNSUPPORTED, "gemm_tc: operands must be bf16, or fp32 with their tf32 split");
   UNET_REQUIRE(a->N % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc: N must be a multiple of 8 (got %lld)", (long long)a->N);
   UNET_REQUIRE(a->C == nullptr || (a->ldc % 4 == 0 && aligned16(a->C)), UNET_EALIGN, "gemm_tc: C needs a 16B-aligned base and ldc%%4==0");
   if (a->epilogue == UNET_EPI_HEAD)

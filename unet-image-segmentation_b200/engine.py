@@ -96,6 +96,9 @@ class UNetEngine:
             self._fz = torch.zeros(max(tot, 64), device=dev)
             self._fold_w: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._stage: Dict[str, torch.Tensor] = {}
+        self._stage32: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}    # fp32 mode: tf32 (hi, lo) parts of the dense kernels
+        import os as _os
+        self.fp32_tensor_cores = _os.environ.get("UNET_B200_FP32_TC", "1") != "0"   # fp32 mode: contractions as 3 x tf32 on tcgen05
         self._stage_fold: Dict[str, torch.Tensor] = {}     # inference: bf16 [Cout, Cin] pointwise kernels with the BN scale folded in
         self.fold_scale_into_weights = True
         self._stage_dirty = True
@@ -204,6 +207,19 @@ class UNetEngine:
                         a = self._stage[name] = torch.empty((r, c), device=self.device, dtype=torch.bfloat16)
                         self._stage[name + "^T"] = torch.empty((c, r), device=self.device, dtype=torch.bfloat16)
                     ops.cast_transpose_bf16(src, a, self._stage[name + "^T"])
+        elif self.fp32_tensor_cores:
+            # fp32 mode on the tensor cores: tf32 (hi, lo) parts of every dense kernel in both orientations
+            for name, p in self.spec.params.items():
+                leaf = name.split("/")[1]
+                if leaf == "pointwise_kernel" or (leaf == "kernel" and p.shape[0] == 2):
+                    src = self._mat(name)
+                    r, c = src.shape
+                    if name not in self._stage32:
+                        mk = lambda *sh: torch.empty(sh, device=self.device, dtype=torch.float32)
+                        self._stage32[name] = (mk(r, c), mk(r, c))
+                        self._stage32[name + "^T"] = (mk(c, r), mk(c, r))
+                    ops.split_tf32(src, *self._stage32[name])
+                    ops.split_tf32(src, *self._stage32[name + "^T"], transpose=True)
         self._stage_dirty = False
 
     def _refold(self) -> None:
@@ -234,24 +250,37 @@ class UNetEngine:
                 ops.gemm(d, self._stage[name + "^T"], out, b_trans=True, **kw)       # tcgen05: B as [Cout, Cin]
             else:
                 ops.gemm(d, self._stage[name], out, **kw)                            # K = 3: CUDA cores
+        elif name + "^T" in self._stage32 and cin % 4 == 0:
+            hi, lo = self._stage32[name + "^T"]                                      # tf32x3 on tcgen05: B as [Cout, Cin]
+            ops.gemm(d, hi, out, b_trans=True, B_lo=lo, **kw)
         else:
             ops.gemm(d, self._mat(name), out, **kw)
 
     def _pw_dgrad(self, prefix, dz, dd):
         name = f"{prefix}_sepconv/pointwise_kernel"
+        if self.act_dtype != torch.bfloat16 and name in self._stage32:
+            hi, lo = self._stage32[name]                                             # [Cin, Cout] = [N, K]
+            ops.gemm(dz, hi, dd, b_trans=True, B_lo=lo)
+            return
         B = self._stage[name] if self.act_dtype == torch.bfloat16 else self._mat(name)    # [Cin, Cout] = [N, K]
         ops.gemm(dz, B, dd, b_trans=True)
 
     def _convt_fwd(self, s, x, dst, drop):
         name = f"dec{s}_upsample/kernel"
         B = self._stage[name] if self.act_dtype == torch.bfloat16 else self._mat(name)    # [(a,b,co), Cin] = [N, K]
+        B_lo = None
+        if self.act_dtype != torch.bfloat16 and name in self._stage32:
+            B, B_lo = self._stage32[name]
         ops.gemm(x, B, dst, b_trans=True, epilogue=ops.EPI_CONVT, shift=self.wview(f"dec{s}_upsample/bias"),
-                 convt_hw=(x.shape[1], x.shape[2]), drop=drop)
+                 convt_hw=(x.shape[1], x.shape[2]), drop=drop, B_lo=B_lo)
 
     def _convt_dgrad(self, s, g2d, dx):
         name = f"dec{s}_upsample/kernel"
         if self.act_dtype == torch.bfloat16:
             ops.gemm(g2d, self._stage[name + "^T"], dx, b_trans=True)                # B as [Cin, 4Cout] = [N, K]
+        elif name + "^T" in self._stage32:
+            hi, lo = self._stage32[name + "^T"]
+            ops.gemm(g2d, hi, dx, b_trans=True, B_lo=lo)
         else:
             ops.gemm(g2d, self._mat(name), dx)                                       # B as [4Cout, Cin] = [K, N]
 

@@ -278,6 +278,29 @@ def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Op
 
 
 # ------------------------------------------------------------------------------------------------ dense contractions
+_split_ws = {}    # device index -> flat fp32 workspace for the (hi, lo) split of the A operand (fp32 mode on the tensor cores)
+
+
+def split_tf32(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, transpose: bool = False) -> None:
+    """hi = tf32(src) (round to nearest), lo = src - hi; hi / lo contiguous [rows, cols] ([cols, rows] with transpose)."""
+    rows, cols, ld = _rows(src, "src")
+    _f32(hi, "hi"); _f32(lo, "lo")
+    if src.dtype != torch.float32 or hi.numel() != rows * cols or lo.numel() != rows * cols:
+        raise ValueError("split_tf32: src must be fp32 and hi / lo hold rows*cols floats")
+    _call("unet_split_tf32", _p(src), ld, rows, cols, _p(hi), _p(lo), int(transpose), _stream(),
+          tag=f"{rows}x{cols}", nbytes=3 * rows * cols * 4)
+
+
+def _a_split(A: torch.Tensor, M: int, K: int):
+    dev = A.device.index or 0
+    ws = _split_ws.get(dev)
+    if ws is None or ws.numel() < 2 * M * K:
+        ws = _split_ws[dev] = torch.empty(2 * M * K, device=A.device, dtype=torch.float32)
+    hi, lo = ws[: M * K].view(M, K), ws[M * K: 2 * M * K].view(M, K)
+    split_tf32(A if A.dim() == 2 else A, hi, lo)
+    return hi, lo
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_trans: bool = False, b_trans: bool = False,
          accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,
          shift: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
@@ -285,12 +308,14 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
          drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None,
          head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
          head_out: Optional[torch.Tensor] = None, A2: Optional[torch.Tensor] = None,
-         B2: Optional[torch.Tensor] = None) -> None:
+         B2: Optional[torch.Tensor] = None, B_lo: Optional[torch.Tensor] = None) -> None:
     """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
     hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
     CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported).
     A2 (a_trans=False): the A operand is [A | A2] along K;  B2 (a_trans=True): the B operand is [B | B2] along N
-    (tensor-core path only; the first part must be a multiple of 64 columns wide)."""
+    (tensor-core path only; the first part must be a multiple of 64 columns wide).
+    B_lo: fp32 operands on the tensor cores — B is the tf32 `hi` part of the [N,K] operand and B_lo its `lo` part
+    (split_tf32); A is split into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products."""
     ar, ac, lda = _rows(A, "A")
     br, bc, ldb = _rows(B, "B")
     M, K = (ac, ar) if a_trans else (ar, ac)
@@ -356,6 +381,23 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
              and (epilogue != EPI_CONVT or ((N // 4) % 64 == 0 and convt_hw[1] > 0 and
                                            (128 % convt_hw[1] == 0 or convt_hw[1] % 128 == 0))))
     use_tc = tc_ok if tensor_core is None else tensor_core
+    if (A.dtype == torch.float32 and B_lo is not None and tensor_core is not False and not a_trans and b_trans and not accumulate
+            and A2 is None and B2 is None and epilogue != EPI_HEAD and Cm is not None and Cm.dtype == torch.float32
+            and K % 4 == 0 and N % 8 == 0 and lda % 4 == 0 and ldb % 4 == 0 and ldc % 4 == 0
+            and (epilogue != EPI_CONVT or ((N // 4) % 32 == 0 and convt_hw[1] > 0 and
+                                           (128 % convt_hw[1] == 0 or convt_hw[1] % 128 == 0)
+                                           and (drop is None or (drop.ctot % 4 == 0 and drop.c0 % 4 == 0))))):
+        if B_lo.dtype != torch.float32 or tuple(B_lo.shape) != tuple(B.shape) or B_lo.stride() != B.stride():
+            raise ValueError("gemm: B_lo must match B (fp32, same shape and strides)")
+        hi, lo = _a_split(A, M, K)
+        args.A, args.lda, args.A_lo, args.B_lo = _p(hi), K, _p(lo), _p(B_lo)
+        csz = Cm.numel() * 4
+        _call("unet_gemm_tc", C.byref(args), _stream(),
+              tag=f"{'convt' if epilogue == EPI_CONVT else 'nt'}:{M}x{N}x{K}:e{epilogue}:tf32x3",
+              nbytes=_nbytes(A, B) + csz, flops=2 * M * N * K)
+        return
+    if A.dtype == torch.float32 and tensor_core is True:
+        raise ValueError("gemm: fp32 operands reach the tensor cores only as C = A * B^T with B_lo given (tf32 split) and aligned shapes")
     csz = (Cm.numel() * Cm.element_size() if Cm is not None else 0) + (head_out.numel() * 4 if head_out is not None else 0)
     _call("unet_gemm_tc" if use_tc else "unet_gemm_simt", C.byref(args), _stream(),
           tag=f"{'wgrad' if a_trans else ('convt' if epilogue == EPI_CONVT else 'nt')}:{M}x{N}x{K}:e{epilogue}",

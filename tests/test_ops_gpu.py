@@ -525,7 +525,7 @@ def test_gemm_tc_fp32_tf32x3(mkn):
     bh, bl = torch.empty((N, K), device="cuda"), torch.empty((N, K), device="cuda")
     ops.split_tf32(dev(b), bh, bl)
     np.testing.assert_array_equal(host(bh) + host(bl), b.astype(np.float64))          # the split is exact
-    assert np.all((bh.view(torch.int32) & 0x1FFF) == 0)                                # hi is a tf32 value
+    assert bool(((bh.view(torch.int32) & 0x1FFF) == 0).all())                          # hi is a tf32 value
     c = torch.zeros((M, N + 4), device="cuda")
     ops.gemm(abuf[:, 4:4 + K], bh, c[:, :N], b_trans=True, B_lo=bl, tensor_core=True)
     got = host(c)

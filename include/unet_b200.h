@@ -93,14 +93,16 @@ typedef struct {
      The split must be a multiple of 64. */
   const void* A2; int64_t lda2; int64_t k_split;
   const void* B2; int64_t ldb2; int64_t n_split;
-  /* fp32 operands on the tensor cores (unet_gemm_tc, in_dtype = UNET_F32, a_trans = 0, b_trans = 1): A and B are the tf32 `hi`
-     parts and A_lo / B_lo the `lo` parts written by unet_split_tf32 (same shapes and pitches as A / B).  The kernel issues
-     hi*hi + lo*hi + hi*lo per k-step (fp32-grade products, error ~2^-21); NULL elsewhere. */
-  const void* A_lo; const void* B_lo;
+  /* fp32 operands on the tensor cores (unet_gemm_tc, in_dtype = UNET_F32, a_trans = 0, b_trans = 1): A and B are the fp32
+     tensors themselves (kind::tf32 ignores the low 13 mantissa bits: they act as hi = trunc(x)) and A_lo / B_lo the `lo` parts
+     written by unet_split_tf32 (same shapes; row pitches lda_lo / ldb_lo).  The kernel issues lo*hi + hi*lo + hi*hi per k-step
+     (fp32-grade products, error ~2^-20); NULL elsewhere. */
+  const void* A_lo; int64_t lda_lo; const void* B_lo; int64_t ldb_lo;
 } unet_gemm_args;
 
-/* fp32 -> tf32 (hi, lo) split for the tensor-core path of fp32 mode: hi = tf32(x) (round to nearest), lo = x - hi (exact).
-   src: [rows, cols] with row pitch ld; hi / lo: contiguous [rows, cols], or [cols, rows] when transpose != 0 (weights). */
+/* fp32 -> tf32 split for the tensor-core path of fp32 mode: lo = tf32_rna(x - trunc13(x)), where trunc13 clears the 13 mantissa
+   bits kind::tf32 ignores, so that x itself is the `hi` operand.  hi (optional, may be NULL) receives x unchanged (useful with
+   transpose).  src: [rows, cols] with row pitch ld; hi / lo: contiguous [rows, cols], or [cols, rows] when transpose != 0. */
 int unet_split_tf32(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo, int transpose, void* stream);
 
 /* ---- library ---- */

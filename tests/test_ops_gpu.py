@@ -522,10 +522,11 @@ def test_gemm_tc_fp32_tf32x3(mkn):
     b = (RNG.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
     ref = a.astype(np.float64) @ b.astype(np.float64).T
     abuf = torch.zeros((M, K + 8), device="cuda"); abuf[:, 4:4 + K] = dev(a)
-    bh, bl = torch.empty((N, K), device="cuda"), torch.empty((N, K), device="cuda")
-    ops.split_tf32(dev(b), bh, bl)
-    np.testing.assert_array_equal(host(bh) + host(bl), b.astype(np.float64))          # the split is exact
-    assert bool(((bh.view(torch.int32) & 0x1FFF) == 0).all())                          # hi is a tf32 value
+    bh, bl = dev(b), torch.empty((N, K), device="cuda")
+    ops.split_tf32(bh, None, bl)
+    trunc = (bh.view(torch.int32) & ~0x1FFF).view(torch.float32)                      # what kind::tf32 multiplies when it reads b
+    assert float((trunc.double() + bl.double() - bh.double()).abs().max()) <= 2.0 ** -21 * float(bh.abs().max())
+    assert bool(((bl.view(torch.int32) & 0x1FFF) == 0).all())                          # lo is a tf32 value
     c = torch.zeros((M, N + 4), device="cuda")
     ops.gemm(abuf[:, 4:4 + K], bh, c[:, :N], b_trans=True, B_lo=bl, tensor_core=True)
     got = host(c)
@@ -535,7 +536,7 @@ def test_gemm_tc_fp32_tf32x3(mkn):
     # transposed split (weights kept as [K, N] in Keras order)
     bth, btl = torch.empty((N, K), device="cuda"), torch.empty((N, K), device="cuda")
     ops.split_tf32(dev(b.T.copy()), bth, btl, transpose=True)
-    np.testing.assert_array_equal(host(bth), host(bh)); np.testing.assert_array_equal(host(btl), host(bl))
+    np.testing.assert_array_equal(host(bth), host(bh)); np.testing.assert_array_equal(host(btl), host(bl))       # hi = raw copy
     # epilogues: scale/shift + ReLU, batch statistics
     sc, sh = RNG.uniform(0.5, 1.5, N).astype(np.float32), RNG.standard_normal(N).astype(np.float32)
     c2 = torch.empty((M, N), device="cuda")
@@ -544,7 +545,7 @@ def test_gemm_tc_fp32_tf32x3(mkn):
     cs, cq = torch.zeros(N, device="cuda", dtype=torch.float64), torch.zeros(N, device="cuda", dtype=torch.float64)
     ops.gemm(dev(a), bh, c2, b_trans=True, B_lo=bl, epilogue=ops.EPI_STATS, colsum=cs, colsq=cq)
     np.testing.assert_allclose(cs.cpu().numpy(), ref.sum(0), rtol=1e-5, atol=1e-3)
-    np.testing.assert_allclose(cq.cpu().numpy(), (ref ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    np.testing.assert_allclose(cq.cpu().numpy(), (ref ** 2).sum(0), rtol=2e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize("rate", [0.0, 0.2])
@@ -555,9 +556,9 @@ def test_convt_tc_fp32_tf32x3(cfg, rate):
     k = (RNG.standard_normal((2, 2, cout, cin)) / np.sqrt(cin)).astype(np.float32)
     b = RNG.standard_normal(cout).astype(np.float32)
     ref = R.convt2x2(x.astype(np.float64), k.astype(np.float64), b.astype(np.float64))
-    Bnk = dev(k.reshape(4 * cout, cin))
-    bh, bl = torch.empty_like(Bnk), torch.empty_like(Bnk)
-    ops.split_tf32(Bnk, bh, bl)
+    bh = dev(k.reshape(4 * cout, cin))
+    bl = torch.empty_like(bh)
+    ops.split_tf32(bh, None, bl)
     concat = torch.zeros((n, 2 * h, 2 * w, 2 * cout), device="cuda")
     drop = ops.make_dropout(rate, 5, ctot=2 * cout, c0=0)
     ops.gemm(dev(x), bh, concat[..., :cout], b_trans=True, B_lo=bl, epilogue=ops.EPI_CONVT, shift=dev(b), convt_hw=(h, w), drop=drop,

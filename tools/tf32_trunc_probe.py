@@ -13,10 +13,13 @@ a = torch.randn(M, K, device="cuda")
 b = torch.randn(N, K, device="cuda") / K ** 0.5
 ref = a.double() @ b.double().T
 c = torch.empty(M, N, device="cuda")
-hi, lo = torch.empty_like(b), torch.empty_like(b)
+lo = torch.empty_like(b)
+ops.split_tf32(b, None, lo)
+ops.gemm(a, b, c, b_trans=True, B_lo=lo, tensor_core=True)
+print("library split (raw b + tf32_rna(b - trunc b)): max err", float((c.double() - ref).abs().max()))
+hi = torch.empty_like(b)
 ops.split_tf32(b, hi, lo)
-ops.gemm(a, hi, c, b_trans=True, B_lo=lo, tensor_core=True)
-print("proper split      : max err", float((c.double() - ref).abs().max()))
+hi = (b.view(torch.int32) + 0x1000 & ~0x1FFF).view(torch.float32)     # rna-rounded hi
 trunc = (b.view(torch.int32) & ~0x1FFF).view(torch.float32)
 ops.gemm(a, b.clone(), c, b_trans=True, B_lo=(b - trunc).contiguous(), tensor_core=True)
 print("raw B, lo = b-trunc: max err", float((c.double() - ref).abs().max()))

@@ -42,7 +42,7 @@ class GemmArgs(C.Structure):
         ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_classes", C.c_int),
         ("A2", C.c_void_p), ("lda2", C.c_int64), ("k_split", C.c_int64),
         ("B2", C.c_void_p), ("ldb2", C.c_int64), ("n_split", C.c_int64),
-        ("A_lo", C.c_void_p), ("B_lo", C.c_void_p),
+        ("A_lo", C.c_void_p), ("lda_lo", C.c_int64), ("B_lo", C.c_void_p), ("ldb_lo", C.c_int64),
     ]
 
 

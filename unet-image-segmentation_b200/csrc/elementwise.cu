@@ -527,10 +527,14 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
   }
 }
 
-// tf32 (hi, lo) split (fp32 mode on the tensor cores): hi = cvt.rna.tf32(x), lo = x - hi
-__device__ __forceinline__ float tf32_rna(float x) {
+// tf32 (hi, lo) split (fp32 mode on the tensor cores).  tcgen05.mma.kind::tf32 reads an fp32 word and IGNORES its low 13 mantissa
+// bits (measured: tools/tf32_trunc_probe.py), so the fp32 tensor itself serves as the `hi` operand (hi = trunc13(x)) and only
+// lo = x - trunc13(x) has to be materialised; lo is rounded to nearest tf32 here so that the hardware's truncation of it does
+// not bias every product toward zero.  `hi` (optional) receives x unchanged — needed only when the split also transposes.
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);     // exact
   uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
   return __uint_as_float(u);
 }
 __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
@@ -541,9 +545,8 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t ld, int
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cv, c = (i - r * cv) << 2;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src + r * ld + c));
-    const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-    *reinterpret_cast<float4*>(hi + r * cols + c) = h;
-    *reinterpret_cast<float4*>(lo + r * cols + c) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+    if (hi) *reinterpret_cast<float4*>(hi + r * cols + c) = v;
+    *reinterpret_cast<float4*>(lo + r * cols + c) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
   }
 }
 __global__ void split_tf32_t_kernel(const float* __restrict__ src, int64_t ld, int R, int C, float* __restrict__ hi_t, float* __restrict__ lo_t) {
@@ -559,9 +562,9 @@ __global__ void split_tf32_t_kernel(const float* __restrict__ src, int64_t ld, i
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c2 = blockIdx.x * 32 + i;
     if (r2 < R && c2 < C) {
-      const float v = tile[threadIdx.x][i], h = tf32_rna(v);
-      hi_t[(int64_t)c2 * R + r2] = h;
-      lo_t[(int64_t)c2 * R + r2] = v - h;
+      const float v = tile[threadIdx.x][i];
+      if (hi_t) hi_t[(int64_t)c2 * R + r2] = v;
+      lo_t[(int64_t)c2 * R + r2] = tf32_lo(v);
     }
   }
 }
@@ -862,13 +865,13 @@ extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t
 }
 
 extern "C" int unet_split_tf32(const float* src, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo, int transpose, void* stream) {
-  UNET_REQUIRE(src && hi && lo && rows > 0 && cols > 0 && ld >= cols, UNET_EINVAL, "split_tf32: bad argument");
+  UNET_REQUIRE(src && lo && rows > 0 && cols > 0 && ld >= cols, UNET_EINVAL, "split_tf32: bad argument");
   if (transpose) {
     UNET_REQUIRE(rows < ((int64_t)1 << 31) && cols < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "split_tf32: transposed split is for weight matrices");
     dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
     launch_pdl(split_tf32_t_kernel, grid, dim3(32, 8), 0, ST, src, ld, (int)rows, (int)cols, hi, lo);
   } else {
-    UNET_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && aligned16(src) && aligned16(hi) && aligned16(lo), UNET_EALIGN,
+    UNET_REQUIRE(cols % 4 == 0 && ld % 4 == 0 && aligned16(src) && (!hi || aligned16(hi)) && aligned16(lo), UNET_EALIGN,
                  "split_tf32: needs cols%%4==0, ld%%4==0 and 16B-aligned pointers");
     const unsigned grid = (unsigned)i64min(ceil_div(rows * (cols / 4), 256), (int64_t)sm_count() * 16);
     launch_pdl(split_tf32_kernel, grid, 256, 0, ST, src, ld, rows, cols, hi, lo);

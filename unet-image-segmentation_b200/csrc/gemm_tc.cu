@@ -143,7 +143,8 @@ __device__ __forceinline__ void stats_flush(const TcParams& p, int lane, int64_t
 constexpr int kNumEpiGroups = 2;
 constexpr int kStageTileBytes = 128 * 128;       // 128 rows x 128 B
 
-// X3 (fp32 mode): operands are fp32, each given as a (hi, lo) pair of tensors with hi = tf32(x), lo = x - hi (unet_split_tf32);
+// X3 (fp32 mode): operands are fp32, each given as a (hi, lo) pair of tensors: hi = the tensor itself (kind::tf32 ignores the low
+// 13 mantissa bits, i.e. multiplies trunc(x)), lo = tf32(x - trunc(x)) from unet_split_tf32;
 // a stage holds [A_hi | A_lo] and [B_hi | B_lo] tiles of 32 k (128 B rows) and every k-step issues three kind::tf32 MMAs
 // (hi*hi + lo*hi + hi*lo): fp32-grade products (error ~2^-21 of |a||b|) at a third of the tf32 rate.
 template <int BLOCK_N, bool X3 = false> struct NtCfg {
@@ -945,7 +946,8 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;
   if (a->in_dtype == UNET_F32) {
     // fp32 mode on the tensor cores: every operand is a (hi, lo) pair from unet_split_tf32, three kind::tf32 MMAs per k-step
-    UNET_REQUIRE(a->A_lo && a->B_lo, UNET_EUNSUPPORTED, "gemm_tc: fp32 operands need their tf32 (hi, lo) split: A/B = hi parts, A_lo/B_lo = lo parts");
+    UNET_REQUIRE(a->A_lo && a->B_lo && a->lda_lo >= a->K && a->ldb_lo >= a->K, UNET_EUNSUPPORTED,
+                 "gemm_tc: fp32 operands need the lo parts of their tf32 split (A_lo, B_lo with pitches lda_lo, ldb_lo >= K)");
     UNET_REQUIRE(!a->a_trans && a->b_trans == 1 && !a->accumulate && !a->A2 && !a->B2, UNET_EUNSUPPORTED,
                  "gemm_tc: the fp32 (tf32x3) path takes C = A * B^T with B given as [N,K] and no operand concatenation");
     UNET_REQUIRE(a->out_dtype == UNET_F32 && a->epilogue != UNET_EPI_HEAD, UNET_EUNSUPPORTED, "gemm_tc: the fp32 path writes fp32 and has no fused head");
@@ -966,9 +968,9 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
     const int bn = a->N > 64 ? 128 : 64;
     CUtensorMap tmA, tmAl, tmB, tmBl, tmC;
     if (int e = make_tmap(&tmA, a->A, a->K, a->M, a->lda, kBlockM, "gemm_tc(A hi)", true)) return e;
-    if (int e = make_tmap(&tmAl, a->A_lo, a->K, a->M, a->lda, kBlockM, "gemm_tc(A lo)", true)) return e;
+    if (int e = make_tmap(&tmAl, a->A_lo, a->K, a->M, a->lda_lo, kBlockM, "gemm_tc(A lo)", true)) return e;
     if (int e = make_tmap(&tmB, a->B, a->K, a->N, a->ldb, bn, "gemm_tc(B hi)", true)) return e;
-    if (int e = make_tmap(&tmBl, a->B_lo, a->K, a->N, a->ldb, bn, "gemm_tc(B lo)", true)) return e;
+    if (int e = make_tmap(&tmBl, a->B_lo, a->K, a->N, a->ldb_lo, bn, "gemm_tc(B lo)", true)) return e;
     if (int e = make_c_tmap(&tmC, a, "gemm_tc(C)")) return e;
     cudaStream_t st = (cudaStream_t)stream;
     return bn == 128 ? launch_nt<128, false, true>(tmA, tmAl, tmB, tmC, p, st, &tmBl) : launch_nt<64, false, true>(tmA, tmAl, tmB, tmC, p, st, &tmBl);

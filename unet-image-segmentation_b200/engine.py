@@ -216,9 +216,9 @@ class UNetEngine:
                     r, c = src.shape
                     if name not in self._stage32:
                         mk = lambda *sh: torch.empty(sh, device=self.device, dtype=torch.float32)
-                        self._stage32[name] = (mk(r, c), mk(r, c))
+                        self._stage32[name] = (src, mk(r, c))                  # the kernel itself is its own `hi` operand
                         self._stage32[name + "^T"] = (mk(c, r), mk(c, r))
-                    ops.split_tf32(src, *self._stage32[name])
+                    ops.split_tf32(src, None, self._stage32[name][1])
                     ops.split_tf32(src, *self._stage32[name + "^T"], transpose=True)
         self._stage_dirty = False
 

@@ -281,24 +281,25 @@ def sepconv_fused(x: torch.Tensor, wd9c: torch.Tensor, wp_t: torch.Tensor, y: Op
 _split_ws = {}    # device index -> flat fp32 workspace for the (hi, lo) split of the A operand (fp32 mode on the tensor cores)
 
 
-def split_tf32(src: torch.Tensor, hi: torch.Tensor, lo: torch.Tensor, transpose: bool = False) -> None:
-    """hi = tf32(src) (round to nearest), lo = src - hi; hi / lo contiguous [rows, cols] ([cols, rows] with transpose)."""
+def split_tf32(src: torch.Tensor, hi: Optional[torch.Tensor], lo: torch.Tensor, transpose: bool = False) -> None:
+    """lo = tf32(src - trunc13(src)): the part of src the tensor cores drop when they read it as tf32 (src itself is the `hi`
+    operand).  hi (optional) receives src unchanged; hi / lo contiguous [rows, cols] ([cols, rows] with transpose)."""
     rows, cols, ld = _rows(src, "src")
     _f32(hi, "hi"); _f32(lo, "lo")
-    if src.dtype != torch.float32 or hi.numel() != rows * cols or lo.numel() != rows * cols:
+    if src.dtype != torch.float32 or lo.numel() != rows * cols or (hi is not None and hi.numel() != rows * cols):
         raise ValueError("split_tf32: src must be fp32 and hi / lo hold rows*cols floats")
     _call("unet_split_tf32", _p(src), ld, rows, cols, _p(hi), _p(lo), int(transpose), _stream(),
-          tag=f"{rows}x{cols}", nbytes=3 * rows * cols * 4)
+          tag=f"{rows}x{cols}", nbytes=(2 if hi is None else 3) * rows * cols * 4)
 
 
-def _a_split(A: torch.Tensor, M: int, K: int):
+def _a_split(A: torch.Tensor, M: int, K: int) -> torch.Tensor:
     dev = A.device.index or 0
     ws = _split_ws.get(dev)
-    if ws is None or ws.numel() < 2 * M * K:
-        ws = _split_ws[dev] = torch.empty(2 * M * K, device=A.device, dtype=torch.float32)
-    hi, lo = ws[: M * K].view(M, K), ws[M * K: 2 * M * K].view(M, K)
-    split_tf32(A if A.dim() == 2 else A, hi, lo)
-    return hi, lo
+    if ws is None or ws.numel() < M * K:
+        ws = _split_ws[dev] = torch.empty(M * K, device=A.device, dtype=torch.float32)
+    lo = ws[: M * K].view(M, K)
+    split_tf32(A, None, lo)
+    return lo
 
 
 def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_trans: bool = False, b_trans: bool = False,
@@ -314,8 +315,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
     CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported).
     A2 (a_trans=False): the A operand is [A | A2] along K;  B2 (a_trans=True): the B operand is [B | B2] along N
     (tensor-core path only; the first part must be a multiple of 64 columns wide).
-    B_lo: fp32 operands on the tensor cores — B is the tf32 `hi` part of the [N,K] operand and B_lo its `lo` part
-    (split_tf32); A is split into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products."""
+    B_lo: fp32 operands on the tensor cores — B_lo is the `lo` part of the [N,K] operand B (split_tf32); A's lo part is
+    written into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products."""
     ar, ac, lda = _rows(A, "A")
     br, bc, ldb = _rows(B, "B")
     M, K = (ac, ar) if a_trans else (ar, ac)
@@ -389,8 +390,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
                                            and (drop is None or (drop.ctot % 4 == 0 and drop.c0 % 4 == 0))))):
         if B_lo.dtype != torch.float32 or tuple(B_lo.shape) != tuple(B.shape) or B_lo.stride() != B.stride():
             raise ValueError("gemm: B_lo must match B (fp32, same shape and strides)")
-        hi, lo = _a_split(A, M, K)
-        args.A, args.lda, args.A_lo, args.B_lo = _p(hi), K, _p(lo), _p(B_lo)
+        lo = _a_split(A, M, K)
+        args.A_lo, args.lda_lo, args.B_lo, args.ldb_lo = _p(lo), K, _p(B_lo), ldb
         csz = Cm.numel() * 4
         _call("unet_gemm_tc", C.byref(args), _stream(),
               tag=f"{'convt' if epilogue == EPI_CONVT else 'nt'}:{M}x{N}x{K}:e{epilogue}:tf32x3",

@@ -548,6 +548,25 @@ def test_gemm_tc_fp32_tf32x3(mkn):
     np.testing.assert_allclose(cq.cpu().numpy(), (ref ** 2).sum(0), rtol=2e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("pmn", [(4096, 64, 64), (10000, 128, 256), (777, 1024, 512), (20000, 8, 64), (3000, 512, 1024), (50, 36, 72)])
+def test_gemm_tc_wgrad_fp32_tf32x3(pmn):
+    """fp32 weight gradient C[M,N] += A[P,M]^T B[P,N] on the tensor cores (both operands MN-major, tf32 split of both)."""
+    P, M, N = pmn
+    a = RNG.standard_normal((P, M)).astype(np.float32)
+    b = RNG.standard_normal((P, N)).astype(np.float32)
+    ref = a.astype(np.float64).T @ b.astype(np.float64)
+    abuf = torch.zeros((P, M + 8), device="cuda"); abuf[:, 4:4 + M] = dev(a)
+    c0 = RNG.standard_normal((M, N)).astype(np.float32)
+    c = dev(c0)
+    ops.gemm(abuf[:, 4:4 + M], dev(b), c, a_trans=True, accumulate=True, tf32x3=True, tensor_core=True)
+    got = host(c) - c0
+    assert np.abs(got - ref).max() <= 1e-5 * np.sqrt(P) + 1e-5, np.abs(got - ref).max()
+    # against the CUDA-core kernel on the same inputs
+    c2 = torch.zeros((M, N), device="cuda")
+    ops.gemm(dev(a), dev(b), c2, a_trans=True, accumulate=True)
+    np.testing.assert_allclose(got, host(c2), rtol=0, atol=1e-5 * np.sqrt(P) + 1e-5)
+
+
 @pytest.mark.parametrize("rate", [0.0, 0.2])
 @pytest.mark.parametrize("cfg", [(2, 4, 4, 128, 64), (1, 8, 16, 256, 32), (3, 6, 128, 64, 64)])
 def test_convt_tc_fp32_tf32x3(cfg, rate):

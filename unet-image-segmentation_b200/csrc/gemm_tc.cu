@@ -61,11 +61,16 @@ constexpr int kSlabPitch = 64 * 4 + 16;        // bytes per staged row: 64 fp32 
 constexpr int kSlabBytes = 32 * kSlabPitch;    // per epilogue warp
 constexpr int kNumEpiWarps = 4;
 
-template <int BLOCK_N> struct TcCfg {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+// X3 (fp32 mode): fp32 operands with their tf32 `lo` parts (see NtCfg); 32 k-rows per stage, 32-column (128-byte) chunks.
+template <int BLOCK_N, bool X3 = false> struct TcCfg {
+  static constexpr int kKRows = X3 ? 32 : 64;                  // k-rows (pixels) per stage
+  static constexpr int kChunkCols = X3 ? 32 : 64;              // elements per 128-byte chunk row
+  static constexpr int kBox = kKRows * 128;                    // one chunk: kKRows rows x 128 B
+  static constexpr int kAChunks = kBlockM / kChunkCols, kBChunks = BLOCK_N / kChunkCols;
+  static constexpr int kABytes = kAChunks * kBox * (X3 ? 2 : 1);   // X3: [hi chunks | lo chunks]
+  static constexpr int kBBytes = kBChunks * kBox * (X3 ? 2 : 1);
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7);
+  static constexpr int kStages = X3 ? (BLOCK_N == 64 ? 3 : 2) : (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 7));
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kNumEpiWarps * kSlabBytes + 256;
 };
@@ -507,15 +512,17 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------ weight-gradient kernel
 // One CTA = one (128 x BLOCK_N) tile of C and one slice of the reduction dimension P; partial products are added to C
 // with fp32 atomics.  Operands are MN-major: each 64-row (P) x 64-column box lands as an 8 KB SWIZZLE_128B chunk.
-template <int BLOCK_N>
+template <int BLOCK_N, bool X3 = false>
 __global__ void __launch_bounds__(256, 1)
-gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
+gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2, const TcParams p) {
+  static_assert(!X3 || BLOCK_N <= 128, "the tf32x3 variant uses tiles up to 128 x 128");
   pdl_launch_dependents();
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, X3>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kChunks = BLOCK_N / 64;
-  constexpr int kBoxBytes = 64 * 128;
+  constexpr int kChunks = BLOCK_N / 64;             // 64-column chunks of the accumulator (epilogue) and of the bf16 B operand
+  constexpr int kBoxBytes = Cfg::kBox;
+  constexpr int kKRows = Cfg::kKRows;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -530,12 +537,12 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int m_blk = tile / p.num_n_tiles, n_blk = tile % p.num_n_tiles;
-  const int64_t total_kb = (p.K + kBlockK - 1) / kBlockK;
+  const int64_t total_kb = (p.K + kKRows - 1) / kKRows;
   const int64_t kb_begin = (int64_t)blockIdx.y * p.kb_per_split;
   const int64_t kb_end = min(total_kb, kb_begin + p.kb_per_split);
   const int num_k = (int)i64max(0, kb_end - kb_begin);
 
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmB2); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmB2); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&tmem_full[0], 1);
@@ -555,7 +562,21 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          const int prow = (int)((kb_begin + kb) * kBlockK);
+          const int prow = (int)((kb_begin + kb) * kKRows);
+          if (X3) {          // fp32 operands: 32-column chunks; tmA2 / tmB2 are the lo tensors
+#pragma unroll
+            for (int c = 0; c < Cfg::kAChunks; ++c) {
+              tma_load_2d(smem_a + stage * Cfg::kABytes + c * kBoxBytes, &tmA, &full_bar[stage], m_blk * kBlockM + c * 32, prow, kEvictFirst);
+              tma_load_2d(smem_a + stage * Cfg::kABytes + (Cfg::kAChunks + c) * kBoxBytes, &tmA2, &full_bar[stage], m_blk * kBlockM + c * 32, prow, kEvictFirst);
+            }
+#pragma unroll
+            for (int c = 0; c < Cfg::kBChunks; ++c) {
+              tma_load_2d(smem_b + stage * Cfg::kBBytes + c * kBoxBytes, &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 32, prow, kEvictFirst);
+              tma_load_2d(smem_b + stage * Cfg::kBBytes + (Cfg::kBChunks + c) * kBoxBytes, &tmB2, &full_bar[stage], n_blk * BLOCK_N + c * 32, prow, kEvictFirst);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 2; ++c)
             tma_load_2d(smem_a + stage * Cfg::kABytes + c * kBoxBytes, &tmA, &full_bar[stage], m_blk * kBlockM + c * 64, prow, kEvictFirst);
@@ -570,13 +591,24 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(BLOCK_N, true, true);
+        constexpr uint32_t idesc = X3 ? (make_idesc_tf32(BLOCK_N) | (1u << 15) | (1u << 16)) : make_idesc(BLOCK_N, true, true);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), kBoxBytes, 1024);
           const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), kBoxBytes, 1024);
+          if (X3) {
+            const uint64_t alo = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes + Cfg::kAChunks * kBoxBytes), kBoxBytes, 1024);
+            const uint64_t blo = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes + Cfg::kBChunks * kBoxBytes), kBoxBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < kKRows / 8; ++k) {   // 8 k-rows x 128 B = 1024 B per kind::tf32 instruction
+              const uint64_t o = (uint64_t)(k * 64);
+              umma_tf32(tmem_base, alo + o, bdesc + o, idesc, (kb | k) != 0);
+              umma_tf32(tmem_base, adesc + o, blo + o, idesc, 1);
+              umma_tf32(tmem_base, adesc + o, bdesc + o, idesc, 1);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)   // 16 k-rows x 128 B = 2048 B per UMMA_K
             umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb | k) != 0);
@@ -872,23 +904,25 @@ static int launch_nt(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUte
   return UNET_OK;
 }
 
-template <int BLOCK_N>
-static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, TcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
+template <int BLOCK_N, bool X3 = false>
+static int launch_wgrad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2, TcParams& p, cudaStream_t st,
+                        const CUtensorMap* tmA2p = nullptr) {
+  using Cfg = TcCfg<BLOCK_N, X3>;
+  const CUtensorMap& tmA2 = tmA2p ? *tmA2p : tmA;
   static SmemAttrOnce once;
-  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_wgrad_kernel<BLOCK_N>, Cfg::kSmemBytes))
+  if (cudaError_t e = ensure_dynamic_smem(once, gemm_tc_wgrad_kernel<BLOCK_N, X3>, Cfg::kSmemBytes))
     return set_cuda_error(e, "gemm_tc: cudaFuncSetAttribute");
   p.num_m_tiles = (int)ceil_div(p.M, kBlockM);
   p.num_n_tiles = (int)ceil_div(p.N, BLOCK_N);
   const int64_t tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
-  const int64_t total_kb = ceil_div(p.K, kBlockK);
+  const int64_t total_kb = ceil_div(p.K, Cfg::kKRows);
   int64_t splits = i64max(1, ((int64_t)sm_count() * 2) / tiles);
   splits = i64min(splits, i64max(1, total_kb / 8));
   splits = i64min(splits, 65535);
   p.kb_per_split = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, p.kb_per_split);
   dim3 grid((unsigned)tiles, (unsigned)splits);
-  launch_pdl(gemm_tc_wgrad_kernel<BLOCK_N>, grid, 256, Cfg::kSmemBytes, st, tmA, tmB, tmB2, p);
+  launch_pdl(gemm_tc_wgrad_kernel<BLOCK_N, X3>, grid, 256, Cfg::kSmemBytes, st, tmA, tmA2, tmB, tmB2, p);
   UNET_LAUNCH_CHECK("gemm_tc_wgrad");
   return UNET_OK;
 }
@@ -946,6 +980,24 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;
   if (a->in_dtype == UNET_F32) {
     // fp32 mode on the tensor cores: every operand is a (hi, lo) pair from unet_split_tf32, three kind::tf32 MMAs per k-step
+    if (a->a_trans) {      // weight gradient C[M,N] += A[K,M]^T * B[K,N]: both operands MN-major, split over K
+      UNET_REQUIRE(a->A_lo && a->B_lo && a->lda_lo >= a->M && a->ldb_lo >= a->N, UNET_EUNSUPPORTED,
+                   "gemm_tc: fp32 operands need the lo parts of their tf32 split (A_lo, B_lo with pitches lda_lo >= M, ldb_lo >= N)");
+      UNET_REQUIRE(a->b_trans == 0 && a->accumulate == 1 && !a->A2 && !a->B2 && a->epilogue == UNET_EPI_NONE && a->out_dtype == UNET_F32,
+                   UNET_EUNSUPPORTED, "gemm_tc(fp32): a_trans=1 needs b_trans=0, accumulate=1, fp32 C and no epilogue");
+      UNET_REQUIRE(a->M % 4 == 0 && a->N % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc(fp32): wgrad needs M%%4==0 and N%%8==0");
+      TcParams p{};
+      fill_params(p, a);
+      p.split_kb = 1 << 30;
+      const int bn = a->N > 64 ? 128 : 64;
+      CUtensorMap tmA, tmAl, tmB, tmBl;
+      if (int e = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 32, "gemm_tc(wgrad A)", true)) return e;
+      if (int e = make_tmap(&tmAl, a->A_lo, a->M, a->K, a->lda_lo, 32, "gemm_tc(wgrad A lo)", true)) return e;
+      if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 32, "gemm_tc(wgrad B)", true)) return e;
+      if (int e = make_tmap(&tmBl, a->B_lo, a->N, a->K, a->ldb_lo, 32, "gemm_tc(wgrad B lo)", true)) return e;
+      cudaStream_t st = (cudaStream_t)stream;
+      return bn == 128 ? launch_wgrad<128, true>(tmA, tmB, tmBl, p, st, &tmAl) : launch_wgrad<64, true>(tmA, tmB, tmBl, p, st, &tmAl);
+    }
     UNET_REQUIRE(a->A_lo && a->B_lo && a->lda_lo >= a->K && a->ldb_lo >= a->K, UNET_EUNSUPPORTED,
                  "gemm_tc: fp32 operands need the lo parts of their tf32 split (A_lo, B_lo with pitches lda_lo, ldb_lo >= K)");
     UNET_REQUIRE(!a->a_trans && a->b_trans == 1 && !a->accumulate && !a->A2 && !a->B2, UNET_EUNSUPPORTED,

@@ -553,7 +553,7 @@ class UNetEngine:
             return None
         if not folded:
             d = pl.t[prefix + "/d"]
-            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True)
+            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
             self._pw_dgrad(prefix, dz, dd)
         wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
@@ -682,7 +682,7 @@ class UNetEngine:
             if not direct:
                 ops.convt_bwd_gather(dcat[s][..., :f], gth, dbias,
                                      drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
-            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True)
+            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
             dy = S[ci][: Mi * 2 * f].view(xi.shape)
             self._convt_dgrad(s, gth, dy)
         if self.grad_hook:

@@ -292,12 +292,12 @@ def split_tf32(src: torch.Tensor, hi: Optional[torch.Tensor], lo: torch.Tensor, 
           tag=f"{rows}x{cols}", nbytes=(2 if hi is None else 3) * rows * cols * 4)
 
 
-def _a_split(A: torch.Tensor, M: int, K: int) -> torch.Tensor:
-    dev = A.device.index or 0
-    ws = _split_ws.get(dev)
-    if ws is None or ws.numel() < M * K:
-        ws = _split_ws[dev] = torch.empty(M * K, device=A.device, dtype=torch.float32)
-    lo = ws[: M * K].view(M, K)
+def _a_split(A: torch.Tensor, rows: int, cols: int, slot: int = 0) -> torch.Tensor:
+    key = (A.device.index or 0, slot)
+    ws = _split_ws.get(key)
+    if ws is None or ws.numel() < rows * cols:
+        ws = _split_ws[key] = torch.empty(rows * cols, device=A.device, dtype=torch.float32)
+    lo = ws[: rows * cols].view(rows, cols)
     split_tf32(A, None, lo)
     return lo
 
@@ -309,14 +309,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
          drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None,
          head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
          head_out: Optional[torch.Tensor] = None, A2: Optional[torch.Tensor] = None,
-         B2: Optional[torch.Tensor] = None, B_lo: Optional[torch.Tensor] = None) -> None:
+         B2: Optional[torch.Tensor] = None, B_lo: Optional[torch.Tensor] = None, tf32x3: bool = False) -> None:
     """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
     hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
     CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported).
     A2 (a_trans=False): the A operand is [A | A2] along K;  B2 (a_trans=True): the B operand is [B | B2] along N
     (tensor-core path only; the first part must be a multiple of 64 columns wide).
     B_lo: fp32 operands on the tensor cores — B_lo is the `lo` part of the [N,K] operand B (split_tf32); A's lo part is
-    written into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products."""
+    written into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products.
+    tf32x3 (a_trans=True, accumulate): the fp32 weight gradient on the tensor cores; both operands are split here."""
     ar, ac, lda = _rows(A, "A")
     br, bc, ldb = _rows(B, "B")
     M, K = (ac, ar) if a_trans else (ar, ac)
@@ -396,6 +397,15 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
         _call("unet_gemm_tc", C.byref(args), _stream(),
               tag=f"{'convt' if epilogue == EPI_CONVT else 'nt'}:{M}x{N}x{K}:e{epilogue}:tf32x3",
               nbytes=_nbytes(A, B) + csz, flops=2 * M * N * K)
+        return
+    if (tf32x3 and A.dtype == torch.float32 and tensor_core is not False and a_trans and not b_trans and accumulate
+            and A2 is None and B2 is None and epilogue == EPI_NONE and Cm is not None and Cm.dtype == torch.float32
+            and M % 4 == 0 and N % 8 == 0 and lda % 4 == 0 and ldb % 4 == 0):
+        a_lo = _a_split(A, K, M, slot=0)
+        b_lo = _a_split(B, K, N, slot=1)
+        args.A_lo, args.lda_lo, args.B_lo, args.ldb_lo = _p(a_lo), M, _p(b_lo), N
+        _call("unet_gemm_tc", C.byref(args), _stream(), tag=f"wgrad:{M}x{N}x{K}:e0:tf32x3",
+              nbytes=_nbytes(A, B) + 2 * Cm.numel() * 4, flops=2 * M * N * K)
         return
     if A.dtype == torch.float32 and tensor_core is True:
         raise ValueError("gemm: fp32 operands reach the tensor cores only as C = A * B^T with B_lo given (tf32 split) and aligned shapes")

@@ -560,11 +560,11 @@ def test_gemm_tc_wgrad_fp32_tf32x3(pmn):
     c = dev(c0)
     ops.gemm(abuf[:, 4:4 + M], dev(b), c, a_trans=True, accumulate=True, tf32x3=True, tensor_core=True)
     got = host(c) - c0
-    assert np.abs(got - ref).max() <= 1e-5 * np.sqrt(P) + 1e-5, np.abs(got - ref).max()
+    assert np.abs(got - ref).max() <= 3e-5 * np.sqrt(P) + 1e-5, np.abs(got - ref).max()     # |C| ~ 4 sqrt(P): ~7e-6 relative, fp32 atomics included
     # against the CUDA-core kernel on the same inputs
     c2 = torch.zeros((M, N), device="cuda")
     ops.gemm(dev(a), dev(b), c2, a_trans=True, accumulate=True)
-    np.testing.assert_allclose(got, host(c2), rtol=0, atol=1e-5 * np.sqrt(P) + 1e-5)
+    np.testing.assert_allclose(got, host(c2), rtol=0, atol=3e-5 * np.sqrt(P) + 1e-5)
 
 
 @pytest.mark.parametrize("rate", [0.0, 0.2])

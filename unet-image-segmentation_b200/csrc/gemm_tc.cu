@@ -21,13 +21,15 @@ int gemm_validate(const unet_gemm_args* a, const char* who);
 // Shared-memory matrix descriptor (SM100 format, version 1), SWIZZLE_128B.
 //   K-major  tile (rows x 64 bf16, 128 B per row): SBO = 1024 B (8 rows), LBO unused.
 //   MN-major tile (64 k-rows x 64 bf16 per 8 KB chunk): SBO = 1024 B (8 k-rows), LBO = chunk stride.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major tf32 tile (fp32 mode): the only layout the hardware takes is SWIZZLE_128B_BASE32B (layout type 1; TMA:
+//   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 128 B (32 fp32 along MN) x 4 k-rows, SBO = 512 B, LBO = chunk stride.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
   d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;          // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor, kind::f16: D fp32, A/B bf16, M = 128.
@@ -596,11 +598,12 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), kBoxBytes, 1024);
-          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), kBoxBytes, 1024);
+          constexpr uint32_t kSbo = X3 ? 512u : 1024u, kLay = X3 ? 1u : 2u;
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), kBoxBytes, kSbo, kLay);
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), kBoxBytes, kSbo, kLay);
           if (X3) {
-            const uint64_t alo = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes + Cfg::kAChunks * kBoxBytes), kBoxBytes, 1024);
-            const uint64_t blo = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes + Cfg::kBChunks * kBoxBytes), kBoxBytes, 1024);
+            const uint64_t alo = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes + Cfg::kAChunks * kBoxBytes), kBoxBytes, kSbo, kLay);
+            const uint64_t blo = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes + Cfg::kBChunks * kBoxBytes), kBoxBytes, kSbo, kLay);
 #pragma unroll
             for (int k = 0; k < kKRows / 8; ++k) {   // 8 k-rows x 128 B = 1024 B per kind::tf32 instruction
               const uint64_t o = (uint64_t)(k * 64);
@@ -825,7 +828,7 @@ pw_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
 // bf16 2-D tensor [outer, inner] with row pitch `ld` elements; box = {64, box_rows}; SWIZZLE_128B; OOB reads give zero
 // (f32: fp32 elements, box = {32, box_rows} — the same 128-byte rows)
 static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_rows, const char* who,
-                     bool f32 = false) {
+                     bool f32 = false, bool atom32 = false) {
   PFN_encodeTiled fn = get_encode_fn();
   UNET_REQUIRE(fn, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
   const int es = f32 ? 4 : 2;
@@ -835,8 +838,8 @@ static int make_tmap(CUtensorMap* map, const void* base, int64_t inner, int64_t 
   cuuint32_t box[2] = {f32 ? 32u : 64u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
   const CUresult r = fn(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "%s: cuTensorMapEncodeTiled failed with CUresult %d", who, (int)r);
   return UNET_OK;
 }
@@ -991,10 +994,10 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
       p.split_kb = 1 << 30;
       const int bn = a->N > 64 ? 128 : 64;
       CUtensorMap tmA, tmAl, tmB, tmBl;
-      if (int e = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 32, "gemm_tc(wgrad A)", true)) return e;
-      if (int e = make_tmap(&tmAl, a->A_lo, a->M, a->K, a->lda_lo, 32, "gemm_tc(wgrad A lo)", true)) return e;
-      if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 32, "gemm_tc(wgrad B)", true)) return e;
-      if (int e = make_tmap(&tmBl, a->B_lo, a->N, a->K, a->ldb_lo, 32, "gemm_tc(wgrad B lo)", true)) return e;
+      if (int e = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 32, "gemm_tc(wgrad A)", true, true)) return e;
+      if (int e = make_tmap(&tmAl, a->A_lo, a->M, a->K, a->lda_lo, 32, "gemm_tc(wgrad A lo)", true, true)) return e;
+      if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 32, "gemm_tc(wgrad B)", true, true)) return e;
+      if (int e = make_tmap(&tmBl, a->B_lo, a->N, a->K, a->ldb_lo, 32, "gemm_tc(wgrad B lo)", true, true)) return e;
       cudaStream_t st = (cudaStream_t)stream;
       return bn == 128 ? launch_wgrad<128, true>(tmA, tmB, tmBl, p, st, &tmAl) : launch_wgrad<64, true>(tmA, tmB, tmBl, p, st, &tmAl);
     }

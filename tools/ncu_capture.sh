@@ -3,7 +3,7 @@
 # captures of the hot kernels at the train512 level-0 shapes.  Outputs land in gpurun_out/.
 set -u
 mkdir -p gpurun_out
-B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline"
+B="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-infer"
 $B > gpurun_out/plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/ncu_launches.log 2>&1
 TAG=${1:-r02}
@@ -18,4 +18,6 @@ done
 # summarise on the box (gpurun merges at most 64 MiB back): tables into gpurun_out/profiles_out/, then keep only three reports
 UNET_PROFILES_OUT=gpurun_out/profiles_out python tools/ncu_summarize.py $TAG
 ls -la gpurun_out/*.ncu-rep
+python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --no-infer --breakdown > gpurun_out/live_bench.json 2> gpurun_out/live_breakdown.txt
+python tools/share_table.py gpurun_out/live_breakdown.txt gpurun_out/launches.csv > gpurun_out/profiles_out/shares_$TAG.md
 for f in gpurun_out/prof_*.ncu-rep; do case "$f" in *dw_bwd_mask*|*convt_dec3.ncu-rep|*pw_bneck2*) ;; *) rm -f "$f";; esac; done

@@ -74,7 +74,7 @@ if os.path.exists(path):
         tot[name][0] += 1; tot[name][1] += ms
     total = sum(v[1] for v in tot.values())
     with open(os.path.join(OUT, f"ncu_launches_{tag}.md"), "w") as o:
-        o.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` under\n"
+        o.write(f"# ncu launch list ({tag}): `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-infer` under\n"
                 "`ncu --metrics gpu__time_duration.sum --clock-control none` — every launch of 5 training steps (train512, batch 64).\n"
                 "Per-launch times are cold-cache and serialised: compare SHARES with bench.py's live CUDA-event table, not absolutes.\n\n")
         o.write(f"launches: {sum(v[0] for v in tot.values())}, total kernel time {total:.1f} ms\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")

@@ -256,11 +256,11 @@ class UNetEngine:
         else:
             ops.gemm(d, self._mat(name), out, **kw)
 
-    def _pw_dgrad(self, prefix, dz, dd):
+    def _pw_dgrad(self, prefix, dz, dd, dz_lo=None):
         name = f"{prefix}_sepconv/pointwise_kernel"
         if self.act_dtype != torch.bfloat16 and name in self._stage32:
             hi, lo = self._stage32[name]                                             # [Cin, Cout] = [N, K]
-            ops.gemm(dz, hi, dd, b_trans=True, B_lo=lo)
+            ops.gemm(dz, hi, dd, b_trans=True, B_lo=lo, A_lo=dz_lo)
             return
         B = self._stage[name] if self.act_dtype == torch.bfloat16 else self._mat(name)    # [Cin, Cout] = [N, K]
         ops.gemm(dz, B, dd, b_trans=True)
@@ -274,13 +274,13 @@ class UNetEngine:
         ops.gemm(x, B, dst, b_trans=True, epilogue=ops.EPI_CONVT, shift=self.wview(f"dec{s}_upsample/bias"),
                  convt_hw=(x.shape[1], x.shape[2]), drop=drop, B_lo=B_lo)
 
-    def _convt_dgrad(self, s, g2d, dx):
+    def _convt_dgrad(self, s, g2d, dx, g_lo=None):
         name = f"dec{s}_upsample/kernel"
         if self.act_dtype == torch.bfloat16:
             ops.gemm(g2d, self._stage[name + "^T"], dx, b_trans=True)                # B as [Cin, 4Cout] = [N, K]
         elif name + "^T" in self._stage32:
             hi, lo = self._stage32[name + "^T"]
-            ops.gemm(g2d, hi, dx, b_trans=True, B_lo=lo)
+            ops.gemm(g2d, hi, dx, b_trans=True, B_lo=lo, A_lo=g_lo)
         else:
             ops.gemm(g2d, self._mat(name), dx)                                       # B as [4Cout, Cin] = [K, N]
 
@@ -553,8 +553,10 @@ class UNetEngine:
             return None
         if not folded:
             d = pl.t[prefix + "/d"]
-            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
-            self._pw_dgrad(prefix, dz, dd)
+            # fp32 mode on the tensor cores: dz feeds both GEMMs, its tf32 `lo` part is made once
+            dz_lo = ops.tf32_lo(dz, slot=2) if (self._stage32 and dz.dtype == torch.float32 and cout % 8 == 0) else None
+            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores, B_lo=dz_lo)
+            self._pw_dgrad(prefix, dz, dd, dz_lo=dz_lo)
         wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
             # both gradients from one pass over dd (+ the producer's ReLU mask and BN-backward reductions)
@@ -682,9 +684,11 @@ class UNetEngine:
             if not direct:
                 ops.convt_bwd_gather(dcat[s][..., :f], gth, dbias,
                                      drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
-            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
+            g_lo = ops.tf32_lo(gth, slot=2) if (self._stage32 and gth.dtype == torch.float32) else None
+            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores,
+                     A_lo=g_lo)
             dy = S[ci][: Mi * 2 * f].view(xi.shape)
-            self._convt_dgrad(s, gth, dy)
+            self._convt_dgrad(s, gth, dy, g_lo=g_lo)
         if self.grad_hook:
             self.grad_hook("decoder")
         # bottleneck

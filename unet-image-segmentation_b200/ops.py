@@ -302,6 +302,13 @@ def _a_split(A: torch.Tensor, rows: int, cols: int, slot: int = 0) -> torch.Tens
     return lo
 
 
+def tf32_lo(t: torch.Tensor, slot: int) -> torch.Tensor:
+    """The tf32 `lo` part of an fp32 operand in workspace `slot` (contiguous [rows, cols]), for handing the same split to
+    several gemm calls (`A_lo=` / `B_lo=`): a gradient tensor feeds both its weight-gradient and its data-gradient GEMM."""
+    rows, cols, _ = _rows(t, "t")
+    return _a_split(t, rows, cols, slot=slot)
+
+
 def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_trans: bool = False, b_trans: bool = False,
          accumulate: bool = False, epilogue: int = EPI_NONE, scale: Optional[torch.Tensor] = None,
          shift: Optional[torch.Tensor] = None, colsum: Optional[torch.Tensor] = None,
@@ -309,7 +316,8 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
          drop: Optional[Dropout] = None, tensor_core: Optional[bool] = None,
          head_w: Optional[torch.Tensor] = None, head_b: Optional[torch.Tensor] = None,
          head_out: Optional[torch.Tensor] = None, A2: Optional[torch.Tensor] = None,
-         B2: Optional[torch.Tensor] = None, B_lo: Optional[torch.Tensor] = None, tf32x3: bool = False) -> None:
+         B2: Optional[torch.Tensor] = None, B_lo: Optional[torch.Tensor] = None, tf32x3: bool = False,
+         A_lo: Optional[torch.Tensor] = None) -> None:
     """C[M,N] (+)= op(A) op(B) with a fused epilogue.  bf16 operands go to the tcgen05 kernel when its layout rules
     hold (forward/dgrad: B given as [N,K]; weight gradient: a_trans, accumulate), everything else to the fp32-exact
     CUDA-core kernel.  `tensor_core` forces the choice (True raises if the layout is not supported).
@@ -391,7 +399,9 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
                                            and (drop is None or (drop.ctot % 4 == 0 and drop.c0 % 4 == 0))))):
         if B_lo.dtype != torch.float32 or tuple(B_lo.shape) != tuple(B.shape) or B_lo.stride() != B.stride():
             raise ValueError("gemm: B_lo must match B (fp32, same shape and strides)")
-        lo = _a_split(A, M, K)
+        lo = A_lo if A_lo is not None else _a_split(A, M, K)
+        if tuple(lo.shape) != (M, K) or not lo.is_contiguous() or lo.dtype != torch.float32:
+            raise ValueError("gemm: A_lo must be a contiguous fp32 [M, K] tensor")
         args.A_lo, args.lda_lo, args.B_lo, args.ldb_lo = _p(lo), K, _p(B_lo), ldb
         csz = Cm.numel() * 4
         _call("unet_gemm_tc", C.byref(args), _stream(),
@@ -401,8 +411,10 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
     if (tf32x3 and A.dtype == torch.float32 and tensor_core is not False and a_trans and not b_trans and accumulate
             and A2 is None and B2 is None and epilogue == EPI_NONE and Cm is not None and Cm.dtype == torch.float32
             and M % 4 == 0 and N % 8 == 0 and lda % 4 == 0 and ldb % 4 == 0):
-        a_lo = _a_split(A, K, M, slot=0)
-        b_lo = _a_split(B, K, N, slot=1)
+        a_lo = A_lo if A_lo is not None else _a_split(A, K, M, slot=0)
+        b_lo = B_lo if B_lo is not None else _a_split(B, K, N, slot=1)
+        if tuple(a_lo.shape) != (K, M) or tuple(b_lo.shape) != (K, N) or not a_lo.is_contiguous() or not b_lo.is_contiguous():
+            raise ValueError("gemm: A_lo / B_lo must be contiguous [K, M] / [K, N] tensors")
         args.A_lo, args.lda_lo, args.B_lo, args.ldb_lo = _p(a_lo), M, _p(b_lo), N
         _call("unet_gemm_tc", C.byref(args), _stream(), tag=f"wgrad:{M}x{N}x{K}:e0:tf32x3",
               nbytes=_nbytes(A, B) + 2 * Cm.numel() * 4, flops=2 * M * N * K)

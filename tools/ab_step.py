@@ -11,6 +11,7 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 B, H, W = 64, 512, 512
 VARIANTS = {
     "all on": {},
+    "direct convT bwd with dropout": {"convt_bwd_direct_drop": True},
     "no fuse_pw_bwd": {"fuse_pw_bwd": False},
     "no convt_bwd_direct": {"convt_bwd_direct": False},
     "no fold_bn_bwd": {"fold_bn_bwd": False},
@@ -28,6 +29,7 @@ for rnd in range(3):
     for name, flags in VARIANTS.items():
         for k in ("fold_bn_bwd", "defer_dropout", "fuse_dw_bwd", "fuse_bn_act", "fuse_pw_bwd", "convt_bwd_direct"):
             setattr(eng, k, flags.get(k, True))
+        eng.convt_bwd_direct_drop = flags.get("convt_bwd_direct_drop", False)
         eng.release_plans()
         for _ in range(3):
             eng.train_step(x, y)
@@ -39,4 +41,4 @@ for rnd in range(3):
         e1.record(); torch.cuda.synchronize()
         res[name].append(e0.elapsed_time(e1) / steps)
 for name, v in res.items():
-    print(f"{name:18s} " + "  ".join(f"{t:7.3f}" for t in v) + f"   min {min(v):7.3f} ms  -> {B / min(v) * 1e3:7.1f} img/s")
+    print(f"{name:30s} " + "  ".join(f"{t:7.3f}" for t in v) + f"   min {min(v):7.3f} ms  -> {B / min(v) * 1e3:7.1f} img/s")

@@ -111,6 +111,7 @@ class UNetEngine:
         self.fuse_dw_bwd = True                 # training: depthwise input + weight gradients from one pass over dy
         self.fuse_pool = True                   # inference: MaxPooling2D from the fused conv_block kernel's staged tile
         self.convt_bwd_direct = True            # training: no un-pixel-shuffle gather pass (the depthwise backward stores that layout)
+        self.convt_bwd_direct_drop = False      # ... also where the concat carries Dropout (dec2-4): the depthwise kernel then masks both halves
         self.fuse_pw_bwd = True                 # training: folded data + weight gradient of a 64-channel pointwise from one pass
         self.fold_bn_bwd = True                 # training (bf16, BN): BatchNormalization backward folded into the block's pointwise
                                                 # data / weight gradient GEMMs (no reduce / apply passes, no dz tensor) wherever the
@@ -673,7 +674,7 @@ class UNetEngine:
             # carries no Dropout (dec1, u_net.py:97: `i < len(filters)-1`): with Dropout the mask of the upsampled half is
             # cheaper in the memory-bound gather than in the issue-bound depthwise kernel (measured: +0.46 vs -0.44 ms).
             cat_drop = self._drop(f"dec{s}_dropout", 2 * f, 0) if s > 1 else None
-            direct = (self.convt_bwd_direct and self.fuse_dw_bwd and cat_drop is None
+            direct = (self.convt_bwd_direct and self.fuse_dw_bwd and (cat_drop is None or self.convt_bwd_direct_drop)
                       and f % (64 if self.act_dtype == torch.bfloat16 else 32) == 0
                       and ops.dwconv3x3_bwd_supported(cats[s], dx, dcat[s]))
             defer = (not direct) and self.defer_dropout and s > 1 and f % 64 == 0

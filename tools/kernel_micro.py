@@ -78,6 +78,18 @@ elif name in ("convt_dec4", "convt_dec3", "convt_dec2", "convt_dec4_nodrop", "co
     run(lambda: ops.gemm(x, Bt, cat[..., :cout], b_trans=True, epilogue=ops.EPI_CONVT, shift=bias, convt_hw=(hh, hh), drop=drop),
         (x.numel() + B * 4 * hh * hh * cout + Bt.numel()) * 2)
     print(f"{name}: {2 * B * hh * hh * cin * 4 * cout / 1e12:.3f} TFLOP per launch")
+elif name in ("gemm64_fp32", "gemm512_fp32", "wgrad64_fp32"):   # fp32 mode on the tensor cores (tf32x3)
+    f32 = torch.float32
+    if name == "wgrad64_fp32":
+        A, Bm, C = rnd(M // 2, 64, dtype=f32), rnd(M // 2, 64, dtype=f32), torch.zeros((64, 64), device=dev)
+        run(lambda: ops.gemm(A, Bm, C, a_trans=True, accumulate=True, tf32x3=True, tensor_core=True), 2 * (M // 2) * 64 * 4 * 2)
+    else:
+        m, k, n = (M // 2, 64, 64) if name == "gemm64_fp32" else (B * 64 * 64, 512, 512)
+        A, W, C = rnd(m, k, dtype=f32), rnd(n, k, dtype=f32), torch.empty((m, n), device=dev)
+        Wl = torch.empty_like(W); ops.split_tf32(W, None, Wl)
+        Al = ops.tf32_lo(A, slot=3)
+        run(lambda: ops.gemm(A, W, C, b_trans=True, B_lo=Wl, A_lo=Al, tensor_core=True), (2 * m * k + m * n) * 4)
+        print(f"{name}: {2 * m * k * n / 1e12:.3f} TFLOP per launch (fp32-equivalent)")
 elif name == "wgrad64":
     A, Bm, C = rnd(M, 64), rnd(M, 64), torch.zeros((64, 64), device=dev)
     run(lambda: ops.gemm(A, Bm, C, a_trans=True, accumulate=True), 2 * M * 64 * 2)

@@ -737,10 +737,8 @@ template <typename T, int CW_ = 1, int PXT_ = 24> struct BwCfg {
   // 4-row window of shared loads without spilling (512 threads would cap at 128)
   static constexpr int TW = PXT * CW, RH = 4;
   static constexpr int kThreads = PXT * 16;
-#ifndef UNET_BW_THREADS_PER_SM
-#define UNET_BW_THREADS_PER_SM 384
-#endif
-  static constexpr int kMinBlocks = UNET_BW_THREADS_PER_SM / kThreads;
+  // (4 CTAs / 128 registers per thread was measured in round 2: the ~40 spilled registers double the kernel's time)
+  static constexpr int kMinBlocks = 384 / kThreads;
   static constexpr int kDBytes = RH * (TW + 2) * 128;
   static constexpr int kXBytes = RH * TW * 128;
   static constexpr int kStageBytes = kDBytes + kXBytes;

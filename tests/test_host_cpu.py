@@ -314,7 +314,8 @@ def test_shard_range_covers_everything():
 
 
 def test_host_copy_paths():
-    """predict()'s staging copy: NumPy path below 8 MB, torch (all CPU threads) above, dtype conversion, tensor/array mixes"""
+    """predict()'s staging copy: NumPy path below 8 MB, torch (this process's share of the CPU threads, also when torchrun pinned
+    OMP_NUM_THREADS=1) above, dtype conversion, tensor/array mixes"""
     import torch
     from unet_b200.keras_api import _host_copy
     rng = np.random.default_rng(3)

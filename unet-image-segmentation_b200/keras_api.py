@@ -324,15 +324,38 @@ class Layer:
 
 
 # ====================================================================================================== input prefetch
+_COPY_THREADS = None
+
+
+def _copy_threads() -> int:
+    """torch's CPU copy kernel is the staging memcpy (measured on the B200 host: 12.8 GB/s on one thread, 50 GB/s on 16; a
+    Python thread pool over np.copyto is slower than ONE thread).  torchrun exports OMP_NUM_THREADS=1, which would leave a 268 MB
+    batch to a single thread: on first use give torch this process's share of the host cores."""
+    global _COPY_THREADS
+    if _COPY_THREADS is None:
+        import torch
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+        want = max(1, min(32, cores // local_world))
+        if torch.get_num_threads() < want:
+            torch.set_num_threads(want)
+        _COPY_THREADS = torch.get_num_threads()
+    return _COPY_THREADS
+
+
 def _host_copy(dst, src) -> None:
-    """Host-to-host copy (with dtype conversion) between NumPy arrays / CPU tensors on all of torch's CPU threads: one thread
-    moves ~10 GB/s, which would cap `predict` of 512x512 batches below what the GPU and PCIe sustain."""
+    """Host-to-host copy (with dtype conversion) between NumPy arrays / CPU tensors on all of this process's CPU threads: one
+    thread moves ~10 GB/s, which would cap `predict` of 512x512 batches below what the GPU and PCIe sustain."""
     import torch
     nbytes = src.numel() * src.element_size() if isinstance(src, torch.Tensor) else src.nbytes
     if nbytes < (8 << 20):                             # small batches: the thread fan-out costs more than it saves
         np.copyto(dst.numpy() if isinstance(dst, torch.Tensor) else dst, src.numpy() if isinstance(src, torch.Tensor) else src,
                   casting="unsafe")
         return
+    _copy_threads()
     try:
         d = dst if isinstance(dst, torch.Tensor) else torch.from_numpy(dst)
         s_ = src if isinstance(src, torch.Tensor) else torch.from_numpy(src if src.flags.writeable else src.copy())
@@ -544,7 +567,7 @@ class Model:
         host, dev, ev = slot
         if ev is not None:
             ev.synchronize()          # the previous H2D out of this pinned buffer has landed (does not wait for compute)
-        np.copyto(host.numpy(), a, casting="unsafe")
+        _host_copy(host, a)
         dev.copy_(host, non_blocking=True)
         slot[2] = torch.cuda.Event()
         slot[2].record()

@@ -115,6 +115,34 @@ def test_callbacks_follow_keras_rules(tmp_path):
     assert "learning_rate" in logs
 
 
+def test_tensorboard_scalars_and_histograms(tmp_path):
+    """TensorBoard(log_dir, histogram_freq=1) as scripts/train.py:299-302 builds it: scalar events for train / validation runs and
+    one weight histogram per variable per epoch, readable by tensorboard's own event reader."""
+    pytest.importorskip("tensorboard")
+    from tensorboard.backend.event_processing.event_file_loader import EventFileLoader
+    from unet_b200.keras_api import TensorBoard
+
+    class M:
+        def get_weights_dict(self):
+            return {"enc1_block1_bn/gamma": np.ones(64, np.float32), "output_mask/kernel": np.linspace(-1, 1, 64, dtype=np.float32).reshape(1, 1, 64, 1)}
+    tb = TensorBoard(log_dir=str(tmp_path), histogram_freq=1)
+    tb.set_model(M())
+    for ep in range(2):
+        tb.on_epoch_end(ep, {"loss": 0.5 - 0.1 * ep, "val_loss": 0.6, "val_mean_io_u": 0.4 + 0.1 * ep})
+    tb.on_train_end()
+    tags = {"train": [], "validation": []}
+    for run in tags:
+        files = [f for f in os.listdir(tmp_path / run) if "tfevents" in f]
+        assert files
+        for ev in EventFileLoader(str(tmp_path / run / files[0])).Load():
+            for v in ev.summary.value:
+                tags[run].append((ev.step, v.tag, v.WhichOneof("value")))
+    assert (0, "epoch_loss", "simple_value") in [(s, t, k) for s, t, k in tags["train"]] or any(t == "epoch_loss" for _, t, _ in tags["train"])
+    assert any(t == "epoch_mean_io_u" for _, t, _ in tags["validation"])
+    histos = [(s, t) for s, t, k in tags["train"] if t in ("enc1_block1_bn/gamma", "output_mask/kernel")]
+    assert sorted(histos) == [(0, "enc1_block1_bn/gamma"), (0, "output_mask/kernel"), (1, "enc1_block1_bn/gamma"), (1, "output_mask/kernel")]
+
+
 def test_h5lite_roundtrip_and_layout():
     from unet_b200 import h5lite
     root = h5lite.Group()

@@ -253,7 +253,8 @@ class ReduceLROnPlateau(Callback):
 
 class TensorBoard(Callback):
     """Scalar summaries per epoch in TensorBoard event-file format (`tensorboard` package if importable, else a CSV in
-    the same directory).  histogram_freq is accepted; weight histograms are not written."""
+    the same directory).  histogram_freq = n > 0 (scripts/train.py:302 passes 1): every n-th epoch the weights of every layer
+    are written as histogram summaries under the Keras tag `<layer>/<weight>` (train run)."""
 
     def __init__(self, log_dir="logs", histogram_freq=0, **_):
         self.log_dir, self.histogram_freq = str(log_dir), histogram_freq
@@ -281,6 +282,24 @@ class TensorBoard(Callback):
                                   summary=Summary(value=[Summary.Value(tag=tag, simple_value=float(v))])))
             else:
                 w.write(f"{epoch},{tag},{float(v)}\n")
+        if self.histogram_freq and (epoch + 1) % int(self.histogram_freq) == 0:
+            self._write_histograms(epoch)
+
+    def _write_histograms(self, epoch):
+        kind, w = self._writer("train")
+        if kind != "tb":
+            return
+        from tensorboard.compat.proto.event_pb2 import Event
+        from tensorboard.compat.proto.summary_pb2 import HistogramProto, Summary
+        values = []
+        for name, arr in self.model.get_weights_dict().items():
+            a = np.asarray(arr, np.float64).reshape(-1)
+            counts, edges = np.histogram(a, bins=30)
+            h = HistogramProto(min=float(a.min()), max=float(a.max()), num=int(a.size), sum=float(a.sum()),
+                               sum_squares=float((a * a).sum()), bucket_limit=[float(e) for e in edges[1:]],
+                               bucket=[float(c) for c in counts])
+            values.append(Summary.Value(tag=name, histo=h))
+        w.add_event(Event(wall_time=time.time(), step=epoch, summary=Summary(value=values)))
 
     def on_train_end(self, logs=None):
         for kind, w in self._writers.values():

@@ -42,7 +42,9 @@ int sm_count();
 //   UNET_B200_PDL=1            attribute + early trigger: 56.03 / 55.95 ms per step (-1.7 %): programmatic edges cost more per
 //                              graph node than the ~195 kernel boundaries of the step give back; inference 512x512 is unchanged
 //                              within run-to-run noise (11.45 / 11.63 vs 11.88 / 11.60 ms).
-// Kept because eager (non-graph) launch sequences can profit; off where it was measured to lose.
+//                              Eager launches of the same step: 55.79 / 56.02 ms without, 56.45 / 56.50 ms with (-1 %): the
+//                              dependents' early CTAs take SM slots from the tail of the kernel they wait for.
+// Kept as a switch (every kernel has the wait in place, so a future longer-tailed schedule can turn it on); off where it lost.
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -58,8 +58,13 @@ template <int BLOCK_N> struct FsCfg {
   // the stage ring bounds the number of patches in flight per SM (a stage is held from its TMA until the MMA that read its
   // pointwise-kernel slice retires): 4 stages where they fit in 227 KB
   static constexpr int kStages = BLOCK_N == 64 ? 4 : 3;
+  // A-tile buffers per producer group.  ncu (r02) shows 40 % of the producers' stall samples waiting for their A tile to be
+  // released, so a second buffer per group was tried (BLOCK_N = 64, paid for with the fourth TMA stage): SLOWER — 0.973 vs
+  // 0.950 ms at 64->64 and 1.63 vs 1.45 ms at 128->64 (512x512, batch 64).  The wait is the pipeline's slack, not its limit;
+  // the patches in flight (TMA stages) matter more.  Kept at one.
+  static constexpr int kABufs = 1;
   static constexpr int kHeadFloats = BLOCK_N == 64 ? 8 * 64 + 8 : 0;     // fused output head: w[class][64] + bias[8], per group
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + 2 * kABufs * kTileBytes /*A*/ + 2 * kTileBytes /*staging*/ +
                                     2 * kPoolBytes /*pooled staging*/ +
                                     2 * (2 * BLOCK_N + kHeadFloats) * 4 /*scale,shift[,head] per group*/ +
                                     9 * kMaxCin * 4 /*dw weights*/ + 256;
@@ -84,19 +89,20 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stages = smem;
-  uint8_t* a_tiles = stages + S * Cfg::kStageBytes;                  // [2][16 KB]
-  uint8_t* out_tiles = a_tiles + 2 * kTileBytes;                     // [group][16 KB]
+  constexpr int NA = Cfg::kABufs;
+  uint8_t* a_tiles = stages + S * Cfg::kStageBytes;                  // [group][NA][16 KB]
+  uint8_t* out_tiles = a_tiles + 2 * NA * kTileBytes;                // [group][16 KB]
   uint8_t* pool_tiles = out_tiles + 2 * kTileBytes;                  // [group][4 KB]
   float* s_par = reinterpret_cast<float*>(pool_tiles + 2 * kPoolBytes);  // [group][2][BLOCK_N]
   float* s_wd = s_par + 2 * (2 * BLOCK_N + Cfg::kHeadFloats);        // [9][Cin]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_wd + 9 * kMaxCin);
   uint64_t* ld_full = bars;              // [S]
   uint64_t* x_empty = bars + S;          // [S]
-  uint64_t* a_full = bars + 2 * S;       // [2]
-  uint64_t* a_empty = bars + 2 * S + 2;  // [2]
-  uint64_t* tmem_full = bars + 2 * S + 4;
-  uint64_t* tmem_empty = bars + 2 * S + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 8);
+  uint64_t* a_full = bars + 2 * S;            // [group][NA]
+  uint64_t* a_empty = bars + 2 * S + 2 * NA;  // [group][NA]
+  uint64_t* tmem_full = bars + 2 * S + 4 * NA;
+  uint64_t* tmem_empty = bars + 2 * S + 4 * NA + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 * NA + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = p.num_k;
@@ -104,10 +110,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmY); tma_prefetch_desc(&tmP); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&ld_full[i], 1); mbar_init(&x_empty[i], 5); }   // 4 producer warps + the MMA commit
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1);
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
-    }
+    for (int i = 0; i < 2 * NA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(tmem_ptr, 2 * BLOCK_N); tmem_relinquish(); }
@@ -139,13 +143,16 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     // ===================================================================== MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = fs_idesc(BLOCK_N);
-      int s = 0; uint32_t ph = 0; int ai = 0; uint32_t aph = 0; int it = 0;
+      int s = 0; uint32_t ph = 0; int step = 0; int it = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_k; ++kb) {
+          // step = global (tile, channel block) counter: group step & 1 produced it, into that group's buffer (step >> 1) % NA
+          const int ai = (step & 1) * NA + ((step >> 1) % NA);
+          const uint32_t aph = (uint32_t)((step >> 1) / NA) & 1u;
           mbar_wait(&ld_full[s], ph);            // pointwise-kernel slice has landed
           mbar_wait(&a_full[ai], aph);           // depthwise tile is complete and visible to the async proxy
           tc_fence_after();
@@ -157,7 +164,7 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           umma_commit(&x_empty[s]);
           if (kb == num_k - 1) umma_commit(&tmem_full[acc]);
           if (++s == S) { s = 0; ph ^= 1; }
-          if (++ai == 2) { ai = 0; aph ^= 1; }
+          ++step;
         }
       }
     }
@@ -170,10 +177,10 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     const int t = ((warp - 4) & 3) * 32 + lane;
     const int cp = t >> 4, cg = t & 15;                   // column pair (patch columns 2cp, 2cp+1), 4-channel group
     const uint32_t x_off = (uint32_t)(2 * cp) * 128u + (uint32_t)cg * 8u;
-    const uint32_t at_s = smem_u32(a_tiles + g * kTileBytes);
+    const uint32_t at_base = smem_u32(a_tiles + g * NA * kTileBytes);
     float2 k9[9][2];                            // fp32 pairs: every FMA below is a packed FFMA2
     int k9_kb = -1;
-    uint32_t aph = 0;
+    int mine = 0;                               // steps this group has produced
     int step = 0;                               // global (tile, channel block) counter; this group takes step % 2 == g
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < num_k; ++kb, ++step) {
@@ -190,8 +197,11 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             } else { k9[i][0] = k9[i][1] = make_float2(0.f, 0.f); }
           }
         }
+        const int ab = mine % NA;                // this group's buffer for this step
+        const uint32_t aph = (uint32_t)(mine / NA) & 1u;
+        const uint32_t at_s = at_base + (uint32_t)ab * kTileBytes;
         mbar_wait(&ld_full[s], ph);
-        mbar_wait(&a_empty[g], aph ^ 1);
+        mbar_wait(&a_empty[g * NA + ab], aph ^ 1);
         const uint32_t xs = smem_u32(stages + s * Cfg::kStageBytes) + x_off;
         const float2 z2 = make_float2(0.f, 0.f);
         float2 prev0[2] = {z2, z2}, cur0[2] = {z2, z2}, prev1[2] = {z2, z2}, cur1[2] = {z2, z2};
@@ -236,8 +246,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         }
         fs_fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05 (async proxy)
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&a_full[g]); mbar_arrive(&x_empty[s]); }
-        aph ^= 1;
+        if (lane == 0) { mbar_arrive(&a_full[g * NA + ab]); mbar_arrive(&x_empty[s]); }
+        ++mine;
       }
     }
   } else if (warp >= 12) {

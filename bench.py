@@ -200,6 +200,13 @@ def run_reference(args):
         "e2e": {"value": round(ips, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "TensorFlow is not installable in this image (no wheel, no network): the CPU arm is the oracle's torch port",
     }
+    if mode == "train" and not args.no_infer:      # the other half of the metric, like the B200 arm's `infer` record
+        bi = cpu_sample_size("infer", H, W)
+        ips_i, sec_i = cpu_infer_sample(H, W, classes, bi, steps, warmup=min(args.warmup, 1))
+        line["infer"] = {"metric": "infer img/s", "value": round(ips_i, 3), "unit": "img/s", "ms_per_step": round(sec_i * 1e3, 2),
+                         "e2e": {"value": round(ips_i, 3), "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                         "cpu_baseline": {"value": round(ips_i, 3), "unit": "img/s", "cores": cores, "kind": "port",
+                                          "sample": f"{steps} step(s) of batch {bi} at {H}x{W}, torch-CPU fp32 port, {cores} threads"}}
     _emit(line)
 
 

@@ -122,14 +122,6 @@ __device__ __forceinline__ float bf16lo_to_f32(uint32_t u) {
   asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(d) : "r"(u));     // bytes (lsb first): 0, 0, u.b0, u.b1
   return __uint_as_float(d);
 }
-// tf32 `lo` part of an fp32 value: what tcgen05.mma.kind::tf32 drops when it reads x (it ignores the low 13 mantissa bits),
-// rounded to nearest tf32 so that the hardware's own truncation of lo does not bias products toward zero
-__device__ __forceinline__ float tf32_lo(float x) {
-  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);     // exact
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
-  return __uint_as_float(u);
-}
 // 8-byte shared-memory load through an explicit shared-window address (pointer arithmetic on the dynamic-smem base
 // otherwise degrades to generic LD)
 __device__ __forceinline__ uint2 lds64(uint32_t saddr) {

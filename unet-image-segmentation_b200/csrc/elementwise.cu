@@ -531,6 +531,12 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
 // bits (measured: tools/tf32_trunc_probe.py), so the fp32 tensor itself serves as the `hi` operand (hi = trunc13(x)) and only
 // lo = x - trunc13(x) has to be materialised; lo is rounded to nearest tf32 here so that the hardware's truncation of it does
 // not bias every product toward zero.  `hi` (optional) receives x unchanged — needed only when the split also transposes.
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float r = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);     // exact
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(r));
+  return __uint_as_float(u);
+}
 __global__ void split_tf32_kernel(const float* __restrict__ src, int64_t ld, int64_t rows, int64_t cols,
                                   float* __restrict__ hi, float* __restrict__ lo) {
   pdl_enter();

@@ -43,8 +43,6 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ void fence_proxy_async_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // ================================================================================================ kernel parameters
 struct TcParams {
   int64_t M, N, K;
@@ -537,7 +535,6 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint64_t* conv_bar = bars + 2 * kStages + 5;      // X3: lo chunks of the stage are written and visible to the async proxy
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
@@ -550,7 +547,6 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmB2); }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    if (X3) for (int i = 0; i < kStages; ++i) mbar_init(&conv_bar[i], kNumEpiWarps);
     mbar_init(&tmem_full[0], 1);
     fence_barrier_init();
   }
@@ -567,16 +563,19 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], X3 ? Cfg::kStageBytes / 2 : Cfg::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
           const int prow = (int)((kb_begin + kb) * kKRows);
-          if (X3) {          // fp32 operands, 32-column chunks: only the tensors themselves (= hi parts) are loaded; the converter warps
-                             // below write the lo chunks behind them
+          if (X3) {          // fp32 operands: 32-column chunks; tmA2 / tmB2 are the lo tensors
 #pragma unroll
-            for (int c = 0; c < Cfg::kAChunks; ++c)
+            for (int c = 0; c < Cfg::kAChunks; ++c) {
               tma_load_2d(smem_a + stage * Cfg::kABytes + c * kBoxBytes, &tmA, &full_bar[stage], m_blk * kBlockM + c * 32, prow, kEvictFirst);
+              tma_load_2d(smem_a + stage * Cfg::kABytes + (Cfg::kAChunks + c) * kBoxBytes, &tmA2, &full_bar[stage], m_blk * kBlockM + c * 32, prow, kEvictFirst);
+            }
 #pragma unroll
-            for (int c = 0; c < Cfg::kBChunks; ++c)
+            for (int c = 0; c < Cfg::kBChunks; ++c) {
               tma_load_2d(smem_b + stage * Cfg::kBBytes + c * kBoxBytes, &tmB, &full_bar[stage], n_blk * BLOCK_N + c * 32, prow, kEvictFirst);
+              tma_load_2d(smem_b + stage * Cfg::kBBytes + (Cfg::kBChunks + c) * kBoxBytes, &tmB2, &full_bar[stage], n_blk * BLOCK_N + c * 32, prow, kEvictFirst);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -597,7 +596,7 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         constexpr uint32_t idesc = X3 ? (make_idesc_tf32(BLOCK_N) | (1u << 15) | (1u << 16)) : make_idesc(BLOCK_N, true, true);
         int stage = 0; uint32_t phase = 0;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(X3 ? &conv_bar[stage] : &full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           constexpr uint32_t kSbo = X3 ? 512u : 1024u, kLay = X3 ? 1u : 2u;
           const uint64_t adesc = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), kBoxBytes, kSbo, kLay);
@@ -623,31 +622,6 @@ gemm_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     } else if (warp >= 4) {
       const int q = warp - 4;
-      if (X3) {
-        // converter: the four epilogue warps are idle until the last MMA retires, so they make the tf32 `lo` chunks of every
-        // stage in shared memory (same swizzled offsets as the hi chunks TMA just wrote: the split is elementwise) — neither a
-        // separate split pass over the operands nor a second copy of them in HBM
-        const int ctid = q * 32 + lane;
-        int stage = 0; uint32_t phase = 0;
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          const uint32_t a_s = smem_u32(smem_a + stage * Cfg::kABytes), b_s = smem_u32(smem_b + stage * Cfg::kBBytes);
-          constexpr int kAVec = Cfg::kAChunks * kBoxBytes / 16, kBVec = Cfg::kBChunks * kBoxBytes / 16;
-#pragma unroll 4
-          for (int i = ctid; i < kAVec + kBVec; i += kNumEpiWarps * 32) {
-            const bool isa = i < kAVec;
-            const uint32_t src = isa ? a_s + (uint32_t)i * 16u : b_s + (uint32_t)(i - kAVec) * 16u;
-            const uint32_t dst = src + (uint32_t)(isa ? Cfg::kAChunks : Cfg::kBChunks) * kBoxBytes;
-            const float4 v = lds128f(src);
-            sts128(dst, make_uint4(__float_as_uint(tf32_lo(v.x)), __float_as_uint(tf32_lo(v.y)),
-                                   __float_as_uint(tf32_lo(v.z)), __float_as_uint(tf32_lo(v.w))));
-          }
-          fence_proxy_async_cta();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&conv_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
-      }
       uint8_t* slab = slabs + q * kSlabBytes;
       float dummy_a[4] = {0, 0, 0, 0}, dummy_b[4] = {0, 0, 0, 0};
       mbar_wait(&tmem_full[0], 0);
@@ -1009,8 +983,9 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
   if (int e = gemm_validate(a, "gemm_tc")) return e;
   if (a->in_dtype == UNET_F32) {
     // fp32 mode on the tensor cores: every operand is a (hi, lo) pair from unet_split_tf32, three kind::tf32 MMAs per k-step
-    if (a->a_trans) {      // weight gradient C[M,N] += A[K,M]^T * B[K,N]: both operands MN-major, split over K; the tf32 lo parts
-                           // are made inside the kernel (A_lo / B_lo are not used)
+    if (a->a_trans) {      // weight gradient C[M,N] += A[K,M]^T * B[K,N]: both operands MN-major, split over K
+      UNET_REQUIRE(a->A_lo && a->B_lo && a->lda_lo >= a->M && a->ldb_lo >= a->N, UNET_EUNSUPPORTED,
+                   "gemm_tc: fp32 operands need the lo parts of their tf32 split (A_lo, B_lo with pitches lda_lo >= M, ldb_lo >= N)");
       UNET_REQUIRE(a->b_trans == 0 && a->accumulate == 1 && !a->A2 && !a->B2 && a->epilogue == UNET_EPI_NONE && a->out_dtype == UNET_F32,
                    UNET_EUNSUPPORTED, "gemm_tc(fp32): a_trans=1 needs b_trans=0, accumulate=1, fp32 C and no epilogue");
       UNET_REQUIRE(a->M % 4 == 0 && a->N % 8 == 0, UNET_EUNSUPPORTED, "gemm_tc(fp32): wgrad needs M%%4==0 and N%%8==0");
@@ -1018,11 +993,13 @@ extern "C" int unet_gemm_tc(const unet_gemm_args* a, void* stream) {
       fill_params(p, a);
       p.split_kb = 1 << 30;
       const int bn = a->N > 64 ? 128 : 64;
-      CUtensorMap tmA, tmB;
+      CUtensorMap tmA, tmAl, tmB, tmBl;
       if (int e = make_tmap(&tmA, a->A, a->M, a->K, a->lda, 32, "gemm_tc(wgrad A)", true, true)) return e;
+      if (int e = make_tmap(&tmAl, a->A_lo, a->M, a->K, a->lda_lo, 32, "gemm_tc(wgrad A lo)", true, true)) return e;
       if (int e = make_tmap(&tmB, a->B, a->N, a->K, a->ldb, 32, "gemm_tc(wgrad B)", true, true)) return e;
+      if (int e = make_tmap(&tmBl, a->B_lo, a->N, a->K, a->ldb_lo, 32, "gemm_tc(wgrad B lo)", true, true)) return e;
       cudaStream_t st = (cudaStream_t)stream;
-      return bn == 128 ? launch_wgrad<128, true>(tmA, tmB, tmB, p, st) : launch_wgrad<64, true>(tmA, tmB, tmB, p, st);
+      return bn == 128 ? launch_wgrad<128, true>(tmA, tmB, tmBl, p, st, &tmAl) : launch_wgrad<64, true>(tmA, tmB, tmBl, p, st, &tmAl);
     }
     UNET_REQUIRE(a->A_lo && a->B_lo && a->lda_lo >= a->K && a->ldb_lo >= a->K, UNET_EUNSUPPORTED,
                  "gemm_tc: fp32 operands need the lo parts of their tf32 split (A_lo, B_lo with pitches lda_lo, ldb_lo >= K)");

@@ -554,9 +554,9 @@ class UNetEngine:
             return None
         if not folded:
             d = pl.t[prefix + "/d"]
-            # fp32 mode on the tensor cores: the weight-gradient kernel splits its operands on chip; the data gradient takes dz's lo part
+            # fp32 mode on the tensor cores: dz feeds both GEMMs, its tf32 `lo` part is made once
             dz_lo = ops.tf32_lo(dz, slot=2) if (self._stage32 and dz.dtype == torch.float32 and cout % 8 == 0) else None
-            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
+            ops.gemm(d, dz, gwp, a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores, B_lo=dz_lo)
             self._pw_dgrad(prefix, dz, dd, dz_lo=dz_lo)
         wd, gwd = self._mat(f"{prefix}_sepconv/depthwise_kernel"), self._mat(f"{prefix}_sepconv/depthwise_kernel", self.g)
         if dx_out is not None and self.fuse_dw_bwd and ops.dwconv3x3_bwd_supported(x, dd, dx_out):
@@ -686,7 +686,8 @@ class UNetEngine:
                 ops.convt_bwd_gather(dcat[s][..., :f], gth, dbias,
                                      drop=self._drop(f"dec{s}_dropout", 2 * f, 0) if defer else None)
             g_lo = ops.tf32_lo(gth, slot=2) if (self._stage32 and gth.dtype == torch.float32) else None
-            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores)
+            ops.gemm(gth, xi, self._mat(f"dec{s}_upsample/kernel", self.g), a_trans=True, accumulate=True, tf32x3=self.fp32_tensor_cores,
+                     A_lo=g_lo)
             dy = S[ci][: Mi * 2 * f].view(xi.shape)
             self._convt_dgrad(s, gth, dy, g_lo=g_lo)
         if self.grad_hook:

@@ -325,7 +325,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
     (tensor-core path only; the first part must be a multiple of 64 columns wide).
     B_lo: fp32 operands on the tensor cores — B_lo is the `lo` part of the [N,K] operand B (split_tf32); A's lo part is
     written into a workspace here; three kind::tf32 MMAs per k-step give fp32-grade products.
-    tf32x3 (a_trans=True, accumulate): the fp32 weight gradient on the tensor cores (operands are split inside the kernel)."""
+    tf32x3 (a_trans=True, accumulate): the fp32 weight gradient on the tensor cores; both operands are split here."""
     ar, ac, lda = _rows(A, "A")
     br, bc, ldb = _rows(B, "B")
     M, K = (ac, ar) if a_trans else (ar, ac)
@@ -411,7 +411,11 @@ def gemm(A: torch.Tensor, B: torch.Tensor, Cm: Optional[torch.Tensor], *, a_tran
     if (tf32x3 and A.dtype == torch.float32 and tensor_core is not False and a_trans and not b_trans and accumulate
             and A2 is None and B2 is None and epilogue == EPI_NONE and Cm is not None and Cm.dtype == torch.float32
             and M % 4 == 0 and N % 8 == 0 and lda % 4 == 0 and ldb % 4 == 0):
-        # the weight-gradient kernel makes the tf32 lo parts of both operands itself (converter warps): nothing to split here
+        a_lo = A_lo if A_lo is not None else _a_split(A, K, M, slot=0)
+        b_lo = B_lo if B_lo is not None else _a_split(B, K, N, slot=1)
+        if tuple(a_lo.shape) != (K, M) or tuple(b_lo.shape) != (K, N) or not a_lo.is_contiguous() or not b_lo.is_contiguous():
+            raise ValueError("gemm: A_lo / B_lo must be contiguous [K, M] / [K, N] tensors")
+        args.A_lo, args.lda_lo, args.B_lo, args.ldb_lo = _p(a_lo), M, _p(b_lo), N
         _call("unet_gemm_tc", C.byref(args), _stream(), tag=f"wgrad:{M}x{N}x{K}:e0:tf32x3",
               nbytes=_nbytes(A, B) + 2 * Cm.numel() * 4, flops=2 * M * N * K)
         return

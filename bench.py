@@ -560,16 +560,12 @@ def main():
         return
     run_b200(args)
     try:
-        import torch.distributed as dist
-        if dist.is_initialized():
-            # the JSON line is out; never let communicator teardown hold the process (and the driver's timer) hostage
-            t = threading.Thread(target=dist.destroy_process_group, daemon=True)
-            t.start()
-            t.join(20.0)
-            if t.is_alive():
-                sys.stderr.write("bench.py: destroy_process_group did not return within 20 s; exiting\n")
-                sys.stderr.flush()
-                os._exit(0)
+        from unet_b200 import dist as D
+        # the JSON line is out; never let communicator teardown hold the process (and the driver's timer) hostage
+        if not D.shutdown(timeout_s=20.0):
+            sys.stderr.write("bench.py: destroy_process_group did not return within 20 s; exiting\n")
+            sys.stderr.flush()
+            os._exit(0)
     except Exception:
         pass
 

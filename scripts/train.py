@@ -172,6 +172,10 @@ def main(argv=None):
             best, best_epoch = float("nan"), "N/A"
         print(f"Best monitored score ({monitor_metric}): {best:.4f} (from epoch {best_epoch})")
         print(f"Best model saved to: {args.model_out}")
+        if world > 1:
+            sys.stdout.flush()
+            if not D.shutdown(model.engine):
+                os._exit(0)
     except KeyboardInterrupt:
         print("\n--- Training interrupted by user ---")
         print(f"Model state might not be saved correctly to {args.model_out} unless a checkpoint occurred.")

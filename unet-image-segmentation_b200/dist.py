@@ -36,6 +36,23 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, local_rank, world
 
 
+def shutdown(engine=None, timeout_s: float = 20.0) -> bool:
+    """Tear the process group down at the end of a run.  CUDA graphs that captured NCCL kernels must be released first
+    (communicator teardown otherwise waits on them forever), and the teardown itself is bounded: returns False when
+    destroy_process_group() did not come back within `timeout_s` (the caller should then leave with os._exit)."""
+    if engine is not None:
+        engine.release_plans()
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    if not dist.is_initialized():
+        return True
+    import threading
+    t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+    t.start()
+    t.join(timeout_s)
+    return not t.is_alive()
+
+
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous shard [lo, hi) of `n_items` units for `rank`; earlier ranks take the remainder."""
     base, rem = divmod(n_items, world)

@@ -157,12 +157,24 @@ elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
         run(lambda: ops.bn_bwd_apply(dy, z, sc, sh, mu, rs, dg, db, dz), 3 * M * 64 * 2)
     else:
         run(lambda: ops.bn_act(z, sc, sh, dz), 2 * M * 64 * 2)
-elif name in ("fused64", "fused128_64", "fused64_128"):
-    cin, cout, hh = {"fused64": (64, 64, 512), "fused128_64": (128, 64, 512), "fused64_128": (64, 128, 256)}[name]
+elif name in ("fused64", "fused64_ns", "fused64_pool", "fused64_head", "fused128_64", "fused64_128", "fused256_128", "fused128_128"):
+    # inference conv_block kernel; _ns: BatchNormalization scale folded into the pointwise kernel (what the engine runs)
+    cin, cout, hh = {"fused64": (64, 64, 512), "fused64_ns": (64, 64, 512), "fused64_pool": (64, 64, 512), "fused64_head": (64, 64, 512), "fused128_64": (128, 64, 512),
+                     "fused64_128": (64, 128, 256), "fused256_128": (256, 128, 256), "fused128_128": (128, 128, 256)}[name]
     x = rnd(B, hh, hh, cin); y = torch.empty((B, hh, hh, cout), device=dev, dtype=bf)
     wd = torch.rand((9, cin), device=dev); wpt = rnd(cout, cin)
     sc, sh = torch.rand(cout, device=dev), torch.rand(cout, device=dev)
-    run(lambda: ops.sepconv_fused(x, wd, wpt, y, scale=sc, shift=sh), (x.numel() + y.numel()) * 2)
+    if name == "fused64":
+        run(lambda: ops.sepconv_fused(x, wd, wpt, y, scale=sc, shift=sh), (x.numel() + y.numel()) * 2)
+    elif name == "fused64_head":            # dec1_block2 + output head: only the probabilities leave the chip
+        hw, hb = torch.rand((cout, 1), device=dev) - 0.5, torch.zeros(1, device=dev)
+        probs = torch.empty((B, hh, hh, 1), device=dev)
+        run(lambda: ops.sepconv_fused(x, wd, wpt, None, shift=sh, head_w=hw, head_b=hb, head_out=probs), x.numel() * 2 + probs.numel() * 4)
+    elif name == "fused64_pool":
+        pooled = torch.empty((B, hh // 2, hh // 2, cout), device=dev, dtype=bf)
+        run(lambda: ops.sepconv_fused(x, wd, wpt, y, shift=sh, pooled=pooled), (x.numel() + y.numel() + pooled.numel()) * 2)
+    else:
+        run(lambda: ops.sepconv_fused(x, wd, wpt, y, shift=sh), (x.numel() + y.numel()) * 2)
 elif name in ("head8_fwd", "head8_bwd", "head1_fwd", "head1_bwd"):
     C = 8 if "8" in name else 1
     Bh = 32

@@ -11,8 +11,12 @@
 //                 block) step: thread = (2 adjacent patch columns, 4 channels); slides down the 10 halo rows with two open
 //                 partial sums per output in registers (4 conflict-free 8-byte shared loads + 2 x 9 packed FFMA2 per row),
 //                 packs bf16 and stores into the A tile (K-major, SWIZZLE_128B) -> fence.proxy.async -> mbarrier
-//   warps 12-19   two epilogue groups (one per accumulator stage): tcgen05.ld -> scale/shift/ReLU -> bf16 -> swizzled staging
-//                 tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC destination;
+//   warps 12-19   two epilogue groups (one per accumulator stage): tcgen05.ld of the whole 64-column chunk -> accumulator stage
+//                 released -> packed scale/shift (FFMA2 / FADD2), ReLU on the bf16 conversion (cvt.rn.relu.bf16x2.f32) ->
+//                 swizzled staging tile -> one 4-D TMA store per 64-channel chunk into the (possibly channel-sliced) NHWC
+//                 destination (r02 ncu: with one 64-channel block per patch the epilogue, not the depthwise producers, set the
+//                 pace — 73 % of the epilogue warps' samples inside ~330 instructions per patch; the packed forms, the early
+//                 release and carried patch coordinates took 0.951 -> 0.891 ms at 64->64 and 1.45 -> 1.385 ms at 128->64);
 //                 optionally MaxPooling2D((2,2)) (u_net.py:69) of the staged tile -> a second 4-D TMA store of the 4x8 pooled
 //                 patch, so the encoder's skip tensor is not read back for pooling
 #include "common.cuh"
@@ -71,7 +75,7 @@ template <int BLOCK_N> struct FsCfg {
 };
 
 struct FsParams {
-  int H, W, Cin, Cout, relu;
+  int H, W, Cin, Cout;
   int tiles_h, tiles_w, total_tiles, num_k;
   const float* wd9c; const float* scale; const float* shift;
   int store_y;                                                       // 0: the activation itself is not needed (head only)
@@ -79,7 +83,14 @@ struct FsParams {
   const float* head_w; const float* head_b; float* head_out; int head_classes;   // optional fused 1x1 output head (Cout <= 64)
 };
 
-template <int BLOCK_N>
+template <bool RELU> __device__ __forceinline__ uint32_t fs_pack(float2 v) {     // bf16x2 {lo = v.x, hi = v.y}
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  return d;
+}
+
+template <int BLOCK_N, bool RELU, bool HEAD>
 __global__ void __launch_bounds__(640, 1)
 sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmP, const FsParams p) {
@@ -261,8 +272,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     float* par_scale = s_par + g * (2 * BLOCK_N + Cfg::kHeadFloats);
     float* par_shift = par_scale + BLOCK_N;
     float* par_head = par_shift + BLOCK_N;
-    constexpr bool kHeadCapable = BLOCK_N == 64;
-    const bool head = kHeadCapable && p.head_out != nullptr;
+    constexpr bool kHeadCapable = HEAD;           // the fused output head is its own instantiation (BLOCK_N = 64)
+    constexpr bool head = HEAD;
     for (int i = gtid; i < BLOCK_N; i += 128) {
       par_scale[i] = (i < p.Cout && p.scale) ? __ldg(p.scale + i) : 1.f;
       par_shift[i] = (i < p.Cout && p.shift) ? __ldg(p.shift + i) : 0.f;
@@ -277,77 +288,100 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     fs_bar_sync(1 + g, 128);
     const uint32_t sw = (uint32_t)(row & 7);
     const uint32_t my_row_s = smem_u32(buf) + (uint32_t)row * 128u;
+    // patch coordinates advance by a fixed stride (2 * gridDim.x tiles): carried additions instead of two divisions per tile
+    const int stride = 2 * (int)gridDim.x;
+    const int st_w = stride % p.tiles_w, st_h = (stride / p.tiles_w) % p.tiles_h, st_n = stride / (p.tiles_w * p.tiles_h);
+    int tile = blockIdx.x + g * gridDim.x;
+    int wb = tile % p.tiles_w, hb = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
     int it = g;
-    for (int tile = blockIdx.x + g * gridDim.x; tile < p.total_tiles; tile += 2 * gridDim.x, it += 2) {
-      const int wb = tile % p.tiles_w; const int t2 = tile / p.tiles_w;
-      const int hb = t2 % p.tiles_h; const int n = t2 / p.tiles_h;
+    for (; tile < p.total_tiles; tile += stride, it += 2) {
       mbar_wait(&tmem_full[g], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + g * BLOCK_N;
       float hacc[kHeadCapable ? 8 : 1];
 #pragma unroll
       for (int i = 0; i < (kHeadCapable ? 8 : 1); ++i) hacc[i] = 0.f;
+      float2 h1a = make_float2(0.f, 0.f), h1b = h1a;
 #pragma unroll
       for (int c = 0; c < BLOCK_N / 64; ++c) {
         if (c * 64 >= p.Cout) break;
+        // the whole 64-column chunk of this row goes to registers at once, so the accumulator stage is handed back to the MMA
+        // issuer before any arithmetic (the next patch's GEMM overlaps this epilogue)
+        // (the head instantiation carries up to 8 class accumulators as well: it takes the chunk in two halves)
+        uint32_t r[HEAD ? 1 : 2][32];
+        const bool last_chunk = c == BLOCK_N / 64 - 1 || (c + 1) * 64 >= p.Cout;
+        tmem_ld_32x32(t_addr + c * 64, r[0]);
+        if (!HEAD) tmem_ld_32x32(t_addr + c * 64 + 32, r[HEAD ? 0 : 1]);
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // previous store has read `buf`
         fs_bar_sync(1 + g, 128);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + c * 64 + half * 32, r);
-          tmem_ld_wait();
-          const uint32_t ps_s = smem_u32(par_scale + c * 64 + half * 32);
-          const uint32_t ph_s = smem_u32(par_shift + c * 64 + half * 32);
-          float v[32];
-          if (p.scale) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 s4 = lds128f(ps_s + i * 4);
-              const float4 h4 = lds128f(ph_s + i * 4);
-              v[i] = fmaf(__uint_as_float(r[i]), s4.x, h4.x); v[i + 1] = fmaf(__uint_as_float(r[i + 1]), s4.y, h4.y);
-              v[i + 2] = fmaf(__uint_as_float(r[i + 2]), s4.z, h4.z); v[i + 3] = fmaf(__uint_as_float(r[i + 3]), s4.w, h4.w);
-            }
-          } else {                                // scale folded into the pointwise kernel: half the broadcast shared loads
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 h4 = lds128f(ph_s + i * 4);
-              v[i] = __uint_as_float(r[i]) + h4.x; v[i + 1] = __uint_as_float(r[i + 1]) + h4.y;
-              v[i + 2] = __uint_as_float(r[i + 2]) + h4.z; v[i + 3] = __uint_as_float(r[i + 3]) + h4.w;
-            }
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (kHeadCapable && head) {             // 1x1 output convolution from the activations as they would be stored (bf16)
-#pragma unroll
-            for (int cls = 0; cls < 8; ++cls) {
-              if (cls < p.head_classes) {
-                const uint32_t hw_s = smem_u32(par_head + cls * 64 + half * 32);
-                float2 a2 = make_float2(hacc[cls], 0.f);     // fp32 activations (not re-rounded to bf16), packed FMAs
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                  const float4 w4 = lds128f(hw_s + i * 4);
-                  a2 = fma2(make_float2(v[i], v[i + 1]), make_float2(w4.x, w4.y), a2);
-                  a2 = fma2(make_float2(v[i + 2], v[i + 3]), make_float2(w4.z, w4.w), a2);
-                }
-                hacc[cls] = a2.x + a2.y;
-              }
-            }
-          }
-          if (!p.store_y) continue;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 o = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                       pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-            sts128(my_row_s + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), o);
-          }
-        }
-        if (c == BLOCK_N / 64 - 1 || (c + 1) * 64 >= p.Cout) {
+        tmem_ld_wait();
+        if (!HEAD && last_chunk) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[g]);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (HEAD && half == 1) {
+            tmem_ld_32x32(t_addr + c * 64 + 32, r[0]);
+            tmem_ld_wait();
+            if (last_chunk) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[g]);
+            }
+          }
+          const float4* sc4 = reinterpret_cast<const float4*>(par_scale + c * 64 + half * 32);
+          const float4* sh4 = reinterpret_cast<const float4*>(par_shift + c * 64 + half * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {           // 8 channels = one 16-byte chunk of the staged row
+            float2 v[4];
+            const float4 h0 = sh4[2 * j], h1 = sh4[2 * j + 1];
+            const uint32_t* rr = &r[HEAD ? 0 : half][8 * j];
+            if (p.scale) {
+              const float4 s0 = sc4[2 * j], s1 = sc4[2 * j + 1];
+              v[0] = fma2(make_float2(__uint_as_float(rr[0]), __uint_as_float(rr[1])), make_float2(s0.x, s0.y), make_float2(h0.x, h0.y));
+              v[1] = fma2(make_float2(__uint_as_float(rr[2]), __uint_as_float(rr[3])), make_float2(s0.z, s0.w), make_float2(h0.z, h0.w));
+              v[2] = fma2(make_float2(__uint_as_float(rr[4]), __uint_as_float(rr[5])), make_float2(s1.x, s1.y), make_float2(h1.x, h1.y));
+              v[3] = fma2(make_float2(__uint_as_float(rr[6]), __uint_as_float(rr[7])), make_float2(s1.z, s1.w), make_float2(h1.z, h1.w));
+            } else {                              // scale folded into the pointwise kernel: half the broadcast shared loads
+              v[0] = add2(make_float2(__uint_as_float(rr[0]), __uint_as_float(rr[1])), make_float2(h0.x, h0.y));
+              v[1] = add2(make_float2(__uint_as_float(rr[2]), __uint_as_float(rr[3])), make_float2(h0.z, h0.w));
+              v[2] = add2(make_float2(__uint_as_float(rr[4]), __uint_as_float(rr[5])), make_float2(h1.x, h1.y));
+              v[3] = add2(make_float2(__uint_as_float(rr[6]), __uint_as_float(rr[7])), make_float2(h1.z, h1.w));
+            }
+            if (kHeadCapable && head) {           // 1x1 output convolution from the fp32 activations (not re-rounded to bf16)
+              if (RELU) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+              }
+              if (p.head_classes == 1) {          // the reference's default: two open packed chains, no per-class branches
+                const float4* hw4 = reinterpret_cast<const float4*>(par_head + half * 32 + 8 * j);
+                const float4 w0 = hw4[0], w1 = hw4[1];
+                h1a = fma2(v[0], make_float2(w0.x, w0.y), h1a);
+                h1b = fma2(v[1], make_float2(w0.z, w0.w), h1b);
+                h1a = fma2(v[2], make_float2(w1.x, w1.y), h1a);
+                h1b = fma2(v[3], make_float2(w1.z, w1.w), h1b);
+              } else {
+#pragma unroll
+                for (int cls = 0; cls < 8; ++cls) {
+                  if (cls < p.head_classes) {
+                    const float4* hw4 = reinterpret_cast<const float4*>(par_head + cls * 64 + half * 32 + 8 * j);
+                    const float4 w0 = hw4[0], w1 = hw4[1];
+                    float2 a2 = fma2(v[0], make_float2(w0.x, w0.y), make_float2(hacc[cls], 0.f));
+                    a2 = fma2(v[1], make_float2(w0.z, w0.w), a2);
+                    a2 = fma2(v[2], make_float2(w1.x, w1.y), a2);
+                    a2 = fma2(v[3], make_float2(w1.z, w1.w), a2);
+                    hacc[cls] = a2.x + a2.y;
+                  }
+                }
+              }
+            }
+            if (p.store_y) {                      // ReLU rides on the bf16 conversion (cvt.rn.relu.bf16x2.f32)
+              const uint4 o = make_uint4(fs_pack<RELU>(v[0]), fs_pack<RELU>(v[1]), fs_pack<RELU>(v[2]), fs_pack<RELU>(v[3]));
+              sts128(my_row_s + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), o);
+            }
+          }
         }
         fs_fence_proxy_async();
         fs_bar_sync(1 + g, 128);
@@ -385,19 +419,22 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           const int ncls = p.head_classes;
           float* dst = p.head_out + (((int64_t)n * p.H + hh) * p.W + ww) * ncls;
           if (ncls == 1) {
-            dst[0] = 1.f / (1.f + expf(-(hacc[0] + par_head[8 * 64])));
+            dst[0] = 1.f / (1.f + expf(-((h1a.x + h1a.y) + (h1b.x + h1b.y) + par_head[8 * 64])));
           } else {
-            float mx = -INFINITY, e[8], den = 0.f;
+            float mx = -INFINITY, e[8], lg[8], den = 0.f;
 #pragma unroll
-            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { hacc[cls] += par_head[8 * 64 + cls]; mx = fmaxf(mx, hacc[cls]); }
+            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { lg[cls] = hacc[cls] + par_head[8 * 64 + cls]; mx = fmaxf(mx, lg[cls]); }
 #pragma unroll
-            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { e[cls] = expf(hacc[cls] - mx); den += e[cls]; }
+            for (int cls = 0; cls < 8; ++cls) if (cls < ncls) { e[cls] = expf(lg[cls] - mx); den += e[cls]; }
             const float inv = 1.f / den;
 #pragma unroll
             for (int cls = 0; cls < 8; ++cls) if (cls < ncls) dst[cls] = e[cls] * inv;
           }
         }
       }
+      wb += st_w; if (wb >= p.tiles_w) { wb -= p.tiles_w; ++hb; }
+      hb += st_h; if (hb >= p.tiles_h) { hb -= p.tiles_h; ++n; }
+      n += st_n;
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -420,14 +457,14 @@ static int fs_tmap_4d(CUtensorMap* map, const void* base, int64_t ld, int N, int
   return UNET_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RELU, bool HEAD = false>
 static int fs_launch(const CUtensorMap& tmX, const CUtensorMap& tmB, const CUtensorMap& tmY, const CUtensorMap& tmP, const FsParams& p, cudaStream_t st) {
   using Cfg = FsCfg<BLOCK_N>;
   static SmemAttrOnce once;
-  if (cudaError_t e = ensure_dynamic_smem(once, sepconv_fused_kernel<BLOCK_N>, Cfg::kSmemBytes))
+  if (cudaError_t e = ensure_dynamic_smem(once, sepconv_fused_kernel<BLOCK_N, RELU, HEAD>, Cfg::kSmemBytes))
     return set_cuda_error(e, "sepconv_fused: cudaFuncSetAttribute");
   const unsigned grid = (unsigned)i64min(p.total_tiles, sm_count());
-  launch_pdl(sepconv_fused_kernel<BLOCK_N>, grid, 640, Cfg::kSmemBytes, st, tmX, tmB, tmY, tmP, p);
+  launch_pdl(sepconv_fused_kernel<BLOCK_N, RELU, HEAD>, grid, 640, Cfg::kSmemBytes, st, tmX, tmB, tmY, tmP, p);
   UNET_LAUNCH_CHECK("sepconv_fused");
   return UNET_OK;
 }
@@ -471,7 +508,7 @@ extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* w
     UNET_REQUIRE(r == CUDA_SUCCESS, UNET_EDRIVER, "sepconv_fused(w): cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   }
   FsParams p{};
-  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.relu = relu;
+  p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout;
   p.tiles_h = (int)ceil_div(H, kPH); p.tiles_w = (int)ceil_div(W, kPW);
   const int64_t tiles = (int64_t)N * p.tiles_h * p.tiles_w;
   UNET_REQUIRE(tiles < ((int64_t)1 << 31), UNET_EUNSUPPORTED, "sepconv_fused: too many tiles");
@@ -481,5 +518,7 @@ extern "C" int unet_sepconv_fused_fwd(const void* x, int64_t ldx, const float* w
   p.store_pool = pooled != nullptr;
   p.head_w = head_w; p.head_b = head_b; p.head_out = head_out; p.head_classes = head_classes;
   cudaStream_t st = (cudaStream_t)stream;
-  return bn == 128 ? fs_launch<128>(tmX, tmB, tmY, tmP, p, st) : fs_launch<64>(tmX, tmB, tmY, tmP, p, st);
+  if (head_out) return relu ? fs_launch<64, true, true>(tmX, tmB, tmY, tmP, p, st) : fs_launch<64, false, true>(tmX, tmB, tmY, tmP, p, st);
+  if (relu) return bn == 128 ? fs_launch<128, true>(tmX, tmB, tmY, tmP, p, st) : fs_launch<64, true>(tmX, tmB, tmY, tmP, p, st);
+  return bn == 128 ? fs_launch<128, false>(tmX, tmB, tmY, tmP, p, st) : fs_launch<64, false>(tmX, tmB, tmY, tmP, p, st);
 }

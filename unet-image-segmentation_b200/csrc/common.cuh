@@ -175,6 +175,27 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
       : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
   return d;
 }
+// Order-pinned forms: ptxas keeps volatile asm statements in source order, so a run of these that share one operand in the
+// same position is issued back to back and the shared operand comes from the operand-reuse cache (2.25 instead of 3.0 FP32-pipe
+// cycles per FFMA2, tools/fp32_pipe_probe.cu); left to itself ptxas flags ~30 % of a depthwise kernel's FFMA2s.
+__device__ __forceinline__ float2 fma2v(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm volatile("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 mul2v(float2 a, float2 b) {
+  float2 d;
+  asm volatile("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   float2 d;
   asm("{\n\t.reg .b64 ra, rb, rd;\n\t"

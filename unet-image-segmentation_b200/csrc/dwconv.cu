@@ -269,13 +269,32 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
             for (int j = 0; j < NP; ++j) v[q][j] = make_float2(0.f, 0.f);
         }
       }
+      // the 9 FMAs per (column, channel pair) of this input row, ordered by the input column they read (the second operand of
+      // each): order-pinned FFMA2 runs that take it from the operand-reuse cache (see fma2v); same summation order as
+      // out = k8*v[q+2] + (k7*v[q+1] + (k6*v[q] + prev))
+      float2 rv[CW][NP], pn[CW][NP], cn[CW][NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+#pragma unroll
+        for (int q = 0; q < CW; ++q) { rv[q][j] = prev[q][j]; pn[q][j] = cur[q][j]; cn[q][j] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int cc = 0; cc < NQ; ++cc)
+#pragma unroll
+          for (int q = 0; q < CW; ++q) {
+            const int sft = cc - q;                 // tap column
+            if (sft < 0 || sft > 2) continue;
+            rv[q][j] = fma2v(k9[6 + sft][j], v[cc][j], rv[q][j]);
+            pn[q][j] = fma2v(k9[3 + sft][j], v[cc][j], pn[q][j]);
+            cn[q][j] = sft == 0 ? mul2v(k9[0][j], v[cc][j]) : fma2v(k9[sft][j], v[cc][j], cn[q][j]);
+          }
+      }
       if (r_in > h0 && r_in <= h1 && live) {   // output row r_in-1 is complete once kernel row 2 has seen input row r_in
 #pragma unroll
         for (int q = 0; q < CW; ++q) {
           float o[NV];
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            const float2 r = fma2(k9[8][j], v[q + 2][j], fma2(k9[7][j], v[q + 1][j], fma2(k9[6][j], v[q][j], prev[q][j])));
+            const float2 r = rv[q][j];
             o[2 * j] = r.x; o[2 * j + 1] = r.y;
           }
           if (DROP) {
@@ -295,10 +314,7 @@ dwconv3x3_strip_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
 #pragma unroll
       for (int q = 0; q < CW; ++q)
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
-          prev[q][j] = fma2(k9[5][j], v[q + 2][j], fma2(k9[4][j], v[q + 1][j], fma2(k9[3][j], v[q][j], cur[q][j])));
-          cur[q][j]  = fma2(k9[2][j], v[q + 2][j], fma2(k9[1][j], v[q + 1][j], mul2(k9[0][j], v[q][j])));
-        }
+        for (int j = 0; j < NP; ++j) { prev[q][j] = pn[q][j]; cur[q][j] = cn[q][j]; }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -893,13 +909,32 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
 #pragma unroll
       for (int q = 0; q < CW; ++q)
 #pragma unroll
-        for (int j = 0; j < NP; ++j) {
+        for (int j = 0; j < NP; ++j)
           if (xp_dead) xp[q][j] = zero2;
-          // weight gradient: dw[r][s] += x[t+r-1][w] * dy[t][w-s+1]   (d[q], d[q+1], d[q+2] = dy at columns w-1, w, w+1)
-          acc[0][j] = fma2(xm[q][j], d[q + 2][j], acc[0][j]); acc[1][j] = fma2(xm[q][j], d[q + 1][j], acc[1][j]); acc[2][j] = fma2(xm[q][j], d[q][j], acc[2][j]);
-          acc[3][j] = fma2(x0[q][j], d[q + 2][j], acc[3][j]); acc[4][j] = fma2(x0[q][j], d[q + 1][j], acc[4][j]); acc[5][j] = fma2(x0[q][j], d[q][j], acc[5][j]);
-          acc[6][j] = fma2(xp[q][j], d[q + 2][j], acc[6][j]); acc[7][j] = fma2(xp[q][j], d[q + 1][j], acc[7][j]); acc[8][j] = fma2(xp[q][j], d[q][j], acc[8][j]);
-        }
+      // All 18 FMAs per (column, channel pair) of this dy row, ordered by the dy column they read (d[c] is the second operand
+      // of every one of them): 6 / 12 / 12 / 6 order-pinned FFMA2s per dy column with CW = 2, so 32 of 36 take that operand
+      // from the operand-reuse cache.  Same summation order per accumulator as the straightforward nesting.
+      //   weight gradient: dw[r][s] += x[t+r-1][w] * dy[t][w-s+1]   (d[q], d[q+1], d[q+2] = dy at columns w-1, w, w+1)
+      //   data gradient:   rows t-1 (vv, complete after this row), t (prev), t+1 (cur) of dx gain flipped-kernel rows 2, 1, 0
+      float2 vv[CW][NP], pn[CW][NP], cn[CW][NP];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+#pragma unroll
+        for (int q = 0; q < CW; ++q) { vv[q][j] = prev[q][j]; pn[q][j] = cur[q][j]; cn[q][j] = zero2; }
+#pragma unroll
+        for (int c = 0; c < NQ; ++c)
+#pragma unroll
+          for (int q = 0; q < CW; ++q) {
+            const int sft = c - q;                  // tap column
+            if (sft < 0 || sft > 2) continue;
+            vv[q][j] = fma2v(kf[6 + sft][j], d[c][j], vv[q][j]);
+            pn[q][j] = fma2v(kf[3 + sft][j], d[c][j], pn[q][j]);
+            cn[q][j] = sft == 0 ? mul2v(kf[0][j], d[c][j]) : fma2v(kf[sft][j], d[c][j], cn[q][j]);
+            acc[2 - sft][j] = fma2v(xm[q][j], d[c][j], acc[2 - sft][j]);
+            acc[5 - sft][j] = fma2v(x0[q][j], d[c][j], acc[5 - sft][j]);
+            acc[8 - sft][j] = fma2v(xp[q][j], d[c][j], acc[8 - sft][j]);
+          }
+      }
       if ((!EDGE || (t > h0 && t <= h1)) && live) {   // dx row t-1 is complete once flipped-kernel row 2 has seen dy row t
         T* up_row = nullptr;
         if (UP && redirect)     // row (n, (t-1)/2) of the un-pixel-shuffled operand, column block ((t-1)%2, .): one wide multiply per row
@@ -909,7 +944,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
           float o[NV];
 #pragma unroll
           for (int j = 0; j < NP; ++j) {
-            float2 v = fma2(kf[8][j], d[q + 2][j], fma2(kf[7][j], d[q + 1][j], fma2(kf[6][j], d[q][j], prev[q][j])));
+            float2 v = vv[q][j];
             if (RELU_MASK) { v.x = xm[q][j].x > 0.f ? v.x : 0.f; v.y = xm[q][j].y > 0.f ? v.y : 0.f; }   // xm = x[t-1] = y of the producer
             o[2 * j] = v.x; o[2 * j + 1] = v.y;
           }
@@ -940,8 +975,7 @@ dwconv3x3_bwd_strip_kernel(const __grid_constant__ CUtensorMap tmD, const __grid
       for (int q = 0; q < CW; ++q)
 #pragma unroll
         for (int j = 0; j < NP; ++j) {
-          prev[q][j] = fma2(kf[5][j], d[q + 2][j], fma2(kf[4][j], d[q + 1][j], fma2(kf[3][j], d[q][j], cur[q][j])));
-          cur[q][j]  = fma2(kf[2][j], d[q + 2][j], fma2(kf[1][j], d[q + 1][j], mul2(kf[0][j], d[q][j])));
+          prev[q][j] = pn[q][j]; cur[q][j] = cn[q][j];
           xm[q][j] = x0[q][j]; x0[q][j] = xp[q][j];
         }
     }

@@ -233,13 +233,25 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           q1[0] = make_float2(bf16lo_to_f32(r1.x), __uint_as_float(r1.x & 0xffff0000u)); q1[1] = make_float2(bf16lo_to_f32(r1.y), __uint_as_float(r1.y & 0xffff0000u));
           q2[0] = make_float2(bf16lo_to_f32(r2.x), __uint_as_float(r2.x & 0xffff0000u)); q2[1] = make_float2(bf16lo_to_f32(r2.y), __uint_as_float(r2.y & 0xffff0000u));
           q3[0] = make_float2(bf16lo_to_f32(r3.x), __uint_as_float(r3.x & 0xffff0000u)); q3[1] = make_float2(bf16lo_to_f32(r3.y), __uint_as_float(r3.y & 0xffff0000u));
-          if (r >= 2) {
-            float2 o0[2], o1[2];
+          // the FMAs of this halo row ordered by the column they read (the second operand): order-pinned FFMA2 runs whose
+          // shared operand comes from the operand-reuse cache (see fma2v); summation order unchanged
+          float2 o0[2], o1[2], pn0[2], pn1[2], cn0[2], cn1[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              o0[j] = fma2(k9[8][j], q2[j], fma2(k9[7][j], q1[j], fma2(k9[6][j], q0[j], prev0[j])));
-              o1[j] = fma2(k9[8][j], q3[j], fma2(k9[7][j], q2[j], fma2(k9[6][j], q1[j], prev1[j])));
-            }
+          for (int j = 0; j < 2; ++j) {
+            if (r >= 2) o0[j] = fma2v(k9[6][j], q0[j], prev0[j]);
+            if (r >= 1 && r <= kXRows - 2) pn0[j] = fma2v(k9[3][j], q0[j], cur0[j]);
+            if (r <= kXRows - 3) cn0[j] = mul2v(k9[0][j], q0[j]);
+            if (r >= 2) { o0[j] = fma2v(k9[7][j], q1[j], o0[j]); o1[j] = fma2v(k9[6][j], q1[j], prev1[j]); }
+            if (r >= 1 && r <= kXRows - 2) { pn0[j] = fma2v(k9[4][j], q1[j], pn0[j]); pn1[j] = fma2v(k9[3][j], q1[j], cur1[j]); }
+            if (r <= kXRows - 3) { cn0[j] = fma2v(k9[1][j], q1[j], cn0[j]); cn1[j] = mul2v(k9[0][j], q1[j]); }
+            if (r >= 2) { o0[j] = fma2v(k9[8][j], q2[j], o0[j]); o1[j] = fma2v(k9[7][j], q2[j], o1[j]); }
+            if (r >= 1 && r <= kXRows - 2) { pn0[j] = fma2v(k9[5][j], q2[j], pn0[j]); pn1[j] = fma2v(k9[4][j], q2[j], pn1[j]); }
+            if (r <= kXRows - 3) { cn0[j] = fma2v(k9[2][j], q2[j], cn0[j]); cn1[j] = fma2v(k9[1][j], q2[j], cn1[j]); }
+            if (r >= 2) o1[j] = fma2v(k9[8][j], q3[j], o1[j]);
+            if (r >= 1 && r <= kXRows - 2) pn1[j] = fma2v(k9[5][j], q3[j], pn1[j]);
+            if (r <= kXRows - 3) cn1[j] = fma2v(k9[2][j], q3[j], cn1[j]);
+          }
+          if (r >= 2) {
             const uint32_t m = (uint32_t)((r - 2) * kPW + 2 * cp);      // GEMM rows m (column 2cp) and m + 1
             const uint32_t hi = ((uint32_t)cg & 1u) << 3;
             sts64(at_s + m * 128u + ((((uint32_t)cg >> 1) ^ (m & 7u)) << 4) + hi,
@@ -249,10 +261,8 @@ sepconv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           }
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            prev0[j] = fma2(k9[5][j], q2[j], fma2(k9[4][j], q1[j], fma2(k9[3][j], q0[j], cur0[j])));
-            prev1[j] = fma2(k9[5][j], q3[j], fma2(k9[4][j], q2[j], fma2(k9[3][j], q1[j], cur1[j])));
-            cur0[j]  = fma2(k9[2][j], q2[j], fma2(k9[1][j], q1[j], mul2(k9[0][j], q0[j])));
-            cur1[j]  = fma2(k9[2][j], q3[j], fma2(k9[1][j], q2[j], mul2(k9[0][j], q1[j])));
+            if (r >= 1 && r <= kXRows - 2) { prev0[j] = pn0[j]; prev1[j] = pn1[j]; }
+            if (r <= kXRows - 3) { cur0[j] = cn0[j]; cur1[j] = cn1[j]; }
           }
         }
         fs_fence_proxy_async();                  // generic-proxy stores -> visible to tcgen05 (async proxy)

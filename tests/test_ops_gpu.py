@@ -363,9 +363,10 @@ def test_stem_fwd_bwd(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
-def test_stem_bwd_folded(dtype):
+@pytest.mark.parametrize("nhw", [(2, 19, 37), (2, 19, 36), (1, 5, 4), (3, 8, 128)])     # W % 4 == 0: four-pixel depthwise kernel (bf16)
+def test_stem_bwd_folded(dtype, nhw):
     """streaming first-block backward: dz = A*g + B*z + K formed in registers == explicit dz fed to the tiled kernel"""
-    n, h, w = 2, 19, 37
+    n, h, w = nhw
     x = RNG.random((n, h, w, 3)).astype(np.float32)
     wd = RNG.standard_normal((3, 3, 3)).astype(np.float32); wp = RNG.standard_normal((3, 64)).astype(np.float32)
     g = RNG.standard_normal((n, h, w, 64)).astype(np.float32); z = RNG.standard_normal((n, h, w, 64)).astype(np.float32)

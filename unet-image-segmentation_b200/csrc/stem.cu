@@ -248,16 +248,25 @@ stem_pw_kernel(const float* __restrict__ d3, const float* __restrict__ wp, T* __
                   d2 = __shfl_sync(0xffffffffu, dv[u], base + 2);
       if (m >= M) continue;
       float o[8];
+      const float2 d0p = make_float2(d0, d0), d1p = make_float2(d1, d1), d2p = make_float2(d2, d2);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = fmaf(d2, w[2][j], fmaf(d1, w[1][j], d0 * w[0][j]));
-        if (!STATS) { v = fmaf(v, sa[j], sb[j]); if (relu) v = fmaxf(v, 0.f); }
-        o[j] = v;
+      for (int j = 0; j < 8; j += 2) {              // packed FFMA2: two channels per instruction, same rounding as fmaf
+        float2 v = fma2(d2p, make_float2(w[2][j], w[2][j + 1]), fma2(d1p, make_float2(w[1][j], w[1][j + 1]),
+                        mul2(d0p, make_float2(w[0][j], w[0][j + 1]))));
+        if (!STATS) {
+          v = fma2(v, make_float2(sa[j], sa[j + 1]), make_float2(sb[j], sb[j + 1]));
+          if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+        }
+        o[j] = v.x; o[j + 1] = v.y;
       }
       store8(out + m * ldo + cg * 8, o);
       if (STATS) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float r = round_to<T>(o[j]); sa[j] += r; sb[j] = fmaf(r, r, sb[j]); }
+        for (int j = 0; j < 8; j += 2) {
+          const float2 r = make_float2(round_to<T>(o[j]), round_to<T>(o[j + 1]));
+          const float2 s2 = add2(make_float2(sa[j], sa[j + 1]), r), q2 = fma2(r, r, make_float2(sb[j], sb[j + 1]));
+          sa[j] = s2.x; sa[j + 1] = s2.y; sb[j] = q2.x; sb[j + 1] = q2.y;
+        }
       }
     }
   }

@@ -300,14 +300,18 @@ head1_fwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     const uint4 raw = lds128u(sx + sl * (256 * 16));
     const float t = (y_true && sub == 0) ? lds32f(stq + sl * (256 * 4)) : 0.f;
     const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
-    float acc = 0.f;
+    // packed FFMA2 (two channels per instruction); the even / odd channel partial sums are added before the lane reduction
+    float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
-      if (aff) { v0 = fmaxf(fmaf(v0, xs[2 * q], xt[2 * q]), 0.f); v1 = fmaxf(fmaf(v1, xs[2 * q + 1], xt[2 * q + 1]), 0.f); }
-      acc = fmaf(v0, wk[2 * q], acc);
-      acc = fmaf(v1, wk[2 * q + 1], acc);
+      float2 v = make_float2(bf16lo_to_f32(u[q]), __uint_as_float(u[q] & 0xffff0000u));
+      if (aff) {
+        v = fma2(v, make_float2(xs[2 * q], xs[2 * q + 1]), make_float2(xt[2 * q], xt[2 * q + 1]));
+        v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+      }
+      acc2 = fma2(v, make_float2(wk[2 * q], wk[2 * q + 1]), acc2);
     }
+    float acc = acc2.x + acc2.y;
     acc += __shfl_xor_sync(0xffffffffu, acc, 1); acc += __shfl_xor_sync(0xffffffffu, acc, 2); acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     if (sub == 0) {
       const float pr = 1.f / (1.f + expf(-(acc + bias)));
@@ -381,13 +385,23 @@ head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
     float o[8];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v0 = __uint_as_float(u[q] << 16), v1 = __uint_as_float(u[q] & 0xffff0000u);
-      if (aff) { v0 = fmaxf(fmaf(v0, xs[2 * q], xt[2 * q]), 0.f); v1 = fmaxf(fmaf(v1, xs[2 * q + 1], xt[2 * q + 1]), 0.f); }
-      dwacc[2 * q] = fmaf(v0, dz, dwacc[2 * q]); dwacc[2 * q + 1] = fmaf(v1, dz, dwacc[2 * q + 1]);
-      float g0 = dz * wk[2 * q], g1 = dz * wk[2 * q + 1];
-      if (SUMS) { g0 = v0 > 0.f ? g0 : 0.f; g1 = v1 > 0.f ? g1 : 0.f; s1[2 * q] += g0; s1[2 * q + 1] += g1; }
-      o[2 * q] = g0; o[2 * q + 1] = g1;
+    const float2 dz2 = make_float2(dz, dz);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                   // packed FFMA2 / FMUL2 / FADD2: two channels per instruction
+      float2 v = make_float2(bf16lo_to_f32(u[q]), __uint_as_float(u[q] & 0xffff0000u));
+      if (aff) {
+        v = fma2(v, make_float2(xs[2 * q], xs[2 * q + 1]), make_float2(xt[2 * q], xt[2 * q + 1]));
+        v = make_float2(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f));
+      }
+      const float2 da = fma2(v, dz2, make_float2(dwacc[2 * q], dwacc[2 * q + 1]));
+      dwacc[2 * q] = da.x; dwacc[2 * q + 1] = da.y;
+      float2 g = mul2(dz2, make_float2(wk[2 * q], wk[2 * q + 1]));
+      if (SUMS) {
+        g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f;
+        const float2 sa = add2(make_float2(s1[2 * q], s1[2 * q + 1]), g);
+        s1[2 * q] = sa.x; s1[2 * q + 1] = sa.y;
+      }
+      o[2 * q] = g.x; o[2 * q + 1] = g.y;
     }
     store8(dx + m * 64 + sub * 8, o);
     if (sub == 0) dbs += dz;

@@ -301,7 +301,7 @@ __device__ __forceinline__ void zero8(StemRaw<float>& r) { r.a = make_float4(0.f
 __device__ __forceinline__ void unraw8(const StemRaw<__nv_bfloat16>& r, float (&v)[8]) {
   const uint32_t u[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+  for (int i = 0; i < 4; ++i) { v[2 * i] = bf16lo_to_f32(u[i]); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
 }
 __device__ __forceinline__ void unraw8(const StemRaw<float>& r, float (&v)[8]) {
   v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
@@ -483,13 +483,22 @@ stem_bwd_folded_kernel(const T* __restrict__ g, int64_t ldg, const T* __restrict
     unraw8(graw, gv); unraw8(zraw, zv);
     const float d0 = __shfl_sync(0xffffffffu, dv, base), d1 = __shfl_sync(0xffffffffu, dv, base + 1),
                 d2 = __shfl_sync(0xffffffffu, dv, base + 2);
-    float dd0 = 0.f, dd1 = 0.f, dd2 = 0.f;
+    // packed FFMA2, two channels per instruction.  A pixel past this thread's count has d0 = d1 = d2 = 0 (dv stays 0), so its
+    // dz (= K) adds nothing to gp, and its dd is not stored: no select on dz needed.
+    float2 dd0p = make_float2(0.f, 0.f), dd1p = dd0p, dd2p = dd0p;
+    const float2 d0p = make_float2(d0, d0), d1p = make_float2(d1, d1), d2p = make_float2(d2, d2);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float dz = live ? fmaf(ca[j], gv[j], fmaf(cb[j], zv[j], ck[j])) : 0.f;
-      gp[0][j] = fmaf(d0, dz, gp[0][j]); gp[1][j] = fmaf(d1, dz, gp[1][j]); gp[2][j] = fmaf(d2, dz, gp[2][j]);
-      dd0 = fmaf(dz, w[0][j], dd0); dd1 = fmaf(dz, w[1][j], dd1); dd2 = fmaf(dz, w[2][j], dd2);
+    for (int j = 0; j < 8; j += 2) {
+      const float2 dz = fma2(make_float2(ca[j], ca[j + 1]), make_float2(gv[j], gv[j + 1]),
+                             fma2(make_float2(cb[j], cb[j + 1]), make_float2(zv[j], zv[j + 1]), make_float2(ck[j], ck[j + 1])));
+      const float2 g0 = fma2(d0p, dz, make_float2(gp[0][j], gp[0][j + 1])), g1 = fma2(d1p, dz, make_float2(gp[1][j], gp[1][j + 1])),
+                   g2 = fma2(d2p, dz, make_float2(gp[2][j], gp[2][j + 1]));
+      gp[0][j] = g0.x; gp[0][j + 1] = g0.y; gp[1][j] = g1.x; gp[1][j + 1] = g1.y; gp[2][j] = g2.x; gp[2][j + 1] = g2.y;
+      dd0p = fma2(dz, make_float2(w[0][j], w[0][j + 1]), dd0p);
+      dd1p = fma2(dz, make_float2(w[1][j], w[1][j + 1]), dd1p);
+      dd2p = fma2(dz, make_float2(w[2][j], w[2][j + 1]), dd2p);
     }
+    float dd0 = dd0p.x + dd0p.y, dd1 = dd1p.x + dd1p.y, dd2 = dd2p.x + dd2p.y;
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
       dd0 += __shfl_xor_sync(0xffffffffu, dd0, o); dd1 += __shfl_xor_sync(0xffffffffu, dd1, o); dd2 += __shfl_xor_sync(0xffffffffu, dd2, o);

@@ -402,6 +402,25 @@ def test_stem_bwd_folded(dtype, nhw):
     np.testing.assert_allclose(host(gwd).reshape(3, 3, 3), gwd_ref, rtol=1e-3, atol=1e-2)
 
 
+@pytest.mark.parametrize("nhw", [(2, 6, 8), (1, 9, 36), (3, 4, 4)])
+def test_stem_depthwise_reads_stay_inside_the_image(nhw):
+    """the four-pixel depthwise kernel loads aligned 32-bit words around each pixel group: with the image embedded between
+    NaN-filled neighbours, any word taken from outside its rows would poison the result"""
+    n, h, w = nhw
+    big = torch.full((n + 2, h, w, 3), float("nan"), device="cuda", dtype=torch.bfloat16)
+    x = torch.rand((n, h, w, 3), device="cuda").to(torch.bfloat16)
+    big[1:n + 1] = x
+    wd = dev(RNG.standard_normal((9, 3))); wp = dev(RNG.standard_normal((3, 64)))
+    out_a = torch.empty((n, h, w, 64), device="cuda", dtype=torch.bfloat16); out_b = torch.empty_like(out_a)
+    d_a = torch.full((n + 2, h, w, 3), 7.0, device="cuda"); d_b = torch.empty((n, h, w, 3), device="cuda")
+    ops.stem_fwd(big[1:n + 1], wd, wp, out_a, d_out=d_a[1:n + 1])
+    ops.stem_fwd(x.clone(), wd, wp, out_b, d_out=d_b)
+    assert bool(torch.isfinite(d_a[1:n + 1]).all()) and torch.equal(d_a[1:n + 1], d_b) and torch.equal(out_a, out_b)
+    assert bool((d_a[0] == 7.0).all()) and bool((d_a[n + 1] == 7.0).all())          # and nothing is written outside either
+    ref = R.dwconv3x3(host(x).astype(np.float64), host(wd).reshape(3, 3, 3).astype(np.float64))
+    np.testing.assert_allclose(host(d_b), ref, rtol=1e-5, atol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------------ GEMM, CUDA cores
 @pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("mkn", [(70, 3, 64), (129, 40, 33), (64, 64, 1), (256, 128, 96)])

@@ -10,7 +10,7 @@ TAG=${1:-r02}
 # r02 adds the tensor-bound GEMMs of SURVEY 8d (tensor-pipe evidence) and the Conv2DTranspose / dropout variants
 for spec in "pw_bneck2:gemm_tc_nt" "pw_dec4b1:gemm_tc_nt" "pw_enc4b2:gemm_tc_nt" "convt_dec4:gemm_tc_nt" "convt_dec3:gemm_tc_nt" "convt_dec2:gemm_tc_nt" \
             "convt_dec3_nodrop:gemm_tc_nt" "gemm64:gemm_tc_nt" "dw_bwd_mask:dwconv3x3_bwd_strip" "dw_bwd_aff:dwconv3x3_bwd_strip" "dw_bwd_drop256:dwconv3x3_bwd_strip" \
-            "dw_fwd_aff:dwconv3x3_strip" "pw_bwd_fused64:pw_bwd_fused" "fused64:sepconv_fused"; do
+            "dw_fwd_aff:dwconv3x3_strip" "pw_bwd_fused64:pw_bwd_fused" "fused64:sepconv_fused" "fused128_64:sepconv_fused"; do
   name=${spec%%:*}; pat=${spec##*:}
   python tools/kernel_micro.py $name 2 > gpurun_out/plain_$name.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 -o gpurun_out/prof_$name python tools/kernel_micro.py $name 2 > gpurun_out/ncu_$name.log 2>&1

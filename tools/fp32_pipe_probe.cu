@@ -25,8 +25,9 @@ constexpr int kIters = 2048, kChains = 12;
 // MODE 1: FFMA2, acc[i] = a[i] * b[i] + acc[i]         (three distinct register pairs)
 // MODE 2: FFMA2, acc[i] = a[i] * s + acc[i]            (s shared by all: one operand can sit in the reuse cache)
 // MODE 3: FFMA, acc[i] = a[i] * s + acc[i]
+// MODE 4: FFMA, acc[i] = a[i] * c + acc[i], c a kernel parameter (constant-bank operand: only two register reads)
 template <int MODE>
-__global__ void probe(float* out, long long* cycles, const float* __restrict__ in) {
+__global__ void probe(float* out, long long* cycles, const float* __restrict__ in, float cparam) {
   // operands come from memory, so that ptxas cannot fold any of them into immediate-form instructions
   float2 acc[kChains], a[kChains], b[kChains];
 #pragma unroll
@@ -47,6 +48,7 @@ __global__ void probe(float* out, long long* cycles, const float* __restrict__ i
       if (MODE == 1) acc[i] = fma2(a[i], b[i], acc[i]);
       if (MODE == 2) acc[i] = fma2(a[i], s, acc[i]);
       if (MODE == 3) { acc[i].x = fmaf(a[i].x, s.x, acc[i].x); acc[i].y = fmaf(a[i].y, s.y, acc[i].y); }
+      if (MODE == 4) { acc[i].x = fmaf(a[i].x, cparam, acc[i].x); acc[i].y = fmaf(a[i].y, cparam, acc[i].y); }
     }
   }
   const long long t1 = clock64();
@@ -68,13 +70,13 @@ template <int MODE> static void run(const char* name, int sms) {
     long long mx = 0;
     for (int rep = 0; rep < 2; ++rep) {
       cudaMemset(cyc, 0, sizeof(long long) * sms);
-      probe<MODE><<<sms, threads>>>(out, cyc, in);
+      probe<MODE><<<sms, threads>>>(out, cyc, in, 0.999f);
       if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) { printf("%s: launch failed\n", name); return; }
       long long h[256]; cudaMemcpy(h, cyc, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
       mx = 0; for (int i = 0; i < sms; ++i) mx = h[i] > mx ? h[i] : mx;
     }
     const double fmas = 2.0 * kChains * (double)kIters * threads;        // per block = per SM (one block per SM)
-    const double instr_per_smsp = (double)kChains * kIters * (threads / 128) * ((MODE == 0 || MODE == 3) ? 2 : 1);
+    const double instr_per_smsp = (double)kChains * kIters * (threads / 128) * ((MODE == 0 || MODE == 3 || MODE == 4) ? 2 : 1);
     printf("%-36s %4d threads/SM: %6.1f FMA lanes/clk/SM, %5.2f cycles per instruction per scheduler\n", name, threads,
            fmas / (double)mx, (double)mx / instr_per_smsp);
   }
@@ -85,6 +87,7 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   const int sms = p.multiProcessorCount;
   printf("%s, %d SMs\n", p.name, sms);
+  run<4>("FFMA  a*const+c (constant bank)", sms);
   run<0>("FFMA  a*b+c, all distinct", sms);
   run<3>("FFMA  a*s+c, s shared", sms);
   run<1>("FFMA2 a*b+c, all distinct", sms);

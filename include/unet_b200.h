@@ -302,6 +302,10 @@ int unet_step_advance(float* hyper, uint32_t* counter, void* stream);
         col_scale (fp32 [C], may be NULL) multiplies column c first: the folded BatchNormalization scale of inference
         (u_net.py:23) goes into the pointwise kernel, so the GEMM epilogue only adds the shift ---- */
 int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t, int R, int C, const float* col_scale, void* stream);
+/* the same for n matrices that live in one fp32 buffer, in one launch (the engine restages every dense kernel after each
+   optimizer step).  table: DEVICE int64 [n][6] = {offset of the matrix in `base` (floats), dst address or 0, dst_t address or 0,
+   R, C, index of its first 32x32 tile}; matrices in ascending tile order; total_tiles = sum of ceil(R/32)*ceil(C/32). */
+int unet_cast_transpose_bf16_batched(const float* base, const int64_t* table, int n, int64_t total_tiles, void* stream);
 /* dst = cast(src) elementwise between fp32/bf16 (n elements) */
 int unet_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 

@@ -421,6 +421,29 @@ def test_stem_depthwise_reads_stay_inside_the_image(nhw):
     np.testing.assert_allclose(host(d_b), ref, rtol=1e-5, atol=1e-5)
 
 
+def test_cast_transpose_bf16_batched_matches_per_matrix():
+    """every dense kernel of the model staged by one launch == one launch per matrix (ragged sizes, either destination absent)"""
+    shapes = [(64, 64), (3, 64), (70, 33), (256, 128), (1, 5), (128, 1024)]
+    base = torch.randn(sum(r * c for r, c in shapes) + 7, device="cuda")
+    items, refs, off = [], [], 3
+    for k, (r, c) in enumerate(shapes):
+        dst = None if k == 2 else torch.full((r, c), 9.0, device="cuda", dtype=torch.bfloat16)
+        dst_t = None if k == 4 else torch.full((c, r), 9.0, device="cuda", dtype=torch.bfloat16)
+        items.append((off, dst, dst_t, r, c))
+        a = torch.empty((r, c), device="cuda", dtype=torch.bfloat16); at = torch.empty((c, r), device="cuda", dtype=torch.bfloat16)
+        ops.cast_transpose_bf16(base[off:off + r * c].view(r, c), a, at)
+        refs.append((a, at))
+        off += r * c
+    table, n, tiles = ops.cast_transpose_table(base, items)
+    ops.cast_transpose_bf16_batched(base, table, n, tiles)
+    for (o, dst, dst_t, r, c), (a, at) in zip(items, refs):
+        assert dst is None or torch.equal(dst, a)
+        assert dst_t is None or torch.equal(dst_t, at)
+        assert torch.equal(a, base[o:o + r * c].view(r, c).to(torch.bfloat16))
+    with pytest.raises(ValueError):
+        ops.cast_transpose_table(base, [(base.numel() - 3, None, None, 2, 2)])
+
+
 # ------------------------------------------------------------------------------------------------ GEMM, CUDA cores
 @pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, False)])
 @pytest.mark.parametrize("mkn", [(70, 3, 64), (129, 40, 33), (64, 64, 1), (256, 128, 96)])

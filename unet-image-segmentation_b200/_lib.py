@@ -86,6 +86,7 @@ _SIGNATURES = {
     "unet_adamw_step": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "unet_step_advance": [_vp, _vp, _vp],
     "unet_cast_transpose_bf16": [_vp, _vp, _vp, _i, _i, _vp, _vp],
+    "unet_cast_transpose_bf16_batched": [_vp, _vp, _i, _i64, _vp],
     "unet_cast": [_vp, _i, _vp, _i, _i64, _vp],
     "unet_preprocess_u8": [_vp, _i, _i, _i, _i64, _vp, _i, _i, _f, _vp],
     "unet_postprocess_mask": [_vp, _i, _i, _i64, _vp, _i, _i, _f, _vp],

@@ -527,6 +527,41 @@ __global__ void cast_transpose_bf16_kernel(const float* __restrict__ src, __nv_b
   }
 }
 
+// All dense kernels of the model in ONE launch (the per-step weight staging of the bf16 engine was 22 launches of a few
+// microseconds each).  `table` (DEVICE, 6 int64 per matrix): {offset of src in `base` (floats), dst address, dst_t address, R, C,
+// first tile}; a block finds its matrix by its tile index (tables are short: linear scan) and then works like the kernel above.
+__global__ void cast_transpose_bf16_batched_kernel(const float* __restrict__ base, const int64_t* __restrict__ table, int n) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  int k = 0;
+  while (k + 1 < n && (int64_t)blockIdx.x >= table[(k + 1) * 6 + 5]) ++k;
+  const int64_t* e = table + k * 6;
+  const float* src = base + e[0];
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(e[1]);
+  __nv_bfloat16* dst_t = reinterpret_cast<__nv_bfloat16*>(e[2]);
+  const int R = (int)e[3], C = (int)e[4];
+  const int t = (int)((int64_t)blockIdx.x - e[5]);
+  const int tiles_c = (C + 31) / 32;
+  const int bx = t % tiles_c, by = t / tiles_c;
+  const int c = bx * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = by * 32 + i;
+    float v = 0.f;
+    if (r < R && c < C) {
+      v = src[(int64_t)r * C + c];
+      if (dst) dst[(int64_t)r * C + c] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (!dst_t) return;
+  const int r2 = by * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c2 = bx * 32 + i;
+    if (r2 < R && c2 < C) dst_t[(int64_t)c2 * R + r2] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
 // tf32 (hi, lo) split (fp32 mode on the tensor cores).  tcgen05.mma.kind::tf32 reads an fp32 word and IGNORES its low 13 mantissa
 // bits (measured: tools/tf32_trunc_probe.py), so the fp32 tensor itself serves as the `hi` operand (hi = trunc13(x)) and only
 // lo = x - trunc13(x) has to be materialised; lo is rounded to nearest tf32 here so that the hardware's truncation of it does
@@ -861,6 +896,14 @@ extern "C" int unet_cast_transpose_bf16(const float* src, void* dst, void* dst_t
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)ceil_div(R, 32));
   launch_pdl(cast_transpose_bf16_kernel, grid, dim3(32, 8), 0, ST, src, (__nv_bfloat16*)dst, (__nv_bfloat16*)dst_t, R, C, col_scale);
   UNET_LAUNCH_CHECK("cast_transpose_bf16");
+  return UNET_OK;
+}
+
+extern "C" int unet_cast_transpose_bf16_batched(const float* base, const int64_t* table, int n, int64_t total_tiles, void* stream) {
+  UNET_REQUIRE(base && table && n > 0 && total_tiles > 0 && total_tiles < ((int64_t)1 << 31), UNET_EINVAL,
+               "cast_transpose_bf16_batched: bad argument");
+  launch_pdl(cast_transpose_bf16_batched_kernel, (unsigned)total_tiles, dim3(32, 8), 0, ST, base, table, n);
+  UNET_LAUNCH_CHECK("cast_transpose_bf16_batched");
   return UNET_OK;
 }
 

@@ -96,6 +96,7 @@ class UNetEngine:
             self._fz = torch.zeros(max(tot, 64), device=dev)
             self._fold_w: Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = {}
         self._stage: Dict[str, torch.Tensor] = {}
+        self._stage_table = None        # (device table, n, tiles) of ops.cast_transpose_bf16_batched over self.w
         self._stage32: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}    # fp32 mode: tf32 (hi, lo) parts of the dense kernels
         import os as _os
         self.fp32_tensor_cores = _os.environ.get("UNET_B200_FP32_TC", "1") != "0"   # fp32 mode: contractions as 3 x tf32 on tcgen05
@@ -198,16 +199,18 @@ class UNetEngine:
         if not self._stage_dirty:
             return
         if self.act_dtype == torch.bfloat16:
-            for name, p in self.spec.params.items():
-                leaf = name.split("/")[1]
-                if leaf == "pointwise_kernel" or (leaf == "kernel" and p.shape[0] == 2):
-                    src = self._mat(name)
-                    r, c = src.shape
-                    a = self._stage.get(name)
-                    if a is None:
+            if self._stage_table is None:     # every dense kernel in one launch: the table of (source offset, destinations) is fixed
+                items = []
+                for name, p in self.spec.params.items():
+                    leaf = name.split("/")[1]
+                    if leaf == "pointwise_kernel" or (leaf == "kernel" and p.shape[0] == 2):
+                        src = self._mat(name)
+                        r, c = src.shape
                         a = self._stage[name] = torch.empty((r, c), device=self.device, dtype=torch.bfloat16)
-                        self._stage[name + "^T"] = torch.empty((c, r), device=self.device, dtype=torch.bfloat16)
-                    ops.cast_transpose_bf16(src, a, self._stage[name + "^T"])
+                        at = self._stage[name + "^T"] = torch.empty((c, r), device=self.device, dtype=torch.bfloat16)
+                        items.append(((src.data_ptr() - self.w.data_ptr()) // 4, a, at, r, c))
+                self._stage_table = ops.cast_transpose_table(self.w, items)
+            ops.cast_transpose_bf16_batched(self.w, *self._stage_table)
         elif self.fp32_tensor_cores:
             # fp32 mode on the tensor cores: tf32 (hi, lo) parts of every dense kernel in both orientations
             for name, p in self.spec.params.items():

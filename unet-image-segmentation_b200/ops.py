@@ -668,6 +668,31 @@ def cast_transpose_bf16(src: torch.Tensor, dst: Optional[torch.Tensor], dst_t: O
     _call("unet_cast_transpose_bf16", _p(src), _p(dst), _p(dst_t), r, c, _p(col_scale), _stream())
 
 
+def cast_transpose_table(base: torch.Tensor, items) -> tuple:
+    """Device table for cast_transpose_bf16_batched.  items: [(offset of the [R, C] fp32 matrix in `base` (elements), dst or None,
+    dst_t or None, R, C)]; destinations are contiguous bf16 [R, C] / [C, R] tensors the caller keeps alive.
+    Returns (table, n, total_tiles)."""
+    rows, tile0 = [], 0
+    for off, dst, dst_t, r, c in items:
+        for t, shape in ((dst, (r, c)), (dst_t, (c, r))):
+            if t is not None and (t.dtype != torch.bfloat16 or tuple(t.shape) != shape or not t.is_contiguous()):
+                raise ValueError("cast_transpose_table: destinations must be contiguous bf16 [R, C] / [C, R]")
+        if off < 0 or off + r * c > base.numel():
+            raise ValueError("cast_transpose_table: matrix outside the source buffer")
+        rows.append([off, _p(dst) or 0, _p(dst_t) or 0, r, c, tile0])
+        tile0 += ((r + 31) // 32) * ((c + 31) // 32)
+    table = torch.tensor(rows, dtype=torch.int64, device=base.device)
+    return table, len(rows), tile0
+
+
+def cast_transpose_bf16_batched(base: torch.Tensor, table: torch.Tensor, n: int, total_tiles: int) -> None:
+    """Every matrix of a cast_transpose_table in one launch: dst = bf16(src), dst_t = bf16(src)^T."""
+    _f32(base, "base")
+    if table.dtype != torch.int64 or not table.is_contiguous() or table.numel() != 6 * n:
+        raise ValueError("cast_transpose_bf16_batched: table must be int64 [n, 6]")
+    _call("unet_cast_transpose_bf16_batched", _p(base), _p(table), n, total_tiles, _stream())
+
+
 def cast(src: torch.Tensor, dst: torch.Tensor) -> None:
     if not src.is_contiguous() or not dst.is_contiguous() or src.numel() != dst.numel():
         raise ValueError("cast: tensors must be contiguous and equal in size")

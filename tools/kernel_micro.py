@@ -147,6 +147,21 @@ elif name in ("dw_bwd", "dw_bwd_mask"):
     dx, w, sums = torch.empty_like(x), torch.rand((9, 64), device=dev), torch.zeros((2, 64), device=dev)
     mask = name.endswith("mask")
     run(lambda: ops.dwconv3x3_bwd(x, dy, w, dx, dw, relu_mask=mask, bn_sums=sums if mask else None), 3 * M * 64 * 2)
+elif name in ("bn_act_pool", "bn_act_pool_cat", "bn_act_cat", "maxpool_bwd"):
+    # encoder block2 activation: y (optionally into the skip half of the concat buffer, ld = 2C) + the 2x2 max-pooled tensor
+    z = rnd(B, H, W, 64)
+    sc, sh = torch.rand(64, device=dev), torch.rand(64, device=dev)
+    cat = torch.empty((B, H, W, 128), device=dev, dtype=bf)
+    y = cat[..., 64:] if name.endswith("cat") else torch.empty((B, H, W, 64), device=dev, dtype=bf)
+    pooled = torch.empty((B, H // 2, W // 2, 64), device=dev, dtype=bf)
+    if name == "maxpool_bwd":
+        dpool, dy, sums = rnd(B, H // 2, W // 2, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf), torch.zeros((2, 64), device=dev)
+        dcat = rnd(B, H, W, 128)
+        run(lambda: ops.maxpool2x2_bwd(z, sc, sh, dpool, dcat[..., 64:], dy, bn_sums=sums), int(3.25 * M * 64 * 2))
+    elif name == "bn_act_cat":
+        run(lambda: ops.bn_act(z, sc, sh, y, relu=True), 2 * M * 64 * 2)
+    else:
+        run(lambda: ops.bn_act(z, sc, sh, y, relu=True, pooled=pooled), int(2.25 * M * 64 * 2))
 elif name in ("bn_bwd_reduce", "bn_bwd_apply", "bn_act"):
     z, dy, dz = rnd(B, H, W, 64), rnd(B, H, W, 64), torch.empty((B, H, W, 64), device=dev, dtype=bf)
     v = lambda: torch.rand(64, device=dev)

@@ -362,3 +362,26 @@ def test_host_copy_paths():
     ro = rng.random((3, 512, 512, 3)).astype(np.float32); ro.setflags(write=False)
     _host_copy(dstb, ro)                                               # read-only source array
     assert np.array_equal(dstb.numpy(), ro)
+
+
+def test_cast_transpose_table_layout():
+    """host side of unet_cast_transpose_bf16_batched: tile offsets accumulate per matrix, destinations are validated
+    (no kernel runs here: CPU tensors stand in for the device buffers)"""
+    import torch
+    from unet_b200 import ops
+    base = torch.zeros(64 * 64 + 3 * 64 + 70 * 33)
+    a = torch.zeros((64, 64), dtype=torch.bfloat16); at = torch.zeros((64, 64), dtype=torch.bfloat16)
+    b_t = torch.zeros((64, 3), dtype=torch.bfloat16)
+    c = torch.zeros((70, 33), dtype=torch.bfloat16)
+    table, n, tiles = ops.cast_transpose_table(base, [(0, a, at, 64, 64), (4096, None, b_t, 3, 64), (4096 + 192, c, None, 70, 33)])
+    assert n == 3 and tiles == 4 + 2 + 3 * 2
+    assert table.dtype == torch.int64 and tuple(table.shape) == (3, 6)
+    rows = table.tolist()
+    assert [r[5] for r in rows] == [0, 4, 6] and [r[0] for r in rows] == [0, 4096, 4288]
+    assert rows[1][1] == 0 and rows[2][2] == 0 and rows[0][1] == a.data_ptr() and rows[1][2] == b_t.data_ptr()
+    with pytest.raises(ValueError):
+        ops.cast_transpose_table(base, [(0, torch.zeros((64, 64)), None, 64, 64)])            # not bf16
+    with pytest.raises(ValueError):
+        ops.cast_transpose_table(base, [(0, None, torch.zeros((64, 3), dtype=torch.bfloat16), 64, 3)])   # dst_t must be [C, R]
+    with pytest.raises(ValueError):
+        ops.cast_transpose_table(base, [(base.numel() - 10, a, None, 64, 64)])                # outside the source buffer

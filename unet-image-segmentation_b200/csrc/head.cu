@@ -384,7 +384,6 @@ head1_bwd_stream_kernel(const __nv_bfloat16* __restrict__ x, const float* __rest
     const float dz = fmaf(ca, t, cb) * pr * (1.f - pr);
     const uint32_t u[4] = {raw.x, raw.y, raw.z, raw.w};
     float o[8];
-#pragma unroll
     const float2 dz2 = make_float2(dz, dz);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {                   // packed FFMA2 / FMUL2 / FADD2: two channels per instruction
